@@ -1,0 +1,169 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of the CPU parity oracle (oracle/qpic_oracle.c).
+
+Nothing under quetzalpic_b200/ imports this module.  It is used by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs, and only as the checker.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libqpic_oracle.so")
+
+FIELDS_2D = ["psi", "psi_prev", "psi_middle", "rho", "jx", "jy", "jz", "jy_next", "jz_next", "djy_dxi", "djz_dxi", "rho_ion"]
+FIELDS_3D = ["aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "by", "bz",
+             "psi", "rho", "jx", "jy", "jz"]  # the last five: per-slice outputs, Fields-file layout
+PARTICLE_FIELDS = ["y", "z", "py", "pz", "n", "gamma", "px", "py_next", "pz_next", "y_middle", "z_middle"]
+
+
+class QoParams(ctypes.Structure):
+    _fields_ = [
+        ("nx", ctypes.c_int), ("ny", ctypes.c_int), ("nz", ctypes.c_int),
+        ("lx", ctypes.c_double), ("ly", ctypes.c_double), ("lz", ctypes.c_double),
+        ("magnetic_field_iterations", ctypes.c_int),
+        ("psi_threshold", ctypes.c_double),
+        ("magnetic_field_D", ctypes.c_double),
+        ("threshold_B", ctypes.c_double),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle with the committed recipe (oracle/Makefile)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.qo_create.restype = ctypes.c_void_p
+        L.qo_create.argtypes = [ctypes.POINTER(QoParams)]
+        L.qo_destroy.argtypes = [ctypes.c_void_p]
+        L.qo_set_laser_gaussian.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 7
+        L.qo_set_a_sqr.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.qo_set_bunch_sources.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.qo_init_wake_particles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.qo_init_wake_particles_uniform.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        L.qo_solve_wakefield.argtypes = [ctypes.c_void_p]
+        L.qo_begin.argtypes = [ctypes.c_void_p]
+        L.qo_step_slice.argtypes = [ctypes.c_void_p]
+        L.qo_finish.argtypes = [ctypes.c_void_p]
+        L.qo_current_slice.argtypes = [ctypes.c_void_p]
+        L.qo_stopped_at.argtypes = [ctypes.c_void_p]
+        L.qo_particle_count.restype = ctypes.c_size_t
+        L.qo_particle_count.argtypes = [ctypes.c_void_p]
+        L.qo_particles.restype = dp
+        L.qo_particles.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.qo_field2d_ptr.restype = dp
+        L.qo_field2d_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.qo_field3d_ptr.restype = dp
+        L.qo_field3d_ptr.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.qo_deposit.argtypes = [ctypes.c_double] * 3 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4
+        L.qo_deposit_raw.argtypes = [ctypes.c_double] * 3 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 2
+        L.qo_gather.restype = ctypes.c_double
+        L.qo_gather.argtypes = [ctypes.c_double] * 2 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4
+        L.qo_gather_yder.restype = ctypes.c_double
+        L.qo_gather_yder.argtypes = [ctypes.c_double] * 2 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 2
+        L.qo_gather_zder.restype = ctypes.c_double
+        L.qo_gather_zder.argtypes = [ctypes.c_double] * 2 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 2
+        L.qo_solve_poisson.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    """One oracle context.  Field / particle accessors return numpy VIEWS of the oracle's memory."""
+
+    def __init__(self, nx, ny, nz, lx, ly, lz, magnetic_field_iterations, psi_threshold=1e-4, magnetic_field_D=10.0,
+                 threshold_B=100.0):
+        self.L = lib()
+        self.params = QoParams(nx, ny, nz, lx, ly, lz, magnetic_field_iterations, psi_threshold, magnetic_field_D, threshold_B)
+        self.ctx = self.L.qo_create(ctypes.byref(self.params))
+        if not self.ctx:
+            raise RuntimeError("qo_create failed")
+        self.nx, self.ny, self.nz = nx, ny, nz
+
+    def close(self):
+        if self.ctx:
+            self.L.qo_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup
+    def set_laser_gaussian(self, amplitude, wx, wy, wz, x0, y0, z0):
+        self.L.qo_set_laser_gaussian(self.ctx, amplitude, wx, wy, wz, x0, y0, z0)
+
+    def set_a_sqr(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == (self.nx, self.ny, self.nz)
+        self.L.qo_set_a_sqr(self.ctx, a.ctypes.data)
+
+    def set_bunch_sources(self, rho_bunch=None, jx_bunch=None):
+        r = None if rho_bunch is None else np.ascontiguousarray(rho_bunch, dtype=np.float64)
+        j = None if jx_bunch is None else np.ascontiguousarray(jx_bunch, dtype=np.float64)
+        self.L.qo_set_bunch_sources(self.ctx, None if r is None else r.ctypes.data, None if j is None else j.ctypes.data)
+
+    def init_wake_particles(self, y, z, n):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        n = np.ascontiguousarray(n, dtype=np.float64)
+        if self.L.qo_init_wake_particles(self.ctx, y.ctypes.data, z.ctypes.data, n.ctypes.data, y.size) != 0:
+            raise RuntimeError("qo_init_wake_particles failed")
+
+    def init_wake_particles_uniform(self, ppcy, ppcz, rho0=-1.0):
+        if self.L.qo_init_wake_particles_uniform(self.ctx, ppcy, ppcz, rho0) != 0:
+            raise RuntimeError("qo_init_wake_particles_uniform failed")
+
+    # -- sweep
+    def solve_wakefield(self):
+        return self.L.qo_solve_wakefield(self.ctx)
+
+    def begin(self):
+        self.L.qo_begin(self.ctx)
+
+    def step_slice(self):
+        return self.L.qo_step_slice(self.ctx)
+
+    def finish(self):
+        self.L.qo_finish(self.ctx)
+
+    @property
+    def current_slice(self):
+        return self.L.qo_current_slice(self.ctx)
+
+    @property
+    def stopped_at(self):
+        return self.L.qo_stopped_at(self.ctx)
+
+    # -- state views
+    @property
+    def particle_count(self):
+        return self.L.qo_particle_count(self.ctx)
+
+    def particles(self, name):
+        p = self.L.qo_particles(self.ctx, PARTICLE_FIELDS.index(name))
+        return np.ctypeslib.as_array(p, shape=(max(self.particle_count, 1),))[: self.particle_count]
+
+    def field2d(self, name):
+        p = self.L.qo_field2d_ptr(self.ctx, FIELDS_2D.index(name))
+        return np.ctypeslib.as_array(p, shape=(self.ny, self.nz))
+
+    def field3d(self, name, per_slice=False):
+        """`per_slice=True` selects the Fields-file style accumulation of the 2-D arrays psi/rho/jx/jy/jz."""
+        idx = FIELDS_3D.index(name, 9) if per_slice else FIELDS_3D.index(name)
+        p = self.L.qo_field3d_ptr(self.ctx, idx)
+        return np.ctypeslib.as_array(p, shape=(self.nx, self.ny, self.nz))
