@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- macroparticle pushes/s and ms per xi-slice of the quasistatic wakefield sweep on B200.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d input 2): 3-D linear laser wake, 2048 x 512 x 512 grid,
+2x2 particles per cell (P = 1 048 576 plasma macroparticles), magnetic_field_iterations = 5, a0 = 1, uniform plasma.
+One bench "step" = SLICES_PER_STEP consecutive xi-slices of that sweep (push + all deposits + all field solves).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 (torchrun, one rank per GPU): the xi-loop is causally sequential, so a sweep never spans GPUs; ranks run
+independent members of the a0 / density parameter scan (BASELINE.json configs[4]), no data-path collective,
+"scaling": "weak".  `value` = total pushes of all ranks / max-over-ranks device time.
+
+--impl reference times the reference's own OpenMP CPU implementation of the same path on this box's host cores:
+oracle/_ref/quasistatic_pic_fast = the UNMODIFIED reference sources built by oracle/Makefile (falls back to the
+plain-C oracle port, 1 thread, if that binary did not travel).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SLICES_PER_STEP = 64
+
+WORKLOAD = dict(
+    name="laser_wake_512x512_4ppc_M5",
+    nx=2048, ny=512, nz=512, lx=32.0, ly=32.0, lz=32.0, ppcy=2, ppcz=2, M=5,
+    a0=1.0, xsigma=4.0, ysigma=8.0, zsigma=8.0, x0=26.0,
+)
+# parameter scan members for N > 1 (configs[4]): (a0, rho0)
+SCAN = [(1.0, -1.0), (0.5, -1.0), (2.0, -1.0), (3.0, -1.0), (1.0, -0.5), (0.5, -0.5), (2.0, -0.5), (3.0, -0.5)]
+
+
+def algorithmic_bytes_per_slice(N, P, M):
+    """8 * [(29 + 44 M) N + (18 + 21 M) P]"""
+    return 8.0 * ((29 + 44 * M) * N + (18 + 21 * M) * P)
+
+
+# algorithmic bytes of ONE launch of each kernel (DESIGN.md section "kernels"): doubles moved per cell (N) / particle (P)
+KERNEL_BYTES = {
+    "k_deposit_charge": lambda N, P: 8.0 * (2 * N + 3 * P),
+    "k_fft_rows_r2c": lambda N, P: 8.0 * (2 * N),
+    "k_fft_rows_c2r": lambda N, P: 8.0 * (2 * N),
+    "k_fft_cols_solve": lambda N, P: 8.0 * (3 * N),  # mean of the half (2N) and full (4N) spectrum launches
+    "k_potential_fixup": lambda N, P: 8.0 * (2 * N),
+    "k_particles_gamma": lambda N, P: 8.0 * (16 * P),
+    "k_deposit_jx_rho_chi": lambda N, P: 8.0 * (3 * N + 5 * P),
+    "k_particles_predict": lambda N, P: 8.0 * (14 * P),
+    "k_particles_correct": lambda N, P: 8.0 * (14 * P),
+    "k_deposit_jy_jz": lambda N, P: 8.0 * (2 * N + 4 * P),
+    "k_fft_rows_b_forward": lambda N, P: 8.0 * (9 * N),
+    "k_fft_rows_b_backward": lambda N, P: 8.0 * (4 * N),
+    "k_particles_advance": lambda N, P: 8.0 * (12 * P),
+    "k_end_of_slice": lambda N, P: 8.0 * (17 * N),
+    "k_scan_chunk_sums": lambda N, P: 4.0 * N,
+    "k_scan_sums": lambda N, P: 8.0 * (N / 1024),
+    "k_scan_apply": lambda N, P: 4.0 * (4 * N),
+    "k_sort_fill": lambda N, P: 4.0 * (3 * P),
+    "k_sort_rank": lambda N, P: 4.0 * (4 * P),
+    "k_next_slice": lambda N, P: 8.0,
+}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------- reference / CPU arm
+
+REF_FAST = os.path.join(ROOT, "oracle", "_ref", "quasistatic_pic_fast")
+
+
+def write_ref_toml(path, w, nx):
+    dx = w["lx"] / w["nx"]
+    lx = nx * dx
+    with open(path, "w") as f:
+        f.write(f"lx = {lx!r}\nly = {w['ly']!r}\nlz = {w['lz']!r}\ndx = {dx!r}\ndy = {w['ly'] / w['ny']!r}\ndz = {w['lz'] / w['nz']!r}\n")
+        f.write(f"ppcy = {w['ppcy']}\nppcz = {w['ppcz']}\nmagnetic_field_iterations = {w['M']}\n\n[laser]\nshape = \"gaussian\"\n")
+        f.write(f"a0 = {w['a0']!r}\nxsigma = {w['xsigma']!r}\nysigma = {w['ysigma']!r}\nzsigma = {w['zsigma']!r}\nx0 = {0.5 * lx!r}\n")
+        f.write("\n[output]\nfields_xy = true\n")
+
+
+def run_reference_sample(w, nx, threads):
+    """One run of the unmodified reference on an nx-slice cut of the workload.  Returns (seconds for the nx-1 pushed
+    slices, kind).  The span is first-FFT to last-FFT as recorded by the fftw3 shim (oracle/shims/fftw3_shim.cpp)."""
+    P = w["ppcy"] * w["ppcz"] * w["ny"] * w["nz"]
+    if os.path.exists(REF_FAST) and os.access(REF_FAST, os.X_OK):
+        with tempfile.TemporaryDirectory() as wd:
+            write_ref_toml(os.path.join(wd, "in.toml"), w, nx)
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads), QPIC_REF_TIMING_FILE=os.path.join(wd, "timing.json"))
+            subprocess.run([REF_FAST, "in.toml"], cwd=wd, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            span = json.load(open(os.path.join(wd, "timing.json")))["first_fft_to_last_fft_s"]
+        return span, "reference", threads, P
+    # the compiled reference did not travel: time the plain-C port (single thread)
+    from oracle.qo import Oracle
+    from quetzalpic_b200 import gaussian_laser_widths, wake_particle_lattice
+    dx = w["lx"] / w["nx"]
+    o = Oracle(nx, w["ny"], w["nz"], nx * dx, w["ly"], w["lz"], w["M"])
+    wx, wy, wz = gaussian_laser_widths(w["xsigma"], w["ysigma"], w["zsigma"])
+    o.set_laser_gaussian(0.5 * w["a0"] ** 2, wx, wy, wz, 0.5 * nx * dx, 0.5 * w["ly"], 0.5 * w["lz"])
+    o.init_wake_particles(*wake_particle_lattice(w["ny"], w["nz"], w["ly"], w["lz"], w["ppcy"], w["ppcz"]))
+    o.begin()
+    t0 = time.perf_counter()
+    for _ in range(nx - 1):
+        o.step_slice()
+    span = time.perf_counter() - t0
+    o.close()
+    return span, "port", 1, P
+
+
+def cpu_baseline(w, target_seconds=15.0):
+    threads = os.cpu_count() or 1
+    # calibrate with a 3-slice run, then size the sample
+    span, kind, used, P = run_reference_sample(w, 3, threads)
+    per_slice = span / 2
+    nx = int(min(33, max(3, round(target_seconds / max(per_slice, 1e-3)) + 1)))
+    if nx > 3:
+        span, kind, used, P = run_reference_sample(w, nx, threads)
+    pushed = nx - 1
+    return {
+        "value": P * pushed / span, "unit": "pushes/s", "cores": used, "kind": kind, "ms_per_slice": 1e3 * span / pushed,
+        "sample": f"{pushed} xi-slices of the same 512x512 4 ppc M=5 workload ({nx}-slice box, laser centred), "
+                  f"{'unmodified reference -Ofast + OpenMP, shim FFT' if kind == 'reference' else 'plain-C oracle port'}, "
+                  f"OMP_NUM_THREADS={used}",
+    }
+
+
+def run_reference_arm(args, w):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    spans, P, kind, used = [], None, None, None
+    nx = 5
+    for it in range(args.warmup + args.steps):
+        if it >= 1 and it < args.warmup:
+            continue  # one warm-up run is enough to page the binary in; CPU runs are slow
+        span, kind, used, P = run_reference_sample(w, nx, threads)
+        if it >= args.warmup:
+            spans.append(span)
+    total = sum(spans)
+    pushed = (nx - 1) * len(spans)
+    value = P * pushed / total
+    line = {
+        "impl": "reference", "metric": "macroparticle pushes/sec (3D laser wake, per-xi-slice push+deposit+field solve)",
+        "value": value, "unit": "pushes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(spans), "ms_per_slice": 1e3 * total / pushed, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "grid": [w["nx"], w["ny"], w["nz"]], "ppc": w["ppcy"] * w["ppcz"], "particles": P,
+                   "magnetic_field_iterations": w["M"], "slices_per_step": nx - 1,
+                   "note": "each step = one run of the reference executable on a 5-slice cut of the workload (4 pushed slices)"},
+        "cpu_baseline": {"value": value, "unit": "pushes/s", "cores": used, "kind": kind,
+                         "sample": f"{len(spans)} runs x 4 xi-slices, 512x512 4 ppc M=5, OMP_NUM_THREADS={used}"},
+        "e2e": {"value": value, "unit": "pushes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+
+def run_b200_arm(args, w):
+    import torch
+    import torch.distributed as dist
+    from quetzalpic_b200 import WakefieldSolver, gaussian_laser_widths, load_library, wake_particle_lattice
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    a0, rho0 = SCAN[rank % len(SCAN)] if world > 1 else (w["a0"], -1.0)
+    S, K, W = args.slices_per_step, args.steps, args.warmup
+    nx, ny, nz, M = w["nx"], w["ny"], w["nz"], w["M"]
+    if (K + W) * S > nx - 1:
+        raise SystemExit(f"(steps + warmup) * {S} slices exceeds the {nx}-slice box")
+    N = ny * nz
+    wx, wy, wz = gaussian_laser_widths(w["xsigma"], w["ysigma"], w["zsigma"])
+    y, z, n = wake_particle_lattice(ny, nz, w["ly"], w["lz"], w["ppcy"], w["ppcz"], rho0=rho0)
+    P = y.size
+    lib = load_library()
+
+    solver = WakefieldSolver(nx, ny, nz, w["lx"], w["ly"], w["lz"], M, device=local, stop_check_interval=S)
+    solver.set_laser_gaussian(0.5 * a0 * a0, wx, wy, wz, w["x0"], 0.5 * w["ly"], 0.5 * w["lz"])
+    solver.init_wake_particles(y, z, n)
+
+    # ---- device-resident throughput: inputs already in HBM, K steps timed with CUDA events on the solver's stream
+    solver.begin()
+    for _ in range(W):
+        solver.step(S, wait=False)
+    solver.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    solver.step(K * S, wait=False)
+    solver.synchronize()
+    ms, launches = solver.last_step_stats()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    stopped = solver.stopped_at
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    pushes_total = float(P) * K * S * world
+    value = pushes_total / (ms_max * 1e-3)
+    ms_per_slice = ms_max / (K * S)
+
+    # ---- per-kernel shares of a slice (eager, one CUDA event per launch), for the roofline of the dominant kernel
+    prof = solver.profile_slices(8)
+    prof_total = sum(v[1] for v in prof.values())
+    kernels = []
+    for name, (count, tot) in prof.items():
+        per_launch_ms = tot / count
+        nbytes = KERNEL_BYTES.get(name, lambda N, P: 0.0)(N, P)
+        kernels.append({"kernel": name, "launches_per_slice": count / 8.0, "us_per_launch": 1e3 * per_launch_ms, "share": tot / prof_total,
+                        "algorithmic_gbs": nbytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None})
+    kernels.sort(key=lambda k: -k["share"])
+    peak, peak_src = measured_peak_gbs()
+    top = kernels[0]
+    top_bytes = KERNEL_BYTES.get(top["kernel"], lambda N, P: 0.0)(N, P)
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": (top["algorithmic_gbs"] or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": top_bytes, "share_of_slice": top["share"]}
+    slice_bytes = algorithmic_bytes_per_slice(N, P, M)
+    slice_gbs = slice_bytes / (ms_per_slice * 1e-3) / 1e9
+    roofline_slice = {"bound": "hbm", "achieved": slice_gbs, "peak": peak, "unit": "GB/s", "frac": slice_gbs / peak,
+                      "algorithmic_bytes_per_slice": slice_bytes, "formula": "8*[(29+44M)N+(18+21M)P] (SURVEY.md 8d)"}
+
+    # ---- end to end through the C ABI with HOST buffers: a fresh sweep; every step uploads that step's a_sqr slices from
+    # pinned host memory and downloads the six field slabs the reference keeps on the host (ex ey ez by bz susceptibility)
+    out_fields = ["ex", "ey", "ez", "by", "bz", "susceptibility"]
+    a_blk, a_ptr = lib.pinned_array((S, ny, nz))
+    outs = [lib.pinned_array((S, ny, nz)) for _ in out_fields]
+    xs = np.arange(nx) * (w["lx"] / nx)
+    yy = np.arange(ny) * (w["ly"] / ny)
+    zz = np.arange(nz) * (w["lz"] / nz)
+    gy = np.exp(-((yy - 0.5 * w["ly"]) ** 2) / wy / wy)[:, None] * np.exp(-((zz - 0.5 * w["lz"]) ** 2) / wz / wz)[None, :]
+    gx = 0.5 * a0 * a0 * np.exp(-((xs - w["x0"]) ** 2) / wx / wx)
+    barrier()
+    t0 = time.perf_counter()
+    solver.init_wake_particles(y, z, n)
+    solver.begin()
+    checksum = 0.0
+    for k in range(K):
+        first = nx - (k + 1) * S
+        a_blk[:] = gx[first:first + S, None, None] * gy[None, :, :]  # host-side envelope for this block of slices
+        solver.upload_a_sqr_slices(first, a_blk)
+        solver.step(S, wait=False)
+        for (blk, _), f in zip(outs, out_fields):
+            solver.download_slices3d(f, first, blk)
+        solver.synchronize()
+        checksum += float(outs[2][0][0, ny // 2, nz // 2])
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = pushes_total / e2e_s
+    h2d = S * N * 8 + (3 * P * 8) // K
+    d2h = len(out_fields) * S * N * 8
+    lib.free_pinned(a_ptr)
+    for _, ptr in outs:
+        lib.free_pinned(ptr)
+    solver.close()
+
+    if rank == 0:
+        cpu = cpu_baseline(w) if (world == 1 and not args.no_cpu_baseline) else None
+        line = {
+            "metric": "macroparticle pushes/sec (3D laser wake, per-xi-slice push+deposit+field solve)",
+            "value": value, "unit": "pushes/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+            "ms_per_slice": ms_per_slice, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "grid": [nx, ny, nz], "ppc": w["ppcy"] * w["ppcz"], "particles_per_gpu": P,
+                       "magnetic_field_iterations": M, "slices_per_step": S, "a0": a0,
+                       "parallelism": "1 sweep per GPU" + (f"; {world}-member a0/density scan, no collective" if world > 1 else ""),
+                       "l2": "inputs larger than L2: particle SoA + per-slice rows of nine 3-D fields (>200 MB touched per slice)",
+                       "stopped_at": stopped},
+            "roofline": roofline, "roofline_slice": roofline_slice, "kernels": kernels[:8],
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "pushes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_slice": 1e3 * e2e_s / (K * S), "checksum": checksum,
+                    "what": "qpic_init_wake_particles + qpic_begin + per step: a_sqr slab H2D (pinned), qpic_step, 6 field slabs D2H (pinned)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slices-per-step", type=int, default=SLICES_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    w = dict(WORKLOAD)
+    # keep (steps + warmup) * slices inside the 2048-slice box whatever K/W the driver asks for
+    while (args.steps + args.warmup) * args.slices_per_step > w["nx"] - 1 and args.slices_per_step > 1:
+        args.slices_per_step //= 2
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+    else:
+        run_b200_arm(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+/* qpic_b200 -- C ABI of the B200-native per-xi-slice quasistatic wakefield solver.
+ *
+ * Drop-in replacement for the body of QuetzalPIC's System_3d::solve_wakefield
+ * (reference src/System_3d.cpp:238-627).  The reference has no FFI / plugin boundary: the hot path is a
+ * private C++ member (src/System_3d.h:29) operating on members of System_3d (src/System_3d.h:67-92).  This
+ * header is the boundary a maintainer would bind instead (INTEGRATION.md shows the System_3d-side patch);
+ * each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all pointers are HOST pointers unless the name starts with d_;
+ *   - every array is float64, row-major, z fastest: 2-D (ny,nz) = array2d (src/array2d.h:15-16),
+ *     3-D (nx,ny,nz) = array3d (src/array3d.h:13-14);
+ *   - functions return QPIC_OK (0) or a negative qpic_status; qpic_last_error() gives the message;
+ *   - one context drives one CUDA device; a context is not thread-safe;
+ *   - there is NO CPU fallback: qpic_create fails with QPIC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef QPIC_B200_H
+#define QPIC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPIC_ABI_VERSION 1
+
+typedef enum {
+    QPIC_OK = 0,
+    QPIC_ERR_INVALID = -1,     /* bad argument (mirrors std::invalid_argument, src/System_3d.cpp:77-85) */
+    QPIC_ERR_CUDA = -2,        /* CUDA runtime failure / no device */
+    QPIC_ERR_STATE = -3,       /* call sequence error (e.g. step before begin) */
+    QPIC_ERR_UNSUPPORTED = -4, /* grid size the batched shared-memory transform cannot handle */
+    QPIC_ERR_NOMEM = -5
+} qpic_status;
+
+typedef struct qpic_ctx qpic_ctx;
+
+/* Scalars of System_3d that the sweep reads (src/System_3d.h:46-59, src/System_3d.cpp:87-95, :326). */
+typedef struct {
+    int nx, ny, nz;                /* n = static_cast<int>(l / d), computed by the caller as the reference does */
+    double lx, ly, lz;             /* box; steps are re-derived as l / n (src/System_3d.cpp:93-95) */
+    int magnetic_field_iterations; /* M >= 0 */
+    double psi_threshold;          /* 1e-4 */
+    double magnetic_field_D;       /* 10.0 */
+    double threshold_B;            /* 100.0 */
+    int device;                    /* CUDA device ordinal */
+    int keep_slices_3d;            /* != 0: accumulate psi,rho,jx,jy,jz per slice on the device, as Output_writer::write_slice
+                                      fills Fields_NNN.h5 (src/System_3d.cpp:663-665); needs 5 more (nx,ny,nz) arrays */
+    int use_graph;                 /* != 0 (default): replay one CUDA graph per slice; 0: eager launches (debugging) */
+    int stop_check_interval;       /* the host polls the device stop flag every this many slices (<=0: 64) */
+} qpic_params;
+
+/* fills *p with the reference defaults (psi_threshold 1e-4, D 10, threshold_B 100, device 0, graph on) */
+void qpic_default_params(qpic_params * p);
+
+/* 2-D working arrays of System_3d (src/System_3d.h:69-72, 84-91) */
+typedef enum {
+    QPIC_F2_PSI = 0, QPIC_F2_PSI_PREV, QPIC_F2_PSI_MIDDLE, QPIC_F2_RHO, QPIC_F2_JX, QPIC_F2_JY, QPIC_F2_JZ,
+    QPIC_F2_JY_NEXT, QPIC_F2_JZ_NEXT, QPIC_F2_RHO_ION,
+    QPIC_F2_BY_CUR, QPIC_F2_BZ_CUR, /* by(i), bz(i) of the slice being solved */
+    QPIC_F2_COUNT
+} qpic_field2d;
+
+/* 3-D arrays; names = HDF5 dataset names (src/System_3d.cpp:49-62) */
+typedef enum {
+    QPIC_F3_ASQR = 0, QPIC_F3_SUSCEPTIBILITY, QPIC_F3_RHO_BUNCH, QPIC_F3_JX_BUNCH, QPIC_F3_EX, QPIC_F3_EY, QPIC_F3_EZ,
+    QPIC_F3_BY, QPIC_F3_BZ,
+    QPIC_F3_PSI, QPIC_F3_RHO, QPIC_F3_JX, QPIC_F3_JY, QPIC_F3_JZ, /* only with keep_slices_3d */
+    QPIC_F3_COUNT
+} qpic_field3d;
+
+/* wake_particle_2d members that persist between slices (src/containers.h:31-43) */
+typedef enum { QPIC_P_Y = 0, QPIC_P_Z, QPIC_P_PY, QPIC_P_PZ, QPIC_P_N, QPIC_P_GAMMA, QPIC_P_PX, QPIC_P_COUNT } qpic_particle_field;
+
+/* ---- lifetime.  Replaces the allocation part of System_3d::System_3d (src/System_3d.cpp:155-193). */
+int qpic_create(const qpic_params * params, qpic_ctx ** out);
+void qpic_destroy(qpic_ctx * ctx);
+/* message of the last failure on ctx (ctx == NULL: of the last failed qpic_create in this thread) */
+const char * qpic_last_error(const qpic_ctx * ctx);
+int qpic_abi_version(void);
+
+/* ---- inputs */
+/* a_sqr(i,j,k) = amplitude * exp(-sum_c (x_c - r0_c)^2 / w_c^2) at nodes x = i*dx ...; replaces init_a_sqr with
+ * gaussian3d (src/System_3d.cpp:805-816, src/profiles.cpp:4-11).  Evaluated on the device. */
+int qpic_set_laser_gaussian(qpic_ctx * ctx, double amplitude, double wx, double wy, double wz, double x0, double y0, double z0);
+/* any other profile: upload nx*ny*nz values (replaces init_a_sqr for arbitrary std::function profiles) */
+int qpic_upload_a_sqr(qpic_ctx * ctx, const double * a_sqr);
+/* rho_bunch / jx_bunch as left by System_3d::deposit_bunch_densities (src/System_3d.cpp:926-946); NULL, NULL => zeros */
+int qpic_upload_bunch_sources(qpic_ctx * ctx, const double * rho_bunch, const double * jx_bunch);
+/* the lattice of System_3d::init_wake_particles (src/System_3d.cpp:724-748), built by the caller: positions and
+ * weights n; momenta start at 0.  Particles with n == 0 must not be passed (the reference skips them, :735). */
+int qpic_init_wake_particles(qpic_ctx * ctx, const double * y, const double * z, const double * n, size_t count);
+
+/* ---- the sweep.  qpic_solve_wakefield == qpic_begin + qpic_step(nx) + qpic_finish. */
+/* whole of solve_wakefield's numerics (src/System_3d.cpp:262-626); returns QPIC_OK also when the |B| stop
+ * condition tripped (the reference exits 0 too) -- query qpic_stopped_at. */
+int qpic_solve_wakefield(qpic_ctx * ctx);
+/* pre-loop zeroing and rho_ion deposition (src/System_3d.cpp:265-326) */
+int qpic_begin(qpic_ctx * ctx);
+/* up to max_slices iterations of the xi-loop body (src/System_3d.cpp:328-619); asynchronous unless the stop flag
+ * has to be polled.  *done (nullable) = 1 once slice 0 has been processed or the stop condition tripped. */
+int qpic_step(qpic_ctx * ctx, int max_slices, int * done);
+/* output_step(0) (src/System_3d.cpp:622) and a device synchronisation */
+int qpic_finish(qpic_ctx * ctx);
+/* waits for all queued device work of this context */
+int qpic_synchronize(qpic_ctx * ctx);
+/* slice index the next qpic_step will process */
+int qpic_current_slice(qpic_ctx * ctx);
+/* -1, or the slice at which |By|,|Bz| > threshold_B or NaN tripped (src/System_3d.cpp:545-550, 573-578, 588-591) */
+int qpic_stopped_at(qpic_ctx * ctx);
+
+/* ---- results / state (each call synchronises) */
+int qpic_download_field3d(qpic_ctx * ctx, qpic_field3d f, double * dst);              /* nx*ny*nz doubles */
+int qpic_download_slice3d(qpic_ctx * ctx, qpic_field3d f, int slice, double * dst);   /* ny*nz doubles */
+int qpic_download_field2d(qpic_ctx * ctx, qpic_field2d f, double * dst);              /* ny*nz doubles */
+int qpic_upload_field2d(qpic_ctx * ctx, qpic_field2d f, const double * src);          /* state injection for per-slice parity tests */
+size_t qpic_particle_count(const qpic_ctx * ctx);
+int qpic_download_particles(qpic_ctx * ctx, qpic_particle_field f, double * dst);     /* count doubles, caller's original order */
+int qpic_upload_particles(qpic_ctx * ctx, qpic_particle_field f, const double * src); /* y,z,py,pz,n only */
+/* forces the slice index the next qpic_step processes (state injection) */
+int qpic_set_current_slice(qpic_ctx * ctx, int slice);
+
+/* ---- building blocks exposed for unit tests and the FFT comparator bench */
+/* (nabla_perp^2 - D) u = src on the periodic ny x nz grid with the 5-point-Laplacian symbol, DC forced to 0, result
+ * normalised by 1/ny/nz (src/System_3d.cpp:686-706 + the division at :361).  In place on a host array. */
+int qpic_solve_poisson_host(qpic_ctx * ctx, double * inout, double D);
+/* By/Bz-style pair of Helmholtz solves done as ONE complex transform (re = first field, im = second) */
+int qpic_solve_helmholtz_pair_host(qpic_ctx * ctx, double * inout_a, double * inout_b, double D);
+/* CUDA-event timing of the last qpic_step call (ms), and kernels launched by it */
+int qpic_last_step_stats(qpic_ctx * ctx, float * ms, long * kernel_launches);
+/* runs up to nslices slices eagerly with a CUDA event after every kernel; report = lines "kernel count total_ms" */
+int qpic_profile_slices(qpic_ctx * ctx, int nslices, char * report, size_t report_len);
+
+/* ---- streaming transfers for callers whose arrays live in host memory (System_3d's array3d members).  Asynchronous on
+ * the context's stream: call qpic_synchronize before touching the host buffers.  Pinned buffers give full PCIe rate. */
+/* a_sqr(first_slice .. first_slice+count-1, :, :)  (the laser envelope is read one slice at a time, src/System_3d.cpp:371) */
+int qpic_upload_a_sqr_slices(qpic_ctx * ctx, int first_slice, int count, const double * src);
+/* rows [first_slice, first_slice+count) of a 3-D field, e.g. what deposit_wakefield_to_bunch / write_array read afterwards */
+int qpic_download_slices3d(qpic_ctx * ctx, qpic_field3d f, int first_slice, int count, double * dst);
+void * qpic_alloc_pinned(size_t bytes);
+void qpic_free_pinned(void * p);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QPIC_B200_H */

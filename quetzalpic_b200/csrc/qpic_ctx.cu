@@ -1,0 +1,960 @@
+// qpic_b200: context, kernel sequencing and the C ABI (include/qpic_b200.h).
+//
+// One context = one CUDA device, one stream.  The whole xi-loop body of System_3d::solve_wakefield
+// (reference src/System_3d.cpp:328-619) is a fixed sequence of kernels that read the slice index from device
+// memory, so it is captured ONCE into a CUDA graph and replayed nx-1 times; the host only polls the stop flag
+// every few dozen slices.  All field and particle arrays stay resident in HBM for the whole sweep.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/qpic_b200.h"
+#include "qpic_compat.h"
+#include "qpic_fft.cuh"
+#include "qpic_kernels.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+using namespace qpic;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t SMEM_OPTIN_LIMIT = 227 * 1024;
+constexpr size_t SMEM_DEFAULT_LIMIT = 48 * 1024;
+
+struct DeviceFft {
+    FftPlan plan;
+    double2 * tw = nullptr;  // device
+};
+
+}  // namespace
+
+struct qpic_ctx {
+    qpic_params prm;
+    Geom g;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool began = false;
+    bool done = false;
+    bool finished = false;
+    bool lists_dirty = false;
+    int cur = 0;          // host mirror of Ctl::slice
+    int stopped_at = -1;
+    int since_poll = 0;
+
+    // device state
+    Ctl * ctl = nullptr;
+    Ctl * ctl_scratch = nullptr;  // for the exposed building blocks (never carries a stop tag)
+    Ctl * ctl_host = nullptr;     // pinned
+    double * f2[QPIC_F2_COUNT] = {};
+    double * f3[QPIC_F3_COUNT] = {};
+    double *fft_in = nullptr, *fft_in2 = nullptr, *raw = nullptr;
+    double2 * spec = nullptr;  // ny * nz complex (the psi solves use the first ny*(nz/2+1))
+    double *sy = nullptr, *sz = nullptr;
+    DeviceFft fy, fz;
+    Particles P = {};
+    int *count = nullptr, *cursor = nullptr, *sums = nullptr, *tmp = nullptr;
+    int *start_b = nullptr, *start_m = nullptr, *perm_b = nullptr, *perm_m = nullptr;
+    int nchunks = 0;
+    std::vector<void *> allocations;
+
+    // launch geometry
+    int rows_threads = 128, cols_threads_h = 128, cols_threads_f = 128;
+    int cpb = 1;
+    size_t rows_smem = 0, cols_smem = 0;
+
+    // graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    long launches_per_slice = 0;
+
+    // stats
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    long last_launches = 0;
+    long launch_counter = 0;
+
+    // per-kernel profiling (qpic_profile_slices): an event after every launch of an eager slice
+    bool profiling = false;
+    std::vector<const char *> prof_names;
+    std::vector<cudaEvent_t> prof_events;
+};
+
+namespace {
+
+int fail(qpic_ctx * c, int code, const char * fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define QPIC_CUDA(c, call)                                                                                            \
+    do {                                                                                                              \
+        cudaError_t e_ = (call);                                                                                      \
+        if (e_ != cudaSuccess) return fail((c), QPIC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define QPIC_TRY(expr)            \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != QPIC_OK) return rc_; \
+    } while (0)
+
+template <class T>
+int dev_alloc(qpic_ctx * c, T ** p, size_t count, bool zero = true) {
+    void * raw = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&raw, bytes);
+    if (e != cudaSuccess) return fail(c, QPIC_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    c->allocations.push_back(raw);
+    *p = static_cast<T *>(raw);
+    if (zero) QPIC_CUDA(c, cudaMemsetAsync(raw, 0, bytes, c->stream));
+    return QPIC_OK;
+}
+
+int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+int pick_threads(int work) {
+    int t = ((work + 31) / 32) * 32;
+    if (t < 64) t = 64;
+    if (t > 512) t = 512;
+    return t;
+}
+
+// factorisation 4,4,...,2,odd primes ascending; twiddle table exp(-2 pi i t / n) in extended precision
+int make_fft(qpic_ctx * c, int n, DeviceFft * out) {
+    FftPlan & P = out->plan;
+    P.n = n;
+    P.nfac = 0;
+    int m = n;
+    auto push = [&](int f) -> bool {
+        if (P.nfac >= FFT_MAX_FACTORS) return false;
+        P.fac[P.nfac++] = f;
+        return true;
+    };
+    while (m % 4 == 0) {
+        if (!push(4)) return fail(c, QPIC_ERR_UNSUPPORTED, "grid size %d has too many factors", n);
+        m /= 4;
+    }
+    while (m % 2 == 0) {
+        if (!push(2)) return fail(c, QPIC_ERR_UNSUPPORTED, "grid size %d has too many factors", n);
+        m /= 2;
+    }
+    for (int f = 3; m > 1; f += 2) {
+        while (m % f == 0) {
+            if (f > 127) return fail(c, QPIC_ERR_UNSUPPORTED, "grid size %d has a prime factor %d > 127; not supported by the shared-memory transform", n, f);
+            if (!push(f)) return fail(c, QPIC_ERR_UNSUPPORTED, "grid size %d has too many factors", n);
+            m /= f;
+        }
+    }
+    std::vector<double2> tw(n);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int t = 0; t < n; t++) {
+        const long double a = two_pi * (long double)t / (long double)n;
+        tw[t].x = (double)cosl(a);
+        tw[t].y = (double)(-sinl(a));
+    }
+    QPIC_TRY(dev_alloc(c, &out->tw, (size_t)n, false));
+    QPIC_CUDA(c, cudaMemcpyAsync(out->tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));  // tw is a local
+    return QPIC_OK;
+}
+
+// the separable parts of the divisor at src/System_3d.cpp:699, evaluated with the host libm exactly as written there
+int make_symbol_tables(qpic_ctx * c) {
+    const int ny = c->g.ny, nz = c->g.nz;
+    std::vector<double> sy(ny), sz(nz);
+    for (int j = 0; j < ny; j++) sy[j] = (2 * cos(2 * M_PI * j / ny) - 2) / c->g.dy / c->g.dy;
+    for (int k = 0; k < nz; k++) sz[k] = (2 * cos(2 * M_PI * k / nz) - 2) / c->g.dz / c->g.dz;
+    QPIC_TRY(dev_alloc(c, &c->sy, (size_t)ny, false));
+    QPIC_TRY(dev_alloc(c, &c->sz, (size_t)nz, false));
+    QPIC_CUDA(c, cudaMemcpyAsync(c->sy, sy.data(), sizeof(double) * ny, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaMemcpyAsync(c->sz, sz.data(), sizeof(double) * nz, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int check_launch(qpic_ctx * c, const char * what) {
+    c->launch_counter++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, QPIC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    if (c->profiling) {
+        cudaEvent_t ev;
+        QPIC_CUDA(c, cudaEventCreate(&ev));
+        QPIC_CUDA(c, cudaEventRecord(ev, c->stream));
+        c->prof_names.push_back(what);
+        c->prof_events.push_back(ev);
+    }
+    return QPIC_OK;
+}
+
+CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, c->perm_b, c->P.fy_b, c->P.fz_b}; }
+CellLists lists_mid(qpic_ctx * c) { return CellLists{c->start_m, c->perm_m, c->P.fy_m, c->P.fz_m}; }
+
+// ---------------------------------------------------------------------------------------------- kernel sequences
+
+// count[] (already accumulated by a particle kernel) -> start[], perm[] in canonical order
+int enqueue_sort(qpic_ctx * c, const Ctl * ctl, const int * cell, int * start, int * perm) {
+    const int n2 = c->g.n2, np = c->P.np;
+    QPIC_LAUNCH(k_scan_chunk_sums, c->nchunks, SCAN_THREADS, 0, c->stream, ctl, c->count, n2, c->sums);
+    QPIC_TRY(check_launch(c, "k_scan_chunk_sums"));
+    QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, c->stream, ctl, c->sums, c->nchunks);
+    QPIC_TRY(check_launch(c, "k_scan_sums"));
+    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, c->stream, ctl, c->count, n2, c->sums, start, c->cursor);
+    QPIC_TRY(check_launch(c, "k_scan_apply"));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_sort_fill, blocks_for(np, 256), 256, 0, c->stream, ctl, np, cell, c->cursor, c->tmp);
+        QPIC_TRY(check_launch(c, "k_sort_fill"));
+        QPIC_LAUNCH_FLAT(k_sort_rank, blocks_for(np, 256), 256, 0, c->stream, ctl, np, cell, start, c->tmp, perm);
+        QPIC_TRY(check_launch(c, "k_sort_rank"));
+    }
+    return QPIC_OK;
+}
+
+// real solve: fft_in -> raw (= solution / ny / nz)
+int enqueue_real_solve(qpic_ctx * c, const Ctl * ctl, double D) {
+    const int ny = c->g.ny, nz = c->g.nz, nzh = nz / 2 + 1;
+    QPIC_LAUNCH(k_fft_rows_r2c, (ny + 1) / 2, c->rows_threads, c->rows_smem, c->stream, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz);
+    QPIC_TRY(check_launch(c, "k_fft_rows_r2c"));
+    QPIC_LAUNCH(k_fft_cols_solve, (nzh + c->cpb - 1) / c->cpb, c->cols_threads_h, c->cols_smem, c->stream, ctl, c->fy.plan, c->fy.tw, c->spec, nzh, nzh,
+                c->cpb, c->sy, c->sz, nz, D);
+    QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
+    QPIC_LAUNCH(k_fft_rows_c2r, (ny + 1) / 2, c->rows_threads, c->rows_smem, c->stream, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz);
+    QPIC_TRY(check_launch(c, "k_fft_rows_c2r"));
+    return QPIC_OK;
+}
+
+// psi (or psi_middle) from the particle lists L: source deposit, solve, normalise + clamp (src/System_3d.cpp:342-365, :446-469)
+int enqueue_potential(qpic_ctx * c, CellLists L, double * dst) {
+    const int n2 = c->g.n2;
+    QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(n2, 128), 128, 0, c->stream, c->ctl, c->g, L, c->P.nw, c->f2[QPIC_F2_RHO_ION], c->f3[QPIC_F3_JX_BUNCH],
+                     c->f3[QPIC_F3_RHO_BUNCH], 1, c->fft_in);
+    QPIC_TRY(check_launch(c, "k_deposit_charge"));
+    QPIC_TRY(enqueue_real_solve(c, c->ctl, 0.0));
+    int fix_blocks = blocks_for(n2, FIX_THREADS * 4);
+    if (fix_blocks < 1) fix_blocks = 1;
+    QPIC_LAUNCH(k_potential_fixup, fix_blocks, FIX_THREADS, 0, c->stream, c->ctl, c->g, c->raw, dst, c->prm.psi_threshold - 1);
+    QPIC_TRY(check_launch(c, "k_potential_fixup"));
+    return QPIC_OK;
+}
+
+int enqueue_jx_rho_chi(qpic_ctx * c) {
+    QPIC_LAUNCH_FLAT(k_deposit_jx_rho_chi, blocks_for(c->g.n2, 128), 128, 0, c->stream, c->ctl, c->g, lists_base(c), c->P.vjx, c->P.vrho, c->P.vchi,
+                     c->f3[QPIC_F3_JX_BUNCH], c->f3[QPIC_F3_RHO_BUNCH], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]);
+    return check_launch(c, "k_deposit_jx_rho_chi");
+}
+
+// K1..K9 of SURVEY.md section 3.2: psi, gamma/px, rho/jx/susceptibility (src/System_3d.cpp:334-407)
+int enqueue_slice_head(qpic_ctx * c, bool want_invariants) {
+    const int np = c->P.np;
+    QPIC_TRY(enqueue_potential(c, lists_base(c), c->f2[QPIC_F2_PSI]));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
+                         want_invariants ? 1 : 0);
+        QPIC_TRY(check_launch(c, "k_particles_gamma"));
+    }
+    return enqueue_jx_rho_chi(c);
+}
+
+SliceOut slice_out(qpic_ctx * c) {
+    SliceOut o;
+    o.ex3 = c->f3[QPIC_F3_EX];
+    o.ey3 = c->f3[QPIC_F3_EY];
+    o.ez3 = c->f3[QPIC_F3_EZ];
+    o.by3 = c->f3[QPIC_F3_BY];
+    o.bz3 = c->f3[QPIC_F3_BZ];
+    o.psi3 = c->f3[QPIC_F3_PSI];
+    o.rho3 = c->f3[QPIC_F3_RHO];
+    o.jx3 = c->f3[QPIC_F3_JX];
+    o.jy3 = c->f3[QPIC_F3_JY];
+    o.jz3 = c->f3[QPIC_F3_JZ];
+    return o;
+}
+
+int enqueue_end_of_slice(qpic_ctx * c, int b_is_zero, int roll, int ignore_stop) {
+    QPIC_LAUNCH_FLAT(k_end_of_slice, blocks_for(c->g.n2, 256), 256, 0, c->stream, c->ctl, c->g, slice_out(c), c->f2[QPIC_F2_PSI], c->f2[QPIC_F2_PSI_PREV],
+                     c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ],
+                     c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT], b_is_zero, roll, ignore_stop);
+    return check_launch(c, "k_end_of_slice");
+}
+
+// one full xi-loop iteration for a slice i >= 1 (src/System_3d.cpp:328-619)
+int enqueue_slice_full(qpic_ctx * c) {
+    const int np = c->P.np, n2 = c->g.n2, ny = c->g.ny, nz = c->g.nz;
+    const int M = c->prm.magnetic_field_iterations;
+    QPIC_TRY(enqueue_slice_head(c, M > 0));
+    for (int it = 0; it < M; it++) {
+        if (np > 0) {
+            QPIC_LAUNCH_FLAT(k_particles_predict, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR],
+                             c->count);
+            QPIC_TRY(check_launch(c, "k_particles_predict"));
+        }
+        QPIC_TRY(enqueue_sort(c, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
+        QPIC_TRY(enqueue_potential(c, lists_mid(c), c->f2[QPIC_F2_PSI_MIDDLE]));
+        if (np > 0) {
+            QPIC_LAUNCH_FLAT(k_particles_correct, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
+            QPIC_TRY(check_launch(c, "k_particles_correct"));
+        }
+        QPIC_LAUNCH_FLAT(k_deposit_jy_jz, blocks_for(n2, 128), 128, 0, c->stream, c->ctl, c->g, lists_mid(c), c->P.vjy, c->P.vjz, c->f2[QPIC_F2_JY_NEXT],
+                         c->f2[QPIC_F2_JZ_NEXT]);
+        QPIC_TRY(check_launch(c, "k_deposit_jy_jz"));
+        QPIC_TRY(enqueue_jx_rho_chi(c));
+        // By + i Bz in one complex solve
+        QPIC_LAUNCH(k_fft_rows_b_forward, ny, c->rows_threads, c->rows_smem, c->stream, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
+                    c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
+                    c->f2[QPIC_F2_JZ_NEXT], c->spec);
+        QPIC_TRY(check_launch(c, "k_fft_rows_b_forward"));
+        QPIC_LAUNCH(k_fft_cols_solve, (nz + c->cpb - 1) / c->cpb, c->cols_threads_f, c->cols_smem, c->stream, c->ctl, c->fy.plan, c->fy.tw, c->spec, nz, nz,
+                    c->cpb, c->sy, c->sz, nz, c->prm.magnetic_field_D);
+        QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
+        QPIC_LAUNCH(k_fft_rows_b_backward, ny, c->rows_threads, c->rows_smem, c->stream, c->ctl, c->fz.plan, c->fz.tw, c->g, c->spec, c->f2[QPIC_F2_BY_CUR],
+                    c->f2[QPIC_F2_BZ_CUR], c->prm.threshold_B, it);
+        QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
+    }
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE], c->count);
+        QPIC_TRY(check_launch(c, "k_particles_advance"));
+    }
+    QPIC_TRY(enqueue_sort(c, c->ctl, c->P.cell_b, c->start_b, c->perm_b));
+    QPIC_TRY(enqueue_end_of_slice(c, 0, 1, 0));
+    QPIC_LAUNCH_FLAT(k_next_slice, 1, 32, 0, c->stream, c->ctl);
+    QPIC_TRY(check_launch(c, "k_next_slice"));
+    return QPIC_OK;
+}
+
+// (re)build the cell lists of (y, z) from scratch
+int enqueue_rebuild_base_lists(qpic_ctx * c) {
+    const int np = c->P.np;
+    QPIC_CUDA(c, cudaMemsetAsync(c->count, 0, sizeof(int) * c->g.n2, c->stream));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(np, 256), 256, 0, c->stream, np, c->g, c->P.y, c->P.z, c->P.cell_b, c->P.fy_b, c->P.fz_b, c->count);
+        QPIC_TRY(check_launch(c, "k_locate_count"));
+    }
+    QPIC_TRY(enqueue_sort(c, c->ctl_scratch, c->P.cell_b, c->start_b, c->perm_b));
+    c->lists_dirty = false;
+    return QPIC_OK;
+}
+
+int alloc_particles(qpic_ctx * c, size_t count) {
+    Particles & P = c->P;
+    P.np = (int)count;
+    double ** dbl[] = {&P.y,  &P.z,   &P.py,   &P.pz,   &P.nw,   &P.gamma, &P.px,  &P.pyn, &P.pzn, &P.fy_b, &P.fz_b, &P.fy_m, &P.fz_m,
+                       &P.q,  &P.ap,  &P.t1y,  &P.t1z,  &P.dpy,  &P.dpz,   &P.vjx, &P.vrho, &P.vchi, &P.vjy, &P.vjz};
+    for (double ** p : dbl) QPIC_TRY(dev_alloc(c, p, count));
+    QPIC_TRY(dev_alloc(c, &P.cell_b, count));
+    QPIC_TRY(dev_alloc(c, &P.cell_m, count));
+    QPIC_TRY(dev_alloc(c, &c->perm_b, count));
+    QPIC_TRY(dev_alloc(c, &c->perm_m, count));
+    QPIC_TRY(dev_alloc(c, &c->tmp, count));
+    return QPIC_OK;
+}
+
+int poll_stop(qpic_ctx * c) {
+    QPIC_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->since_poll = 0;
+    if (c->ctl_host->stop_tag != 0) {
+        c->stopped_at = (c->ctl_host->stop_tag - 1) / STOP_TAG_STRIDE;
+        c->cur = c->stopped_at;
+        c->done = true;
+    }
+    return QPIC_OK;
+}
+
+int build_graph(qpic_ctx * c) {
+#ifdef QPIC_EMU
+    (void)c;
+    return QPIC_OK;
+#else
+    if (c->graph_exec) return QPIC_OK;
+    QPIC_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const long before = c->launch_counter;
+    int rc = enqueue_slice_full(c);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != QPIC_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess) return fail(c, QPIC_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    c->launches_per_slice = c->launch_counter - before;
+    c->launch_counter = before;
+    c->graph = graph;
+    QPIC_CUDA(c, cudaGraphInstantiate(&c->graph_exec, graph, 0));
+    return QPIC_OK;
+#endif
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+
+extern "C" {
+
+int qpic_abi_version(void) { return QPIC_ABI_VERSION; }
+
+void qpic_default_params(qpic_params * p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->psi_threshold = 1e-4;
+    p->magnetic_field_D = 10.0;
+    p->threshold_B = 100.0;
+    p->device = 0;
+    p->keep_slices_3d = 0;
+    p->use_graph = 1;
+    p->stop_check_interval = 64;
+}
+
+const char * qpic_last_error(const qpic_ctx * ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void qpic_destroy(qpic_ctx * c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+#ifndef QPIC_EMU
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+#endif
+    for (void * p : c->allocations) cudaFree(p);
+    if (c->ctl_host) cudaFreeHost(c->ctl_host);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int create_impl(qpic_ctx * c) {
+    const qpic_params & p = c->prm;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        return fail(c, QPIC_ERR_CUDA, "no CUDA device available: qpic_b200 has no CPU fallback");
+    }
+    if (p.device < 0 || p.device >= ndev) return fail(c, QPIC_ERR_INVALID, "device %d out of range (%d devices)", p.device, ndev);
+    QPIC_CUDA(c, cudaSetDevice(p.device));
+    QPIC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    QPIC_CUDA(c, cudaEventCreate(&c->ev0));
+    QPIC_CUDA(c, cudaEventCreate(&c->ev1));
+
+    Geom & g = c->g;
+    g.nx = p.nx;
+    g.ny = p.ny;
+    g.nz = p.nz;
+    g.n2 = p.ny * p.nz;
+    g.dx = p.lx / p.nx;  // src/System_3d.cpp:93-95
+    g.dy = p.ly / p.ny;
+    g.dz = p.lz / p.nz;
+    g.ly = p.ly;
+    g.lz = p.lz;
+
+    const size_t n2 = (size_t)g.n2, n3 = n2 * g.nx;
+    QPIC_TRY(make_fft(c, g.ny, &c->fy));
+    QPIC_TRY(make_fft(c, g.nz, &c->fz));
+    QPIC_TRY(make_symbol_tables(c));
+
+    // launch geometry of the transforms
+    c->rows_smem = sizeof(double2) * 2 * (size_t)g.nz;
+    if (c->rows_smem > SMEM_OPTIN_LIMIT) return fail(c, QPIC_ERR_UNSUPPORTED, "nz = %d does not fit the shared-memory row transform", g.nz);
+    c->cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;
+    c->cols_smem = sizeof(double2) * 2 * (size_t)c->cpb * g.ny;
+    if (c->cols_smem > SMEM_OPTIN_LIMIT) return fail(c, QPIC_ERR_UNSUPPORTED, "ny = %d does not fit the shared-memory column transform", g.ny);
+    c->rows_threads = pick_threads(g.nz / 4);
+    c->cols_threads_h = pick_threads(c->cpb * g.ny / 4);
+    c->cols_threads_f = c->cols_threads_h;
+    if (c->rows_smem > SMEM_DEFAULT_LIMIT) {
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
+    }
+    if (c->cols_smem > SMEM_DEFAULT_LIMIT) {
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cols_smem));
+    }
+
+    QPIC_TRY(dev_alloc(c, &c->ctl, 1));
+    QPIC_TRY(dev_alloc(c, &c->ctl_scratch, 1));
+    QPIC_CUDA(c, cudaMallocHost(&c->ctl_host, sizeof(Ctl)));
+    for (int f = 0; f < QPIC_F2_COUNT; f++) QPIC_TRY(dev_alloc(c, &c->f2[f], n2));
+    for (int f = 0; f < QPIC_F3_COUNT; f++) {
+        const bool bunch = (f == QPIC_F3_RHO_BUNCH || f == QPIC_F3_JX_BUNCH);  // allocated on upload
+        const bool slices = (f >= QPIC_F3_PSI);
+        if (bunch || (slices && !p.keep_slices_3d)) continue;
+        QPIC_TRY(dev_alloc(c, &c->f3[f], n3));
+    }
+    QPIC_TRY(dev_alloc(c, &c->fft_in, n2));
+    QPIC_TRY(dev_alloc(c, &c->fft_in2, n2));
+    QPIC_TRY(dev_alloc(c, &c->raw, n2));
+    QPIC_TRY(dev_alloc(c, &c->spec, n2));
+    c->nchunks = blocks_for(n2, SCAN_CHUNK);
+    QPIC_TRY(dev_alloc(c, &c->count, n2));
+    QPIC_TRY(dev_alloc(c, &c->cursor, n2));
+    QPIC_TRY(dev_alloc(c, &c->sums, (size_t)c->nchunks));
+    QPIC_TRY(dev_alloc(c, &c->start_b, n2 + 1));
+    QPIC_TRY(dev_alloc(c, &c->start_m, n2 + 1));
+    QPIC_TRY(alloc_particles(c, 0));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->cur = g.nx - 1;
+    return QPIC_OK;
+}
+
+int qpic_create(const qpic_params * params, qpic_ctx ** out) {
+    if (!out) return fail(nullptr, QPIC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!params) return fail(nullptr, QPIC_ERR_INVALID, "params is NULL");
+    if (params->nx < 1 || params->ny < 1 || params->nz < 1) return fail(nullptr, QPIC_ERR_INVALID, "grid dimensions must be positive");
+    if (!(params->lx > 0) || !(params->ly > 0) || !(params->lz > 0)) return fail(nullptr, QPIC_ERR_INVALID, "box sizes must be positive");
+    if (params->magnetic_field_iterations < 0) {
+        return fail(nullptr, QPIC_ERR_INVALID, "Magnetic field iterations should be non-negative");  // src/System_3d.cpp:77-79
+    }
+    if (params->magnetic_field_iterations >= STOP_TAG_STRIDE) return fail(nullptr, QPIC_ERR_INVALID, "too many magnetic field iterations");
+    if ((double)params->ny * params->nz > 1.0e9 || (double)params->nx * params->ny * params->nz > 8.0e18) {
+        return fail(nullptr, QPIC_ERR_INVALID, "grid too large");
+    }
+    qpic_ctx * c = new (std::nothrow) qpic_ctx();
+    if (!c) return fail(nullptr, QPIC_ERR_NOMEM, "out of host memory");
+    c->prm = *params;
+    if (c->prm.stop_check_interval <= 0) c->prm.stop_check_interval = 64;
+#ifdef QPIC_EMU
+    c->prm.use_graph = 0;
+#endif
+    int rc = create_impl(c);
+    if (rc != QPIC_OK) {
+        g_create_error = c->err;
+        qpic_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return QPIC_OK;
+}
+
+int qpic_set_laser_gaussian(qpic_ctx * c, double amplitude, double wx, double wy, double wz, double x0, double y0, double z0) {
+    if (!c) return QPIC_ERR_INVALID;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t total = (size_t)c->g.nx * c->g.n2;
+    int blocks = blocks_for(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    QPIC_LAUNCH_FLAT(k_init_a_sqr, blocks, 256, 0, c->stream, c->g, c->f3[QPIC_F3_ASQR], amplitude, wx, wy, wz, x0, y0, z0);
+    QPIC_TRY(check_launch(c, "k_init_a_sqr"));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_upload_a_sqr(qpic_ctx * c, const double * a_sqr) {
+    if (!c || !a_sqr) return fail(c, QPIC_ERR_INVALID, "a_sqr is NULL");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(c->f3[QPIC_F3_ASQR], a_sqr, sizeof(double) * (size_t)c->g.nx * c->g.n2, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_upload_bunch_sources(qpic_ctx * c, const double * rho_bunch, const double * jx_bunch) {
+    if (!c) return QPIC_ERR_INVALID;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t n3 = (size_t)c->g.nx * c->g.n2;
+    const double * src[2] = {rho_bunch, jx_bunch};
+    const int idx[2] = {QPIC_F3_RHO_BUNCH, QPIC_F3_JX_BUNCH};
+    if (c->graph_exec && (!c->f3[idx[0]] || !c->f3[idx[1]]) && (rho_bunch || jx_bunch)) {
+        return fail(c, QPIC_ERR_STATE, "bunch sources must be uploaded before the first qpic_step of a context");
+    }
+    for (int t = 0; t < 2; t++) {
+        if (src[t]) {
+            if (!c->f3[idx[t]]) QPIC_TRY(dev_alloc(c, &c->f3[idx[t]], n3, false));
+            QPIC_CUDA(c, cudaMemcpyAsync(c->f3[idx[t]], src[t], sizeof(double) * n3, cudaMemcpyHostToDevice, c->stream));
+        } else if (c->f3[idx[t]]) {
+            QPIC_CUDA(c, cudaMemsetAsync(c->f3[idx[t]], 0, sizeof(double) * n3, c->stream));
+        }
+    }
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, const double * n, size_t count) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (count > 0 && (!y || !z || !n)) return fail(c, QPIC_ERR_INVALID, "particle arrays are NULL");
+    if (count > (size_t)std::numeric_limits<int>::max() - 1024) return fail(c, QPIC_ERR_INVALID, "too many particles for 32-bit particle indices");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (c->graph_exec && (int)count != c->P.np) {
+        return fail(c, QPIC_ERR_STATE, "the particle count cannot change after the first qpic_step of a context");
+    }
+    if ((int)count != c->P.np || !c->P.y) {
+        // (re)allocation: the previous arrays stay owned by the context until qpic_destroy
+        QPIC_TRY(alloc_particles(c, count));
+    } else {
+        double * zero[] = {c->P.py, c->P.pz, c->P.pyn, c->P.pzn, c->P.gamma, c->P.px};
+        for (double * p : zero) QPIC_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * count, c->stream));
+    }
+    if (count > 0) {
+        QPIC_CUDA(c, cudaMemcpyAsync(c->P.y, y, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+        QPIC_CUDA(c, cudaMemcpyAsync(c->P.z, z, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+        QPIC_CUDA(c, cudaMemcpyAsync(c->P.nw, n, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+    }
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->lists_dirty = true;
+    c->began = false;
+    return QPIC_OK;
+}
+
+int qpic_begin(qpic_ctx * c) {
+    if (!c) return QPIC_ERR_INVALID;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const Geom & g = c->g;
+    const size_t n2 = (size_t)g.n2, n3 = n2 * g.nx;
+    // src/System_3d.cpp:265-316
+    QPIC_CUDA(c, cudaMemsetAsync(c->f3[QPIC_F3_EX] + n2 * (size_t)(g.nx - 1), 0, sizeof(double) * n2, c->stream));
+    QPIC_CUDA(c, cudaMemsetAsync(c->f3[QPIC_F3_BY], 0, sizeof(double) * n3, c->stream));
+    QPIC_CUDA(c, cudaMemsetAsync(c->f3[QPIC_F3_BZ], 0, sizeof(double) * n3, c->stream));
+    const int zero2[] = {QPIC_F2_PSI, QPIC_F2_PSI_PREV, QPIC_F2_PSI_MIDDLE, QPIC_F2_JY, QPIC_F2_JZ, QPIC_F2_JY_NEXT, QPIC_F2_JZ_NEXT,
+                         QPIC_F2_BY_CUR, QPIC_F2_BZ_CUR, QPIC_F2_RHO_ION};
+    for (int f : zero2) QPIC_CUDA(c, cudaMemsetAsync(c->f2[f], 0, sizeof(double) * n2, c->stream));
+    Ctl init;
+    init.slice = g.nx - 1;
+    init.stop_tag = 0;
+    init.pad0 = init.pad1 = 0;
+    *c->ctl_host = init;
+    QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    QPIC_TRY(enqueue_rebuild_base_lists(c));
+    // rho_ion (src/System_3d.cpp:319-323)
+    QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(g.n2, 128), 128, 0, c->stream, c->ctl_scratch, c->g, lists_base(c), c->P.nw, (const double *)nullptr,
+                     (const double *)nullptr, (const double *)nullptr, 0, c->f2[QPIC_F2_RHO_ION]);
+    QPIC_TRY(check_launch(c, "k_deposit_charge"));
+    c->cur = g.nx - 1;
+    c->stopped_at = -1;
+    c->done = false;
+    c->finished = false;
+    c->began = true;
+    c->since_poll = 0;
+    return QPIC_OK;
+}
+
+int qpic_step(qpic_ctx * c, int max_slices, int * done) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (!c->began) return fail(c, QPIC_ERR_STATE, "qpic_step called before qpic_begin");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (c->lists_dirty) QPIC_TRY(enqueue_rebuild_base_lists(c));
+    const long launches_before = c->launch_counter;
+    long graph_launches = 0;
+    QPIC_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    int processed = 0;
+    while (!c->done && processed < max_slices) {
+        if (c->cur == 0) {
+            // slice 0: the loop body up to the `i == 0` break (src/System_3d.cpp:334-411)
+            QPIC_TRY(enqueue_slice_head(c, false));
+            c->done = true;
+            processed++;
+            break;
+        }
+#ifndef QPIC_EMU
+        if (c->prm.use_graph) {
+            QPIC_TRY(build_graph(c));
+            QPIC_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+            graph_launches++;
+        } else
+#endif
+        {
+            QPIC_TRY(enqueue_slice_full(c));
+        }
+        c->cur--;
+        processed++;
+        if (c->prm.magnetic_field_iterations > 0 && ++c->since_poll >= c->prm.stop_check_interval) QPIC_TRY(poll_stop(c));
+    }
+    QPIC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->last_launches = (c->launch_counter - launches_before) + graph_launches * c->launches_per_slice;
+    if (done) {
+        // the caller wants a definite answer: make sure a stop raised by the slices queued above is seen
+        if (!c->done && c->prm.magnetic_field_iterations > 0 && c->since_poll > 0) QPIC_TRY(poll_stop(c));
+        *done = c->done ? 1 : 0;
+    }
+    return QPIC_OK;
+}
+
+int qpic_finish(qpic_ctx * c) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (!c->began) return fail(c, QPIC_ERR_STATE, "qpic_finish called before qpic_begin");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (c->prm.magnetic_field_iterations > 0) QPIC_TRY(poll_stop(c));
+    const size_t n2 = (size_t)c->g.n2;
+    if (c->stopped_at >= 0) {
+        // the reference wrote by(i), bz(i) of the stopping slice in place (src/System_3d.cpp:544, :572) and then broke out
+        // of both loops (:582-591); slice 0 is still emitted (:622) with by(0) = bz(0) = 0.
+        QPIC_CUDA(c, cudaMemcpyAsync(c->f3[QPIC_F3_BY] + n2 * c->stopped_at, c->f2[QPIC_F2_BY_CUR], sizeof(double) * n2, cudaMemcpyDeviceToDevice, c->stream));
+        QPIC_CUDA(c, cudaMemcpyAsync(c->f3[QPIC_F3_BZ] + n2 * c->stopped_at, c->f2[QPIC_F2_BZ_CUR], sizeof(double) * n2, cudaMemcpyDeviceToDevice, c->stream));
+        QPIC_TRY(enqueue_end_of_slice(c, 1, 0, 1));
+    } else {
+        QPIC_TRY(enqueue_end_of_slice(c, 0, 0, 0));
+    }
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->finished = true;
+    return QPIC_OK;
+}
+
+int qpic_solve_wakefield(qpic_ctx * c) {
+    QPIC_TRY(qpic_begin(c));
+    int done = 0;
+    while (!done) QPIC_TRY(qpic_step(c, c->prm.stop_check_interval, &done));
+    return qpic_finish(c);
+}
+
+int qpic_synchronize(qpic_ctx * c) {
+    if (!c) return QPIC_ERR_INVALID;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_current_slice(qpic_ctx * c) { return c ? c->cur : -1; }
+
+int qpic_stopped_at(qpic_ctx * c) {
+    if (!c) return -1;
+    if (c->began && !c->finished && c->prm.magnetic_field_iterations > 0) poll_stop(c);
+    return c->stopped_at;
+}
+
+int qpic_last_step_stats(qpic_ctx * c, float * ms, long * kernel_launches) {
+    if (!c) return QPIC_ERR_INVALID;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaEventSynchronize(c->ev1));
+    QPIC_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (ms) *ms = c->last_ms;
+    if (kernel_launches) *kernel_launches = c->last_launches;
+    return QPIC_OK;
+}
+
+// ---- state access
+
+static int copy_out(qpic_ctx * c, const double * src, double * dst, size_t count) {
+    if (!dst) return fail(c, QPIC_ERR_INVALID, "dst is NULL");
+    if (!src) return fail(c, QPIC_ERR_STATE, "this array is not resident (see keep_slices_3d / qpic_upload_bunch_sources)");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_download_field3d(qpic_ctx * c, qpic_field3d f, double * dst) {
+    if (!c || f < 0 || f >= QPIC_F3_COUNT) return fail(c, QPIC_ERR_INVALID, "bad field id");
+    const size_t n3 = (size_t)c->g.nx * c->g.n2;
+    if ((f == QPIC_F3_RHO_BUNCH || f == QPIC_F3_JX_BUNCH) && !c->f3[f]) {
+        if (!dst) return fail(c, QPIC_ERR_INVALID, "dst is NULL");
+        std::memset(dst, 0, sizeof(double) * n3);  // never uploaded == zeros
+        return QPIC_OK;
+    }
+    return copy_out(c, c->f3[f], dst, n3);
+}
+
+int qpic_download_slice3d(qpic_ctx * c, qpic_field3d f, int slice, double * dst) {
+    if (!c || f < 0 || f >= QPIC_F3_COUNT) return fail(c, QPIC_ERR_INVALID, "bad field id");
+    if (slice < 0 || slice >= c->g.nx) return fail(c, QPIC_ERR_INVALID, "slice out of range");
+    const size_t n2 = (size_t)c->g.n2;
+    if ((f == QPIC_F3_RHO_BUNCH || f == QPIC_F3_JX_BUNCH) && !c->f3[f]) {
+        if (!dst) return fail(c, QPIC_ERR_INVALID, "dst is NULL");
+        std::memset(dst, 0, sizeof(double) * n2);
+        return QPIC_OK;
+    }
+    return copy_out(c, c->f3[f] ? c->f3[f] + n2 * slice : nullptr, dst, n2);
+}
+
+int qpic_download_field2d(qpic_ctx * c, qpic_field2d f, double * dst) {
+    if (!c || f < 0 || f >= QPIC_F2_COUNT) return fail(c, QPIC_ERR_INVALID, "bad field id");
+    return copy_out(c, c->f2[f], dst, (size_t)c->g.n2);
+}
+
+int qpic_upload_field2d(qpic_ctx * c, qpic_field2d f, const double * src) {
+    if (!c || f < 0 || f >= QPIC_F2_COUNT || !src) return fail(c, QPIC_ERR_INVALID, "bad field id or NULL src");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(c->f2[f], src, sizeof(double) * (size_t)c->g.n2, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+size_t qpic_particle_count(const qpic_ctx * c) { return c ? (size_t)c->P.np : 0; }
+
+static double * particle_array(qpic_ctx * c, qpic_particle_field f) {
+    switch (f) {
+        case QPIC_P_Y: return c->P.y;
+        case QPIC_P_Z: return c->P.z;
+        case QPIC_P_PY: return c->P.py;
+        case QPIC_P_PZ: return c->P.pz;
+        case QPIC_P_N: return c->P.nw;
+        case QPIC_P_GAMMA: return c->P.gamma;
+        case QPIC_P_PX: return c->P.px;
+        default: return nullptr;
+    }
+}
+
+int qpic_download_particles(qpic_ctx * c, qpic_particle_field f, double * dst) {
+    if (!c) return QPIC_ERR_INVALID;
+    double * src = particle_array(c, f);
+    if (!src) return fail(c, QPIC_ERR_INVALID, "bad particle field id");
+    if (c->P.np == 0) return QPIC_OK;
+    return copy_out(c, src, dst, (size_t)c->P.np);
+}
+
+int qpic_upload_particles(qpic_ctx * c, qpic_particle_field f, const double * src) {
+    if (!c) return QPIC_ERR_INVALID;
+    double * dst = particle_array(c, f);
+    if (!dst || f == QPIC_P_GAMMA || f == QPIC_P_PX || !src) return fail(c, QPIC_ERR_INVALID, "only y, z, py, pz, n can be uploaded");
+    if (c->P.np == 0) return QPIC_OK;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)c->P.np, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (f == QPIC_P_Y || f == QPIC_P_Z) c->lists_dirty = true;
+    return QPIC_OK;
+}
+
+int qpic_set_current_slice(qpic_ctx * c, int slice) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (!c->began) return fail(c, QPIC_ERR_STATE, "qpic_set_current_slice called before qpic_begin");
+    if (slice < 0 || slice >= c->g.nx) return fail(c, QPIC_ERR_INVALID, "slice out of range");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->ctl_host->slice = slice;
+    c->ctl_host->stop_tag = 0;
+    QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->cur = slice;
+    c->done = false;
+    c->finished = false;
+    c->stopped_at = -1;
+    return QPIC_OK;
+}
+
+// ---- building blocks
+
+int qpic_solve_poisson_host(qpic_ctx * c, double * inout, double D) {
+    if (!c || !inout) return fail(c, QPIC_ERR_INVALID, "inout is NULL");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t n2 = (size_t)c->g.n2;
+    QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
+    QPIC_TRY(enqueue_real_solve(c, c->ctl_scratch, D));
+    QPIC_CUDA(c, cudaMemcpyAsync(inout, c->raw, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inout_b, double D) {
+    if (!c || !inout_a || !inout_b) return fail(c, QPIC_ERR_INVALID, "inout is NULL");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t n2 = (size_t)c->g.n2;
+    const int ny = c->g.ny, nz = c->g.nz;
+    QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout_a, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in2, inout_b, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
+    QPIC_LAUNCH(k_fft_rows_c2c, ny, c->rows_threads, c->rows_smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, nz);
+    QPIC_TRY(check_launch(c, "k_fft_rows_c2c"));
+    QPIC_LAUNCH(k_fft_cols_solve, (nz + c->cpb - 1) / c->cpb, c->cols_threads_f, c->cols_smem, c->stream, c->ctl_scratch, c->fy.plan, c->fy.tw, c->spec, nz,
+                nz, c->cpb, c->sy, c->sz, nz, D);
+    QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
+    QPIC_LAUNCH(k_fft_rows_b_backward, ny, c->rows_threads, c->rows_smem, c->stream, c->ctl_scratch, c->fz.plan, c->fz.tw, c->g, c->spec, c->fft_in,
+                c->fft_in2, std::numeric_limits<double>::infinity(), 0);
+    QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
+    QPIC_CUDA(c, cudaMemcpyAsync(inout_a, c->fft_in, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaMemcpyAsync(inout_b, c->fft_in2, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    // a NaN input would have tagged the scratch control block; clear it
+    QPIC_CUDA(c, cudaMemsetAsync(c->ctl_scratch, 0, sizeof(Ctl), c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+// ---- slice-range transfers (streaming a_sqr in / fields out, used by the end-to-end path)
+
+int qpic_upload_a_sqr_slices(qpic_ctx * c, int first_slice, int count, const double * src) {
+    if (!c || !src) return fail(c, QPIC_ERR_INVALID, "src is NULL");
+    if (first_slice < 0 || count < 0 || first_slice + count > c->g.nx) return fail(c, QPIC_ERR_INVALID, "slice range out of bounds");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t n2 = (size_t)c->g.n2;
+    QPIC_CUDA(c, cudaMemcpyAsync(c->f3[QPIC_F3_ASQR] + n2 * first_slice, src, sizeof(double) * n2 * count, cudaMemcpyHostToDevice, c->stream));
+    return QPIC_OK;
+}
+
+int qpic_download_slices3d(qpic_ctx * c, qpic_field3d f, int first_slice, int count, double * dst) {
+    if (!c || f < 0 || f >= QPIC_F3_COUNT || !dst) return fail(c, QPIC_ERR_INVALID, "bad field id or NULL dst");
+    if (first_slice < 0 || count < 0 || first_slice + count > c->g.nx) return fail(c, QPIC_ERR_INVALID, "slice range out of bounds");
+    if (!c->f3[f]) return fail(c, QPIC_ERR_STATE, "this array is not resident (see keep_slices_3d / qpic_upload_bunch_sources)");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t n2 = (size_t)c->g.n2;
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, c->f3[f] + n2 * first_slice, sizeof(double) * n2 * count, cudaMemcpyDeviceToHost, c->stream));
+    return QPIC_OK;
+}
+
+void * qpic_alloc_pinned(size_t bytes) {
+    void * p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void qpic_free_pinned(void * p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- per-kernel timing of eager slices: "name count total_ms\n" lines, one per kernel, in launch order of first use
+int qpic_profile_slices(qpic_ctx * c, int nslices, char * report, size_t report_len) {
+    if (!c || !report || report_len == 0) return fail(c, QPIC_ERR_INVALID, "report buffer is NULL");
+    if (!c->began) return fail(c, QPIC_ERR_STATE, "qpic_profile_slices called before qpic_begin");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (c->lists_dirty) QPIC_TRY(enqueue_rebuild_base_lists(c));
+    report[0] = 0;
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->profiling = true;
+    c->prof_names.clear();
+    c->prof_events.clear();
+    cudaEvent_t first;
+    QPIC_CUDA(c, cudaEventCreate(&first));
+    QPIC_CUDA(c, cudaEventRecord(first, c->stream));
+    c->prof_names.push_back("(start)");
+    c->prof_events.push_back(first);
+    int rc = QPIC_OK;
+    for (int sidx = 0; sidx < nslices && c->cur > 0 && rc == QPIC_OK; sidx++) {
+        rc = enqueue_slice_full(c);
+        c->cur--;
+    }
+    c->profiling = false;
+    if (rc != QPIC_OK) return rc;
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<const char *> names;
+    std::vector<double> total;
+    std::vector<long> count;
+    for (size_t e = 1; e < c->prof_events.size(); e++) {
+        float ms = 0.f;
+        QPIC_CUDA(c, cudaEventElapsedTime(&ms, c->prof_events[e - 1], c->prof_events[e]));
+        size_t k = 0;
+        for (; k < names.size(); k++) {
+            if (std::strcmp(names[k], c->prof_names[e]) == 0) break;
+        }
+        if (k == names.size()) {
+            names.push_back(c->prof_names[e]);
+            total.push_back(0.0);
+            count.push_back(0);
+        }
+        total[k] += ms;
+        count[k] += 1;
+    }
+    for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
+    c->prof_events.clear();
+    c->prof_names.clear();
+    size_t used = 0;
+    for (size_t k = 0; k < names.size(); k++) {
+        int w = snprintf(report + used, report_len - used, "%s %ld %.6f\n", names[k], count[k], total[k]);
+        if (w < 0 || (size_t)w >= report_len - used) break;
+        used += (size_t)w;
+    }
+    QPIC_TRY(poll_stop(c));
+    return QPIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,611 @@
+// Particle / grid kernels of the per-xi-slice solver (sm_100a, FP64).  Everything here is HBM/L2-bound FP64 work:
+// no tensor cores.  Citations are to /root/reference/src (file:line) -- the behaviour each kernel reproduces.
+//
+// Data layout
+//   2-D fields: double[ny*nz], z fastest (array2d, src/array2d.h:15-16).  3-D fields: double[nx*ny*nz], x slowest.
+//   Plasma macro-particles: SoA of doubles (the reference's AoS wake_particle_2d, src/containers.h:31-43), plus a
+//   per-particle "cell descriptor" (cell = jc*nz+kc, fy, fz) = the (int)(y/dy) / fractional split every deposit and
+//   gather of the reference starts with (src/array_utils.cpp:121-127).  Staggered indices are derived from it.
+//
+// Deterministic deposition: particles are counting-sorted by cell (index lists, canonical order inside a cell),
+// then ONE THREAD PER GRID NODE sums the contributions of the particles in the neighbouring cells in a fixed order
+// -- no floating-point atomics anywhere, so every run gives identical bits.
+#pragma once
+
+#include "qpic_compat.h"
+
+namespace qpic {
+
+struct Ctl {
+    int slice;     // xi-slice being solved (nx-1 ... 0)
+    int stop_tag;  // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
+    int pad0, pad1;
+};
+constexpr int STOP_TAG_STRIDE = 1024;
+
+struct Geom {
+    int nx, ny, nz;
+    int n2;  // ny * nz
+    double dx, dy, dz;
+    double ly, lz;
+};
+
+// ------------------------------------------------------------------------------------------------ index helpers
+
+// (int)(y/d) and the fractional part, as every reference deposit / gather begins (src/array_utils.cpp:121-127; for
+// y >= 0 identical to floor((y - 0)/d), :90-96).  y within an ulp of l can round y/d up to n: the reference would
+// index out of bounds there (asserts are compiled out); we map it to the same periodic point, cell 0.
+__device__ __forceinline__ void locate(double y, double d, int n, int & jc, double & f) {
+    const double t = y / d;
+    jc = (int)t;
+    f = t - (double)jc;
+    if (jc >= n) {
+        jc = 0;
+        f = 0.0;
+    }
+}
+
+// index / fraction on a grid whose origin is shifted by +d/2 (jy, jz, by, bz staggering, src/System_3d.cpp:180-193;
+// derivative gathers' floor(y/d - 0.5), src/array_utils.cpp:194-196)
+__device__ __forceinline__ void stagger(int jc, double f, int n, int & j1, double & fs) {
+    if (f >= 0.5) {
+        j1 = jc;
+        fs = f - 0.5;
+    } else {
+        j1 = jc - 1;
+        if (j1 < 0) j1 += n;
+        fs = f + 0.5;
+    }
+}
+
+__device__ __forceinline__ int wrap_inc(int j, int n) {  // (j + 1) % n for 0 <= j < n
+    j += 1;
+    return j >= n ? j - n : j;
+}
+
+__device__ __forceinline__ int wrap_dec(int j, int n) {  // (j - 1 + n) % n
+    return j == 0 ? n - 1 : j - 1;
+}
+
+// 4-point CIC gather given first index / fraction per axis (src/array_utils.cpp:167-188)
+__device__ __forceinline__ double gather4(const double * __restrict__ a, int nz, int j1, int j2, int k1, int k2, double fy, double fz) {
+    return a[nz * j1 + k1] * (1 - fy) * (1 - fz) + a[nz * j2 + k1] * fy * (1 - fz) + a[nz * j1 + k2] * (1 - fy) * fz +
+           a[nz * j2 + k2] * fy * fz;
+}
+
+// node-centred field at the particle
+__device__ __forceinline__ double gather_node(const double * __restrict__ a, int ny, int nz, int jc, int kc, double fy, double fz) {
+    return gather4(a, nz, jc, wrap_inc(jc, ny), kc, wrap_inc(kc, nz), fy, fz);
+}
+
+// d/dy at half points: 6-cell stencil (src/array_utils.cpp:240-263 / :190-213)
+__device__ __forceinline__ double gather_yder(const double * __restrict__ a, int ny, int nz, double dy, int jc, int kc, double fy, double fz) {
+    int j1;
+    double fs;
+    stagger(jc, fy, ny, j1, fs);
+    const int j2 = wrap_inc(j1, ny), j3 = wrap_inc(j2, ny);
+    const int k1 = kc, k2 = wrap_inc(kc, nz);
+    const double d11 = (a[nz * j2 + k1] - a[nz * j1 + k1]) / dy;
+    const double d21 = (a[nz * j3 + k1] - a[nz * j2 + k1]) / dy;
+    const double d12 = (a[nz * j2 + k2] - a[nz * j1 + k2]) / dy;
+    const double d22 = (a[nz * j3 + k2] - a[nz * j2 + k2]) / dy;
+    return d11 * (1 - fs) * (1 - fz) + d21 * fs * (1 - fz) + d12 * (1 - fs) * fz + d22 * fs * fz;
+}
+
+// d/dz at half points (src/array_utils.cpp:265-288 / :215-238)
+__device__ __forceinline__ double gather_zder(const double * __restrict__ a, int ny, int nz, double dz, int jc, int kc, double fy, double fz) {
+    int k1;
+    double fs;
+    stagger(kc, fz, nz, k1, fs);
+    const int k2 = wrap_inc(k1, nz), k3 = wrap_inc(k2, nz);
+    const int j1 = jc, j2 = wrap_inc(jc, ny);
+    const double d11 = (a[nz * j1 + k2] - a[nz * j1 + k1]) / dz;
+    const double d21 = (a[nz * j2 + k2] - a[nz * j2 + k1]) / dz;
+    const double d12 = (a[nz * j1 + k3] - a[nz * j1 + k2]) / dz;
+    const double d22 = (a[nz * j2 + k3] - a[nz * j2 + k2]) / dz;
+    return d11 * (1 - fy) * (1 - fs) + d21 * fy * (1 - fs) + d12 * (1 - fy) * fs + d22 * fy * fs;
+}
+
+// src/System_3d.cpp:668-684
+__device__ __forceinline__ double wrap_coordinate(double y, double l) {
+    y = fmod(y, l);
+    if (y < 0) y += l;
+    return y;
+}
+
+// ------------------------------------------------------------------------------------------------ setup kernels
+
+// a_sqr = amplitude * exp(-(x-x0)^2/wx/wx - (y-y0)^2/wy/wy - (z-z0)^2/wz/wz), node centred
+// (src/System_3d.cpp:805-816, src/profiles.cpp:4-11)
+__global__ void k_init_a_sqr(Geom g, double * __restrict__ a, double amp, double wx, double wy, double wz, double x0, double y0, double z0) {
+    const size_t total = (size_t)g.nx * g.n2;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % g.nz);
+        const int j = (int)((t / g.nz) % g.ny);
+        const int i = (int)(t / g.n2);
+        const double x = i * g.dx, y = j * g.dy, z = k * g.dz;
+        a[t] = amp * exp(-(x - x0) * (x - x0) / wx / wx - (y - y0) * (y - y0) / wy / wy - (z - z0) * (z - z0) / wz / wz);
+    }
+}
+
+// cell descriptors of (y, z) + per-cell population count (integer atomics: order independent)
+__global__ void k_locate_count(int np, Geom g, const double * __restrict__ y, const double * __restrict__ z, int * __restrict__ cell,
+                               double * __restrict__ fy, double * __restrict__ fz, int * __restrict__ count) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    int jc, kc;
+    double f1, f2;
+    locate(y[p], g.dy, g.ny, jc, f1);
+    locate(z[p], g.dz, g.nz, kc, f2);
+    const int c = jc * g.nz + kc;
+    cell[p] = c;
+    fy[p] = f1;
+    fz[p] = f2;
+    atomicAdd(&count[c], 1);
+}
+
+// ------------------------------------------------------------------------------------------------ counting sort by cell
+// count[] -> start[] (exclusive prefix sum), cursor[] = start[], count[] reset to 0 for the next use.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+// exclusive prefix of v over the 256 threads of the block; total = block sum (valid in all threads)
+__device__ __forceinline__ int block_exclusive_scan(int v, int & total) {
+    __shared__ int warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // protects warp_sums against the previous call
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    int offset = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        const int s = warp_sums[w];
+        if (w < wid) offset += s;
+        tot += s;
+    }
+    total = tot;
+    return offset + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunk_sums(const Ctl * ctl, const int * __restrict__ count, int n, int * __restrict__ sums) {
+    if (ctl->stop_tag) return;
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    int v = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; t++) {
+        if (base + t < n) v += count[base + t];
+    }
+    int total;
+    block_exclusive_scan(v, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the chunk sums in place
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int * __restrict__ sums, int nchunks) {
+    if (ctl->stop_tag) return;
+    int carry = 0;
+    for (int base = 0; base < nchunks; base += SCAN_THREADS) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < nchunks ? sums[idx] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, total);
+        if (idx < nchunks) sums[idx] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    k_scan_apply(const Ctl * ctl, int * __restrict__ count, int n, const int * __restrict__ sums, int * __restrict__ start, int * __restrict__ cursor) {
+    if (ctl->stop_tag) return;
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    int c[SCAN_ITEMS];
+    int v = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; t++) {
+        c[t] = (base + t < n) ? count[base + t] : 0;
+        v += c[t];
+    }
+    int total;
+    int run = sums[blockIdx.x] + block_exclusive_scan(v, total);
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; t++) {
+        if (base + t < n) {
+            start[base + t] = run;
+            cursor[base + t] = run;
+            count[base + t] = 0;
+            run += c[t];
+        }
+    }
+    // the last thread of the last chunk ends on the grand total
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) start[n] = run;
+}
+
+// bucket fill: slot order inside a cell is whatever order the integer atomics resolve in ...
+__global__ void k_sort_fill(const Ctl * ctl, int np, const int * __restrict__ cell, int * __restrict__ cursor, int * __restrict__ tmp) {
+    if (ctl->stop_tag) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int slot = atomicAdd(&cursor[cell[p]], 1);
+    tmp[slot] = p;
+}
+
+// ... so each cell's bucket is put into canonical (ascending particle index) order: rank = number of smaller ids.
+// Buckets hold ~ppc entries (a few; tens at strong compression), so the O(k) scan per entry stays in L1.
+__global__ void k_sort_rank(const Ctl * ctl, int np, const int * __restrict__ cell, const int * __restrict__ start, const int * __restrict__ tmp,
+                            int * __restrict__ perm) {
+    if (ctl->stop_tag) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= np) return;
+    const int p = tmp[s];
+    const int c = cell[p];
+    const int b = start[c], e = start[c + 1];
+    int rank = 0;
+    for (int t = b; t < e; t++) rank += (tmp[t] < p) ? 1 : 0;
+    perm[b + rank] = p;
+}
+
+// ------------------------------------------------------------------------------------------------ node-centric deposits
+// One thread per grid node (j,k).  Node-centred target: the node receives from the particles of cells
+// (j,k) [weight (1-fy)(1-fz)], (j-1,k) [fy(1-fz)], (j,k-1) [(1-fy)fz], (j-1,k-1) [fy fz] -- the transpose of the
+// 4-point scatter of src/array_utils.cpp:75-82 / :134-141, each product evaluated as (value*wy)*wz like there.
+
+struct CellLists {
+    const int * start;  // n2 + 1
+    const int * perm;   // np, particle indices grouped by cell
+    const double * fy;
+    const double * fz;
+};
+
+// psi source: fourier.in = jx_bunch(i) - rho_bunch(i) - rho_ion, then deposit of -n (src/System_3d.cpp:342-353, :446-457)
+// with_background == 0: plain deposit of -n, i.e. rho_ion itself (src/System_3d.cpp:319-323)
+__global__ void k_deposit_charge(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ nw, const double * __restrict__ rho_ion,
+                                 const double * __restrict__ jxb3, const double * __restrict__ rhob3, int with_background,
+                                 double * __restrict__ out) {
+    if (ctl->stop_tag) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n2) return;
+    const int j = t / g.nz, k = t - j * g.nz;
+    double acc = 0.0;
+    if (with_background) {
+        const size_t off = (size_t)ctl->slice * g.n2 + t;
+        const double jb = jxb3 ? jxb3[off] : 0.0;
+        const double rb = rhob3 ? rhob3[off] : 0.0;
+        acc = jb - rb - rho_ion[t];
+    }
+    const int jm = wrap_dec(j, g.ny), km = wrap_dec(k, g.nz);
+#pragma unroll
+    for (int oy = 0; oy < 2; oy++) {
+#pragma unroll
+        for (int oz = 0; oz < 2; oz++) {
+            const int c = (oy ? jm : j) * g.nz + (oz ? km : k);
+            const int e = L.start[c + 1];
+            for (int s = L.start[c]; s < e; s++) {
+                const int p = L.perm[s];
+                const double f1 = L.fy[p], f2 = L.fz[p];
+                const double wy = oy ? f1 : 1 - f1;
+                const double wz = oz ? f2 : 1 - f2;
+                acc += -nw[p] * wy * wz;
+            }
+        }
+    }
+    out[t] = acc;
+}
+
+// jx, rho, susceptibility(i) from per-particle values at (y,z) (src/System_3d.cpp:381-397 and :511-527)
+__global__ void k_deposit_jx_rho_chi(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ vjx, const double * __restrict__ vrho,
+                                     const double * __restrict__ vchi, const double * __restrict__ jxb3, const double * __restrict__ rhob3,
+                                     double * __restrict__ jx, double * __restrict__ rho, double * __restrict__ chi3) {
+    if (ctl->stop_tag) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n2) return;
+    const int j = t / g.nz, k = t - j * g.nz;
+    const size_t off = (size_t)ctl->slice * g.n2 + t;
+    double ajx = jxb3 ? jxb3[off] : 0.0;
+    double arho = rhob3 ? rhob3[off] : 0.0;
+    double achi = 0.0;
+    const int jm = wrap_dec(j, g.ny), km = wrap_dec(k, g.nz);
+#pragma unroll
+    for (int oy = 0; oy < 2; oy++) {
+#pragma unroll
+        for (int oz = 0; oz < 2; oz++) {
+            const int c = (oy ? jm : j) * g.nz + (oz ? km : k);
+            const int e = L.start[c + 1];
+            for (int s = L.start[c]; s < e; s++) {
+                const int p = L.perm[s];
+                const double f1 = L.fy[p], f2 = L.fz[p];
+                const double wy = oy ? f1 : 1 - f1;
+                const double wz = oz ? f2 : 1 - f2;
+                ajx += vjx[p] * wy * wz;
+                arho += vrho[p] * wy * wz;
+                achi += vchi[p] * wy * wz;
+            }
+        }
+    }
+    jx[t] = ajx;
+    rho[t] = arho;
+    chi3[off] = achi;
+}
+
+// Weight of a particle with unstaggered fraction f, sitting `role` cells (-1, 0, +1) away from the node's own index,
+// towards a node of the grid shifted by half a cell (see stagger()).  Returns false when the reference's 4-point
+// scatter would not touch this node at all (so that a non-finite value never spreads further than it does there).
+__device__ __forceinline__ bool staggered_weight(int role, double f, double & w) {
+    if (role == 0) {
+        w = (f >= 0.5) ? 1 - (f - 0.5) : f + 0.5;
+        return true;
+    }
+    if (role > 0) {
+        w = 1 - (f + 0.5);
+        return f < 0.5;
+    }
+    w = f - 0.5;
+    return f >= 0.5;
+}
+
+__device__ __forceinline__ bool node_weight(int role, double f, double & w) {
+    w = (role == 0) ? 1 - f : f;
+    return role <= 0;
+}
+
+// jy_next (origin dy/2 in y) and jz_next (origin dz/2 in z) from the half-step positions (src/System_3d.cpp:472-486,
+// staggering :190-193)
+__global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ vjy, const double * __restrict__ vjz,
+                                double * __restrict__ jy_next, double * __restrict__ jz_next) {
+    if (ctl->stop_tag) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n2) return;
+    const int j = t / g.nz, k = t - j * g.nz;
+    double ajy = 0.0, ajz = 0.0;
+    int jr[3], kr[3];
+    jr[0] = wrap_dec(j, g.ny);
+    jr[1] = j;
+    jr[2] = wrap_inc(j, g.ny);
+    kr[0] = wrap_dec(k, g.nz);
+    kr[1] = k;
+    kr[2] = wrap_inc(k, g.nz);
+#pragma unroll
+    for (int ry = -1; ry <= 1; ry++) {
+#pragma unroll
+        for (int rz = -1; rz <= 1; rz++) {
+            if (ry == 1 && rz == 1) continue;  // contributes to neither array
+            const int c = jr[ry + 1] * g.nz + kr[rz + 1];
+            const int e = L.start[c + 1];
+            for (int s = L.start[c]; s < e; s++) {
+                const int p = L.perm[s];
+                const double f1 = L.fy[p], f2 = L.fz[p];
+                double wys, wzn, wyn, wzs;
+                // jy_next: staggered in y, node centred in z;  jz_next: node centred in y, staggered in z
+                const bool in_jy = staggered_weight(ry, f1, wys) & node_weight(rz, f2, wzn);
+                const bool in_jz = node_weight(ry, f1, wyn) & staggered_weight(rz, f2, wzs);
+                if (in_jy) ajy += vjy[p] * wys * wzn;
+                if (in_jz) ajz += vjz[p] * wyn * wzs;
+            }
+        }
+    }
+    jy_next[t] = ajy;
+    jz_next[t] = ajz;
+}
+
+// ------------------------------------------------------------------------------------------------ potential fix-up
+// psi = max(raw - mean(first column U first row), psi_threshold - 1): normalize_potential + increase_minimum
+// (src/System_3d.cpp:30-47, :830-841, call sites :364-365 / :468-469).  Every block recomputes the (ny+nz-1)-term
+// border mean with the same fixed-order tree, so all blocks subtract bit-identical values without a second launch.
+constexpr int FIX_THREADS = 256;
+
+__global__ void __launch_bounds__(FIX_THREADS) k_potential_fixup(const Ctl * ctl, Geom g, const double * __restrict__ raw, double * __restrict__ dst, double floor_value) {
+    if (ctl->stop_tag) return;
+    __shared__ double red[FIX_THREADS];
+    double part = 0.0;
+    const int nb = g.ny + g.nz - 1;
+    for (int t = threadIdx.x; t < nb; t += FIX_THREADS) {
+        part += (t < g.ny) ? raw[(size_t)g.nz * t] : raw[t - g.ny + 1];
+    }
+    red[threadIdx.x] = part;
+    __syncthreads();
+    for (int s = FIX_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double border = red[0] / nb;
+    for (int t = blockIdx.x * FIX_THREADS + threadIdx.x; t < g.n2; t += gridDim.x * FIX_THREADS) {
+        double v = raw[t] - border;
+        if (v < floor_value) v = floor_value;
+        dst[t] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ particle kernels
+
+struct Particles {
+    int np;
+    double *y, *z, *py, *pz, *nw;       // persistent state
+    double *gamma, *px;                  // src/containers.h:41-42
+    double *pyn, *pzn;                   // py_next, pz_next
+    int *cell_b, *cell_m;                // cell of (y,z) / of (y_middle,z_middle)
+    double *fy_b, *fz_b, *fy_m, *fz_m;   // fractional positions inside that cell
+    // slice invariants of the B iterations (the reference re-gathers them every iteration, src/System_3d.cpp:419-423,
+    // :501-502; (y,z), psi and a_sqr(i) do not change inside the iteration loop)
+    double *q;                           // 1 + psi@p
+    double *ap;                          // a_sqr@p
+    double *t1y, *t1z;                   // dx*0.5*d(a_sqr)/dy@p / (1+psi@p), same for z
+    double *dpy, *dpz;                   // dpsi/dy@p, dpsi/dz@p
+    double *vjx, *vrho, *vchi, *vjy, *vjz;  // per-particle deposit values
+};
+
+__device__ __forceinline__ void store_currents(const Particles & P, int p, double nw, double gamma, double px) {
+    const double vx = px / gamma;
+    P.vjx[p] = nw * vx / (1 - vx);
+    P.vrho[p] = nw / (1 - vx);
+    P.vchi[p] = -nw / (1 - vx) / gamma;
+}
+
+// initial gamma, px (src/System_3d.cpp:368-378) + the values deposited at :390-397 + iteration invariants
+__global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ a_sqr3, const double * __restrict__ psi,
+                                  int want_invariants) {
+    if (ctl->stop_tag) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.np) return;
+    const double * a_sqr = a_sqr3 + (size_t)ctl->slice * g.n2;
+    const int c = P.cell_b[p];
+    const int jc = c / g.nz, kc = c - jc * g.nz;
+    const double fy = P.fy_b[p], fz = P.fz_b[p];
+    const double a_particle = gather_node(a_sqr, g.ny, g.nz, jc, kc, fy, fz);
+    const double psi_particle = gather_node(psi, g.ny, g.nz, jc, kc, fy, fz);
+    const double py = P.py[p], pz = P.pz[p];
+    const double gamma = 0.5 * (1 + py * py + pz * pz + a_particle + (1 + psi_particle) * (1 + psi_particle)) / (1 + psi_particle);
+    const double px = 0.5 * (1 + py * py + pz * pz + a_particle - (1 + psi_particle) * (1 + psi_particle)) / (1 + psi_particle);
+    P.gamma[p] = gamma;
+    P.px[p] = px;
+    store_currents(P, p, P.nw[p], gamma, px);
+    if (want_invariants) {
+        const double q = 1 + psi_particle;
+        P.q[p] = q;
+        P.ap[p] = a_particle;
+        P.t1y[p] = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.dy, jc, kc, fy, fz) / q;
+        P.t1z[p] = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.dz, jc, kc, fy, fz) / q;
+        P.dpy[p] = gather_yder(psi, g.ny, g.nz, g.dy, jc, kc, fy, fz);
+        P.dpz[p] = gather_zder(psi, g.ny, g.nz, g.dz, jc, kc, fy, fz);
+    }
+}
+
+// predictor: py_next, pz_next (src/System_3d.cpp:416-433), half-step position (:436-443) and its cell descriptor
+__global__ void k_particles_predict(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
+                                    int * __restrict__ count) {
+    if (ctl->stop_tag) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.np) return;
+    const int c = P.cell_b[p];
+    const int jc = c / g.nz, kc = c - jc * g.nz;
+    const double fy = P.fy_b[p], fz = P.fz_b[p];
+    int js, ks;
+    double fys, fzs;
+    stagger(jc, fy, g.ny, js, fys);
+    stagger(kc, fz, g.nz, ks, fzs);
+    // by lives at (y, z + dz/2), bz at (y + dy/2, z)  (src/System_3d.cpp:180-181)
+    const double by_particle = gather4(by, g.nz, jc, wrap_inc(jc, g.ny), ks, wrap_inc(ks, g.nz), fy, fzs);
+    const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
+    const double q = P.q[p], gamma = P.gamma[p];
+    double pyn = P.py[p] - P.t1y[p];
+    pyn += g.dx * gamma * P.dpy[p] / q;
+    pyn -= g.dx * bz_particle;
+    double pzn = P.pz[p] - P.t1z[p];
+    pzn += g.dx * gamma * P.dpz[p] / q;
+    pzn += g.dx * by_particle;
+    P.pyn[p] = pyn;
+    P.pzn[p] = pzn;
+    const double ym = wrap_coordinate(P.y[p] + 0.5 * g.dx * pyn / q, g.ly);
+    const double zm = wrap_coordinate(P.z[p] + 0.5 * g.dx * pzn / q, g.lz);
+    int jm, km;
+    double f1, f2;
+    locate(ym, g.dy, g.ny, jm, f1);
+    locate(zm, g.dz, g.nz, km, f2);
+    const int cm = jm * g.nz + km;
+    P.cell_m[p] = cm;
+    P.fy_m[p] = f1;
+    P.fz_m[p] = f2;
+    atomicAdd(&count[cm], 1);
+}
+
+// values for the jy/jz deposit (src/System_3d.cpp:480-486) and the corrector gamma, px (:498-508) + :520-527 values
+__global__ void k_particles_correct(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle) {
+    if (ctl->stop_tag) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.np) return;
+    const int cm = P.cell_m[p];
+    const int jm = cm / g.nz, km = cm - jm * g.nz;
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[p], P.fz_m[p]);
+    const double nw = P.nw[p], pyn = P.pyn[p], pzn = P.pzn[p], py = P.py[p], pz = P.pz[p];
+    P.vjy[p] = nw * pyn / (1 + psi_particle);
+    P.vjz[p] = nw * pzn / (1 + psi_particle);
+    const double q = P.q[p], a_particle = P.ap[p];
+    const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
+    const double gamma = 0.5 * (1 + p_squared + a_particle + q * q) / q;
+    const double px = 0.5 * (1 + p_squared + a_particle - q * q) / q;
+    P.gamma[p] = gamma;
+    P.px[p] = px;
+    store_currents(P, p, nw, gamma, px);
+}
+
+// py <- py_next, pz <- pz_next (src/System_3d.cpp:593-598), coordinate advance with psi_middle gathered at (y,z)
+// (:601-608), new cell descriptor + population count for the next slice's lists
+__global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle, int * __restrict__ count) {
+    if (ctl->stop_tag) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.np) return;
+    const int c = P.cell_b[p];
+    const int jc = c / g.nz, kc = c - jc * g.nz;
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jc, kc, P.fy_b[p], P.fz_b[p]);
+    const double py = P.pyn[p], pz = P.pzn[p];
+    P.py[p] = py;
+    P.pz[p] = pz;
+    const double y = wrap_coordinate(P.y[p] + g.dx * py / (1 + psi_particle), g.ly);
+    const double z = wrap_coordinate(P.z[p] + g.dx * pz / (1 + psi_particle), g.lz);
+    P.y[p] = y;
+    P.z[p] = z;
+    int jn, kn;
+    double f1, f2;
+    locate(y, g.dy, g.ny, jn, f1);
+    locate(z, g.dz, g.nz, kn, f2);
+    const int cn = jn * g.nz + kn;
+    P.cell_b[p] = cn;
+    P.fy_b[p] = f1;
+    P.fz_b[p] = f2;
+    atomicAdd(&count[cn], 1);
+}
+
+// ------------------------------------------------------------------------------------------------ end of slice
+// output_step (src/System_3d.cpp:629-666): ex(i), ey(i), ez(i); by(i)/bz(i) go to their 3-D rows; optional per-slice
+// copies of psi,rho,jx,jy,jz (write_slice, :663-665); then the K1/K31 copies psi_prev<-psi, jy<-jy_next, jz<-jz_next
+// (:334-339, :612-618) which are elementwise and therefore safe to do here.
+struct SliceOut {
+    double *ex3, *ey3, *ez3, *by3, *bz3;
+    double *psi3, *rho3, *jx3, *jy3, *jz3;  // nullable
+};
+
+__global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double * __restrict__ psi, double * __restrict__ psi_prev,
+                               const double * __restrict__ by, const double * __restrict__ bz, const double * __restrict__ rho,
+                               const double * __restrict__ jx, double * __restrict__ jy, double * __restrict__ jz,
+                               const double * __restrict__ jy_next, const double * __restrict__ jz_next, int b_is_zero, int roll, int ignore_stop) {
+    if (ctl->stop_tag && !ignore_stop) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n2) return;
+    const int i = ignore_stop ? 0 : ctl->slice;
+    const int j = t / g.nz, k = t - j * g.nz;
+    const size_t off = (size_t)i * g.n2 + t;
+    const double ps = psi[t];
+    if (i < g.nx - 1) o.ex3[off] = (ps - psi_prev[t]) / g.dx;
+    const double b_y = b_is_zero ? 0.0 : by[t];
+    const double b_z = b_is_zero ? 0.0 : bz[t];
+    o.ey3[off] = -(psi[wrap_inc(j, g.ny) * g.nz + k] - ps) / g.dy + b_z;
+    o.ez3[off] = -(psi[j * g.nz + wrap_inc(k, g.nz)] - ps) / g.dz - b_y;
+    if (!b_is_zero) {
+        o.by3[off] = b_y;
+        o.bz3[off] = b_z;
+    }
+    if (o.psi3) {
+        o.psi3[off] = ps;
+        o.rho3[off] = rho[t];
+        o.jx3[off] = jx[t];
+        o.jy3[off] = jy[t];
+        o.jz3[off] = jz[t];
+    }
+    if (roll) {
+        psi_prev[t] = ps;
+        jy[t] = jy_next[t];
+        jz[t] = jz_next[t];
+    }
+}
+
+__global__ void k_next_slice(Ctl * ctl) {
+    if (ctl->stop_tag) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctl->slice -= 1;
+}
+
+}  // namespace qpic

@@ -1,0 +1,366 @@
+"""ctypes binding of the qpic_b200 C ABI (include/qpic_b200.h) and a host-side mirror of the reference's
+solver interface.
+
+The reference is a C++ program without a plugin boundary; its hot path is `System_3d::solve_wakefield`
+(reference src/System_3d.cpp:238-627) operating on `System_3d`'s members.  `WakefieldSolver` below exposes
+the same state under the reference's names (psi, rho, jx, jy, jz, by, bz, ex, ey, ez, aSqr, susceptibility;
+src/System_3d.cpp:49-62) and the same call order (init_wake_particles -> solve_wakefield), so the parity
+tests read like a transcript of `System_3d::run()` (src/System_3d.cpp:199-236).
+
+There is NO CPU fallback here: the shared library is CUDA-only and loading / creating a context fails loudly
+without a B200-class device.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_PKG_DIR, "libqpic_b200.so")
+
+FIELDS_2D = ["psi", "psi_prev", "psi_middle", "rho", "jx", "jy", "jz", "jy_next", "jz_next", "rho_ion", "by_cur", "bz_cur"]
+FIELDS_3D = ["aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "by", "bz"]
+SLICE_FIELDS_3D = ["psi", "rho", "jx", "jy", "jz"]  # filled slice by slice, like Output_writer::write_slice
+PARTICLE_FIELDS = ["y", "z", "py", "pz", "n", "gamma", "px"]
+
+# every symbol include/qpic_b200.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "qpic_default_params", "qpic_create", "qpic_destroy", "qpic_last_error", "qpic_abi_version",
+    "qpic_set_laser_gaussian", "qpic_upload_a_sqr", "qpic_upload_bunch_sources", "qpic_init_wake_particles",
+    "qpic_solve_wakefield", "qpic_begin", "qpic_step", "qpic_finish", "qpic_synchronize", "qpic_current_slice",
+    "qpic_stopped_at", "qpic_download_field3d", "qpic_download_slice3d", "qpic_download_field2d",
+    "qpic_upload_field2d", "qpic_particle_count", "qpic_download_particles", "qpic_upload_particles",
+    "qpic_set_current_slice", "qpic_solve_poisson_host", "qpic_solve_helmholtz_pair_host", "qpic_last_step_stats",
+    "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
+]
+
+
+class QpicError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"qpic_b200 error {code}: {message}")
+        self.code = code
+
+
+class QpicParams(ctypes.Structure):
+    _fields_ = [
+        ("nx", ctypes.c_int), ("ny", ctypes.c_int), ("nz", ctypes.c_int),
+        ("lx", ctypes.c_double), ("ly", ctypes.c_double), ("lz", ctypes.c_double),
+        ("magnetic_field_iterations", ctypes.c_int),
+        ("psi_threshold", ctypes.c_double),
+        ("magnetic_field_D", ctypes.c_double),
+        ("threshold_B", ctypes.c_double),
+        ("device", ctypes.c_int),
+        ("keep_slices_3d", ctypes.c_int),
+        ("use_graph", ctypes.c_int),
+        ("stop_check_interval", ctypes.c_int),
+    ]
+
+
+class QpicLibrary:
+    """A loaded qpic_b200 shared library with typed entry points."""
+
+    def __init__(self, path=LIBRARY_PATH):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path = path
+        L = ctypes.CDLL(path)
+        vp, dbl, ci = ctypes.c_void_p, ctypes.c_double, ctypes.c_int
+        L.qpic_default_params.argtypes = [ctypes.POINTER(QpicParams)]
+        L.qpic_default_params.restype = None
+        L.qpic_create.argtypes = [ctypes.POINTER(QpicParams), ctypes.POINTER(vp)]
+        L.qpic_destroy.argtypes = [vp]
+        L.qpic_destroy.restype = None
+        L.qpic_last_error.argtypes = [vp]
+        L.qpic_last_error.restype = ctypes.c_char_p
+        L.qpic_set_laser_gaussian.argtypes = [vp] + [dbl] * 7
+        L.qpic_upload_a_sqr.argtypes = [vp, vp]
+        L.qpic_upload_bunch_sources.argtypes = [vp, vp, vp]
+        L.qpic_init_wake_particles.argtypes = [vp, vp, vp, vp, ctypes.c_size_t]
+        L.qpic_solve_wakefield.argtypes = [vp]
+        L.qpic_begin.argtypes = [vp]
+        L.qpic_step.argtypes = [vp, ci, ctypes.POINTER(ci)]
+        L.qpic_finish.argtypes = [vp]
+        L.qpic_synchronize.argtypes = [vp]
+        L.qpic_current_slice.argtypes = [vp]
+        L.qpic_stopped_at.argtypes = [vp]
+        L.qpic_download_field3d.argtypes = [vp, ci, vp]
+        L.qpic_download_slice3d.argtypes = [vp, ci, ci, vp]
+        L.qpic_download_field2d.argtypes = [vp, ci, vp]
+        L.qpic_upload_field2d.argtypes = [vp, ci, vp]
+        L.qpic_particle_count.argtypes = [vp]
+        L.qpic_particle_count.restype = ctypes.c_size_t
+        L.qpic_download_particles.argtypes = [vp, ci, vp]
+        L.qpic_upload_particles.argtypes = [vp, ci, vp]
+        L.qpic_set_current_slice.argtypes = [vp, ci]
+        L.qpic_solve_poisson_host.argtypes = [vp, vp, dbl]
+        L.qpic_solve_helmholtz_pair_host.argtypes = [vp, vp, vp, dbl]
+        L.qpic_last_step_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_long)]
+        L.qpic_profile_slices.argtypes = [vp, ci, ctypes.c_char_p, ctypes.c_size_t]
+        L.qpic_upload_a_sqr_slices.argtypes = [vp, ci, ci, vp]
+        L.qpic_download_slices3d.argtypes = [vp, ci, ci, ci, vp]
+        L.qpic_alloc_pinned.argtypes = [ctypes.c_size_t]
+        L.qpic_alloc_pinned.restype = vp
+        L.qpic_free_pinned.argtypes = [vp]
+        L.qpic_free_pinned.restype = None
+        self.L = L
+
+    def pinned_array(self, shape):
+        """float64 numpy array backed by page-locked host memory (freed with free_pinned)."""
+        count = int(np.prod(shape))
+        ptr = self.L.qpic_alloc_pinned(count * 8)
+        if not ptr:
+            raise MemoryError("cudaMallocHost failed")
+        buf = (ctypes.c_double * count).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)
+        return arr, ptr
+
+    def free_pinned(self, ptr):
+        self.L.qpic_free_pinned(ptr)
+
+
+_product_library = None
+
+
+def load_library():
+    """The product library, quetzalpic_b200/libqpic_b200.so (CUDA, sm_100a)."""
+    global _product_library
+    if _product_library is None:
+        _product_library = QpicLibrary(LIBRARY_PATH)
+    return _product_library
+
+
+def grid_dimensions(l, d):
+    """n = static_cast<int>(l / d) per axis (reference src/System_3d.cpp:87-89; note 4.8/0.2 -> 23)."""
+    return tuple(int(float(a) / float(b)) for a, b in zip(l, d))
+
+
+def wake_particle_lattice(ny, nz, ly, lz, ppcy, ppcz, profile=None, rho0=-1.0):
+    """Positions and weights of System_3d::init_wake_particles (reference src/System_3d.cpp:724-748).
+
+    `profile(y, z)` (vectorised) gives the plasma density; None = constant2d(rho0) (src/profiles.cpp:47-51).
+    Particles where the profile is exactly 0 are skipped (:735).  Order: y-major, then z (:730-731).
+    """
+    dy, dz = ly / ny, lz / nz
+    yy = (np.arange(ppcy * ny) + 0.5) * dy / ppcy
+    zz = (np.arange(ppcz * nz) + 0.5) * dz / ppcz
+    y, z = np.meshgrid(yy, zz, indexing="ij")
+    y, z = y.ravel(), z.ravel()
+    value = np.full(y.shape, float(rho0)) if profile is None else np.asarray(profile(y, z), dtype=np.float64)
+    keep = value != 0
+    return y[keep].copy(), z[keep].copy(), (value[keep] / ppcy / ppcz).copy()
+
+
+def powerlaw2d(power, radius, y0, z0, min_factor=0.0, max_factor=1e10, amplitude=-1.0):
+    """Plasma channel profile, reference src/profiles.cpp:53-64 (Config_reader.cpp:243-252 passes amplitude -1)."""
+    def profile(y, z):
+        r = np.sqrt((y - y0) * (y - y0) + (z - z0) * (z - z0))
+        value = np.power(r / radius, power)
+        value = np.minimum(value, max_factor)
+        value = np.maximum(value, min_factor)
+        return amplitude * value
+    return profile
+
+
+def gaussian_laser_widths(xsigma, ysigma, zsigma):
+    """Full width at 1/e^2 -> Gaussian parameter, reference src/Config_reader.cpp:124-126."""
+    s = np.sqrt(8.0)
+    return xsigma / s, ysigma / s, zsigma / s
+
+
+class WakefieldSolver:
+    """Device-resident quasistatic wakefield solver: the state System_3d::solve_wakefield works on."""
+
+    def __init__(self, nx, ny, nz, lx, ly, lz, magnetic_field_iterations, psi_threshold=1e-4, magnetic_field_D=10.0,
+                 threshold_B=100.0, device=0, keep_slices_3d=False, use_graph=True, stop_check_interval=64, library=None):
+        self.lib = library if library is not None else load_library()
+        L = self.lib.L
+        p = QpicParams()
+        L.qpic_default_params(ctypes.byref(p))
+        p.nx, p.ny, p.nz = int(nx), int(ny), int(nz)
+        p.lx, p.ly, p.lz = float(lx), float(ly), float(lz)
+        p.magnetic_field_iterations = int(magnetic_field_iterations)
+        p.psi_threshold, p.magnetic_field_D, p.threshold_B = float(psi_threshold), float(magnetic_field_D), float(threshold_B)
+        p.device = int(device)
+        p.keep_slices_3d = int(bool(keep_slices_3d))
+        p.use_graph = int(bool(use_graph))
+        p.stop_check_interval = int(stop_check_interval)
+        self.params = p
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.keep_slices_3d = bool(keep_slices_3d)
+        handle = ctypes.c_void_p()
+        rc = L.qpic_create(ctypes.byref(p), ctypes.byref(handle))
+        if rc != 0:
+            raise QpicError(rc, L.qpic_last_error(None).decode())
+        self.ctx = handle
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise QpicError(rc, self.lib.L.qpic_last_error(self.ctx).decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.L.qpic_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- inputs
+    def set_laser_gaussian(self, amplitude, wx, wy, wz, x0, y0, z0):
+        self._check(self.lib.L.qpic_set_laser_gaussian(self.ctx, amplitude, wx, wy, wz, x0, y0, z0))
+
+    def upload_a_sqr(self, a_sqr):
+        a = np.ascontiguousarray(a_sqr, dtype=np.float64)
+        if a.shape != (self.nx, self.ny, self.nz):
+            raise ValueError("a_sqr must have shape (nx, ny, nz)")
+        self._check(self.lib.L.qpic_upload_a_sqr(self.ctx, a.ctypes.data))
+
+    def upload_bunch_sources(self, rho_bunch=None, jx_bunch=None):
+        arrs = []
+        for a in (rho_bunch, jx_bunch):
+            if a is None:
+                arrs.append(None)
+            else:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                if a.shape != (self.nx, self.ny, self.nz):
+                    raise ValueError("bunch sources must have shape (nx, ny, nz)")
+                arrs.append(a)
+        self._check(self.lib.L.qpic_upload_bunch_sources(
+            self.ctx, None if arrs[0] is None else arrs[0].ctypes.data, None if arrs[1] is None else arrs[1].ctypes.data))
+
+    def init_wake_particles(self, y, z, n):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        n = np.ascontiguousarray(n, dtype=np.float64)
+        if not (y.shape == z.shape == n.shape and y.ndim == 1):
+            raise ValueError("y, z, n must be 1-D arrays of equal length")
+        self._check(self.lib.L.qpic_init_wake_particles(self.ctx, y.ctypes.data, z.ctypes.data, n.ctypes.data, y.size))
+
+    # -- sweep
+    def solve_wakefield(self):
+        self._check(self.lib.L.qpic_solve_wakefield(self.ctx))
+        return self.stopped_at
+
+    def begin(self):
+        self._check(self.lib.L.qpic_begin(self.ctx))
+
+    def step(self, max_slices=1, wait=True):
+        """Runs up to max_slices xi-slices.  wait=True returns whether the sweep is over (synchronises);
+        wait=False only queues the work."""
+        if wait:
+            done = ctypes.c_int(0)
+            self._check(self.lib.L.qpic_step(self.ctx, int(max_slices), ctypes.byref(done)))
+            return bool(done.value)
+        self._check(self.lib.L.qpic_step(self.ctx, int(max_slices), None))
+        return None
+
+    def finish(self):
+        self._check(self.lib.L.qpic_finish(self.ctx))
+
+    def synchronize(self):
+        self._check(self.lib.L.qpic_synchronize(self.ctx))
+
+    @property
+    def current_slice(self):
+        return self.lib.L.qpic_current_slice(self.ctx)
+
+    @current_slice.setter
+    def current_slice(self, value):
+        self._check(self.lib.L.qpic_set_current_slice(self.ctx, int(value)))
+
+    @property
+    def stopped_at(self):
+        return self.lib.L.qpic_stopped_at(self.ctx)
+
+    def last_step_stats(self):
+        ms = ctypes.c_float(0)
+        launches = ctypes.c_long(0)
+        self._check(self.lib.L.qpic_last_step_stats(self.ctx, ctypes.byref(ms), ctypes.byref(launches)))
+        return ms.value, launches.value
+
+    def profile_slices(self, nslices=1):
+        """Eager slices with an event after every kernel: {kernel: (launches, total_ms)} in first-launch order."""
+        buf = ctypes.create_string_buffer(16384)
+        self._check(self.lib.L.qpic_profile_slices(self.ctx, int(nslices), buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, count, ms = line.split()
+            out[name] = (int(count), float(ms))
+        return out
+
+    def upload_a_sqr_slices(self, first_slice, a_sqr_block):
+        """asynchronous; a_sqr_block: (count, ny, nz) contiguous float64 (ideally pinned)"""
+        assert a_sqr_block.flags["C_CONTIGUOUS"] and a_sqr_block.dtype == np.float64
+        self._check(self.lib.L.qpic_upload_a_sqr_slices(self.ctx, int(first_slice), int(a_sqr_block.shape[0]), a_sqr_block.ctypes.data))
+
+    def download_slices3d(self, name, first_slice, out_block, per_slice=False):
+        """asynchronous; out_block: (count, ny, nz) contiguous float64 (ideally pinned); synchronize() before reading"""
+        assert out_block.flags["C_CONTIGUOUS"] and out_block.dtype == np.float64
+        self._check(self.lib.L.qpic_download_slices3d(self.ctx, self._field3d_index(name, per_slice), int(first_slice),
+                                                      int(out_block.shape[0]), out_block.ctypes.data))
+
+    # -- state
+    def field2d(self, name):
+        out = np.empty((self.ny, self.nz))
+        self._check(self.lib.L.qpic_download_field2d(self.ctx, FIELDS_2D.index(name), out.ctypes.data))
+        return out
+
+    def set_field2d(self, name, value):
+        a = np.ascontiguousarray(value, dtype=np.float64)
+        if a.shape != (self.ny, self.nz):
+            raise ValueError("2-D fields have shape (ny, nz)")
+        self._check(self.lib.L.qpic_upload_field2d(self.ctx, FIELDS_2D.index(name), a.ctypes.data))
+
+    def _field3d_index(self, name, per_slice):
+        if per_slice:
+            return len(FIELDS_3D) + SLICE_FIELDS_3D.index(name)
+        return FIELDS_3D.index(name)
+
+    def field3d(self, name, per_slice=False):
+        """(nx, ny, nz) array; per_slice=True selects the slice-by-slice accumulation of psi/rho/jx/jy/jz."""
+        out = np.empty((self.nx, self.ny, self.nz))
+        self._check(self.lib.L.qpic_download_field3d(self.ctx, self._field3d_index(name, per_slice), out.ctypes.data))
+        return out
+
+    def slice3d(self, name, i, per_slice=False):
+        out = np.empty((self.ny, self.nz))
+        self._check(self.lib.L.qpic_download_slice3d(self.ctx, self._field3d_index(name, per_slice), int(i), out.ctypes.data))
+        return out
+
+    @property
+    def particle_count(self):
+        return self.lib.L.qpic_particle_count(self.ctx)
+
+    def particles(self, name):
+        out = np.empty(self.particle_count)
+        self._check(self.lib.L.qpic_download_particles(self.ctx, PARTICLE_FIELDS.index(name), out.ctypes.data))
+        return out
+
+    def set_particles(self, name, value):
+        a = np.ascontiguousarray(value, dtype=np.float64)
+        if a.shape != (self.particle_count,):
+            raise ValueError("particle arrays have shape (particle_count,)")
+        self._check(self.lib.L.qpic_upload_particles(self.ctx, PARTICLE_FIELDS.index(name), a.ctypes.data))
+
+    # -- building blocks
+    def solve_poisson(self, src, D=0.0):
+        a = np.array(src, dtype=np.float64, order="C")
+        self._check(self.lib.L.qpic_solve_poisson_host(self.ctx, a.ctypes.data, float(D)))
+        return a
+
+    def solve_helmholtz_pair(self, src_a, src_b, D):
+        a = np.array(src_a, dtype=np.float64, order="C")
+        b = np.array(src_b, dtype=np.float64, order="C")
+        self._check(self.lib.L.qpic_solve_helmholtz_pair_host(self.ctx, a.ctypes.data, b.ctypes.data, float(D)))
+        return a, b

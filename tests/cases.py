@@ -1,0 +1,111 @@
+"""Shared helpers for the parity tests: build the same problem for the CPU oracle and the CUDA solver."""
+import os
+import re
+
+import numpy as np
+
+from quetzalpic_b200 import gaussian_laser_widths, grid_dimensions, powerlaw2d, wake_particle_lattice
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def parse_toml(path):
+    """Tiny reader for the reference-style input files used as fixtures (key = value, [table])."""
+    root, cur = {}, None
+    cur = root
+    for line in open(path):
+        line = line.split("#", 1)[0].strip()
+        if not line:
+            continue
+        m = re.match(r"\[(\w+)\]", line)
+        if m:
+            cur = root.setdefault(m.group(1), {})
+            continue
+        k, v = [s.strip() for s in line.split("=", 1)]
+        if v in ("true", "false"):
+            cur[k] = v == "true"
+        elif v[0] in "\"'":
+            cur[k] = v[1:-1]
+        else:
+            cur[k] = float(v) if any(c in v for c in ".eE") else int(v)
+    return root
+
+
+class Case:
+    """Everything System_3d derives from an input file before solve_wakefield (reference src/System_3d.cpp:64-197,
+    src/Config_reader.cpp:18-262)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        l = (float(cfg["lx"]), float(cfg["ly"]), float(cfg["lz"]))
+        d = (float(cfg["dx"]), float(cfg["dy"]), float(cfg["dz"]))
+        self.l = l
+        self.n = grid_dimensions(l, d)
+        self.M = int(cfg.get("magnetic_field_iterations", 0))
+        self.ppcy = int(cfg.get("ppcy", 1))
+        self.ppcz = int(cfg.get("ppcz", 1))
+        self.laser = None
+        if "laser" in cfg:
+            ls = cfg["laser"]
+            wx, wy, wz = gaussian_laser_widths(ls["xsigma"], ls["ysigma"], ls["zsigma"])
+            self.laser = (0.5 * ls["a0"] * ls["a0"], wx, wy, wz, float(ls.get("x0", ls["xsigma"])),
+                          float(ls.get("y0", 0.5 * l[1])), float(ls.get("z0", 0.5 * l[2])))
+        profile, rho0 = None, -1.0
+        if "plasma" in cfg:
+            pl = cfg["plasma"]
+            if pl["profile"] == "powerlaw":
+                profile = powerlaw2d(pl["power"], pl["radius"], pl.get("y0", 0.5 * l[1]), pl.get("z0", 0.5 * l[2]),
+                                     pl.get("min_factor", 0.0), pl.get("max_factor", 1e10), -1.0)
+            else:
+                rho0 = float(pl.get("rho0", -1))
+        nx, ny, nz = self.n
+        self.particles = wake_particle_lattice(ny, nz, l[1], l[2], self.ppcy, self.ppcz, profile=profile, rho0=rho0)
+
+    @classmethod
+    def from_toml(cls, name):
+        return cls(parse_toml(os.path.join(GOLDEN, "inputs", name + ".toml")))
+
+    @classmethod
+    def synthetic(cls, n, d, M, ppc=(1, 1), a0=1.0, sigma=None, x0=None, **extra):
+        nx, ny, nz = n
+        cfg = dict(lx=nx * d[0], ly=ny * d[1], lz=nz * d[2], dx=d[0], dy=d[1], dz=d[2], ppcy=ppc[0], ppcz=ppc[1],
+                   magnetic_field_iterations=M)
+        if a0:
+            sigma = sigma or (0.5 * cfg["lx"], 0.5 * cfg["ly"], 0.5 * cfg["lz"])
+            cfg["laser"] = dict(a0=a0, xsigma=sigma[0], ysigma=sigma[1], zsigma=sigma[2], x0=x0 if x0 is not None else 0.6 * cfg["lx"])
+        cfg.update(extra)
+        c = cls(cfg)
+        c.n = (nx, ny, nz)  # exact by construction
+        return c
+
+    def make_oracle(self, **kw):
+        from oracle.qo import Oracle
+        nx, ny, nz = self.n
+        o = Oracle(nx, ny, nz, self.l[0], self.l[1], self.l[2], self.M, **kw)
+        if self.laser:
+            o.set_laser_gaussian(*self.laser)
+        o.init_wake_particles(*self.particles)
+        return o
+
+    def make_solver(self, a_sqr=None, **kw):
+        from quetzalpic_b200 import WakefieldSolver
+        nx, ny, nz = self.n
+        s = WakefieldSolver(nx, ny, nz, self.l[0], self.l[1], self.l[2], self.M, **kw)
+        if a_sqr is not None:
+            s.upload_a_sqr(a_sqr)
+        elif self.laser:
+            s.set_laser_gaussian(*self.laser)
+        s.init_wake_particles(*self.particles)
+        return s
+
+
+def rel_l2(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0)
+
+
+def slice_rel_l2(a, b):
+    """max over slices of ||a_i - b_i|| / max_i ||b_i|| (early slices can be ~1e-90: SURVEY.md section 8c)."""
+    diff = np.sqrt(((a - b) ** 2).sum(axis=(1, 2)))
+    ref = np.sqrt((b ** 2).sum(axis=(1, 2))).max()
+    return diff.max() / (ref if ref > 0 else 1.0)

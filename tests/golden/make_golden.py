@@ -1,0 +1,93 @@
+"""Generates the golden fixtures in tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Only works in the build container (needs /root/reference and `make -C oracle ref`); the GPU box and the
+test-suite only read the committed .npz files.  Usage:  python tests/golden/make_golden.py
+
+The reference executable is oracle/_ref/quasistatic_pic_O2: /root/reference/src/*.cpp compiled unmodified with
+-O2 (IEEE, no fast-math) against the shim headers in oracle/shims/, run with OMP_NUM_THREADS=1 so that its
+atomic deposits land in index order and the output is reproducible to the last bit.
+
+Fixtures:
+  <name>.npz for the tiny inputs     every dataset of Fields_000.h5 (full 3-D) and Fields_xy_000.h5 + attributes
+  laser_test_summary.npz             the shipped inputs/test/laser_test.toml (200^3): per-field min/max/L2 norm,
+                                     per-slice L2 norms, on-axis lines [:, ny/2, nz/2], transverse lines through
+                                     slice 100, and the value at [100,100,100]
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "quasistatic_pic_O2")
+NAMES_3D = ["aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "by", "bz", "psi", "rho", "jx", "jy", "jz"]
+
+
+def read_attrs(path):
+    out = {}
+    if not os.path.exists(path):
+        return out
+    for line in open(path):
+        parts = line.split()
+        name, dtype, count = parts[0], parts[1], int(parts[2])
+        vals = parts[3:3 + count]
+        out[name] = np.array([float(v) for v in vals]) if dtype == "<f8" else np.array([int(v) for v in vals], dtype=np.int32)
+    return out
+
+
+def run_reference(toml_path, workdir):
+    name = os.path.basename(toml_path)
+    shutil.copy(toml_path, os.path.join(workdir, name))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    log = subprocess.run([REF_EXE, name], cwd=workdir, env=env, check=True, capture_output=True, text=True).stdout
+    return log
+
+
+def collect(workdir, log):
+    data = {}
+    for kind, sub in (("f3", "Fields_000.h5.d"), ("xy", "Fields_xy_000.h5.d")):
+        for nm in NAMES_3D:
+            data[f"{kind}/{nm}"] = np.load(os.path.join(workdir, sub, nm + ".npy"))
+            for an, av in read_attrs(os.path.join(workdir, sub, nm + ".attrs")).items():
+                data[f"{kind}/{nm}@{an}"] = av
+    data["stopped"] = np.array(int("Stop condition encountered" in log))
+    data["stdout"] = np.array(log)
+    return data
+
+
+def main():
+    if not os.path.exists(REF_EXE):
+        sys.exit("build the reference first: make -C oracle ref")
+    for name in ["tiny_laser", "tiny_profile", "tiny_bunch", "tiny_bunch_stop"]:
+        with tempfile.TemporaryDirectory() as wd:
+            log = run_reference(os.path.join(HERE, "inputs", name + ".toml"), wd)
+            data = collect(wd, log)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, data["f3/psi"].shape, "stopped" if data["stopped"] else "")
+
+    with tempfile.TemporaryDirectory() as wd:
+        log = run_reference(os.path.join(HERE, "inputs", "laser_test.toml"), wd)
+        data = collect(wd, log)
+    summary = {"stdout": data["stdout"], "stopped": data["stopped"]}
+    for nm in NAMES_3D:
+        a = data["f3/" + nm]
+        nx, ny, nz = a.shape
+        summary[nm + "/min"] = a.min()
+        summary[nm + "/max"] = a.max()
+        summary[nm + "/l2"] = np.linalg.norm(a)
+        summary[nm + "/slice_l2"] = np.sqrt((a ** 2).sum(axis=(1, 2)))
+        summary[nm + "/axis"] = a[:, ny // 2, nz // 2].copy()
+        summary[nm + "/line_y"] = a[100, :, nz // 2].copy()
+        summary[nm + "/line_z"] = a[100, ny // 2, :].copy()
+        summary[nm + "/probe"] = a[100, 100, 100]
+        summary[nm + "/xy"] = data["xy/" + nm][::4, ::4].copy()
+    np.savez_compressed(os.path.join(HERE, "laser_test_summary.npz"), **summary)
+    print("laser_test summary written")
+
+
+if __name__ == "__main__":
+    main()
