@@ -1,0 +1,112 @@
+"""CPU suite (no GPU): host-side logic and the C-ABI surface.  No compute call is made without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import quetzalpic_b200 as qp
+from cases import Case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "qpic_b200.h")).read()
+    declared = set(re.findall(r"\b(qpic_[a-z0-9_]+)\s*\(", header))
+    declared -= {"qpic_ctx", "qpic_params", "qpic_status"}
+    assert declared == set(qp.ABI_SYMBOLS), declared ^ set(qp.ABI_SYMBOLS)
+    lib = qp.load_library()
+    for sym in declared:
+        assert hasattr(lib.L, sym), sym
+    assert lib.L.qpic_abi_version() == 1
+
+
+def test_library_is_cuda_only_and_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(qp.QpicError) as e:
+        qp.WakefieldSolver(4, 4, 4, 1.0, 1.0, 1.0, 1)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_parameter_validation_mirrors_reference_exceptions():
+    """std::invalid_argument cases of System_3d::System_3d (src/System_3d.cpp:77-85) -> QPIC_ERR_INVALID, before any CUDA call."""
+    lib = qp.load_library()
+    p = qp.solver.QpicParams()
+    lib.L.qpic_default_params(ctypes.byref(p))
+    assert (p.psi_threshold, p.magnetic_field_D, p.threshold_B, p.use_graph) == (1e-4, 10.0, 100.0, 1)
+    handle = ctypes.c_void_p()
+    p.nx, p.ny, p.nz, p.lx, p.ly, p.lz = 4, 4, 4, 1.0, 1.0, 1.0
+    p.magnetic_field_iterations = -1
+    assert lib.L.qpic_create(ctypes.byref(p), ctypes.byref(handle)) == -1
+    assert b"Magnetic field iterations should be non-negative" in lib.L.qpic_last_error(None)
+    p.magnetic_field_iterations = 1
+    p.ny = 0
+    assert lib.L.qpic_create(ctypes.byref(p), ctypes.byref(handle)) == -1
+    assert lib.L.qpic_create(None, ctypes.byref(handle)) == -1
+
+
+def test_wake_particle_lattice_matches_reference_init():
+    """System_3d::init_wake_particles (src/System_3d.cpp:724-748): y-major order, (i+0.5)*d/ppc, n = profile/ppcy/ppcz,
+    zero-density sites skipped."""
+    y, z, n = qp.wake_particle_lattice(3, 2, 3.0, 1.0, 2, 1)
+    assert y.size == 3 * 2 * 2
+    assert np.allclose(y[:2], 0.25) and np.allclose(z[:2], [0.25, 0.75]) and np.all(n == -0.5)
+    prof = qp.powerlaw2d(2, 1.0, 1.5, 0.5, min_factor=0.0)
+    y, z, n = qp.wake_particle_lattice(3, 1, 3.0, 1.0, 1, 1, profile=prof)
+    assert y.size == 2 and np.allclose(n, [-1.0, -1.0])  # the centre site has r = 0 -> density 0 -> skipped
+    assert qp.grid_dimensions((4.8, 2.4, 20), (0.2, 0.2, 0.1)) == (23, 11, 200)
+
+
+def test_oracle_and_solver_build_the_same_problem():
+    case = Case.from_toml("tiny_profile")
+    o = case.make_oracle()
+    assert o.particle_count == case.particles[0].size
+    assert np.array_equal(o.particles("n"), case.particles[2])
+
+
+def _scan_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import bench
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    r, w, l = bench.dist_env()
+    a0, rho0 = bench.SCAN[r % len(bench.SCAN)]
+    # every rank times its own member; the job-level time is the MAX over ranks, the job-level work the SUM
+    t = torch.tensor([10.0 + r], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    work = torch.tensor([1.0], dtype=torch.float64)
+    dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    out.put((r, a0, rho0, float(t.item()), float(work.item())))
+    dist.destroy_process_group()
+
+
+def test_parameter_scan_sharding_world_size_2_gloo():
+    """N > 1 = independent members of the a0/density scan, one per rank, no data-path collective; only the timing
+    reduction (max) crosses ranks.  Exercised with gloo on CPU."""
+    import torch.multiprocessing as mp
+    import sys
+    sys.path.insert(0, ROOT)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_scan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[0] for r in res] == [0, 1]
+    assert (res[0][1], res[0][2]) != (res[1][1], res[1][2])          # different scan members
+    assert res[0][3] == res[1][3] == 11.0 and res[0][4] == res[1][4] == 2.0
+
+
+def test_bench_bytes_formula():
+    import bench
+    # 1.554 GB per slice at config #2
+    assert abs(bench.algorithmic_bytes_per_slice(512 * 512, 4 * 512 * 512, 5) - 1.554e9) < 1e6
