@@ -49,6 +49,8 @@ typedef struct {
                                       fills Fields_NNN.h5 (src/System_3d.cpp:663-665); needs 5 more (nx,ny,nz) arrays */
     int use_graph;                 /* != 0 (default): replay one CUDA graph per slice; 0: eager launches (debugging) */
     int stop_check_interval;       /* the host polls the device stop flag every this many slices (<=0: 64) */
+    int force_general_deposit;     /* != 0: always use the sort-based deposit (valid for any half-step displacement) instead of
+                                      trying the sort-free tile deposit first (valid for displacements <= 1 cell, with rollback) */
 } qpic_params;
 
 /* fills *p with the reference defaults (psi_threshold 1e-4, D 10, threshold_B 100, device 0, graph on) */
@@ -129,6 +131,8 @@ int qpic_solve_poisson_host(qpic_ctx * ctx, double * inout, double D);
 int qpic_solve_helmholtz_pair_host(qpic_ctx * ctx, double * inout_a, double * inout_b, double D);
 /* CUDA-event timing of the last qpic_step call (ms), and kernels launched by it */
 int qpic_last_step_stats(qpic_ctx * ctx, float * ms, long * kernel_launches);
+/* how many times the sort-free deposit had to be abandoned for a slice (half-step displacement > 1 cell) */
+long qpic_fast_path_aborts(const qpic_ctx * ctx);
 /* runs up to nslices slices eagerly with a CUDA event after every kernel; report = lines "kernel count total_ms" */
 int qpic_profile_slices(qpic_ctx * ctx, int nslices, char * report, size_t report_len);
 

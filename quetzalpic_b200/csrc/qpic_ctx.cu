@@ -44,6 +44,14 @@ struct qpic_ctx {
     Geom g;
     std::string err;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // second branch of the per-iteration fork (see enqueue_slice_full)
+    std::vector<cudaEvent_t> ev_pool;
+    int ev_next = 0;
+    bool fast_capable = false;  // sort-free tile deposits usable for this grid
+    int general_left = 0;       // slices still to run on the general path after a fast-path abort
+    int general_penalty = 16;
+    long fast_aborts = 0;
+    int target = 0;             // slice index the caller has asked the sweep to reach (-1: slice 0 processed too)
     bool began = false;
     bool done = false;
     bool finished = false;
@@ -68,15 +76,19 @@ struct qpic_ctx {
     int nchunks = 0;
     std::vector<void *> allocations;
 
-    // launch geometry
-    int rows_threads = 128, cols_threads_h = 128, cols_threads_f = 128;
-    int cpb = 1;
-    size_t rows_smem = 0, cols_smem = 0;
+    // launch geometry of the transforms: sequences per block, threads, dynamic shared memory
+    struct FftLaunch {
+        int spb = 1, threads = 128, blocks = 1;
+        size_t smem = 0;
+    };
+    FftLaunch rows_real, rows_cplx, cols_half, cols_full;
+    bool pow2_y = false, pow2_z = false;
+    double inv_scale = 0.0;  // 1/(ny*nz) when that is exactly representable (power of two), else 0 = divide
 
     // graph
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    long launches_per_slice = 0;
+    cudaGraph_t graph = nullptr, graph_fast = nullptr;
+    cudaGraphExec_t graph_exec = nullptr, graph_exec_fast = nullptr;
+    long launches_per_slice = 0, launches_per_slice_fast = 0;
 
     // stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -141,6 +153,10 @@ int make_fft(qpic_ctx * c, int n, DeviceFft * out) {
     FftPlan & P = out->plan;
     P.n = n;
     P.nfac = 0;
+    P.log2n = 0;
+    if (n >= 64 && (n & (n - 1)) == 0) {
+        while ((1 << P.log2n) < n) P.log2n++;
+    }
     int m = n;
     auto push = [&](int f) -> bool {
         if (P.nfac >= FFT_MAX_FACTORS) return false;
@@ -172,6 +188,32 @@ int make_fft(qpic_ctx * c, int n, DeviceFft * out) {
     QPIC_TRY(dev_alloc(c, &out->tw, (size_t)n, false));
     QPIC_CUDA(c, cudaMemcpyAsync(out->tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));  // tw is a local
+    return QPIC_OK;
+}
+
+// nseq sequences of length n: how many per block.  Power-of-two engine: exactly n/8 threads per sequence, in place;
+// generic engine: one block-wide loop, ping-pong buffers.
+int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what) {
+    const int n = P.n;
+    if (P.log2n > 0) {
+        const int e8 = n / 8;
+        int spb = 256 / e8;
+        if (spb < 1) spb = 1;
+        const int want = nseq / 148;  // keep at least ~one block per SM when there is enough work
+        if (spb > want) spb = want;
+        if (spb < 1) spb = 1;
+        while (spb * e8 < 32) spb *= 2;
+        L->spb = spb;
+        L->threads = spb * e8;
+        L->smem = sizeof(double2) * (size_t)spb * n;
+    } else {
+        L->spb = 1;
+        L->threads = pick_threads(n / 4);
+        L->smem = sizeof(double2) * 2 * (size_t)n;
+    }
+    if (L->threads > 1024) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d needs more than 1024 threads per block", what, n);
+    if (L->smem > SMEM_OPTIN_LIMIT) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d does not fit the shared-memory transform", what, n);
+    L->blocks = (nseq + L->spb - 1) / L->spb;
     return QPIC_OK;
 }
 
@@ -207,68 +249,194 @@ CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, c->perm_b, c->
 CellLists lists_mid(qpic_ctx * c) { return CellLists{c->start_m, c->perm_m, c->P.fy_m, c->P.fz_m}; }
 
 // ---------------------------------------------------------------------------------------------- kernel sequences
+//
+// Two variants of the slice body exist:
+//   FAST     sort-free tile deposits (k_tile_deposit); valid while every half-step displacement stays within +-1 cell.
+//            A violation raises Ctl::fast_fail on the device, which turns the rest of the sweep into no-ops; the host
+//            notices at its next poll, restores By/Bz of the slice start and redoes the slice on the
+//   GENERAL  path: counting sort of the half-step positions + node-centric deposits, valid for any displacement.
+// Independent branches of an iteration (corrector gamma + jx deposit  ||  psi_middle solve + jy/jz deposit) are issued
+// on two streams joined by events, so they become parallel branches of the captured graph.
+
+cudaEvent_t next_event(qpic_ctx * c) {
+    cudaEvent_t e = c->ev_pool[c->ev_next];
+    c->ev_next = (c->ev_next + 1) % (int)c->ev_pool.size();
+    return e;
+}
+
+// work queued on `to` after this call waits for everything queued on `from` so far
+int stream_depend(qpic_ctx * c, cudaStream_t from, cudaStream_t to) {
+    if (from == to) return QPIC_OK;
+    cudaEvent_t e = next_event(c);
+    QPIC_CUDA(c, cudaEventRecord(e, from));
+    QPIC_CUDA(c, cudaStreamWaitEvent(to, e, 0));
+    return QPIC_OK;
+}
 
 // count[] (already accumulated by a particle kernel) -> start[], perm[] in canonical order
-int enqueue_sort(qpic_ctx * c, const Ctl * ctl, const int * cell, int * start, int * perm) {
+int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cell, int * start, int * perm) {
     const int n2 = c->g.n2, np = c->P.np;
-    QPIC_LAUNCH(k_scan_chunk_sums, c->nchunks, SCAN_THREADS, 0, c->stream, ctl, c->count, n2, c->sums);
+    QPIC_LAUNCH(k_scan_chunk_sums, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums);
     QPIC_TRY(check_launch(c, "k_scan_chunk_sums"));
-    QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, c->stream, ctl, c->sums, c->nchunks);
+    QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, st, ctl, c->sums, c->nchunks);
     QPIC_TRY(check_launch(c, "k_scan_sums"));
-    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, c->stream, ctl, c->count, n2, c->sums, start, c->cursor);
+    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums, start, c->cursor);
     QPIC_TRY(check_launch(c, "k_scan_apply"));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_sort_fill, blocks_for(np, 256), 256, 0, c->stream, ctl, np, cell, c->cursor, c->tmp);
+        QPIC_LAUNCH_FLAT(k_sort_fill, blocks_for(np, 256), 256, 0, st, ctl, np, cell, c->cursor, c->tmp);
         QPIC_TRY(check_launch(c, "k_sort_fill"));
-        QPIC_LAUNCH_FLAT(k_sort_rank, blocks_for(np, 256), 256, 0, c->stream, ctl, np, cell, start, c->tmp, perm);
+        QPIC_LAUNCH_FLAT(k_sort_rank, blocks_for(np, 256), 256, 0, st, ctl, np, cell, start, c->tmp, perm);
         QPIC_TRY(check_launch(c, "k_sort_rank"));
     }
     return QPIC_OK;
 }
 
 // real solve: fft_in -> raw (= solution / ny / nz)
-int enqueue_real_solve(qpic_ctx * c, const Ctl * ctl, double D) {
+int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D) {
     const int ny = c->g.ny, nz = c->g.nz, nzh = nz / 2 + 1;
-    QPIC_LAUNCH(k_fft_rows_r2c, (ny + 1) / 2, c->rows_threads, c->rows_smem, c->stream, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz);
+    auto r2c = c->pow2_z ? k_fft_rows_r2c<true> : k_fft_rows_r2c<false>;
+    auto c2r = c->pow2_z ? k_fft_rows_c2r<true> : k_fft_rows_c2r<false>;
+    auto cols = c->pow2_y ? k_fft_cols_solve<true> : k_fft_cols_solve<false>;
+    QPIC_LAUNCH(r2c, c->rows_real.blocks, c->rows_real.threads, c->rows_real.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz,
+                c->rows_real.spb);
     QPIC_TRY(check_launch(c, "k_fft_rows_r2c"));
-    QPIC_LAUNCH(k_fft_cols_solve, (nzh + c->cpb - 1) / c->cpb, c->cols_threads_h, c->cols_smem, c->stream, ctl, c->fy.plan, c->fy.tw, c->spec, nzh, nzh,
-                c->cpb, c->sy, c->sz, nz, D);
+    QPIC_LAUNCH(cols, c->cols_half.blocks, c->cols_half.threads, c->cols_half.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, nzh, nzh, c->cols_half.spb,
+                c->sy, c->sz, nz, D);
     QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
-    QPIC_LAUNCH(k_fft_rows_c2r, (ny + 1) / 2, c->rows_threads, c->rows_smem, c->stream, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz);
+    QPIC_LAUNCH(c2r, c->rows_real.blocks, c->rows_real.threads, c->rows_real.smem, st, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz,
+                c->rows_real.spb, c->inv_scale);
     QPIC_TRY(check_launch(c, "k_fft_rows_c2r"));
     return QPIC_OK;
 }
 
-// psi (or psi_middle) from the particle lists L: source deposit, solve, normalise + clamp (src/System_3d.cpp:342-365, :446-469)
-int enqueue_potential(qpic_ctx * c, CellLists L, double * dst) {
-    const int n2 = c->g.n2;
-    QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(n2, 128), 128, 0, c->stream, c->ctl, c->g, L, c->P.nw, c->f2[QPIC_F2_RHO_ION], c->f3[QPIC_F3_JX_BUNCH],
-                     c->f3[QPIC_F3_RHO_BUNCH], 1, c->fft_in);
-    QPIC_TRY(check_launch(c, "k_deposit_charge"));
-    QPIC_TRY(enqueue_real_solve(c, c->ctl, 0.0));
-    int fix_blocks = blocks_for(n2, FIX_THREADS * 4);
+// complex solve of (re, im) = (by, bz) style pairs: spec must already hold the forward row transforms
+int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D) {
+    const int nz = c->g.nz;
+    auto cols = c->pow2_y ? k_fft_cols_solve<true> : k_fft_cols_solve<false>;
+    QPIC_LAUNCH(cols, c->cols_full.blocks, c->cols_full.threads, c->cols_full.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, nz, nz, c->cols_full.spb,
+                c->sy, c->sz, nz, D);
+    return check_launch(c, "k_fft_cols_solve");
+}
+
+// ---- tile deposit jobs (FAST path)
+
+dim3 tile_grid(qpic_ctx * c) { return dim3((c->g.nz + TILE - 1) / TILE, (c->g.ny + TILE - 1) / TILE); }
+
+TileOutput tile_output(const double * val, double sign, int at_mid, int stag_y, int stag_z, int bg_mode, const double * bg3, double * out, int out_3d) {
+    TileOutput o;
+    o.val = val;
+    o.sign = sign;
+    o.at_mid = at_mid;
+    o.stag_y = stag_y;
+    o.stag_z = stag_z;
+    o.bg_mode = bg_mode;
+    o.bg3 = bg3;
+    o.out = out;
+    o.out_3d = out_3d;
+    return o;
+}
+
+TileJob tile_job(qpic_ctx * c) {
+    TileJob j;
+    std::memset(&j, 0, sizeof(j));
+    j.jxb3 = c->f3[QPIC_F3_JX_BUNCH];
+    j.rhob3 = c->f3[QPIC_F3_RHO_BUNCH];
+    j.rho_ion = c->f2[QPIC_F2_RHO_ION];
+    return j;
+}
+
+// psi source from positions (y,z) [at_mid = 0] or the half-step positions [at_mid = 1] -> fft_in
+int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
+    TileJob j = tile_job(c);
+    j.nout = 1;
+    j.o[0] = tile_output(c->P.nw, -1.0, at_mid, 0, 0, 1, nullptr, c->fft_in, 0);
+    if (at_mid) {
+        auto kern = k_tile_deposit<2, 1, false>;
+        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 3, TILE + 3), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
+    } else {
+        auto kern = k_tile_deposit<1, 0, false>;
+        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 1, TILE + 1), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
+    }
+    return check_launch(c, at_mid ? "k_tile_deposit_charge_mid" : "k_tile_deposit_charge");
+}
+
+// deposits at (y,z): jx and / or rho + susceptibility(i)
+int enqueue_tile_base_currents(qpic_ctx * c, cudaStream_t st, bool with_jx, bool with_rho_chi, bool final_pass) {
+    TileJob j = tile_job(c);
+    int n = 0;
+    if (with_jx) j.o[n++] = tile_output(c->P.vjx, 1.0, 0, 0, 0, 2, c->f3[QPIC_F3_JX_BUNCH], c->f2[QPIC_F2_JX], 0);
+    if (with_rho_chi) {
+        j.o[n++] = tile_output(c->P.vrho, 1.0, 0, 0, 0, 2, c->f3[QPIC_F3_RHO_BUNCH], c->f2[QPIC_F2_RHO], 0);
+        j.o[n++] = tile_output(c->P.vchi, 1.0, 0, 0, 0, 0, nullptr, c->f3[QPIC_F3_SUSCEPTIBILITY], 1);
+    }
+    j.nout = n;
+    if (final_pass) {
+        auto kern = k_tile_deposit<1, 0, true>;
+        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 1, TILE + 1), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
+    } else {
+        auto kern = k_tile_deposit<1, 0, false>;
+        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 1, TILE + 1), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
+    }
+    return check_launch(c, with_jx ? (with_rho_chi ? "k_tile_deposit_jx_rho_chi" : "k_tile_deposit_jx") : "k_tile_deposit_rho_chi");
+}
+
+// jy_next (staggered in y) and jz_next (staggered in z) at the half-step positions
+int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
+    TileJob j = tile_job(c);
+    j.nout = 2;
+    j.o[0] = tile_output(c->P.vjy, 1.0, 1, 1, 0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
+    j.o[1] = tile_output(c->P.vjz, 1.0, 1, 0, 1, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
+    auto kern = k_tile_deposit<2, 2, false>;
+    QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 4, TILE + 4), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
+    return check_launch(c, "k_tile_deposit_jy_jz");
+}
+
+// ---- potentials
+
+int enqueue_fixup(qpic_ctx * c, cudaStream_t st, double * dst) {
+    int fix_blocks = blocks_for(c->g.n2, FIX_THREADS * 4);
     if (fix_blocks < 1) fix_blocks = 1;
-    QPIC_LAUNCH(k_potential_fixup, fix_blocks, FIX_THREADS, 0, c->stream, c->ctl, c->g, c->raw, dst, c->prm.psi_threshold - 1);
-    QPIC_TRY(check_launch(c, "k_potential_fixup"));
-    return QPIC_OK;
+    QPIC_LAUNCH(k_potential_fixup, fix_blocks, FIX_THREADS, 0, st, c->ctl, c->g, c->raw, dst, c->prm.psi_threshold - 1);
+    return check_launch(c, "k_potential_fixup");
 }
 
-int enqueue_jx_rho_chi(qpic_ctx * c) {
-    QPIC_LAUNCH_FLAT(k_deposit_jx_rho_chi, blocks_for(c->g.n2, 128), 128, 0, c->stream, c->ctl, c->g, lists_base(c), c->P.vjx, c->P.vrho, c->P.vchi,
-                     c->f3[QPIC_F3_JX_BUNCH], c->f3[QPIC_F3_RHO_BUNCH], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]);
-    return check_launch(c, "k_deposit_jx_rho_chi");
+// psi (at_mid = 0) or psi_middle (at_mid = 1): source deposit, solve, normalise + clamp (src/System_3d.cpp:342-365, :446-469)
+int enqueue_potential(qpic_ctx * c, cudaStream_t st, bool fast, int at_mid, double * dst) {
+    if (fast) {
+        QPIC_TRY(enqueue_tile_charge(c, st, at_mid));
+    } else {
+        CellLists L = at_mid ? lists_mid(c) : lists_base(c);
+        QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(c->g.n2, 128), 128, 0, st, c->ctl, c->g, L, c->P.nw, c->f2[QPIC_F2_RHO_ION], c->f3[QPIC_F3_JX_BUNCH],
+                         c->f3[QPIC_F3_RHO_BUNCH], 1, c->fft_in);
+        QPIC_TRY(check_launch(c, "k_deposit_charge"));
+    }
+    QPIC_TRY(enqueue_real_solve(c, st, c->ctl, 0.0));
+    return enqueue_fixup(c, st, dst);
 }
 
-// K1..K9 of SURVEY.md section 3.2: psi, gamma/px, rho/jx/susceptibility (src/System_3d.cpp:334-407)
-int enqueue_slice_head(qpic_ctx * c, bool want_invariants) {
+// deposits at (y,z) on either path
+int enqueue_base_currents(qpic_ctx * c, cudaStream_t st, bool fast, bool with_jx, bool with_rho_chi, bool final_pass) {
+    if (fast) return enqueue_tile_base_currents(c, st, with_jx, with_rho_chi, final_pass);
+    const int blocks = blocks_for(c->g.n2, 128);
+    auto kern = with_jx ? (with_rho_chi ? k_deposit_jx_rho_chi<true, true> : k_deposit_jx_rho_chi<true, false>) : k_deposit_jx_rho_chi<false, true>;
+    QPIC_LAUNCH_FLAT(kern, blocks, 128, 0, st, c->ctl, c->g, lists_base(c), c->P.vjx, c->P.vrho, c->P.vchi, c->f3[QPIC_F3_JX_BUNCH], c->f3[QPIC_F3_RHO_BUNCH],
+                     c->f2[QPIC_F2_JX], c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY], final_pass ? 1 : 0);
+    return check_launch(c, with_jx ? (with_rho_chi ? "k_deposit_jx_rho_chi" : "k_deposit_jx") : "k_deposit_rho_chi");
+}
+
+// K1..K6 of SURVEY.md section 3.2: psi, gamma/px (src/System_3d.cpp:334-378).  with_deposit: also rho/jx/susceptibility
+// (:381-397) -- needed only when no B iteration follows (M = 0, or slice 0), every iteration redeposits them.
+int enqueue_slice_head(qpic_ctx * c, bool fast, bool want_invariants, bool with_deposit) {
     const int np = c->P.np;
-    QPIC_TRY(enqueue_potential(c, lists_base(c), c->f2[QPIC_F2_PSI]));
+    cudaStream_t st = c->stream;
+    QPIC_TRY(enqueue_potential(c, st, fast, 0, c->f2[QPIC_F2_PSI]));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
+        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, 128), 128, 0, st, c->ctl, c->g, c->P, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
                          want_invariants ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_gamma"));
     }
-    return enqueue_jx_rho_chi(c);
+    if (with_deposit) QPIC_TRY(enqueue_base_currents(c, st, fast, true, true, false));
+    return QPIC_OK;
 }
 
 SliceOut slice_out(qpic_ctx * c) {
@@ -294,45 +462,73 @@ int enqueue_end_of_slice(qpic_ctx * c, int b_is_zero, int roll, int ignore_stop)
 }
 
 // one full xi-loop iteration for a slice i >= 1 (src/System_3d.cpp:328-619)
-int enqueue_slice_full(qpic_ctx * c) {
-    const int np = c->P.np, n2 = c->g.n2, ny = c->g.ny, nz = c->g.nz;
+int enqueue_slice_full(qpic_ctx * c, bool fast) {
+    const int np = c->P.np, n2 = c->g.n2;
     const int M = c->prm.magnetic_field_iterations;
-    QPIC_TRY(enqueue_slice_head(c, M > 0));
+    cudaStream_t sa = c->stream;
+    cudaStream_t sb = c->profiling ? c->stream : c->stream2;  // per-kernel timing wants one serial stream
+    QPIC_TRY(enqueue_slice_head(c, fast, M > 0, M == 0));
     for (int it = 0; it < M; it++) {
         if (np > 0) {
-            QPIC_LAUNCH_FLAT(k_particles_predict, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR],
-                             c->count);
+            auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
+            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
-        QPIC_TRY(enqueue_sort(c, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
-        QPIC_TRY(enqueue_potential(c, lists_mid(c), c->f2[QPIC_F2_PSI_MIDDLE]));
+        // branch B: corrector gamma / px and the jx deposit at (y,z) need only py_next, pz_next
+        QPIC_TRY(stream_depend(c, sa, sb));
         if (np > 0) {
-            QPIC_LAUNCH_FLAT(k_particles_correct, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
-            QPIC_TRY(check_launch(c, "k_particles_correct"));
+            QPIC_LAUNCH_FLAT(k_particles_correct_gamma, blocks_for(np, 128), 128, 0, sb, c->ctl, c->g, c->P);
+            QPIC_TRY(check_launch(c, "k_particles_correct_gamma"));
         }
-        QPIC_LAUNCH_FLAT(k_deposit_jy_jz, blocks_for(n2, 128), 128, 0, c->stream, c->ctl, c->g, lists_mid(c), c->P.vjy, c->P.vjz, c->f2[QPIC_F2_JY_NEXT],
-                         c->f2[QPIC_F2_JZ_NEXT]);
-        QPIC_TRY(check_launch(c, "k_deposit_jy_jz"));
-        QPIC_TRY(enqueue_jx_rho_chi(c));
+        QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
+        // branch A: psi_middle, then jy_next / jz_next
+        if (!fast) QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
+        QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
+        if (np > 0) {
+            QPIC_LAUNCH_FLAT(k_particles_currents_yz, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
+            QPIC_TRY(check_launch(c, "k_particles_currents_yz"));
+        }
+        if (fast) {
+            QPIC_TRY(enqueue_tile_jy_jz(c, sa));
+        } else {
+            QPIC_LAUNCH_FLAT(k_deposit_jy_jz, blocks_for(n2, 128), 128, 0, sa, c->ctl, c->g, lists_mid(c), c->P.vjy, c->P.vjz, c->f2[QPIC_F2_JY_NEXT],
+                             c->f2[QPIC_F2_JZ_NEXT]);
+            QPIC_TRY(check_launch(c, "k_deposit_jy_jz"));
+        }
+        QPIC_TRY(stream_depend(c, sb, sa));
         // By + i Bz in one complex solve
-        QPIC_LAUNCH(k_fft_rows_b_forward, ny, c->rows_threads, c->rows_smem, c->stream, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
-                    c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
-                    c->f2[QPIC_F2_JZ_NEXT], c->spec);
-        QPIC_TRY(check_launch(c, "k_fft_rows_b_forward"));
-        QPIC_LAUNCH(k_fft_cols_solve, (nz + c->cpb - 1) / c->cpb, c->cols_threads_f, c->cols_smem, c->stream, c->ctl, c->fy.plan, c->fy.tw, c->spec, nz, nz,
-                    c->cpb, c->sy, c->sz, nz, c->prm.magnetic_field_D);
-        QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
-        QPIC_LAUNCH(k_fft_rows_b_backward, ny, c->rows_threads, c->rows_smem, c->stream, c->ctl, c->fz.plan, c->fz.tw, c->g, c->spec, c->f2[QPIC_F2_BY_CUR],
-                    c->f2[QPIC_F2_BZ_CUR], c->prm.threshold_B, it);
-        QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
+        {
+            auto bfwd = c->pow2_z ? k_fft_rows_b_forward<true> : k_fft_rows_b_forward<false>;
+            auto bbwd = c->pow2_z ? k_fft_rows_b_backward<true> : k_fft_rows_b_backward<false>;
+            QPIC_LAUNCH(bfwd, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
+                        c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
+                        c->f2[QPIC_F2_JZ_NEXT], c->spec, c->rows_cplx.spb);
+            QPIC_TRY(check_launch(c, "k_fft_rows_b_forward"));
+            QPIC_TRY(enqueue_complex_columns(c, sa, c->ctl, c->prm.magnetic_field_D));
+            QPIC_LAUNCH(bbwd, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->spec,
+                        c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->prm.threshold_B, it, c->rows_cplx.spb, c->inv_scale);
+            QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
+        }
+    }
+    // rho and susceptibility(i) from the last executed iteration (see k_deposit_jx_rho_chi); reads the cell lists and
+    // fractions of (y,z), so it must finish before the push below rewrites them
+    if (M > 0) QPIC_TRY(enqueue_base_currents(c, sa, fast, false, true, true));
+    // branch B: fields of this slice + the psi_prev / jy / jz roll;  branch A: push + cell lists of the new positions
+    QPIC_TRY(stream_depend(c, sa, sb));
+    {
+        cudaStream_t keep = c->stream;
+        c->stream = sb;
+        int rc = enqueue_end_of_slice(c, 0, 1, 0);
+        c->stream = keep;
+        QPIC_TRY(rc);
     }
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, c->stream, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE], c->count);
+        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE], c->count);
         QPIC_TRY(check_launch(c, "k_particles_advance"));
     }
-    QPIC_TRY(enqueue_sort(c, c->ctl, c->P.cell_b, c->start_b, c->perm_b));
-    QPIC_TRY(enqueue_end_of_slice(c, 0, 1, 0));
-    QPIC_LAUNCH_FLAT(k_next_slice, 1, 32, 0, c->stream, c->ctl);
+    QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_b, c->start_b, c->perm_b));
+    QPIC_TRY(stream_depend(c, sb, sa));
+    QPIC_LAUNCH_FLAT(k_next_slice, 1, 32, 0, sa, c->ctl);
     QPIC_TRY(check_launch(c, "k_next_slice"));
     return QPIC_OK;
 }
@@ -345,7 +541,7 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
         QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(np, 256), 256, 0, c->stream, np, c->g, c->P.y, c->P.z, c->P.cell_b, c->P.fy_b, c->P.fz_b, c->count);
         QPIC_TRY(check_launch(c, "k_locate_count"));
     }
-    QPIC_TRY(enqueue_sort(c, c->ctl_scratch, c->P.cell_b, c->start_b, c->perm_b));
+    QPIC_TRY(enqueue_sort(c, c->stream, c->ctl_scratch, c->P.cell_b, c->start_b, c->perm_b));
     c->lists_dirty = false;
     return QPIC_OK;
 }
@@ -358,13 +554,18 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     for (double ** p : dbl) QPIC_TRY(dev_alloc(c, p, count));
     QPIC_TRY(dev_alloc(c, &P.cell_b, count));
     QPIC_TRY(dev_alloc(c, &P.cell_m, count));
+    QPIC_TRY(dev_alloc(c, &P.off_m, count));
     QPIC_TRY(dev_alloc(c, &c->perm_b, count));
     QPIC_TRY(dev_alloc(c, &c->perm_m, count));
     QPIC_TRY(dev_alloc(c, &c->tmp, count));
     return QPIC_OK;
 }
 
-int poll_stop(qpic_ctx * c) {
+// Reads the device control block (synchronises).  Handles the two asynchronous events of a sweep:
+//   stop condition  -> the sweep is over (src/System_3d.cpp:588-591);
+//   fast-path abort -> roll the slice back (By/Bz of the slice start = row i+1 of the 3-D arrays, or zero for the first
+//                      slice; nothing else the slice wrote is read before being rewritten) and schedule the general path.
+int poll_ctl(qpic_ctx * c) {
     QPIC_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->since_poll = 0;
@@ -372,19 +573,41 @@ int poll_stop(qpic_ctx * c) {
         c->stopped_at = (c->ctl_host->stop_tag - 1) / STOP_TAG_STRIDE;
         c->cur = c->stopped_at;
         c->done = true;
+        return QPIC_OK;
+    }
+    if (c->ctl_host->fast_fail != 0) {
+        const int slice = c->ctl_host->slice;
+        const size_t n2 = (size_t)c->g.n2;
+        if (slice < c->g.nx - 1) {
+            QPIC_CUDA(c, cudaMemcpyAsync(c->f2[QPIC_F2_BY_CUR], c->f3[QPIC_F3_BY] + n2 * (slice + 1), sizeof(double) * n2, cudaMemcpyDeviceToDevice, c->stream));
+            QPIC_CUDA(c, cudaMemcpyAsync(c->f2[QPIC_F2_BZ_CUR], c->f3[QPIC_F3_BZ] + n2 * (slice + 1), sizeof(double) * n2, cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            QPIC_CUDA(c, cudaMemsetAsync(c->f2[QPIC_F2_BY_CUR], 0, sizeof(double) * n2, c->stream));
+            QPIC_CUDA(c, cudaMemsetAsync(c->f2[QPIC_F2_BZ_CUR], 0, sizeof(double) * n2, c->stream));
+        }
+        c->ctl_host->fast_fail = 0;
+        QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
+        QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->cur = slice;
+        c->done = false;
+        c->general_left = c->general_penalty;
+        if (c->general_penalty < 4096) c->general_penalty *= 2;
+        c->fast_aborts++;
     }
     return QPIC_OK;
 }
 
-int build_graph(qpic_ctx * c) {
+int build_graph(qpic_ctx * c, bool fast) {
 #ifdef QPIC_EMU
     (void)c;
+    (void)fast;
     return QPIC_OK;
 #else
-    if (c->graph_exec) return QPIC_OK;
+    cudaGraphExec_t & exec = fast ? c->graph_exec_fast : c->graph_exec;
+    if (exec) return QPIC_OK;
     QPIC_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     const long before = c->launch_counter;
-    int rc = enqueue_slice_full(c);
+    int rc = enqueue_slice_full(c, fast);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     if (rc != QPIC_OK) {
@@ -392,12 +615,58 @@ int build_graph(qpic_ctx * c) {
         return rc;
     }
     if (e != cudaSuccess) return fail(c, QPIC_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-    c->launches_per_slice = c->launch_counter - before;
+    (fast ? c->launches_per_slice_fast : c->launches_per_slice) = c->launch_counter - before;
     c->launch_counter = before;
-    c->graph = graph;
-    QPIC_CUDA(c, cudaGraphInstantiate(&c->graph_exec, graph, 0));
+    (fast ? c->graph_fast : c->graph) = graph;
+    QPIC_CUDA(c, cudaGraphInstantiate(&exec, graph, 0));
     return QPIC_OK;
 #endif
+}
+
+// queues up to `count` slices starting at the host's idea of the current slice; polls the device every
+// stop_check_interval slices (a poll may move c->cur back up after a fast-path abort)
+int launch_slices(qpic_ctx * c, int count) {
+    const int M = c->prm.magnetic_field_iterations;
+    int launched = 0;
+    while (!c->done && launched < count) {
+        const bool fast = c->fast_capable && c->general_left == 0;
+        if (c->cur == 0) {
+            // slice 0: the loop body up to the `i == 0` break (src/System_3d.cpp:334-411)
+            QPIC_TRY(enqueue_slice_head(c, fast, false, true));
+            c->done = true;
+            launched++;
+            break;
+        }
+#ifndef QPIC_EMU
+        if (c->prm.use_graph) {
+            QPIC_TRY(build_graph(c, fast));
+            QPIC_CUDA(c, cudaGraphLaunch(fast ? c->graph_exec_fast : c->graph_exec, c->stream));
+            c->launch_counter += fast ? c->launches_per_slice_fast : c->launches_per_slice;
+        } else
+#endif
+        {
+            QPIC_TRY(enqueue_slice_full(c, fast));
+        }
+        if (!fast && c->general_left > 0) c->general_left--;
+        c->cur--;
+        launched++;
+        if (M > 0 && ++c->since_poll >= c->prm.stop_check_interval) QPIC_TRY(poll_ctl(c));
+    }
+    return QPIC_OK;
+}
+
+// brings the device to the position the caller has asked for (c->target), resolving pending fast-path aborts
+int resolve(qpic_ctx * c) {
+    const int M = c->prm.magnetic_field_iterations;
+    for (int guard = 0; guard < 1 << 20; guard++) {
+        if (M > 0) QPIC_TRY(poll_ctl(c));
+        else QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->stopped_at >= 0) return QPIC_OK;
+        const bool head_pending = (c->target < 0) && !c->done;  // target -1: slice 0 processed as well
+        if (c->cur <= (c->target < 0 ? 0 : c->target) && !head_pending) return QPIC_OK;
+        QPIC_TRY(launch_slices(c, c->cur - (c->target < 0 ? -1 : c->target)));
+    }
+    return fail(c, QPIC_ERR_STATE, "resolve did not converge");
 }
 
 }  // namespace
@@ -429,11 +698,15 @@ void qpic_destroy(qpic_ctx * c) {
 #ifndef QPIC_EMU
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
+    if (c->graph_exec_fast) cudaGraphExecDestroy(c->graph_exec_fast);
+    if (c->graph_fast) cudaGraphDestroy(c->graph_fast);
 #endif
     for (void * p : c->allocations) cudaFree(p);
     if (c->ctl_host) cudaFreeHost(c->ctl_host);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -447,6 +720,12 @@ static int create_impl(qpic_ctx * c) {
     if (p.device < 0 || p.device >= ndev) return fail(c, QPIC_ERR_INVALID, "device %d out of range (%d devices)", p.device, ndev);
     QPIC_CUDA(c, cudaSetDevice(p.device));
     QPIC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    QPIC_CUDA(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (int e = 0; e < 64; e++) {
+        cudaEvent_t ev;
+        QPIC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->ev_pool.push_back(ev);
+    }
     QPIC_CUDA(c, cudaEventCreate(&c->ev0));
     QPIC_CUDA(c, cudaEventCreate(&c->ev1));
 
@@ -467,23 +746,47 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(make_symbol_tables(c));
 
     // launch geometry of the transforms
-    c->rows_smem = sizeof(double2) * 2 * (size_t)g.nz;
-    if (c->rows_smem > SMEM_OPTIN_LIMIT) return fail(c, QPIC_ERR_UNSUPPORTED, "nz = %d does not fit the shared-memory row transform", g.nz);
-    c->cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;
-    c->cols_smem = sizeof(double2) * 2 * (size_t)c->cpb * g.ny;
-    if (c->cols_smem > SMEM_OPTIN_LIMIT) return fail(c, QPIC_ERR_UNSUPPORTED, "ny = %d does not fit the shared-memory column transform", g.ny);
-    c->rows_threads = pick_threads(g.nz / 4);
-    c->cols_threads_h = pick_threads(c->cpb * g.ny / 4);
-    c->cols_threads_f = c->cols_threads_h;
-    if (c->rows_smem > SMEM_DEFAULT_LIMIT) {
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->rows_smem));
+    {
+        const long long prod = (long long)g.ny * g.nz;
+        c->inv_scale = ((prod & (prod - 1)) == 0) ? 1.0 / (double)prod : 0.0;
     }
-    if (c->cols_smem > SMEM_DEFAULT_LIMIT) {
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cols_smem));
+    c->pow2_y = c->fy.plan.log2n > 0;
+    c->pow2_z = c->fz.plan.log2n > 0;
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, (g.ny + 1) / 2, &c->rows_real, "row transform"));
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, g.ny, &c->rows_cplx, "row transform"));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, g.nz / 2 + 1, &c->cols_half, "column transform"));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, g.nz, &c->cols_full, "column transform"));
+    if (!c->pow2_y) {
+        // generic engine: two adjacent columns per block when they fit, so that global accesses are 32-byte sectors
+        const int cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;
+        for (qpic_ctx::FftLaunch * L : {&c->cols_half, &c->cols_full}) {
+            const int ncols = (L == &c->cols_half) ? g.nz / 2 + 1 : g.nz;
+            L->spb = cpb;
+            L->threads = pick_threads(cpb * g.ny / 4);
+            L->smem = sizeof(double2) * 2 * (size_t)cpb * g.ny;
+            L->blocks = (ncols + cpb - 1) / cpb;
+        }
+    }
+    {
+        size_t rows_max = c->rows_real.smem > c->rows_cplx.smem ? c->rows_real.smem : c->rows_cplx.smem;
+        size_t cols_max = c->cols_half.smem > c->cols_full.smem ? c->cols_half.smem : c->cols_full.smem;
+        if (rows_max > SMEM_DEFAULT_LIMIT) {
+            const int b = (int)rows_max;
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_r2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_r2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2r<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2r<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+        }
+        if (cols_max > SMEM_DEFAULT_LIMIT) {
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+        }
     }
 
     QPIC_TRY(dev_alloc(c, &c->ctl, 1));
@@ -509,6 +812,9 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(alloc_particles(c, 0));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cur = g.nx - 1;
+    c->target = g.nx - 1;
+    // the tile deposit needs unambiguous minimal-image cell offsets
+    c->fast_capable = !p.force_general_deposit && g.ny >= 8 && g.nz >= 8;
     return QPIC_OK;
 }
 
@@ -568,7 +874,7 @@ int qpic_upload_bunch_sources(qpic_ctx * c, const double * rho_bunch, const doub
     const size_t n3 = (size_t)c->g.nx * c->g.n2;
     const double * src[2] = {rho_bunch, jx_bunch};
     const int idx[2] = {QPIC_F3_RHO_BUNCH, QPIC_F3_JX_BUNCH};
-    if (c->graph_exec && (!c->f3[idx[0]] || !c->f3[idx[1]]) && (rho_bunch || jx_bunch)) {
+    if ((c->graph_exec || c->graph_exec_fast) && (!c->f3[idx[0]] || !c->f3[idx[1]]) && (rho_bunch || jx_bunch)) {
         return fail(c, QPIC_ERR_STATE, "bunch sources must be uploaded before the first qpic_step of a context");
     }
     for (int t = 0; t < 2; t++) {
@@ -588,7 +894,7 @@ int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, c
     if (count > 0 && (!y || !z || !n)) return fail(c, QPIC_ERR_INVALID, "particle arrays are NULL");
     if (count > (size_t)std::numeric_limits<int>::max() - 1024) return fail(c, QPIC_ERR_INVALID, "too many particles for 32-bit particle indices");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
-    if (c->graph_exec && (int)count != c->P.np) {
+    if ((c->graph_exec || c->graph_exec_fast) && (int)count != c->P.np) {
         return fail(c, QPIC_ERR_STATE, "the particle count cannot change after the first qpic_step of a context");
     }
     if ((int)count != c->P.np || !c->P.y) {
@@ -624,7 +930,8 @@ int qpic_begin(qpic_ctx * c) {
     Ctl init;
     init.slice = g.nx - 1;
     init.stop_tag = 0;
-    init.pad0 = init.pad1 = 0;
+    init.fast_fail = 0;
+    init.pad1 = 0;
     *c->ctl_host = init;
     QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -634,52 +941,37 @@ int qpic_begin(qpic_ctx * c) {
                      (const double *)nullptr, (const double *)nullptr, 0, c->f2[QPIC_F2_RHO_ION]);
     QPIC_TRY(check_launch(c, "k_deposit_charge"));
     c->cur = g.nx - 1;
+    c->target = g.nx - 1;
     c->stopped_at = -1;
     c->done = false;
     c->finished = false;
     c->began = true;
     c->since_poll = 0;
+    c->general_left = 0;
+    c->general_penalty = 16;
     return QPIC_OK;
 }
 
 int qpic_step(qpic_ctx * c, int max_slices, int * done) {
     if (!c) return QPIC_ERR_INVALID;
     if (!c->began) return fail(c, QPIC_ERR_STATE, "qpic_step called before qpic_begin");
+    if (max_slices < 0) return fail(c, QPIC_ERR_INVALID, "max_slices must be non-negative");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     if (c->lists_dirty) QPIC_TRY(enqueue_rebuild_base_lists(c));
     const long launches_before = c->launch_counter;
-    long graph_launches = 0;
     QPIC_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-    int processed = 0;
-    while (!c->done && processed < max_slices) {
-        if (c->cur == 0) {
-            // slice 0: the loop body up to the `i == 0` break (src/System_3d.cpp:334-411)
-            QPIC_TRY(enqueue_slice_head(c, false));
-            c->done = true;
-            processed++;
-            break;
-        }
-#ifndef QPIC_EMU
-        if (c->prm.use_graph) {
-            QPIC_TRY(build_graph(c));
-            QPIC_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
-            graph_launches++;
-        } else
-#endif
-        {
-            QPIC_TRY(enqueue_slice_full(c));
-        }
-        c->cur--;
-        processed++;
-        if (c->prm.magnetic_field_iterations > 0 && ++c->since_poll >= c->prm.stop_check_interval) QPIC_TRY(poll_stop(c));
-    }
-    QPIC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    c->last_launches = (c->launch_counter - launches_before) + graph_launches * c->launches_per_slice;
+    // the position the caller wants to reach: `target` counts down from nx-1; -1 means slice 0 has been processed too
+    long want = (long)c->target - max_slices;
+    if (want < -1) want = -1;
+    c->target = (int)want;
+    if (!c->done) QPIC_TRY(launch_slices(c, c->cur - c->target));
     if (done) {
-        // the caller wants a definite answer: make sure a stop raised by the slices queued above is seen
-        if (!c->done && c->prm.magnetic_field_iterations > 0 && c->since_poll > 0) QPIC_TRY(poll_stop(c));
+        // the caller wants a definite answer: wait, and redo whatever a fast-path abort cancelled
+        QPIC_TRY(resolve(c));
         *done = c->done ? 1 : 0;
     }
+    QPIC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->last_launches = c->launch_counter - launches_before;
     return QPIC_OK;
 }
 
@@ -687,7 +979,7 @@ int qpic_finish(qpic_ctx * c) {
     if (!c) return QPIC_ERR_INVALID;
     if (!c->began) return fail(c, QPIC_ERR_STATE, "qpic_finish called before qpic_begin");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
-    if (c->prm.magnetic_field_iterations > 0) QPIC_TRY(poll_stop(c));
+    QPIC_TRY(resolve(c));
     const size_t n2 = (size_t)c->g.n2;
     if (c->stopped_at >= 0) {
         // the reference wrote by(i), bz(i) of the stopping slice in place (src/System_3d.cpp:544, :572) and then broke out
@@ -713,6 +1005,7 @@ int qpic_solve_wakefield(qpic_ctx * c) {
 int qpic_synchronize(qpic_ctx * c) {
     if (!c) return QPIC_ERR_INVALID;
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (c->began && !c->finished) return resolve(c);
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     return QPIC_OK;
 }
@@ -721,9 +1014,11 @@ int qpic_current_slice(qpic_ctx * c) { return c ? c->cur : -1; }
 
 int qpic_stopped_at(qpic_ctx * c) {
     if (!c) return -1;
-    if (c->began && !c->finished && c->prm.magnetic_field_iterations > 0) poll_stop(c);
+    if (c->began && !c->finished) resolve(c);
     return c->stopped_at;
 }
+
+long qpic_fast_path_aborts(const qpic_ctx * c) { return c ? c->fast_aborts : 0; }
 
 int qpic_last_step_stats(qpic_ctx * c, float * ms, long * kernel_launches) {
     if (!c) return QPIC_ERR_INVALID;
@@ -741,6 +1036,7 @@ static int copy_out(qpic_ctx * c, const double * src, double * dst, size_t count
     if (!dst) return fail(c, QPIC_ERR_INVALID, "dst is NULL");
     if (!src) return fail(c, QPIC_ERR_STATE, "this array is not resident (see keep_slices_3d / qpic_upload_bunch_sources)");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (c->began && !c->finished) QPIC_TRY(resolve(c));
     QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     return QPIC_OK;
@@ -825,9 +1121,11 @@ int qpic_set_current_slice(qpic_ctx * c, int slice) {
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->ctl_host->slice = slice;
     c->ctl_host->stop_tag = 0;
+    c->ctl_host->fast_fail = 0;
     QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cur = slice;
+    c->target = slice;
     c->done = false;
     c->finished = false;
     c->stopped_at = -1;
@@ -841,7 +1139,7 @@ int qpic_solve_poisson_host(qpic_ctx * c, double * inout, double D) {
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
-    QPIC_TRY(enqueue_real_solve(c, c->ctl_scratch, D));
+    QPIC_TRY(enqueue_real_solve(c, c->stream, c->ctl_scratch, D));
     QPIC_CUDA(c, cudaMemcpyAsync(inout, c->raw, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     return QPIC_OK;
@@ -854,13 +1152,14 @@ int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inou
     const int ny = c->g.ny, nz = c->g.nz;
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout_a, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in2, inout_b, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
-    QPIC_LAUNCH(k_fft_rows_c2c, ny, c->rows_threads, c->rows_smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, nz);
+    auto c2c = c->pow2_z ? k_fft_rows_c2c<true> : k_fft_rows_c2c<false>;
+    auto bbwd = c->pow2_z ? k_fft_rows_b_backward<true> : k_fft_rows_b_backward<false>;
+    QPIC_LAUNCH(c2c, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny,
+                nz, c->rows_cplx.spb);
     QPIC_TRY(check_launch(c, "k_fft_rows_c2c"));
-    QPIC_LAUNCH(k_fft_cols_solve, (nz + c->cpb - 1) / c->cpb, c->cols_threads_f, c->cols_smem, c->stream, c->ctl_scratch, c->fy.plan, c->fy.tw, c->spec, nz,
-                nz, c->cpb, c->sy, c->sz, nz, D);
-    QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
-    QPIC_LAUNCH(k_fft_rows_b_backward, ny, c->rows_threads, c->rows_smem, c->stream, c->ctl_scratch, c->fz.plan, c->fz.tw, c->g, c->spec, c->fft_in,
-                c->fft_in2, std::numeric_limits<double>::infinity(), 0);
+    QPIC_TRY(enqueue_complex_columns(c, c->stream, c->ctl_scratch, D));
+    QPIC_LAUNCH(bbwd, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, c->stream, c->ctl_scratch, c->fz.plan, c->fz.tw, c->g, c->spec,
+                c->fft_in, c->fft_in2, std::numeric_limits<double>::infinity(), 0, c->rows_cplx.spb, c->inv_scale);
     QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
     QPIC_CUDA(c, cudaMemcpyAsync(inout_a, c->fft_in, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaMemcpyAsync(inout_b, c->fft_in2, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
@@ -920,8 +1219,9 @@ int qpic_profile_slices(qpic_ctx * c, int nslices, char * report, size_t report_
     c->prof_events.push_back(first);
     int rc = QPIC_OK;
     for (int sidx = 0; sidx < nslices && c->cur > 0 && rc == QPIC_OK; sidx++) {
-        rc = enqueue_slice_full(c);
+        rc = enqueue_slice_full(c, c->fast_capable && c->general_left == 0);
         c->cur--;
+        c->target = c->cur;
     }
     c->profiling = false;
     if (rc != QPIC_OK) return rc;
@@ -953,7 +1253,7 @@ int qpic_profile_slices(qpic_ctx * c, int nslices, char * report, size_t report_
         if (w < 0 || (size_t)w >= report_len - used) break;
         used += (size_t)w;
     }
-    QPIC_TRY(poll_stop(c));
+    QPIC_TRY(resolve(c));
     return QPIC_OK;
 }
 

@@ -17,10 +17,15 @@
 namespace qpic {
 
 struct Ctl {
-    int slice;     // xi-slice being solved (nx-1 ... 0)
-    int stop_tag;  // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
-    int pad0, pad1;
+    int slice;      // xi-slice being solved (nx-1 ... 0)
+    int stop_tag;   // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
+    int fast_fail;  // != 0: a half-step displacement left the +-1 cell window of the sort-free deposit; the fast-path
+                    // kernels of this and later slices are no-ops until the host redoes the slice on the general path
+    int pad1;
 };
+
+// every kernel of the xi-loop starts with this test (the B backward rows have their own, see qpic_fft.cuh)
+__device__ __forceinline__ bool cancelled(const Ctl * ctl) { return (ctl->stop_tag | ctl->fast_fail) != 0; }
 constexpr int STOP_TAG_STRIDE = 1024;
 
 struct Geom {
@@ -175,7 +180,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int & total) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunk_sums(const Ctl * ctl, const int * __restrict__ count, int n, int * __restrict__ sums) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int v = 0;
 #pragma unroll
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunk_sums(const Ctl * ct
 
 // single block: exclusive scan of the chunk sums in place
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int * __restrict__ sums, int nchunks) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     int carry = 0;
     for (int base = 0; base < nchunks; base += SCAN_THREADS) {
         const int idx = base + threadIdx.x;
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int
 
 __global__ void __launch_bounds__(SCAN_THREADS)
     k_scan_apply(const Ctl * ctl, int * __restrict__ count, int n, const int * __restrict__ sums, int * __restrict__ start, int * __restrict__ cursor) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int c[SCAN_ITEMS];
     int v = 0;
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 
 // bucket fill: slot order inside a cell is whatever order the integer atomics resolve in ...
 __global__ void k_sort_fill(const Ctl * ctl, int np, const int * __restrict__ cell, int * __restrict__ cursor, int * __restrict__ tmp) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     const int slot = atomicAdd(&cursor[cell[p]], 1);
@@ -240,7 +245,7 @@ __global__ void k_sort_fill(const Ctl * ctl, int np, const int * __restrict__ ce
 // Buckets hold ~ppc entries (a few; tens at strong compression), so the O(k) scan per entry stays in L1.
 __global__ void k_sort_rank(const Ctl * ctl, int np, const int * __restrict__ cell, const int * __restrict__ start, const int * __restrict__ tmp,
                             int * __restrict__ perm) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= np) return;
     const int p = tmp[s];
@@ -268,7 +273,7 @@ struct CellLists {
 __global__ void k_deposit_charge(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ nw, const double * __restrict__ rho_ion,
                                  const double * __restrict__ jxb3, const double * __restrict__ rhob3, int with_background,
                                  double * __restrict__ out) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
     const int j = t / g.nz, k = t - j * g.nz;
@@ -298,17 +303,25 @@ __global__ void k_deposit_charge(const Ctl * ctl, Geom g, CellLists L, const dou
     out[t] = acc;
 }
 
-// jx, rho, susceptibility(i) from per-particle values at (y,z) (src/System_3d.cpp:381-397 and :511-527)
+// jx, rho, susceptibility(i) from per-particle values at (y,z) (src/System_3d.cpp:381-397 and :511-527).  Inside the B
+// iterations only jx feeds a solve (:533, :558); rho and susceptibility(i) are overwritten by every later iteration, so
+// they are deposited once, from the last executed iteration's values (WITH_RHO_CHI), which is what the reference ends
+// up with.  `final_pass`: also runs in the slice where the stop condition tripped (values of the stopping iteration).
+template <bool WITH_JX, bool WITH_RHO_CHI>
 __global__ void k_deposit_jx_rho_chi(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ vjx, const double * __restrict__ vrho,
                                      const double * __restrict__ vchi, const double * __restrict__ jxb3, const double * __restrict__ rhob3,
-                                     double * __restrict__ jx, double * __restrict__ rho, double * __restrict__ chi3) {
-    if (ctl->stop_tag) return;
+                                     double * __restrict__ jx, double * __restrict__ rho, double * __restrict__ chi3, int final_pass) {
+    if (final_pass) {
+        if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
+    } else if (cancelled(ctl)) {
+        return;
+    }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
     const int j = t / g.nz, k = t - j * g.nz;
     const size_t off = (size_t)ctl->slice * g.n2 + t;
-    double ajx = jxb3 ? jxb3[off] : 0.0;
-    double arho = rhob3 ? rhob3[off] : 0.0;
+    double ajx = (WITH_JX && jxb3) ? jxb3[off] : 0.0;
+    double arho = (WITH_RHO_CHI && rhob3) ? rhob3[off] : 0.0;
     double achi = 0.0;
     const int jm = wrap_dec(j, g.ny), km = wrap_dec(k, g.nz);
 #pragma unroll
@@ -322,15 +335,19 @@ __global__ void k_deposit_jx_rho_chi(const Ctl * ctl, Geom g, CellLists L, const
                 const double f1 = L.fy[p], f2 = L.fz[p];
                 const double wy = oy ? f1 : 1 - f1;
                 const double wz = oz ? f2 : 1 - f2;
-                ajx += vjx[p] * wy * wz;
-                arho += vrho[p] * wy * wz;
-                achi += vchi[p] * wy * wz;
+                if (WITH_JX) ajx += vjx[p] * wy * wz;
+                if (WITH_RHO_CHI) {
+                    arho += vrho[p] * wy * wz;
+                    achi += vchi[p] * wy * wz;
+                }
             }
         }
     }
-    jx[t] = ajx;
-    rho[t] = arho;
-    chi3[off] = achi;
+    if (WITH_JX) jx[t] = ajx;
+    if (WITH_RHO_CHI) {
+        rho[t] = arho;
+        chi3[off] = achi;
+    }
 }
 
 // Weight of a particle with unstaggered fraction f, sitting `role` cells (-1, 0, +1) away from the node's own index,
@@ -358,7 +375,7 @@ __device__ __forceinline__ bool node_weight(int role, double f, double & w) {
 // staggering :190-193)
 __global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ vjy, const double * __restrict__ vjz,
                                 double * __restrict__ jy_next, double * __restrict__ jz_next) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
     const int j = t / g.nz, k = t - j * g.nz;
@@ -400,7 +417,7 @@ __global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const doub
 constexpr int FIX_THREADS = 256;
 
 __global__ void __launch_bounds__(FIX_THREADS) k_potential_fixup(const Ctl * ctl, Geom g, const double * __restrict__ raw, double * __restrict__ dst, double floor_value) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     __shared__ double red[FIX_THREADS];
     double part = 0.0;
     const int nb = g.ny + g.nz - 1;
@@ -429,6 +446,7 @@ struct Particles {
     double *gamma, *px;                  // src/containers.h:41-42
     double *pyn, *pzn;                   // py_next, pz_next
     int *cell_b, *cell_m;                // cell of (y,z) / of (y_middle,z_middle)
+    int *off_m;                          // (jm - jc + 2) | (km - kc + 2) << 3, minimal-image cell offsets of the half step
     double *fy_b, *fz_b, *fy_m, *fz_m;   // fractional positions inside that cell
     // slice invariants of the B iterations (the reference re-gathers them every iteration, src/System_3d.cpp:419-423,
     // :501-502; (y,z), psi and a_sqr(i) do not change inside the iteration loop)
@@ -449,7 +467,7 @@ __device__ __forceinline__ void store_currents(const Particles & P, int p, doubl
 // initial gamma, px (src/System_3d.cpp:368-378) + the values deposited at :390-397 + iteration invariants
 __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ a_sqr3, const double * __restrict__ psi,
                                   int want_invariants) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.np) return;
     const double * a_sqr = a_sqr3 + (size_t)ctl->slice * g.n2;
@@ -475,10 +493,21 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const do
     }
 }
 
-// predictor: py_next, pz_next (src/System_3d.cpp:416-433), half-step position (:436-443) and its cell descriptor
-__global__ void k_particles_predict(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
+// minimal-image cell offset jm - jc folded into [-n/2, n/2]
+__device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
+    int o = jm - jc;
+    if (2 * o > n) o -= n;
+    if (2 * o < -n) o += n;
+    return o;
+}
+
+// predictor: py_next, pz_next (src/System_3d.cpp:416-433), half-step position (:436-443) and its cell descriptor.
+// FAST (sort-free deposit): records the cell offset of the half step instead of counting cell populations, and raises
+// Ctl::fast_fail if a particle leaves the +-1 cell window the tile deposit covers.
+template <bool FAST>
+__global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
                                     int * __restrict__ count) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.np) return;
     const int c = P.cell_b[p];
@@ -510,20 +539,27 @@ __global__ void k_particles_predict(const Ctl * ctl, Geom g, Particles P, const 
     P.cell_m[p] = cm;
     P.fy_m[p] = f1;
     P.fz_m[p] = f2;
-    atomicAdd(&count[cm], 1);
+    if (FAST) {
+        const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
+        // !(x <= 1) also catches the NaN positions of a blown-up run
+        if (oy < -1 || oy > 1 || oz < -1 || oz > 1 || !(f1 >= 0.0) || !(f2 >= 0.0)) {
+            atomicExch(&ctl->fast_fail, 1);
+            P.off_m[p] = 2 | (2 << 3);
+        } else {
+            P.off_m[p] = (oy + 2) | ((oz + 2) << 3);
+        }
+    } else {
+        atomicAdd(&count[cm], 1);
+    }
 }
 
-// values for the jy/jz deposit (src/System_3d.cpp:480-486) and the corrector gamma, px (:498-508) + :520-527 values
-__global__ void k_particles_correct(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle) {
-    if (ctl->stop_tag) return;
+// corrector gamma, px (src/System_3d.cpp:498-508) and the values deposited at :520-527.  Needs only py_next, pz_next, so it
+// runs concurrently with the psi_middle solve.
+__global__ void k_particles_correct_gamma(const Ctl * ctl, Geom g, Particles P) {
+    if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.np) return;
-    const int cm = P.cell_m[p];
-    const int jm = cm / g.nz, km = cm - jm * g.nz;
-    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[p], P.fz_m[p]);
     const double nw = P.nw[p], pyn = P.pyn[p], pzn = P.pzn[p], py = P.py[p], pz = P.pz[p];
-    P.vjy[p] = nw * pyn / (1 + psi_particle);
-    P.vjz[p] = nw * pzn / (1 + psi_particle);
     const double q = P.q[p], a_particle = P.ap[p];
     const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
     const double gamma = 0.5 * (1 + p_squared + a_particle + q * q) / q;
@@ -533,10 +569,23 @@ __global__ void k_particles_correct(const Ctl * ctl, Geom g, Particles P, const 
     store_currents(P, p, nw, gamma, px);
 }
 
+// values for the jy/jz deposit: n py_next / (1 + psi_middle@(y_middle, z_middle))  (src/System_3d.cpp:480-486)
+__global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle) {
+    if (cancelled(ctl)) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.np) return;
+    const int cm = P.cell_m[p];
+    const int jm = cm / g.nz, km = cm - jm * g.nz;
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[p], P.fz_m[p]);
+    const double nw = P.nw[p];
+    P.vjy[p] = nw * P.pyn[p] / (1 + psi_particle);
+    P.vjz[p] = nw * P.pzn[p] / (1 + psi_particle);
+}
+
 // py <- py_next, pz <- pz_next (src/System_3d.cpp:593-598), coordinate advance with psi_middle gathered at (y,z)
 // (:601-608), new cell descriptor + population count for the next slice's lists
 __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle, int * __restrict__ count) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.np) return;
     const int c = P.cell_b[p];
@@ -573,7 +622,7 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
                                const double * __restrict__ by, const double * __restrict__ bz, const double * __restrict__ rho,
                                const double * __restrict__ jx, double * __restrict__ jy, double * __restrict__ jz,
                                const double * __restrict__ jy_next, const double * __restrict__ jz_next, int b_is_zero, int roll, int ignore_stop) {
-    if (ctl->stop_tag && !ignore_stop) return;
+    if (cancelled(ctl) && !ignore_stop) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
     const int i = ignore_stop ? 0 : ctl->slice;
@@ -604,8 +653,165 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
 }
 
 __global__ void k_next_slice(Ctl * ctl) {
-    if (ctl->stop_tag) return;
+    if (cancelled(ctl)) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) ctl->slice -= 1;
+}
+
+// ------------------------------------------------------------------------------------------------ sort-free tile deposit
+// Deterministic deposition without sorting the half-step positions.  A block owns a TILE x TILE patch of grid nodes;
+// ONE THREAD PER SOURCE CELL of the patch plus a halo walks that cell's particles (the cell lists of the slice-start
+// positions, built once per slice).  A particle's target cell on the output grid is  source cell + offset, with the
+// offset in a small window (0 for deposits at (y,z); [-1,1] for the half-step position, one more on the low side for the
+// half-cell staggered jy/jz grids).  Contributions are first reduced per TARGET CELL into four "corner sums"
+// (the four nodes a CIC particle of that cell touches, src/array_utils.cpp:75-82) kept in shared memory.  The reduction
+// runs in PHASES, one per offset: within a phase the map source cell -> target cell is a bijection, so every target cell
+// has exactly one owner thread, which adds its particles in list order with plain (non-atomic) adds; phases follow each
+// other in a fixed order with a barrier in between.  Finally each node sums the corner sums of its four neighbouring
+// target cells, again in a fixed order.  No floating-point atomics, no dependence on scheduling: bit-reproducible.
+// Halo cells are processed redundantly by neighbouring blocks (identical arithmetic, identical bits).
+constexpr int TILE = 16;
+constexpr int TILE_MAX_OUT = 3;
+
+struct TileOutput {
+    const double * val;    // per-particle value
+    double sign;           // +1 / -1 (charge deposits use -n)
+    int at_mid;            // 1: deposit at the half-step position (fy_m, fz_m, off_m), 0: at (y,z) (fy_b, fz_b)
+    int stag_y, stag_z;    // output grid origin shifted by +dy/2 / +dz/2 (jy_next / jz_next, src/System_3d.cpp:190-193)
+    int bg_mode;           // 0: none, 1: jx_bunch(i) - rho_bunch(i) - rho_ion (psi source, :345), 2: bg3(i)
+    const double * bg3;    // bg_mode 2: a 3-D array whose slice i initialises the sum (rho_bunch / jx_bunch, :384-385)
+    double * out;          // 2-D array, or a 3-D array when out_3d
+    int out_3d;
+};
+
+struct TileJob {
+    int nout;
+    TileOutput o[TILE_MAX_OUT];
+    const double *jxb3, *rhob3, *rho_ion;  // for bg_mode 1
+};
+
+__device__ __forceinline__ int mod_wrap(int j, int n) {
+    j %= n;
+    return j < 0 ? j + n : j;
+}
+
+// HL / HH: halo of source cells below / above the patch.  Launch with blockDim = (TILE+HL+HH, TILE+HL+HH).
+template <int HL, int HH, bool FINAL_PASS>
+__global__ void __launch_bounds__((TILE + HL + HH) * (TILE + HL + HH))
+    k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, const int * __restrict__ perm, Particles P, TileJob job) {
+    if (FINAL_PASS) {
+        if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
+    } else if (cancelled(ctl)) {
+        return;
+    }
+    constexpr int ACC = TILE + 1;
+    __shared__ double acc[TILE_MAX_OUT * ACC * ACC * 4];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    for (int t = tid; t < job.nout * ACC * ACC * 4; t += nthreads) acc[t] = 0.0;
+
+    const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
+    const int jb = mod_wrap(j0 - HL + (int)threadIdx.y, g.ny);
+    const int kb = mod_wrap(k0 - HL + (int)threadIdx.x, g.nz);
+    const int cell = jb * g.nz + kb;
+    const int s0 = start[cell], s1 = start[cell + 1];
+    __syncthreads();
+
+    for (int a = 0; a < job.nout; a++) {
+        const TileOutput & o = job.o[a];
+        const double * __restrict__ val = o.val;
+        const double * __restrict__ fyv = o.at_mid ? P.fy_m : P.fy_b;
+        const double * __restrict__ fzv = o.at_mid ? P.fz_m : P.fz_b;
+        const int wlo_y = (o.at_mid ? -1 : 0) - o.stag_y, whi_y = o.at_mid ? 1 : 0;
+        const int wlo_z = (o.at_mid ? -1 : 0) - o.stag_z, whi_z = o.at_mid ? 1 : 0;
+        // which offsets occur among this cell's particles (bit = (oy+2)*4 + (oz+2))
+        unsigned mask = 0;
+        for (int s = s0; s < s1; s++) {
+            const int p = perm[s];
+            int oy = 0, oz = 0;
+            if (o.at_mid) {
+                const int code = P.off_m[p];
+                oy = (code & 7) - 2;
+                oz = ((code >> 3) & 7) - 2;
+            }
+            if (o.stag_y && fyv[p] < 0.5) oy -= 1;
+            if (o.stag_z && fzv[p] < 0.5) oz -= 1;
+            mask |= 1u << ((oy + 2) * 4 + (oz + 2));
+        }
+        double * acc_a = acc + a * ACC * ACC * 4;
+        for (int oy = wlo_y; oy <= whi_y; oy++) {
+            for (int oz = wlo_z; oz <= whi_z; oz++) {
+                const int ay = (int)threadIdx.y - HL + 1 + oy, az = (int)threadIdx.x - HL + 1 + oz;
+                if (((mask >> ((oy + 2) * 4 + (oz + 2))) & 1u) && ay >= 0 && ay < ACC && az >= 0 && az < ACC) {
+                    double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
+                    for (int s = s0; s < s1; s++) {
+                        const int p = perm[s];
+                        int py_ = 0, pz_ = 0;
+                        if (o.at_mid) {
+                            const int code = P.off_m[p];
+                            py_ = (code & 7) - 2;
+                            pz_ = ((code >> 3) & 7) - 2;
+                        }
+                        double ty = fyv[p], tz = fzv[p];
+                        if (o.stag_y) {
+                            if (ty < 0.5) {
+                                py_ -= 1;
+                                ty += 0.5;
+                            } else {
+                                ty -= 0.5;
+                            }
+                        }
+                        if (o.stag_z) {
+                            if (tz < 0.5) {
+                                pz_ -= 1;
+                                tz += 0.5;
+                            } else {
+                                tz -= 0.5;
+                            }
+                        }
+                        if (py_ != oy || pz_ != oz) continue;
+                        const double v = o.sign * val[p];
+                        c00 += v * (1 - ty) * (1 - tz);
+                        c10 += v * ty * (1 - tz);
+                        c01 += v * (1 - ty) * tz;
+                        c11 += v * ty * tz;
+                    }
+                    double * t4 = acc_a + (ay * ACC + az) * 4;
+                    t4[0] += c00;
+                    t4[1] += c10;
+                    t4[2] += c01;
+                    t4[3] += c11;
+                }
+                __syncthreads();
+            }
+        }
+    }
+
+    // nodes of the patch: own cell's (1-fy)(1-fz) sum, then the y-, z- and diagonal neighbours' sums, fixed order
+    if ((int)threadIdx.y < TILE && (int)threadIdx.x < TILE) {
+        const int j = j0 + threadIdx.y, k = k0 + threadIdx.x;
+        if (j < g.ny && k < g.nz) {
+            const int t = j * g.nz + k;
+            const size_t off3 = (size_t)ctl->slice * g.n2 + t;
+            for (int a = 0; a < job.nout; a++) {
+                const TileOutput & o = job.o[a];
+                double v = 0.0;
+                if (o.bg_mode == 1) {
+                    const double jb_ = job.jxb3 ? job.jxb3[off3] : 0.0;
+                    const double rb_ = job.rhob3 ? job.rhob3[off3] : 0.0;
+                    v = jb_ - rb_ - job.rho_ion[t];
+                } else if (o.bg_mode == 2 && o.bg3) {
+                    v = o.bg3[off3];
+                }
+                const double * acc_a = acc + a * ACC * ACC * 4;
+                const int ay = threadIdx.y + 1, az = threadIdx.x + 1;
+                v += acc_a[(ay * ACC + az) * 4 + 0];
+                v += acc_a[((ay - 1) * ACC + az) * 4 + 1];
+                v += acc_a[(ay * ACC + az - 1) * 4 + 2];
+                v += acc_a[((ay - 1) * ACC + az - 1) * 4 + 3];
+                o.out[o.out_3d ? off3 : (size_t)t] = v;
+            }
+        }
+    }
 }
 
 }  // namespace qpic

@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "qpic_upload_field2d", "qpic_particle_count", "qpic_download_particles", "qpic_upload_particles",
     "qpic_set_current_slice", "qpic_solve_poisson_host", "qpic_solve_helmholtz_pair_host", "qpic_last_step_stats",
     "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
+    "qpic_fast_path_aborts",
 ]
 
 
@@ -53,6 +54,7 @@ class QpicParams(ctypes.Structure):
         ("keep_slices_3d", ctypes.c_int),
         ("use_graph", ctypes.c_int),
         ("stop_check_interval", ctypes.c_int),
+        ("force_general_deposit", ctypes.c_int),
     ]
 
 
@@ -103,6 +105,8 @@ class QpicLibrary:
         L.qpic_alloc_pinned.restype = vp
         L.qpic_free_pinned.argtypes = [vp]
         L.qpic_free_pinned.restype = None
+        L.qpic_fast_path_aborts.argtypes = [vp]
+        L.qpic_fast_path_aborts.restype = ctypes.c_long
         self.L = L
 
     def pinned_array(self, shape):
@@ -172,7 +176,8 @@ class WakefieldSolver:
     """Device-resident quasistatic wakefield solver: the state System_3d::solve_wakefield works on."""
 
     def __init__(self, nx, ny, nz, lx, ly, lz, magnetic_field_iterations, psi_threshold=1e-4, magnetic_field_D=10.0,
-                 threshold_B=100.0, device=0, keep_slices_3d=False, use_graph=True, stop_check_interval=64, library=None):
+                 threshold_B=100.0, device=0, keep_slices_3d=False, use_graph=True, stop_check_interval=64, force_general_deposit=False,
+                 library=None):
         self.lib = library if library is not None else load_library()
         L = self.lib.L
         p = QpicParams()
@@ -185,6 +190,7 @@ class WakefieldSolver:
         p.keep_slices_3d = int(bool(keep_slices_3d))
         p.use_graph = int(bool(use_graph))
         p.stop_check_interval = int(stop_check_interval)
+        p.force_general_deposit = int(bool(force_general_deposit))
         self.params = p
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.keep_slices_3d = bool(keep_slices_3d)
@@ -282,6 +288,10 @@ class WakefieldSolver:
     @property
     def stopped_at(self):
         return self.lib.L.qpic_stopped_at(self.ctx)
+
+    @property
+    def fast_path_aborts(self):
+        return self.lib.L.qpic_fast_path_aborts(self.ctx)
 
     def last_step_stats(self):
         ms = ctypes.c_float(0)

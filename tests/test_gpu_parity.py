@@ -75,8 +75,9 @@ def test_spectral_solve_linearity_full_size():
         assert rel_l2(lap, a - a.mean()) < 1e-11
 
 
+@pytest.mark.parametrize("general", [False, True], ids=["tile-deposit", "sorted-deposit"])
 @pytest.mark.parametrize("name", ["odd", "pow2", "tiny_laser_shape", "m0", "ppc22"])
-def test_sweep_matches_oracle(name):
+def test_sweep_matches_oracle(name, general):
     cfgs = {
         "odd": dict(n=(5, 15, 9), d=(0.2, 0.2, 0.2), M=2, ppc=(1, 2), a0=1.0),
         "pow2": dict(n=(6, 16, 32), d=(0.2, 0.2, 0.2), M=2, ppc=(2, 2), a0=1.2),
@@ -87,9 +88,24 @@ def test_sweep_matches_oracle(name):
     case = Case.synthetic(**cfgs[name])
     o = case.make_oracle()
     o.solve_wakefield()
-    with case.make_solver(a_sqr=o.field3d("aSqr"), keep_slices_3d=True) as s:
+    with case.make_solver(a_sqr=o.field3d("aSqr"), keep_slices_3d=True, force_general_deposit=general) as s:
         assert s.solve_wakefield() == o.stopped_at == -1
         compare_sweep(s, o, TOL_SWEEP)
+        assert s.fast_path_aborts == 0
+
+
+def test_fast_path_abort_rolls_back_to_the_general_deposit():
+    """Strong drive on a coarse xi step: half-step displacements exceed one cell, so the sort-free tile deposit must give
+    up (device flag), the host must restore By/Bz of the slice start and redo the slice with the sorted deposit -- and the
+    result must still match the oracle."""
+    case = Case.synthetic(n=(10, 16, 16), d=(0.4, 0.2, 0.2), M=2, ppc=(1, 1), a0=2.5, sigma=(2.0, 1.6, 1.6), x0=2.8)
+    o = case.make_oracle()
+    o.solve_wakefield()
+    for interval in (3, 64):
+        with case.make_solver(a_sqr=o.field3d("aSqr"), keep_slices_3d=True, stop_check_interval=interval) as s:
+            assert s.solve_wakefield() == o.stopped_at
+            assert s.fast_path_aborts >= 1
+            compare_sweep(s, o, TOL_SWEEP)
 
 
 def test_device_laser_profile_matches_libm():
@@ -105,6 +121,7 @@ def test_eager_and_graph_paths_are_bit_identical_and_deterministic():
     results = []
     for use_graph in (True, False, True):
         with case.make_solver(keep_slices_3d=True, use_graph=use_graph) as s:
+            assert s.fast_path_aborts == 0
             s.solve_wakefield()
             results.append({f: s.field3d(f) for f in FIELDS} | {f + "_s": s.field3d(f, per_slice=True) for f in SLICE_FIELDS}
                            | {"p." + f: s.particles(f) for f in ["y", "z", "py", "pz"]})

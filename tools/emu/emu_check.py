@@ -17,11 +17,17 @@ from quetzalpic_b200.solver import QpicLibrary, WakefieldSolver, gaussian_laser_
 
 EMU = QpicLibrary(os.path.join(ROOT, "tools", "emu", "_build", "libqpic_emu_debug.so"))
 
+FORCE_GENERAL = False
+
 CASES = {
+    # strong drive on a coarse longitudinal step: half-step displacements exceed one cell -> fast path must roll back
+    "abort": dict(n=(10, 16, 16), l=(4.0, 3.2, 3.2), M=2, ppc=(1, 1), a0=2.5, sig=(2.0, 1.6, 1.6), x0=2.8, poll=3),
     # name: nx, ny, nz, lx, ly, lz, M, ppcy, ppcz, a0, (xs, ys, zs), x0
     "tiny_laser": dict(n=(16, 20, 23), l=(3.2, 4.0, 4.8), M=3, ppc=(2, 1), a0=1.5, sig=(1.2, 2.0, 2.4), x0=2.2),
     "pow2": dict(n=(6, 16, 32), l=(1.2, 3.2, 6.4), M=2, ppc=(2, 2), a0=1.2, sig=(0.8, 1.6, 3.0), x0=0.8),
     "odd": dict(n=(5, 15, 9), l=(1.0, 3.0, 1.8), M=2, ppc=(1, 2), a0=1.0, sig=(0.8, 1.6, 1.0), x0=0.6),
+    "p64": dict(n=(4, 64, 128), l=(0.8, 6.4, 12.8), M=2, ppc=(1, 1), a0=1.3, sig=(0.8, 3.0, 6.0), x0=0.5),
+    "p256": dict(n=(3, 256, 64), l=(0.6, 25.6, 6.4), M=1, ppc=(1, 1), a0=1.3, sig=(0.8, 12.0, 3.0), x0=0.4),
     "m0": dict(n=(4, 8, 12), l=(0.8, 1.6, 2.4), M=0, ppc=(1, 1), a0=1.0, sig=(0.8, 1.6, 1.0), x0=0.5),
 }
 
@@ -44,7 +50,8 @@ def run_case(name, cfg):
     t0 = time.time()
     o.solve_wakefield()
     t1 = time.time()
-    s = WakefieldSolver(nx, ny, nz, lx, ly, lz, M, keep_slices_3d=True, library=EMU)
+    s = WakefieldSolver(nx, ny, nz, lx, ly, lz, M, keep_slices_3d=True, library=EMU, force_general_deposit=FORCE_GENERAL,
+                        stop_check_interval=cfg.get("poll", 64))
     s.upload_a_sqr(o.field3d("aSqr"))
     s.init_wake_particles(y, z, n)
     s.solve_wakefield()
@@ -62,12 +69,41 @@ def run_case(name, cfg):
         e = rel(s.particles(f), o.particles(f))
         worst = max(worst, e)
         print(f"  p.{f:13s} {e:.3e}")
-    print(f"{name}: worst {worst:.3e}  (oracle {t1 - t0:.2f}s, emu {t2 - t1:.2f}s) stopped {s.stopped_at} / {o.stopped_at}")
+    print(f"{name}: worst {worst:.3e}  (oracle {t1 - t0:.2f}s, emu {t2 - t1:.2f}s) stopped {s.stopped_at} / {o.stopped_at}"
+          f"  fast-path aborts {s.fast_path_aborts}  general={FORCE_GENERAL}")
     s.close()
     return worst
 
 
+def fft_check():
+    from oracle.qo import lib
+    bad = 0
+    for ny, nz in [(64, 128), (128, 64), (256, 64), (64, 1024), (20, 23), (512, 64)]:
+        rng = np.random.default_rng(ny + nz)
+        src, src2 = rng.standard_normal((ny, nz)), rng.standard_normal((ny, nz))
+        o = Oracle(1, ny, nz, 1.0, 0.1 * ny, 0.07 * nz, 0)
+        s = WakefieldSolver(1, ny, nz, 1.0, 0.1 * ny, 0.07 * nz, 0, library=EMU)
+        for D in (0.0, 10.0):
+            ref, ref2 = src.copy(), src2.copy()
+            lib().qo_solve_poisson(o.ctx, ref.ctypes.data, D)
+            lib().qo_solve_poisson(o.ctx, ref2.ctypes.data, D)
+            ref /= ny * nz
+            ref2 /= ny * nz
+            e1 = rel(s.solve_poisson(src, D), ref)
+            a, b = s.solve_helmholtz_pair(src, src2, D)
+            e2, e3 = rel(a, ref), rel(b, ref2)
+            print(f"fft {ny}x{nz} D={D}: real {e1:.2e} pair {e2:.2e} {e3:.2e}")
+            bad += (max(e1, e2, e3) > 1e-13)
+        s.close()
+    return bad
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["fft"]:
+        sys.exit(int(fft_check()))
+    if "--general" in sys.argv:
+        FORCE_GENERAL = True
+        sys.argv.remove("--general")
     names = sys.argv[1:] or list(CASES)
     bad = 0
     for nm in names:

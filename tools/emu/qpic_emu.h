@@ -263,6 +263,7 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t * e, unsigned) {
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float * ms, cudaEvent_t, cudaEvent_t) {
     *ms = 0.f;
     return 0;
