@@ -17,6 +17,7 @@
 #include "../../include/qpic_b200.h"
 #include "qpic_compat.h"
 #include "qpic_fft.cuh"
+#include "qpic_fft_pow2.cuh"
 #include "qpic_kernels.cuh"
 
 #ifndef M_PI
@@ -73,6 +74,8 @@ struct qpic_ctx {
     Particles P = {};
     int *count = nullptr, *cursor = nullptr, *sums = nullptr, *tmp = nullptr;
     int *start_b = nullptr, *start_m = nullptr, *perm_b = nullptr, *perm_m = nullptr;
+    unsigned long long * pmask[3] = {nullptr, nullptr, nullptr};  // presence masks of the half-step classes, rotating per iteration
+    int pmask_cur = 0;
     int nchunks = 0;
     std::vector<void *> allocations;
 
@@ -84,6 +87,12 @@ struct qpic_ctx {
     FftLaunch rows_real, rows_cplx, cols_half, cols_full;
     bool pow2_y = false, pow2_z = false;
     double inv_scale = 0.0;  // 1/(ny*nz) when that is exactly representable (power of two), else 0 = divide
+    struct InvSymbol {
+        double D;
+        bool full;
+        double * table;  // device, [ncols][ny]
+    };
+    std::vector<InvSymbol> inv_symbols;  // for the power-of-two column kernel
 
     // graph
     cudaGraph_t graph = nullptr, graph_fast = nullptr;
@@ -197,15 +206,15 @@ int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaun
     const int n = P.n;
     if (P.log2n > 0) {
         const int e8 = n / 8;
-        int spb = 256 / e8;
-        if (spb < 1) spb = 1;
-        const int want = nseq / 148;  // keep at least ~one block per SM when there is enough work
-        if (spb > want) spb = want;
+        // These kernels are latency bound (a few warps per SM at most), so the fastest shape is ONE wave of fat blocks:
+        // as many sequences per block as it takes to cover the batch with <= 148 blocks, within 1024 threads / 227 KB.
+        int spb = (nseq + 147) / 148;
+        while (spb > 1 && (spb * e8 > 1024 || sizeof(double2) * 2 * (size_t)spb * n > SMEM_OPTIN_LIMIT)) spb--;
         if (spb < 1) spb = 1;
         while (spb * e8 < 32) spb *= 2;
         L->spb = spb;
         L->threads = spb * e8;
-        L->smem = sizeof(double2) * (size_t)spb * n;
+        L->smem = sizeof(double2) * 2 * (size_t)spb * n;  // two alternating exchange buffers per sequence
     } else {
         L->spb = 1;
         L->threads = pick_threads(n / 4);
@@ -231,6 +240,35 @@ int make_symbol_tables(qpic_ctx * c) {
     return QPIC_OK;
 }
 
+// 1 / (-D + sy[j] + sz[min(k, nz-k)]) laid out [k][j] (a column of the spectrum reads it contiguously); the divisor is the
+// reference's expression (src/System_3d.cpp:699) evaluated on the host, bin (0,0) is 0 (:688-689)
+int get_inv_symbol(qpic_ctx * c, double D, bool full, const double ** out) {
+    for (const auto & e : c->inv_symbols) {
+        if (e.D == D && e.full == full) {
+            *out = e.table;
+            return QPIC_OK;
+        }
+    }
+    const int ny = c->g.ny, nz = c->g.nz;
+    const int ncols = full ? nz : nz / 2 + 1;
+    std::vector<double> h((size_t)ncols * ny);
+    for (int k = 0; k < ncols; k++) {
+        const int kk = (k <= nz - k) ? k : nz - k;
+        for (int j = 0; j < ny; j++) {
+            const double multiplier =
+                -D + (2 * cos(2 * M_PI * j / ny) - 2) / c->g.dy / c->g.dy + (2 * cos(2 * M_PI * kk / nz) - 2) / c->g.dz / c->g.dz;
+            h[(size_t)k * ny + j] = (j == 0 && k == 0) ? 0.0 : 1.0 / multiplier;
+        }
+    }
+    double * d = nullptr;
+    QPIC_TRY(dev_alloc(c, &d, h.size(), false));
+    QPIC_CUDA(c, cudaMemcpyAsync(d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->inv_symbols.push_back({D, full, d});
+    *out = d;
+    return QPIC_OK;
+}
+
 int check_launch(qpic_ctx * c, const char * what) {
     c->launch_counter++;
     cudaError_t e = cudaGetLastError();
@@ -245,7 +283,9 @@ int check_launch(qpic_ctx * c, const char * what) {
     return QPIC_OK;
 }
 
-CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, c->perm_b, c->P.fy_b, c->P.fz_b}; }
+// lists of the slice-start positions: values in slot order (identity permutation) ...
+CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, nullptr, c->P.fy_b, c->P.fz_b}; }
+// lists of the half-step positions: permutation of slots
 CellLists lists_mid(qpic_ctx * c) { return CellLists{c->start_m, c->perm_m, c->P.fy_m, c->P.fz_m}; }
 
 // ---------------------------------------------------------------------------------------------- kernel sequences
@@ -291,31 +331,55 @@ int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cel
     return QPIC_OK;
 }
 
+// columns forward, / symbol, backward over `ncols` columns of spec (leading dimension ld)
+int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bool full) {
+    const int nz = c->g.nz, nzh = nz / 2 + 1;
+    const int ncols = full ? nz : nzh;
+    const qpic_ctx::FftLaunch & L = full ? c->cols_full : c->cols_half;
+    if (c->pow2_y) {
+        const double * inv = nullptr;
+        QPIC_TRY(get_inv_symbol(c, D, full, &inv));
+        QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, c->spec, ncols, ncols, inv);
+    } else {
+        QPIC_LAUNCH(k_fft_cols_solve<false>, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, ncols, ncols, L.spb, c->sy, c->sz, nz, D);
+    }
+    return check_launch(c, "k_fft_cols_solve");
+}
+
 // real solve: fft_in -> raw (= solution / ny / nz)
 int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D) {
-    const int ny = c->g.ny, nz = c->g.nz, nzh = nz / 2 + 1;
-    auto r2c = c->pow2_z ? k_fft_rows_r2c<true> : k_fft_rows_r2c<false>;
-    auto c2r = c->pow2_z ? k_fft_rows_c2r<true> : k_fft_rows_c2r<false>;
-    auto cols = c->pow2_y ? k_fft_cols_solve<true> : k_fft_cols_solve<false>;
-    QPIC_LAUNCH(r2c, c->rows_real.blocks, c->rows_real.threads, c->rows_real.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz,
-                c->rows_real.spb);
+    const int ny = c->g.ny, nz = c->g.nz;
+    const qpic_ctx::FftLaunch & R = c->rows_real;
+    if (c->pow2_z) {
+        QPIC_LAUNCH(k_p2_rows_r2c, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->spec, ny);
+    } else {
+        QPIC_LAUNCH(k_fft_rows_r2c<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz, R.spb);
+    }
     QPIC_TRY(check_launch(c, "k_fft_rows_r2c"));
-    QPIC_LAUNCH(cols, c->cols_half.blocks, c->cols_half.threads, c->cols_half.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, nzh, nzh, c->cols_half.spb,
-                c->sy, c->sz, nz, D);
-    QPIC_TRY(check_launch(c, "k_fft_cols_solve"));
-    QPIC_LAUNCH(c2r, c->rows_real.blocks, c->rows_real.threads, c->rows_real.smem, st, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz,
-                c->rows_real.spb, c->inv_scale);
+    QPIC_TRY(enqueue_columns(c, st, ctl, D, false));
+    if (c->pow2_z) {
+        QPIC_LAUNCH(k_p2_rows_c2r, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->spec, c->raw, ny, c->inv_scale);
+    } else {
+        QPIC_LAUNCH(k_fft_rows_c2r<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz, R.spb, c->inv_scale);
+    }
     QPIC_TRY(check_launch(c, "k_fft_rows_c2r"));
     return QPIC_OK;
 }
 
 // complex solve of (re, im) = (by, bz) style pairs: spec must already hold the forward row transforms
-int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D) {
-    const int nz = c->g.nz;
-    auto cols = c->pow2_y ? k_fft_cols_solve<true> : k_fft_cols_solve<false>;
-    QPIC_LAUNCH(cols, c->cols_full.blocks, c->cols_full.threads, c->cols_full.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, nz, nz, c->cols_full.spb,
-                c->sy, c->sz, nz, D);
-    return check_launch(c, "k_fft_cols_solve");
+int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D) { return enqueue_columns(c, st, ctl, D, true); }
+
+// backward rows of a complex solve into (by, bz) with the stop test
+int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, double * bz, double threshold, int iteration) {
+    const qpic_ctx::FftLaunch & R = c->rows_cplx;
+    if (c->pow2_z) {
+        QPIC_LAUNCH(k_p2_rows_b_backward, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
+                    c->inv_scale);
+    } else {
+        QPIC_LAUNCH(k_fft_rows_b_backward<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
+                    R.spb, c->inv_scale);
+    }
+    return check_launch(c, "k_fft_rows_b_backward");
 }
 
 // ---- tile deposit jobs (FAST path)
@@ -345,19 +409,62 @@ TileJob tile_job(qpic_ctx * c) {
     return j;
 }
 
+// source-cell window (relative to the target cell) that can reach a target: 0 for deposits at (y,z); the half step moves
+// a particle by at most one cell ([-1,1]); a half-cell staggered grid adds one cell on the high side
+void tile_finish(qpic_ctx * c, TileJob & j) {
+    j.at_mid = j.o[0].at_mid;
+    j.pmask = c->pmask[c->pmask_cur];
+    // which (offset, half-cell) classes of a source cell at window position (dy, dz) can reach the target on any of the
+    // job's output grids: the particle must sit ry = dy + oy, rz = dz + oz cells above the target with
+    // ry == (staggered && lower half), same in z (see k_tile_deposit::visit)
+    for (int dy = -1; dy <= 2; dy++) {
+        for (int dz = -1; dz <= 2; dz++) {
+            unsigned long long need = 0;
+            for (int a = 0; a < j.nout; a++) {
+                for (int oy = -1; oy <= 1; oy++)
+                    for (int oz = -1; oz <= 1; oz++)
+                        for (int hy = 0; hy <= 1; hy++)
+                            for (int hz = 0; hz <= 1; hz++) {
+                                const int need_y = (j.o[a].stag_y && !hy) ? 1 : 0, need_z = (j.o[a].stag_z && !hz) ? 1 : 0;
+                                if (dy + oy == need_y && dz + oz == need_z) need |= 1ull << offset_class(oy, oz, hy, hz);
+                            }
+            }
+            j.need[(dy + 1) * 4 + (dz + 1)] = need;
+        }
+    }
+    j.wy_lo = j.wz_lo = j.at_mid ? -1 : 0;
+    j.wy_hi = j.wz_hi = j.at_mid ? 1 : 0;
+    for (int a = 0; a < j.nout; a++) {
+        if (j.o[a].stag_y) j.wy_hi = (j.at_mid ? 1 : 0) + 1;
+        if (j.o[a].stag_z) j.wz_hi = (j.at_mid ? 1 : 0) + 1;
+    }
+}
+
+int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, const char * name, bool yz_inline = false) {
+    tile_finish(c, j);
+    const dim3 grid = tile_grid(c), block(TILE_ACC, TILE_ACC);
+    if (yz_inline) {
+        auto kern = k_tile_deposit<2, false, true>;
+        QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
+    } else if (j.nout == 1) {
+        auto kern = final_pass ? k_tile_deposit<1, true, false> : k_tile_deposit<1, false, false>;
+        QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
+    } else if (j.nout == 2) {
+        auto kern = final_pass ? k_tile_deposit<2, true, false> : k_tile_deposit<2, false, false>;
+        QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
+    } else {
+        auto kern = final_pass ? k_tile_deposit<3, true, false> : k_tile_deposit<3, false, false>;
+        QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
+    }
+    return check_launch(c, name);
+}
+
 // psi source from positions (y,z) [at_mid = 0] or the half-step positions [at_mid = 1] -> fft_in
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
     j.nout = 1;
-    j.o[0] = tile_output(c->P.nw, -1.0, at_mid, 0, 0, 1, nullptr, c->fft_in, 0);
-    if (at_mid) {
-        auto kern = k_tile_deposit<2, 1, false>;
-        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 3, TILE + 3), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
-    } else {
-        auto kern = k_tile_deposit<1, 0, false>;
-        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 1, TILE + 1), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
-    }
-    return check_launch(c, at_mid ? "k_tile_deposit_charge_mid" : "k_tile_deposit_charge");
+    j.o[0] = tile_output(c->P.nw_s, -1.0, at_mid, 0, 0, 1, nullptr, c->fft_in, 0);
+    return launch_tile(c, st, j, false, at_mid ? "k_tile_deposit_charge_mid" : "k_tile_deposit_charge");
 }
 
 // deposits at (y,z): jx and / or rho + susceptibility(i)
@@ -370,25 +477,19 @@ int enqueue_tile_base_currents(qpic_ctx * c, cudaStream_t st, bool with_jx, bool
         j.o[n++] = tile_output(c->P.vchi, 1.0, 0, 0, 0, 0, nullptr, c->f3[QPIC_F3_SUSCEPTIBILITY], 1);
     }
     j.nout = n;
-    if (final_pass) {
-        auto kern = k_tile_deposit<1, 0, true>;
-        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 1, TILE + 1), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
-    } else {
-        auto kern = k_tile_deposit<1, 0, false>;
-        QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 1, TILE + 1), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
-    }
-    return check_launch(c, with_jx ? (with_rho_chi ? "k_tile_deposit_jx_rho_chi" : "k_tile_deposit_jx") : "k_tile_deposit_rho_chi");
+    return launch_tile(c, st, j, final_pass, with_jx ? (with_rho_chi ? "k_tile_deposit_jx_rho_chi" : "k_tile_deposit_jx") : "k_tile_deposit_rho_chi");
 }
 
 // jy_next (staggered in y) and jz_next (staggered in z) at the half-step positions
 int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     TileJob j = tile_job(c);
     j.nout = 2;
-    j.o[0] = tile_output(c->P.vjy, 1.0, 1, 1, 0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
-    j.o[1] = tile_output(c->P.vjz, 1.0, 1, 0, 1, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
-    auto kern = k_tile_deposit<2, 2, false>;
-    QPIC_LAUNCH(kern, tile_grid(c), dim3(TILE + 4, TILE + 4), 0, st, c->ctl, c->g, c->start_b, c->perm_b, c->P, j);
-    return check_launch(c, "k_tile_deposit_jy_jz");
+    // values n py_next / (1 + psi_middle@particle) are formed inside the deposit (no k_particles_currents_yz on this path)
+    j.o[0] = tile_output(c->P.pyn, 1.0, 1, 1, 0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
+    j.o[1] = tile_output(c->P.pzn, 1.0, 1, 0, 1, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
+    j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
+    j.nw = c->P.nw_s;
+    return launch_tile(c, st, j, false, "k_tile_deposit_jy_jz", true);
 }
 
 // ---- potentials
@@ -406,7 +507,7 @@ int enqueue_potential(qpic_ctx * c, cudaStream_t st, bool fast, int at_mid, doub
         QPIC_TRY(enqueue_tile_charge(c, st, at_mid));
     } else {
         CellLists L = at_mid ? lists_mid(c) : lists_base(c);
-        QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(c->g.n2, 128), 128, 0, st, c->ctl, c->g, L, c->P.nw, c->f2[QPIC_F2_RHO_ION], c->f3[QPIC_F3_JX_BUNCH],
+        QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(c->g.n2, 128), 128, 0, st, c->ctl, c->g, L, c->P.nw_s, c->f2[QPIC_F2_RHO_ION], c->f3[QPIC_F3_JX_BUNCH],
                          c->f3[QPIC_F3_RHO_BUNCH], 1, c->fft_in);
         QPIC_TRY(check_launch(c, "k_deposit_charge"));
     }
@@ -431,7 +532,7 @@ int enqueue_slice_head(qpic_ctx * c, bool fast, bool want_invariants, bool with_
     cudaStream_t st = c->stream;
     QPIC_TRY(enqueue_potential(c, st, fast, 0, c->f2[QPIC_F2_PSI]));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, 128), 128, 0, st, c->ctl, c->g, c->P, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
+        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, 128), 128, 0, st, c->ctl, c->g, c->P, c->perm_b, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
                          want_invariants ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_gamma"));
     }
@@ -469,9 +570,19 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     cudaStream_t sb = c->profiling ? c->stream : c->stream2;  // per-kernel timing wants one serial stream
     QPIC_TRY(enqueue_slice_head(c, fast, M > 0, M == 0));
     for (int it = 0; it < M; it++) {
+        // Presence-mask buffer of this iteration.  The buffer of the NEXT predictor (next iteration, or iteration 0 of the
+        // next slice: the graph is replayed) is cleared on branch B meanwhile, so it must differ from the one in use.
+        auto mask_buffer = [M](int i) { return (i == M - 1 && i > 0 && i % 3 == 0) ? 1 : i % 3; };
+        c->pmask_cur = mask_buffer(it);
+        const int pmask_next = mask_buffer(it + 1 < M ? it + 1 : 0);
+        if (fast && pmask_next == c->pmask_cur) {
+            // M == 1: a single buffer, cleared in line
+            QPIC_CUDA(c, cudaMemsetAsync(c->pmask[c->pmask_cur], 0, sizeof(unsigned long long) * c->g.n2, sa));
+        }
         if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
-            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count);
+            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
+                             c->pmask[c->pmask_cur]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
         // branch B: corrector gamma / px and the jx deposit at (y,z) need only py_next, pz_next
@@ -481,16 +592,20 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             QPIC_TRY(check_launch(c, "k_particles_correct_gamma"));
         }
         QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
+        // the other presence-mask buffer was last read by the previous iteration's deposits: clear it for the next one
+        if (fast && pmask_next != c->pmask_cur) {
+            QPIC_CUDA(c, cudaMemsetAsync(c->pmask[pmask_next], 0, sizeof(unsigned long long) * c->g.n2, sb));
+        }
         // branch A: psi_middle, then jy_next / jz_next
         if (!fast) QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
         QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
-        if (np > 0) {
-            QPIC_LAUNCH_FLAT(k_particles_currents_yz, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
-            QPIC_TRY(check_launch(c, "k_particles_currents_yz"));
-        }
         if (fast) {
             QPIC_TRY(enqueue_tile_jy_jz(c, sa));
         } else {
+            if (np > 0) {
+                QPIC_LAUNCH_FLAT(k_particles_currents_yz, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
+                QPIC_TRY(check_launch(c, "k_particles_currents_yz"));
+            }
             QPIC_LAUNCH_FLAT(k_deposit_jy_jz, blocks_for(n2, 128), 128, 0, sa, c->ctl, c->g, lists_mid(c), c->P.vjy, c->P.vjz, c->f2[QPIC_F2_JY_NEXT],
                              c->f2[QPIC_F2_JZ_NEXT]);
             QPIC_TRY(check_launch(c, "k_deposit_jy_jz"));
@@ -498,16 +613,19 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(stream_depend(c, sb, sa));
         // By + i Bz in one complex solve
         {
-            auto bfwd = c->pow2_z ? k_fft_rows_b_forward<true> : k_fft_rows_b_forward<false>;
-            auto bbwd = c->pow2_z ? k_fft_rows_b_backward<true> : k_fft_rows_b_backward<false>;
-            QPIC_LAUNCH(bfwd, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
-                        c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
-                        c->f2[QPIC_F2_JZ_NEXT], c->spec, c->rows_cplx.spb);
+            const qpic_ctx::FftLaunch & R = c->rows_cplx;
+            if (c->pow2_z) {
+                QPIC_LAUNCH(k_p2_rows_b_forward, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D,
+                            c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
+                            c->f2[QPIC_F2_JZ_NEXT], c->spec);
+            } else {
+                QPIC_LAUNCH(k_fft_rows_b_forward<false>, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
+                            c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
+                            c->f2[QPIC_F2_JZ_NEXT], c->spec, R.spb);
+            }
             QPIC_TRY(check_launch(c, "k_fft_rows_b_forward"));
             QPIC_TRY(enqueue_complex_columns(c, sa, c->ctl, c->prm.magnetic_field_D));
-            QPIC_LAUNCH(bbwd, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->spec,
-                        c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->prm.threshold_B, it, c->rows_cplx.spb, c->inv_scale);
-            QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
+            QPIC_TRY(enqueue_b_backward(c, sa, c->ctl, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->prm.threshold_B, it));
         }
     }
     // rho and susceptibility(i) from the last executed iteration (see k_deposit_jx_rho_chi); reads the cell lists and
@@ -523,10 +641,14 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(rc);
     }
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE], c->count);
+        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->perm_b, c->f2[QPIC_F2_PSI_MIDDLE], c->count);
         QPIC_TRY(check_launch(c, "k_particles_advance"));
     }
-    QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_b, c->start_b, c->perm_b));
+    QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, sa, c->ctl, c->P, c->perm_b);
+        QPIC_TRY(check_launch(c, "k_particles_to_slots"));
+    }
     QPIC_TRY(stream_depend(c, sb, sa));
     QPIC_LAUNCH_FLAT(k_next_slice, 1, 32, 0, sa, c->ctl);
     QPIC_TRY(check_launch(c, "k_next_slice"));
@@ -538,10 +660,14 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
     const int np = c->P.np;
     QPIC_CUDA(c, cudaMemsetAsync(c->count, 0, sizeof(int) * c->g.n2, c->stream));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(np, 256), 256, 0, c->stream, np, c->g, c->P.y, c->P.z, c->P.cell_b, c->P.fy_b, c->P.fz_b, c->count);
+        QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(np, 256), 256, 0, c->stream, np, c->g, c->P.y, c->P.z, c->P.cell_p, c->P.fy_p, c->P.fz_p, c->count);
         QPIC_TRY(check_launch(c, "k_locate_count"));
     }
-    QPIC_TRY(enqueue_sort(c, c->stream, c->ctl_scratch, c->P.cell_b, c->start_b, c->perm_b));
+    QPIC_TRY(enqueue_sort(c, c->stream, c->ctl_scratch, c->P.cell_p, c->start_b, c->perm_b));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, c->stream, c->ctl_scratch, c->P, c->perm_b);
+        QPIC_TRY(check_launch(c, "k_particles_to_slots"));
+    }
     c->lists_dirty = false;
     return QPIC_OK;
 }
@@ -549,9 +675,11 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
 int alloc_particles(qpic_ctx * c, size_t count) {
     Particles & P = c->P;
     P.np = (int)count;
-    double ** dbl[] = {&P.y,  &P.z,   &P.py,   &P.pz,   &P.nw,   &P.gamma, &P.px,  &P.pyn, &P.pzn, &P.fy_b, &P.fz_b, &P.fy_m, &P.fz_m,
-                       &P.q,  &P.ap,  &P.t1y,  &P.t1z,  &P.dpy,  &P.dpz,   &P.vjx, &P.vrho, &P.vchi, &P.vjy, &P.vjz};
+    double ** dbl[] = {&P.y,   &P.z,   &P.py,  &P.pz,  &P.nw,   &P.gamma, &P.px,  &P.fy_p, &P.fz_p, &P.fy_b, &P.fz_b, &P.y_s, &P.z_s, &P.py_s, &P.pz_s,
+                       &P.nw_s, &P.gam, &P.pxs, &P.pyn, &P.pzn,  &P.fy_m,  &P.fz_m, &P.q,    &P.ap,   &P.t1y,  &P.t1z,  &P.dpy, &P.dpz, &P.vjx,  &P.vrho,
+                       &P.vchi, &P.vjy, &P.vjz};
     for (double ** p : dbl) QPIC_TRY(dev_alloc(c, p, count));
+    QPIC_TRY(dev_alloc(c, &P.cell_p, count));
     QPIC_TRY(dev_alloc(c, &P.cell_b, count));
     QPIC_TRY(dev_alloc(c, &P.cell_m, count));
     QPIC_TRY(dev_alloc(c, &P.off_m, count));
@@ -739,6 +867,9 @@ static int create_impl(qpic_ctx * c) {
     g.dz = p.lz / p.nz;
     g.ly = p.ly;
     g.lz = p.lz;
+    g.inv_dx = 1.0 / g.dx;
+    g.inv_dy = 1.0 / g.dy;
+    g.inv_dz = 1.0 / g.dz;
 
     const size_t n2 = (size_t)g.n2, n3 = n2 * g.nx;
     QPIC_TRY(make_fft(c, g.ny, &c->fy));
@@ -772,21 +903,27 @@ static int create_impl(qpic_ctx * c) {
         size_t cols_max = c->cols_half.smem > c->cols_full.smem ? c->cols_half.smem : c->cols_full.smem;
         if (rows_max > SMEM_DEFAULT_LIMIT) {
             const int b = (int)rows_max;
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_r2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_r2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2r<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2r<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
         }
         if (cols_max > SMEM_DEFAULT_LIMIT) {
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
         }
+    }
+    // the inverse-symbol tables of the two operators of the sweep (psi: D = 0, half spectrum; By + i Bz: D, full spectrum)
+    if (c->pow2_y) {
+        const double * unused = nullptr;
+        QPIC_TRY(get_inv_symbol(c, 0.0, false, &unused));
+        QPIC_TRY(get_inv_symbol(c, p.magnetic_field_D, true, &unused));
     }
 
     QPIC_TRY(dev_alloc(c, &c->ctl, 1));
@@ -809,6 +946,7 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(dev_alloc(c, &c->sums, (size_t)c->nchunks));
     QPIC_TRY(dev_alloc(c, &c->start_b, n2 + 1));
     QPIC_TRY(dev_alloc(c, &c->start_m, n2 + 1));
+    for (int b = 0; b < 3; b++) QPIC_TRY(dev_alloc(c, &c->pmask[b], n2));
     QPIC_TRY(alloc_particles(c, 0));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cur = g.nx - 1;
@@ -901,7 +1039,7 @@ int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, c
         // (re)allocation: the previous arrays stay owned by the context until qpic_destroy
         QPIC_TRY(alloc_particles(c, count));
     } else {
-        double * zero[] = {c->P.py, c->P.pz, c->P.pyn, c->P.pzn, c->P.gamma, c->P.px};
+        double * zero[] = {c->P.py, c->P.pz, c->P.pyn, c->P.pzn, c->P.gamma, c->P.px, c->P.gam, c->P.pxs};
         for (double * p : zero) QPIC_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * count, c->stream));
     }
     if (count > 0) {
@@ -937,7 +1075,7 @@ int qpic_begin(qpic_ctx * c) {
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     QPIC_TRY(enqueue_rebuild_base_lists(c));
     // rho_ion (src/System_3d.cpp:319-323)
-    QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(g.n2, 128), 128, 0, c->stream, c->ctl_scratch, c->g, lists_base(c), c->P.nw, (const double *)nullptr,
+    QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(g.n2, 128), 128, 0, c->stream, c->ctl_scratch, c->g, lists_base(c), c->P.nw_s, (const double *)nullptr,
                      (const double *)nullptr, (const double *)nullptr, 0, c->f2[QPIC_F2_RHO_ION]);
     QPIC_TRY(check_launch(c, "k_deposit_charge"));
     c->cur = g.nx - 1;
@@ -1152,15 +1290,17 @@ int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inou
     const int ny = c->g.ny, nz = c->g.nz;
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout_a, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in2, inout_b, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
-    auto c2c = c->pow2_z ? k_fft_rows_c2c<true> : k_fft_rows_c2c<false>;
-    auto bbwd = c->pow2_z ? k_fft_rows_b_backward<true> : k_fft_rows_b_backward<false>;
-    QPIC_LAUNCH(c2c, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny,
-                nz, c->rows_cplx.spb);
-    QPIC_TRY(check_launch(c, "k_fft_rows_c2c"));
+    {
+        const qpic_ctx::FftLaunch & R = c->rows_cplx;
+        if (c->pow2_z) {
+            QPIC_LAUNCH(k_p2_rows_c2c, R.blocks, R.threads, R.smem, c->stream, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny);
+        } else {
+            QPIC_LAUNCH(k_fft_rows_c2c<false>, R.blocks, R.threads, R.smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny, nz, R.spb);
+        }
+        QPIC_TRY(check_launch(c, "k_fft_rows_c2c"));
+    }
     QPIC_TRY(enqueue_complex_columns(c, c->stream, c->ctl_scratch, D));
-    QPIC_LAUNCH(bbwd, c->rows_cplx.blocks, c->rows_cplx.threads, c->rows_cplx.smem, c->stream, c->ctl_scratch, c->fz.plan, c->fz.tw, c->g, c->spec,
-                c->fft_in, c->fft_in2, std::numeric_limits<double>::infinity(), 0, c->rows_cplx.spb, c->inv_scale);
-    QPIC_TRY(check_launch(c, "k_fft_rows_b_backward"));
+    QPIC_TRY(enqueue_b_backward(c, c->stream, c->ctl_scratch, c->fft_in, c->fft_in2, std::numeric_limits<double>::infinity(), 0));
     QPIC_CUDA(c, cudaMemcpyAsync(inout_a, c->fft_in, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaMemcpyAsync(inout_b, c->fft_in2, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));

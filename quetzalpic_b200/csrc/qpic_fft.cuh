@@ -411,11 +411,11 @@ __global__ void k_fft_rows_b_forward(const Ctl * ctl, FftPlan Pz, const double2 
         for (int k = threadIdx.x; k < nz; k += blockDim.x) {
             const int t = j * nz + k;
             const int kp = wrap_inc(k, nz);
-            const double djz_dxi = (jz[t] - jz_next[t]) / g.dx;
-            const double djy_dxi = (jy[t] - jy_next[t]) / g.dx;
+            const double djz_dxi = (jz[t] - jz_next[t]) * g.inv_dx;
+            const double djy_dxi = (jy[t] - jy_next[t]) * g.inv_dx;
             const double jxt = jx[t];
-            a[b * nz + k] = make_double2(-D * by[t] - (jx[j * nz + kp] - jxt) / g.dz + djz_dxi,
-                                         -D * bz[jq * nz + k] + (jx[jp * nz + k] - jxt) / g.dy - djy_dxi);
+            a[b * nz + k] = make_double2(-D * by[t] - (jx[j * nz + kp] - jxt) * g.inv_dz + djz_dxi,
+                                         -D * bz[jq * nz + k] + (jx[jp * nz + k] - jxt) * g.inv_dy - djy_dxi);
         }
     }
     __syncthreads();

@@ -1,0 +1,275 @@
+// Register-resident transforms for power-of-two lengths (512, 1024, 4096: the BASELINE transverse grids).
+//
+// Every thread owns 8 points of its sequence, t + (n/8) e for e = 0..7, in registers.  A transform is a chain of radix-8
+// Stockham passes (plus one radix-4 / radix-2 pass to finish): butterfly in registers, twiddle, exchange through
+// shared memory (two alternating buffers -> one barrier per exchange), next pass.  The ownership pattern is the same
+// before the first and after the last pass, so forward transform -> spectral division -> backward transform of a column
+// runs without the data ever leaving registers except for the 2 (n = 512) exchanges per transform, and the row kernels
+// read / write global memory directly from / to registers, fully coalesced.
+//
+// Per pass a thread fetches 3 table twiddles (w, w^2, w^4; exact to 1/2 ulp) and forms w^3, w^5, w^6, w^7 with four complex
+// products instead of issuing seven dependent table loads.
+//
+// The spectral division multiplies by a host-built table of 1 / (-D + (2cos(2 pi j/ny)-2)/dy^2 + (2cos(2 pi k/nz)-2)/dz^2)
+// (src/System_3d.cpp:699; entry (0,0) = 0, :688-689), stored column-major so that a column reads it contiguously.
+#pragma once
+
+#include "qpic_fft.cuh"
+
+namespace qpic {
+
+// one transform of the sequence whose exchange buffers are xa / xb (n points each); v[e] = point t + (n/8) e
+template <bool INV>
+__device__ __forceinline__ void fft_pow2_regs(double2 (&v)[8], double2 * xa, double2 * xb, int t, int log2n, const double2 * __restrict__ tw) {
+    const int le8 = log2n - 3;
+    int log2s = 0;
+    int rem = log2n;
+    int flip = 0;
+    while (true) {
+        const int lr = rem >= 3 ? 3 : rem;
+        if (lr == 3) {
+            dft8<INV>(v);
+        } else if (lr == 2) {
+            dft4<INV>(v[0], v[2], v[4], v[6]);
+            dft4<INV>(v[1], v[3], v[5], v[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double2 a0 = v[i], a1 = v[i + 4];
+                v[i] = cadd(a0, a1);
+                v[i + 4] = csub(a0, a1);
+            }
+        }
+        rem -= lr;
+        if (rem == 0) break;  // the finishing pass has p = 0 (no twiddles) and leaves v[e] = point t + (n/8) e
+        // a radix-8 pass that is not the last one: twiddle by w_p^k and exchange
+        const int p = t >> log2s, q = t & ((1 << log2s) - 1);
+        const double2 w1 = twiddle<INV>(tw, p << log2s);
+        const double2 w2 = twiddle<INV>(tw, (2 * p) << log2s);
+        const double2 w4 = twiddle<INV>(tw, (4 * p) << log2s);
+        const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
+        const double2 w7 = cmul(w4, w3);
+        double2 * y = (flip ? xb : xa) + q + ((8 * p) << log2s);
+        y[0] = v[0];
+        y[1 << log2s] = cmul(v[1], w1);
+        y[2 << log2s] = cmul(v[2], w2);
+        y[3 << log2s] = cmul(v[3], w3);
+        y[4 << log2s] = cmul(v[4], w4);
+        y[5 << log2s] = cmul(v[5], w5);
+        y[6 << log2s] = cmul(v[6], w6);
+        y[7 << log2s] = cmul(v[7], w7);
+        __syncthreads();
+        const double2 * x = (flip ? xb : xa) + t;
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = x[e << le8];
+        flip ^= 1;
+        log2s += 3;
+    }
+}
+
+// thread layout shared by all kernels below: blockDim.x = spb * n/8; sequence b = threadIdx.x / (n/8), lane t
+struct Pow2Lane {
+    int b, t, e8;
+    double2 *xa, *xb;
+};
+
+__device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
+    Pow2Lane L;
+    const int le8 = log2n - 3;
+    L.e8 = 1 << le8;
+    L.b = threadIdx.x >> le8;
+    L.t = threadIdx.x & (L.e8 - 1);
+    L.xa = sm + ((size_t)L.b << (log2n + 1));
+    L.xb = L.xa + (1 << log2n);
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------ real field (psi)
+
+// forward rows, two real rows per sequence -> half spectra spec[ny][nzh]
+__global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, double2 * __restrict__ spec,
+                              int ny) {
+    if (cancelled(ctl)) return;
+    QPIC_DYN_SMEM(double2, sm);
+    const Pow2Lane L = pow2_lane(sm, log2n);
+    const int nz = 1 << log2n, nzh = nz / 2 + 1;
+    const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
+    double2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = L.t + e * L.e8;
+        v[e] = make_double2(j0 < ny ? src[(size_t)j0 * nz + k] : 0.0, j1 < ny ? src[(size_t)j1 * nz + k] : 0.0);
+    }
+    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    // the split needs Z_k and Z_{n-k}: one more exchange.  The last exchange of the transform used the other buffer
+    // (or none at all), so this buffer is free once every thread has left the transform's final read.
+    __syncthreads();
+    double2 * z = L.xa;
+#pragma unroll
+    for (int e = 0; e < 8; e++) z[L.t + e * L.e8] = v[e];
+    __syncthreads();
+    if (j0 >= ny) return;
+    for (int k = L.t; k < nzh; k += L.e8) {
+        const double2 zk = z[k];
+        const double2 zm = z[k == 0 ? 0 : nz - k];
+        // U0 = (Z_k + conj(Z_{n-k})) / 2,  U1 = (Z_k - conj(Z_{n-k})) / (2i)
+        spec[(size_t)j0 * nzh + k] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        if (j1 < ny) spec[(size_t)j1 * nzh + k] = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+    }
+}
+
+// backward rows: two half spectra -> one complex sequence -> two real rows, scaled by 1/ny/nz (src/System_3d.cpp:361)
+__global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double2 * __restrict__ spec, double * __restrict__ dst,
+                              int ny, double inv_scale) {
+    if (cancelled(ctl)) return;
+    QPIC_DYN_SMEM(double2, sm);
+    const Pow2Lane L = pow2_lane(sm, log2n);
+    const int nz = 1 << log2n, nzh = nz / 2 + 1;
+    const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
+    double2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int i = L.t + e * L.e8;
+        const bool mirror = i > nz / 2;
+        const int k = mirror ? nz - i : i;
+        double2 v0 = (j0 < ny) ? spec[(size_t)j0 * nzh + k] : make_double2(0.0, 0.0);
+        double2 v1 = (j1 < ny) ? spec[(size_t)j1 * nzh + k] : make_double2(0.0, 0.0);
+        if (k == 0 || 2 * k == nz) {
+            // c2r ignores the imaginary part of the DC / Nyquist bins (they are rounding noise for a real field)
+            v0.y = 0.0;
+            v1.y = 0.0;
+        }
+        // Z_k = V0 + i V1;  Z_{n-k} = conj(V0) + i conj(V1)
+        v[e] = mirror ? make_double2(v0.x + v1.y, v1.x - v0.y) : make_double2(v0.x - v1.y, v0.y + v1.x);
+    }
+    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = L.t + e * L.e8;
+        if (j0 < ny) dst[(size_t)j0 * nz + k] = scale_result(v[e].x, ny, nz, inv_scale);
+        if (j1 < ny) dst[(size_t)j1 * nz + k] = scale_result(v[e].y, ny, nz, inv_scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ columns + symbol
+// one column per sequence; inv_symbol is [ncols][ny] (column-major for this kernel), entry (k=0, j=0) = 0
+__global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
+                                const double * __restrict__ inv_symbol) {
+    if (cancelled(ctl)) return;
+    QPIC_DYN_SMEM(double2, sm);
+    const Pow2Lane L = pow2_lane(sm, log2n);
+    const int ny = 1 << log2n;
+    const int k = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    const bool live = k < ncols;
+    double2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = live ? spec[(size_t)(L.t + e * L.e8) * ld + k] : make_double2(0.0, 0.0);
+    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twy);
+    if (live) {
+        const double * __restrict__ inv = inv_symbol + (size_t)k * ny;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int j = L.t + e * L.e8;
+            const double r = inv[j];
+            v[e] = (j == 0 && k == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * r, v[e].y * r);
+        }
+    }
+    // the forward transform's last exchange buffer may still be read by slower threads of this sequence
+    __syncthreads();
+    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy);
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) spec[(size_t)(L.t + e * L.e8) * ld + k] = v[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ complex field (By + i Bz)
+
+// see k_fft_rows_b_forward (qpic_fft.cuh) for the source terms (src/System_3d.cpp:489-495, :530-536, :555-564 incl. :563)
+__global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
+                                    const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
+                                    const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
+                                    double2 * __restrict__ spec) {
+    if (cancelled(ctl)) return;
+    QPIC_DYN_SMEM(double2, sm);
+    const Pow2Lane L = pow2_lane(sm, log2n);
+    const int nz = g.nz, ny = g.ny;
+    const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    const bool live = j < ny;
+    const int jp = live ? wrap_inc(j, ny) : 0;
+    const int jq = (j == ny - 1) ? 0 : j;
+    double2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = L.t + e * L.e8;
+        if (live) {
+            const int t = j * nz + k;
+            const int kp = wrap_inc(k, nz);
+            const double djz_dxi = (jz[t] - jz_next[t]) * g.inv_dx;
+            const double djy_dxi = (jy[t] - jy_next[t]) * g.inv_dx;
+            const double jxt = jx[t];
+            v[e] = make_double2(-D * by[t] - (jx[j * nz + kp] - jxt) * g.inv_dz + djz_dxi, -D * bz[jq * nz + k] + (jx[jp * nz + k] - jxt) * g.inv_dy - djy_dxi);
+        } else {
+            v[e] = make_double2(0.0, 0.0);
+        }
+    }
+    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) spec[(size_t)j * nz + L.t + e * L.e8] = v[e];
+    }
+}
+
+// by(i) = re/ny/nz, bz(i) = im/ny/nz and the stop test (src/System_3d.cpp:541-552, :569-580)
+__global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, const double2 * __restrict__ spec,
+                                     double * __restrict__ by, double * __restrict__ bz, double threshold, int iteration, double inv_scale) {
+    // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
+    const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
+    const int tag = ctl->stop_tag;
+    if ((tag != 0 && tag != my_tag) || ctl->fast_fail) return;
+    QPIC_DYN_SMEM(double2, sm);
+    const Pow2Lane L = pow2_lane(sm, log2n);
+    const int nz = g.nz, ny = g.ny;
+    const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    const bool live = j < ny;
+    double2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = live ? spec[(size_t)j * nz + L.t + e * L.e8] : make_double2(0.0, 0.0);
+    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+    if (!live) return;
+    bool bad = false;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = L.t + e * L.e8;
+        const double vy = scale_result(v[e].x, ny, nz, inv_scale);
+        const double vz = scale_result(v[e].y, ny, nz, inv_scale);
+        by[(size_t)j * nz + k] = vy;
+        bz[(size_t)j * nz + k] = vz;
+        // !(|v| <= threshold) is true for |v| > threshold and for NaN
+        if (!(fabs(vy) <= threshold) || !(fabs(vz) <= threshold)) bad = true;
+    }
+    if (bad) atomicExch(&ctl->stop_tag, my_tag);
+}
+
+// plain complex rows (exposed Helmholtz-pair building block)
+__global__ void k_p2_rows_c2c(int log2n, const double2 * __restrict__ twz, const double * __restrict__ re, const double * __restrict__ im,
+                              double2 * __restrict__ spec, int ny) {
+    QPIC_DYN_SMEM(double2, sm);
+    const Pow2Lane L = pow2_lane(sm, log2n);
+    const int nz = 1 << log2n;
+    const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    const bool live = j < ny;
+    double2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const size_t gidx = (size_t)j * nz + L.t + e * L.e8;
+        v[e] = live ? make_double2(re[gidx], im[gidx]) : make_double2(0.0, 0.0);
+    }
+    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) spec[(size_t)j * nz + L.t + e * L.e8] = v[e];
+    }
+}
+
+}  // namespace qpic

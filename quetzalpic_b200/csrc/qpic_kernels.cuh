@@ -33,6 +33,9 @@ struct Geom {
     int n2;  // ny * nz
     double dx, dy, dz;
     double ly, lz;
+    // 1/dx, 1/dy, 1/dz: finite differences multiply by these instead of dividing (exact when the step is a power of two,
+    // as in the BASELINE grids; otherwise within an ulp of the reference's quotient).  Positions -> cells keep the division.
+    double inv_dx, inv_dy, inv_dz;
 };
 
 // ------------------------------------------------------------------------------------------------ index helpers
@@ -84,30 +87,30 @@ __device__ __forceinline__ double gather_node(const double * __restrict__ a, int
 }
 
 // d/dy at half points: 6-cell stencil (src/array_utils.cpp:240-263 / :190-213)
-__device__ __forceinline__ double gather_yder(const double * __restrict__ a, int ny, int nz, double dy, int jc, int kc, double fy, double fz) {
+__device__ __forceinline__ double gather_yder(const double * __restrict__ a, int ny, int nz, double inv_dy, int jc, int kc, double fy, double fz) {
     int j1;
     double fs;
     stagger(jc, fy, ny, j1, fs);
     const int j2 = wrap_inc(j1, ny), j3 = wrap_inc(j2, ny);
     const int k1 = kc, k2 = wrap_inc(kc, nz);
-    const double d11 = (a[nz * j2 + k1] - a[nz * j1 + k1]) / dy;
-    const double d21 = (a[nz * j3 + k1] - a[nz * j2 + k1]) / dy;
-    const double d12 = (a[nz * j2 + k2] - a[nz * j1 + k2]) / dy;
-    const double d22 = (a[nz * j3 + k2] - a[nz * j2 + k2]) / dy;
+    const double d11 = (a[nz * j2 + k1] - a[nz * j1 + k1]) * inv_dy;
+    const double d21 = (a[nz * j3 + k1] - a[nz * j2 + k1]) * inv_dy;
+    const double d12 = (a[nz * j2 + k2] - a[nz * j1 + k2]) * inv_dy;
+    const double d22 = (a[nz * j3 + k2] - a[nz * j2 + k2]) * inv_dy;
     return d11 * (1 - fs) * (1 - fz) + d21 * fs * (1 - fz) + d12 * (1 - fs) * fz + d22 * fs * fz;
 }
 
 // d/dz at half points (src/array_utils.cpp:265-288 / :215-238)
-__device__ __forceinline__ double gather_zder(const double * __restrict__ a, int ny, int nz, double dz, int jc, int kc, double fy, double fz) {
+__device__ __forceinline__ double gather_zder(const double * __restrict__ a, int ny, int nz, double inv_dz, int jc, int kc, double fy, double fz) {
     int k1;
     double fs;
     stagger(kc, fz, nz, k1, fs);
     const int k2 = wrap_inc(k1, nz), k3 = wrap_inc(k2, nz);
     const int j1 = jc, j2 = wrap_inc(jc, ny);
-    const double d11 = (a[nz * j1 + k2] - a[nz * j1 + k1]) / dz;
-    const double d21 = (a[nz * j2 + k2] - a[nz * j2 + k1]) / dz;
-    const double d12 = (a[nz * j1 + k3] - a[nz * j1 + k2]) / dz;
-    const double d22 = (a[nz * j2 + k3] - a[nz * j2 + k2]) / dz;
+    const double d11 = (a[nz * j1 + k2] - a[nz * j1 + k1]) * inv_dz;
+    const double d21 = (a[nz * j2 + k2] - a[nz * j2 + k1]) * inv_dz;
+    const double d12 = (a[nz * j1 + k3] - a[nz * j1 + k2]) * inv_dz;
+    const double d22 = (a[nz * j2 + k3] - a[nz * j2 + k2]) * inv_dz;
     return d11 * (1 - fy) * (1 - fs) + d21 * fy * (1 - fs) + d12 * (1 - fy) * fs + d22 * fy * fs;
 }
 
@@ -263,7 +266,7 @@ __global__ void k_sort_rank(const Ctl * ctl, int np, const int * __restrict__ ce
 
 struct CellLists {
     const int * start;  // n2 + 1
-    const int * perm;   // np, particle indices grouped by cell
+    const int * perm;   // np, indices grouped by cell; NULL = identity (the value arrays are already in list order)
     const double * fy;
     const double * fz;
 };
@@ -292,7 +295,7 @@ __global__ void k_deposit_charge(const Ctl * ctl, Geom g, CellLists L, const dou
             const int c = (oy ? jm : j) * g.nz + (oz ? km : k);
             const int e = L.start[c + 1];
             for (int s = L.start[c]; s < e; s++) {
-                const int p = L.perm[s];
+                const int p = L.perm ? L.perm[s] : s;
                 const double f1 = L.fy[p], f2 = L.fz[p];
                 const double wy = oy ? f1 : 1 - f1;
                 const double wz = oz ? f2 : 1 - f2;
@@ -331,7 +334,7 @@ __global__ void k_deposit_jx_rho_chi(const Ctl * ctl, Geom g, CellLists L, const
             const int c = (oy ? jm : j) * g.nz + (oz ? km : k);
             const int e = L.start[c + 1];
             for (int s = L.start[c]; s < e; s++) {
-                const int p = L.perm[s];
+                const int p = L.perm ? L.perm[s] : s;
                 const double f1 = L.fy[p], f2 = L.fz[p];
                 const double wy = oy ? f1 : 1 - f1;
                 const double wz = oz ? f2 : 1 - f2;
@@ -395,7 +398,7 @@ __global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const doub
             const int c = jr[ry + 1] * g.nz + kr[rz + 1];
             const int e = L.start[c + 1];
             for (int s = L.start[c]; s < e; s++) {
-                const int p = L.perm[s];
+                const int p = L.perm ? L.perm[s] : s;
                 const double f1 = L.fy[p], f2 = L.fz[p];
                 double wys, wzn, wyn, wzs;
                 // jy_next: staggered in y, node centred in z;  jz_next: node centred in y, staggered in z
@@ -439,57 +442,113 @@ __global__ void __launch_bounds__(FIX_THREADS) k_potential_fixup(const Ctl * ctl
 }
 
 // ------------------------------------------------------------------------------------------------ particle kernels
-
+//
+// Two index spaces:
+//   p  particle id = the caller's order.  Only the state that survives a slice lives here (y z py pz n, + gamma px for
+//      inspection) together with the cell descriptor of (y,z) that the push leaves behind for the cell sort.
+//   s  SLOT in the cell-sorted order of the slice-start positions, perm_b[s] = p.  Everything a slice computes per
+//      particle is stored by slot, so all M iterations stream contiguous memory and a cell's particles are adjacent
+//      (what the tile deposit relies on).  Only two kernels per slice (gamma at the start, push at the end) touch
+//      the p-indexed arrays.
 struct Particles {
     int np;
-    double *y, *z, *py, *pz, *nw;       // persistent state
-    double *gamma, *px;                  // src/containers.h:41-42
-    double *pyn, *pzn;                   // py_next, pz_next
-    int *cell_b, *cell_m;                // cell of (y,z) / of (y_middle,z_middle)
-    int *off_m;                          // (jm - jc + 2) | (km - kc + 2) << 3, minimal-image cell offsets of the half step
-    double *fy_b, *fz_b, *fy_m, *fz_m;   // fractional positions inside that cell
+    // ---- by particle id
+    double *y, *z, *py, *pz, *nw;
+    double *gamma, *px;             // src/containers.h:41-42 (kept for inspection / dumps)
+    int * cell_p;                   // cell of (y,z)
+    double *fy_p, *fz_p;            // fractional position inside it
+    // ---- by slot
+    int * cell_b;                   // copies of the above in slot order
+    double *fy_b, *fz_b;
+    double *y_s, *z_s, *py_s, *pz_s, *nw_s;
+    double *gam, *pxs;              // gamma, px of the current iteration
+    double *pyn, *pzn;              // py_next, pz_next
+    int * cell_m;                   // cell of (y_middle, z_middle)
+    int * off_m;                    // packed minimal-image cell offset of the half step + half-cell bits (see pack_offset)
+    double *fy_m, *fz_m;
     // slice invariants of the B iterations (the reference re-gathers them every iteration, src/System_3d.cpp:419-423,
     // :501-502; (y,z), psi and a_sqr(i) do not change inside the iteration loop)
-    double *q;                           // 1 + psi@p
-    double *ap;                          // a_sqr@p
-    double *t1y, *t1z;                   // dx*0.5*d(a_sqr)/dy@p / (1+psi@p), same for z
-    double *dpy, *dpz;                   // dpsi/dy@p, dpsi/dz@p
+    double *q;                      // 1 + psi@p
+    double *ap;                     // a_sqr@p
+    double *t1y, *t1z;              // dx*0.5*d(a_sqr)/dy@p / (1+psi@p), same for z
+    double *dpy, *dpz;              // dpsi/dy@p, dpsi/dz@p
     double *vjx, *vrho, *vchi, *vjy, *vjz;  // per-particle deposit values
 };
 
-__device__ __forceinline__ void store_currents(const Particles & P, int p, double nw, double gamma, double px) {
+// (oy+2) | (oz+2) << 3 | (fy >= 1/2) << 6 | (fz >= 1/2) << 7 | (kc & 3) << 8
+// oy, oz: minimal-image cell offset of the half step; fy, fz: fraction inside the half-step cell; kc: z index of the
+// slice-start cell (lets a thread that scans a contiguous run of <= 4 source cells tell which one a particle is from)
+__device__ __forceinline__ int pack_offset(int oy, int oz, double fy, double fz, int kc) {
+    return (oy + 2) | ((oz + 2) << 3) | ((fy >= 0.5) ? 64 : 0) | ((fz >= 0.5) ? 128 : 0) | ((kc & 3) << 8);
+}
+
+__device__ __forceinline__ void store_currents(const Particles & P, int s, double nw, double gamma, double px) {
     const double vx = px / gamma;
-    P.vjx[p] = nw * vx / (1 - vx);
-    P.vrho[p] = nw / (1 - vx);
-    P.vchi[p] = -nw / (1 - vx) / gamma;
+    const double w = 1 - vx;
+    P.vjx[s] = nw * vx / w;
+    const double r = nw / w;
+    P.vrho[s] = r;
+    P.vchi[s] = -r / gamma;  // == -nw / (1 - vx) / gamma bit for bit (negation is exact)
+}
+
+// fmod(y, l) then +l if negative (src/System_3d.cpp:668-684), without the fmod call in the common cases: for
+// 0 <= y < l the result is y; for l <= y < 2l it is y - l, which is exact (Sterbenz), i.e. equal to fmod's; for
+// -l < y < 0 fmod returns y and the reference adds l.
+__device__ __forceinline__ double wrap_fast(double y, double l) {
+    if (y >= 0.0) {
+        if (y < l) return y;
+        if (y < 2.0 * l) return y - l;
+    } else if (y > -l) {
+        return y + l;
+    }
+    return wrap_coordinate(y, l);
+}
+
+// after the cell sort of the slice-start positions: copy the particle's slice inputs from id order to slot order
+__global__ void k_particles_to_slots(const Ctl * ctl, Particles P, const int * __restrict__ perm_b) {
+    if (cancelled(ctl)) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.np) return;
+    const int p = perm_b[s];
+    P.cell_b[s] = P.cell_p[p];
+    P.fy_b[s] = P.fy_p[p];
+    P.fz_b[s] = P.fz_p[p];
+    P.y_s[s] = P.y[p];
+    P.z_s[s] = P.z[p];
+    P.py_s[s] = P.py[p];
+    P.pz_s[s] = P.pz[p];
+    P.nw_s[s] = P.nw[p];
 }
 
 // initial gamma, px (src/System_3d.cpp:368-378) + the values deposited at :390-397 + iteration invariants
-__global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ a_sqr3, const double * __restrict__ psi,
-                                  int want_invariants) {
+__global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b, const double * __restrict__ a_sqr3,
+                                  const double * __restrict__ psi, int want_invariants) {
     if (cancelled(ctl)) return;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.np) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.np) return;
     const double * a_sqr = a_sqr3 + (size_t)ctl->slice * g.n2;
-    const int c = P.cell_b[p];
+    const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double fy = P.fy_b[p], fz = P.fz_b[p];
+    const double fy = P.fy_b[s], fz = P.fz_b[s];
     const double a_particle = gather_node(a_sqr, g.ny, g.nz, jc, kc, fy, fz);
     const double psi_particle = gather_node(psi, g.ny, g.nz, jc, kc, fy, fz);
-    const double py = P.py[p], pz = P.pz[p];
-    const double gamma = 0.5 * (1 + py * py + pz * pz + a_particle + (1 + psi_particle) * (1 + psi_particle)) / (1 + psi_particle);
-    const double px = 0.5 * (1 + py * py + pz * pz + a_particle - (1 + psi_particle) * (1 + psi_particle)) / (1 + psi_particle);
+    const double py = P.py_s[s], pz = P.pz_s[s], nw = P.nw_s[s];
+    const double q = 1 + psi_particle;
+    const double gamma = 0.5 * (1 + py * py + pz * pz + a_particle + q * q) / q;
+    const double px = 0.5 * (1 + py * py + pz * pz + a_particle - q * q) / q;
+    const int p = perm_b[s];
     P.gamma[p] = gamma;
     P.px[p] = px;
-    store_currents(P, p, P.nw[p], gamma, px);
+    P.gam[s] = gamma;
+    P.pxs[s] = px;
+    store_currents(P, s, nw, gamma, px);
     if (want_invariants) {
-        const double q = 1 + psi_particle;
-        P.q[p] = q;
-        P.ap[p] = a_particle;
-        P.t1y[p] = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.dy, jc, kc, fy, fz) / q;
-        P.t1z[p] = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.dz, jc, kc, fy, fz) / q;
-        P.dpy[p] = gather_yder(psi, g.ny, g.nz, g.dy, jc, kc, fy, fz);
-        P.dpz[p] = gather_zder(psi, g.ny, g.nz, g.dz, jc, kc, fy, fz);
+        P.q[s] = q;
+        P.ap[s] = a_particle;
+        P.t1y[s] = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz) / q;
+        P.t1z[s] = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz) / q;
+        P.dpy[s] = gather_yder(psi, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz);
+        P.dpz[s] = gather_zder(psi, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz);
     }
 }
 
@@ -504,15 +563,18 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 // predictor: py_next, pz_next (src/System_3d.cpp:416-433), half-step position (:436-443) and its cell descriptor.
 // FAST (sort-free deposit): records the cell offset of the half step instead of counting cell populations, and raises
 // Ctl::fast_fail if a particle leaves the +-1 cell window the tile deposit covers.
+// class of a half step for the presence masks of the tile deposit: cell offset (oy, oz) in [-1,1]^2 and the half-cell bits
+__device__ __host__ __forceinline__ int offset_class(int oy, int oz, int hy, int hz) { return ((oy + 1) * 3 + (oz + 1)) * 4 + hy * 2 + hz; }
+
 template <bool FAST>
 __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
-                                    int * __restrict__ count) {
+                                    int * __restrict__ count, unsigned long long * __restrict__ pmask) {
     if (cancelled(ctl)) return;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.np) return;
-    const int c = P.cell_b[p];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.np) return;
+    const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double fy = P.fy_b[p], fz = P.fz_b[p];
+    const double fy = P.fy_b[s], fz = P.fz_b[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -520,33 +582,36 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     // by lives at (y, z + dz/2), bz at (y + dy/2, z)  (src/System_3d.cpp:180-181)
     const double by_particle = gather4(by, g.nz, jc, wrap_inc(jc, g.ny), ks, wrap_inc(ks, g.nz), fy, fzs);
     const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
-    const double q = P.q[p], gamma = P.gamma[p];
-    double pyn = P.py[p] - P.t1y[p];
-    pyn += g.dx * gamma * P.dpy[p] / q;
+    const double q = P.q[s], gamma = P.gam[s];
+    double pyn = P.py_s[s] - P.t1y[s];
+    pyn += g.dx * gamma * P.dpy[s] / q;
     pyn -= g.dx * bz_particle;
-    double pzn = P.pz[p] - P.t1z[p];
-    pzn += g.dx * gamma * P.dpz[p] / q;
+    double pzn = P.pz_s[s] - P.t1z[s];
+    pzn += g.dx * gamma * P.dpz[s] / q;
     pzn += g.dx * by_particle;
-    P.pyn[p] = pyn;
-    P.pzn[p] = pzn;
-    const double ym = wrap_coordinate(P.y[p] + 0.5 * g.dx * pyn / q, g.ly);
-    const double zm = wrap_coordinate(P.z[p] + 0.5 * g.dx * pzn / q, g.lz);
+    P.pyn[s] = pyn;
+    P.pzn[s] = pzn;
+    const double ym = wrap_fast(P.y_s[s] + 0.5 * g.dx * pyn / q, g.ly);
+    const double zm = wrap_fast(P.z_s[s] + 0.5 * g.dx * pzn / q, g.lz);
     int jm, km;
     double f1, f2;
     locate(ym, g.dy, g.ny, jm, f1);
     locate(zm, g.dz, g.nz, km, f2);
     const int cm = jm * g.nz + km;
-    P.cell_m[p] = cm;
-    P.fy_m[p] = f1;
-    P.fz_m[p] = f2;
+    P.cell_m[s] = cm;
+    P.fy_m[s] = f1;
+    P.fz_m[s] = f2;
     if (FAST) {
         const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
-        // !(x <= 1) also catches the NaN positions of a blown-up run
+        // !(f >= 0) catches the NaN positions of a blown-up run
         if (oy < -1 || oy > 1 || oz < -1 || oz > 1 || !(f1 >= 0.0) || !(f2 >= 0.0)) {
             atomicExch(&ctl->fast_fail, 1);
-            P.off_m[p] = 2 | (2 << 3);
+            P.off_m[s] = pack_offset(0, 0, 0.0, 0.0, kc);
         } else {
-            P.off_m[p] = (oy + 2) | ((oz + 2) << 3);
+            P.off_m[s] = pack_offset(oy, oz, f1, f2, kc);
+            // which (offset, half-cell) classes occur in this source cell: lets the deposit skip cells that cannot
+            // contribute to a target (integer OR: order independent)
+            atomicOr(&pmask[c], 1ull << offset_class(oy, oz, f1 >= 0.5 ? 1 : 0, f2 >= 0.5 ? 1 : 0));
         }
     } else {
         atomicAdd(&count[cm], 1);
@@ -557,45 +622,51 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
 // runs concurrently with the psi_middle solve.
 __global__ void k_particles_correct_gamma(const Ctl * ctl, Geom g, Particles P) {
     if (cancelled(ctl)) return;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.np) return;
-    const double nw = P.nw[p], pyn = P.pyn[p], pzn = P.pzn[p], py = P.py[p], pz = P.pz[p];
-    const double q = P.q[p], a_particle = P.ap[p];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.np) return;
+    const double nw = P.nw_s[s], pyn = P.pyn[s], pzn = P.pzn[s], py = P.py_s[s], pz = P.pz_s[s];
+    const double q = P.q[s], a_particle = P.ap[s];
     const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
     const double gamma = 0.5 * (1 + p_squared + a_particle + q * q) / q;
     const double px = 0.5 * (1 + p_squared + a_particle - q * q) / q;
-    P.gamma[p] = gamma;
-    P.px[p] = px;
-    store_currents(P, p, nw, gamma, px);
+    P.gam[s] = gamma;
+    P.pxs[s] = px;
+    store_currents(P, s, nw, gamma, px);
 }
 
 // values for the jy/jz deposit: n py_next / (1 + psi_middle@(y_middle, z_middle))  (src/System_3d.cpp:480-486)
 __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle) {
     if (cancelled(ctl)) return;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.np) return;
-    const int cm = P.cell_m[p];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.np) return;
+    const int cm = P.cell_m[s];
     const int jm = cm / g.nz, km = cm - jm * g.nz;
-    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[p], P.fz_m[p]);
-    const double nw = P.nw[p];
-    P.vjy[p] = nw * P.pyn[p] / (1 + psi_particle);
-    P.vjz[p] = nw * P.pzn[p] / (1 + psi_particle);
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[s], P.fz_m[s]);
+    const double nw = P.nw_s[s];
+    const double w = 1 + psi_particle;
+    P.vjy[s] = nw * P.pyn[s] / w;
+    P.vjz[s] = nw * P.pzn[s] / w;
 }
 
 // py <- py_next, pz <- pz_next (src/System_3d.cpp:593-598), coordinate advance with psi_middle gathered at (y,z)
-// (:601-608), new cell descriptor + population count for the next slice's lists
-__global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle, int * __restrict__ count) {
+// (:601-608), new cell descriptor + population count for the next slice's lists; back to particle-id order
+__global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b, const double * __restrict__ psi_middle,
+                                    int * __restrict__ count) {
     if (cancelled(ctl)) return;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P.np) return;
-    const int c = P.cell_b[p];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.np) return;
+    const int p = perm_b[s];
+    const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jc, kc, P.fy_b[p], P.fz_b[p]);
-    const double py = P.pyn[p], pz = P.pzn[p];
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jc, kc, P.fy_b[s], P.fz_b[s]);
+    const double py = P.pyn[s], pz = P.pzn[s];
     P.py[p] = py;
     P.pz[p] = pz;
-    const double y = wrap_coordinate(P.y[p] + g.dx * py / (1 + psi_particle), g.ly);
-    const double z = wrap_coordinate(P.z[p] + g.dx * pz / (1 + psi_particle), g.lz);
+    P.gamma[p] = P.gam[s];
+    P.px[p] = P.pxs[s];
+    const double w = 1 + psi_particle;
+    const double y = wrap_fast(P.y_s[s] + g.dx * py / w, g.ly);
+    const double z = wrap_fast(P.z_s[s] + g.dx * pz / w, g.lz);
     P.y[p] = y;
     P.z[p] = z;
     int jn, kn;
@@ -603,9 +674,9 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
     locate(y, g.dy, g.ny, jn, f1);
     locate(z, g.dz, g.nz, kn, f2);
     const int cn = jn * g.nz + kn;
-    P.cell_b[p] = cn;
-    P.fy_b[p] = f1;
-    P.fz_b[p] = f2;
+    P.cell_p[p] = cn;
+    P.fy_p[p] = f1;
+    P.fz_p[p] = f2;
     atomicAdd(&count[cn], 1);
 }
 
@@ -629,11 +700,11 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
     const int j = t / g.nz, k = t - j * g.nz;
     const size_t off = (size_t)i * g.n2 + t;
     const double ps = psi[t];
-    if (i < g.nx - 1) o.ex3[off] = (ps - psi_prev[t]) / g.dx;
+    if (i < g.nx - 1) o.ex3[off] = (ps - psi_prev[t]) * g.inv_dx;
     const double b_y = b_is_zero ? 0.0 : by[t];
     const double b_z = b_is_zero ? 0.0 : bz[t];
-    o.ey3[off] = -(psi[wrap_inc(j, g.ny) * g.nz + k] - ps) / g.dy + b_z;
-    o.ez3[off] = -(psi[j * g.nz + wrap_inc(k, g.nz)] - ps) / g.dz - b_y;
+    o.ey3[off] = -(psi[wrap_inc(j, g.ny) * g.nz + k] - ps) * g.inv_dy + b_z;
+    o.ez3[off] = -(psi[j * g.nz + wrap_inc(k, g.nz)] - ps) * g.inv_dz - b_y;
     if (!b_is_zero) {
         o.by3[off] = b_y;
         o.bz3[off] = b_z;
@@ -658,22 +729,22 @@ __global__ void k_next_slice(Ctl * ctl) {
 }
 
 // ------------------------------------------------------------------------------------------------ sort-free tile deposit
-// Deterministic deposition without sorting the half-step positions.  A block owns a TILE x TILE patch of grid nodes;
-// ONE THREAD PER SOURCE CELL of the patch plus a halo walks that cell's particles (the cell lists of the slice-start
-// positions, built once per slice).  A particle's target cell on the output grid is  source cell + offset, with the
-// offset in a small window (0 for deposits at (y,z); [-1,1] for the half-step position, one more on the low side for the
-// half-cell staggered jy/jz grids).  Contributions are first reduced per TARGET CELL into four "corner sums"
-// (the four nodes a CIC particle of that cell touches, src/array_utils.cpp:75-82) kept in shared memory.  The reduction
-// runs in PHASES, one per offset: within a phase the map source cell -> target cell is a bijection, so every target cell
-// has exactly one owner thread, which adds its particles in list order with plain (non-atomic) adds; phases follow each
-// other in a fixed order with a barrier in between.  Finally each node sums the corner sums of its four neighbouring
-// target cells, again in a fixed order.  No floating-point atomics, no dependence on scheduling: bit-reproducible.
-// Halo cells are processed redundantly by neighbouring blocks (identical arithmetic, identical bits).
+// Deterministic deposition without sorting the half-step positions.  A block owns a TILE x TILE patch of grid nodes and
+// runs ONE THREAD PER TARGET CELL of the patch (plus one halo row / column below it).  A particle's target cell on an
+// output grid is  source cell + offset, where the source cell is its cell at the start of the slice (the slot order
+// groups particles by that cell, so a cell's particles are one contiguous range) and the offset lies in a small
+// window: 0 for deposits at (y,z); [-1,1] for the half-step position, one cell more for the half-cell staggered jy / jz
+// grids.  The thread scans the source cells that can reach its target cell in a fixed order, picks the particles whose
+// packed offset code (written by the predictor) points at it, and adds their four CIC corner contributions
+// (src/array_utils.cpp:75-82) in slot order into four private "corner sums".  After one barrier every node sums the
+// corner sums of its four neighbouring target cells, again in a fixed order.  No floating-point atomics, no dependence on
+// scheduling: bit-reproducible.  The halo target cells are recomputed by the neighbouring block (same arithmetic, same bits).
 constexpr int TILE = 16;
+constexpr int TILE_ACC = TILE + 1;
 constexpr int TILE_MAX_OUT = 3;
 
 struct TileOutput {
-    const double * val;    // per-particle value
+    const double * val;    // per-particle value (slot order)
     double sign;           // +1 / -1 (charge deposits use -n)
     int at_mid;            // 1: deposit at the half-step position (fy_m, fz_m, off_m), 0: at (y,z) (fy_b, fz_b)
     int stag_y, stag_z;    // output grid origin shifted by +dy/2 / +dz/2 (jy_next / jz_next, src/System_3d.cpp:190-193)
@@ -685,8 +756,13 @@ struct TileOutput {
 
 struct TileJob {
     int nout;
+    int at_mid;                        // all outputs of a job share the position set
+    int wy_lo, wy_hi, wz_lo, wz_hi;    // window of source cells relative to the target cell, union over the outputs
     TileOutput o[TILE_MAX_OUT];
     const double *jxb3, *rhob3, *rho_ion;  // for bg_mode 1
+    const double *psi_mid, *nw;            // YZ_INLINE jobs
+    const unsigned long long * pmask;      // at_mid jobs: per source cell, which offset classes occur (see offset_class)
+    unsigned long long need[16];           // at_mid jobs: classes that reach the target from window position (dy+1)*4 + (dz+1)
 };
 
 __device__ __forceinline__ int mod_wrap(int j, int n) {
@@ -694,105 +770,113 @@ __device__ __forceinline__ int mod_wrap(int j, int n) {
     return j < 0 ? j + n : j;
 }
 
-// HL / HH: halo of source cells below / above the patch.  Launch with blockDim = (TILE+HL+HH, TILE+HL+HH).
-template <int HL, int HH, bool FINAL_PASS>
-__global__ void __launch_bounds__((TILE + HL + HH) * (TILE + HL + HH))
-    k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, const int * __restrict__ perm, Particles P, TileJob job) {
+// YZ_INLINE: the job is the (jy_next, jz_next) pair and the deposited values n py_next / (1 + psi_middle@particle),
+// n pz_next / (1 + psi_middle@particle) (src/System_3d.cpp:483-485) are formed here instead of being stored by a
+// separate particle kernel; o[0].val / o[1].val then hold py_next / pz_next and job.psi_mid, job.nw are used.
+template <int NOUT, bool FINAL_PASS, bool YZ_INLINE>
+__global__ void __launch_bounds__(TILE_ACC * TILE_ACC)
+    k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     if (FINAL_PASS) {
         if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
     } else if (cancelled(ctl)) {
         return;
     }
-    constexpr int ACC = TILE + 1;
-    __shared__ double acc[TILE_MAX_OUT * ACC * ACC * 4];
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int nthreads = blockDim.x * blockDim.y;
-    for (int t = tid; t < job.nout * ACC * ACC * 4; t += nthreads) acc[t] = 0.0;
-
+    __shared__ double acc[NOUT * TILE_ACC * TILE_ACC * 4];
+    const int ay = threadIdx.y, az = threadIdx.x;
     const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
-    const int jb = mod_wrap(j0 - HL + (int)threadIdx.y, g.ny);
-    const int kb = mod_wrap(k0 - HL + (int)threadIdx.x, g.nz);
-    const int cell = jb * g.nz + kb;
-    const int s0 = start[cell], s1 = start[cell + 1];
-    __syncthreads();
-
-    for (int a = 0; a < job.nout; a++) {
-        const TileOutput & o = job.o[a];
-        const double * __restrict__ val = o.val;
-        const double * __restrict__ fyv = o.at_mid ? P.fy_m : P.fy_b;
-        const double * __restrict__ fzv = o.at_mid ? P.fz_m : P.fz_b;
-        const int wlo_y = (o.at_mid ? -1 : 0) - o.stag_y, whi_y = o.at_mid ? 1 : 0;
-        const int wlo_z = (o.at_mid ? -1 : 0) - o.stag_z, whi_z = o.at_mid ? 1 : 0;
-        // which offsets occur among this cell's particles (bit = (oy+2)*4 + (oz+2))
-        unsigned mask = 0;
-        for (int s = s0; s < s1; s++) {
-            const int p = perm[s];
-            int oy = 0, oz = 0;
-            if (o.at_mid) {
-                const int code = P.off_m[p];
-                oy = (code & 7) - 2;
-                oz = ((code >> 3) & 7) - 2;
-            }
-            if (o.stag_y && fyv[p] < 0.5) oy -= 1;
-            if (o.stag_z && fzv[p] < 0.5) oz -= 1;
-            mask |= 1u << ((oy + 2) * 4 + (oz + 2));
-        }
-        double * acc_a = acc + a * ACC * ACC * 4;
-        for (int oy = wlo_y; oy <= whi_y; oy++) {
-            for (int oz = wlo_z; oz <= whi_z; oz++) {
-                const int ay = (int)threadIdx.y - HL + 1 + oy, az = (int)threadIdx.x - HL + 1 + oz;
-                if (((mask >> ((oy + 2) * 4 + (oz + 2))) & 1u) && ay >= 0 && ay < ACC && az >= 0 && az < ACC) {
-                    double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
-                    for (int s = s0; s < s1; s++) {
-                        const int p = perm[s];
-                        int py_ = 0, pz_ = 0;
-                        if (o.at_mid) {
-                            const int code = P.off_m[p];
-                            py_ = (code & 7) - 2;
-                            pz_ = ((code >> 3) & 7) - 2;
-                        }
-                        double ty = fyv[p], tz = fzv[p];
-                        if (o.stag_y) {
-                            if (ty < 0.5) {
-                                py_ -= 1;
-                                ty += 0.5;
-                            } else {
-                                ty -= 0.5;
-                            }
-                        }
-                        if (o.stag_z) {
-                            if (tz < 0.5) {
-                                pz_ -= 1;
-                                tz += 0.5;
-                            } else {
-                                tz -= 0.5;
-                            }
-                        }
-                        if (py_ != oy || pz_ != oz) continue;
-                        const double v = o.sign * val[p];
-                        c00 += v * (1 - ty) * (1 - tz);
-                        c10 += v * ty * (1 - tz);
-                        c01 += v * (1 - ty) * tz;
-                        c11 += v * ty * tz;
-                    }
-                    double * t4 = acc_a + (ay * ACC + az) * 4;
-                    t4[0] += c00;
-                    t4[1] += c10;
-                    t4[2] += c01;
-                    t4[3] += c11;
-                }
-                __syncthreads();
-            }
-        }
+    const int jt = j0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped target cell
+    const double * __restrict__ fyv = job.at_mid ? P.fy_m : P.fy_b;
+    const double * __restrict__ fzv = job.at_mid ? P.fz_m : P.fz_b;
+    const int * __restrict__ code_v = P.off_m;
+    const int at_mid = job.at_mid;
+    int stag_y_bits = 0, stag_z_bits = 0;
+#pragma unroll
+    for (int a = 0; a < NOUT; a++) {
+        stag_y_bits |= (job.o[a].stag_y ? 1 : 0) << a;
+        stag_z_bits |= (job.o[a].stag_z ? 1 : 0) << a;
     }
 
+    double c00[NOUT], c10[NOUT], c01[NOUT], c11[NOUT];
+#pragma unroll
+    for (int a = 0; a < NOUT; a++) c00[a] = c10[a] = c01[a] = c11[a] = 0.0;
+
+    // particle s sits (ry, rz) cells above the target cell (hy / hz: upper half of its cell)
+    auto visit = [&](int s, int ry, int rz, int hy, int hz) {
+        if ((ry | rz) & ~1) return;  // not within [0,1] x [0,1]: cannot reach this target on any grid flavour
+        int mask = 0;
+#pragma unroll
+        for (int a = 0; a < NOUT; a++) {
+            // on a staggered grid a particle in the lower half of its cell belongs to the staggered cell below
+            const int need_y = (stag_y_bits >> a) & (hy ^ 1), need_z = (stag_z_bits >> a) & (hz ^ 1);
+            if (ry == need_y && rz == need_z) mask |= 1 << a;
+        }
+        if (!mask) return;
+        const double fy = fyv[s], fz = fzv[s];
+        double w = 1.0, nw = 0.0;
+        if (YZ_INLINE) {
+            // psi_middle at the particle: its own (unstaggered) half-step cell is (jt + ry, kt + rz)
+            int jm = jt + ry, km = kt + rz;
+            jm += (jm < 0) ? g.ny : 0;
+            jm -= (jm >= g.ny) ? g.ny : 0;
+            km += (km < 0) ? g.nz : 0;
+            km -= (km >= g.nz) ? g.nz : 0;
+            w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
+            nw = job.nw[s];
+        }
+#pragma unroll
+        for (int a = 0; a < NOUT; a++) {
+            if (!((mask >> a) & 1)) continue;
+            const TileOutput & o = job.o[a];
+            const double ty = o.stag_y ? (hy ? fy - 0.5 : fy + 0.5) : fy;
+            const double tz = o.stag_z ? (hz ? fz - 0.5 : fz + 0.5) : fz;
+            const double v = YZ_INLINE ? nw * o.val[s] / w : o.sign * o.val[s];
+            c00[a] += v * (1 - ty) * (1 - tz);
+            c10[a] += v * ty * (1 - tz);
+            c01[a] += v * (1 - ty) * tz;
+            c11[a] += v * ty * tz;
+        }
+    };
+
+    int jb = mod_wrap(jt + job.wy_lo, g.ny);
+    const int kb0 = mod_wrap(kt + job.wz_lo, g.nz);
+    for (int dy_ = job.wy_lo; dy_ <= job.wy_hi; dy_++) {
+        int kb = kb0;
+        for (int dz_ = job.wz_lo; dz_ <= job.wz_hi; dz_++) {
+            const int cell = jb * g.nz + kb;
+            kb = wrap_inc(kb, g.nz);
+            if (at_mid) {
+                // skip source cells that hold no particle of a class that can reach this target from this position
+                if (!(job.pmask[cell] & job.need[(dy_ + 1) * 4 + (dz_ + 1)])) continue;
+                const int s1 = start[cell + 1];
+                for (int s = start[cell]; s < s1; s++) {
+                    const int code = code_v[s];
+                    visit(s, dy_ + (code & 7) - 2, dz_ + ((code >> 3) & 7) - 2, (code >> 6) & 1, (code >> 7) & 1);
+                }
+            } else {
+                const int s1 = start[cell + 1];
+                for (int s = start[cell]; s < s1; s++) visit(s, dy_, dz_, 1, 1);
+            }
+        }
+        jb = wrap_inc(jb, g.ny);
+    }
+#pragma unroll
+    for (int a = 0; a < NOUT; a++) {
+        double * t4 = acc + ((a * TILE_ACC + ay) * TILE_ACC + az) * 4;
+        t4[0] = c00[a];
+        t4[1] = c10[a];
+        t4[2] = c01[a];
+        t4[3] = c11[a];
+    }
+    __syncthreads();
+
     // nodes of the patch: own cell's (1-fy)(1-fz) sum, then the y-, z- and diagonal neighbours' sums, fixed order
-    if ((int)threadIdx.y < TILE && (int)threadIdx.x < TILE) {
-        const int j = j0 + threadIdx.y, k = k0 + threadIdx.x;
+    if (ay >= 1 && az >= 1) {
+        const int j = jt, k = kt;
         if (j < g.ny && k < g.nz) {
             const int t = j * g.nz + k;
             const size_t off3 = (size_t)ctl->slice * g.n2 + t;
-            for (int a = 0; a < job.nout; a++) {
+#pragma unroll
+            for (int a = 0; a < NOUT; a++) {
                 const TileOutput & o = job.o[a];
                 double v = 0.0;
                 if (o.bg_mode == 1) {
@@ -802,12 +886,11 @@ __global__ void __launch_bounds__((TILE + HL + HH) * (TILE + HL + HH))
                 } else if (o.bg_mode == 2 && o.bg3) {
                     v = o.bg3[off3];
                 }
-                const double * acc_a = acc + a * ACC * ACC * 4;
-                const int ay = threadIdx.y + 1, az = threadIdx.x + 1;
-                v += acc_a[(ay * ACC + az) * 4 + 0];
-                v += acc_a[((ay - 1) * ACC + az) * 4 + 1];
-                v += acc_a[(ay * ACC + az - 1) * 4 + 2];
-                v += acc_a[((ay - 1) * ACC + az - 1) * 4 + 3];
+                const double * acc_a = acc + a * TILE_ACC * TILE_ACC * 4;
+                v += acc_a[(ay * TILE_ACC + az) * 4 + 0];
+                v += acc_a[((ay - 1) * TILE_ACC + az) * 4 + 1];
+                v += acc_a[(ay * TILE_ACC + az - 1) * 4 + 2];
+                v += acc_a[((ay - 1) * TILE_ACC + az - 1) * 4 + 3];
                 o.out[o.out_3d ? off3 : (size_t)t] = v;
             }
         }

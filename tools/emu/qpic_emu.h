@@ -163,6 +163,11 @@ static inline int atomicOr(int * addr, int v) {
     *addr = old | v;
     return old;
 }
+static inline unsigned long long atomicOr(unsigned long long * addr, unsigned long long v) {
+    unsigned long long old = *addr;
+    *addr = old | v;
+    return old;
+}
 static inline int atomicMax(int * addr, int v) {
     int old = *addr;
     if (v > old) *addr = v;
