@@ -136,12 +136,15 @@ long qpic_fast_path_aborts(const qpic_ctx * ctx);
 /* runs up to nslices slices eagerly with a CUDA event after every kernel; report = lines "kernel count total_ms" */
 int qpic_profile_slices(qpic_ctx * ctx, int nslices, char * report, size_t report_len);
 
-/* ---- streaming transfers for callers whose arrays live in host memory (System_3d's array3d members).  Asynchronous on
- * the context's stream: call qpic_synchronize before touching the host buffers.  Pinned buffers give full PCIe rate. */
+/* ---- streaming transfers for callers whose arrays live in host memory (System_3d's array3d members).  They run on a
+ * separate copy stream and overlap the sweep: an upload is waited for by every slice queued after the call, a download
+ * waits for every slice queued before the call.  Call qpic_wait_transfers (or qpic_synchronize) before touching the
+ * host buffers.  Pinned buffers (qpic_alloc_pinned) give full PCIe rate and true asynchrony. */
 /* a_sqr(first_slice .. first_slice+count-1, :, :)  (the laser envelope is read one slice at a time, src/System_3d.cpp:371) */
 int qpic_upload_a_sqr_slices(qpic_ctx * ctx, int first_slice, int count, const double * src);
 /* rows [first_slice, first_slice+count) of a 3-D field, e.g. what deposit_wakefield_to_bunch / write_array read afterwards */
 int qpic_download_slices3d(qpic_ctx * ctx, qpic_field3d f, int first_slice, int count, double * dst);
+int qpic_wait_transfers(qpic_ctx * ctx);
 void * qpic_alloc_pinned(size_t bytes);
 void qpic_free_pinned(void * p);
 

@@ -46,6 +46,8 @@ struct qpic_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // second branch of the per-iteration fork (see enqueue_slice_full)
+    cudaStream_t copy_stream = nullptr;  // streaming transfers (a_sqr slabs in, field slabs out) overlap the sweep
+    cudaEvent_t ev_copy = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     int ev_next = 0;
     bool fast_capable = false;  // sort-free tile deposits usable for this grid
@@ -835,6 +837,11 @@ void qpic_destroy(qpic_ctx * c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -849,6 +856,8 @@ static int create_impl(qpic_ctx * c) {
     QPIC_CUDA(c, cudaSetDevice(p.device));
     QPIC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     QPIC_CUDA(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    QPIC_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    QPIC_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     for (int e = 0; e < 64; e++) {
         cudaEvent_t ev;
         QPIC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1143,6 +1152,7 @@ int qpic_solve_wakefield(qpic_ctx * c) {
 int qpic_synchronize(qpic_ctx * c) {
     if (!c) return QPIC_ERR_INVALID;
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     if (c->began && !c->finished) return resolve(c);
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     return QPIC_OK;
@@ -1317,7 +1327,10 @@ int qpic_upload_a_sqr_slices(qpic_ctx * c, int first_slice, int count, const dou
     if (first_slice < 0 || count < 0 || first_slice + count > c->g.nx) return fail(c, QPIC_ERR_INVALID, "slice range out of bounds");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
-    QPIC_CUDA(c, cudaMemcpyAsync(c->f3[QPIC_F3_ASQR] + n2 * first_slice, src, sizeof(double) * n2 * count, cudaMemcpyHostToDevice, c->stream));
+    // on the copy stream, so that it overlaps slices already queued; slices queued AFTER this call wait for it
+    QPIC_CUDA(c, cudaMemcpyAsync(c->f3[QPIC_F3_ASQR] + n2 * first_slice, src, sizeof(double) * n2 * count, cudaMemcpyHostToDevice, c->copy_stream));
+    QPIC_CUDA(c, cudaEventRecord(c->ev_copy, c->copy_stream));
+    QPIC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     return QPIC_OK;
 }
 
@@ -1327,7 +1340,17 @@ int qpic_download_slices3d(qpic_ctx * c, qpic_field3d f, int first_slice, int co
     if (!c->f3[f]) return fail(c, QPIC_ERR_STATE, "this array is not resident (see keep_slices_3d / qpic_upload_bunch_sources)");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
-    QPIC_CUDA(c, cudaMemcpyAsync(dst, c->f3[f] + n2 * first_slice, sizeof(double) * n2 * count, cudaMemcpyDeviceToHost, c->stream));
+    // waits for the slices queued so far, then runs on the copy stream while later slices compute
+    QPIC_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+    QPIC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, c->f3[f] + n2 * first_slice, sizeof(double) * n2 * count, cudaMemcpyDeviceToHost, c->copy_stream));
+    return QPIC_OK;
+}
+
+int qpic_wait_transfers(qpic_ctx * c) {
+    if (!c) return QPIC_ERR_INVALID;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     return QPIC_OK;
 }
 

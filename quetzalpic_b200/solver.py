@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "qpic_upload_field2d", "qpic_particle_count", "qpic_download_particles", "qpic_upload_particles",
     "qpic_set_current_slice", "qpic_solve_poisson_host", "qpic_solve_helmholtz_pair_host", "qpic_last_step_stats",
     "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
-    "qpic_fast_path_aborts",
+    "qpic_fast_path_aborts", "qpic_wait_transfers",
 ]
 
 
@@ -105,6 +105,7 @@ class QpicLibrary:
         L.qpic_alloc_pinned.restype = vp
         L.qpic_free_pinned.argtypes = [vp]
         L.qpic_free_pinned.restype = None
+        L.qpic_wait_transfers.argtypes = [vp]
         L.qpic_fast_path_aborts.argtypes = [vp]
         L.qpic_fast_path_aborts.restype = ctypes.c_long
         self.L = L
@@ -319,6 +320,9 @@ class WakefieldSolver:
         assert out_block.flags["C_CONTIGUOUS"] and out_block.dtype == np.float64
         self._check(self.lib.L.qpic_download_slices3d(self.ctx, self._field3d_index(name, per_slice), int(first_slice),
                                                       int(out_block.shape[0]), out_block.ctypes.data))
+
+    def wait_transfers(self):
+        self._check(self.lib.L.qpic_wait_transfers(self.ctx))
 
     # -- state
     def field2d(self, name):
