@@ -49,19 +49,33 @@ def algorithmic_bytes_per_slice(N, P, M):
 
 # algorithmic bytes of ONE launch of each kernel (DESIGN.md section "kernels"): doubles moved per cell (N) / particle (P)
 KERNEL_BYTES = {
+    # sort-free tile deposits (fast path); charge: slot arrays fy fz n (+ packed offset code, presence mask) -> one grid
+    "k_tile_deposit_charge": lambda N, P: 8.0 * (2 * N + 3 * P),
+    "k_tile_deposit_charge_mid": lambda N, P: 8.0 * (3 * N + 3.5 * P),
+    "k_tile_deposit_jx": lambda N, P: 8.0 * (2 * N + 3 * P),
+    "k_tile_deposit_jx_rho_chi": lambda N, P: 8.0 * (5 * N + 5 * P),
+    "k_tile_deposit_rho_chi": lambda N, P: 8.0 * (3 * N + 4 * P),
+    "k_tile_deposit_jy_jz": lambda N, P: 8.0 * (4 * N + 5.5 * P),  # fy fz py_next pz_next n + code; psi_middle, mask; 2 grids out
+    # sorted (general) path
     "k_deposit_charge": lambda N, P: 8.0 * (2 * N + 3 * P),
+    "k_deposit_jx_rho_chi": lambda N, P: 8.0 * (3 * N + 5 * P),
+    "k_deposit_jx": lambda N, P: 8.0 * (2 * N + 3 * P),
+    "k_deposit_rho_chi": lambda N, P: 8.0 * (3 * N + 4 * P),
+    "k_deposit_jy_jz": lambda N, P: 8.0 * (2 * N + 4 * P),
+    "k_particles_currents_yz": lambda N, P: 8.0 * (7.5 * P),
+    # transforms
     "k_fft_rows_r2c": lambda N, P: 8.0 * (2 * N),
     "k_fft_rows_c2r": lambda N, P: 8.0 * (2 * N),
-    "k_fft_cols_solve": lambda N, P: 8.0 * (3 * N),  # mean of the half (2N) and full (4N) spectrum launches
+    "k_fft_cols_solve": lambda N, P: 8.0 * (3.5 * N),  # mean of the half (2N + N/2 table) and full (4N + N table) spectrum launches
     "k_potential_fixup": lambda N, P: 8.0 * (2 * N),
-    "k_particles_gamma": lambda N, P: 8.0 * (16 * P),
-    "k_deposit_jx_rho_chi": lambda N, P: 8.0 * (3 * N + 5 * P),
-    "k_particles_predict": lambda N, P: 8.0 * (14 * P),
-    "k_particles_correct": lambda N, P: 8.0 * (14 * P),
-    "k_deposit_jy_jz": lambda N, P: 8.0 * (2 * N + 4 * P),
     "k_fft_rows_b_forward": lambda N, P: 8.0 * (9 * N),
     "k_fft_rows_b_backward": lambda N, P: 8.0 * (4 * N),
-    "k_particles_advance": lambda N, P: 8.0 * (12 * P),
+    # particles
+    "k_particles_gamma": lambda N, P: 8.0 * (17.5 * P),
+    "k_particles_predict": lambda N, P: 8.0 * (18.5 * P),
+    "k_particles_correct_gamma": lambda N, P: 8.0 * (12 * P),
+    "k_particles_advance": lambda N, P: 8.0 * (15 * P),
+    "k_particles_to_slots": lambda N, P: 8.0 * (15.5 * P),
     "k_end_of_slice": lambda N, P: 8.0 * (17 * N),
     "k_scan_chunk_sums": lambda N, P: 4.0 * N,
     "k_scan_sums": lambda N, P: 8.0 * (N / 1024),

@@ -1,0 +1,199 @@
+// quasistatic_pic_b200 <input.toml> -- drop-in driver for laser-wake runs of QuetzalPIC on one B200 (C++14 host code over
+// the qpic_b200 C ABI).
+//
+// Keeps the reference's process-level contracts: the CLI (reference src/quasistatic_pic.cpp:8-46),
+// the TOML keys / defaults / stdout echo (src/Config_reader.cpp), the banner printed by System_3d's constructor
+// (src/System_3d.cpp:91-152), the per-iteration messages of System_3d::run (:199-236) and the output datasets
+// (src/Output_writer.cpp; see output_npy.h for the file format).  solve_wakefield itself runs on the device.
+// Beam drivers ([bunch]) need the bunch deposit / push path, which is a "next" row: such inputs are refused.
+#include <chrono>
+#include <cstdio>
+#include <iostream>
+#include <vector>
+
+#include "../include/qpic_b200.h"
+#include "config.h"
+#include "output_npy.h"
+
+using namespace qhost;
+
+static std::string memory_formatter(long bytes) {  // "{:5.1f} {}" with binary prefixes (src/System_3d.cpp:19-28)
+    double res = static_cast<double>(bytes);
+    const char * prefixes[] = {"  B", "KiB", "MiB", "GiB", "TiB", "PiB"};
+    int index = 0;
+    while (res > 1024) {
+        res /= 1024;
+        index++;
+    }
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%5.1f %s", res, prefixes[index]);
+    return buf;
+}
+
+static void check(int rc, qpic_ctx * ctx) {
+    if (rc != QPIC_OK) throw std::runtime_error(qpic_last_error(ctx));
+}
+
+int main(int argc, char const * argv[]) {
+    if (argc < 2) {
+        std::cout << "Provide a path to the input .toml file as the first argument. Aborting." << std::endl;
+        return -1;
+    }
+    if (argc > 2) {
+        std::cout << "WARNING: more than one command-line argument are not supported. Additional arguments will be ignored" << std::endl;
+    }
+    const std::string config_filename = argv[1];
+    std::ostream & out = std::cout;
+    out << "----------------------------------------" << std::endl;
+    const System_parameters params = Config_reader(config_filename, out).get_parameters();
+    out << "----------------------------------------" << std::endl;
+    out << "Device: one CUDA GPU through libqpic_b200 (ABI " << qpic_abi_version() << ")" << std::endl;
+    out << "----------------------------------------" << std::endl;
+    const auto t_begin = std::chrono::high_resolution_clock::now();
+
+    if (params.magnetic_field_iterations < 0) throw std::invalid_argument("Magnetic field iterations should be non-negative");
+    if (params.ppcy <= 0) throw std::invalid_argument("ppcy should be positive");
+    if (params.ppcz <= 0) throw std::invalid_argument("ppcz should be positive");
+
+    // System_3d::System_3d (src/System_3d.cpp:87-104)
+    const int nx = static_cast<int>(params.lx / params.dx), ny = static_cast<int>(params.ly / params.dy), nz = static_cast<int>(params.lz / params.dz);
+    out << "Spatial dimensions:  [" << nx << ", " << ny << ", " << nz << "]" << std::endl;
+    const double dx = params.lx / nx, dy = params.ly / ny, dz = params.lz / nz;
+    out << "Steps:               [" << fmt_double(dx) << ", " << fmt_double(dy) << ", " << fmt_double(dz) << "]" << std::endl;
+    out << "Simulation box size: [" << fmt_double(params.lx) << ", " << fmt_double(params.ly) << ", " << fmt_double(params.lz) << "]" << std::endl;
+    const int time_iterations = static_cast<int>(params.t_end / params.dt) + 1;
+    const double t_end = params.dt * (time_iterations - 1);
+    out << "Timestep: " << fmt_double(params.dt) << ", end time: " << fmt_double(t_end) << ", iterations: " << time_iterations << std::endl;
+    out << "----------------------------------------" << std::endl;
+    const Plasma_units units(params.base_frequency_SI);
+    out << "PLASMA UNITS\n";
+    out << "Frequency " << fmt_g4(units.frequency) << " rad/s\n";
+    out << "Density " << fmt_g4(units.density) << " cm^-3\n";
+    out << "Wavelength " << fmt_g4(units.wavelength) << " cm\n";
+    out << "Schwinger field in plasma units: " << fmt_g4(units.field_schwinger) << "\n";
+    out << "----------------------------------------" << std::endl;
+    out << "REGISTERED SPECIES\n";
+    for (const auto & s : params.species.get_species()) {
+        out << (s.is_photon ? s.name + " (is photon)" : s.name) << ": charge " << fmt_g4(s.charge) << ", mass " << fmt_g4(s.mass)
+            << ", charge_to_mass_ratio " << fmt_g4(s.charge_to_mass_ratio) << "\n";
+    }
+    out << "----------------------------------------" << std::endl;
+
+    if (params.bunch_count > 0) {
+        out << "This driver covers the plasma-wake path; [bunch] drivers need the bunch deposit / push path, which is not built yet." << std::endl;
+        return 2;
+    }
+
+    // plasma macro-particle lattice, System_3d::count_wake_particles / init_wake_particles (src/System_3d.cpp:708-748)
+    std::vector<double> py, pz, pn;
+    for (int i = 0; i < params.ppcy * ny; i++) {
+        for (int j = 0; j < params.ppcz * nz; j++) {
+            const double y = (i + 0.5) * dy / params.ppcy;
+            const double z = (j + 0.5) * dz / params.ppcz;
+            const double value = params.plasma_profile(y, z);
+            if (value != 0) {
+                py.push_back(y);
+                pz.push_back(z);
+                pn.push_back(value / params.ppcy / params.ppcz);
+            }
+        }
+    }
+
+    const long fourier_memory = sizeof(double) * (long)ny * nz + 2 * sizeof(double) * (long)ny * (nz / 2 + 1);
+    const long array2d_memory = 12l * sizeof(double) * ny * nz;
+    const long array3d_memory = 9l * sizeof(double) * nx * ny * nz;
+    const long wake_particle_memory = 88l * static_cast<long>(py.size());  // sizeof(wake_particle_2d), src/containers.h:31-43
+    out << "Expected RAM usage:\n";
+    out << "3D arrays:       " << memory_formatter(array3d_memory) << "\n"
+        << "2D arrays:       " << memory_formatter(array2d_memory) << "\n"
+        << "Fourier:         " << memory_formatter(fourier_memory) << "\n"
+        << "Wake particles:  " << memory_formatter(wake_particle_memory) << "\n"
+        << "Bunch particles: " << memory_formatter(0) << "\n"
+        << "Total:           " << memory_formatter(array2d_memory + array3d_memory + wake_particle_memory + fourier_memory) << std::endl;
+    out << "----------------------------------------" << std::endl;
+
+    qpic_params p;
+    qpic_default_params(&p);
+    p.nx = nx;
+    p.ny = ny;
+    p.nz = nz;
+    p.lx = params.lx;
+    p.ly = params.ly;
+    p.lz = params.lz;
+    p.magnetic_field_iterations = params.magnetic_field_iterations;
+    const bool any_output = params.output.output3d || params.output.output_xy;
+    p.keep_slices_3d = any_output ? 1 : 0;
+    qpic_ctx * ctx = nullptr;
+    if (qpic_create(&p, &ctx) != QPIC_OK) {
+        std::cerr << "qpic_create failed: " << qpic_last_error(nullptr) << std::endl;
+        return 1;
+    }
+    try {
+        if (params.laser.present) {
+            const Laser_gaussian & L = params.laser;
+            check(qpic_set_laser_gaussian(ctx, L.amplitude, L.wx, L.wy, L.wz, L.x0, L.y0, L.z0), ctx);
+        }
+        for (int ti = 0; ti < time_iterations; ti++) {  // System_3d::run (src/System_3d.cpp:199-236); no bunch => every sweep is identical
+            out << "Iteration " << ti << std::endl;
+            out << "Depositing bunch densities..." << std::endl;
+            out << "Solving wakefield" << std::flush;
+            Output_writer writer(params.output.output3d, params.output.output_xy, params.output.output_bunch, params.output.z0, ti, nx, ny, nz, dx, dy, dz);
+            check(qpic_init_wake_particles(ctx, py.data(), pz.data(), pn.data(), py.size()), ctx);
+            check(qpic_begin(ctx), ctx);
+            int done = 0;
+            while (!done) {
+                const int before = qpic_current_slice(ctx);  // first slice this call will start
+                check(qpic_step(ctx, 10, &done), ctx);
+                const int stopped = qpic_stopped_at(ctx);
+                const int last_started = done ? (stopped >= 0 ? stopped : 0) : qpic_current_slice(ctx) + 1;
+                for (int i = before; i >= last_started; i--) {  // one dot per started slice whose index is divisible by 10 (:329-331)
+                    if (i % 10 == 0) out << "." << std::flush;
+                }
+            }
+            if (qpic_stopped_at(ctx) >= 0) out << "Stop condition encountered, stopping the simulation" << std::endl;
+            out << std::endl;
+            check(qpic_finish(ctx), ctx);
+            if (any_output) {
+                std::vector<double> buf((size_t)nx * ny * nz);
+                struct Entry {
+                    qpic_field3d id;
+                    Field_meta meta;
+                };
+                const Entry entries[] = {
+                    // the five per-slice arrays (initialize_slice_array / write_slice, src/System_3d.cpp:251-260, :663-665)
+                    {QPIC_F3_PSI, {"psi", 0, 0, 0}},
+                    {QPIC_F3_RHO, {"rho", 0, 0, 0}},
+                    {QPIC_F3_JX, {"jx", 0, 0, 0}},
+                    {QPIC_F3_JY, {"jy", -0.5 * dx, 0.5 * dy, 0}},
+                    {QPIC_F3_JZ, {"jz", -0.5 * dx, 0, 0.5 * dz}},
+                    // the nine whole arrays (src/System_3d.cpp:240-249, :624-626)
+                    {QPIC_F3_ASQR, {"aSqr", 0, 0, 0}},
+                    {QPIC_F3_SUSCEPTIBILITY, {"susceptibility", 0, 0, 0}},
+                    {QPIC_F3_RHO_BUNCH, {"rho_bunch", 0, 0, 0}},
+                    {QPIC_F3_JX_BUNCH, {"jx_bunch", 0, 0, 0}},
+                    {QPIC_F3_EX, {"ex", -0.5 * dx, 0, 0}},
+                    {QPIC_F3_EY, {"ey", 0, 0.5 * dy, 0}},
+                    {QPIC_F3_EZ, {"ez", 0, 0, 0.5 * dz}},
+                    {QPIC_F3_BY, {"by", 0, 0, 0.5 * dz}},
+                    {QPIC_F3_BZ, {"bz", 0, 0.5 * dy, 0}},
+                };
+                for (const Entry & e : entries) {
+                    check(qpic_download_field3d(ctx, e.id, buf.data()), ctx);
+                    writer.write_array(e.meta, buf.data());
+                }
+            }
+            out << "Depositing fields to particles..." << std::endl;
+            out << "Advancing particles..." << std::endl;
+            out << std::endl;
+        }
+    } catch (const std::exception & e) {
+        std::cerr << "error: " << e.what() << std::endl;
+        qpic_destroy(ctx);
+        return 1;
+    }
+    qpic_destroy(ctx);
+    const auto t_done = std::chrono::high_resolution_clock::now();
+    out << "----------------------------------------" << std::endl;
+    std::printf("Finished in %ld s\n", (long)std::chrono::duration_cast<std::chrono::seconds>(t_done - t_begin).count());
+    return 0;
+}

@@ -1,0 +1,111 @@
+// Output contract of the drop-in driver (C++14).
+//
+// The reference writes HDF5 (src/Output_writer.cpp): Fields_NNN.h5 with (nx,ny,nz) datasets + `steps` / `origin` attributes,
+// Fields_xy_NNN.h5 with (nx,ny) cuts at z0 + `steps` / `origin` / `plane` / `plane_coordinate`, Photons_NNN.h5, Bunch_NNN.h5.
+// libhdf5 does not exist in this image, so the same datasets are written as one NumPy file each:
+//     Fields_000.h5  ->  directory Fields_000.h5.d/ with <dataset>.npy and <dataset>.attrs ("name dtype count values...")
+// which is the layout oracle/shims/H5Cpp.h produces for the unmodified reference, so both outputs can be diffed directly.
+// A real HDF5 back end is a "next" row.
+#pragma once
+
+#include <sys/stat.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace qhost {
+
+struct Field_meta {
+    std::string name;
+    double ox, oy, oz;  // origin (src/System_3d.cpp:176-193)
+};
+
+inline void write_npy(const std::string & path, const double * data, const std::vector<size_t> & shape) {
+    FILE * f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot create " + path);
+    std::string sh = "(";
+    size_t total = 1;
+    for (size_t d : shape) {
+        sh += std::to_string(d) + ",";
+        total *= d;
+    }
+    sh += ")";
+    const std::string dict = "{'descr': '<f8', 'fortran_order': False, 'shape': " + sh + ", }";
+    char header[128];
+    std::memset(header, ' ', sizeof(header));
+    std::memcpy(header, "\x93NUMPY\x01\x00", 8);
+    header[8] = static_cast<char>((sizeof(header) - 10) & 0xff);
+    header[9] = static_cast<char>((sizeof(header) - 10) >> 8);
+    std::memcpy(header + 10, dict.data(), dict.size());
+    header[sizeof(header) - 1] = '\n';
+    std::fwrite(header, 1, sizeof(header), f);
+    if (total) std::fwrite(data, sizeof(double), total, f);
+    std::fclose(f);
+}
+
+inline void write_attrs(const std::string & path, const std::vector<double> & steps, const std::vector<double> & origin, bool with_plane,
+                        double plane_coordinate) {
+    FILE * f = std::fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot create " + path);
+    std::fprintf(f, "steps <f8 %zu", steps.size());
+    for (double v : steps) std::fprintf(f, " %.17g", v);
+    std::fprintf(f, "\norigin <f8 %zu", origin.size());
+    for (double v : origin) std::fprintf(f, " %.17g", v);
+    std::fprintf(f, "\n");
+    if (with_plane) std::fprintf(f, "plane <i4 1 1\nplane_coordinate <f8 1 %.17g\n", plane_coordinate);
+    std::fclose(f);
+}
+
+class Output_writer {
+public:
+    Output_writer(bool output3d, bool output_xy, bool output_bunch, double z0, int count, int nx, int ny, int nz, double dx, double dy, double dz)
+        : output3d(output3d), output_xy(output_xy), z0(z0), nx(nx), ny(ny), nz(nz), dx(dx), dy(dy), dz(dz) {
+        char name[64];
+        std::snprintf(name, sizeof(name), "Fields_%03d.h5.d", count);
+        dir3d = name;
+        std::snprintf(name, sizeof(name), "Fields_xy_%03d.h5.d", count);
+        dirxy = name;
+        if (output3d) mkdir(dir3d.c_str(), 0777);
+        if (output_xy) mkdir(dirxy.c_str(), 0777);
+        if (output_bunch) {
+            std::snprintf(name, sizeof(name), "Bunch_%03d.h5.d", count);
+            mkdir(name, 0777);
+        }
+        std::snprintf(name, sizeof(name), "Photons_%03d.h5.d", count);  // always created (src/System_parameters.h:12)
+        mkdir(name, 0777);
+    }
+
+    // a full (nx,ny,nz) array: whole to Fields, z-interpolated cut to Fields_xy (src/array_utils.cpp:7-24)
+    void write_array(const Field_meta & m, const double * a) {
+        if (output3d) {
+            write_npy(dir3d + "/" + m.name + ".npy", a, {(size_t)nx, (size_t)ny, (size_t)nz});
+            write_attrs(dir3d + "/" + m.name + ".attrs", {dx, dy, dz}, {m.ox, m.oy, m.oz}, false, 0);
+        }
+        if (output_xy) {
+            const int k0 = static_cast<int>(std::floor((z0 - m.oz) / dz));
+            const double z_frac = (z0 - m.oz) / dz - k0;
+            std::vector<double> cut((size_t)nx * ny);
+            for (int i = 0; i < nx; i++) {
+                for (int j = 0; j < ny; j++) {
+                    const double * row = a + ((size_t)i * ny + j) * nz;
+                    cut[(size_t)i * ny + j] = (1 - z_frac) * row[k0] + z_frac * row[k0 + 1];
+                }
+            }
+            write_npy(dirxy + "/" + m.name + ".npy", cut.data(), {(size_t)nx, (size_t)ny});
+            write_attrs(dirxy + "/" + m.name + ".attrs", {dx, dy}, {m.ox, m.oy}, true, z0);
+        }
+    }
+
+private:
+    bool output3d, output_xy;
+    double z0;
+    int nx, ny, nz;
+    double dx, dy, dz;
+    std::string dir3d, dirxy;
+};
+
+}  // namespace qhost
