@@ -69,7 +69,9 @@ def test_driver_output_files_match_reference(name, golden_dir, tmp_path):
         assert slice_rel_l2(a, g["f3/" + nm]) < 1e-9, nm
         xy = np.load(os.path.join(tmp_path, "Fields_xy_000.h5.d", nm + ".npy"))
         ref = g["xy/" + nm]
-        assert np.linalg.norm(xy - ref) <= 1e-9 * max(np.linalg.norm(ref), 1e-300), nm
+        # the cut sits on the symmetry plane, where odd fields (ez, by, jz) are pure rounding noise: scale by the 3-D field
+        scale = np.abs(g["f3/" + nm]).max()
+        assert np.abs(xy - ref).max() <= 1e-9 * scale + 1e-300, nm
         attrs = dict(line.split(None, 3)[0::3] for line in open(os.path.join(tmp_path, "Fields_000.h5.d", nm + ".attrs")))
         assert np.allclose([float(v) for v in attrs["origin"].split()], g[f"f3/{nm}@origin"], rtol=0, atol=1e-15)
         assert np.allclose([float(v) for v in attrs["steps"].split()], g[f"f3/{nm}@steps"], rtol=0, atol=1e-15)
