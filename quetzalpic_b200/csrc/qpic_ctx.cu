@@ -71,6 +71,9 @@ struct qpic_ctx {
     double * f3[QPIC_F3_COUNT] = {};
     double *fft_in = nullptr, *fft_in2 = nullptr, *raw = nullptr;
     double2 * spec = nullptr;  // ny * nz complex (the psi solves use the first ny*(nz/2+1))
+    double2 *spec_row0 = nullptr, *spec_colsum = nullptr;  // nz/2+1 each: U(0,k) and sum_j U(j,k) for the fused potential fix-up
+    int * cols_ticket = nullptr;                           // "last block" counter of the column kernel
+    double * border_mean = nullptr;                        // mean over first column U first row of the solved potential
     double *sy = nullptr, *sz = nullptr;
     DeviceFft fy, fz;
     Particles P = {};
@@ -334,33 +337,40 @@ int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cel
 }
 
 // columns forward, / symbol, backward over `ncols` columns of spec (leading dimension ld)
-int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bool full) {
+int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bool full, bool want_border_sums = false) {
     const int nz = c->g.nz, nzh = nz / 2 + 1;
     const int ncols = full ? nz : nzh;
     const qpic_ctx::FftLaunch & L = full ? c->cols_full : c->cols_half;
     if (c->pow2_y) {
         const double * inv = nullptr;
         QPIC_TRY(get_inv_symbol(c, D, full, &inv));
-        QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, c->spec, ncols, ncols, inv);
+        QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, c->spec, ncols, ncols, inv,
+                    want_border_sums ? c->spec_row0 : (double2 *)nullptr, want_border_sums ? c->spec_colsum : (double2 *)nullptr, c->cols_ticket,
+                    c->border_mean, nz);
     } else {
         QPIC_LAUNCH(k_fft_cols_solve<false>, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, ncols, ncols, L.spb, c->sy, c->sz, nz, D);
     }
     return check_launch(c, "k_fft_cols_solve");
 }
 
-// real solve: fft_in -> raw (= solution / ny / nz)
-int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D) {
+// real solve: fft_in -> raw (= solution / ny / nz).  With fixed_dst != NULL and both axes on the power-of-two engine the
+// potential fix-up (border mean, clamp) is fused into the backward rows and the result goes straight to fixed_dst;
+// returns whether that happened through *fused.
+int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, double * fixed_dst = nullptr, bool * fused = nullptr) {
     const int ny = c->g.ny, nz = c->g.nz;
     const qpic_ctx::FftLaunch & R = c->rows_real;
+    const bool fuse = fixed_dst != nullptr && c->pow2_y && c->pow2_z;
+    if (fused) *fused = fuse;
     if (c->pow2_z) {
         QPIC_LAUNCH(k_p2_rows_r2c, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->spec, ny);
     } else {
         QPIC_LAUNCH(k_fft_rows_r2c<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz, R.spb);
     }
     QPIC_TRY(check_launch(c, "k_fft_rows_r2c"));
-    QPIC_TRY(enqueue_columns(c, st, ctl, D, false));
+    QPIC_TRY(enqueue_columns(c, st, ctl, D, false, fuse));
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_c2r, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->spec, c->raw, ny, c->inv_scale);
+        QPIC_LAUNCH(k_p2_rows_c2r, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->spec, fuse ? fixed_dst : c->raw, ny, c->inv_scale,
+                    fuse ? 1 : 0, c->border_mean, c->prm.psi_threshold - 1);
     } else {
         QPIC_LAUNCH(k_fft_rows_c2r<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz, R.spb, c->inv_scale);
     }
@@ -513,7 +523,9 @@ int enqueue_potential(qpic_ctx * c, cudaStream_t st, bool fast, int at_mid, doub
                          c->f3[QPIC_F3_RHO_BUNCH], 1, c->fft_in);
         QPIC_TRY(check_launch(c, "k_deposit_charge"));
     }
-    QPIC_TRY(enqueue_real_solve(c, st, c->ctl, 0.0));
+    bool fused = false;
+    QPIC_TRY(enqueue_real_solve(c, st, c->ctl, 0.0, dst, &fused));
+    if (fused) return QPIC_OK;
     return enqueue_fixup(c, st, dst);
 }
 
@@ -949,6 +961,10 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(dev_alloc(c, &c->fft_in2, n2));
     QPIC_TRY(dev_alloc(c, &c->raw, n2));
     QPIC_TRY(dev_alloc(c, &c->spec, n2));
+    QPIC_TRY(dev_alloc(c, &c->spec_row0, (size_t)g.nz / 2 + 1));
+    QPIC_TRY(dev_alloc(c, &c->spec_colsum, (size_t)g.nz / 2 + 1));
+    QPIC_TRY(dev_alloc(c, &c->cols_ticket, 1));
+    QPIC_TRY(dev_alloc(c, &c->border_mean, 1));
     c->nchunks = blocks_for(n2, SCAN_CHUNK);
     QPIC_TRY(dev_alloc(c, &c->count, n2));
     QPIC_TRY(dev_alloc(c, &c->cursor, n2));

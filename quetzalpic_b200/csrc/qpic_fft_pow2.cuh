@@ -118,14 +118,22 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
     }
 }
 
-// backward rows: two half spectra -> one complex sequence -> two real rows, scaled by 1/ny/nz (src/System_3d.cpp:361)
+// backward rows: two half spectra -> one complex sequence -> two real rows, scaled by 1/ny/nz (src/System_3d.cpp:361).
+// With fix != 0 the potential fix-up is fused in: psi = max(u - mean(first column U first row of u), floor)
+// (normalize_potential + increase_minimum, src/System_3d.cpp:30-47, :830-841).  The border mean is obtained from the
+// spectrum U = ny nz FFT2(u) that the column kernel leaves behind, so no second pass over the field is needed:
+//     sum_j u(j,0)  = (1/nz) sum_kz U(0,kz)            (row0[], Hermitian in kz)
+//     sum_k u(0,k)  = (1/ny) sum_ky U(ky,0)            (colsum[0])
+//     u(0,0)        = (1/(ny nz)) sum_ky sum_kz U      (colsum[], Hermitian in kz)
+// The column kernel's last block reduces these sums with a fixed-order tree and leaves the mean in *border_mean.
 __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double2 * __restrict__ spec, double * __restrict__ dst,
-                              int ny, double inv_scale) {
+                              int ny, double inv_scale, int fix, const double * __restrict__ border_mean, double floor_value) {
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = 1 << log2n, nzh = nz / 2 + 1;
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
+    const double mean = fix ? *border_mean : 0.0;
     double2 v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
@@ -146,15 +154,23 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int k = L.t + e * L.e8;
-        if (j0 < ny) dst[(size_t)j0 * nz + k] = scale_result(v[e].x, ny, nz, inv_scale);
-        if (j1 < ny) dst[(size_t)j1 * nz + k] = scale_result(v[e].y, ny, nz, inv_scale);
+        double a = scale_result(v[e].x, ny, nz, inv_scale), b = scale_result(v[e].y, ny, nz, inv_scale);
+        if (fix) {
+            a -= mean;
+            b -= mean;
+            if (a < floor_value) a = floor_value;
+            if (b < floor_value) b = floor_value;
+        }
+        if (j0 < ny) dst[(size_t)j0 * nz + k] = a;
+        if (j1 < ny) dst[(size_t)j1 * nz + k] = b;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ columns + symbol
 // one column per sequence; inv_symbol is [ncols][ny] (column-major for this kernel), entry (k=0, j=0) = 0
 __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
-                                const double * __restrict__ inv_symbol) {
+                                const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum,
+                                int * __restrict__ ticket, double * __restrict__ border_mean, int nz) {
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -174,12 +190,77 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
             v[e] = (j == 0 && k == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * r, v[e].y * r);
         }
     }
+    if (colsum) {
+        // what the fused potential fix-up of k_p2_rows_c2r needs: U(0,k) and sum_j U(j,k), fixed-order reductions
+        __shared__ double2 red[32];
+        double2 acc = v[0];
+#pragma unroll
+        for (int e = 1; e < 8; e++) acc = cadd(acc, v[e]);
+        const int seg = L.e8 < 32 ? L.e8 : 32;
+        for (int o = seg >> 1; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (L.e8 > 32) {
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (L.t == 0) {
+                const int w0 = threadIdx.x >> 5, nw = L.e8 >> 5;
+                acc = red[w0];
+                for (int w = 1; w < nw; w++) acc = cadd(acc, red[w0 + w]);
+            }
+        }
+        if (live && L.t == 0) {
+            colsum[k] = acc;
+            row0[k] = v[0];  // thread t = 0 owns j = 0 in v[0]
+        }
+    }
     // the forward transform's last exchange buffer may still be read by slower threads of this sequence
     __syncthreads();
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy);
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) spec[(size_t)(L.t + e * L.e8) * ld + k] = v[e];
+    }
+    if (colsum) {
+        // The block that takes the last ticket sees every block's row0[] / colsum[] (release: fence before the ticket;
+        // acquire: fence after it) and reduces them to the border mean -- see k_p2_rows_c2r for the formulas.
+        __shared__ int is_last;
+        __shared__ double red_a[1024], red_b[1024];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const int nzh = nz / 2 + 1;
+            double pa = 0.0, pb = 0.0;  // Hermitian-weighted sums of Re U(0,k) and Re sum_j U(j,k)
+            for (int kk = threadIdx.x; kk < nzh; kk += blockDim.x) {
+                const double wgt = (kk == 0 || 2 * kk == nz) ? 1.0 : 2.0;
+                pa += wgt * row0[kk].x;
+                pb += wgt * colsum[kk].x;
+            }
+            red_a[threadIdx.x] = pa;
+            red_b[threadIdx.x] = pb;
+            __syncthreads();
+            int n = blockDim.x;  // tree over an arbitrary block size: fold the upper part onto the lower one
+            while (n > 1) {
+                const int half = (n + 1) / 2;
+                if ((int)threadIdx.x < n - half) {
+                    red_a[threadIdx.x] += red_a[threadIdx.x + half];
+                    red_b[threadIdx.x] += red_b[threadIdx.x + half];
+                }
+                __syncthreads();
+                n = half;
+            }
+            if (threadIdx.x == 0) {
+                const double s_col0 = red_a[0] / nz;      // sum_j u(j,0)
+                const double s_row0 = colsum[0].x / ny;   // sum_k u(0,k)
+                const double u00 = red_b[0] / ny / nz;    // u(0,0), counted in both
+                *border_mean = (s_col0 + s_row0 - u00) / (ny + nz - 1);
+                *ticket = 0;
+            }
+        }
     }
 }
 
