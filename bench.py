@@ -210,7 +210,7 @@ def cpu_baseline(w, target_seconds=15.0):
     return {
         "value": P * pushed / span, "unit": "pushes/s", "cores": used, "kind": kind, "ms_per_slice": 1e3 * span / pushed,
         "sample": f"{pushed} xi-slices of the same 512x512 4 ppc M=5 workload ({nx}-slice box, laser centred), "
-                  f"{'unmodified reference -Ofast + OpenMP, shim FFT' if kind == 'reference' else 'plain-C oracle port'}, "
+                  f"{'unmodified reference -Ofast + OpenMP, MKL FFT (DFTI in libtorch_cpu)' if kind == 'reference' else 'plain-C oracle port'}, "
                   f"OMP_NUM_THREADS={used}",
     }
 
