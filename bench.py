@@ -86,6 +86,16 @@ KERNEL_BYTES = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on the bench workload's transverse shape, from the
+# ncu capture committed as profiles/r01_final_launches_ncu.csv (cold-cache replays: an upper bound on the in-graph traffic)
+NCU_TRAFFIC = {
+    "k_tile_deposit_jy_jz": 51.43e6, "k_tile_deposit_charge_mid": 34.6e6, "k_tile_deposit_jx": 26.2e6, "k_tile_deposit_charge": 26.2e6,
+    "k_particles_predict": 124.2e6, "k_particles_correct_gamma": 61.0e6, "k_particles_gamma": 105.0e6, "k_particles_advance": 102.7e6,
+    "k_particles_to_slots": 85.4e6, "k_fft_cols_solve": 4.8e6, "k_fft_rows_b_forward": 14.7e6, "k_fft_rows_b_backward": 4.2e6,
+    "k_fft_rows_r2c": 2.1e6, "k_fft_rows_c2r": 2.2e6,
+}
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -319,7 +329,7 @@ def run_b200_arm(args, w):
     top = kernels[0]
     top_bytes = KERNEL_BYTES.get(top["kernel"], lambda N, P: 0.0)(N, P)
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": (top["algorithmic_gbs"] or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                "frac": (top["algorithmic_gbs"] or 0.0) / peak, "traffic": NCU_TRAFFIC.get(top["kernel"]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top_bytes, "share_of_slice": top["share"]}
     slice_bytes = algorithmic_bytes_per_slice(N, P, M)
     slice_gbs = slice_bytes / (ms_per_slice * 1e-3) / 1e9
