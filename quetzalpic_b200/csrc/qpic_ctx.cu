@@ -591,7 +591,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         const int pmask_next = mask_buffer(it + 1 < M ? it + 1 : 0);
         if (fast && pmask_next == c->pmask_cur) {
             // M == 1: a single buffer, cleared in line
-            QPIC_CUDA(c, cudaMemsetAsync(c->pmask[c->pmask_cur], 0, sizeof(unsigned long long) * c->g.n2, sa));
+            QPIC_LAUNCH_FLAT(k_clear_masks, 148, 256, 0, sa, c->ctl, c->pmask[c->pmask_cur], c->g.n2);
+            QPIC_TRY(check_launch(c, "k_clear_masks"));
         }
         if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
@@ -608,7 +609,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
         // the other presence-mask buffer was last read by the previous iteration's deposits: clear it for the next one
         if (fast && pmask_next != c->pmask_cur) {
-            QPIC_CUDA(c, cudaMemsetAsync(c->pmask[pmask_next], 0, sizeof(unsigned long long) * c->g.n2, sb));
+            QPIC_LAUNCH_FLAT(k_clear_masks, 148, 256, 0, sb, c->ctl, c->pmask[pmask_next], c->g.n2);
+            QPIC_TRY(check_launch(c, "k_clear_masks"));
         }
         // branch A: psi_middle, then jy_next / jz_next
         if (!fast) QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_m, c->start_m, c->perm_m));

@@ -563,6 +563,13 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 // predictor: py_next, pz_next (src/System_3d.cpp:416-433), half-step position (:436-443) and its cell descriptor.
 // FAST (sort-free deposit): records the cell offset of the half step instead of counting cell populations, and raises
 // Ctl::fast_fail if a particle leaves the +-1 cell window the tile deposit covers.
+// clears a presence-mask buffer.  A kernel rather than a memset node: memset nodes of a graph may be executed by a copy
+// engine and then queue behind the large streaming transfers of the caller (qpic_download_slices3d).
+__global__ void k_clear_masks(const Ctl * ctl, unsigned long long * __restrict__ m, int n) {
+    if (cancelled(ctl)) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) m[t] = 0ull;
+}
+
 // class of a half step for the presence masks of the tile deposit: cell offset (oy, oz) in [-1,1]^2 and the half-cell bits
 __device__ __host__ __forceinline__ int offset_class(int oy, int oz, int hy, int hz) { return ((oy + 1) * 3 + (oz + 1)) * 4 + hy * 2 + hz; }
 
