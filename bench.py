@@ -72,8 +72,7 @@ KERNEL_BYTES = {
     "k_fft_rows_b_backward": lambda N, P: 8.0 * (4 * N),
     # particles
     "k_particles_gamma": lambda N, P: 8.0 * (17.5 * P),
-    "k_particles_predict": lambda N, P: 8.0 * (18.5 * P),
-    "k_particles_correct_gamma": lambda N, P: 8.0 * (12 * P),
+    "k_particles_predict": lambda N, P: 8.0 * (24 * P),  # predictor + corrector: reads 14.5, writes 9.5 doubles per particle
     "k_particles_advance": lambda N, P: 8.0 * (15 * P),
     "k_particles_to_slots": lambda N, P: 8.0 * (15.5 * P),
     "k_end_of_slice": lambda N, P: 8.0 * (17 * N),
@@ -90,7 +89,7 @@ KERNEL_BYTES = {
 # ncu capture committed as profiles/r01_final_launches_ncu.csv (cold-cache replays: an upper bound on the in-graph traffic)
 NCU_TRAFFIC = {
     "k_tile_deposit_jy_jz": 51.43e6, "k_tile_deposit_charge_mid": 34.6e6, "k_tile_deposit_jx": 26.2e6, "k_tile_deposit_charge": 26.2e6,
-    "k_particles_predict": 124.2e6, "k_particles_correct_gamma": 61.0e6, "k_particles_gamma": 105.0e6, "k_particles_advance": 102.7e6,
+    "k_particles_predict": 124.2e6, "k_particles_gamma": 105.0e6, "k_particles_advance": 102.7e6,
     "k_particles_to_slots": 85.4e6, "k_fft_cols_solve": 4.8e6, "k_fft_rows_b_forward": 14.7e6, "k_fft_rows_b_backward": 4.2e6,
     "k_fft_rows_r2c": 2.1e6, "k_fft_rows_c2r": 2.2e6,
 }

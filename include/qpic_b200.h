@@ -135,6 +135,11 @@ int qpic_last_step_stats(qpic_ctx * ctx, float * ms, long * kernel_launches);
 long qpic_fast_path_aborts(const qpic_ctx * ctx);
 /* runs up to nslices slices eagerly with a CUDA event after every kernel; report = lines "kernel count total_ms" */
 int qpic_profile_slices(qpic_ctx * ctx, int nslices, char * report, size_t report_len);
+/* development build only (-DQPIC_TIMELINE): globaltimer stamps left by every kernel of the slices run since the reset;
+ * records = 4 values per entry (kernel id, kind 0 = start / 1 = end, t0, t1 in ns); returns the entry count or -1 */
+int qpic_timeline_reset(qpic_ctx * ctx);
+long qpic_timeline_read(qpic_ctx * ctx, long long * records, long cap);
+const char * qpic_timeline_kernel_name(int kernel_id);
 
 /* ---- streaming transfers for callers whose arrays live in host memory (System_3d's array3d members).  They run on a
  * separate copy stream and overlap the sweep: an upload is waited for by every slice queued after the call, a download

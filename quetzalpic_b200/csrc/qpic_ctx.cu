@@ -600,12 +600,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
                              c->pmask[c->pmask_cur]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
-        // branch B: corrector gamma / px and the jx deposit at (y,z) need only py_next, pz_next
+        // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored
         QPIC_TRY(stream_depend(c, sa, sb));
-        if (np > 0) {
-            QPIC_LAUNCH_FLAT(k_particles_correct_gamma, blocks_for(np, 128), 128, 0, sb, c->ctl, c->g, c->P);
-            QPIC_TRY(check_launch(c, "k_particles_correct_gamma"));
-        }
         QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
         // the other presence-mask buffer was last read by the previous iteration's deposits: clear it for the next one
         if (fast && pmask_next != c->pmask_cur) {
@@ -1436,6 +1432,53 @@ int qpic_profile_slices(qpic_ctx * c, int nslices, char * report, size_t report_
     }
     QPIC_TRY(resolve(c));
     return QPIC_OK;
+}
+
+// ---- in-graph timeline (only in the -DQPIC_TIMELINE development build, tools/timeline.py): globaltimer stamps that
+// block 0 / the last block of every kernel leave behind.  records = int64[4 * cap]: kid, kind, t0, t1 (ns).
+int qpic_timeline_reset(qpic_ctx * c) {
+#ifdef QPIC_TIMELINE
+    const int zero = 0;
+    QPIC_CUDA(c, cudaDeviceSynchronize());
+    QPIC_CUDA(c, cudaMemcpyToSymbol(g_tl_n, &zero, sizeof(int)));
+    return QPIC_OK;
+#else
+    return fail(c, QPIC_ERR_STATE, "not a timeline build (compile with -DQPIC_TIMELINE)");
+#endif
+}
+
+long qpic_timeline_read(qpic_ctx * c, long long * records, long cap) {
+#ifdef QPIC_TIMELINE
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    int n = 0;
+    if (cudaMemcpyFromSymbol(&n, g_tl_n, sizeof(int)) != cudaSuccess) return -1;
+    if (n > TL_CAPACITY) n = TL_CAPACITY;
+    if (n > cap) n = (int)cap;
+    std::vector<TlRecord> host((size_t)n);
+    if (n > 0 && cudaMemcpyFromSymbol(host.data(), g_tl, sizeof(TlRecord) * (size_t)n) != cudaSuccess) return -1;
+    for (int i = 0; i < n; i++) {
+        records[4 * i + 0] = host[i].kid;
+        records[4 * i + 1] = host[i].kind;
+        records[4 * i + 2] = (long long)host[i].t0;
+        records[4 * i + 3] = (long long)host[i].t1;
+    }
+    return n;
+#else
+    (void)records;
+    (void)cap;
+    fail(c, QPIC_ERR_STATE, "not a timeline build (compile with -DQPIC_TIMELINE)");
+    return -1;
+#endif
+}
+
+// name of a kernel id of the timeline records ("" when out of range)
+const char * qpic_timeline_kernel_name(int kid) {
+    static const char * names[] = QPIC_KERNEL_NAMES;
+    static const char * tile[] = {"k_tile_deposit_charge", "k_tile_deposit_charge_mid", "k_tile_deposit_jx", "?", "?", "k_tile_deposit_jy_jz", "?", "?", "?", "?",
+                                  "k_tile_deposit_rho_chi", "?", "?", "?", "?", "?", "k_p2_cols_solve_complex"};
+    if (kid >= 0 && kid < KID_COUNT) return names[kid];
+    if (kid >= KID_COUNT && kid <= KID_COUNT + 16) return tile[kid - KID_COUNT];
+    return "";
 }
 
 }  // extern "C"

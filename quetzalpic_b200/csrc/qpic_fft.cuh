@@ -245,6 +245,7 @@ __device__ __forceinline__ double2 * fft_smem(double2 * a, double2 * w, int nb, 
 template <bool POW2>
 __global__ void k_fft_rows_r2c(const Ctl * ctl, FftPlan Pz, const double2 * __restrict__ twz, const double * __restrict__ src, double2 * __restrict__ spec,
                                int ny, int nz, int spb) {
+    QPIC_KERNEL_BEGIN(KID_k_fft_rows_r2c);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     double2 * a = sm;
@@ -285,6 +286,7 @@ __device__ __forceinline__ double scale_result(double v, int ny, int nz, double 
 template <bool POW2>
 __global__ void k_fft_rows_c2r(const Ctl * ctl, FftPlan Pz, const double2 * __restrict__ twz, const double2 * __restrict__ spec, double * __restrict__ dst,
                                int ny, int nz, int spb, double inv_scale) {
+    QPIC_KERNEL_BEGIN(KID_k_fft_rows_c2r);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     double2 * a = sm;
@@ -327,6 +329,7 @@ __global__ void k_fft_rows_c2r(const Ctl * ctl, FftPlan Pz, const double2 * __re
 template <bool POW2>
 __global__ void k_fft_cols_solve(const Ctl * ctl, FftPlan Py, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols, int cpb,
                                  const double * __restrict__ sy, const double * __restrict__ sz, int nz_full, double D) {
+    QPIC_KERNEL_BEGIN(KID_k_fft_cols_solve);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const int ny = Py.n;
@@ -394,6 +397,7 @@ __global__ void k_fft_rows_b_forward(const Ctl * ctl, FftPlan Pz, const double2 
                                      const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                      const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
                                      double2 * __restrict__ spec, int spb) {
+    QPIC_KERNEL_BEGIN(KID_k_fft_rows_b_forward);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const int nz = g.nz, ny = g.ny;
@@ -430,6 +434,7 @@ __global__ void k_fft_rows_b_forward(const Ctl * ctl, FftPlan Pz, const double2 
 template <bool POW2>
 __global__ void k_fft_rows_b_backward(Ctl * ctl, FftPlan Pz, const double2 * __restrict__ twz, Geom g, const double2 * __restrict__ spec,
                                       double * __restrict__ by, double * __restrict__ bz, double threshold, int iteration, int spb, double inv_scale) {
+    QPIC_KERNEL_BEGIN(KID_k_fft_rows_b_backward);
     // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
     const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
     const int tag = ctl->stop_tag;
@@ -465,6 +470,7 @@ __global__ void k_fft_rows_b_backward(Ctl * ctl, FftPlan Pz, const double2 * __r
 template <bool POW2>
 __global__ void k_fft_rows_c2c(FftPlan Pz, const double2 * __restrict__ twz, const double * __restrict__ re, const double * __restrict__ im,
                                double2 * __restrict__ spec, int ny, int nz, int spb) {
+    QPIC_KERNEL_BEGIN(KID_k_fft_rows_c2c);
     QPIC_DYN_SMEM(double2, sm);
     double2 * a = sm;
     double2 * w = sm + spb * nz;

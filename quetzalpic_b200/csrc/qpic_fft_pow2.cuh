@@ -89,6 +89,7 @@ __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
 // forward rows, two real rows per sequence -> half spectra spec[ny][nzh]
 __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, double2 * __restrict__ spec,
                               int ny) {
+    QPIC_KERNEL_BEGIN(KID_k_p2_rows_r2c);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -128,6 +129,7 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
 // The column kernel's last block reduces these sums with a fixed-order tree and leaves the mean in *border_mean.
 __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double2 * __restrict__ spec, double * __restrict__ dst,
                               int ny, double inv_scale, int fix, const double * __restrict__ border_mean, double floor_value) {
+    QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2r);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -171,6 +173,7 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
 __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
                                 const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum,
                                 int * __restrict__ ticket, double * __restrict__ border_mean, int nz) {
+    QPIC_KERNEL_BEGIN(colsum ? KID_k_p2_cols_solve : KID_COUNT + 16);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -271,6 +274,7 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
                                     const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                     const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
                                     double2 * __restrict__ spec) {
+    QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_forward);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -304,6 +308,7 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
 // by(i) = re/ny/nz, bz(i) = im/ny/nz and the stop test (src/System_3d.cpp:541-552, :569-580)
 __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, const double2 * __restrict__ spec,
                                      double * __restrict__ by, double * __restrict__ bz, double threshold, int iteration, double inv_scale) {
+    QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_backward);
     // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
     const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
     const int tag = ctl->stop_tag;
@@ -335,6 +340,7 @@ __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __res
 // plain complex rows (exposed Helmholtz-pair building block)
 __global__ void k_p2_rows_c2c(int log2n, const double2 * __restrict__ twz, const double * __restrict__ re, const double * __restrict__ im,
                               double2 * __restrict__ spec, int ny) {
+    QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2c);
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = 1 << log2n;

@@ -16,6 +16,102 @@
 
 namespace qpic {
 
+// ------------------------------------------------------------------------------------------------ kernel prologue
+// Every kernel starts with QPIC_KERNEL_BEGIN(id):
+//   * griddepcontrol.wait -- the kernels of a slice are launched with programmatic stream serialization (PDL), so a
+//     kernel's blocks may become resident while its predecessor in the stream is still running; nothing produced by an
+//     earlier kernel (including the control block) may be read before this point.  Without the launch attribute the
+//     instruction is a no-op.
+//   * griddepcontrol.launch_dependents right after it: the successor may be staged as soon as all blocks of this kernel
+//     have passed their own wait (i.e. at most one waiting kernel is resident at a time).
+//   * -DQPIC_TIMELINE (tools/timeline.py, separate library): block 0 records globaltimer stamps before / after the wait and
+//     the last block to leave records the end, giving the in-graph timeline of a slice (gaps, overlaps) that ncu cannot.
+enum KernelId {
+    KID_k_init_a_sqr,
+    KID_k_locate_count,
+    KID_k_scan_chunk_sums,
+    KID_k_scan_sums,
+    KID_k_scan_apply,
+    KID_k_sort_fill,
+    KID_k_sort_rank,
+    KID_k_deposit_charge,
+    KID_k_deposit_jx_rho_chi,
+    KID_k_deposit_jy_jz,
+    KID_k_potential_fixup,
+    KID_k_particles_to_slots,
+    KID_k_particles_gamma,
+    KID_k_clear_masks,
+    KID_k_particles_predict,
+    KID_k_particles_currents_yz,
+    KID_k_particles_advance,
+    KID_k_end_of_slice,
+    KID_k_next_slice,
+    KID_k_tile_deposit,
+    KID_k_fft_rows_r2c,
+    KID_k_fft_rows_c2r,
+    KID_k_fft_cols_solve,
+    KID_k_fft_rows_b_forward,
+    KID_k_fft_rows_b_backward,
+    KID_k_fft_rows_c2c,
+    KID_k_p2_rows_r2c,
+    KID_k_p2_rows_c2r,
+    KID_k_p2_cols_solve,
+    KID_k_p2_rows_b_forward,
+    KID_k_p2_rows_b_backward,
+    KID_k_p2_rows_c2c,
+    KID_COUNT
+};
+#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_clear_masks", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c" }
+
+#ifdef QPIC_EMU
+#define QPIC_KERNEL_BEGIN(id) ((void)0)
+#else
+__device__ __forceinline__ void pdl_grid_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#ifdef QPIC_TIMELINE
+constexpr int TL_CAPACITY = 1 << 16;
+struct TlRecord {
+    int kid, kind;  // kind 0: start (t0 = block 0 resident, t1 = dependencies satisfied), 1: end (t0)
+    unsigned long long t0, t1;
+};
+__device__ TlRecord g_tl[TL_CAPACITY];
+__device__ int g_tl_n;
+__device__ unsigned int g_tl_exit[KID_COUNT + 32];
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+struct TlSpan {
+    int kid;
+    __device__ __forceinline__ TlSpan(int kid_) : kid(kid_) {
+        const bool first = (threadIdx.x | threadIdx.y | blockIdx.x | blockIdx.y) == 0;
+        const unsigned long long t0 = first ? tl_now() : 0ull;
+        pdl_grid_sync();
+        if (first) {
+            const int slot = atomicAdd(&g_tl_n, 1);
+            if (slot < TL_CAPACITY) g_tl[slot] = TlRecord{kid, 0, t0, tl_now()};
+        }
+    }
+    __device__ __forceinline__ ~TlSpan() {
+        if ((threadIdx.x | threadIdx.y) == 0) {
+            const unsigned int total = gridDim.x * gridDim.y;
+            const unsigned int n = atomicAdd(&g_tl_exit[kid], 1u) + 1u;
+            if (n % total == 0u) {
+                const int slot = atomicAdd(&g_tl_n, 1);
+                if (slot < TL_CAPACITY) g_tl[slot] = TlRecord{kid, 1, tl_now(), 0ull};
+            }
+        }
+    }
+};
+#define QPIC_KERNEL_BEGIN(id) qpic::TlSpan qpic_tl_span_(id)
+#else
+#define QPIC_KERNEL_BEGIN(id) qpic::pdl_grid_sync()
+#endif
+#endif
+
 struct Ctl {
     int slice;      // xi-slice being solved (nx-1 ... 0)
     int stop_tag;   // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
@@ -126,6 +222,7 @@ __device__ __forceinline__ double wrap_coordinate(double y, double l) {
 // a_sqr = amplitude * exp(-(x-x0)^2/wx/wx - (y-y0)^2/wy/wy - (z-z0)^2/wz/wz), node centred
 // (src/System_3d.cpp:805-816, src/profiles.cpp:4-11)
 __global__ void k_init_a_sqr(Geom g, double * __restrict__ a, double amp, double wx, double wy, double wz, double x0, double y0, double z0) {
+    QPIC_KERNEL_BEGIN(KID_k_init_a_sqr);
     const size_t total = (size_t)g.nx * g.n2;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(t % g.nz);
@@ -139,6 +236,7 @@ __global__ void k_init_a_sqr(Geom g, double * __restrict__ a, double amp, double
 // cell descriptors of (y, z) + per-cell population count (integer atomics: order independent)
 __global__ void k_locate_count(int np, Geom g, const double * __restrict__ y, const double * __restrict__ z, int * __restrict__ cell,
                                double * __restrict__ fy, double * __restrict__ fz, int * __restrict__ count) {
+    QPIC_KERNEL_BEGIN(KID_k_locate_count);
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     int jc, kc;
@@ -183,6 +281,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int & total) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunk_sums(const Ctl * ctl, const int * __restrict__ count, int n, int * __restrict__ sums) {
+    QPIC_KERNEL_BEGIN(KID_k_scan_chunk_sums);
     if (cancelled(ctl)) return;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int v = 0;
@@ -197,6 +296,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunk_sums(const Ctl * ct
 
 // single block: exclusive scan of the chunk sums in place
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int * __restrict__ sums, int nchunks) {
+    QPIC_KERNEL_BEGIN(KID_k_scan_sums);
     if (cancelled(ctl)) return;
     int carry = 0;
     for (int base = 0; base < nchunks; base += SCAN_THREADS) {
@@ -211,6 +311,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int
 
 __global__ void __launch_bounds__(SCAN_THREADS)
     k_scan_apply(const Ctl * ctl, int * __restrict__ count, int n, const int * __restrict__ sums, int * __restrict__ start, int * __restrict__ cursor) {
+    QPIC_KERNEL_BEGIN(KID_k_scan_apply);
     if (cancelled(ctl)) return;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int c[SCAN_ITEMS];
@@ -237,6 +338,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 
 // bucket fill: slot order inside a cell is whatever order the integer atomics resolve in ...
 __global__ void k_sort_fill(const Ctl * ctl, int np, const int * __restrict__ cell, int * __restrict__ cursor, int * __restrict__ tmp) {
+    QPIC_KERNEL_BEGIN(KID_k_sort_fill);
     if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
@@ -248,6 +350,7 @@ __global__ void k_sort_fill(const Ctl * ctl, int np, const int * __restrict__ ce
 // Buckets hold ~ppc entries (a few; tens at strong compression), so the O(k) scan per entry stays in L1.
 __global__ void k_sort_rank(const Ctl * ctl, int np, const int * __restrict__ cell, const int * __restrict__ start, const int * __restrict__ tmp,
                             int * __restrict__ perm) {
+    QPIC_KERNEL_BEGIN(KID_k_sort_rank);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= np) return;
@@ -276,6 +379,7 @@ struct CellLists {
 __global__ void k_deposit_charge(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ nw, const double * __restrict__ rho_ion,
                                  const double * __restrict__ jxb3, const double * __restrict__ rhob3, int with_background,
                                  double * __restrict__ out) {
+    QPIC_KERNEL_BEGIN(KID_k_deposit_charge);
     if (cancelled(ctl)) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
@@ -314,6 +418,7 @@ template <bool WITH_JX, bool WITH_RHO_CHI>
 __global__ void k_deposit_jx_rho_chi(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ vjx, const double * __restrict__ vrho,
                                      const double * __restrict__ vchi, const double * __restrict__ jxb3, const double * __restrict__ rhob3,
                                      double * __restrict__ jx, double * __restrict__ rho, double * __restrict__ chi3, int final_pass) {
+    QPIC_KERNEL_BEGIN(KID_k_deposit_jx_rho_chi);
     if (final_pass) {
         if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
     } else if (cancelled(ctl)) {
@@ -378,6 +483,7 @@ __device__ __forceinline__ bool node_weight(int role, double f, double & w) {
 // staggering :190-193)
 __global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const double * __restrict__ vjy, const double * __restrict__ vjz,
                                 double * __restrict__ jy_next, double * __restrict__ jz_next) {
+    QPIC_KERNEL_BEGIN(KID_k_deposit_jy_jz);
     if (cancelled(ctl)) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
@@ -420,6 +526,7 @@ __global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const doub
 constexpr int FIX_THREADS = 256;
 
 __global__ void __launch_bounds__(FIX_THREADS) k_potential_fixup(const Ctl * ctl, Geom g, const double * __restrict__ raw, double * __restrict__ dst, double floor_value) {
+    QPIC_KERNEL_BEGIN(KID_k_potential_fixup);
     if (cancelled(ctl)) return;
     __shared__ double red[FIX_THREADS];
     double part = 0.0;
@@ -506,6 +613,7 @@ __device__ __forceinline__ double wrap_fast(double y, double l) {
 
 // after the cell sort of the slice-start positions: copy the particle's slice inputs from id order to slot order
 __global__ void k_particles_to_slots(const Ctl * ctl, Particles P, const int * __restrict__ perm_b) {
+    QPIC_KERNEL_BEGIN(KID_k_particles_to_slots);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.np) return;
@@ -523,6 +631,7 @@ __global__ void k_particles_to_slots(const Ctl * ctl, Particles P, const int * _
 // initial gamma, px (src/System_3d.cpp:368-378) + the values deposited at :390-397 + iteration invariants
 __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b, const double * __restrict__ a_sqr3,
                                   const double * __restrict__ psi, int want_invariants) {
+    QPIC_KERNEL_BEGIN(KID_k_particles_gamma);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.np) return;
@@ -566,6 +675,7 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 // clears a presence-mask buffer.  A kernel rather than a memset node: memset nodes of a graph may be executed by a copy
 // engine and then queue behind the large streaming transfers of the caller (qpic_download_slices3d).
 __global__ void k_clear_masks(const Ctl * ctl, unsigned long long * __restrict__ m, int n) {
+    QPIC_KERNEL_BEGIN(KID_k_clear_masks);
     if (cancelled(ctl)) return;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) m[t] = 0ull;
 }
@@ -573,15 +683,24 @@ __global__ void k_clear_masks(const Ctl * ctl, unsigned long long * __restrict__
 // class of a half step for the presence masks of the tile deposit: cell offset (oy, oz) in [-1,1]^2 and the half-cell bits
 __device__ __host__ __forceinline__ int offset_class(int oy, int oz, int hy, int hz) { return ((oy + 1) * 3 + (oz + 1)) * 4 + hy * 2 + hz; }
 
+// The corrector gamma / px (src/System_3d.cpp:498-508) and the values deposited at :520-527 depend only on py_next, pz_next,
+// so they are formed here as well: one streaming pass over the slot arrays per iteration instead of two.
 template <bool FAST>
 __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
                                     int * __restrict__ count, unsigned long long * __restrict__ pmask) {
+    QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.np) return;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double fy = P.fy_b[s], fz = P.fz_b[s];
+    // issue the independent streaming loads before the dependent field gathers
+    const double q = P.q[s], gamma = P.gam[s];
+    const double py = P.py_s[s], pz = P.pz_s[s];
+    const double t1y = P.t1y[s], t1z = P.t1z[s], dpy = P.dpy[s], dpz = P.dpz[s];
+    const double y0 = P.y_s[s], z0 = P.z_s[s];
+    const double a_particle = P.ap[s], nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -589,23 +708,31 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     // by lives at (y, z + dz/2), bz at (y + dy/2, z)  (src/System_3d.cpp:180-181)
     const double by_particle = gather4(by, g.nz, jc, wrap_inc(jc, g.ny), ks, wrap_inc(ks, g.nz), fy, fzs);
     const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
-    const double q = P.q[s], gamma = P.gam[s];
-    double pyn = P.py_s[s] - P.t1y[s];
-    pyn += g.dx * gamma * P.dpy[s] / q;
+    double pyn = py - t1y;
+    pyn += g.dx * gamma * dpy / q;
     pyn -= g.dx * bz_particle;
-    double pzn = P.pz_s[s] - P.t1z[s];
-    pzn += g.dx * gamma * P.dpz[s] / q;
+    double pzn = pz - t1z;
+    pzn += g.dx * gamma * dpz / q;
     pzn += g.dx * by_particle;
     P.pyn[s] = pyn;
     P.pzn[s] = pzn;
-    const double ym = wrap_fast(P.y_s[s] + 0.5 * g.dx * pyn / q, g.ly);
-    const double zm = wrap_fast(P.z_s[s] + 0.5 * g.dx * pzn / q, g.lz);
+    {
+        // corrector (the gamma read above was the previous iteration's; this thread owns element s)
+        const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
+        const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) / q;
+        const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) / q;
+        P.gam[s] = gamma_c;
+        P.pxs[s] = px_c;
+        store_currents(P, s, nw, gamma_c, px_c);
+    }
+    const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn / q, g.ly);
+    const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn / q, g.lz);
     int jm, km;
     double f1, f2;
     locate(ym, g.dy, g.ny, jm, f1);
     locate(zm, g.dz, g.nz, km, f2);
     const int cm = jm * g.nz + km;
-    P.cell_m[s] = cm;
+    if (!FAST) P.cell_m[s] = cm;  // only the general path's cell sort reads it
     P.fy_m[s] = f1;
     P.fz_m[s] = f2;
     if (FAST) {
@@ -625,24 +752,9 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     }
 }
 
-// corrector gamma, px (src/System_3d.cpp:498-508) and the values deposited at :520-527.  Needs only py_next, pz_next, so it
-// runs concurrently with the psi_middle solve.
-__global__ void k_particles_correct_gamma(const Ctl * ctl, Geom g, Particles P) {
-    if (cancelled(ctl)) return;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.np) return;
-    const double nw = P.nw_s[s], pyn = P.pyn[s], pzn = P.pzn[s], py = P.py_s[s], pz = P.pz_s[s];
-    const double q = P.q[s], a_particle = P.ap[s];
-    const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
-    const double gamma = 0.5 * (1 + p_squared + a_particle + q * q) / q;
-    const double px = 0.5 * (1 + p_squared + a_particle - q * q) / q;
-    P.gam[s] = gamma;
-    P.pxs[s] = px;
-    store_currents(P, s, nw, gamma, px);
-}
-
 // values for the jy/jz deposit: n py_next / (1 + psi_middle@(y_middle, z_middle))  (src/System_3d.cpp:480-486)
 __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, const double * __restrict__ psi_middle) {
+    QPIC_KERNEL_BEGIN(KID_k_particles_currents_yz);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.np) return;
@@ -659,6 +771,7 @@ __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, co
 // (:601-608), new cell descriptor + population count for the next slice's lists; back to particle-id order
 __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b, const double * __restrict__ psi_middle,
                                     int * __restrict__ count) {
+    QPIC_KERNEL_BEGIN(KID_k_particles_advance);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.np) return;
@@ -700,6 +813,7 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
                                const double * __restrict__ by, const double * __restrict__ bz, const double * __restrict__ rho,
                                const double * __restrict__ jx, double * __restrict__ jy, double * __restrict__ jz,
                                const double * __restrict__ jy_next, const double * __restrict__ jz_next, int b_is_zero, int roll, int ignore_stop) {
+    QPIC_KERNEL_BEGIN(KID_k_end_of_slice);
     if (cancelled(ctl) && !ignore_stop) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.n2) return;
@@ -731,6 +845,7 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
 }
 
 __global__ void k_next_slice(Ctl * ctl) {
+    QPIC_KERNEL_BEGIN(KID_k_next_slice);
     if (cancelled(ctl)) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) ctl->slice -= 1;
 }
@@ -783,6 +898,7 @@ __device__ __forceinline__ int mod_wrap(int j, int n) {
 template <int NOUT, bool FINAL_PASS, bool YZ_INLINE>
 __global__ void __launch_bounds__(TILE_ACC * TILE_ACC)
     k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + (job.at_mid ? 1 : 0) + (job.o[0].bg_mode == 2 ? 2 : 0) + (YZ_INLINE ? 4 : 0) + (FINAL_PASS ? 8 : 0));
     if (FINAL_PASS) {
         if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
     } else if (cancelled(ctl)) {

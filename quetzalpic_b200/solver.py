@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "qpic_upload_field2d", "qpic_particle_count", "qpic_download_particles", "qpic_upload_particles",
     "qpic_set_current_slice", "qpic_solve_poisson_host", "qpic_solve_helmholtz_pair_host", "qpic_last_step_stats",
     "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
-    "qpic_fast_path_aborts", "qpic_wait_transfers",
+    "qpic_fast_path_aborts", "qpic_wait_transfers", "qpic_timeline_reset", "qpic_timeline_read", "qpic_timeline_kernel_name",
 ]
 
 
