@@ -79,8 +79,6 @@ struct qpic_ctx {
     Particles P = {};
     int *count = nullptr, *cursor = nullptr, *sums = nullptr, *tmp = nullptr;
     int *start_b = nullptr, *start_m = nullptr, *perm_b = nullptr, *perm_m = nullptr;
-    unsigned long long * pmask[3] = {nullptr, nullptr, nullptr};  // presence masks of the half-step classes, rotating per iteration
-    int pmask_cur = 0;
     int nchunks = 0;
     std::vector<void *> allocations;
 
@@ -398,13 +396,10 @@ int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, do
 
 dim3 tile_grid(qpic_ctx * c) { return dim3((c->g.nz + TILE - 1) / TILE, (c->g.ny + TILE - 1) / TILE); }
 
-TileOutput tile_output(const double * val, double sign, int at_mid, int stag_y, int stag_z, int bg_mode, const double * bg3, double * out, int out_3d) {
+TileOutput tile_output(const double * val, double sign, int bg_mode, const double * bg3, double * out, int out_3d) {
     TileOutput o;
     o.val = val;
     o.sign = sign;
-    o.at_mid = at_mid;
-    o.stag_y = stag_y;
-    o.stag_z = stag_z;
     o.bg_mode = bg_mode;
     o.bg3 = bg3;
     o.out = out;
@@ -421,51 +416,17 @@ TileJob tile_job(qpic_ctx * c) {
     return j;
 }
 
-// source-cell window (relative to the target cell) that can reach a target: 0 for deposits at (y,z); the half step moves
-// a particle by at most one cell ([-1,1]); a half-cell staggered grid adds one cell on the high side
-void tile_finish(qpic_ctx * c, TileJob & j) {
-    j.at_mid = j.o[0].at_mid;
-    j.pmask = c->pmask[c->pmask_cur];
-    // which (offset, half-cell) classes of a source cell at window position (dy, dz) can reach the target on any of the
-    // job's output grids: the particle must sit ry = dy + oy, rz = dz + oz cells above the target with
-    // ry == (staggered && lower half), same in z (see k_tile_deposit::visit)
-    for (int dy = -1; dy <= 2; dy++) {
-        for (int dz = -1; dz <= 2; dz++) {
-            unsigned long long need = 0;
-            for (int a = 0; a < j.nout; a++) {
-                for (int oy = -1; oy <= 1; oy++)
-                    for (int oz = -1; oz <= 1; oz++)
-                        for (int hy = 0; hy <= 1; hy++)
-                            for (int hz = 0; hz <= 1; hz++) {
-                                const int need_y = (j.o[a].stag_y && !hy) ? 1 : 0, need_z = (j.o[a].stag_z && !hz) ? 1 : 0;
-                                if (dy + oy == need_y && dz + oz == need_z) need |= 1ull << offset_class(oy, oz, hy, hz);
-                            }
-            }
-            j.need[(dy + 1) * 4 + (dz + 1)] = need;
-        }
-    }
-    j.wy_lo = j.wz_lo = j.at_mid ? -1 : 0;
-    j.wy_hi = j.wz_hi = j.at_mid ? 1 : 0;
-    for (int a = 0; a < j.nout; a++) {
-        if (j.o[a].stag_y) j.wy_hi = (j.at_mid ? 1 : 0) + 1;
-        if (j.o[a].stag_z) j.wz_hi = (j.at_mid ? 1 : 0) + 1;
-    }
-}
-
-int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, const char * name, bool yz_inline = false) {
-    tile_finish(c, j);
+// deposits at (y,z)
+int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, const char * name) {
     const dim3 grid = tile_grid(c), block(TILE_ACC, TILE_ACC);
-    if (yz_inline) {
-        auto kern = k_tile_deposit<2, false, true>;
-        QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
-    } else if (j.nout == 1) {
-        auto kern = final_pass ? k_tile_deposit<1, true, false> : k_tile_deposit<1, false, false>;
+    if (j.nout == 1) {
+        auto kern = final_pass ? k_tile_deposit<1, true> : k_tile_deposit<1, false>;
         QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
     } else if (j.nout == 2) {
-        auto kern = final_pass ? k_tile_deposit<2, true, false> : k_tile_deposit<2, false, false>;
+        auto kern = final_pass ? k_tile_deposit<2, true> : k_tile_deposit<2, false>;
         QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
     } else {
-        auto kern = final_pass ? k_tile_deposit<3, true, false> : k_tile_deposit<3, false, false>;
+        auto kern = final_pass ? k_tile_deposit<3, true> : k_tile_deposit<3, false>;
         QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
     }
     return check_launch(c, name);
@@ -475,18 +436,21 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
     j.nout = 1;
-    j.o[0] = tile_output(c->P.nw_s, -1.0, at_mid, 0, 0, 1, nullptr, c->fft_in, 0);
-    return launch_tile(c, st, j, false, at_mid ? "k_tile_deposit_charge_mid" : "k_tile_deposit_charge");
+    j.o[0] = tile_output(c->P.nw_s, -1.0, 1, nullptr, c->fft_in, 0);
+    if (!at_mid) return launch_tile(c, st, j, false, "k_tile_deposit_charge");
+    const dim3 block(TILE_ACC + 2, TILE_ACC + 2);
+    QPIC_LAUNCH(k_tile_bin_deposit<0>, tile_grid(c), block, tile_bin_smem_bytes<0>(), st, c->ctl, c->g, c->start_b, c->P, j);
+    return check_launch(c, "k_tile_deposit_charge_mid");
 }
 
 // deposits at (y,z): jx and / or rho + susceptibility(i)
 int enqueue_tile_base_currents(qpic_ctx * c, cudaStream_t st, bool with_jx, bool with_rho_chi, bool final_pass) {
     TileJob j = tile_job(c);
     int n = 0;
-    if (with_jx) j.o[n++] = tile_output(c->P.vjx, 1.0, 0, 0, 0, 2, c->f3[QPIC_F3_JX_BUNCH], c->f2[QPIC_F2_JX], 0);
+    if (with_jx) j.o[n++] = tile_output(c->P.vjx, 1.0, 2, c->f3[QPIC_F3_JX_BUNCH], c->f2[QPIC_F2_JX], 0);
     if (with_rho_chi) {
-        j.o[n++] = tile_output(c->P.vrho, 1.0, 0, 0, 0, 2, c->f3[QPIC_F3_RHO_BUNCH], c->f2[QPIC_F2_RHO], 0);
-        j.o[n++] = tile_output(c->P.vchi, 1.0, 0, 0, 0, 0, nullptr, c->f3[QPIC_F3_SUSCEPTIBILITY], 1);
+        j.o[n++] = tile_output(c->P.vrho, 1.0, 2, c->f3[QPIC_F3_RHO_BUNCH], c->f2[QPIC_F2_RHO], 0);
+        j.o[n++] = tile_output(c->P.vchi, 1.0, 0, nullptr, c->f3[QPIC_F3_SUSCEPTIBILITY], 1);
     }
     j.nout = n;
     return launch_tile(c, st, j, final_pass, with_jx ? (with_rho_chi ? "k_tile_deposit_jx_rho_chi" : "k_tile_deposit_jx") : "k_tile_deposit_rho_chi");
@@ -497,11 +461,13 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     TileJob j = tile_job(c);
     j.nout = 2;
     // values n py_next / (1 + psi_middle@particle) are formed inside the deposit (no k_particles_currents_yz on this path)
-    j.o[0] = tile_output(c->P.pyn, 1.0, 1, 1, 0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
-    j.o[1] = tile_output(c->P.pzn, 1.0, 1, 0, 1, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
+    j.o[0] = tile_output(c->P.pyn, 1.0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
+    j.o[1] = tile_output(c->P.pzn, 1.0, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
     j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
     j.nw = c->P.nw_s;
-    return launch_tile(c, st, j, false, "k_tile_deposit_jy_jz", true);
+    const dim3 block(TILE_ACC + 3, TILE_ACC + 3);
+    QPIC_LAUNCH(k_tile_bin_deposit<1>, tile_grid(c), block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
+    return check_launch(c, "k_tile_deposit_jy_jz");
 }
 
 // ---- potentials
@@ -584,30 +550,14 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     cudaStream_t sb = c->profiling ? c->stream : c->stream2;  // per-kernel timing wants one serial stream
     QPIC_TRY(enqueue_slice_head(c, fast, M > 0, M == 0));
     for (int it = 0; it < M; it++) {
-        // Presence-mask buffer of this iteration.  The buffer of the NEXT predictor (next iteration, or iteration 0 of the
-        // next slice: the graph is replayed) is cleared on branch B meanwhile, so it must differ from the one in use.
-        auto mask_buffer = [M](int i) { return (i == M - 1 && i > 0 && i % 3 == 0) ? 1 : i % 3; };
-        c->pmask_cur = mask_buffer(it);
-        const int pmask_next = mask_buffer(it + 1 < M ? it + 1 : 0);
-        if (fast && pmask_next == c->pmask_cur) {
-            // M == 1: a single buffer, cleared in line
-            QPIC_LAUNCH_FLAT(k_clear_masks, 148, 256, 0, sa, c->ctl, c->pmask[c->pmask_cur], c->g.n2);
-            QPIC_TRY(check_launch(c, "k_clear_masks"));
-        }
         if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
-            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
-                             c->pmask[c->pmask_cur]);
+            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
         // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored
         QPIC_TRY(stream_depend(c, sa, sb));
         QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
-        // the other presence-mask buffer was last read by the previous iteration's deposits: clear it for the next one
-        if (fast && pmask_next != c->pmask_cur) {
-            QPIC_LAUNCH_FLAT(k_clear_masks, 148, 256, 0, sb, c->ctl, c->pmask[pmask_next], c->g.n2);
-            QPIC_TRY(check_launch(c, "k_clear_masks"));
-        }
         // branch A: psi_middle, then jy_next / jz_next
         if (!fast) QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
         QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
@@ -938,6 +888,9 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
         }
     }
+    if (tile_bin_smem_bytes<1>() > SMEM_DEFAULT_LIMIT) {
+        QPIC_CUDA(c, cudaFuncSetAttribute(k_tile_bin_deposit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bin_smem_bytes<1>()));
+    }
     // the inverse-symbol tables of the two operators of the sweep (psi: D = 0, half spectrum; By + i Bz: D, full spectrum)
     if (c->pow2_y) {
         const double * unused = nullptr;
@@ -969,7 +922,6 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(dev_alloc(c, &c->sums, (size_t)c->nchunks));
     QPIC_TRY(dev_alloc(c, &c->start_b, n2 + 1));
     QPIC_TRY(dev_alloc(c, &c->start_m, n2 + 1));
-    for (int b = 0; b < 3; b++) QPIC_TRY(dev_alloc(c, &c->pmask[b], n2));
     QPIC_TRY(alloc_particles(c, 0));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cur = g.nx - 1;

@@ -40,7 +40,6 @@ enum KernelId {
     KID_k_potential_fixup,
     KID_k_particles_to_slots,
     KID_k_particles_gamma,
-    KID_k_clear_masks,
     KID_k_particles_predict,
     KID_k_particles_currents_yz,
     KID_k_particles_advance,
@@ -61,7 +60,7 @@ enum KernelId {
     KID_k_p2_rows_c2c,
     KID_COUNT
 };
-#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_clear_masks", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c" }
+#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c" }
 
 #ifdef QPIC_EMU
 #define QPIC_KERNEL_BEGIN(id) ((void)0)
@@ -672,22 +671,11 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 // predictor: py_next, pz_next (src/System_3d.cpp:416-433), half-step position (:436-443) and its cell descriptor.
 // FAST (sort-free deposit): records the cell offset of the half step instead of counting cell populations, and raises
 // Ctl::fast_fail if a particle leaves the +-1 cell window the tile deposit covers.
-// clears a presence-mask buffer.  A kernel rather than a memset node: memset nodes of a graph may be executed by a copy
-// engine and then queue behind the large streaming transfers of the caller (qpic_download_slices3d).
-__global__ void k_clear_masks(const Ctl * ctl, unsigned long long * __restrict__ m, int n) {
-    QPIC_KERNEL_BEGIN(KID_k_clear_masks);
-    if (cancelled(ctl)) return;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) m[t] = 0ull;
-}
-
-// class of a half step for the presence masks of the tile deposit: cell offset (oy, oz) in [-1,1]^2 and the half-cell bits
-__device__ __host__ __forceinline__ int offset_class(int oy, int oz, int hy, int hz) { return ((oy + 1) * 3 + (oz + 1)) * 4 + hy * 2 + hz; }
-
 // The corrector gamma / px (src/System_3d.cpp:498-508) and the values deposited at :520-527 depend only on py_next, pz_next,
 // so they are formed here as well: one streaming pass over the slot arrays per iteration instead of two.
 template <bool FAST>
 __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
-                                    int * __restrict__ count, unsigned long long * __restrict__ pmask) {
+                                    int * __restrict__ count) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -743,9 +731,6 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
             P.off_m[s] = pack_offset(0, 0, 0.0, 0.0, kc);
         } else {
             P.off_m[s] = pack_offset(oy, oz, f1, f2, kc);
-            // which (offset, half-cell) classes occur in this source cell: lets the deposit skip cells that cannot
-            // contribute to a target (integer OR: order independent)
-            atomicOr(&pmask[c], 1ull << offset_class(oy, oz, f1 >= 0.5 ? 1 : 0, f2 >= 0.5 ? 1 : 0));
         }
     } else {
         atomicAdd(&count[cm], 1);
@@ -850,26 +835,36 @@ __global__ void k_next_slice(Ctl * ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) ctl->slice -= 1;
 }
 
-// ------------------------------------------------------------------------------------------------ sort-free tile deposit
-// Deterministic deposition without sorting the half-step positions.  A block owns a TILE x TILE patch of grid nodes and
-// runs ONE THREAD PER TARGET CELL of the patch (plus one halo row / column below it).  A particle's target cell on an
-// output grid is  source cell + offset, where the source cell is its cell at the start of the slice (the slot order
-// groups particles by that cell, so a cell's particles are one contiguous range) and the offset lies in a small
-// window: 0 for deposits at (y,z); [-1,1] for the half-step position, one cell more for the half-cell staggered jy / jz
-// grids.  The thread scans the source cells that can reach its target cell in a fixed order, picks the particles whose
-// packed offset code (written by the predictor) points at it, and adds their four CIC corner contributions
-// (src/array_utils.cpp:75-82) in slot order into four private "corner sums".  After one barrier every node sums the
-// corner sums of its four neighbouring target cells, again in a fixed order.  No floating-point atomics, no dependence on
-// scheduling: bit-reproducible.  The halo target cells are recomputed by the neighbouring block (same arithmetic, same bits).
+// ------------------------------------------------------------------------------------------------ sort-free tile deposits
+// Deterministic deposition without sorting the half-step positions globally.  A block owns a TILE x TILE patch of grid
+// nodes = the TILE_ACC x TILE_ACC target cells whose CIC corners touch them (one halo row / column below the patch, recomputed
+// identically by the neighbouring block).  The slot order groups particles by their cell at the start of the slice, so a
+// cell's particles are one contiguous slot range.  Every target cell sums the four CIC corner contributions
+// (src/array_utils.cpp:75-82) of the particles that land in it IN ASCENDING SLOT ORDER into four private corner sums; after a
+// barrier every node adds the corner sums of its four neighbouring target cells in a fixed order.  No floating-point
+// atomics, no dependence on scheduling: bit-reproducible.
+//
+//   k_tile_deposit       deposits at (y,z): the target cell IS the source cell, a thread walks its own cell's particles.
+//   k_tile_bin_deposit   deposits at the half-step position: a particle moves by at most one cell per half step (checked by
+//                        the predictor, Ctl::fast_fail), so the particles that can land in the block's target cells sit in
+//                        its source cells = targets + 1 ring (+1 more on the high side of a half-cell staggered grid).
+//                        Phase A: one thread per SOURCE cell reads the packed offset codes of its particles and appends
+//                        each slot to the list of its target cell in shared memory (integer atomics -- only the order of
+//                        the list depends on scheduling).  Phase B: one thread per TARGET cell sorts its short list by slot
+//                        (canonical order) and accumulates.  Lists longer than BIN_K fall back to an in-order scan of the
+//                        source window.  Every particle visit is useful work: no divergent window scans.
 constexpr int TILE = 16;
 constexpr int TILE_ACC = TILE + 1;
+constexpr int TILE_CELLS = TILE_ACC * TILE_ACC;
 constexpr int TILE_MAX_OUT = 3;
+#ifndef QPIC_BIN_K
+#define QPIC_BIN_K 16  // list capacity per target cell and output (tests build the emulator with 1 to force the in-order fallback)
+#endif
+constexpr int BIN_K = QPIC_BIN_K;
 
 struct TileOutput {
     const double * val;    // per-particle value (slot order)
     double sign;           // +1 / -1 (charge deposits use -n)
-    int at_mid;            // 1: deposit at the half-step position (fy_m, fz_m, off_m), 0: at (y,z) (fy_b, fz_b)
-    int stag_y, stag_z;    // output grid origin shifted by +dy/2 / +dz/2 (jy_next / jz_next, src/System_3d.cpp:190-193)
     int bg_mode;           // 0: none, 1: jx_bunch(i) - rho_bunch(i) - rho_ion (psi source, :345), 2: bg3(i)
     const double * bg3;    // bg_mode 2: a 3-D array whose slice i initialises the sum (rho_bunch / jx_bunch, :384-385)
     double * out;          // 2-D array, or a 3-D array when out_3d
@@ -878,13 +873,9 @@ struct TileOutput {
 
 struct TileJob {
     int nout;
-    int at_mid;                        // all outputs of a job share the position set
-    int wy_lo, wy_hi, wz_lo, wz_hi;    // window of source cells relative to the target cell, union over the outputs
     TileOutput o[TILE_MAX_OUT];
     const double *jxb3, *rhob3, *rho_ion;  // for bg_mode 1
-    const double *psi_mid, *nw;            // YZ_INLINE jobs
-    const unsigned long long * pmask;      // at_mid jobs: per source cell, which offset classes occur (see offset_class)
-    unsigned long long need[16];           // at_mid jobs: classes that reach the target from window position (dy+1)*4 + (dz+1)
+    const double *psi_mid, *nw;            // jy/jz job
 };
 
 __device__ __forceinline__ int mod_wrap(int j, int n) {
@@ -892,132 +883,222 @@ __device__ __forceinline__ int mod_wrap(int j, int n) {
     return j < 0 ? j + n : j;
 }
 
-// YZ_INLINE: the job is the (jy_next, jz_next) pair and the deposited values n py_next / (1 + psi_middle@particle),
-// n pz_next / (1 + psi_middle@particle) (src/System_3d.cpp:483-485) are formed here instead of being stored by a
-// separate particle kernel; o[0].val / o[1].val then hold py_next / pz_next and job.psi_mid, job.nw are used.
-template <int NOUT, bool FINAL_PASS, bool YZ_INLINE>
-__global__ void __launch_bounds__(TILE_ACC * TILE_ACC)
-    k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
-    QPIC_KERNEL_BEGIN(KID_COUNT + (job.at_mid ? 1 : 0) + (job.o[0].bg_mode == 2 ? 2 : 0) + (YZ_INLINE ? 4 : 0) + (FINAL_PASS ? 8 : 0));
+// nodes of the patch: own cell's (1-fy)(1-fz) sum, then the y-, z- and diagonal neighbours' sums, fixed order.
+// acc layout: [output][corner][target cell] (conflict-free), target cell (ty, tz) = (node - patch origin + 1)
+template <int NOUT>
+__device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g, const TileJob & job, const double * acc, int ty, int tz, int j, int k) {
+    if (ty < 1 || tz < 1 || j >= g.ny || k >= g.nz) return;
+    const int t = j * g.nz + k;
+    const size_t off3 = (size_t)ctl->slice * g.n2 + t;
+#pragma unroll
+    for (int a = 0; a < NOUT; a++) {
+        const TileOutput & o = job.o[a];
+        double v = 0.0;
+        if (o.bg_mode == 1) {
+            const double jb_ = job.jxb3 ? job.jxb3[off3] : 0.0;
+            const double rb_ = job.rhob3 ? job.rhob3[off3] : 0.0;
+            v = jb_ - rb_ - job.rho_ion[t];
+        } else if (o.bg_mode == 2 && o.bg3) {
+            v = o.bg3[off3];
+        }
+        const double * acc_a = acc + a * 4 * TILE_CELLS;
+        v += acc_a[0 * TILE_CELLS + ty * TILE_ACC + tz];
+        v += acc_a[1 * TILE_CELLS + (ty - 1) * TILE_ACC + tz];
+        v += acc_a[2 * TILE_CELLS + ty * TILE_ACC + tz - 1];
+        v += acc_a[3 * TILE_CELLS + (ty - 1) * TILE_ACC + tz - 1];
+        o.out[o.out_3d ? off3 : (size_t)t] = v;
+    }
+}
+
+template <int NOUT, bool FINAL_PASS>
+__global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + (job.o[0].bg_mode == 2 ? 2 : 0) + (FINAL_PASS ? 8 : 0));
     if (FINAL_PASS) {
         if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
     } else if (cancelled(ctl)) {
         return;
     }
-    __shared__ double acc[NOUT * TILE_ACC * TILE_ACC * 4];
+    __shared__ double acc[NOUT * 4 * TILE_CELLS];
     const int ay = threadIdx.y, az = threadIdx.x;
-    const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
-    const int jt = j0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped target cell
-    const double * __restrict__ fyv = job.at_mid ? P.fy_m : P.fy_b;
-    const double * __restrict__ fzv = job.at_mid ? P.fz_m : P.fz_b;
-    const int * __restrict__ code_v = P.off_m;
-    const int at_mid = job.at_mid;
-    int stag_y_bits = 0, stag_z_bits = 0;
-#pragma unroll
-    for (int a = 0; a < NOUT; a++) {
-        stag_y_bits |= (job.o[a].stag_y ? 1 : 0) << a;
-        stag_z_bits |= (job.o[a].stag_z ? 1 : 0) << a;
-    }
-
+    const int tcell = ay * TILE_ACC + az;
+    const int jt = blockIdx.y * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
+    const int cell = mod_wrap(jt, g.ny) * g.nz + mod_wrap(kt, g.nz);
+    const int s0 = start[cell], s1 = start[cell + 1];
     double c00[NOUT], c10[NOUT], c01[NOUT], c11[NOUT];
 #pragma unroll
     for (int a = 0; a < NOUT; a++) c00[a] = c10[a] = c01[a] = c11[a] = 0.0;
-
-    // particle s sits (ry, rz) cells above the target cell (hy / hz: upper half of its cell)
-    auto visit = [&](int s, int ry, int rz, int hy, int hz) {
-        if ((ry | rz) & ~1) return;  // not within [0,1] x [0,1]: cannot reach this target on any grid flavour
-        int mask = 0;
+    // chunks of 4 particles: all loads of a chunk are issued before the (ordered) accumulation
+    for (int sb = s0; sb < s1; sb += 4) {
+        double fy[4], fz[4], v[NOUT][4];
 #pragma unroll
-        for (int a = 0; a < NOUT; a++) {
-            // on a staggered grid a particle in the lower half of its cell belongs to the staggered cell below
-            const int need_y = (stag_y_bits >> a) & (hy ^ 1), need_z = (stag_z_bits >> a) & (hz ^ 1);
-            if (ry == need_y && rz == need_z) mask |= 1 << a;
-        }
-        if (!mask) return;
-        const double fy = fyv[s], fz = fzv[s];
-        double w = 1.0, nw = 0.0;
-        if (YZ_INLINE) {
-            // psi_middle at the particle: its own (unstaggered) half-step cell is (jt + ry, kt + rz)
-            int jm = jt + ry, km = kt + rz;
-            jm += (jm < 0) ? g.ny : 0;
-            jm -= (jm >= g.ny) ? g.ny : 0;
-            km += (km < 0) ? g.nz : 0;
-            km -= (km >= g.nz) ? g.nz : 0;
-            w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
-            nw = job.nw[s];
+        for (int u = 0; u < 4; u++) {
+            const int s = sb + u < s1 ? sb + u : s0;
+            fy[u] = P.fy_b[s];
+            fz[u] = P.fz_b[s];
+#pragma unroll
+            for (int a = 0; a < NOUT; a++) v[a][u] = job.o[a].val[s];
         }
 #pragma unroll
-        for (int a = 0; a < NOUT; a++) {
-            if (!((mask >> a) & 1)) continue;
-            const TileOutput & o = job.o[a];
-            const double ty = o.stag_y ? (hy ? fy - 0.5 : fy + 0.5) : fy;
-            const double tz = o.stag_z ? (hz ? fz - 0.5 : fz + 0.5) : fz;
-            const double v = YZ_INLINE ? nw * o.val[s] / w : o.sign * o.val[s];
-            c00[a] += v * (1 - ty) * (1 - tz);
-            c10[a] += v * ty * (1 - tz);
-            c01[a] += v * (1 - ty) * tz;
-            c11[a] += v * ty * tz;
-        }
-    };
-
-    int jb = mod_wrap(jt + job.wy_lo, g.ny);
-    const int kb0 = mod_wrap(kt + job.wz_lo, g.nz);
-    for (int dy_ = job.wy_lo; dy_ <= job.wy_hi; dy_++) {
-        int kb = kb0;
-        for (int dz_ = job.wz_lo; dz_ <= job.wz_hi; dz_++) {
-            const int cell = jb * g.nz + kb;
-            kb = wrap_inc(kb, g.nz);
-            if (at_mid) {
-                // skip source cells that hold no particle of a class that can reach this target from this position
-                if (!(job.pmask[cell] & job.need[(dy_ + 1) * 4 + (dz_ + 1)])) continue;
-                const int s1 = start[cell + 1];
-                for (int s = start[cell]; s < s1; s++) {
-                    const int code = code_v[s];
-                    visit(s, dy_ + (code & 7) - 2, dz_ + ((code >> 3) & 7) - 2, (code >> 6) & 1, (code >> 7) & 1);
+        for (int u = 0; u < 4; u++) {
+            if (sb + u < s1) {
+#pragma unroll
+                for (int a = 0; a < NOUT; a++) {
+                    const double vv = job.o[a].sign * v[a][u];
+                    c00[a] += vv * (1 - fy[u]) * (1 - fz[u]);
+                    c10[a] += vv * fy[u] * (1 - fz[u]);
+                    c01[a] += vv * (1 - fy[u]) * fz[u];
+                    c11[a] += vv * fy[u] * fz[u];
                 }
-            } else {
-                const int s1 = start[cell + 1];
-                for (int s = start[cell]; s < s1; s++) visit(s, dy_, dz_, 1, 1);
             }
         }
-        jb = wrap_inc(jb, g.ny);
     }
 #pragma unroll
     for (int a = 0; a < NOUT; a++) {
-        double * t4 = acc + ((a * TILE_ACC + ay) * TILE_ACC + az) * 4;
-        t4[0] = c00[a];
-        t4[1] = c10[a];
-        t4[2] = c01[a];
-        t4[3] = c11[a];
+        double * acc_a = acc + a * 4 * TILE_CELLS;
+        acc_a[0 * TILE_CELLS + tcell] = c00[a];
+        acc_a[1 * TILE_CELLS + tcell] = c10[a];
+        acc_a[2 * TILE_CELLS + tcell] = c01[a];
+        acc_a[3 * TILE_CELLS + tcell] = c11[a];
     }
     __syncthreads();
+    tile_store_nodes<NOUT>(ctl, g, job, acc, ay, az, jt, kt);
+}
 
-    // nodes of the patch: own cell's (1-fy)(1-fz) sum, then the y-, z- and diagonal neighbours' sums, fixed order
-    if (ay >= 1 && az >= 1) {
-        const int j = jt, k = kt;
-        if (j < g.ny && k < g.nz) {
-            const int t = j * g.nz + k;
-            const size_t off3 = (size_t)ctl->slice * g.n2 + t;
+// MODE 0: psi_middle source = jx_bunch(i) - rho_bunch(i) - rho_ion + deposit(-n) at the half-step positions (src/System_3d.cpp:446-457)
+// MODE 1: (jy_next, jz_next), staggered by half a cell in y / z (src/System_3d.cpp:472-486, :190-193); the deposited values
+//         n py_next / (1 + psi_middle@particle), n pz_next / (1 + psi_middle@particle) (:483-485) are formed here; o[0].val /
+//         o[1].val hold py_next / pz_next.
+// Block = (TILE_ACC + 2 + MODE) x (TILE_ACC + 2 + MODE) threads: thread (sy, sz) <-> source cell (j0 - 2 + sy, k0 - 2 + sz) in phase
+// A, <-> target cell (j0 - 2 + sy, k0 - 2 + sz) for 1 <= sy, sz <= TILE_ACC in phase B (j0, k0: first node of the patch).
+template <int MODE>
+inline size_t tile_bin_smem_bytes() {
+    constexpr int NOUT = MODE == 0 ? 1 : 2;
+    return (size_t)NOUT * TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
+    k_tile_bin_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + 1 + 4 * MODE);
+    if (cancelled(ctl)) return;
+    constexpr int NOUT = MODE == 0 ? 1 : 2;
+    QPIC_DYN_SMEM(double, acc);                                            // [NOUT][4][TILE_CELLS]
+    int * cnt = reinterpret_cast<int *>(acc + NOUT * 4 * TILE_CELLS);      // [NOUT][TILE_CELLS]
+    int * lst = cnt + NOUT * TILE_CELLS;                                   // [NOUT][BIN_K][TILE_CELLS]
+    const int sy = threadIdx.y, sz = threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
+    const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
+    const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
+    // staggering of output a in y / z
+    auto stag_y = [](int a) { return MODE == 1 && a == 0; };
+    auto stag_z = [](int a) { return MODE == 1 && a == 1; };
+
+    for (int i = tid; i < NOUT * TILE_CELLS; i += nthreads) cnt[i] = 0;
+    __syncthreads();
+
+    // ---- phase A: bin the particles of this source cell
+    {
+        const int cell = mod_wrap(ju, g.ny) * g.nz + mod_wrap(ku, g.nz);
+        const int s0 = start[cell], s1 = start[cell + 1];
+        for (int sb = s0; sb < s1; sb += 4) {
+            int code[4];
 #pragma unroll
-            for (int a = 0; a < NOUT; a++) {
-                const TileOutput & o = job.o[a];
-                double v = 0.0;
-                if (o.bg_mode == 1) {
-                    const double jb_ = job.jxb3 ? job.jxb3[off3] : 0.0;
-                    const double rb_ = job.rhob3 ? job.rhob3[off3] : 0.0;
-                    v = jb_ - rb_ - job.rho_ion[t];
-                } else if (o.bg_mode == 2 && o.bg3) {
-                    v = o.bg3[off3];
+            for (int u = 0; u < 4; u++) code[u] = P.off_m[sb + u < s1 ? sb + u : s0];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (sb + u >= s1) break;
+                const int oy = (code[u] & 7) - 2, oz = ((code[u] >> 3) & 7) - 2;
+                const int hy = (code[u] >> 6) & 1, hz = (code[u] >> 7) & 1;
+#pragma unroll
+                for (int a = 0; a < NOUT; a++) {
+                    // on a staggered grid a particle in the lower half of its cell belongs to the staggered cell below
+                    const int ty = sy - 1 + oy - ((stag_y(a) && !hy) ? 1 : 0);
+                    const int tz = sz - 1 + oz - ((stag_z(a) && !hz) ? 1 : 0);
+                    if (ty >= 0 && ty < TILE_ACC && tz >= 0 && tz < TILE_ACC) {
+                        const int t = ty * TILE_ACC + tz;
+                        const int pos = atomicAdd(&cnt[a * TILE_CELLS + t], 1);
+                        if (pos < BIN_K) lst[(a * BIN_K + pos) * TILE_CELLS + t] = ((sb + u) << 2) | (hy << 1) | hz;
+                    }
                 }
-                const double * acc_a = acc + a * TILE_ACC * TILE_ACC * 4;
-                v += acc_a[(ay * TILE_ACC + az) * 4 + 0];
-                v += acc_a[((ay - 1) * TILE_ACC + az) * 4 + 1];
-                v += acc_a[(ay * TILE_ACC + az - 1) * 4 + 2];
-                v += acc_a[((ay - 1) * TILE_ACC + az - 1) * 4 + 3];
-                o.out[o.out_3d ? off3 : (size_t)t] = v;
             }
         }
     }
+    __syncthreads();
+
+    // ---- phase B: ordered accumulation per target cell
+    const bool is_target = sy >= 1 && sy <= TILE_ACC && sz >= 1 && sz <= TILE_ACC;
+    const int ty = sy - 1, tz = sz - 1;
+    const int tcell = ty * TILE_ACC + tz;
+    if (is_target) {
+#pragma unroll
+        for (int a = 0; a < NOUT; a++) {
+            double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
+            const double * __restrict__ val = job.o[a].val;
+            auto visit = [&](int s, int hy, int hz) {
+                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                double v;
+                if (MODE == 1) {
+                    // psi_middle at the particle: its own (unstaggered) half-step cell
+                    int jm = ju + ((stag_y(a) && !hy) ? 1 : 0), km = ku + ((stag_z(a) && !hz) ? 1 : 0);
+                    jm += (jm < 0) ? g.ny : 0;
+                    jm -= (jm >= g.ny) ? g.ny : 0;
+                    km += (km < 0) ? g.nz : 0;
+                    km -= (km >= g.nz) ? g.nz : 0;
+                    const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
+                    v = job.nw[s] * val[s] / w;
+                } else {
+                    v = job.o[a].sign * val[s];
+                }
+                const double wy = stag_y(a) ? (hy ? fy - 0.5 : fy + 0.5) : fy;
+                const double wz = stag_z(a) ? (hz ? fz - 0.5 : fz + 0.5) : fz;
+                c00 += v * (1 - wy) * (1 - wz);
+                c10 += v * wy * (1 - wz);
+                c01 += v * (1 - wy) * wz;
+                c11 += v * wy * wz;
+            };
+            const int n = cnt[a * TILE_CELLS + tcell];
+            int * mine = lst + a * BIN_K * TILE_CELLS + tcell;  // entry i at mine[i * TILE_CELLS]
+            if (n <= BIN_K) {
+                // insertion sort: ascending slot = canonical order
+                for (int i = 1; i < n; i++) {
+                    const int e = mine[i * TILE_CELLS];
+                    int q = i - 1;
+                    while (q >= 0 && mine[q * TILE_CELLS] > e) {
+                        mine[(q + 1) * TILE_CELLS] = mine[q * TILE_CELLS];
+                        q--;
+                    }
+                    mine[(q + 1) * TILE_CELLS] = e;
+                }
+                for (int i = 0; i < n; i++) {
+                    const int e = mine[i * TILE_CELLS];
+                    visit(e >> 2, (e >> 1) & 1, e & 1);
+                }
+            } else {
+                // crowded target (strong compression): scan the source window in order
+                const int hi_y = stag_y(a) ? 2 : 1, hi_z = stag_z(a) ? 2 : 1;
+                for (int dy_ = -1; dy_ <= hi_y; dy_++) {
+                    for (int dz_ = -1; dz_ <= hi_z; dz_++) {
+                        const int cell = mod_wrap(ju + dy_, g.ny) * g.nz + mod_wrap(ku + dz_, g.nz);
+                        const int e1 = start[cell + 1];
+                        for (int s = start[cell]; s < e1; s++) {
+                            const int code = P.off_m[s];
+                            const int hy = (code >> 6) & 1, hz = (code >> 7) & 1;
+                            const int ry = dy_ + (code & 7) - 2 - ((stag_y(a) && !hy) ? 1 : 0);
+                            const int rz = dz_ + ((code >> 3) & 7) - 2 - ((stag_z(a) && !hz) ? 1 : 0);
+                            if (ry == 0 && rz == 0) visit(s, hy, hz);
+                        }
+                    }
+                }
+            }
+            double * acc_a = acc + a * 4 * TILE_CELLS;
+            acc_a[0 * TILE_CELLS + tcell] = c00;
+            acc_a[1 * TILE_CELLS + tcell] = c10;
+            acc_a[2 * TILE_CELLS + tcell] = c01;
+            acc_a[3 * TILE_CELLS + tcell] = c11;
+        }
+    }
+    __syncthreads();
+    if (is_target) tile_store_nodes<NOUT>(ctl, g, job, acc, ty, tz, ju, ku);
 }
 
 }  // namespace qpic
