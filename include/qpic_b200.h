@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define QPIC_ABI_VERSION 1
+#define QPIC_ABI_VERSION 2
 
 typedef enum {
     QPIC_OK = 0,
@@ -51,6 +51,12 @@ typedef struct {
     int stop_check_interval;       /* the host polls the device stop flag every this many slices (<=0: 64) */
     int force_general_deposit;     /* != 0: always use the sort-based deposit (valid for any half-step displacement) instead of
                                       trying the sort-free tile deposit first (valid for displacements <= 1 cell, with rollback) */
+    /* slab-decomposed sweep of ONE large transverse grid on several GPUs (dist_world > 1, one context per GPU): the context
+     * owns rows [dist_rank * ny / dist_world, (dist_rank + 1) * ny / dist_world) and the particles in them.  Power-of-two ny, nz
+     * >= 64 with ny / dist_world a multiple of 16 and >= 32; after qpic_create the ranks exchange their regions
+     * (qpic_dist_*) before anything else is called. */
+    int dist_rank, dist_world;
+    size_t particle_capacity;      /* distributed: room for the particles this rank may hold after migration (0: 1.25 x + 64K) */
 } qpic_params;
 
 /* fills *p with the reference defaults (psi_threshold 1e-4, D 10, threshold_B 100, device 0, graph on) */
@@ -140,6 +146,21 @@ int qpic_profile_slices(qpic_ctx * ctx, int nslices, char * report, size_t repor
 int qpic_timeline_reset(qpic_ctx * ctx);
 long qpic_timeline_read(qpic_ctx * ctx, long long * records, long cap);
 const char * qpic_timeline_kernel_name(int kernel_id);
+
+/* ---- slab-decomposed multi-GPU sweep (qpic_params::dist_world > 1).  Each rank allocates an "exchange region" of
+ * identical layout; the ranks map each other's regions and from then on exchange transform transposes, halo rows and
+ * migrating particles with peer loads / stores over NVLink inside the slice graph.  Between processes: every rank calls
+ * qpic_dist_ipc_handle, the 64-byte handles are all-gathered by the host (MPI / torch.distributed), then every rank calls
+ * qpic_dist_attach_ipc with the handles in rank order.  Inside one process: qpic_dist_attach_pointers with the
+ * qpic_dist_region pointers of all ranks.  Fields are downloaded per rank (qpic_download_*): own rows are valid.
+ * qpic_init_wake_particles takes the particles of the rank's own rows only. */
+size_t qpic_dist_region_bytes(const qpic_ctx * ctx);
+void * qpic_dist_region(qpic_ctx * ctx);
+int qpic_dist_ipc_handle(qpic_ctx * ctx, void * handle64);
+int qpic_dist_attach_ipc(qpic_ctx * ctx, const void * handles);
+int qpic_dist_attach_pointers(qpic_ctx * ctx, void * const * regions);
+/* first own row / number of own rows (whole grid on a single GPU) */
+int qpic_dist_row_range(const qpic_ctx * ctx, int * row0, int * nrows);
 
 /* ---- streaming transfers for callers whose arrays live in host memory (System_3d's array3d members).  They run on a
  * separate copy stream and overlap the sweep: an upload is waited for by every slice queued after the call, a download

@@ -19,6 +19,7 @@
 #include "qpic_fft.cuh"
 #include "qpic_fft_pow2.cuh"
 #include "qpic_kernels.cuh"
+#include "qpic_dist.cuh"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -73,7 +74,6 @@ struct qpic_ctx {
     double2 * spec = nullptr;  // ny * nz complex (the psi solves use the first ny*(nz/2+1))
     double2 *spec_row0 = nullptr, *spec_colsum = nullptr;  // nz/2+1 each: U(0,k) and sum_j U(j,k) for the fused potential fix-up
     int * cols_ticket = nullptr;                           // "last block" counter of the column kernel
-    double * border_mean = nullptr;                        // mean over first column U first row of the solved potential
     double *sy = nullptr, *sz = nullptr;
     DeviceFft fy, fz;
     Particles P = {};
@@ -107,6 +107,20 @@ struct qpic_ctx {
     float last_ms = 0.f;
     long last_launches = 0;
     long launch_counter = 0;
+
+    // slab-decomposed multi-GPU sweep (qpic_dist.cuh)
+    struct Dist {
+        bool on = false, attached = false;
+        DistView v = {};
+        char * region = nullptr;
+        int cpr_half = 0, cpr_full = 0;            // columns per rank of the half / full spectrum
+        int col0_half = 0, ncols_half = 0, col0_full = 0, ncols_full = 0;
+        int * out_count = nullptr;                 // emigrant counters [2]
+        long long * epoch = nullptr;
+        int live0 = 0;                             // particles handed to qpic_init_wake_particles
+        std::vector<void *> opened;                // cudaIpcOpenMemHandle mappings
+    } dist;
+    double * partials = nullptr;  // border-sum partials of the fused potential fix-up, [world][4] (inside the region when distributed)
 
     // per-kernel profiling (qpic_profile_slices): an event after every launch of an eager slice
     bool profiling = false;
@@ -291,6 +305,78 @@ CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, nullptr, c->P.
 // lists of the half-step positions: permutation of slots
 CellLists lists_mid(qpic_ctx * c) { return CellLists{c->start_m, c->perm_m, c->P.fy_m, c->P.fz_m}; }
 
+// ---- where things live, single GPU vs one slab of a distributed grid
+int row_first(const qpic_ctx * c) { return c->dist.on ? c->dist.v.row0 : 0; }
+int row_count(const qpic_ctx * c) { return c->dist.on ? c->dist.v.ny_loc : c->g.ny; }
+
+SpecMap spec_map(const qpic_ctx * c, bool full) {
+    SpecMap m = {};
+    if (c->dist.on) {
+        m.world = c->dist.v.world;
+        m.cpr = full ? c->dist.cpr_full : c->dist.cpr_half;
+        for (int q = 0; q < m.world; q++) m.base[q] = reinterpret_cast<double2 *>(c->dist.v.base[q] + c->dist.v.lay.cols);
+    } else {
+        m.world = 1;
+        m.cpr = full ? c->g.nz : c->g.nz / 2 + 1;
+        m.base[0] = c->spec;
+    }
+    return m;
+}
+
+SpecMap partials_map(const qpic_ctx * c) {
+    SpecMap m = {};
+    m.world = c->dist.on ? c->dist.v.world : 1;
+    for (int q = 0; q < m.world; q++) {
+        m.base[q] = c->dist.on ? reinterpret_cast<double2 *>(c->dist.v.base[q] + c->dist.v.lay.partials) : reinterpret_cast<double2 *>(c->partials);
+    }
+    return m;
+}
+
+// ---- exchange steps of a slab-decomposed sweep (no-ops on a single GPU)
+int dist_barrier(qpic_ctx * c, cudaStream_t st) {
+    if (!c->dist.on) return QPIC_OK;
+    QPIC_LAUNCH(k_xchg_barrier, 1, 32, 0, st, c->dist.v);
+    return check_launch(c, "k_xchg_barrier");
+}
+
+HaloJob halo_job(std::initializer_list<double *> arrays, std::initializer_list<int> slots, std::initializer_list<int> slice3d = {}) {
+    HaloJob j = {};
+    for (double * a : arrays) j.a[j.n++] = a;
+    int i = 0;
+    for (int sl : slots) j.slot[i++] = sl;
+    i = 0;
+    for (int s3 : slice3d) j.slice3d[i++] = s3;
+    return j;
+}
+
+int halo_blocks(const qpic_ctx * c, const HaloJob & j) {
+    int b = blocks_for((size_t)j.n * 2 * DIST_HALO * c->g.nz, 256);
+    return b > 592 ? 592 : b;
+}
+
+// partial sums that the local particles left in the halo rows -> neighbours; theirs -> added to my edge rows
+int dist_reduce(qpic_ctx * c, cudaStream_t st, const HaloJob & j) {
+    if (!c->dist.on) return QPIC_OK;
+    QPIC_LAUNCH(k_halo_reduce_send, halo_blocks(c, j), 256, 0, st, c->ctl, c->g, c->dist.v, j);
+    QPIC_TRY(check_launch(c, "k_halo_reduce_send"));
+    QPIC_TRY(dist_barrier(c, st));
+    QPIC_LAUNCH(k_halo_reduce_add, halo_blocks(c, j), 256, 0, st, c->ctl, c->g, c->dist.v, j);
+    return check_launch(c, "k_halo_reduce_add");
+}
+
+// my edge rows of region fields -> the neighbours' halo rows
+int dist_fill(qpic_ctx * c, cudaStream_t st, std::initializer_list<int> fields) {
+    if (!c->dist.on) return QPIC_OK;
+    HaloJob j = {};
+    for (int f : fields) {
+        j.field_off[j.n] = c->dist.v.lay.field[f];
+        j.slot[j.n++] = f;
+    }
+    QPIC_LAUNCH(k_halo_fill, halo_blocks(c, j), 256, 0, st, c->g, c->dist.v, j);
+    QPIC_TRY(check_launch(c, "k_halo_fill"));
+    return dist_barrier(c, st);
+}
+
 // ---------------------------------------------------------------------------------------------- kernel sequences
 //
 // Two variants of the slice body exist:
@@ -318,12 +404,14 @@ int stream_depend(qpic_ctx * c, cudaStream_t from, cudaStream_t to) {
 
 // count[] (already accumulated by a particle kernel) -> start[], perm[] in canonical order
 int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cell, int * start, int * perm) {
-    const int n2 = c->g.n2, np = c->P.np;
+    // distributed: bucket n2 collects the entries of emigrated particles; the live count is the start of that bucket
+    const int n2 = c->g.n2 + (c->dist.on ? 1 : 0), np = c->P.np;
+    int * live_out = (c->dist.on && ctl == c->ctl) ? &c->ctl->np1 : nullptr;
     QPIC_LAUNCH(k_scan_chunk_sums, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums);
     QPIC_TRY(check_launch(c, "k_scan_chunk_sums"));
     QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, st, ctl, c->sums, c->nchunks);
     QPIC_TRY(check_launch(c, "k_scan_sums"));
-    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums, start, c->cursor);
+    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums, start, c->cursor, live_out);
     QPIC_TRY(check_launch(c, "k_scan_apply"));
     if (np > 0) {
         QPIC_LAUNCH_FLAT(k_sort_fill, blocks_for(np, 256), 256, 0, st, ctl, np, cell, c->cursor, c->tmp);
@@ -342,9 +430,14 @@ int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bo
     if (c->pow2_y) {
         const double * inv = nullptr;
         QPIC_TRY(get_inv_symbol(c, D, full, &inv));
-        QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, c->spec, ncols, ncols, inv,
+        // distributed: this rank's block of columns, [ny][cpr] in its exchange region, filled by the peers' row kernels
+        const SpecMap m = spec_map(c, full);
+        const int col0 = c->dist.on ? (full ? c->dist.col0_full : c->dist.col0_half) : 0;
+        const int mine = c->dist.on ? (full ? c->dist.ncols_full : c->dist.ncols_half) : ncols;
+        double2 * cols = c->dist.on ? m.base[c->dist.v.rank] : c->spec;
+        QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, cols, m.cpr, mine, inv + (size_t)col0 * c->g.ny,
                     want_border_sums ? c->spec_row0 : (double2 *)nullptr, want_border_sums ? c->spec_colsum : (double2 *)nullptr, c->cols_ticket,
-                    c->border_mean, nz);
+                    partials_map(c), c->dist.on ? c->dist.v.rank : 0, col0, nz);
     } else {
         QPIC_LAUNCH(k_fft_cols_solve<false>, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, ncols, ncols, L.spb, c->sy, c->sz, nz, D);
     }
@@ -359,16 +452,20 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     const qpic_ctx::FftLaunch & R = c->rows_real;
     const bool fuse = fixed_dst != nullptr && c->pow2_y && c->pow2_z;
     if (fused) *fused = fuse;
+    if (c->dist.on && !fuse) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the fused power-of-two solve");
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_r2c, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->spec, ny);
+        QPIC_LAUNCH(k_p2_rows_r2c, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_r2c<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz, R.spb);
     }
     QPIC_TRY(check_launch(c, "k_fft_rows_r2c"));
+    QPIC_TRY(dist_barrier(c, st));  // the peers' rows of my columns have arrived
     QPIC_TRY(enqueue_columns(c, st, ctl, D, false, fuse));
+    QPIC_TRY(dist_barrier(c, st));  // every rank's columns (and border-sum partials) are done
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_c2r, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->spec, fuse ? fixed_dst : c->raw, ny, c->inv_scale,
-                    fuse ? 1 : 0, c->border_mean, c->prm.psi_threshold - 1);
+        QPIC_LAUNCH(k_p2_rows_c2r, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
+                    row_first(c), ny, c->inv_scale, fuse ? 1 : 0, c->dist.on ? reinterpret_cast<const double *>(c->dist.region + c->dist.v.lay.partials) : c->partials,
+                    c->prm.psi_threshold - 1);
     } else {
         QPIC_LAUNCH(k_fft_rows_c2r<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz, R.spb, c->inv_scale);
     }
@@ -383,8 +480,8 @@ int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, doub
 int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, double * bz, double threshold, int iteration) {
     const qpic_ctx::FftLaunch & R = c->rows_cplx;
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_b_backward, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
-                    c->inv_scale);
+        QPIC_LAUNCH(k_p2_rows_b_backward, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
+                    c->inv_scale, row_first(c), row_count(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_b_backward<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
                     R.spb, c->inv_scale);
@@ -394,7 +491,8 @@ int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, do
 
 // ---- tile deposit jobs (FAST path)
 
-dim3 tile_grid(qpic_ctx * c) { return dim3((c->g.nz + TILE - 1) / TILE, (c->g.ny + TILE - 1) / TILE); }
+// distributed: the tile rows the rank's particles can reach = own rows + one tile row on either side
+dim3 tile_grid(qpic_ctx * c) { return dim3((c->g.nz + TILE - 1) / TILE, c->dist.on ? c->dist.v.ny_loc / TILE + 2 : (c->g.ny + TILE - 1) / TILE); }
 
 TileOutput tile_output(const double * val, double sign, int bg_mode, const double * bg3, double * out, int out_3d) {
     TileOutput o;
@@ -413,6 +511,10 @@ TileJob tile_job(qpic_ctx * c) {
     j.jxb3 = c->f3[QPIC_F3_JX_BUNCH];
     j.rhob3 = c->f3[QPIC_F3_RHO_BUNCH];
     j.rho_ion = c->f2[QPIC_F2_RHO_ION];
+    j.tile_rows = (c->g.ny + TILE - 1) / TILE;
+    j.tile_row0 = c->dist.on ? (c->dist.v.row0 / TILE - 1 + j.tile_rows) % j.tile_rows : 0;
+    j.own_row0 = row_first(c);
+    j.own_rows = row_count(c);
     return j;
 }
 
@@ -489,9 +591,14 @@ int enqueue_potential(qpic_ctx * c, cudaStream_t st, bool fast, int at_mid, doub
                          c->f3[QPIC_F3_RHO_BUNCH], 1, c->fft_in);
         QPIC_TRY(check_launch(c, "k_deposit_charge"));
     }
+    // distributed: at_mid sources are reduced by the caller together with jx (one exchange)
+    if (!at_mid) QPIC_TRY(dist_reduce(c, st, halo_job({c->fft_in}, {RB_CHARGE})));
     bool fused = false;
     QPIC_TRY(enqueue_real_solve(c, st, c->ctl, 0.0, dst, &fused));
-    if (fused) return QPIC_OK;
+    if (fused) {
+        if (!at_mid) QPIC_TRY(dist_fill(c, st, {DF_PSI}));
+        return QPIC_OK;
+    }
     return enqueue_fixup(c, st, dst);
 }
 
@@ -516,7 +623,10 @@ int enqueue_slice_head(qpic_ctx * c, bool fast, bool want_invariants, bool with_
                          want_invariants ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_gamma"));
     }
-    if (with_deposit) QPIC_TRY(enqueue_base_currents(c, st, fast, true, true, false));
+    if (with_deposit) {
+        QPIC_TRY(enqueue_base_currents(c, st, fast, true, true, false));
+        QPIC_TRY(dist_reduce(c, st, halo_job({c->f2[QPIC_F2_JX], c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]}, {RB_JX, RB_RHO, RB_CHI}, {0, 0, 1})));
+    }
     return QPIC_OK;
 }
 
@@ -536,10 +646,26 @@ SliceOut slice_out(qpic_ctx * c) {
 }
 
 int enqueue_end_of_slice(qpic_ctx * c, int b_is_zero, int roll, int ignore_stop) {
-    QPIC_LAUNCH_FLAT(k_end_of_slice, blocks_for(c->g.n2, 256), 256, 0, c->stream, c->ctl, c->g, slice_out(c), c->f2[QPIC_F2_PSI], c->f2[QPIC_F2_PSI_PREV],
-                     c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ],
-                     c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT], b_is_zero, roll, ignore_stop);
+    QPIC_LAUNCH_FLAT(k_end_of_slice, blocks_for((size_t)row_count(c) * c->g.nz, 256), 256, 0, c->stream, c->ctl, c->g, slice_out(c), c->f2[QPIC_F2_PSI],
+                     c->f2[QPIC_F2_PSI_PREV], c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY],
+                     c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT], b_is_zero, roll, ignore_stop, row_first(c), row_count(c));
     return check_launch(c, "k_end_of_slice");
+}
+
+MigrateView migrate_view(qpic_ctx * c) {
+    MigrateView m = {};
+    if (!c->dist.on) return m;
+    const DistView & v = c->dist.v;
+    m.enabled = 1;
+    m.row0 = v.row0;
+    m.ny_loc = v.ny_loc;
+    m.cap = v.mig_cap;
+    // box 0 of a rank collects what its upper neighbour sends down, box 1 what its lower neighbour sends up
+    m.out[0] = reinterpret_cast<double *>(v.base[v.below] + v.lay.inbox);
+    m.out[1] = reinterpret_cast<double *>(v.base[v.above] + v.lay.inbox) + (size_t)5 * v.mig_cap;
+    m.out_count = c->dist.out_count;
+    m.error = &c->ctl->dist_error;
+    return m;
 }
 
 // one full xi-loop iteration for a slice i >= 1 (src/System_3d.cpp:328-619)
@@ -547,7 +673,10 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     const int np = c->P.np, n2 = c->g.n2;
     const int M = c->prm.magnetic_field_iterations;
     cudaStream_t sa = c->stream;
-    cudaStream_t sb = c->profiling ? c->stream : c->stream2;  // per-kernel timing wants one serial stream
+    // per-kernel timing wants one serial stream; so do distributed sweeps (all ranks must issue their exchange barriers in
+    // the same order)
+    cudaStream_t sb = (c->profiling || c->dist.on) ? c->stream : c->stream2;
+    if (c->dist.on && !fast) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps run on the sort-free deposit path only");
     QPIC_TRY(enqueue_slice_head(c, fast, M > 0, M == 0));
     for (int it = 0; it < M; it++) {
         if (np > 0) {
@@ -560,9 +689,19 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
         // branch A: psi_middle, then jy_next / jz_next
         if (!fast) QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
-        QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
+        if (c->dist.on) {
+            // source deposit, then ONE exchange for the psi_middle source and jx, then the solve
+            QPIC_TRY(enqueue_tile_charge(c, sa, 1));
+            QPIC_TRY(dist_reduce(c, sa, halo_job({c->fft_in, c->f2[QPIC_F2_JX]}, {RB_CHARGE, RB_JX})));
+            bool fused = false;
+            QPIC_TRY(enqueue_real_solve(c, sa, c->ctl, 0.0, c->f2[QPIC_F2_PSI_MIDDLE], &fused));
+            QPIC_TRY(dist_fill(c, sa, {DF_PSI_MIDDLE, DF_JX}));
+        } else {
+            QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
+        }
         if (fast) {
             QPIC_TRY(enqueue_tile_jy_jz(c, sa));
+            QPIC_TRY(dist_reduce(c, sa, halo_job({c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT]}, {RB_JY, RB_JZ})));
         } else {
             if (np > 0) {
                 QPIC_LAUNCH_FLAT(k_particles_currents_yz, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
@@ -579,20 +718,26 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             if (c->pow2_z) {
                 QPIC_LAUNCH(k_p2_rows_b_forward, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D,
                             c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
-                            c->f2[QPIC_F2_JZ_NEXT], c->spec);
+                            c->f2[QPIC_F2_JZ_NEXT], spec_map(c, true), row_first(c), row_count(c));
             } else {
                 QPIC_LAUNCH(k_fft_rows_b_forward<false>, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
                             c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
                             c->f2[QPIC_F2_JZ_NEXT], c->spec, R.spb);
             }
             QPIC_TRY(check_launch(c, "k_fft_rows_b_forward"));
+            QPIC_TRY(dist_barrier(c, sa));
             QPIC_TRY(enqueue_complex_columns(c, sa, c->ctl, c->prm.magnetic_field_D));
+            QPIC_TRY(dist_barrier(c, sa));
             QPIC_TRY(enqueue_b_backward(c, sa, c->ctl, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->prm.threshold_B, it));
+            QPIC_TRY(dist_fill(c, sa, {DF_BY, DF_BZ}));
         }
     }
     // rho and susceptibility(i) from the last executed iteration (see k_deposit_jx_rho_chi); reads the cell lists and
     // fractions of (y,z), so it must finish before the push below rewrites them
-    if (M > 0) QPIC_TRY(enqueue_base_currents(c, sa, fast, false, true, true));
+    if (M > 0) {
+        QPIC_TRY(enqueue_base_currents(c, sa, fast, false, true, true));
+        QPIC_TRY(dist_reduce(c, sa, halo_job({c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]}, {RB_RHO, RB_CHI}, {0, 1})));
+    }
     // branch B: fields of this slice + the psi_prev / jy / jz roll;  branch A: push + cell lists of the new positions
     QPIC_TRY(stream_depend(c, sa, sb));
     {
@@ -603,8 +748,17 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(rc);
     }
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->perm_b, c->f2[QPIC_F2_PSI_MIDDLE], c->count);
+        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->dist.on ? (const int *)nullptr : c->perm_b,
+                         c->f2[QPIC_F2_PSI_MIDDLE], c->count, migrate_view(c));
         QPIC_TRY(check_launch(c, "k_particles_advance"));
+    }
+    if (c->dist.on) {
+        // emigrants are in the neighbours' inboxes: publish the counts, meet, append the arrivals to the id arrays
+        QPIC_LAUNCH(k_migrate_publish, 1, 32, 0, sa, c->dist.v, c->dist.out_count);
+        QPIC_TRY(check_launch(c, "k_migrate_publish"));
+        QPIC_TRY(dist_barrier(c, sa));
+        QPIC_LAUNCH(k_migrate_unpack, 148, 256, 0, sa, c->ctl, c->g, c->dist.v, c->P, c->P.np, c->count);
+        QPIC_TRY(check_launch(c, "k_migrate_unpack"));
     }
     QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
@@ -619,15 +773,17 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
 
 // (re)build the cell lists of (y, z) from scratch
 int enqueue_rebuild_base_lists(qpic_ctx * c) {
-    const int np = c->P.np;
-    QPIC_CUDA(c, cudaMemsetAsync(c->count, 0, sizeof(int) * c->g.n2, c->stream));
-    if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(np, 256), 256, 0, c->stream, np, c->g, c->P.y, c->P.z, c->P.cell_p, c->P.fy_p, c->P.fz_p, c->count);
+    // distributed: P.np is the capacity of the arrays, the live entries are counted on the device (Ctl::np1)
+    const int np = c->P.np, live = c->dist.on ? c->dist.live0 : np;
+    Ctl * ctl = c->dist.on ? c->ctl : c->ctl_scratch;
+    QPIC_CUDA(c, cudaMemsetAsync(c->count, 0, sizeof(int) * (c->g.n2 + 1), c->stream));
+    if (live > 0) {
+        QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(live, 256), 256, 0, c->stream, live, c->g, c->P.y, c->P.z, c->P.cell_p, c->P.fy_p, c->P.fz_p, c->count);
         QPIC_TRY(check_launch(c, "k_locate_count"));
     }
-    QPIC_TRY(enqueue_sort(c, c->stream, c->ctl_scratch, c->P.cell_p, c->start_b, c->perm_b));
+    QPIC_TRY(enqueue_sort(c, c->stream, ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, c->stream, c->ctl_scratch, c->P, c->perm_b);
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, c->stream, ctl, c->P, c->perm_b);
         QPIC_TRY(check_launch(c, "k_particles_to_slots"));
     }
     c->lists_dirty = false;
@@ -659,6 +815,16 @@ int poll_ctl(qpic_ctx * c) {
     QPIC_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->since_poll = 0;
+    if (c->dist.on) {
+        static const char * why[] = {"", "an exchange barrier timed out (a peer stopped or the ranks diverged)", "more emigrants in one slice than the inbox holds",
+                                     "particle_capacity exceeded after migration", "a particle moved further than the neighbouring slab"};
+        const int e = c->ctl_host->dist_error;
+        if (e != 0) return fail(c, QPIC_ERR_STATE, "distributed sweep failed on rank %d: %s", c->dist.v.rank, why[e > 0 && e < 5 ? e : 0]);
+        if (c->ctl_host->fast_fail != 0) {
+            return fail(c, QPIC_ERR_UNSUPPORTED, "rank %d: a half step moved a particle by more than one cell; the sorted-deposit fallback is not available in distributed sweeps",
+                        c->dist.v.rank);
+        }
+    }
     if (c->ctl_host->stop_tag != 0) {
         c->stopped_at = (c->ctl_host->stop_tag - 1) / STOP_TAG_STRIDE;
         c->cur = c->stopped_at;
@@ -777,6 +943,9 @@ void qpic_default_params(qpic_params * p) {
     p->keep_slices_3d = 0;
     p->use_graph = 1;
     p->stop_check_interval = 64;
+    p->dist_rank = 0;
+    p->dist_world = 1;
+    p->particle_capacity = 0;
 }
 
 const char * qpic_last_error(const qpic_ctx * ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -792,6 +961,9 @@ void qpic_destroy(qpic_ctx * c) {
     if (c->graph_fast) cudaGraphDestroy(c->graph_fast);
 #endif
     for (void * p : c->allocations) cudaFree(p);
+#ifndef QPIC_EMU
+    for (void * m : c->dist.opened) cudaIpcCloseMemHandle(m);
+#endif
     if (c->ctl_host) cudaFreeHost(c->ctl_host);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -841,6 +1013,32 @@ static int create_impl(qpic_ctx * c) {
     g.inv_dz = 1.0 / g.dz;
 
     const size_t n2 = (size_t)g.n2, n3 = n2 * g.nx;
+    qpic_ctx::Dist & D = c->dist;
+    D.on = p.dist_world > 1;
+    if (D.on) {
+        const int G = p.dist_world;
+        const bool pow2 = (g.ny & (g.ny - 1)) == 0 && (g.nz & (g.nz - 1)) == 0 && g.ny >= 64 && g.nz >= 64;
+        if (G > DIST_MAX || p.dist_rank < 0 || p.dist_rank >= G) return fail(c, QPIC_ERR_INVALID, "dist_rank / dist_world out of range (at most %d ranks)", DIST_MAX);
+        if (!pow2 || g.ny % G != 0 || (g.ny / G) % TILE != 0 || g.ny / G < 2 * TILE || g.nz % G != 0 || p.force_general_deposit || p.keep_slices_3d) {
+            return fail(c, QPIC_ERR_UNSUPPORTED,
+                        "distributed sweeps need power-of-two ny, nz >= 64, ny / world a multiple of %d and >= %d, the sort-free deposit and no per-slice 3-D copies",
+                        TILE, 2 * TILE);
+        }
+        DistView & v = D.v;
+        v.rank = p.dist_rank;
+        v.world = G;
+        v.below = (p.dist_rank + G - 1) % G;
+        v.above = (p.dist_rank + 1) % G;
+        v.ny_loc = g.ny / G;
+        v.row0 = p.dist_rank * v.ny_loc;
+        const int nzh = g.nz / 2 + 1;
+        D.cpr_half = (nzh + G - 1) / G;
+        D.cpr_full = g.nz / G;
+        D.col0_half = p.dist_rank * D.cpr_half;
+        D.ncols_half = nzh - D.col0_half < 0 ? 0 : (nzh - D.col0_half < D.cpr_half ? nzh - D.col0_half : D.cpr_half);
+        D.col0_full = p.dist_rank * D.cpr_full;
+        D.ncols_full = D.cpr_full;
+    }
     QPIC_TRY(make_fft(c, g.ny, &c->fy));
     QPIC_TRY(make_fft(c, g.nz, &c->fz));
     QPIC_TRY(make_symbol_tables(c));
@@ -852,10 +1050,10 @@ static int create_impl(qpic_ctx * c) {
     }
     c->pow2_y = c->fy.plan.log2n > 0;
     c->pow2_z = c->fz.plan.log2n > 0;
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, (g.ny + 1) / 2, &c->rows_real, "row transform"));
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, g.ny, &c->rows_cplx, "row transform"));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, g.nz / 2 + 1, &c->cols_half, "column transform"));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, g.nz, &c->cols_full, "column transform"));
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform"));
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform"));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform"));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform"));
     if (!c->pow2_y) {
         // generic engine: two adjacent columns per block when they fit, so that global accesses are 32-byte sectors
         const int cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;
@@ -901,7 +1099,39 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(dev_alloc(c, &c->ctl, 1));
     QPIC_TRY(dev_alloc(c, &c->ctl_scratch, 1));
     QPIC_CUDA(c, cudaMallocHost(&c->ctl_host, sizeof(Ctl)));
-    for (int f = 0; f < QPIC_F2_COUNT; f++) QPIC_TRY(dev_alloc(c, &c->f2[f], n2));
+    if (D.on) {
+        // the exchange region: same layout on every rank
+        DistView & v = D.v;
+        DistLayout & L = v.lay;
+        v.mig_cap = 64 * g.nz;  // particles that may cross one slab edge in one slice
+        size_t off = 0;
+        auto take = [&off](size_t bytes) {
+            const size_t at = off;
+            off += (bytes + 255) / 256 * 256;
+            return at;
+        };
+        L.flags = take(sizeof(long long) * DIST_MAX);
+        L.partials = take(sizeof(double) * 4 * DIST_MAX);
+        L.inbox_count = take(sizeof(int) * 2);
+        const int cpr_max = D.cpr_half > D.cpr_full ? D.cpr_half : D.cpr_full;
+        L.cols = take(sizeof(double2) * (size_t)g.ny * cpr_max);
+        L.rbuf = take(sizeof(double) * RB_COUNT * 2 * DIST_HALO * g.nz);
+        L.inbox = take(sizeof(double) * 2 * 5 * (size_t)v.mig_cap);
+        for (int f = 0; f < DF_COUNT; f++) L.field[f] = take(sizeof(double) * n2);
+        L.total = off;
+        QPIC_TRY(dev_alloc(c, &D.region, L.total));
+        for (int q = 0; q < DIST_MAX; q++) v.base[q] = nullptr;
+        v.base[v.rank] = D.region;
+        QPIC_TRY(dev_alloc(c, &D.out_count, 2));
+        QPIC_TRY(dev_alloc(c, &D.epoch, 1));
+        v.epoch = D.epoch;
+        v.error = &c->ctl->dist_error;
+        const int in_region[DF_COUNT] = {QPIC_F2_PSI, QPIC_F2_PSI_MIDDLE, QPIC_F2_BY_CUR, QPIC_F2_BZ_CUR, QPIC_F2_JX};
+        for (int f = 0; f < DF_COUNT; f++) c->f2[in_region[f]] = reinterpret_cast<double *>(D.region + L.field[f]);
+    }
+    for (int f = 0; f < QPIC_F2_COUNT; f++) {
+        if (!c->f2[f]) QPIC_TRY(dev_alloc(c, &c->f2[f], n2));
+    }
     for (int f = 0; f < QPIC_F3_COUNT; f++) {
         const bool bunch = (f == QPIC_F3_RHO_BUNCH || f == QPIC_F3_JX_BUNCH);  // allocated on upload
         const bool slices = (f >= QPIC_F3_PSI);
@@ -915,19 +1145,59 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(dev_alloc(c, &c->spec_row0, (size_t)g.nz / 2 + 1));
     QPIC_TRY(dev_alloc(c, &c->spec_colsum, (size_t)g.nz / 2 + 1));
     QPIC_TRY(dev_alloc(c, &c->cols_ticket, 1));
-    QPIC_TRY(dev_alloc(c, &c->border_mean, 1));
-    c->nchunks = blocks_for(n2, SCAN_CHUNK);
-    QPIC_TRY(dev_alloc(c, &c->count, n2));
-    QPIC_TRY(dev_alloc(c, &c->cursor, n2));
+    QPIC_TRY(dev_alloc(c, &c->partials, 4 * DIST_MAX));
+    c->nchunks = blocks_for(n2 + 1, SCAN_CHUNK);  // + the "emigrated" bucket of distributed sweeps
+    QPIC_TRY(dev_alloc(c, &c->count, n2 + 1));
+    QPIC_TRY(dev_alloc(c, &c->cursor, n2 + 1));
     QPIC_TRY(dev_alloc(c, &c->sums, (size_t)c->nchunks));
-    QPIC_TRY(dev_alloc(c, &c->start_b, n2 + 1));
-    QPIC_TRY(dev_alloc(c, &c->start_m, n2 + 1));
+    QPIC_TRY(dev_alloc(c, &c->start_b, n2 + 2));
+    QPIC_TRY(dev_alloc(c, &c->start_m, n2 + 2));
     QPIC_TRY(alloc_particles(c, 0));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cur = g.nx - 1;
     c->target = g.nx - 1;
     // the tile deposit needs unambiguous minimal-image cell offsets
     c->fast_capable = !p.force_general_deposit && g.ny >= 8 && g.nz >= 8;
+    if (D.on && !(c->pow2_y && c->pow2_z)) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the power-of-two transform engine");
+#ifndef QPIC_EMU
+    if (D.on) {
+        // CUDA loads kernels lazily, and loading one synchronises the context: with several ranks in ONE process (shared
+        // context) that would wait for ever on a peer's spinning barrier kernel.  Load everything the sweep launches now.
+        cudaFuncAttributes fa;
+#define QPIC_PRELOAD(k) QPIC_CUDA(c, cudaFuncGetAttributes(&fa, k))
+        QPIC_PRELOAD(k_xchg_barrier);
+        QPIC_PRELOAD(k_halo_reduce_send);
+        QPIC_PRELOAD(k_halo_reduce_add);
+        QPIC_PRELOAD(k_halo_fill);
+        QPIC_PRELOAD(k_migrate_publish);
+        QPIC_PRELOAD(k_migrate_unpack);
+        QPIC_PRELOAD((k_tile_deposit<1, false>));
+        QPIC_PRELOAD((k_tile_deposit<2, false>));
+        QPIC_PRELOAD((k_tile_deposit<3, false>));
+        QPIC_PRELOAD((k_tile_deposit<2, true>));
+        QPIC_PRELOAD(k_tile_bin_deposit<0>);
+        QPIC_PRELOAD(k_tile_bin_deposit<1>);
+        QPIC_PRELOAD(k_particles_predict<true>);
+        QPIC_PRELOAD(k_particles_gamma);
+        QPIC_PRELOAD(k_particles_advance);
+        QPIC_PRELOAD(k_particles_to_slots);
+        QPIC_PRELOAD(k_locate_count);
+        QPIC_PRELOAD(k_scan_chunk_sums);
+        QPIC_PRELOAD(k_scan_sums);
+        QPIC_PRELOAD(k_scan_apply);
+        QPIC_PRELOAD(k_sort_fill);
+        QPIC_PRELOAD(k_sort_rank);
+        QPIC_PRELOAD(k_end_of_slice);
+        QPIC_PRELOAD(k_next_slice);
+        QPIC_PRELOAD(k_init_a_sqr);
+        QPIC_PRELOAD(k_p2_rows_r2c);
+        QPIC_PRELOAD(k_p2_rows_c2r);
+        QPIC_PRELOAD(k_p2_cols_solve);
+        QPIC_PRELOAD(k_p2_rows_b_forward);
+        QPIC_PRELOAD(k_p2_rows_b_backward);
+#undef QPIC_PRELOAD
+    }
+#endif
     return QPIC_OK;
 }
 
@@ -1007,15 +1277,23 @@ int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, c
     if (count > 0 && (!y || !z || !n)) return fail(c, QPIC_ERR_INVALID, "particle arrays are NULL");
     if (count > (size_t)std::numeric_limits<int>::max() - 1024) return fail(c, QPIC_ERR_INVALID, "too many particles for 32-bit particle indices");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
-    if ((c->graph_exec || c->graph_exec_fast) && (int)count != c->P.np) {
+    // distributed: the arrays hold `capacity` entries, the live count is kept on the device and changes with migration
+    size_t capacity = count;
+    if (c->dist.on) {
+        capacity = c->prm.particle_capacity ? c->prm.particle_capacity : count + count / 4 + 65536;
+        if (capacity < count) return fail(c, QPIC_ERR_INVALID, "particle_capacity is smaller than the particle count");
+        if (capacity > (size_t)std::numeric_limits<int>::max() / 4 - 1024) return fail(c, QPIC_ERR_INVALID, "too many particles per rank");
+        c->dist.live0 = (int)count;
+    }
+    if ((c->graph_exec || c->graph_exec_fast) && (int)capacity != c->P.np) {
         return fail(c, QPIC_ERR_STATE, "the particle count cannot change after the first qpic_step of a context");
     }
-    if ((int)count != c->P.np || !c->P.y) {
+    if ((int)capacity != c->P.np || !c->P.y) {
         // (re)allocation: the previous arrays stay owned by the context until qpic_destroy
-        QPIC_TRY(alloc_particles(c, count));
+        QPIC_TRY(alloc_particles(c, capacity));
     } else {
         double * zero[] = {c->P.py, c->P.pz, c->P.pyn, c->P.pzn, c->P.gamma, c->P.px, c->P.gam, c->P.pxs};
-        for (double * p : zero) QPIC_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * count, c->stream));
+        for (double * p : zero) QPIC_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * capacity, c->stream));
     }
     if (count > 0) {
         QPIC_CUDA(c, cudaMemcpyAsync(c->P.y, y, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
@@ -1044,15 +1322,27 @@ int qpic_begin(qpic_ctx * c) {
     init.slice = g.nx - 1;
     init.stop_tag = 0;
     init.fast_fail = 0;
-    init.pad1 = 0;
+    init.dist_error = 0;
+    init.np1 = c->dist.on ? c->dist.live0 + 1 : 0;
+    init.np_p1 = init.np1;
+    init.pad[0] = init.pad[1] = 0;
+    if (c->dist.on && !c->dist.attached) return fail(c, QPIC_ERR_STATE, "distributed context: attach the peers' exchange regions first (qpic_dist_attach_*)");
     *c->ctl_host = init;
     QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     QPIC_TRY(enqueue_rebuild_base_lists(c));
     // rho_ion (src/System_3d.cpp:319-323)
-    QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(g.n2, 128), 128, 0, c->stream, c->ctl_scratch, c->g, lists_base(c), c->P.nw_s, (const double *)nullptr,
-                     (const double *)nullptr, (const double *)nullptr, 0, c->f2[QPIC_F2_RHO_ION]);
-    QPIC_TRY(check_launch(c, "k_deposit_charge"));
+    if (c->dist.on) {
+        TileJob j = tile_job(c);
+        j.nout = 1;
+        j.o[0] = tile_output(c->P.nw_s, -1.0, 0, nullptr, c->f2[QPIC_F2_RHO_ION], 0);
+        QPIC_TRY(launch_tile(c, c->stream, j, false, "k_tile_deposit_rho_ion"));
+        QPIC_TRY(dist_reduce(c, c->stream, halo_job({c->f2[QPIC_F2_RHO_ION]}, {RB_RHO})));
+    } else {
+        QPIC_LAUNCH_FLAT(k_deposit_charge, blocks_for(g.n2, 128), 128, 0, c->stream, c->ctl_scratch, c->g, lists_base(c), c->P.nw_s, (const double *)nullptr,
+                         (const double *)nullptr, (const double *)nullptr, 0, c->f2[QPIC_F2_RHO_ION]);
+        QPIC_TRY(check_launch(c, "k_deposit_charge"));
+    }
     c->cur = g.nx - 1;
     c->target = g.nx - 1;
     c->stopped_at = -1;
@@ -1192,7 +1482,18 @@ int qpic_upload_field2d(qpic_ctx * c, qpic_field2d f, const double * src) {
     return QPIC_OK;
 }
 
-size_t qpic_particle_count(const qpic_ctx * c) { return c ? (size_t)c->P.np : 0; }
+size_t qpic_particle_count(const qpic_ctx * c) {
+    if (!c) return 0;
+    if (c->dist.on) {
+        // live particles of this rank right now (changes with migration); synchronises
+        int np1 = 0;
+        cudaSetDevice(c->prm.device);
+        cudaStreamSynchronize(c->stream);
+        if (cudaMemcpy(&np1, &c->ctl->np1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+        return np1 > 0 ? (size_t)(np1 - 1) : (size_t)c->dist.live0;
+    }
+    return (size_t)c->P.np;
+}
 
 static double * particle_array(qpic_ctx * c, qpic_particle_field f) {
     switch (f) {
@@ -1209,6 +1510,7 @@ static double * particle_array(qpic_ctx * c, qpic_particle_field f) {
 
 int qpic_download_particles(qpic_ctx * c, qpic_particle_field f, double * dst) {
     if (!c) return QPIC_ERR_INVALID;
+    if (c->dist.on) return fail(c, QPIC_ERR_UNSUPPORTED, "particle arrays of a distributed sweep have no caller order");
     double * src = particle_array(c, f);
     if (!src) return fail(c, QPIC_ERR_INVALID, "bad particle field id");
     if (c->P.np == 0) return QPIC_OK;
@@ -1217,6 +1519,7 @@ int qpic_download_particles(qpic_ctx * c, qpic_particle_field f, double * dst) {
 
 int qpic_upload_particles(qpic_ctx * c, qpic_particle_field f, const double * src) {
     if (!c) return QPIC_ERR_INVALID;
+    if (c->dist.on) return fail(c, QPIC_ERR_UNSUPPORTED, "particle arrays of a distributed sweep have no caller order");
     double * dst = particle_array(c, f);
     if (!dst || f == QPIC_P_GAMMA || f == QPIC_P_PX || !src) return fail(c, QPIC_ERR_INVALID, "only y, z, py, pz, n can be uploaded");
     if (c->P.np == 0) return QPIC_OK;
@@ -1250,6 +1553,7 @@ int qpic_set_current_slice(qpic_ctx * c, int slice) {
 
 int qpic_solve_poisson_host(qpic_ctx * c, double * inout, double D) {
     if (!c || !inout) return fail(c, QPIC_ERR_INVALID, "inout is NULL");
+    if (c->dist.on) return fail(c, QPIC_ERR_UNSUPPORTED, "host building blocks are single-GPU");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
@@ -1261,6 +1565,7 @@ int qpic_solve_poisson_host(qpic_ctx * c, double * inout, double D) {
 
 int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inout_b, double D) {
     if (!c || !inout_a || !inout_b) return fail(c, QPIC_ERR_INVALID, "inout is NULL");
+    if (c->dist.on) return fail(c, QPIC_ERR_UNSUPPORTED, "host building blocks are single-GPU");
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
     const int ny = c->g.ny, nz = c->g.nz;
@@ -1384,6 +1689,86 @@ int qpic_profile_slices(qpic_ctx * c, int nslices, char * report, size_t report_
     }
     QPIC_TRY(resolve(c));
     return QPIC_OK;
+}
+
+// ---- slab-decomposed multi-GPU sweep: mapping the peers' exchange regions
+size_t qpic_dist_region_bytes(const qpic_ctx * c) { return (c && c->dist.on) ? c->dist.v.lay.total : 0; }
+
+void * qpic_dist_region(qpic_ctx * c) { return (c && c->dist.on) ? c->dist.region : nullptr; }
+
+int qpic_dist_row_range(const qpic_ctx * c, int * row0, int * nrows) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (row0) *row0 = row_first(c);
+    if (nrows) *nrows = row_count(c);
+    return QPIC_OK;
+}
+
+int qpic_dist_ipc_handle(qpic_ctx * c, void * handle64) {
+#ifdef QPIC_EMU
+    (void)handle64;
+    return fail(c, QPIC_ERR_UNSUPPORTED, "no IPC in the emulator");
+#else
+    if (!c || !handle64) return fail(c, QPIC_ERR_INVALID, "handle is NULL");
+    if (!c->dist.on) return fail(c, QPIC_ERR_STATE, "not a distributed context");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are 64 bytes");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    cudaIpcMemHandle_t h;
+    QPIC_CUDA(c, cudaIpcGetMemHandle(&h, c->dist.region));
+    std::memcpy(handle64, &h, sizeof(h));
+    return QPIC_OK;
+#endif
+}
+
+static int dist_finish_attach(qpic_ctx * c) {
+    // the view is baked into kernel arguments from here on
+    c->dist.attached = true;
+    QPIC_CUDA(c, cudaMemsetAsync(c->dist.region + c->dist.v.lay.flags, 0, sizeof(long long) * DIST_MAX, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_dist_attach_ipc(qpic_ctx * c, const void * handles) {
+#ifdef QPIC_EMU
+    (void)handles;
+    return fail(c, QPIC_ERR_UNSUPPORTED, "no IPC in the emulator");
+#else
+    if (!c || !handles) return fail(c, QPIC_ERR_INVALID, "handles is NULL");
+    if (!c->dist.on) return fail(c, QPIC_ERR_STATE, "not a distributed context");
+    if (c->dist.attached) return fail(c, QPIC_ERR_STATE, "already attached");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    for (int q = 0; q < c->dist.v.world; q++) {
+        if (q == c->dist.v.rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char *>(handles) + 64 * (size_t)q, sizeof(h));
+        void * mapped = nullptr;
+        QPIC_CUDA(c, cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+        c->dist.opened.push_back(mapped);
+        c->dist.v.base[q] = static_cast<char *>(mapped);
+    }
+    return dist_finish_attach(c);
+#endif
+}
+
+int qpic_dist_attach_pointers(qpic_ctx * c, void * const * regions) {
+    if (!c || !regions) return fail(c, QPIC_ERR_INVALID, "regions is NULL");
+    if (!c->dist.on) return fail(c, QPIC_ERR_STATE, "not a distributed context");
+    if (c->dist.attached) return fail(c, QPIC_ERR_STATE, "already attached");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    for (int q = 0; q < c->dist.v.world; q++) {
+        if (q == c->dist.v.rank) continue;
+        if (!regions[q]) return fail(c, QPIC_ERR_INVALID, "region of rank %d is NULL", q);
+#ifndef QPIC_EMU
+        // peers on other devices of this process: enable direct access once (ignored when already on)
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, regions[q]) == cudaSuccess && attr.device != c->prm.device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, QPIC_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+#endif
+        c->dist.v.base[q] = static_cast<char *>(regions[q]);
+    }
+    return dist_finish_attach(c);
 }
 
 // ---- in-graph timeline (only in the -DQPIC_TIMELINE development build, tools/timeline.py): globaltimer stamps that

@@ -67,6 +67,32 @@ __device__ __forceinline__ void fft_pow2_regs(double2 (&v)[8], double2 * xa, dou
     }
 }
 
+// Where element (global row j, column k) of a spectrum lives.  Single GPU: one buffer spec[j][k] with leading dimension
+// cpr = number of columns.  Slab-decomposed runs (qpic_dist.cuh): the columns are dealt out in blocks of cpr to the ranks;
+// base[q] is rank q's column buffer [ny][cpr] (a peer pointer over NVLink), so a forward row kernel's store IS the transpose.
+struct SpecMap {
+    double2 * base[8];
+    int cpr;
+    int world;
+};
+
+// (the peer table is only ever indexed with compile-time constants: a dynamically indexed kernel parameter would be copied
+// to local memory by every thread)
+__device__ __forceinline__ double2 * spec_base(const SpecMap & m, int q) {
+    double2 * b = m.base[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        if (q == i) b = m.base[i];
+    }
+    return b;
+}
+
+__device__ __forceinline__ double2 * spec_at(const SpecMap & m, int j, int k) {
+    if (m.world == 1) return m.base[0] + (size_t)j * m.cpr + k;
+    const int q = k / m.cpr;
+    return spec_base(m, q) + (size_t)j * m.cpr + (k - q * m.cpr);
+}
+
 // thread layout shared by all kernels below: blockDim.x = spb * n/8; sequence b = threadIdx.x / (n/8), lane t
 struct Pow2Lane {
     int b, t, e8;
@@ -87,8 +113,9 @@ __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
 // ------------------------------------------------------------------------------------------------ real field (psi)
 
 // forward rows, two real rows per sequence -> half spectra spec[ny][nzh]
-__global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, double2 * __restrict__ spec,
-                              int ny) {
+// rows [row0, row0 + ny) of src (a full-size array)
+__global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, SpecMap spec, int ny,
+                              int row0) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_r2c);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
@@ -99,7 +126,7 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int k = L.t + e * L.e8;
-        v[e] = make_double2(j0 < ny ? src[(size_t)j0 * nz + k] : 0.0, j1 < ny ? src[(size_t)j1 * nz + k] : 0.0);
+        v[e] = make_double2(j0 < ny ? src[(size_t)(row0 + j0) * nz + k] : 0.0, j1 < ny ? src[(size_t)(row0 + j1) * nz + k] : 0.0);
     }
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
     // the split needs Z_k and Z_{n-k}: one more exchange.  The last exchange of the transform used the other buffer
@@ -114,8 +141,8 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
         const double2 zk = z[k];
         const double2 zm = z[k == 0 ? 0 : nz - k];
         // U0 = (Z_k + conj(Z_{n-k})) / 2,  U1 = (Z_k - conj(Z_{n-k})) / (2i)
-        spec[(size_t)j0 * nzh + k] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-        if (j1 < ny) spec[(size_t)j1 * nzh + k] = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+        *spec_at(spec, row0 + j0, k) = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        if (j1 < ny) *spec_at(spec, row0 + j1, k) = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
     }
 }
 
@@ -127,23 +154,36 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
 //     sum_k u(0,k)  = (1/ny) sum_ky U(ky,0)            (colsum[0])
 //     u(0,0)        = (1/(ny nz)) sum_ky sum_kz U      (colsum[], Hermitian in kz)
 // The column kernel's last block reduces these sums with a fixed-order tree and leaves the mean in *border_mean.
-__global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double2 * __restrict__ spec, double * __restrict__ dst,
-                              int ny, double inv_scale, int fix, const double * __restrict__ border_mean, double floor_value) {
+// `ny` rows starting at global row `row0` of a field with ny_total rows.  The border mean is assembled from the per-rank
+// partial sums the column kernels left in partials[rank][0..2] (one rank on a single GPU), in rank order.
+__global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, SpecMap spec, double * __restrict__ dst, int ny, int row0,
+                              int ny_total, double inv_scale, int fix, const double * __restrict__ partials, double floor_value) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2r);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
-    const int nz = 1 << log2n, nzh = nz / 2 + 1;
+    const int nz = 1 << log2n;
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
-    const double mean = fix ? *border_mean : 0.0;
+    // loads now, arithmetic after the transform (the divisions then hide behind the spectrum loads)
+    double pa = 0.0, pb = 0.0, pc = 0.0;
+    if (fix) {
+        pc = partials[2];  // column 0 belongs to rank 0
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (r < spec.world) {
+                pa += partials[4 * r + 0];
+                pb += partials[4 * r + 1];
+            }
+        }
+    }
     double2 v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int i = L.t + e * L.e8;
         const bool mirror = i > nz / 2;
         const int k = mirror ? nz - i : i;
-        double2 v0 = (j0 < ny) ? spec[(size_t)j0 * nzh + k] : make_double2(0.0, 0.0);
-        double2 v1 = (j1 < ny) ? spec[(size_t)j1 * nzh + k] : make_double2(0.0, 0.0);
+        double2 v0 = (j0 < ny) ? *spec_at(spec, row0 + j0, k) : make_double2(0.0, 0.0);
+        double2 v1 = (j1 < ny) ? *spec_at(spec, row0 + j1, k) : make_double2(0.0, 0.0);
         if (k == 0 || 2 * k == nz) {
             // c2r ignores the imaginary part of the DC / Nyquist bins (they are rounding noise for a real field)
             v0.y = 0.0;
@@ -153,18 +193,25 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
         v[e] = mirror ? make_double2(v0.x + v1.y, v1.x - v0.y) : make_double2(v0.x - v1.y, v0.y + v1.x);
     }
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+    double mean = 0.0;
+    if (fix) {
+        const double s_col0 = pa / nz;              // sum_j u(j,0)
+        const double s_row0 = pc / ny_total;        // sum_k u(0,k)
+        const double u00 = pb / ny_total / nz;      // u(0,0), counted in both
+        mean = (s_col0 + s_row0 - u00) / (ny_total + nz - 1);
+    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int k = L.t + e * L.e8;
-        double a = scale_result(v[e].x, ny, nz, inv_scale), b = scale_result(v[e].y, ny, nz, inv_scale);
+        double a = scale_result(v[e].x, ny_total, nz, inv_scale), b = scale_result(v[e].y, ny_total, nz, inv_scale);
         if (fix) {
             a -= mean;
             b -= mean;
             if (a < floor_value) a = floor_value;
             if (b < floor_value) b = floor_value;
         }
-        if (j0 < ny) dst[(size_t)j0 * nz + k] = a;
-        if (j1 < ny) dst[(size_t)j1 * nz + k] = b;
+        if (j0 < ny) dst[(size_t)(row0 + j0) * nz + k] = a;
+        if (j1 < ny) dst[(size_t)(row0 + j1) * nz + k] = b;
     }
 }
 
@@ -172,14 +219,14 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
 // one column per sequence; inv_symbol is [ncols][ny] (column-major for this kernel), entry (k=0, j=0) = 0
 __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
                                 const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum,
-                                int * __restrict__ ticket, double * __restrict__ border_mean, int nz) {
+                                int * __restrict__ ticket, SpecMap partials, int my_rank, int col0, int nz) {
     QPIC_KERNEL_BEGIN(colsum ? KID_k_p2_cols_solve : KID_COUNT + 16);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
-    const int ny = 1 << log2n;
     const int k = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const bool live = k < ncols;
+    const int ny = 1 << log2n;
     double2 v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = live ? spec[(size_t)(L.t + e * L.e8) * ld + k] : make_double2(0.0, 0.0);
@@ -190,7 +237,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
         for (int e = 0; e < 8; e++) {
             const int j = L.t + e * L.e8;
             const double r = inv[j];
-            v[e] = (j == 0 && k == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * r, v[e].y * r);
+            v[e] = (j == 0 && k + col0 == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * r, v[e].y * r);
         }
     }
     if (colsum) {
@@ -236,10 +283,10 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
         __syncthreads();
         if (is_last) {
             __threadfence();
-            const int nzh = nz / 2 + 1;
-            double pa = 0.0, pb = 0.0;  // Hermitian-weighted sums of Re U(0,k) and Re sum_j U(j,k)
-            for (int kk = threadIdx.x; kk < nzh; kk += blockDim.x) {
-                const double wgt = (kk == 0 || 2 * kk == nz) ? 1.0 : 2.0;
+            double pa = 0.0, pb = 0.0;  // Hermitian-weighted sums of Re U(0,k) and Re sum_j U(j,k) over this rank's columns
+            for (int kk = threadIdx.x; kk < ncols; kk += blockDim.x) {
+                const int kg = kk + col0;
+                const double wgt = (kg == 0 || 2 * kg == nz) ? 1.0 : 2.0;
                 pa += wgt * row0[kk].x;
                 pb += wgt * colsum[kk].x;
             }
@@ -257,10 +304,16 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
                 n = half;
             }
             if (threadIdx.x == 0) {
-                const double s_col0 = red_a[0] / nz;      // sum_j u(j,0)
-                const double s_row0 = colsum[0].x / ny;   // sum_k u(0,k)
-                const double u00 = red_b[0] / ny / nz;    // u(0,0), counted in both
-                *border_mean = (s_col0 + s_row0 - u00) / (ny + nz - 1);
+                // every rank gets this rank's partial sums (slot my_rank of its table); k_p2_rows_c2r adds them up in rank order
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (q < partials.world) {
+                        double * dst = reinterpret_cast<double *>(partials.base[q]) + 4 * my_rank;
+                        dst[0] = red_a[0];
+                        dst[1] = red_b[0];
+                        dst[2] = colsum[0].x;  // meaningful on the rank that owns column 0
+                    }
+                }
                 *ticket = 0;
             }
         }
@@ -273,14 +326,15 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
                                     const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                     const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
-                                    double2 * __restrict__ spec) {
+                                    SpecMap spec, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_forward);
     if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = g.nz, ny = g.ny;
-    const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
-    const bool live = j < ny;
+    const int jl = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    const int j = row0 + jl;
+    const bool live = jl < nrows;
     const int jp = live ? wrap_inc(j, ny) : 0;
     const int jq = (j == ny - 1) ? 0 : j;
     double2 v[8];
@@ -301,13 +355,13 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
     if (live) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) spec[(size_t)j * nz + L.t + e * L.e8] = v[e];
+        for (int e = 0; e < 8; e++) *spec_at(spec, j, L.t + e * L.e8) = v[e];
     }
 }
 
 // by(i) = re/ny/nz, bz(i) = im/ny/nz and the stop test (src/System_3d.cpp:541-552, :569-580)
-__global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, const double2 * __restrict__ spec,
-                                     double * __restrict__ by, double * __restrict__ bz, double threshold, int iteration, double inv_scale) {
+__global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, SpecMap spec, double * __restrict__ by,
+                                     double * __restrict__ bz, double threshold, int iteration, double inv_scale, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_backward);
     // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
     const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
@@ -316,11 +370,12 @@ __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __res
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = g.nz, ny = g.ny;
-    const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
-    const bool live = j < ny;
+    const int jl = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    const int j = row0 + jl;
+    const bool live = jl < nrows;
     double2 v[8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = live ? spec[(size_t)j * nz + L.t + e * L.e8] : make_double2(0.0, 0.0);
+    for (int e = 0; e < 8; e++) v[e] = live ? *spec_at(spec, j, L.t + e * L.e8) : make_double2(0.0, 0.0);
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
     if (!live) return;
     bool bad = false;

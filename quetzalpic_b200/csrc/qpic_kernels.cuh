@@ -58,9 +58,15 @@ enum KernelId {
     KID_k_p2_rows_b_forward,
     KID_k_p2_rows_b_backward,
     KID_k_p2_rows_c2c,
+    KID_k_xchg_barrier,
+    KID_k_halo_reduce_send,
+    KID_k_halo_reduce_add,
+    KID_k_halo_fill,
+    KID_k_migrate_publish,
+    KID_k_migrate_unpack,
     KID_COUNT
 };
-#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c" }
+#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack" }
 
 #ifdef QPIC_EMU
 #define QPIC_KERNEL_BEGIN(id) ((void)0)
@@ -116,8 +122,22 @@ struct Ctl {
     int stop_tag;   // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
     int fast_fail;  // != 0: a half-step displacement left the +-1 cell window of the sort-free deposit; the fast-path
                     // kernels of this and later slices are no-ops until the host redoes the slice on the general path
-    int pad1;
+    int dist_error; // slab-decomposed runs: != 0 after a bounded exchange spin gave up or an exchange buffer overflowed
+    // Slab-decomposed runs migrate particles between GPUs, so the particle counts live on the device (count + 1; 0 = use
+    // the static count the kernel was launched with -- what a zero-initialised control block of a single-GPU run gives):
+    int np1;        // live slots of this slice
+    int np_p1;      // entries of the particle-id arrays (live + emigrated + just arrived) the cell sort has to look at
+    int pad[2];
 };
+
+__device__ __forceinline__ int live_count(const Ctl * ctl, int np_static) {
+    const int v = ctl->np1;
+    return v ? v - 1 : np_static;
+}
+__device__ __forceinline__ int entry_count(const Ctl * ctl, int np_static) {
+    const int v = ctl->np_p1;
+    return v ? v - 1 : np_static;
+}
 
 // every kernel of the xi-loop starts with this test (the B backward rows have their own, see qpic_fft.cuh)
 __device__ __forceinline__ bool cancelled(const Ctl * ctl) { return (ctl->stop_tag | ctl->fast_fail) != 0; }
@@ -309,7 +329,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-    k_scan_apply(const Ctl * ctl, int * __restrict__ count, int n, const int * __restrict__ sums, int * __restrict__ start, int * __restrict__ cursor) {
+    k_scan_apply(const Ctl * ctl, int * __restrict__ count, int n, const int * __restrict__ sums, int * __restrict__ start, int * __restrict__ cursor,
+                 int * __restrict__ live_out) {
     QPIC_KERNEL_BEGIN(KID_k_scan_apply);
     if (cancelled(ctl)) return;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
@@ -328,6 +349,8 @@ __global__ void __launch_bounds__(SCAN_THREADS)
             start[base + t] = run;
             cursor[base + t] = run;
             count[base + t] = 0;
+            // slab-decomposed runs: the last bucket collects the emigrated entries, everything before it is live
+            if (live_out && base + t == n - 1) *live_out = run + 1;
             run += c[t];
         }
     }
@@ -340,7 +363,7 @@ __global__ void k_sort_fill(const Ctl * ctl, int np, const int * __restrict__ ce
     QPIC_KERNEL_BEGIN(KID_k_sort_fill);
     if (cancelled(ctl)) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
+    if (p >= entry_count(ctl, np)) return;
     const int slot = atomicAdd(&cursor[cell[p]], 1);
     tmp[slot] = p;
 }
@@ -352,7 +375,7 @@ __global__ void k_sort_rank(const Ctl * ctl, int np, const int * __restrict__ ce
     QPIC_KERNEL_BEGIN(KID_k_sort_rank);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= np) return;
+    if (s >= entry_count(ctl, np)) return;
     const int p = tmp[s];
     const int c = cell[p];
     const int b = start[c], e = start[c + 1];
@@ -615,7 +638,7 @@ __global__ void k_particles_to_slots(const Ctl * ctl, Particles P, const int * _
     QPIC_KERNEL_BEGIN(KID_k_particles_to_slots);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.np) return;
+    if (s >= live_count(ctl, P.np)) return;
     const int p = perm_b[s];
     P.cell_b[s] = P.cell_p[p];
     P.fy_b[s] = P.fy_p[p];
@@ -633,7 +656,7 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     QPIC_KERNEL_BEGIN(KID_k_particles_gamma);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.np) return;
+    if (s >= live_count(ctl, P.np)) return;
     const double * a_sqr = a_sqr3 + (size_t)ctl->slice * g.n2;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
@@ -679,7 +702,7 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.np) return;
+    if (s >= live_count(ctl, P.np)) return;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double fy = P.fy_b[s], fz = P.fz_b[s];
@@ -742,7 +765,7 @@ __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, co
     QPIC_KERNEL_BEGIN(KID_k_particles_currents_yz);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.np) return;
+    if (s >= live_count(ctl, P.np)) return;
     const int cm = P.cell_m[s];
     const int jm = cm / g.nz, km = cm - jm * g.nz;
     const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[s], P.fz_m[s]);
@@ -752,15 +775,26 @@ __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, co
     P.vjz[s] = nw * P.pzn[s] / w;
 }
 
+// ---- particle migration of slab-decomposed runs (qpic_dist.cuh): where emigrants of k_particles_advance go
+struct MigrateView {
+    int enabled;
+    int row0, ny_loc, cap;
+    double * out[2];   // peer inboxes: [0] of the rank below (its "from above" box), [1] of the rank above; SoA [5][cap]
+    int * out_count;   // local int[2]
+    int * error;
+};
+
 // py <- py_next, pz <- pz_next (src/System_3d.cpp:593-598), coordinate advance with psi_middle gathered at (y,z)
-// (:601-608), new cell descriptor + population count for the next slice's lists; back to particle-id order
+// (:601-608), new cell descriptor + population count for the next slice's lists; back to particle-id order.
+// Slab-decomposed runs: the id of a particle is simply its slot (perm_b == NULL); a particle whose new cell belongs to a
+// neighbouring rank is appended to that rank's inbox and its own entry is parked in the extra "emigrated" bucket n2.
 __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b, const double * __restrict__ psi_middle,
-                                    int * __restrict__ count) {
+                                    int * __restrict__ count, MigrateView mig) {
     QPIC_KERNEL_BEGIN(KID_k_particles_advance);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.np) return;
-    const int p = perm_b[s];
+    if (s >= live_count(ctl, P.np)) return;
+    const int p = perm_b ? perm_b[s] : s;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jc, kc, P.fy_b[s], P.fz_b[s]);
@@ -778,7 +812,28 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
     double f1, f2;
     locate(y, g.dy, g.ny, jn, f1);
     locate(z, g.dz, g.nz, kn, f2);
-    const int cn = jn * g.nz + kn;
+    int cn = jn * g.nz + kn;
+    if (mig.enabled) {
+        const double nw = P.nw_s[s];
+        P.nw[p] = nw;
+        int rel = jn - mig.row0;  // row relative to the slab, minimal image
+        if (2 * rel > g.ny) rel -= g.ny;
+        if (2 * rel < -g.ny) rel += g.ny;
+        if (rel < 0 || rel >= mig.ny_loc) {
+            const int side = rel < 0 ? 0 : 1;
+            if (rel < -mig.ny_loc || rel >= 2 * mig.ny_loc) atomicExch(mig.error, 4);  // beyond the neighbouring slab
+            const int i = atomicAdd(&mig.out_count[side], 1);
+            if (i < mig.cap) {
+                double * b = side == 0 ? mig.out[0] : mig.out[1];
+                b[0 * (size_t)mig.cap + i] = y;
+                b[1 * (size_t)mig.cap + i] = z;
+                b[2 * (size_t)mig.cap + i] = py;
+                b[3 * (size_t)mig.cap + i] = pz;
+                b[4 * (size_t)mig.cap + i] = nw;
+            }
+            cn = g.n2;  // the "emigrated" bucket
+        }
+    }
     P.cell_p[p] = cn;
     P.fy_p[p] = f1;
     P.fz_p[p] = f2;
@@ -797,11 +852,13 @@ struct SliceOut {
 __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double * __restrict__ psi, double * __restrict__ psi_prev,
                                const double * __restrict__ by, const double * __restrict__ bz, const double * __restrict__ rho,
                                const double * __restrict__ jx, double * __restrict__ jy, double * __restrict__ jz,
-                               const double * __restrict__ jy_next, const double * __restrict__ jz_next, int b_is_zero, int roll, int ignore_stop) {
+                               const double * __restrict__ jy_next, const double * __restrict__ jz_next, int b_is_zero, int roll, int ignore_stop,
+                               int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_end_of_slice);
     if (cancelled(ctl) && !ignore_stop) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n2) return;
+    // rows [row0, row0 + nrows): all of them on a single GPU, the own slab in a distributed sweep
+    if (blockIdx.x * blockDim.x + threadIdx.x >= (unsigned)(nrows * g.nz)) return;
+    const int t = row0 * g.nz + blockIdx.x * blockDim.x + threadIdx.x;
     const int i = ignore_stop ? 0 : ctl->slice;
     const int j = t / g.nz, k = t - j * g.nz;
     const size_t off = (size_t)i * g.n2 + t;
@@ -873,6 +930,10 @@ struct TileOutput {
 
 struct TileJob {
     int nout;
+    // slab-decomposed runs launch only the tile rows that the rank's particles can reach (own rows + one tile row on either
+    // side) and add the background terms on own rows only; single GPU: tile_row0 = 0, tile_rows = all, own = [0, ny)
+    int tile_row0, tile_rows;
+    int own_row0, own_rows;
     TileOutput o[TILE_MAX_OUT];
     const double *jxb3, *rhob3, *rho_ion;  // for bg_mode 1
     const double *psi_mid, *nw;            // jy/jz job
@@ -890,15 +951,16 @@ __device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g
     if (ty < 1 || tz < 1 || j >= g.ny || k >= g.nz) return;
     const int t = j * g.nz + k;
     const size_t off3 = (size_t)ctl->slice * g.n2 + t;
+    const bool own = (unsigned)(j - job.own_row0) < (unsigned)job.own_rows;
 #pragma unroll
     for (int a = 0; a < NOUT; a++) {
         const TileOutput & o = job.o[a];
         double v = 0.0;
-        if (o.bg_mode == 1) {
+        if (o.bg_mode == 1 && own) {
             const double jb_ = job.jxb3 ? job.jxb3[off3] : 0.0;
             const double rb_ = job.rhob3 ? job.rhob3[off3] : 0.0;
             v = jb_ - rb_ - job.rho_ion[t];
-        } else if (o.bg_mode == 2 && o.bg3) {
+        } else if (o.bg_mode == 2 && o.bg3 && own) {
             v = o.bg3[off3];
         }
         const double * acc_a = acc + a * 4 * TILE_CELLS;
@@ -921,7 +983,7 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
     __shared__ double acc[NOUT * 4 * TILE_CELLS];
     const int ay = threadIdx.y, az = threadIdx.x;
     const int tcell = ay * TILE_ACC + az;
-    const int jt = blockIdx.y * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
+    const int jt = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
     const int cell = mod_wrap(jt, g.ny) * g.nz + mod_wrap(kt, g.nz);
     const int s0 = start[cell], s1 = start[cell + 1];
     double c00[NOUT], c10[NOUT], c01[NOUT], c11[NOUT];
@@ -987,7 +1049,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
     int * lst = cnt + NOUT * TILE_CELLS;                                   // [NOUT][BIN_K][TILE_CELLS]
     const int sy = threadIdx.y, sz = threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
-    const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
+    const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
     const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
     // staggering of output a in y / z
     auto stag_y = [](int a) { return MODE == 1 && a == 0; };

@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "qpic_set_current_slice", "qpic_solve_poisson_host", "qpic_solve_helmholtz_pair_host", "qpic_last_step_stats",
     "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
     "qpic_fast_path_aborts", "qpic_wait_transfers", "qpic_timeline_reset", "qpic_timeline_read", "qpic_timeline_kernel_name",
+    "qpic_dist_region_bytes", "qpic_dist_region", "qpic_dist_ipc_handle", "qpic_dist_attach_ipc", "qpic_dist_attach_pointers", "qpic_dist_row_range",
 ]
 
 
@@ -55,6 +56,8 @@ class QpicParams(ctypes.Structure):
         ("use_graph", ctypes.c_int),
         ("stop_check_interval", ctypes.c_int),
         ("force_general_deposit", ctypes.c_int),
+        ("dist_rank", ctypes.c_int), ("dist_world", ctypes.c_int),
+        ("particle_capacity", ctypes.c_size_t),
     ]
 
 
@@ -108,6 +111,14 @@ class QpicLibrary:
         L.qpic_wait_transfers.argtypes = [vp]
         L.qpic_fast_path_aborts.argtypes = [vp]
         L.qpic_fast_path_aborts.restype = ctypes.c_long
+        L.qpic_dist_region_bytes.argtypes = [vp]
+        L.qpic_dist_region_bytes.restype = ctypes.c_size_t
+        L.qpic_dist_region.argtypes = [vp]
+        L.qpic_dist_region.restype = vp
+        L.qpic_dist_ipc_handle.argtypes = [vp, vp]
+        L.qpic_dist_attach_ipc.argtypes = [vp, vp]
+        L.qpic_dist_attach_pointers.argtypes = [vp, ctypes.POINTER(vp)]
+        L.qpic_dist_row_range.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
         self.L = L
 
     def pinned_array(self, shape):
@@ -178,7 +189,7 @@ class WakefieldSolver:
 
     def __init__(self, nx, ny, nz, lx, ly, lz, magnetic_field_iterations, psi_threshold=1e-4, magnetic_field_D=10.0,
                  threshold_B=100.0, device=0, keep_slices_3d=False, use_graph=True, stop_check_interval=64, force_general_deposit=False,
-                 library=None):
+                 library=None, dist_rank=0, dist_world=1, particle_capacity=0):
         self.lib = library if library is not None else load_library()
         L = self.lib.L
         p = QpicParams()
@@ -192,6 +203,8 @@ class WakefieldSolver:
         p.use_graph = int(bool(use_graph))
         p.stop_check_interval = int(stop_check_interval)
         p.force_general_deposit = int(bool(force_general_deposit))
+        p.dist_rank, p.dist_world, p.particle_capacity = int(dist_rank), int(dist_world), int(particle_capacity)
+        self.dist_rank, self.dist_world = int(dist_rank), int(dist_world)
         self.params = p
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.keep_slices_3d = bool(keep_slices_3d)
@@ -366,6 +379,32 @@ class WakefieldSolver:
         if a.shape != (self.particle_count,):
             raise ValueError("particle arrays have shape (particle_count,)")
         self._check(self.lib.L.qpic_upload_particles(self.ctx, PARTICLE_FIELDS.index(name), a.ctypes.data))
+
+    # -- slab-decomposed multi-GPU sweep (see quetzalpic_b200/dist.py)
+    @property
+    def row_range(self):
+        """(first own row, number of own rows): the whole grid on a single GPU"""
+        r0, n = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self.lib.L.qpic_dist_row_range(self.ctx, ctypes.byref(r0), ctypes.byref(n)))
+        return r0.value, n.value
+
+    def dist_ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.L.qpic_dist_ipc_handle(self.ctx, buf))
+        return buf.raw
+
+    def dist_attach_ipc(self, handles):
+        """handles: the 64-byte handles of all ranks, in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.dist_world
+        self._check(self.lib.L.qpic_dist_attach_ipc(self.ctx, blob))
+
+    def dist_region(self):
+        return self.lib.L.qpic_dist_region(self.ctx)
+
+    def dist_attach_pointers(self, regions):
+        arr = (ctypes.c_void_p * self.dist_world)(*regions)
+        self._check(self.lib.L.qpic_dist_attach_pointers(self.ctx, arr))
 
     # -- building blocks
     def solve_poisson(self, src, D=0.0):

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = qp.load_library()
     for sym in declared:
         assert hasattr(lib.L, sym), sym
-    assert lib.L.qpic_abi_version() == 1
+    assert lib.L.qpic_abi_version() == 2
 
 
 def test_library_is_cuda_only_and_fails_loudly_without_device():
@@ -110,3 +110,70 @@ def test_bench_bytes_formula():
     import bench
     # 1.554 GB per slice at config #2
     assert abs(bench.algorithmic_bytes_per_slice(512 * 512, 4 * 512 * 512, 5) - 1.554e9) < 1e6
+
+
+# ---- host logic of the slab-decomposed sweep (quetzalpic_b200/dist.py)
+
+def test_slab_partition_covers_every_particle_once():
+    import numpy as np
+    from quetzalpic_b200 import wake_particle_lattice
+    from quetzalpic_b200.dist import gather_rows, half_spectrum_columns, slab_particles, slab_rows
+    ny, nz, ly, lz = 64, 32, 6.4, 3.2
+    y, z, n = wake_particle_lattice(ny, nz, ly, lz, 2, 2)
+    for world in (2, 4):
+        parts = [slab_particles(y, z, n, ny, ly, r, world) for r in range(world)]
+        assert sum(p[0].size for p in parts) == y.size
+        for r, (py, pz, pn) in enumerate(parts):
+            r0, nr = slab_rows(ny, r, world)
+            rows = (py / (ly / ny)).astype(int)
+            assert rows.min() >= r0 and rows.max() < r0 + nr
+        cols = [half_spectrum_columns(nz, r, world) for r in range(world)]
+        assert sum(c[1] for c in cols) == nz // 2 + 1
+        assert all(cols[r][0] == cols[r - 1][0] + cols[r - 1][1] for r in range(1, world) if cols[r][1] > 0)
+        full = np.arange(3 * ny * nz, dtype=float).reshape(3, ny, nz)
+        per_rank = []
+        for r in range(world):
+            a = np.full_like(full, np.nan)
+            r0, nr = slab_rows(ny, r, world)
+            a[:, r0:r0 + nr] = full[:, r0:r0 + nr]
+            per_rank.append(a)
+        assert np.array_equal(gather_rows(per_rank, ny, axis=1), full)
+
+
+def _gloo_worker(rank, world, port, out):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from quetzalpic_b200 import dist as qd
+
+        class FakeSolver:
+            dist_world = world
+
+            def dist_ipc_handle(self):
+                return bytes([rank]) * 64
+
+            def dist_attach_ipc(self, handles):
+                out.put((rank, [h[0] for h in handles], [len(h) for h in handles]))
+
+        qd.attach_process_group(FakeSolver())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_over_gloo_world_size_2():
+    """attach_process_group all-gathers the 64-byte handles in rank order (gloo, two CPU processes)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(out.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [(0, [0, 1], [64, 64]), (1, [0, 1], [64, 64])]

@@ -8,8 +8,9 @@
 
 namespace qemu {
 
-Block * g_block = nullptr;
-Fiber * g_fiber = nullptr;
+// thread_local: two contexts can be driven from two host threads (the slab-decomposed sweep, tools/emu/emu_dist_check.py)
+thread_local Block * g_block = nullptr;
+thread_local Fiber * g_fiber = nullptr;
 
 static const size_t STACK_BYTES = 256 * 1024;
 

@@ -44,7 +44,7 @@ static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __constant__ static
 
 namespace qemu {
@@ -78,8 +78,8 @@ struct Block {
     ucontext_t sched;
 };
 
-extern Block * g_block;
-extern Fiber * g_fiber;
+extern thread_local Block * g_block;
+extern thread_local Fiber * g_fiber;
 
 void launch(dim3 grid, dim3 block, size_t smem, bool flat, const std::function<void()> & body);
 void yield_fiber();
@@ -117,6 +117,7 @@ static inline void __syncthreads() { qemu::sync_threads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { qemu::sync_warp(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
 
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int lane, int = 32) {
