@@ -454,7 +454,7 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     if (fused) *fused = fuse;
     if (c->dist.on && !fuse) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the fused power-of-two solve");
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_r2c, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
+        QPIC_LAUNCH((c->dist.on ? k_p2_rows_r2c<true> : k_p2_rows_r2c<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_r2c<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz, R.spb);
     }
@@ -463,7 +463,7 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     QPIC_TRY(enqueue_columns(c, st, ctl, D, false, fuse));
     QPIC_TRY(dist_barrier(c, st));  // every rank's columns (and border-sum partials) are done
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_c2r, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
+        QPIC_LAUNCH((c->dist.on ? k_p2_rows_c2r<true> : k_p2_rows_c2r<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
                     row_first(c), ny, c->inv_scale, fuse ? 1 : 0, c->dist.on ? reinterpret_cast<const double *>(c->dist.region + c->dist.v.lay.partials) : c->partials,
                     c->prm.psi_threshold - 1);
     } else {
@@ -480,7 +480,7 @@ int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, doub
 int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, double * bz, double threshold, int iteration) {
     const qpic_ctx::FftLaunch & R = c->rows_cplx;
     if (c->pow2_z) {
-        QPIC_LAUNCH(k_p2_rows_b_backward, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
+        QPIC_LAUNCH((c->dist.on ? k_p2_rows_b_backward<true> : k_p2_rows_b_backward<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
                     c->inv_scale, row_first(c), row_count(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_b_backward<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
@@ -568,7 +568,9 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
     j.nw = c->P.nw_s;
     const dim3 block(TILE_ACC + 3, TILE_ACC + 3);
-    QPIC_LAUNCH(k_tile_bin_deposit<1>, tile_grid(c), block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
+    dim3 grid = tile_grid(c);
+    grid.z = 2;  // jy_next / jz_next
+    QPIC_LAUNCH(k_tile_bin_deposit<1>, grid, block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
     return check_launch(c, "k_tile_deposit_jy_jz");
 }
 
@@ -716,7 +718,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         {
             const qpic_ctx::FftLaunch & R = c->rows_cplx;
             if (c->pow2_z) {
-                QPIC_LAUNCH(k_p2_rows_b_forward, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D,
+                QPIC_LAUNCH((c->dist.on ? k_p2_rows_b_forward<true> : k_p2_rows_b_forward<false>), R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D,
                             c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
                             c->f2[QPIC_F2_JZ_NEXT], spec_map(c, true), row_first(c), row_count(c));
             } else {
@@ -1075,10 +1077,14 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
         }
         if (cols_max > SMEM_DEFAULT_LIMIT) {
@@ -1190,11 +1196,11 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_end_of_slice);
         QPIC_PRELOAD(k_next_slice);
         QPIC_PRELOAD(k_init_a_sqr);
-        QPIC_PRELOAD(k_p2_rows_r2c);
-        QPIC_PRELOAD(k_p2_rows_c2r);
+        QPIC_PRELOAD(k_p2_rows_r2c<true>);
+        QPIC_PRELOAD(k_p2_rows_c2r<true>);
         QPIC_PRELOAD(k_p2_cols_solve);
-        QPIC_PRELOAD(k_p2_rows_b_forward);
-        QPIC_PRELOAD(k_p2_rows_b_backward);
+        QPIC_PRELOAD(k_p2_rows_b_forward<true>);
+        QPIC_PRELOAD(k_p2_rows_b_backward<true>);
 #undef QPIC_PRELOAD
     }
 #endif

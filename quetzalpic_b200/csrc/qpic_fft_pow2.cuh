@@ -87,8 +87,10 @@ __device__ __forceinline__ double2 * spec_base(const SpecMap & m, int q) {
     return b;
 }
 
+// DIST is a template parameter of the row kernels so that the single-GPU instantiation keeps plain [j][k] indexing
+template <bool DIST>
 __device__ __forceinline__ double2 * spec_at(const SpecMap & m, int j, int k) {
-    if (m.world == 1) return m.base[0] + (size_t)j * m.cpr + k;
+    if (!DIST) return m.base[0] + (size_t)j * m.cpr + k;
     const int q = k / m.cpr;
     return spec_base(m, q) + (size_t)j * m.cpr + (k - q * m.cpr);
 }
@@ -114,10 +116,10 @@ __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
 
 // forward rows, two real rows per sequence -> half spectra spec[ny][nzh]
 // rows [row0, row0 + ny) of src (a full-size array)
+template <bool DIST>
 __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, SpecMap spec, int ny,
                               int row0) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_r2c);
-    if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = 1 << log2n, nzh = nz / 2 + 1;
@@ -128,6 +130,7 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
         const int k = L.t + e * L.e8;
         v[e] = make_double2(j0 < ny ? src[(size_t)(row0 + j0) * nz + k] : 0.0, j1 < ny ? src[(size_t)(row0 + j1) * nz + k] : 0.0);
     }
+    if (cancelled(ctl)) return;  // tested after the loads are in flight (uniform over the block)
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
     // the split needs Z_k and Z_{n-k}: one more exchange.  The last exchange of the transform used the other buffer
     // (or none at all), so this buffer is free once every thread has left the transform's final read.
@@ -141,8 +144,8 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
         const double2 zk = z[k];
         const double2 zm = z[k == 0 ? 0 : nz - k];
         // U0 = (Z_k + conj(Z_{n-k})) / 2,  U1 = (Z_k - conj(Z_{n-k})) / (2i)
-        *spec_at(spec, row0 + j0, k) = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-        if (j1 < ny) *spec_at(spec, row0 + j1, k) = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+        *spec_at<DIST>(spec, row0 + j0, k) = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+        if (j1 < ny) *spec_at<DIST>(spec, row0 + j1, k) = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
     }
 }
 
@@ -156,10 +159,10 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
 // The column kernel's last block reduces these sums with a fixed-order tree and leaves the mean in *border_mean.
 // `ny` rows starting at global row `row0` of a field with ny_total rows.  The border mean is assembled from the per-rank
 // partial sums the column kernels left in partials[rank][0..2] (one rank on a single GPU), in rank order.
+template <bool DIST>
 __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, SpecMap spec, double * __restrict__ dst, int ny, int row0,
                               int ny_total, double inv_scale, int fix, const double * __restrict__ partials, double floor_value) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2r);
-    if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = 1 << log2n;
@@ -182,8 +185,8 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
         const int i = L.t + e * L.e8;
         const bool mirror = i > nz / 2;
         const int k = mirror ? nz - i : i;
-        double2 v0 = (j0 < ny) ? *spec_at(spec, row0 + j0, k) : make_double2(0.0, 0.0);
-        double2 v1 = (j1 < ny) ? *spec_at(spec, row0 + j1, k) : make_double2(0.0, 0.0);
+        double2 v0 = (j0 < ny) ? *spec_at<DIST>(spec, row0 + j0, k) : make_double2(0.0, 0.0);
+        double2 v1 = (j1 < ny) ? *spec_at<DIST>(spec, row0 + j1, k) : make_double2(0.0, 0.0);
         if (k == 0 || 2 * k == nz) {
             // c2r ignores the imaginary part of the DC / Nyquist bins (they are rounding noise for a real field)
             v0.y = 0.0;
@@ -192,6 +195,7 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
         // Z_k = V0 + i V1;  Z_{n-k} = conj(V0) + i conj(V1)
         v[e] = mirror ? make_double2(v0.x + v1.y, v1.x - v0.y) : make_double2(v0.x - v1.y, v0.y + v1.x);
     }
+    if (cancelled(ctl)) return;
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
     double mean = 0.0;
     if (fix) {
@@ -221,7 +225,6 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
                                 const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum,
                                 int * __restrict__ ticket, SpecMap partials, int my_rank, int col0, int nz) {
     QPIC_KERNEL_BEGIN(colsum ? KID_k_p2_cols_solve : KID_COUNT + 16);
-    if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int k = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
@@ -230,14 +233,17 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
     double2 v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = live ? spec[(size_t)(L.t + e * L.e8) * ld + k] : make_double2(0.0, 0.0);
+    // 1 / symbol: fetched together with the column so that it is there when the forward transform ends
+    double rinv[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) rinv[e] = live ? inv_symbol[(size_t)k * ny + L.t + e * L.e8] : 0.0;
+    if (cancelled(ctl)) return;
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twy);
     if (live) {
-        const double * __restrict__ inv = inv_symbol + (size_t)k * ny;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int j = L.t + e * L.e8;
-            const double r = inv[j];
-            v[e] = (j == 0 && k + col0 == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * r, v[e].y * r);
+            v[e] = (j == 0 && k + col0 == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * rinv[e], v[e].y * rinv[e]);
         }
     }
     if (colsum) {
@@ -323,12 +329,12 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 // ------------------------------------------------------------------------------------------------ complex field (By + i Bz)
 
 // see k_fft_rows_b_forward (qpic_fft.cuh) for the source terms (src/System_3d.cpp:489-495, :530-536, :555-564 incl. :563)
+template <bool DIST>
 __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
                                     const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                     const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
                                     SpecMap spec, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_forward);
-    if (cancelled(ctl)) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = g.nz, ny = g.ny;
@@ -352,21 +358,20 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
             v[e] = make_double2(0.0, 0.0);
         }
     }
+    if (cancelled(ctl)) return;
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
     if (live) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) *spec_at(spec, j, L.t + e * L.e8) = v[e];
+        for (int e = 0; e < 8; e++) *spec_at<DIST>(spec, j, L.t + e * L.e8) = v[e];
     }
 }
 
 // by(i) = re/ny/nz, bz(i) = im/ny/nz and the stop test (src/System_3d.cpp:541-552, :569-580)
+template <bool DIST>
 __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, SpecMap spec, double * __restrict__ by,
                                      double * __restrict__ bz, double threshold, int iteration, double inv_scale, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_backward);
     // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
-    const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
-    const int tag = ctl->stop_tag;
-    if ((tag != 0 && tag != my_tag) || ctl->fast_fail) return;
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
     const int nz = g.nz, ny = g.ny;
@@ -375,7 +380,10 @@ __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __res
     const bool live = jl < nrows;
     double2 v[8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = live ? *spec_at(spec, j, L.t + e * L.e8) : make_double2(0.0, 0.0);
+    for (int e = 0; e < 8; e++) v[e] = live ? *spec_at<DIST>(spec, j, L.t + e * L.e8) : make_double2(0.0, 0.0);
+    const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
+    const int tag = ctl->stop_tag;
+    if ((tag != 0 && tag != my_tag) || ctl->fast_fail) return;
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
     if (!live) return;
     bool bad = false;

@@ -92,7 +92,7 @@ __device__ __forceinline__ unsigned long long tl_now() {
 struct TlSpan {
     int kid;
     __device__ __forceinline__ TlSpan(int kid_) : kid(kid_) {
-        const bool first = (threadIdx.x | threadIdx.y | blockIdx.x | blockIdx.y) == 0;
+        const bool first = (threadIdx.x | threadIdx.y | blockIdx.x | blockIdx.y | blockIdx.z) == 0;
         const unsigned long long t0 = first ? tl_now() : 0ull;
         pdl_grid_sync();
         if (first) {
@@ -102,7 +102,7 @@ struct TlSpan {
     }
     __device__ __forceinline__ ~TlSpan() {
         if ((threadIdx.x | threadIdx.y) == 0) {
-            const unsigned int total = gridDim.x * gridDim.y;
+            const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
             const unsigned int n = atomicAdd(&g_tl_exit[kid], 1u) + 1u;
             if (n % total == 0u) {
                 const int slot = atomicAdd(&g_tl_n, 1);
@@ -667,9 +667,13 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     const double q = 1 + psi_particle;
     const double gamma = 0.5 * (1 + py * py + pz * pz + a_particle + q * q) / q;
     const double px = 0.5 * (1 + py * py + pz * pz + a_particle - q * q) / q;
-    const int p = perm_b[s];
-    P.gamma[p] = gamma;
-    P.px[p] = px;
+    if (!want_invariants) {
+        // no B iterations / no push follow (M = 0 or slice 0): this is the final gamma, px of the particle (the push
+        // writes them otherwise)
+        const int p = perm_b[s];
+        P.gamma[p] = gamma;
+        P.px[p] = px;
+    }
     P.gam[s] = gamma;
     P.pxs[s] = px;
     store_currents(P, s, nw, gamma, px);
@@ -700,9 +704,10 @@ template <bool FAST>
 __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
                                     int * __restrict__ count) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
-    if (cancelled(ctl)) return;
+    // The control block is tested only before the first store: its load then overlaps the streaming loads instead of
+    // heading the dependent chain (every slot < P.np is readable whatever the flags say).
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= live_count(ctl, P.np)) return;
+    if (s >= P.np) return;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double fy = P.fy_b[s], fz = P.fz_b[s];
@@ -719,6 +724,7 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     // by lives at (y, z + dz/2), bz at (y + dy/2, z)  (src/System_3d.cpp:180-181)
     const double by_particle = gather4(by, g.nz, jc, wrap_inc(jc, g.ny), ks, wrap_inc(ks, g.nz), fy, fzs);
     const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
+    if (cancelled(ctl) || s >= live_count(ctl, P.np)) return;
     double pyn = py - t1y;
     pyn += g.dx * gamma * dpy / q;
     pyn -= g.dx * bz_particle;
@@ -946,8 +952,17 @@ __device__ __forceinline__ int mod_wrap(int j, int n) {
 
 // nodes of the patch: own cell's (1-fy)(1-fz) sum, then the y-, z- and diagonal neighbours' sums, fixed order.
 // acc layout: [output][corner][target cell] (conflict-free), target cell (ty, tz) = (node - patch origin + 1)
+// rho_ion at the node of target cell (ty, tz), fetched at the start of a kernel whose first output has bg_mode 1 so that the
+// load is not part of the dependent chain at its end
 template <int NOUT>
-__device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g, const TileJob & job, const double * acc, int ty, int tz, int j, int k) {
+__device__ __forceinline__ double tile_prefetch_ion(const Geom & g, const TileJob & job, int ty, int tz, int j, int k) {
+    if (job.o[0].bg_mode != 1 || ty < 1 || tz < 1 || j >= g.ny || k >= g.nz) return 0.0;
+    return job.rho_ion[j * g.nz + k];
+}
+
+template <int NOUT>
+__device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g, const TileJob & job, const double * acc, int ty, int tz, int j, int k,
+                                                 double ion) {
     if (ty < 1 || tz < 1 || j >= g.ny || k >= g.nz) return;
     const int t = j * g.nz + k;
     const size_t off3 = (size_t)ctl->slice * g.n2 + t;
@@ -959,7 +974,7 @@ __device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g
         if (o.bg_mode == 1 && own) {
             const double jb_ = job.jxb3 ? job.jxb3[off3] : 0.0;
             const double rb_ = job.rhob3 ? job.rhob3[off3] : 0.0;
-            v = jb_ - rb_ - job.rho_ion[t];
+            v = jb_ - rb_ - (a == 0 ? ion : job.rho_ion[t]);
         } else if (o.bg_mode == 2 && o.bg3 && own) {
             v = o.bg3[off3];
         }
@@ -975,17 +990,14 @@ __device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g
 template <int NOUT, bool FINAL_PASS>
 __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     QPIC_KERNEL_BEGIN(KID_COUNT + (job.o[0].bg_mode == 2 ? 2 : 0) + (FINAL_PASS ? 8 : 0));
-    if (FINAL_PASS) {
-        if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
-    } else if (cancelled(ctl)) {
-        return;
-    }
+    // (the control block is tested after the particle loop: see k_particles_predict)
     __shared__ double acc[NOUT * 4 * TILE_CELLS];
     const int ay = threadIdx.y, az = threadIdx.x;
     const int tcell = ay * TILE_ACC + az;
     const int jt = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
     const int cell = mod_wrap(jt, g.ny) * g.nz + mod_wrap(kt, g.nz);
     const int s0 = start[cell], s1 = start[cell + 1];
+    const double ion = tile_prefetch_ion<NOUT>(g, job, ay, az, jt, kt);
     double c00[NOUT], c10[NOUT], c01[NOUT], c11[NOUT];
 #pragma unroll
     for (int a = 0; a < NOUT; a++) c00[a] = c10[a] = c01[a] = c11[a] = 0.0;
@@ -1014,6 +1026,11 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
             }
         }
     }
+    if (FINAL_PASS) {
+        if (ctl->fast_fail || (ctl->stop_tag != 0 && (ctl->stop_tag - 1) / STOP_TAG_STRIDE != ctl->slice)) return;
+    } else if (cancelled(ctl)) {
+        return;
+    }
 #pragma unroll
     for (int a = 0; a < NOUT; a++) {
         double * acc_a = acc + a * 4 * TILE_CELLS;
@@ -1023,7 +1040,7 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
         acc_a[3 * TILE_CELLS + tcell] = c11[a];
     }
     __syncthreads();
-    tile_store_nodes<NOUT>(ctl, g, job, acc, ay, az, jt, kt);
+    tile_store_nodes<NOUT>(ctl, g, job, acc, ay, az, jt, kt, ion);
 }
 
 // MODE 0: psi_middle source = jx_bunch(i) - rho_bunch(i) - rho_ion + deposit(-n) at the half-step positions (src/System_3d.cpp:446-457)
@@ -1034,28 +1051,32 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
 // A, <-> target cell (j0 - 2 + sy, k0 - 2 + sz) for 1 <= sy, sz <= TILE_ACC in phase B (j0, k0: first node of the patch).
 template <int MODE>
 inline size_t tile_bin_smem_bytes() {
-    constexpr int NOUT = MODE == 0 ? 1 : 2;
-    return (size_t)NOUT * TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int));
+    return (size_t)TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int));
 }
 
 template <int MODE>
 __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
     k_tile_bin_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 1 + 4 * MODE);
-    if (cancelled(ctl)) return;
-    constexpr int NOUT = MODE == 0 ? 1 : 2;
-    QPIC_DYN_SMEM(double, acc);                                            // [NOUT][4][TILE_CELLS]
-    int * cnt = reinterpret_cast<int *>(acc + NOUT * 4 * TILE_CELLS);      // [NOUT][TILE_CELLS]
-    int * lst = cnt + NOUT * TILE_CELLS;                                   // [NOUT][BIN_K][TILE_CELLS]
+    // MODE 1: jy_next and jz_next are deposited by separate blocks (blockIdx.z): twice the blocks with half the work and
+    // half the shared memory each fill the SMs better than one block doing both.  (The control block is tested before the
+    // final stores only: see k_particles_predict.)
+    constexpr int NOUT = 1;
+    const int out_a = MODE == 1 ? (int)blockIdx.z : 0;
+    QPIC_DYN_SMEM(double, acc);                                            // [4][TILE_CELLS]
+    int * cnt = reinterpret_cast<int *>(acc + NOUT * 4 * TILE_CELLS);      // [TILE_CELLS]
+    int * lst = cnt + NOUT * TILE_CELLS;                                   // [BIN_K][TILE_CELLS]
     const int sy = threadIdx.y, sz = threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
     const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
     const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
-    // staggering of output a in y / z
-    auto stag_y = [](int a) { return MODE == 1 && a == 0; };
-    auto stag_z = [](int a) { return MODE == 1 && a == 1; };
+    // staggering of this block's output in y / z
+    const bool sty = MODE == 1 && out_a == 0, stz = MODE == 1 && out_a == 1;
+    auto stag_y = [sty](int) { return sty; };
+    auto stag_z = [stz](int) { return stz; };
 
     for (int i = tid; i < NOUT * TILE_CELLS; i += nthreads) cnt[i] = 0;
+    const double ion = tile_prefetch_ion<1>(g, job, sy - 1, sz - 1, ju, ku);
     __syncthreads();
 
     // ---- phase A: bin the particles of this source cell
@@ -1095,7 +1116,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
 #pragma unroll
         for (int a = 0; a < NOUT; a++) {
             double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
-            const double * __restrict__ val = job.o[a].val;
+            const double * __restrict__ val = out_a == 0 ? job.o[0].val : job.o[1].val;
             auto visit = [&](int s, int hy, int hz) {
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
                 double v;
@@ -1109,7 +1130,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                     const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
                     v = job.nw[s] * val[s] / w;
                 } else {
-                    v = job.o[a].sign * val[s];
+                    v = job.o[0].sign * val[s];
                 }
                 const double wy = stag_y(a) ? (hy ? fy - 0.5 : fy + 0.5) : fy;
                 const double wz = stag_z(a) ? (hz ? fz - 0.5 : fz + 0.5) : fz;
@@ -1160,7 +1181,17 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
         }
     }
     __syncthreads();
-    if (is_target) tile_store_nodes<NOUT>(ctl, g, job, acc, ty, tz, ju, ku);
+    if (cancelled(ctl)) return;
+    if (is_target) {
+        if (MODE == 1 && out_a == 1) {
+            // the second output of the job is this block's only one
+            TileJob mine = job;
+            mine.o[0] = job.o[1];
+            tile_store_nodes<1>(ctl, g, mine, acc, ty, tz, ju, ku, 0.0);
+        } else {
+            tile_store_nodes<1>(ctl, g, job, acc, ty, tz, ju, ku, ion);
+        }
+    }
 }
 
 }  // namespace qpic

@@ -25,9 +25,9 @@ def test_slab_sweep_matches_oracle_and_single_gpu(world, n, ppc, a0):
     from quetzalpic_b200.dist import SlabGroup
     nx, ny, nz = n
     case = Case.synthetic(n=n, d=(0.2, 0.1, 0.1), M=3, ppc=ppc, a0=a0, sigma=(1.2, 0.25 * ny * 0.1, 0.3 * nz * 0.1))
-    # the laser sits on a slab edge so that particles migrate in both directions
+    # the laser sits a few cells off a slab edge so that particles migrate (and the ranks' counts change)
     wx, wy, wz = case.laser[1:4]
-    case.laser = (0.5 * a0 * a0, wx, wy, wz, 0.6 * nx * 0.2, 0.1 * ny / world, 0.05 * nz)
+    case.laser = (0.5 * a0 * a0, wx, wy, wz, 0.6 * nx * 0.2, 0.1 * ny / world - 0.63, 0.05 * nz)
     o = case.make_oracle()
     o.solve_wakefield()
     with case.make_solver() as single:
