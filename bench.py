@@ -60,7 +60,7 @@ KERNEL_BYTES = {
     "k_deposit_charge": lambda N, P: 8.0 * (2 * N + 3 * P),
     "k_deposit_jx_rho_chi": lambda N, P: 8.0 * (3 * N + 5 * P),
     "k_deposit_jx": lambda N, P: 8.0 * (2 * N + 3 * P),
-    "k_deposit_rho_chi": lambda N, P: 8.0 * (3 * N + 4 * P),
+    "k_deposit_rho_chi": lambda N, P: 8.0 * (3 * N + 5 * P),
     "k_deposit_jy_jz": lambda N, P: 8.0 * (2 * N + 4 * P),
     "k_particles_currents_yz": lambda N, P: 8.0 * (7.5 * P),
     # transforms
@@ -72,7 +72,7 @@ KERNEL_BYTES = {
     "k_fft_rows_b_backward": lambda N, P: 8.0 * (4 * N),
     # particles
     "k_particles_gamma": lambda N, P: 8.0 * (17.5 * P),
-    "k_particles_predict": lambda N, P: 8.0 * (24 * P),  # predictor + corrector: reads 14.5, writes 9.5 doubles per particle
+    "k_particles_predict": lambda N, P: 8.0 * (22 * P),  # predictor + corrector: reads 14.5, writes 7.5 doubles per particle
     "k_particles_advance": lambda N, P: 8.0 * (15 * P),
     "k_particles_to_slots": lambda N, P: 8.0 * (15.5 * P),
     "k_end_of_slice": lambda N, P: 8.0 * (17 * N),
@@ -86,12 +86,12 @@ KERNEL_BYTES = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on the bench workload's transverse shape, from the
-# ncu capture committed as profiles/r01_final_launches_ncu.csv (cold-cache replays: an upper bound on the in-graph traffic)
+# ncu capture committed as profiles/r02_launches_ncu.csv (cold-cache replays: an upper bound on the in-graph traffic)
 NCU_TRAFFIC = {
-    "k_tile_deposit_jy_jz": 51.43e6, "k_tile_deposit_charge_mid": 34.6e6, "k_tile_deposit_jx": 26.2e6, "k_tile_deposit_charge": 26.2e6,
-    "k_particles_predict": 124.2e6, "k_particles_gamma": 105.0e6, "k_particles_advance": 102.7e6,
-    "k_particles_to_slots": 85.4e6, "k_fft_cols_solve": 4.8e6, "k_fft_rows_b_forward": 14.7e6, "k_fft_rows_b_backward": 4.2e6,
-    "k_fft_rows_r2c": 2.1e6, "k_fft_rows_c2r": 2.2e6,
+    "k_tile_deposit_jy_jz": 49.33e6, "k_tile_deposit_charge_mid": 32.52e6, "k_tile_deposit_jx": 26.57e6, "k_tile_deposit_charge": 26.57e6,
+    "k_tile_deposit_rho_chi": 43.01e6, "k_particles_predict": 135.73e6, "k_particles_gamma": 85.90e6, "k_particles_advance": 103.64e6,
+    "k_particles_to_slots": 83.92e6, "k_fft_cols_solve": 4.61e6, "k_fft_rows_b_forward": 14.70e6, "k_fft_rows_b_backward": 4.23e6,
+    "k_fft_rows_r2c": 2.11e6, "k_fft_rows_c2r": 2.17e6,
 }
 
 

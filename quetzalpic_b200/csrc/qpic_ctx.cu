@@ -525,7 +525,8 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
         auto kern = final_pass ? k_tile_deposit<1, true> : k_tile_deposit<1, false>;
         QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
     } else if (j.nout == 2) {
-        auto kern = final_pass ? k_tile_deposit<2, true> : k_tile_deposit<2, false>;
+        // rho + susceptibility after the B iterations: the values are formed in the deposit (the predictor kernel does not store them)
+        auto kern = final_pass ? k_tile_deposit<2, true, true> : k_tile_deposit<2, false>;
         QPIC_LAUNCH(kern, grid, block, 0, st, c->ctl, c->g, c->start_b, c->P, j);
     } else {
         auto kern = final_pass ? k_tile_deposit<3, true> : k_tile_deposit<3, false>;
@@ -568,9 +569,7 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
     j.nw = c->P.nw_s;
     const dim3 block(TILE_ACC + 3, TILE_ACC + 3);
-    dim3 grid = tile_grid(c);
-    grid.z = 2;  // jy_next / jz_next
-    QPIC_LAUNCH(k_tile_bin_deposit<1>, grid, block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
+    QPIC_LAUNCH(k_tile_bin_deposit<1>, tile_grid(c), block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
     return check_launch(c, "k_tile_deposit_jy_jz");
 }
 
@@ -1180,7 +1179,7 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD((k_tile_deposit<1, false>));
         QPIC_PRELOAD((k_tile_deposit<2, false>));
         QPIC_PRELOAD((k_tile_deposit<3, false>));
-        QPIC_PRELOAD((k_tile_deposit<2, true>));
+        QPIC_PRELOAD((k_tile_deposit<2, true, true>));
         QPIC_PRELOAD(k_tile_bin_deposit<0>);
         QPIC_PRELOAD(k_tile_bin_deposit<1>);
         QPIC_PRELOAD(k_particles_predict<true>);

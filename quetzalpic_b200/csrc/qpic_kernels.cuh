@@ -73,8 +73,11 @@ enum KernelId {
 #else
 __device__ __forceinline__ void pdl_grid_sync() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef QPIC_PDL_NO_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
+
 #ifdef QPIC_TIMELINE
 constexpr int TL_CAPACITY = 1 << 16;
 struct TlRecord {
@@ -117,6 +120,15 @@ struct TlSpan {
 #endif
 #endif
 
+// streaming load: the line is marked evict-first in L2.  For slot arrays that are read once per iteration, so that they do not
+// push out the arrays the deposit kernels are about to read.
+__device__ __forceinline__ double ld_stream(const double * p) {
+#if defined(QPIC_NO_STREAM_HINT) || defined(QPIC_EMU)
+    return *p;
+#else
+    return __ldcs(p);
+#endif
+}
 struct Ctl {
     int slice;      // xi-slice being solved (nx-1 ... 0)
     int stop_tag;   // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
@@ -611,13 +623,18 @@ __device__ __forceinline__ int pack_offset(int oy, int oz, double fy, double fz,
     return (oy + 2) | ((oz + 2) << 3) | ((fy >= 0.5) ? 64 : 0) | ((fz >= 0.5) ? 128 : 0) | ((kc & 3) << 8);
 }
 
+// WITH_RHO_CHI = false: inside the B iterations only jx feeds a solve; rho and susceptibility are deposited once per slice by
+// a k_tile_deposit<2, true, true> that forms the same two values from gamma, px, n (see there)
+template <bool WITH_RHO_CHI>
 __device__ __forceinline__ void store_currents(const Particles & P, int s, double nw, double gamma, double px) {
     const double vx = px / gamma;
     const double w = 1 - vx;
     P.vjx[s] = nw * vx / w;
-    const double r = nw / w;
-    P.vrho[s] = r;
-    P.vchi[s] = -r / gamma;  // == -nw / (1 - vx) / gamma bit for bit (negation is exact)
+    if (WITH_RHO_CHI) {
+        const double r = nw / w;
+        P.vrho[s] = r;
+        P.vchi[s] = -r / gamma;  // == -nw / (1 - vx) / gamma bit for bit (negation is exact)
+    }
 }
 
 // fmod(y, l) then +l if negative (src/System_3d.cpp:668-684), without the fmod call in the common cases: for
@@ -676,7 +693,7 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     }
     P.gam[s] = gamma;
     P.pxs[s] = px;
-    store_currents(P, s, nw, gamma, px);
+    store_currents<true>(P, s, nw, gamma, px);
     if (want_invariants) {
         P.q[s] = q;
         P.ap[s] = a_particle;
@@ -712,11 +729,11 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double fy = P.fy_b[s], fz = P.fz_b[s];
     // issue the independent streaming loads before the dependent field gathers
-    const double q = P.q[s], gamma = P.gam[s];
-    const double py = P.py_s[s], pz = P.pz_s[s];
-    const double t1y = P.t1y[s], t1z = P.t1z[s], dpy = P.dpy[s], dpz = P.dpz[s];
-    const double y0 = P.y_s[s], z0 = P.z_s[s];
-    const double a_particle = P.ap[s], nw = P.nw_s[s];
+    const double q = ld_stream(P.q + s), gamma = P.gam[s];
+    const double py = ld_stream(P.py_s + s), pz = ld_stream(P.pz_s + s);
+    const double t1y = ld_stream(P.t1y + s), t1z = ld_stream(P.t1z + s), dpy = ld_stream(P.dpy + s), dpz = ld_stream(P.dpz + s);
+    const double y0 = ld_stream(P.y_s + s), z0 = ld_stream(P.z_s + s);
+    const double a_particle = ld_stream(P.ap + s), nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -740,7 +757,7 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
         const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) / q;
         P.gam[s] = gamma_c;
         P.pxs[s] = px_c;
-        store_currents(P, s, nw, gamma_c, px_c);
+        store_currents<!FAST>(P, s, nw, gamma_c, px_c);  // the general path's node-centric deposit reads vrho / vchi
     }
     const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn / q, g.ly);
     const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn / q, g.lz);
@@ -987,7 +1004,9 @@ __device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g
     }
 }
 
-template <int NOUT, bool FINAL_PASS>
+// RHO_CHI (NOUT = 2): the outputs are rho and susceptibility(i) and the deposited values n / (1 - px/gamma), -n / (1 - px/gamma) / gamma
+// (src/System_3d.cpp:520-527, same expressions as store_currents) are formed here from the corrector's gamma, px.
+template <int NOUT, bool FINAL_PASS, bool RHO_CHI = false>
 __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     QPIC_KERNEL_BEGIN(KID_COUNT + (job.o[0].bg_mode == 2 ? 2 : 0) + (FINAL_PASS ? 8 : 0));
     // (the control block is tested after the particle loop: see k_particles_predict)
@@ -1009,8 +1028,16 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
             const int s = sb + u < s1 ? sb + u : s0;
             fy[u] = P.fy_b[s];
             fz[u] = P.fz_b[s];
+            if (RHO_CHI) {
+                const double gamma = P.gam[s];
+                const double vx = P.pxs[s] / gamma;
+                const double r = P.nw_s[s] / (1 - vx);
+                v[0][u] = r;
+                v[NOUT - 1][u] = -r / gamma;
+            } else {
 #pragma unroll
-            for (int a = 0; a < NOUT; a++) v[a][u] = job.o[a].val[s];
+                for (int a = 0; a < NOUT; a++) v[a][u] = job.o[a].val[s];
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -1051,32 +1078,30 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
 // A, <-> target cell (j0 - 2 + sy, k0 - 2 + sz) for 1 <= sy, sz <= TILE_ACC in phase B (j0, k0: first node of the patch).
 template <int MODE>
 inline size_t tile_bin_smem_bytes() {
-    return (size_t)TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int));
+    constexpr int NOUT = MODE == 0 ? 1 : 2;
+    return (size_t)NOUT * TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int));
 }
 
 template <int MODE>
 __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
     k_tile_bin_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 1 + 4 * MODE);
-    // MODE 1: jy_next and jz_next are deposited by separate blocks (blockIdx.z): twice the blocks with half the work and
-    // half the shared memory each fill the SMs better than one block doing both.  (The control block is tested before the
-    // final stores only: see k_particles_predict.)
-    constexpr int NOUT = 1;
-    const int out_a = MODE == 1 ? (int)blockIdx.z : 0;
-    QPIC_DYN_SMEM(double, acc);                                            // [4][TILE_CELLS]
-    int * cnt = reinterpret_cast<int *>(acc + NOUT * 4 * TILE_CELLS);      // [TILE_CELLS]
-    int * lst = cnt + NOUT * TILE_CELLS;                                   // [BIN_K][TILE_CELLS]
+    // (The control block is tested before the final stores only: see k_particles_predict.  Splitting the two outputs of
+    // MODE 1 over separate blocks was measured slower: 36.9 vs 34.8 us.)
+    constexpr int NOUT = MODE == 0 ? 1 : 2;
+    QPIC_DYN_SMEM(double, acc);                                            // [NOUT][4][TILE_CELLS]
+    int * cnt = reinterpret_cast<int *>(acc + NOUT * 4 * TILE_CELLS);      // [NOUT][TILE_CELLS]
+    int * lst = cnt + NOUT * TILE_CELLS;                                   // [NOUT][BIN_K][TILE_CELLS]
     const int sy = threadIdx.y, sz = threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
     const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
     const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
-    // staggering of this block's output in y / z
-    const bool sty = MODE == 1 && out_a == 0, stz = MODE == 1 && out_a == 1;
-    auto stag_y = [sty](int) { return sty; };
-    auto stag_z = [stz](int) { return stz; };
+    // staggering of output a in y / z
+    auto stag_y = [](int a) { return MODE == 1 && a == 0; };
+    auto stag_z = [](int a) { return MODE == 1 && a == 1; };
 
     for (int i = tid; i < NOUT * TILE_CELLS; i += nthreads) cnt[i] = 0;
-    const double ion = tile_prefetch_ion<1>(g, job, sy - 1, sz - 1, ju, ku);
+    const double ion = tile_prefetch_ion<NOUT>(g, job, sy - 1, sz - 1, ju, ku);
     __syncthreads();
 
     // ---- phase A: bin the particles of this source cell
@@ -1116,7 +1141,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
 #pragma unroll
         for (int a = 0; a < NOUT; a++) {
             double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
-            const double * __restrict__ val = out_a == 0 ? job.o[0].val : job.o[1].val;
+            const double * __restrict__ val = job.o[a].val;
             auto visit = [&](int s, int hy, int hz) {
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
                 double v;
@@ -1130,7 +1155,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                     const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
                     v = job.nw[s] * val[s] / w;
                 } else {
-                    v = job.o[0].sign * val[s];
+                    v = job.o[a].sign * val[s];
                 }
                 const double wy = stag_y(a) ? (hy ? fy - 0.5 : fy + 0.5) : fy;
                 const double wz = stag_z(a) ? (hz ? fz - 0.5 : fz + 0.5) : fz;
@@ -1182,16 +1207,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
     }
     __syncthreads();
     if (cancelled(ctl)) return;
-    if (is_target) {
-        if (MODE == 1 && out_a == 1) {
-            // the second output of the job is this block's only one
-            TileJob mine = job;
-            mine.o[0] = job.o[1];
-            tile_store_nodes<1>(ctl, g, mine, acc, ty, tz, ju, ku, 0.0);
-        } else {
-            tile_store_nodes<1>(ctl, g, job, acc, ty, tz, ju, ku, ion);
-        }
-    }
+    if (is_target) tile_store_nodes<NOUT>(ctl, g, job, acc, ty, tz, ju, ku, ion);
 }
 
 }  // namespace qpic

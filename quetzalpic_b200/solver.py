@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_PKG_DIR, "libqpic_b200.so")
+# QPIC_B200_LIBRARY: development override (A/B builds of the same sources)
+LIBRARY_PATH = os.environ.get("QPIC_B200_LIBRARY") or os.path.join(_PKG_DIR, "libqpic_b200.so")
 
 FIELDS_2D = ["psi", "psi_prev", "psi_middle", "rho", "jx", "jy", "jz", "jy_next", "jz_next", "rho_ion", "by_cur", "bz_cur"]
 FIELDS_3D = ["aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "by", "bz"]

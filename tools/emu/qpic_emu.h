@@ -183,6 +183,10 @@ template <class T>
 static inline T __ldg(const T * p) {
     return *p;
 }
+template <class T>
+static inline T __ldcs(const T * p) {
+    return *p;
+}
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
