@@ -335,13 +335,16 @@ def run_b200_arm(args, w):
     roofline_slice = {"bound": "hbm", "achieved": slice_gbs, "peak": peak, "unit": "GB/s", "frac": slice_gbs / peak,
                       "algorithmic_bytes_per_slice": slice_bytes, "formula": "8*[(29+44M)N+(18+21M)P] (SURVEY.md 8d)"}
 
-    # ---- end to end through the C ABI with HOST buffers: a fresh sweep; every step uploads that step's a_sqr slices from
-    # pinned host memory and downloads the six field slabs the reference keeps on the host (ex ey ez by bz susceptibility)
-    out_fields = ["ex", "ey", "ez", "by", "bz", "susceptibility"]
-    # the laser envelope as the caller holds it: a host array (System_3d::a_sqr), built before the timed region like
-    # init_a_sqr in the reference; only the K*S slices this run sweeps are materialised
+    solver.close()
+
+    # ---- end to end through the C ABI with HOST buffers.  The laser envelope is a host array as the caller holds it
+    # (System_3d::a_sqr, built before the timed region like init_a_sqr in the reference; only the K*S slices this run sweeps are
+    # materialised).  Two output contracts of the reference's Output_writer:
+    #   "xy"  [output] fields_xy = true -- what BASELINE config #2 names: the (nx, ny) cuts of all datasets; the device evaluates the
+    #         cuts (qpic_download_xy_cut), only they cross PCIe;
+    #   "3d"  the six (nx, ny, nz) field arrays the reference keeps in host memory (ex, ey, ez, by, bz, susceptibility) come down
+    #         every step: 805 MB per step, PCIe-bound on this box.
     a_host, a_ptr = lib.pinned_array((K * S, ny, nz))
-    outs = [[lib.pinned_array((S, ny, nz)) for _ in out_fields] for _ in range(2)]
     xs = np.arange(nx) * (w["lx"] / nx)
     yy = np.arange(ny) * (w["ly"] / ny)
     zz = np.arange(nz) * (w["lz"] / nz)
@@ -355,38 +358,62 @@ def run_b200_arm(args, w):
         first = nx - (k + 1) * S
         return first, a_host[first - lo:first - lo + S]
 
-    barrier()
-    t0 = time.perf_counter()
-    solver.init_wake_particles(y, z, n)
-    solver.begin()
-    checksum = 0.0
-    solver.upload_a_sqr_slices(*a_block(0))
-    for k in range(K):
-        first = nx - (k + 1) * S
-        solver.step(S, wait=False)                      # block k computes ...
-        if k + 1 < K:
-            solver.upload_a_sqr_slices(*a_block(k + 1))  # ... while block k+1 of the envelope goes up ...
-        if k >= 1:
-            solver.wait_transfers()                     # ... and block k-1's results finish landing in host memory
-            checksum += float(outs[(k - 1) % 2][2][0][0, ny // 2, nz // 2])
-        for (dst, _), f in zip(outs[k % 2], out_fields):
-            solver.download_slices3d(f, first, dst)     # queued behind block k on the copy stream
-    solver.synchronize()
-    checksum += float(outs[(K - 1) % 2][2][0][0, ny // 2, nz // 2])
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    e2e_value = pushes_total / e2e_s
-    h2d = S * N * 8 + (3 * P * 8) // K
-    d2h = len(out_fields) * S * N * 8
+    def run_e2e(mode):
+        if mode == "xy":
+            fields = [("aSqr", False), ("susceptibility", False), ("ex", False), ("ey", False), ("ez", False), ("by", False), ("bz", False),
+                      ("psi", True), ("rho", True), ("jx", True), ("jy", True), ("jz", True)]
+            shape = (S, ny)
+        else:
+            fields = [(f, False) for f in ["ex", "ey", "ez", "by", "bz", "susceptibility"]]
+            shape = (S, ny, nz)
+        # the stop flag is polled every 8 steps here, so qpic_step only queues work and the copies of step k-1 / k+1 overlap step k
+        sv = WakefieldSolver(nx, ny, nz, w["lx"], w["ly"], w["lz"], M, device=local, stop_check_interval=8 * S, keep_xy_cuts=(mode == "xy"))
+        outs = [[lib.pinned_array(shape) for _ in fields] for _ in range(2)]
+        probe = (0, ny // 2) if mode == "xy" else (0, ny // 2, nz // 2)
+        barrier()
+        t0 = time.perf_counter()
+        sv.init_wake_particles(y, z, n)
+        sv.begin()
+        checksum = 0.0
+        sv.upload_a_sqr_slices(*a_block(0))
+        for k in range(K):
+            first = nx - (k + 1) * S
+            sv.step(S, wait=False)                           # block k computes ...
+            if k + 1 < K:
+                sv.upload_a_sqr_slices(*a_block(k + 1))      # ... while block k+1 of the envelope goes up ...
+            if k >= 1:
+                sv.wait_transfers()                          # ... and block k-1's results finish landing in host memory
+                checksum += float(outs[(k - 1) % 2][2][0][probe])
+            for (dst, _), (f, per_slice) in zip(outs[k % 2], fields):
+                if mode == "xy":
+                    sv.download_xy_cut(f, first, dst, per_slice=per_slice)   # queued behind block k on the copy stream
+                else:
+                    sv.download_slices3d(f, first, dst)
+        sv.synchronize()
+        checksum += float(outs[(K - 1) % 2][2][0][probe])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        te = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        seconds = float(te.item())
+        stopped_e2e = sv.stopped_at
+        for bufs in outs:
+            for _, ptr in bufs:
+                lib.free_pinned(ptr)
+        sv.close()
+        d2h = len(fields) * int(np.prod(shape)) * 8
+        return {"value": pushes_total / seconds, "unit": "pushes/s", "h2d_bytes_per_step": S * N * 8 + (3 * P * 8) // K, "d2h_bytes_per_step": d2h,
+                "ms_per_slice": 1e3 * seconds / (K * S), "checksum": checksum, "stopped_at": stopped_e2e}
+
+    e2e_xy = run_e2e("xy")
+    e2e_3d = run_e2e("3d")
     lib.free_pinned(a_ptr)
-    for bufs in outs:
-        for _, ptr in bufs:
-            lib.free_pinned(ptr)
-    solver.close()
+    e2e_xy["what"] = ("output contract of the named config ([output] fields_xy = true): qpic_init_wake_particles + qpic_begin + per step: a_sqr slab H2D "
+                      "(pinned), qpic_step, the (nx, ny) Fields_xy cuts of 12 datasets D2H (pinned, cuts evaluated on the device); transfers on the "
+                      "library's copy stream, double buffered, overlapping the next step's slices")
+    e2e_3d["what"] = ("same, but the six (nx, ny, nz) field arrays the reference keeps in host memory (ex, ey, ez, by, bz, susceptibility) come down "
+                      "every step instead of the cuts: PCIe-bound on this box")
 
     if rank == 0:
         cpu = cpu_baseline(w) if (world == 1 and not args.no_cpu_baseline) else None
@@ -402,10 +429,7 @@ def run_b200_arm(args, w):
                        "stopped_at": stopped},
             "roofline": roofline, "roofline_slice": roofline_slice, "kernels": kernels[:8],
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "pushes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_slice": 1e3 * e2e_s / (K * S), "checksum": checksum,
-                    "what": "qpic_init_wake_particles + qpic_begin + per step: a_sqr slab H2D (pinned), qpic_step, 6 field slabs D2H (pinned); "
-                            "transfers run on the library's copy stream, double buffered, overlapping the next step's slices"},
+            "e2e": e2e_xy, "e2e_fields_3d": e2e_3d,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -422,6 +446,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--slices-per-step", type=int, default=SLICES_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="wake512", choices=["wake512", "slab4096"],
+                    help="wake512 (default): BASELINE config #2 per GPU (N > 1: independent scan members); slab4096: config #4, ONE 4096^2 16 ppc "
+                         "grid slab-decomposed over the N GPUs (strong scaling; tools/dist_run.py)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -429,6 +456,11 @@ def main():
     # keep (steps + warmup) * slices inside the 2048-slice box whatever K/W the driver asks for
     while (args.steps + args.warmup) * args.slices_per_step > w["nx"] - 1 and args.slices_per_step > 1:
         args.slices_per_step //= 2
+    if args.workload == "slab4096" and args.impl == "b200":
+        # config #4: one process per GPU, exchange regions mapped over CUDA IPC; a step = one xi-slice of the 268 M particle grid
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import dist_run
+        sys.exit(dist_run.bench(argparse.Namespace(n=4096, nx=64, ppc=4, M=5, a0=1.0, slices=max(1, min(args.steps, 48)), warm=max(3, min(args.warmup, 8)))))
     if args.impl == "reference":
         run_reference_arm(args, w)
     else:

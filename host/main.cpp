@@ -6,6 +6,7 @@
 // (src/System_3d.cpp:91-152), the per-iteration messages of System_3d::run (:199-236) and the output datasets
 // (src/Output_writer.cpp; see output_npy.h for the file format).  solve_wakefield itself runs on the device.
 // Beam drivers ([bunch]) need the bunch deposit / push path, which is a "next" row: such inputs are refused.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -122,7 +123,12 @@ int main(int argc, char const * argv[]) {
     p.lz = params.lz;
     p.magnetic_field_iterations = params.magnetic_field_iterations;
     const bool any_output = params.output.output3d || params.output.output_xy;
-    p.keep_slices_3d = any_output ? 1 : 0;
+    // Fields_xy alone needs no (nx,ny,nz) per-slice copies: the device collects the cuts slice by slice and evaluates the
+    // cuts of the resident arrays itself (qpic_download_xy_cut); Fields needs the full per-slice arrays
+    const bool xy_only = params.output.output_xy && !params.output.output3d;
+    p.keep_slices_3d = (any_output && !xy_only) ? 1 : 0;
+    p.keep_xy_cuts = xy_only ? 1 : 0;
+    p.xy_z0 = params.output.z0;
     qpic_ctx * ctx = nullptr;
     if (qpic_create(&p, &ctx) != QPIC_OK) {
         std::cerr << "qpic_create failed: " << qpic_last_error(nullptr) << std::endl;
@@ -154,7 +160,7 @@ int main(int argc, char const * argv[]) {
             out << std::endl;
             check(qpic_finish(ctx), ctx);
             if (any_output) {
-                std::vector<double> buf((size_t)nx * ny * nz);
+                std::vector<double> buf(xy_only ? 1 : (size_t)nx * ny * nz);
                 struct Entry {
                     qpic_field3d id;
                     Field_meta meta;
@@ -177,9 +183,23 @@ int main(int argc, char const * argv[]) {
                     {QPIC_F3_BY, {"by", 0, 0, 0.5 * dz}},
                     {QPIC_F3_BZ, {"bz", 0, 0.5 * dy, 0}},
                 };
-                for (const Entry & e : entries) {
-                    check(qpic_download_field3d(ctx, e.id, buf.data()), ctx);
-                    writer.write_array(e.meta, buf.data());
+                if (xy_only) {
+                    std::vector<double> cut((size_t)nx * ny);
+                    for (const Entry & e : entries) {
+                        const bool bunch = (e.id == QPIC_F3_RHO_BUNCH || e.id == QPIC_F3_JX_BUNCH);  // no bunch in this driver: zeros (not resident)
+                        if (bunch) {
+                            std::fill(cut.begin(), cut.end(), 0.0);
+                        } else {
+                            check(qpic_download_xy_cut(ctx, e.id, 0, nx, cut.data()), ctx);
+                            check(qpic_wait_transfers(ctx), ctx);
+                        }
+                        writer.write_xy(e.meta, cut.data());
+                    }
+                } else {
+                    for (const Entry & e : entries) {
+                        check(qpic_download_field3d(ctx, e.id, buf.data()), ctx);
+                        writer.write_array(e.meta, buf.data());
+                    }
                 }
             }
             out << "Depositing fields to particles..." << std::endl;

@@ -100,6 +100,12 @@ public:
         }
     }
 
+    // a cut that the device already evaluated (qpic_download_xy_cut): Fields_xy only
+    void write_xy(const Field_meta & m, const double * cut) {
+        write_npy(dirxy + "/" + m.name + ".npy", cut, {(size_t)nx, (size_t)ny});
+        write_attrs(dirxy + "/" + m.name + ".attrs", {dx, dy}, {m.ox, m.oy}, true, z0);
+    }
+
 private:
     bool output3d, output_xy;
     double z0;

@@ -57,6 +57,11 @@ typedef struct {
      * (qpic_dist_*) before anything else is called. */
     int dist_rank, dist_world;
     size_t particle_capacity;      /* distributed: room for the particles this rank may hold after migration (0: 1.25 x + 64K) */
+    /* Fields_xy output (Output_writer with output_xy, src/Output_writer.cpp:147-187): cuts at z = xy_z0 (< 0: lz / 2, the
+     * reference default, src/Config_reader.cpp:218-234).  keep_xy_cuts != 0: the (nx, ny) cuts of the per-slice datasets psi, rho,
+     * jx, jy, jz are collected on the device slice by slice, so that Fields_xy needs no (nx, ny, nz) per-slice copies. */
+    int keep_xy_cuts;
+    double xy_z0;
 } qpic_params;
 
 /* fills *p with the reference defaults (psi_threshold 1e-4, D 10, threshold_B 100, device 0, graph on) */
@@ -146,6 +151,12 @@ int qpic_profile_slices(qpic_ctx * ctx, int nslices, char * report, size_t repor
 int qpic_timeline_reset(qpic_ctx * ctx);
 long qpic_timeline_read(qpic_ctx * ctx, long long * records, long cap);
 const char * qpic_timeline_kernel_name(int kernel_id);
+
+/* (count, ny) cut at z = xy_z0 of slices first_slice .. first_slice + count - 1 of a dataset: calculate_xy_slice /
+ * calculate_y_slice (src/array_utils.cpp:7-45) evaluated on the device, honouring the array's z-origin (by, ez, jz: dz / 2).
+ * Asynchronous like qpic_download_slices3d (copy stream; qpic_wait_transfers before reading dst).  psi, rho, jx, jy, jz need
+ * keep_xy_cuts or keep_slices_3d. */
+int qpic_download_xy_cut(qpic_ctx * ctx, qpic_field3d f, int first_slice, int count, double * dst);
 
 /* ---- slab-decomposed multi-GPU sweep (qpic_params::dist_world > 1).  Each rank allocates an "exchange region" of
  * identical layout; the ranks map each other's regions and from then on exchange transform transposes, halo rows and

@@ -120,6 +120,8 @@ struct qpic_ctx {
         int live0 = 0;                             // particles handed to qpic_init_wake_particles
         std::vector<void *> opened;                // cudaIpcOpenMemHandle mappings
     } dist;
+    double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
+    double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
     double * partials = nullptr;  // border-sum partials of the fused potential fix-up, [world][4] (inside the region when distributed)
 
     // per-kernel profiling (qpic_profile_slices): an event after every launch of an eager slice
@@ -646,7 +648,27 @@ SliceOut slice_out(qpic_ctx * c) {
     return o;
 }
 
+// z0 of the Fields_xy cuts and the two planes / weight it falls between on a grid whose z-origin is oz
+double xy_z0(const qpic_ctx * c) { return c->prm.xy_z0 < 0 ? 0.5 * c->prm.lz : c->prm.xy_z0; }
+
+XyCut xy_cut(const qpic_ctx * c, double oz) {
+    XyCut x;
+    const double t = (xy_z0(c) - oz) / c->g.dz;  // src/array_utils.cpp:14-15
+    int k0 = (int)std::floor(t);
+    x.frac = t - k0;
+    k0 = ((k0 % c->g.nz) + c->g.nz) % c->g.nz;
+    x.k0 = k0;
+    x.k1 = k0 + 1 >= c->g.nz ? 0 : k0 + 1;
+    return x;
+}
+
 int enqueue_end_of_slice(qpic_ctx * c, int b_is_zero, int roll, int ignore_stop) {
+    if (c->xy[0]) {
+        XyLines o = {c->xy[0], c->xy[1], c->xy[2], c->xy[3], c->xy[4]};
+        QPIC_LAUNCH_FLAT(k_xy_lines, blocks_for(row_count(c), 128), 128, 0, c->stream, c->ctl, c->g, o, xy_cut(c, 0.0), xy_cut(c, 0.5 * c->g.dz), c->f2[QPIC_F2_PSI],
+                         c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], ignore_stop, row_first(c), row_count(c));
+        QPIC_TRY(check_launch(c, "k_xy_lines"));
+    }
     QPIC_LAUNCH_FLAT(k_end_of_slice, blocks_for((size_t)row_count(c) * c->g.nz, 256), 256, 0, c->stream, c->ctl, c->g, slice_out(c), c->f2[QPIC_F2_PSI],
                      c->f2[QPIC_F2_PSI_PREV], c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY],
                      c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT], b_is_zero, roll, ignore_stop, row_first(c), row_count(c));
@@ -947,6 +969,8 @@ void qpic_default_params(qpic_params * p) {
     p->dist_rank = 0;
     p->dist_world = 1;
     p->particle_capacity = 0;
+    p->keep_xy_cuts = 0;
+    p->xy_z0 = -1.0;
 }
 
 const char * qpic_last_error(const qpic_ctx * ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -1142,6 +1166,9 @@ static int create_impl(qpic_ctx * c) {
         const bool slices = (f >= QPIC_F3_PSI);
         if (bunch || (slices && !p.keep_slices_3d)) continue;
         QPIC_TRY(dev_alloc(c, &c->f3[f], n3));
+    }
+    if (p.keep_xy_cuts) {
+        for (int f = 0; f < 5; f++) QPIC_TRY(dev_alloc(c, &c->xy[f], (size_t)g.nx * g.ny));
     }
     QPIC_TRY(dev_alloc(c, &c->fft_in, n2));
     QPIC_TRY(dev_alloc(c, &c->fft_in2, n2));
@@ -1620,6 +1647,34 @@ int qpic_download_slices3d(qpic_ctx * c, qpic_field3d f, int first_slice, int co
     QPIC_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
     QPIC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
     QPIC_CUDA(c, cudaMemcpyAsync(dst, c->f3[f] + n2 * first_slice, sizeof(double) * n2 * count, cudaMemcpyDeviceToHost, c->copy_stream));
+    return QPIC_OK;
+}
+
+int qpic_download_xy_cut(qpic_ctx * c, qpic_field3d f, int first_slice, int count, double * dst) {
+    if (!c || f < 0 || f >= QPIC_F3_COUNT || !dst) return fail(c, QPIC_ERR_INVALID, "bad field id or NULL dst");
+    if (first_slice < 0 || count < 0 || first_slice + count > c->g.nx) return fail(c, QPIC_ERR_INVALID, "slice range out of bounds");
+    if (count == 0) return QPIC_OK;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t ny = (size_t)c->g.ny;
+    // after the slices queued so far, on the copy stream
+    QPIC_CUDA(c, cudaEventRecord(c->ev_copy, c->stream));
+    QPIC_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+    const double * src = nullptr;
+    if (f >= QPIC_F3_PSI && c->xy[0]) {
+        src = c->xy[f - QPIC_F3_PSI] + ny * first_slice;
+    } else {
+        if (!c->f3[f]) return fail(c, QPIC_ERR_STATE, "this array is not resident (see keep_xy_cuts / keep_slices_3d / qpic_upload_bunch_sources)");
+        if (!c->xy_scratch) QPIC_TRY(dev_alloc(c, &c->xy_scratch, (size_t)c->g.nx * ny, false));
+        const bool half = (f == QPIC_F3_BY || f == QPIC_F3_EZ || f == QPIC_F3_JZ);  // z-origin dz / 2 (src/System_3d.cpp:171-193)
+        int blocks = blocks_for((size_t)count * ny, 256);
+        if (blocks > 1184) blocks = 1184;
+        QPIC_LAUNCH_FLAT(k_xy_cut, blocks, 256, 0, c->copy_stream, c->g, c->f3[f] + (size_t)c->g.n2 * first_slice, count, xy_cut(c, half ? 0.5 * c->g.dz : 0.0),
+                         c->xy_scratch + ny * first_slice);
+        c->launch_counter++;
+        QPIC_CUDA(c, cudaGetLastError());
+        src = c->xy_scratch + ny * first_slice;
+    }
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * ny * count, cudaMemcpyDeviceToHost, c->copy_stream));
     return QPIC_OK;
 }
 

@@ -64,9 +64,11 @@ enum KernelId {
     KID_k_halo_fill,
     KID_k_migrate_publish,
     KID_k_migrate_unpack,
+    KID_k_xy_cut,
+    KID_k_xy_lines,
     KID_COUNT
 };
-#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack" }
+#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack", "k_xy_cut", "k_xy_lines" }
 
 #ifdef QPIC_EMU
 #define QPIC_KERNEL_BEGIN(id) ((void)0)
@@ -907,6 +909,48 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
         jy[t] = jy_next[t];
         jz[t] = jz_next[t];
     }
+}
+
+// ---- Fields_xy output (Output_writer with output_xy, src/Output_writer.cpp:176-187): cuts at z = z0, linear in z between the
+// two neighbouring planes of the array's own z-origin (calculate_xy_slice / calculate_y_slice, src/array_utils.cpp:7-45).
+// k1 = k0 + 1 wraps at the box edge (the reference would read past the row there).
+struct XyCut {
+    int k0, k1;
+    double frac;
+};
+
+// cut of `count` slices of a 3-D array starting at a3 -> dst[count][ny]
+__global__ void k_xy_cut(Geom g, const double * __restrict__ a3, int count, XyCut c, double * __restrict__ dst) {
+    QPIC_KERNEL_BEGIN(KID_k_xy_cut);
+    const size_t total = (size_t)count * g.ny;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const double * row = a3 + t * g.nz;
+        dst[t] = (1 - c.frac) * row[c.k0] + c.frac * row[c.k1];
+    }
+}
+
+// the per-slice datasets psi, rho, jx, jy, jz (write_slice, src/System_3d.cpp:663-665): line i of their (nx, ny) cuts, taken
+// BEFORE the jy / jz roll like the slices themselves (:610 vs :612-618).  node: z-origin 0; half: z-origin dz/2 (jz)
+struct XyLines {
+    double *psi, *rho, *jx, *jy, *jz;  // (nx, ny) each
+};
+
+__global__ void k_xy_lines(const Ctl * ctl, Geom g, XyLines o, XyCut node, XyCut half, const double * __restrict__ psi, const double * __restrict__ rho,
+                           const double * __restrict__ jx, const double * __restrict__ jy, const double * __restrict__ jz, int ignore_stop, int row0,
+                           int nrows) {
+    QPIC_KERNEL_BEGIN(KID_k_xy_lines);
+    if (cancelled(ctl) && !ignore_stop) return;
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= nrows) return;
+    const int j = row0 + jl;
+    const int i = ignore_stop ? 0 : ctl->slice;
+    const size_t at = (size_t)i * g.ny + j;
+    const size_t r = (size_t)j * g.nz;
+    o.psi[at] = (1 - node.frac) * psi[r + node.k0] + node.frac * psi[r + node.k1];
+    o.rho[at] = (1 - node.frac) * rho[r + node.k0] + node.frac * rho[r + node.k1];
+    o.jx[at] = (1 - node.frac) * jx[r + node.k0] + node.frac * jx[r + node.k1];
+    o.jy[at] = (1 - node.frac) * jy[r + node.k0] + node.frac * jy[r + node.k1];
+    o.jz[at] = (1 - half.frac) * jz[r + half.k0] + half.frac * jz[r + half.k1];
 }
 
 __global__ void k_next_slice(Ctl * ctl) {

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "qpic_set_current_slice", "qpic_solve_poisson_host", "qpic_solve_helmholtz_pair_host", "qpic_last_step_stats",
     "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
     "qpic_fast_path_aborts", "qpic_wait_transfers", "qpic_timeline_reset", "qpic_timeline_read", "qpic_timeline_kernel_name",
-    "qpic_dist_region_bytes", "qpic_dist_region", "qpic_dist_ipc_handle", "qpic_dist_attach_ipc", "qpic_dist_attach_pointers", "qpic_dist_row_range",
+    "qpic_dist_region_bytes", "qpic_dist_region", "qpic_dist_ipc_handle", "qpic_dist_attach_ipc", "qpic_dist_attach_pointers", "qpic_dist_row_range", "qpic_download_xy_cut",
 ]
 
 
@@ -59,6 +59,7 @@ class QpicParams(ctypes.Structure):
         ("force_general_deposit", ctypes.c_int),
         ("dist_rank", ctypes.c_int), ("dist_world", ctypes.c_int),
         ("particle_capacity", ctypes.c_size_t),
+        ("keep_xy_cuts", ctypes.c_int), ("xy_z0", ctypes.c_double),
     ]
 
 
@@ -112,6 +113,7 @@ class QpicLibrary:
         L.qpic_wait_transfers.argtypes = [vp]
         L.qpic_fast_path_aborts.argtypes = [vp]
         L.qpic_fast_path_aborts.restype = ctypes.c_long
+        L.qpic_download_xy_cut.argtypes = [vp, ci, ci, ci, vp]
         L.qpic_dist_region_bytes.argtypes = [vp]
         L.qpic_dist_region_bytes.restype = ctypes.c_size_t
         L.qpic_dist_region.argtypes = [vp]
@@ -190,7 +192,7 @@ class WakefieldSolver:
 
     def __init__(self, nx, ny, nz, lx, ly, lz, magnetic_field_iterations, psi_threshold=1e-4, magnetic_field_D=10.0,
                  threshold_B=100.0, device=0, keep_slices_3d=False, use_graph=True, stop_check_interval=64, force_general_deposit=False,
-                 library=None, dist_rank=0, dist_world=1, particle_capacity=0):
+                 library=None, dist_rank=0, dist_world=1, particle_capacity=0, keep_xy_cuts=False, xy_z0=None):
         self.lib = library if library is not None else load_library()
         L = self.lib.L
         p = QpicParams()
@@ -206,6 +208,8 @@ class WakefieldSolver:
         p.force_general_deposit = int(bool(force_general_deposit))
         p.dist_rank, p.dist_world, p.particle_capacity = int(dist_rank), int(dist_world), int(particle_capacity)
         self.dist_rank, self.dist_world = int(dist_rank), int(dist_world)
+        p.keep_xy_cuts = int(bool(keep_xy_cuts))
+        p.xy_z0 = -1.0 if xy_z0 is None else float(xy_z0)
         self.params = p
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.keep_slices_3d = bool(keep_slices_3d)
@@ -334,6 +338,19 @@ class WakefieldSolver:
         assert out_block.flags["C_CONTIGUOUS"] and out_block.dtype == np.float64
         self._check(self.lib.L.qpic_download_slices3d(self.ctx, self._field3d_index(name, per_slice), int(first_slice),
                                                       int(out_block.shape[0]), out_block.ctypes.data))
+
+    def download_xy_cut(self, name, first_slice, out_block, per_slice=False):
+        """asynchronous; out_block: (count, ny) contiguous float64: the Fields_xy cut (z = xy_z0) of `count` slices"""
+        assert out_block.flags["C_CONTIGUOUS"] and out_block.dtype == np.float64 and out_block.shape[1] == self.ny
+        self._check(self.lib.L.qpic_download_xy_cut(self.ctx, self._field3d_index(name, per_slice), int(first_slice), int(out_block.shape[0]),
+                                                    out_block.ctypes.data))
+
+    def xy_cut(self, name, per_slice=False):
+        """(nx, ny) Fields_xy dataset of a field (reference src/array_utils.cpp:7-24)"""
+        out = np.empty((self.nx, self.ny))
+        self.download_xy_cut(name, 0, out, per_slice=per_slice)
+        self.wait_transfers()
+        return out
 
     def wait_transfers(self):
         self._check(self.lib.L.qpic_wait_transfers(self.ctx))

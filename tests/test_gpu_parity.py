@@ -233,3 +233,38 @@ def test_charge_conservation_full_size():
         assert s.step(10) is True
         s.finish()
         assert s.stopped_at == -1
+
+
+@pytest.mark.parametrize("z0", [None, 1.37, 6.35])
+def test_xy_cuts_match_interpolation_of_the_full_arrays(z0):
+    """qpic_download_xy_cut == calculate_xy_slice / calculate_y_slice (src/array_utils.cpp:7-45) of the downloaded arrays,
+    for resident 3-D arrays (incl. the dz/2 z-origin of by, ez) and for the per-slice lines collected with keep_xy_cuts."""
+    case = Case.synthetic(n=(6, 16, 32), d=(0.2, 0.2, 0.2), M=2, ppc=(2, 2), a0=1.2)
+    nx, ny, nz = case.n
+    dz = case.l[2] / nz
+    zz = 0.5 * case.l[2] if z0 is None else z0
+    with case.make_solver(keep_slices_3d=True, keep_xy_cuts=True, xy_z0=z0) as s:
+        s.solve_wakefield()
+        for name, per_slice, oz in [("ex", False, 0), ("ez", False, 0.5 * dz), ("by", False, 0.5 * dz), ("bz", False, 0), ("aSqr", False, 0),
+                                    ("susceptibility", False, 0), ("psi", True, 0), ("rho", True, 0), ("jx", True, 0), ("jy", True, 0), ("jz", True, 0.5 * dz)]:
+            a = s.field3d(name, per_slice=per_slice)
+            t = (zz - oz) / dz
+            k0 = int(np.floor(t))
+            f = t - k0
+            ref = (1 - f) * a[:, :, k0 % nz] + f * a[:, :, (k0 + 1) % nz]
+            got = s.xy_cut(name, per_slice=per_slice)
+            assert np.abs(got - ref).max() <= 4e-16 * max(np.abs(ref).max(), 1e-300), name
+    # without keep_xy_cuts the per-slice datasets fall back to the per-slice 3-D copies; without either they are refused
+    with case.make_solver(keep_slices_3d=True, xy_z0=z0) as s:
+        s.solve_wakefield()
+        a = s.field3d("jz", per_slice=True)
+        t = (zz - 0.5 * dz) / dz
+        k0 = int(np.floor(t))
+        f = t - k0
+        ref = (1 - f) * a[:, :, k0 % nz] + f * a[:, :, (k0 + 1) % nz]
+        assert np.abs(s.xy_cut("jz", per_slice=True) - ref).max() <= 4e-16 * max(np.abs(ref).max(), 1e-300)
+    with case.make_solver() as s:
+        s.solve_wakefield()
+        from quetzalpic_b200 import QpicError
+        with pytest.raises(QpicError):
+            s.xy_cut("psi", per_slice=True)

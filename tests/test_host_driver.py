@@ -76,3 +76,24 @@ def test_driver_output_files_match_reference(name, golden_dir, tmp_path):
         assert np.allclose([float(v) for v in attrs["origin"].split()], g[f"f3/{nm}@origin"], rtol=0, atol=1e-15)
         assert np.allclose([float(v) for v in attrs["steps"].split()], g[f"f3/{nm}@steps"], rtol=0, atol=1e-15)
     assert os.path.isdir(os.path.join(tmp_path, "Photons_000.h5.d"))
+
+
+@pytest.mark.gpu
+def test_driver_fields_xy_only_uses_device_side_cuts(golden_dir, tmp_path):
+    """fields_xy without fields_3d: no (nx,ny,nz) per-slice copies, the cuts come from qpic_download_xy_cut
+    (calculate_xy_slice / calculate_y_slice, src/array_utils.cpp:7-45); same datasets as the reference's Fields_xy file."""
+    build_driver()
+    name = "tiny_laser"
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    text = open(os.path.join(golden_dir, "inputs", name + ".toml")).read().replace("fields_3d = true", "fields_3d = false")
+    with open(os.path.join(tmp_path, name + ".toml"), "w") as f:
+        f.write(text)
+    r = subprocess.run([DRIVER, name + ".toml"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert not os.path.isdir(os.path.join(tmp_path, "Fields_000.h5.d"))
+    for nm in NAMES:
+        xy = np.load(os.path.join(tmp_path, "Fields_xy_000.h5.d", nm + ".npy"))
+        ref = g["xy/" + nm]
+        assert xy.shape == ref.shape
+        scale = np.abs(g["f3/" + nm]).max()
+        assert np.abs(xy - ref).max() <= 1e-9 * scale + 1e-300, nm
