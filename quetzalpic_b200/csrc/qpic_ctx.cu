@@ -221,14 +221,41 @@ int make_fft(qpic_ctx * c, int n, DeviceFft * out) {
 
 // nseq sequences of length n: how many per block.  Power-of-two engine: exactly n/8 threads per sequence, in place;
 // generic engine: one block-wide loop, ping-pong buffers.
-int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what) {
+// what a set of kernels that share a launch shape allows per block: threads (register use) and dynamic shared memory (227 KB
+// minus their static shared memory)
+struct KernelLimits {
+    int max_threads = 1024;
+    size_t max_dyn_smem = SMEM_OPTIN_LIMIT;
+};
+
+template <class... K>
+KernelLimits kernel_limits(K... kernels) {
+    KernelLimits lim;
+#ifndef QPIC_EMU
+    const void * list[] = {reinterpret_cast<const void *>(kernels)...};
+    for (const void * k : list) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        if (fa.maxThreadsPerBlock < lim.max_threads) lim.max_threads = fa.maxThreadsPerBlock;
+        const size_t room = SMEM_OPTIN_LIMIT > fa.sharedSizeBytes ? SMEM_OPTIN_LIMIT - fa.sharedSizeBytes : 0;
+        if (room < lim.max_dyn_smem) lim.max_dyn_smem = room;
+    }
+#endif
+    return lim;
+}
+
+int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what, const KernelLimits & lim = KernelLimits()) {
     const int n = P.n;
     if (P.log2n > 0) {
         const int e8 = n / 8;
         // These kernels are latency bound (a few warps per SM at most), so the fastest shape is ONE wave of fat blocks:
-        // as many sequences per block as it takes to cover the batch with <= 148 blocks, within 1024 threads / 227 KB.
+        // as many sequences per block as it takes to cover the batch with <= 148 blocks, within the kernels' thread (register)
+        // and shared-memory limits.
         int spb = (nseq + 147) / 148;
-        while (spb > 1 && (spb * e8 > 1024 || sizeof(double2) * 2 * (size_t)spb * n > SMEM_OPTIN_LIMIT)) spb--;
+        while (spb > 1 && (spb * e8 > lim.max_threads || sizeof(double2) * 2 * (size_t)spb * n > lim.max_dyn_smem)) spb--;
         if (spb < 1) spb = 1;
         while (spb * e8 < 32) spb *= 2;
         L->spb = spb;
@@ -239,8 +266,8 @@ int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaun
         L->threads = pick_threads(n / 4);
         L->smem = sizeof(double2) * 2 * (size_t)n;
     }
-    if (L->threads > 1024) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d needs more than 1024 threads per block", what, n);
-    if (L->smem > SMEM_OPTIN_LIMIT) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d does not fit the shared-memory transform", what, n);
+    if (L->threads > lim.max_threads) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d needs more than %d threads per block", what, n, lim.max_threads);
+    if (L->smem > lim.max_dyn_smem) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d does not fit the shared-memory transform", what, n);
     L->blocks = (nseq + L->spb - 1) / L->spb;
     return QPIC_OK;
 }
@@ -1075,10 +1102,14 @@ static int create_impl(qpic_ctx * c) {
     }
     c->pow2_y = c->fy.plan.log2n > 0;
     c->pow2_z = c->fz.plan.log2n > 0;
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform"));
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform"));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform"));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform"));
+    const KernelLimits lim_real = kernel_limits(k_p2_rows_r2c<false>, k_p2_rows_r2c<true>, k_p2_rows_c2r<false>, k_p2_rows_c2r<true>);
+    const KernelLimits lim_cplx = kernel_limits(k_p2_rows_b_forward<false>, k_p2_rows_b_forward<true>, k_p2_rows_b_backward<false>, k_p2_rows_b_backward<true>,
+                                                k_p2_rows_c2c);
+    const KernelLimits lim_cols = kernel_limits(k_p2_cols_solve);
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform", lim_real));
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform", lim_cplx));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform", lim_cols));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform", lim_cols));
     if (!c->pow2_y) {
         // generic engine: two adjacent columns per block when they fit, so that global accesses are 32-byte sectors
         const int cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;

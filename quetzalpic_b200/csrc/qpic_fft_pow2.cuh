@@ -132,6 +132,7 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
     }
     if (cancelled(ctl)) return;  // tested after the loads are in flight (uniform over the block)
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    QPIC_KERNEL_TAIL();
     // the split needs Z_k and Z_{n-k}: one more exchange.  The last exchange of the transform used the other buffer
     // (or none at all), so this buffer is free once every thread has left the transform's final read.
     __syncthreads();
@@ -197,6 +198,7 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
     }
     if (cancelled(ctl)) return;
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+    QPIC_KERNEL_TAIL();
     double mean = 0.0;
     if (fix) {
         const double s_col0 = pa / nz;              // sum_j u(j,0)
@@ -274,6 +276,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
     // the forward transform's last exchange buffer may still be read by slower threads of this sequence
     __syncthreads();
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy);
+    QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) spec[(size_t)(L.t + e * L.e8) * ld + k] = v[e];
@@ -360,6 +363,7 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
     }
     if (cancelled(ctl)) return;
     fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) *spec_at<DIST>(spec, j, L.t + e * L.e8) = v[e];
@@ -385,6 +389,7 @@ __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __res
     const int tag = ctl->stop_tag;
     if ((tag != 0 && tag != my_tag) || ctl->fast_fail) return;
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+    QPIC_KERNEL_TAIL();
     if (!live) return;
     bool bad = false;
 #pragma unroll

@@ -34,7 +34,8 @@ def compare_sweep(s, o, tol, check_particles=True):
     return worst
 
 
-@pytest.mark.parametrize("ny,nz", [(20, 23), (16, 32), (15, 9), (200, 200), (512, 512), (64, 100), (2, 2), (1, 8), (7, 1)])
+@pytest.mark.parametrize("ny,nz", [(20, 23), (16, 32), (15, 9), (200, 200), (512, 512), (64, 100), (2, 2), (1, 8), (7, 1), (1024, 64), (64, 1024), (1024, 1024),
+                                   (4096, 64), (64, 4096)])
 @pytest.mark.parametrize("D", [0.0, 10.0])
 def test_spectral_solve_matches_oracle(ny, nz, D):
     """(laplacian - D) u = src, src/System_3d.cpp:686-706, incl. radix-5 (200), prime (23) and degenerate sizes."""
@@ -268,3 +269,16 @@ def test_xy_cuts_match_interpolation_of_the_full_arrays(z0):
         from quetzalpic_b200 import QpicError
         with pytest.raises(QpicError):
             s.xy_cut("psi", per_slice=True)
+
+
+@pytest.mark.parametrize("n", [(3, 1024, 64), (3, 64, 1024), (3, 2048, 64)])
+def test_long_power_of_two_axes_sweep(n):
+    """1024 / 2048 point axes (BASELINE configs #3, #4 use 1024 and 4096): launch shapes must respect the kernels' register and
+    static shared-memory limits (a 1024 x 1024 grid once asked for more dynamic shared memory than the column kernel can take)."""
+    case = Case.synthetic(n=n, d=(0.2, 0.1, 0.1), M=2, ppc=(1, 1), a0=1.3)
+    o = case.make_oracle()
+    o.solve_wakefield()
+    with case.make_solver() as s:
+        assert s.solve_wakefield() == -1
+        for f in FIELDS:
+            assert slice_rel_l2(s.field3d(f), o.field3d(f)) < 1e-10, f
