@@ -120,6 +120,8 @@ struct qpic_ctx {
         int live0 = 0;                             // particles handed to qpic_init_wake_particles
         std::vector<void *> opened;                // cudaIpcOpenMemHandle mappings
     } dist;
+    int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
+    bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
     double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
     double * partials = nullptr;  // border-sum partials of the fused potential fix-up, [world][4] (inside the region when distributed)
@@ -544,6 +546,13 @@ TileJob tile_job(qpic_ctx * c) {
     j.tile_row0 = c->dist.on ? (c->dist.v.row0 / TILE - 1 + j.tile_rows) % j.tile_rows : 0;
     j.own_row0 = row_first(c);
     j.own_rows = row_count(c);
+    if (c->jyjz_lists) {
+        j.bin_cnt = c->bin_cnt;
+        j.bin_lst = c->bin_lst;
+        // rows of the target cells of the launched tile rows: j0 - 1 ... j0 + TILE - 1 each
+        j.list_row0 = c->dist.on ? (j.tile_row0 * TILE - 1 + c->g.ny) % c->g.ny : 0;
+        j.list_rows = c->dist.on ? (c->dist.v.ny_loc / TILE + 2) * TILE + 1 : c->g.ny;
+    }
     return j;
 }
 
@@ -597,6 +606,11 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     j.o[1] = tile_output(c->P.pzn, 1.0, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
     j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
     j.nw = c->P.nw_s;
+    if (c->jyjz_lists) {
+        // the lists of the half-step positions were published by the psi_middle source deposit of this iteration
+        QPIC_LAUNCH(k_tile_list_deposit, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j);
+        return check_launch(c, "k_tile_deposit_jy_jz");
+    }
     const dim3 block(TILE_ACC + 3, TILE_ACC + 3);
     QPIC_LAUNCH(k_tile_bin_deposit<1>, tile_grid(c), block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
     return check_launch(c, "k_tile_deposit_jy_jz");
@@ -1198,6 +1212,16 @@ static int create_impl(qpic_ctx * c) {
         if (bunch || (slices && !p.keep_slices_3d)) continue;
         QPIC_TRY(dev_alloc(c, &c->f3[f], n3));
     }
+    {
+        const char * e = getenv("QPIC_JYJZ_LISTS");
+        c->jyjz_lists = !(e && e[0] == '0');
+        if (c->jyjz_lists && !p.force_general_deposit) {
+            QPIC_TRY(dev_alloc(c, &c->bin_cnt, n2));
+            QPIC_TRY(dev_alloc(c, &c->bin_lst, (size_t)BIN_K * n2));
+        } else {
+            c->jyjz_lists = false;
+        }
+    }
     if (p.keep_xy_cuts) {
         for (int f = 0; f < 5; f++) QPIC_TRY(dev_alloc(c, &c->xy[f], (size_t)g.nx * g.ny));
     }
@@ -1240,6 +1264,7 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD((k_tile_deposit<2, true, true>));
         QPIC_PRELOAD(k_tile_bin_deposit<0>);
         QPIC_PRELOAD(k_tile_bin_deposit<1>);
+        QPIC_PRELOAD(k_tile_list_deposit);
         QPIC_PRELOAD(k_particles_predict<true>);
         QPIC_PRELOAD(k_particles_gamma);
         QPIC_PRELOAD(k_particles_advance);

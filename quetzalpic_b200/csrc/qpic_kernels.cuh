@@ -1011,6 +1011,13 @@ struct TileJob {
     TileOutput o[TILE_MAX_OUT];
     const double *jxb3, *rhob3, *rho_ion;  // for bg_mode 1
     const double *psi_mid, *nw;            // jy/jz job
+    // Per-cell lists of the half-step positions, left in global memory by the psi_middle source deposit (k_tile_bin_deposit<0>)
+    // for the jy/jz deposit of the same iteration (k_tile_list_deposit): bin_cnt[cell] entries bin_lst[i * n2 + cell], sorted by
+    // slot, entry = slot << 2 | hy << 1 | hz; a count above BIN_K means "not listed, scan the window".  list_row0 / list_rows:
+    // the cell rows whose lists were written (all of them on a single GPU).
+    int * bin_cnt;
+    int * bin_lst;
+    int list_row0, list_rows;
 };
 
 __device__ __forceinline__ int mod_wrap(int j, int n) {
@@ -1221,6 +1228,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                 c11 += v * wy * wz;
             };
             const int n = cnt[a * TILE_CELLS + tcell];
+            if (MODE == 0 && job.bin_cnt) job.bin_cnt[wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz)] = n;  // (halo cells: same value from the neighbour block)
             int * mine = lst + a * BIN_K * TILE_CELLS + tcell;  // entry i at mine[i * TILE_CELLS]
             if (n <= BIN_K) {
                 // insertion sort: ascending slot = canonical order
@@ -1236,6 +1244,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                 for (int i = 0; i < n; i++) {
                     const int e = mine[i * TILE_CELLS];
                     visit(e >> 2, (e >> 1) & 1, e & 1);
+                    if (MODE == 0 && job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz)] = e;
                 }
             } else {
                 // crowded target (strong compression): scan the source window in order
@@ -1265,6 +1274,117 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
     __syncthreads();
     if (cancelled(ctl)) return;
     if (is_target) tile_store_nodes<NOUT>(ctl, g, job, acc, ty, tz, ju, ku, ion);
+}
+
+// jy_next (staggered by dy/2 in y) and jz_next (dz/2 in z) from the lists the psi_middle source deposit of the same iteration
+// published (src/System_3d.cpp:472-486, :190-193).  Thread = target cell (jt, kt) of BOTH outputs:
+//   list of cell (jt, kt):     upper-half-in-y particles -> jy target (jt, kt);  upper-half-in-z particles -> jz target (jt, kt)
+//   list of cell (jt+1, kt):   lower-half-in-y particles -> jy target (jt, kt)   (they belong to the staggered cell below)
+//   list of cell (jt, kt+1):   lower-half-in-z particles -> jz target (jt, kt)
+// each list in slot order, lists in this order: deterministic.  No binning, no sort, no halo source cells, and a particle
+// of cell (jt, kt) that feeds both outputs gets its 1 / (1 + psi_middle) gather once.  Deposited values as in
+// k_tile_bin_deposit<1>: n py_next / (1 + psi_middle@particle), n pz_next / (1 + psi_middle@particle) (:483-485).
+#ifndef QPIC_LIST_MINB
+#define QPIC_LIST_MINB 3  // 64 registers: measured 0.794 ms/slice vs 0.931 (90 registers, 2 blocks / SM) and 0.829 (48, spills)
+#endif
+__global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + 5);
+    __shared__ double acc[2 * 4 * TILE_CELLS];
+    const int ay = threadIdx.y, az = threadIdx.x;
+    const int tcell = ay * TILE_ACC + az;
+    const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
+    const int jt = j0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped target cell
+    const int jw = wrap_near(jt, g.ny), kw = wrap_near(kt, g.nz);
+    const int jw1 = wrap_near(jt + 1, g.ny), kw1 = wrap_near(kt + 1, g.nz);
+    const int cell_c = jw * g.nz + kw, cell_y = jw1 * g.nz + kw, cell_z = jw * g.nz + kw1;
+    auto listed = [&](int j) {  // rows whose lists exist (distributed sweeps list only the tile rows around the slab)
+        int r = j - job.list_row0;
+        r += (r < 0) ? g.ny : 0;
+        return r < job.list_rows;
+    };
+    const int n_c = listed(jw) ? job.bin_cnt[cell_c] : 0;
+    const int n_y = listed(jw1) ? job.bin_cnt[cell_y] : 0;
+    const int n_z = listed(jw) ? job.bin_cnt[cell_z] : 0;
+    const double * __restrict__ pyn = job.o[0].val;
+    const double * __restrict__ pzn = job.o[1].val;
+    double y00 = 0.0, y10 = 0.0, y01 = 0.0, y11 = 0.0;  // jy corner sums of staggered cell (jt, kt)
+    double z00 = 0.0, z10 = 0.0, z01 = 0.0, z11 = 0.0;  // jz
+    auto add_y = [&](double v, double wy, double wz) {
+        y00 += v * (1 - wy) * (1 - wz);
+        y10 += v * wy * (1 - wz);
+        y01 += v * (1 - wy) * wz;
+        y11 += v * wy * wz;
+    };
+    auto add_z = [&](double v, double wy, double wz) {
+        z00 += v * (1 - wy) * (1 - wz);
+        z10 += v * wy * (1 - wz);
+        z01 += v * (1 - wy) * wz;
+        z11 += v * wy * wz;
+    };
+    if (n_c <= BIN_K && n_y <= BIN_K && n_z <= BIN_K) {
+        for (int i = 0; i < n_c; i++) {
+            const int e = job.bin_lst[(size_t)i * g.n2 + cell_c];
+            const int s = e >> 2, hy = (e >> 1) & 1, hz = e & 1;
+            if (hy | hz) {
+                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw, fy, fz);
+                const double nw = job.nw[s];
+                if (hy) add_y(nw * pyn[s] / w, fy - 0.5, fz);
+                if (hz) add_z(nw * pzn[s] / w, fy, fz - 0.5);
+            }
+        }
+        for (int i = 0; i < n_y; i++) {
+            const int e = job.bin_lst[(size_t)i * g.n2 + cell_y];
+            if (!((e >> 1) & 1)) {
+                const int s = e >> 2;
+                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw1, kw, fy, fz);
+                add_y(job.nw[s] * pyn[s] / w, fy + 0.5, fz);
+            }
+        }
+        for (int i = 0; i < n_z; i++) {
+            const int e = job.bin_lst[(size_t)i * g.n2 + cell_z];
+            if (!(e & 1)) {
+                const int s = e >> 2;
+                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw1, fy, fz);
+                add_z(job.nw[s] * pzn[s] / w, fy, fz + 0.5);
+            }
+        }
+    } else {
+        // a crowded cell was not listed (strong compression): scan the source window of either output in order
+        for (int a = 0; a < 2; a++) {
+            const int hi_y = a == 0 ? 2 : 1, hi_z = a == 1 ? 2 : 1;
+            for (int dy_ = -1; dy_ <= hi_y; dy_++) {
+                for (int dz_ = -1; dz_ <= hi_z; dz_++) {
+                    const int cell = wrap_near(jt + dy_, g.ny) * g.nz + wrap_near(kt + dz_, g.nz);
+                    const int e1 = start[cell + 1];
+                    for (int s = start[cell]; s < e1; s++) {
+                        const int code = P.off_m[s];
+                        const int hy = (code >> 6) & 1, hz = (code >> 7) & 1;
+                        const int need_y = (a == 0 && !hy) ? 1 : 0, need_z = (a == 1 && !hz) ? 1 : 0;
+                        if (dy_ + (code & 7) - 2 - need_y != 0 || dz_ + ((code >> 3) & 7) - 2 - need_z != 0) continue;
+                        const double fy = P.fy_m[s], fz = P.fz_m[s];
+                        const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, wrap_near(jt + need_y, g.ny), wrap_near(kt + need_z, g.nz), fy, fz);
+                        if (a == 0) add_y(job.nw[s] * pyn[s] / w, hy ? fy - 0.5 : fy + 0.5, fz);
+                        else add_z(job.nw[s] * pzn[s] / w, fy, hz ? fz - 0.5 : fz + 0.5);
+                    }
+                }
+            }
+        }
+    }
+    if (cancelled(ctl)) return;
+    QPIC_KERNEL_TAIL();
+    acc[0 * TILE_CELLS + tcell] = y00;
+    acc[1 * TILE_CELLS + tcell] = y10;
+    acc[2 * TILE_CELLS + tcell] = y01;
+    acc[3 * TILE_CELLS + tcell] = y11;
+    acc[4 * TILE_CELLS + tcell] = z00;
+    acc[5 * TILE_CELLS + tcell] = z10;
+    acc[6 * TILE_CELLS + tcell] = z01;
+    acc[7 * TILE_CELLS + tcell] = z11;
+    __syncthreads();
+    tile_store_nodes<2>(ctl, g, job, acc, ay, az, jt, kt, 0.0);
 }
 
 }  // namespace qpic
