@@ -120,6 +120,7 @@ struct qpic_ctx {
         int live0 = 0;                             // particles handed to qpic_init_wake_particles
         std::vector<void *> opened;                // cudaIpcOpenMemHandle mappings
     } dist;
+    double2 * b_src = nullptr;                     // sources of the By + i Bz solve formed by the jy/jz deposit (TileJob::b_src)
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
@@ -608,6 +609,13 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     j.nw = c->P.nw_s;
     if (c->jyjz_lists) {
         // the lists of the half-step positions were published by the psi_middle source deposit of this iteration
+        j.b_src = c->b_src;
+        j.b_by = c->f2[QPIC_F2_BY_CUR];
+        j.b_bz = c->f2[QPIC_F2_BZ_CUR];
+        j.b_jx = c->f2[QPIC_F2_JX];
+        j.b_jy = c->f2[QPIC_F2_JY];
+        j.b_jz = c->f2[QPIC_F2_JZ];
+        j.b_D = c->prm.magnetic_field_D;
         QPIC_LAUNCH(k_tile_list_deposit, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j);
         return check_launch(c, "k_tile_deposit_jy_jz");
     }
@@ -764,6 +772,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
         }
         if (fast) {
+            if (c->jyjz_lists && c->b_src) QPIC_TRY(stream_depend(c, sb, sa));  // the deposit's epilogue reads jx (branch B)
             QPIC_TRY(enqueue_tile_jy_jz(c, sa));
             QPIC_TRY(dist_reduce(c, sa, halo_job({c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT]}, {RB_JY, RB_JZ})));
         } else {
@@ -780,9 +789,11 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         {
             const qpic_ctx::FftLaunch & R = c->rows_cplx;
             if (c->pow2_z) {
-                QPIC_LAUNCH((c->dist.on ? k_p2_rows_b_forward<true> : k_p2_rows_b_forward<false>), R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D,
-                            c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
-                            c->f2[QPIC_F2_JZ_NEXT], spec_map(c, true), row_first(c), row_count(c));
+                const bool pre = fast && c->jyjz_lists && c->b_src;
+                auto kern = c->dist.on ? k_p2_rows_b_forward<true, false> : (pre ? k_p2_rows_b_forward<false, true> : k_p2_rows_b_forward<false, false>);
+                QPIC_LAUNCH(kern, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D, c->f2[QPIC_F2_BY_CUR],
+                            c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT],
+                            (const double2 *)c->b_src, spec_map(c, true), row_first(c), row_count(c));
             } else {
                 QPIC_LAUNCH(k_fft_rows_b_forward<false>, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan, c->fz.tw, c->g, c->prm.magnetic_field_D,
                             c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT],
@@ -1117,7 +1128,7 @@ static int create_impl(qpic_ctx * c) {
     c->pow2_y = c->fy.plan.log2n > 0;
     c->pow2_z = c->fz.plan.log2n > 0;
     const KernelLimits lim_real = kernel_limits(k_p2_rows_r2c<false>, k_p2_rows_r2c<true>, k_p2_rows_c2r<false>, k_p2_rows_c2r<true>);
-    const KernelLimits lim_cplx = kernel_limits(k_p2_rows_b_forward<false>, k_p2_rows_b_forward<true>, k_p2_rows_b_backward<false>, k_p2_rows_b_backward<true>,
+    const KernelLimits lim_cplx = kernel_limits(k_p2_rows_b_forward<false, false>, k_p2_rows_b_forward<false, true>, k_p2_rows_b_forward<true, false>, k_p2_rows_b_backward<false>, k_p2_rows_b_backward<true>,
                                                 k_p2_rows_c2c);
     const KernelLimits lim_cols = kernel_limits(k_p2_cols_solve);
     QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform", lim_real));
@@ -1149,8 +1160,9 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -1218,6 +1230,8 @@ static int create_impl(qpic_ctx * c) {
         if (c->jyjz_lists && !p.force_general_deposit) {
             QPIC_TRY(dev_alloc(c, &c->bin_cnt, n2));
             QPIC_TRY(dev_alloc(c, &c->bin_lst, (size_t)BIN_K * n2));
+            // (distributed sweeps reduce jy_next / jz_next over the slab edges first, so their row kernel builds the sources)
+            if (!D.on && c->pow2_z) QPIC_TRY(dev_alloc(c, &c->b_src, n2));
         } else {
             c->jyjz_lists = false;
         }
@@ -1281,7 +1295,7 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_p2_rows_r2c<true>);
         QPIC_PRELOAD(k_p2_rows_c2r<true>);
         QPIC_PRELOAD(k_p2_cols_solve);
-        QPIC_PRELOAD(k_p2_rows_b_forward<true>);
+        QPIC_PRELOAD((k_p2_rows_b_forward<true, false>));
         QPIC_PRELOAD(k_p2_rows_b_backward<true>);
 #undef QPIC_PRELOAD
     }

@@ -332,11 +332,12 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 // ------------------------------------------------------------------------------------------------ complex field (By + i Bz)
 
 // see k_fft_rows_b_forward (qpic_fft.cuh) for the source terms (src/System_3d.cpp:489-495, :530-536, :555-564 incl. :563)
-template <bool DIST>
+// PRE: the sources were already formed by the jy/jz deposit (TileJob::b_src) and are simply loaded
+template <bool DIST, bool PRE>
 __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
                                     const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                     const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
-                                    SpecMap spec, int row0, int nrows) {
+                                    const double2 * __restrict__ b_src, SpecMap spec, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_forward);
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -350,7 +351,9 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int k = L.t + e * L.e8;
-        if (live) {
+        if (live && PRE) {
+            v[e] = b_src[j * nz + k];
+        } else if (live) {
             const int t = j * nz + k;
             const int kp = wrap_inc(k, nz);
             const double djz_dxi = (jz[t] - jz_next[t]) * g.inv_dx;

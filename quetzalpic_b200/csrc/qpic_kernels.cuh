@@ -1018,6 +1018,12 @@ struct TileJob {
     int * bin_cnt;
     int * bin_lst;
     int list_row0, list_rows;
+    // jy/jz job on a single GPU: the node that has just formed jy_next, jz_next also forms the sources of the By + i Bz solve
+    // (src/System_3d.cpp:489-495, :530-536, :555-564 incl. the :563 quirk) into b_src, so that the forward rows of that solve
+    // load one complex array instead of seven real ones with their stencils.  NULL: the row kernel builds them.
+    double2 * b_src;
+    const double *b_by, *b_bz, *b_jx, *b_jy, *b_jz;
+    double b_D;
 };
 
 __device__ __forceinline__ int mod_wrap(int j, int n) {
@@ -1384,7 +1390,30 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
     acc[6 * TILE_CELLS + tcell] = z01;
     acc[7 * TILE_CELLS + tcell] = z11;
     __syncthreads();
-    tile_store_nodes<2>(ctl, g, job, acc, ay, az, jt, kt, 0.0);
+    if (ay < 1 || az < 1 || jt >= g.ny || kt >= g.nz) return;
+    // node (jt, kt): corner sums of its four neighbouring staggered cells, in the fixed order of tile_store_nodes
+    const int t = jt * g.nz + kt;
+    double jyn = 0.0, jzn = 0.0;
+    jyn += acc[0 * TILE_CELLS + ay * TILE_ACC + az];
+    jyn += acc[1 * TILE_CELLS + (ay - 1) * TILE_ACC + az];
+    jyn += acc[2 * TILE_CELLS + ay * TILE_ACC + az - 1];
+    jyn += acc[3 * TILE_CELLS + (ay - 1) * TILE_ACC + az - 1];
+    jzn += acc[4 * TILE_CELLS + ay * TILE_ACC + az];
+    jzn += acc[5 * TILE_CELLS + (ay - 1) * TILE_ACC + az];
+    jzn += acc[6 * TILE_CELLS + ay * TILE_ACC + az - 1];
+    jzn += acc[7 * TILE_CELLS + (ay - 1) * TILE_ACC + az - 1];
+    job.o[0].out[t] = jyn;
+    job.o[1].out[t] = jzn;
+    if (job.b_src) {
+        // same expressions as k_p2_rows_b_forward
+        const int jp = wrap_inc(jt, g.ny), kp = wrap_inc(kt, g.nz);
+        const int jq = (jt == g.ny - 1) ? 0 : jt;
+        const double djz_dxi = (job.b_jz[t] - jzn) * g.inv_dx;
+        const double djy_dxi = (job.b_jy[t] - jyn) * g.inv_dx;
+        const double jxt = job.b_jx[t];
+        job.b_src[t] = make_double2(-job.b_D * job.b_by[t] - (job.b_jx[jt * g.nz + kp] - jxt) * g.inv_dz + djz_dxi,
+                                    -job.b_D * job.b_bz[jq * g.nz + kt] + (job.b_jx[jp * g.nz + kt] - jxt) * g.inv_dy - djy_dxi);
+    }
 }
 
 }  // namespace qpic
