@@ -73,6 +73,7 @@ struct qpic_ctx {
     double *fft_in = nullptr, *fft_in2 = nullptr, *raw = nullptr;
     double2 * spec = nullptr;  // ny * nz complex (the psi solves use the first ny*(nz/2+1))
     double2 *spec_row0 = nullptr, *spec_colsum = nullptr;  // nz/2+1 each: U(0,k) and sum_j U(j,k) for the fused potential fix-up
+    int * eos_ticket = nullptr;                            // "last block" counter of k_end_of_slice (advances Ctl::slice)
     int * cols_ticket = nullptr;                           // "last block" counter of the column kernel
     double *sy = nullptr, *sz = nullptr;
     DeviceFft fy, fz;
@@ -441,9 +442,14 @@ int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cel
     int * live_out = (c->dist.on && ctl == c->ctl) ? &c->ctl->np1 : nullptr;
     QPIC_LAUNCH(k_scan_chunk_sums, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums);
     QPIC_TRY(check_launch(c, "k_scan_chunk_sums"));
-    QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, st, ctl, c->sums, c->nchunks);
-    QPIC_TRY(check_launch(c, "k_scan_sums"));
-    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums, start, c->cursor, live_out);
+    // few chunks (<= 1024, i.e. grids up to 1024 x 1024): every block of the apply kernel adds up the chunk totals before its own
+    // instead of a separate single-block scan kernel
+    const int fold = c->nchunks <= 1024 ? 1 : 0;
+    if (!fold) {
+        QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, st, ctl, c->sums, c->nchunks);
+        QPIC_TRY(check_launch(c, "k_scan_sums"));
+    }
+    QPIC_LAUNCH(k_scan_apply, c->nchunks, SCAN_THREADS, 0, st, ctl, c->count, n2, c->sums, start, c->cursor, live_out, fold);
     QPIC_TRY(check_launch(c, "k_scan_apply"));
     if (np > 0) {
         QPIC_LAUNCH_FLAT(k_sort_fill, blocks_for(np, 256), 256, 0, st, ctl, np, cell, c->cursor, c->tmp);
@@ -718,9 +724,10 @@ int enqueue_end_of_slice(qpic_ctx * c, int b_is_zero, int roll, int ignore_stop)
                          c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], ignore_stop, row_first(c), row_count(c));
         QPIC_TRY(check_launch(c, "k_xy_lines"));
     }
-    QPIC_LAUNCH_FLAT(k_end_of_slice, blocks_for((size_t)row_count(c) * c->g.nz, 256), 256, 0, c->stream, c->ctl, c->g, slice_out(c), c->f2[QPIC_F2_PSI],
+    QPIC_LAUNCH(k_end_of_slice, blocks_for((size_t)row_count(c) * c->g.nz, 256), 256, 0, c->stream, c->ctl, c->g, slice_out(c), c->f2[QPIC_F2_PSI],
                      c->f2[QPIC_F2_PSI_PREV], c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_RHO], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY],
-                     c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT], b_is_zero, roll, ignore_stop, row_first(c), row_count(c));
+                     c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT], b_is_zero, roll, ignore_stop, row_first(c), row_count(c), c->ctl,
+                     roll ? c->eos_ticket : (int *)nullptr);
     return check_launch(c, "k_end_of_slice");
 }
 
@@ -840,9 +847,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, sa, c->ctl, c->P, c->perm_b);
         QPIC_TRY(check_launch(c, "k_particles_to_slots"));
     }
+    // (the last block of k_end_of_slice has moved Ctl::slice on)
     QPIC_TRY(stream_depend(c, sb, sa));
-    QPIC_LAUNCH_FLAT(k_next_slice, 1, 32, 0, sa, c->ctl);
-    QPIC_TRY(check_launch(c, "k_next_slice"));
     return QPIC_OK;
 }
 
@@ -1246,6 +1252,7 @@ static int create_impl(qpic_ctx * c) {
     QPIC_TRY(dev_alloc(c, &c->spec_row0, (size_t)g.nz / 2 + 1));
     QPIC_TRY(dev_alloc(c, &c->spec_colsum, (size_t)g.nz / 2 + 1));
     QPIC_TRY(dev_alloc(c, &c->cols_ticket, 1));
+    QPIC_TRY(dev_alloc(c, &c->eos_ticket, 1));
     QPIC_TRY(dev_alloc(c, &c->partials, 4 * DIST_MAX));
     c->nchunks = blocks_for(n2 + 1, SCAN_CHUNK);  // + the "emigrated" bucket of distributed sweeps
     QPIC_TRY(dev_alloc(c, &c->count, n2 + 1));
@@ -1290,7 +1297,6 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_sort_fill);
         QPIC_PRELOAD(k_sort_rank);
         QPIC_PRELOAD(k_end_of_slice);
-        QPIC_PRELOAD(k_next_slice);
         QPIC_PRELOAD(k_init_a_sqr);
         QPIC_PRELOAD(k_p2_rows_r2c<true>);
         QPIC_PRELOAD(k_p2_rows_c2r<true>);

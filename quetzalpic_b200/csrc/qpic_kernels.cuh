@@ -350,9 +350,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const Ctl * ctl, int
 
 __global__ void __launch_bounds__(SCAN_THREADS)
     k_scan_apply(const Ctl * ctl, int * __restrict__ count, int n, const int * __restrict__ sums, int * __restrict__ start, int * __restrict__ cursor,
-                 int * __restrict__ live_out) {
+                 int * __restrict__ live_out, int fold_sums) {
     QPIC_KERNEL_BEGIN(KID_k_scan_apply);
     if (cancelled(ctl)) return;
+    // fold_sums: sums[] still holds the raw chunk totals (k_scan_sums was skipped: few chunks) and every block adds up the chunks
+    // before its own -- integer sums, so the order is irrelevant
+    int chunk_offset;
+    if (fold_sums) {
+        int part = 0;
+        for (int i = threadIdx.x; i < (int)blockIdx.x; i += SCAN_THREADS) part += sums[i];
+        block_exclusive_scan(part, chunk_offset);
+    } else {
+        chunk_offset = sums[blockIdx.x];
+    }
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int c[SCAN_ITEMS];
     int v = 0;
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
         v += c[t];
     }
     int total;
-    int run = sums[blockIdx.x] + block_exclusive_scan(v, total);
+    int run = chunk_offset + block_exclusive_scan(v, total);
 #pragma unroll
     for (int t = 0; t < SCAN_ITEMS; t++) {
         if (base + t < n) {
@@ -885,13 +895,29 @@ __global__ void k_end_of_slice(const Ctl * ctl, Geom g, SliceOut o, const double
                                const double * __restrict__ by, const double * __restrict__ bz, const double * __restrict__ rho,
                                const double * __restrict__ jx, double * __restrict__ jy, double * __restrict__ jz,
                                const double * __restrict__ jy_next, const double * __restrict__ jz_next, int b_is_zero, int roll, int ignore_stop,
-                               int row0, int nrows) {
+                               int row0, int nrows, Ctl * ctl_rw, int * __restrict__ ticket) {
     QPIC_KERNEL_BEGIN(KID_k_end_of_slice);
     if (cancelled(ctl) && !ignore_stop) return;
+    // ticket != NULL (slice body): the block that finishes last moves the sweep to the next slice (every block has read
+    // ctl->slice by then; nothing that runs concurrently with this kernel reads it)
+    struct Advance {
+        Ctl * ctl;
+        int * ticket;
+        __device__ ~Advance() {
+            if (ticket == nullptr || threadIdx.x != 0) return;
+            __threadfence();
+            if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+                *ticket = 0;
+                ctl->slice -= 1;
+            }
+        }
+    };
+    const int i = ignore_stop ? 0 : ctl->slice;
+    __syncthreads();  // the whole block has read the control block before thread 0 may leave
+    Advance advance_on_exit{ctl_rw, ticket};
     // rows [row0, row0 + nrows): all of them on a single GPU, the own slab in a distributed sweep
     if (blockIdx.x * blockDim.x + threadIdx.x >= (unsigned)(nrows * g.nz)) return;
     const int t = row0 * g.nz + blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = ignore_stop ? 0 : ctl->slice;
     const int j = t / g.nz, k = t - j * g.nz;
     const size_t off = (size_t)i * g.n2 + t;
     const double ps = psi[t];
@@ -960,11 +986,6 @@ __global__ void k_xy_lines(const Ctl * ctl, Geom g, XyLines o, XyCut node, XyCut
     o.jz[at] = (1 - half.frac) * jz[r + half.k0] + half.frac * jz[r + half.k1];
 }
 
-__global__ void k_next_slice(Ctl * ctl) {
-    QPIC_KERNEL_BEGIN(KID_k_next_slice);
-    if (cancelled(ctl)) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) ctl->slice -= 1;
-}
 
 // ------------------------------------------------------------------------------------------------ sort-free tile deposits
 // Deterministic deposition without sorting the half-step positions globally.  A block owns a TILE x TILE patch of grid
@@ -1327,9 +1348,14 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
         z01 += v * (1 - wy) * wz;
         z11 += v * wy * wz;
     };
+    // first entries of the three lists: fetched together with the counts (position 0 exists whatever the count); inside the loops
+    // the next entry is requested before the current one is processed, so the head of each dependent chain (entry -> slot ->
+    // particle data) overlaps the previous visit
+    int e_c = job.bin_lst[cell_c], e_y = job.bin_lst[cell_y], e_z = job.bin_lst[cell_z];
     if (n_c <= BIN_K && n_y <= BIN_K && n_z <= BIN_K) {
         for (int i = 0; i < n_c; i++) {
-            const int e = job.bin_lst[(size_t)i * g.n2 + cell_c];
+            const int e = e_c;
+            if (i + 1 < n_c) e_c = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_c];
             const int s = e >> 2, hy = (e >> 1) & 1, hz = e & 1;
             if (hy | hz) {
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
@@ -1340,7 +1366,8 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             }
         }
         for (int i = 0; i < n_y; i++) {
-            const int e = job.bin_lst[(size_t)i * g.n2 + cell_y];
+            const int e = e_y;
+            if (i + 1 < n_y) e_y = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_y];
             if (!((e >> 1) & 1)) {
                 const int s = e >> 2;
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
@@ -1349,7 +1376,8 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             }
         }
         for (int i = 0; i < n_z; i++) {
-            const int e = job.bin_lst[(size_t)i * g.n2 + cell_z];
+            const int e = e_z;
+            if (i + 1 < n_z) e_z = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_z];
             if (!(e & 1)) {
                 const int s = e >> 2;
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
