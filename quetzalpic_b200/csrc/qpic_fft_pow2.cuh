@@ -285,7 +285,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
         // The block that takes the last ticket sees every block's row0[] / colsum[] (release: fence before the ticket;
         // acquire: fence after it) and reduces them to the border mean -- see k_p2_rows_c2r for the formulas.
         __shared__ int is_last;
-        __shared__ double red_a[1024], red_b[1024];
+        __shared__ double red_a[32], red_b[32];  // one partial per warp
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
@@ -299,18 +299,23 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
                 pa += wgt * row0[kk].x;
                 pb += wgt * colsum[kk].x;
             }
-            red_a[threadIdx.x] = pa;
-            red_b[threadIdx.x] = pb;
+            // fixed-order reduction: shuffle tree inside each warp, then the warps' partials in order
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pa += __shfl_down_sync(0xffffffffu, pa, o);
+                pb += __shfl_down_sync(0xffffffffu, pb, o);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                red_a[threadIdx.x >> 5] = pa;
+                red_b[threadIdx.x >> 5] = pb;
+            }
             __syncthreads();
-            int n = blockDim.x;  // tree over an arbitrary block size: fold the upper part onto the lower one
-            while (n > 1) {
-                const int half = (n + 1) / 2;
-                if ((int)threadIdx.x < n - half) {
-                    red_a[threadIdx.x] += red_a[threadIdx.x + half];
-                    red_b[threadIdx.x] += red_b[threadIdx.x + half];
+            if (threadIdx.x == 0) {
+                const int nwarps = (blockDim.x + 31) >> 5;
+                for (int w = 1; w < nwarps; w++) {
+                    red_a[0] += red_a[w];
+                    red_b[0] += red_b[w];
                 }
-                __syncthreads();
-                n = half;
             }
             if (threadIdx.x == 0) {
                 // every rank gets this rank's partial sums (slot my_rank of its table); k_p2_rows_c2r adds them up in rank order
