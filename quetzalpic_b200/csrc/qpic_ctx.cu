@@ -368,7 +368,7 @@ SpecMap partials_map(const qpic_ctx * c) {
 // ---- exchange steps of a slab-decomposed sweep (no-ops on a single GPU)
 int dist_barrier(qpic_ctx * c, cudaStream_t st) {
     if (!c->dist.on) return QPIC_OK;
-    QPIC_LAUNCH(k_xchg_barrier, 1, 32, 0, st, c->dist.v);
+    QPIC_LAUNCH(k_xchg_barrier, 1, 32, 0, st, c->dist.v, c->ctl);
     return check_launch(c, "k_xchg_barrier");
 }
 
@@ -1203,6 +1203,7 @@ static int create_impl(qpic_ctx * c) {
             return at;
         };
         L.flags = take(sizeof(long long) * DIST_MAX);
+        L.stops = take(sizeof(int) * DIST_MAX);
         L.partials = take(sizeof(double) * 4 * DIST_MAX);
         L.inbox_count = take(sizeof(int) * 2);
         const int cpr_max = D.cpr_half > D.cpr_full ? D.cpr_half : D.cpr_full;

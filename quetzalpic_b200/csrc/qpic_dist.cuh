@@ -32,7 +32,8 @@ enum DistReduceSlot { RB_CHARGE = 0, RB_JX, RB_JY, RB_JZ, RB_RHO, RB_CHI, RB_COU
 enum DistField { DF_PSI = 0, DF_PSI_MIDDLE, DF_BY, DF_BZ, DF_JX, DF_COUNT };
 
 struct DistLayout {  // byte offsets inside an exchange region (identical on all ranks)
-    size_t flags;        // long long[DIST_MAX]
+    size_t flags;        // long long[DIST_MAX]: epoch of the last barrier each rank has entered
+    size_t stops;        // int[DIST_MAX]: Ctl::stop_tag of each rank as of its last barrier
     size_t partials;     // double[DIST_MAX][4]: border-sum partials of the fused potential fix-up
     size_t inbox_count;  // int[2]
     size_t cols;         // double2[ny * cpr_max]: this rank's columns of the spectrum
@@ -96,7 +97,10 @@ __device__ __forceinline__ unsigned long long dist_now_ns() {
 
 // Everything this GPU stored before the barrier (previous kernels of the stream) is visible to the peers once they leave
 // it, and vice versa.  NOT skipped after a stop / abort: the peers would wait for ever.
-__global__ void k_xchg_barrier(DistView d) {
+// The |B| stop condition (src/System_3d.cpp:545-550) is made global here: every rank publishes its stop tag with the barrier
+// and adopts a peer's, so that from the first barrier after the B solve that tripped it (the By / Bz halo fill) all ranks
+// cancel the rest of the sweep at the same point of their streams, as the single-GPU sweep does.
+__global__ void k_xchg_barrier(DistView d, Ctl * ctl) {
     QPIC_KERNEL_BEGIN(KID_k_xchg_barrier);
     __shared__ long long ep;
     if (threadIdx.x == 0) {
@@ -104,8 +108,9 @@ __global__ void k_xchg_barrier(DistView d) {
         *d.epoch = ep;
     }
     __syncthreads();
-    __threadfence_system();
     const int q = threadIdx.x;
+    if (q < d.world) reinterpret_cast<int *>(dist_base(d, q) + d.lay.stops)[d.rank] = ctl->stop_tag;
+    __threadfence_system();
     if (q < d.world) {
         st_release_sys(reinterpret_cast<long long *>(dist_base(d, q) + d.lay.flags) + d.rank, ep);
         const long long * mine = reinterpret_cast<const long long *>(dist_base(d, d.rank) + d.lay.flags) + q;
@@ -116,6 +121,9 @@ __global__ void k_xchg_barrier(DistView d) {
                 break;
             }
         }
+        // rank q's tag was stored before its flag (release) and is read after it (acquire)
+        const int peer_tag = reinterpret_cast<const int *>(dist_base(d, d.rank) + d.lay.stops)[q];
+        if (peer_tag != 0) atomicCAS(&ctl->stop_tag, 0, peer_tag);
     }
     __threadfence_system();
 }

@@ -61,3 +61,27 @@ def test_slab_context_rejects_unsupported_shapes():
         assert s.row_range == (32, 32)
         with pytest.raises(QpicError):
             s.begin()  # peers not attached
+
+
+def test_stop_condition_reaches_every_rank():
+    """|B| > threshold_B on one slab (src/System_3d.cpp:545-550): the stop tag travels with the next exchange barrier, every rank ends
+    the sweep at the same slice and the fields written so far match the single-domain oracle."""
+    from quetzalpic_b200.dist import SlabGroup
+    nx, ny, nz = 10, 64, 64
+    case = Case.synthetic(n=(nx, ny, nz), d=(0.2, 0.1, 0.1), M=2, ppc=(1, 1), a0=0.0)
+    x = (np.arange(nx) * 0.2)[:, None, None]
+    y = (np.arange(ny) * 0.1)[None, :, None]
+    z = (np.arange(nz) * 0.1)[None, None, :]
+    # a thin, dense driver in rank 0's slab (rows < 32): B blows up in slice 6 before the plasma has moved
+    bunch = -20000.0 * np.exp(-((x - 1.2) / 0.05) ** 2 - ((y - 2.9) / 0.5) ** 2 - ((z - 3.2) / 0.5) ** 2)
+    o = case.make_oracle()
+    o.set_bunch_sources(bunch, bunch)
+    o.solve_wakefield()
+    assert o.stopped_at == 6
+    with SlabGroup(2, nx, ny, nz, case.l[0], case.l[1], case.l[2], case.M, devices=devices_for(2), stop_check_interval=3) as g:
+        for s in g.ranks:
+            s.upload_bunch_sources(bunch, bunch)
+        g.init_wake_particles(*case.particles)
+        assert g.solve_wakefield() == [6, 6]
+        for f in FIELDS:
+            assert slice_rel_l2(g.field3d(f), o.field3d(f)) < 1e-9, f

@@ -174,6 +174,11 @@ static inline int atomicMax(int * addr, int v) {
     if (v > old) *addr = v;
     return old;
 }
+static inline int atomicCAS(int * addr, int compare, int v) {
+    int old = *addr;
+    if (old == compare) *addr = v;
+    return old;
+}
 static inline int atomicExch(int * addr, int v) {
     int old = *addr;
     *addr = v;
