@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define QPIC_ABI_VERSION 2
+#define QPIC_ABI_VERSION 3
 
 typedef enum {
     QPIC_OK = 0,
@@ -133,6 +133,35 @@ int qpic_download_particles(qpic_ctx * ctx, qpic_particle_field f, double * dst)
 int qpic_upload_particles(qpic_ctx * ctx, qpic_particle_field f, const double * src); /* y,z,py,pz,n only */
 /* forces the slice index the next qpic_step processes (state injection) */
 int qpic_set_current_slice(qpic_ctx * ctx, int slice);
+
+/* ---- beam ("bunch") macroparticles: the part of System_3d::run around solve_wakefield (src/System_3d.cpp:199-236).  The
+ * particles (bunch_particle_3d, src/containers.h:45-61) live on the device as SoA arrays; rho_bunch / jx_bunch and the five
+ * field arrays they interact with are the resident arrays of the sweep, so a time iteration moves nothing over PCIe.
+ * One time iteration of the reference is
+ *     qpic_bunch_deposit_densities; qpic_init_wake_particles; qpic_solve_wakefield; qpic_bunch_gather_fields;
+ *     [Bunch_NNN output: qpic_bunch_download]; qpic_bunch_advance (all but the last iteration).
+ * QED photon emission (qed = true, src/System_3d.cpp:887-921) is not covered. */
+typedef enum {
+    QPIC_B_X = 0, QPIC_B_Y, QPIC_B_Z, QPIC_B_PX, QPIC_B_PY, QPIC_B_PZ, QPIC_B_GAMMA, QPIC_B_N,
+    QPIC_B_EX, QPIC_B_EY, QPIC_B_EZ, QPIC_B_BY, QPIC_B_BZ, QPIC_B_CHI, QPIC_B_COUNT
+} qpic_bunch_field;
+/* the Species_register (src/Species_register.h:6-27, built-ins src/Config_reader.cpp:19-22) by species id; at most 16 entries */
+int qpic_bunch_set_species(qpic_ctx * ctx, int count, const double * charge, const double * charge_to_mass_ratio, const int * is_photon);
+/* the particles System_3d::init_bunch_particles builds (src/System_3d.cpp:767-803), concatenated over the bunches; the field
+ * members and chi start at 0.  Must precede the first qpic_step of the context (rho_bunch / jx_bunch become resident). */
+int qpic_bunch_init(qpic_ctx * ctx, size_t count, const double * x, const double * y, const double * z, const double * px, const double * py,
+                    const double * pz, const double * gamma, const double * n, const int * species_id);
+size_t qpic_bunch_count(const qpic_ctx * ctx);
+/* System_3d::deposit_bunch_densities (src/System_3d.cpp:926-946) with the 8-point deposit of src/array_utils.cpp:290-338:
+ * deterministic (cell lists + one thread per node), no floating-point atomics */
+int qpic_bunch_deposit_densities(qpic_ctx * ctx);
+/* System_3d::deposit_wakefield_to_bunch (src/System_3d.cpp:843-860): ex, ey, ez, by, bz at the particles (8-point gather
+ * honouring each array's origin, src/array_utils.cpp:340-375) and chi; field_schwinger = Plasma_units::field_schwinger */
+int qpic_bunch_gather_fields(qpic_ctx * ctx, double field_schwinger);
+/* System_3d::advance_bunch_particles with qed == false (src/System_3d.cpp:862-886) */
+int qpic_bunch_advance(qpic_ctx * ctx, double dt);
+int qpic_bunch_download(qpic_ctx * ctx, qpic_bunch_field f, double * dst); /* qpic_bunch_count doubles */
+int qpic_bunch_upload(qpic_ctx * ctx, qpic_bunch_field f, const double * src);
 
 /* ---- building blocks exposed for unit tests and the FFT comparator bench */
 /* (nabla_perp^2 - D) u = src on the periodic ny x nz grid with the 5-point-Laplacian symbol, DC forced to 0, result

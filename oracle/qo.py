@@ -167,3 +167,49 @@ class Oracle:
         idx = FIELDS_3D.index(name, 9) if per_slice else FIELDS_3D.index(name)
         p = self.L.qo_field3d_ptr(self.ctx, idx)
         return np.ctypeslib.as_array(p, shape=(self.nx, self.ny, self.nz))
+
+
+# ---------------------------------------------------------------------------------------------- beam particles (oracle/qo_bunch.c)
+BUNCH_FIELDS = ["x", "y", "z", "px", "py", "pz", "gamma", "n", "ex", "ey", "ez", "by", "bz", "chi"]
+
+
+class QoBunch(ctypes.Structure):
+    _fields_ = [("count", ctypes.c_size_t)] + [(k, ctypes.c_void_p) for k in BUNCH_FIELDS] + [("species_id", ctypes.c_void_p)]
+
+
+class OracleBunch:
+    """bunch_particles of System_3d and the three beam-side steps of System_3d::run (reference src/System_3d.cpp:199-236),
+    operating on an Oracle's 3-D arrays.  species: list of (charge, mass, is_photon) by species id."""
+
+    def __init__(self, oracle, particles, species):
+        self.o = oracle
+        L = self.L = lib()
+        vp, ci, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+        L.qo_bunch_deposit_densities.argtypes = [vp, vp, ci, ci, ci, dbl, dbl, dbl, vp, vp]
+        L.qo_bunch_gather_fields.argtypes = [vp, ci, ci, ci, dbl, dbl, dbl, vp, vp, vp, vp, vp, dbl]
+        L.qo_bunch_advance.argtypes = [vp, vp, vp, dbl]
+        count = len(particles["species_id"])
+        self.a = {k: np.zeros(count) for k in BUNCH_FIELDS}
+        for k in ["x", "y", "z", "px", "py", "pz", "gamma", "n"]:
+            self.a[k][:] = particles[k]
+        self.species_id = np.ascontiguousarray(particles["species_id"], dtype=np.int32)
+        self.charge = np.array([s[0] for s in species], dtype=np.float64)
+        self.cmr = np.array([0.0 if s[1] == 0.0 else s[0] / s[1] for s in species], dtype=np.float64)
+        self.photon = np.array([1 if s[2] else 0 for s in species], dtype=np.int32)
+        self.s = QoBunch(count, *[self.a[k].ctypes.data for k in BUNCH_FIELDS], self.species_id.ctypes.data)
+        p = oracle.params
+        self.geom = (p.nx, p.ny, p.nz, p.lx / p.nx, p.ly / p.ny, p.lz / p.nz)
+
+    def __getitem__(self, name):
+        return self.a[name]
+
+    def deposit_bunch_densities(self):
+        self.L.qo_bunch_deposit_densities(ctypes.byref(self.s), self.charge.ctypes.data, *self.geom,
+                                          self.o.field3d("rho_bunch").ctypes.data, self.o.field3d("jx_bunch").ctypes.data)
+
+    def deposit_wakefield_to_bunch(self, field_schwinger):
+        f = [self.o.field3d(k).ctypes.data for k in ["ex", "ey", "ez", "by", "bz"]]
+        self.L.qo_bunch_gather_fields(ctypes.byref(self.s), *self.geom, *f, float(field_schwinger))
+
+    def advance_bunch_particles(self, dt):
+        self.L.qo_bunch_advance(ctypes.byref(self.s), self.cmr.ctypes.data, self.photon.ctypes.data, float(dt))

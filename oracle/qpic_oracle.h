@@ -87,6 +87,27 @@ double qo_gather_zder(double y, double z, const double * array, int ny, int nz, 
  * (caller divides by ny and nz), in place in `inout` (src/System_3d.cpp:686-706) */
 void qo_solve_poisson(qo_ctx * ctx, double * inout, double D);
 
+
+/* ---- beam ("bunch") side of System_3d::run (src/System_3d.cpp:199-236), oracle/qo_bunch.c.  bunch_particle_3d
+ * (src/containers.h:45-61) as caller-owned SoA arrays of `count` entries. */
+typedef struct {
+    size_t count;
+    double *x, *y, *z, *px, *py, *pz, *gamma, *n, *ex, *ey, *ez, *by, *bz, *chi;
+    int * species_id;
+} qo_bunch;
+void qo_deposit3d(double x, double y, double z, double value, double * array, int nx, int ny, int nz, double dx, double dy, double dz,
+                  double ox, double oy, double oz);
+double qo_gather3d(double x, double y, double z, const double * array, int nx, int ny, int nz, double dx, double dy, double dz,
+                   double ox, double oy, double oz);
+/* deposit_bunch_densities (src/System_3d.cpp:926-946): zeroes and fills rho_bunch, jx_bunch (nx*ny*nz each) */
+void qo_bunch_deposit_densities(const qo_bunch * b, const double * species_charge, int nx, int ny, int nz, double dx, double dy, double dz,
+                                double * rho_bunch, double * jx_bunch);
+/* deposit_wakefield_to_bunch (src/System_3d.cpp:843-860) */
+void qo_bunch_gather_fields(qo_bunch * b, int nx, int ny, int nz, double dx, double dy, double dz, const double * ex, const double * ey,
+                            const double * ez, const double * by, const double * bz, double field_schwinger);
+/* advance_bunch_particles with qed == false (src/System_3d.cpp:862-886) */
+void qo_bunch_advance(qo_bunch * b, const double * species_charge_to_mass, const int * species_is_photon, double dt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,4 +7,6 @@ reference's solver state.  CUDA only -- there is no CPU fallback.
 from .solver import (  # noqa: F401
     ABI_SYMBOLS, FIELDS_2D, FIELDS_3D, LIBRARY_PATH, PARTICLE_FIELDS, SLICE_FIELDS_3D, QpicError, QpicLibrary,
     WakefieldSolver, gaussian_laser_widths, grid_dimensions, load_library, powerlaw2d, wake_particle_lattice,
+    BUNCH_FIELDS, SPECIES, SPECIES_IDS, bunch_particle_lattice, bunch_profile_from_table, concatenate_bunches, cylindrical3d, gaussian3d,
+    parabolic3d, plasma_units,
 )

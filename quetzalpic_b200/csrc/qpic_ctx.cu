@@ -20,6 +20,7 @@
 #include "qpic_fft_pow2.cuh"
 #include "qpic_kernels.cuh"
 #include "qpic_dist.cuh"
+#include "qpic_bunch.cuh"
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -127,6 +128,17 @@ struct qpic_ctx {
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
     double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
     double * partials = nullptr;  // border-sum partials of the fused potential fix-up, [world][4] (inside the region when distributed)
+
+    // beam macroparticles and the cell lists of their deposit (qpic_bunch.cuh)
+    struct BunchState {
+        Bunch b = {};
+        BunchSpecies species = {};
+        int nspecies = 0;
+        int capacity = 0;
+        int *cell = nullptr, *tmp = nullptr, *perm = nullptr;     // per particle
+        int *count = nullptr, *start = nullptr, *sums = nullptr;  // per cell of the (nx, ny, nz) grid / per scan chunk
+        int nchunks = 0;
+    } bunch;
 
     // per-kernel profiling (qpic_profile_slices): an event after every launch of an eager slice
     bool profiling = false;
@@ -1265,8 +1277,9 @@ static int create_impl(qpic_ctx * c) {
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cur = g.nx - 1;
     c->target = g.nx - 1;
-    // the tile deposit needs unambiguous minimal-image cell offsets
-    c->fast_capable = !p.force_general_deposit && g.ny >= 8 && g.nz >= 8;
+    // the tile deposit needs unambiguous minimal-image cell offsets, and its halo cells (up to index TILE of a grid that fits in
+    // one tile) have to stay below 2 n for wrap_near: n >= 9
+    c->fast_capable = !p.force_general_deposit && g.ny >= 9 && g.nz >= 9;
     if (D.on && !(c->pow2_y && c->pow2_z)) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the power-of-two transform engine");
 #ifndef QPIC_EMU
     if (D.on) {
@@ -1910,6 +1923,164 @@ int qpic_dist_attach_pointers(qpic_ctx * c, void * const * regions) {
 
 // ---- in-graph timeline (only in the -DQPIC_TIMELINE development build, tools/timeline.py): globaltimer stamps that
 // block 0 / the last block of every kernel leave behind.  records = int64[4 * cap]: kid, kind, t0, t1 (ns).
+// ------------------------------------------------------------------------------------------------ beam particles
+
+int qpic_bunch_set_species(qpic_ctx * c, int count, const double * charge, const double * charge_to_mass_ratio, const int * is_photon) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (count < 1 || count > BUNCH_MAX_SPECIES || !charge || !charge_to_mass_ratio || !is_photon) {
+        return fail(c, QPIC_ERR_INVALID, "species table: 1..%d entries with charge, charge_to_mass_ratio and is_photon", BUNCH_MAX_SPECIES);
+    }
+    for (int s = 0; s < count; s++) {
+        c->bunch.species.charge[s] = charge[s];
+        c->bunch.species.charge_to_mass[s] = charge_to_mass_ratio[s];
+        c->bunch.species.is_photon[s] = is_photon[s] ? 1 : 0;
+    }
+    c->bunch.nspecies = count;
+    return QPIC_OK;
+}
+
+static double * bunch_array(qpic_ctx * c, qpic_bunch_field f) {
+    Bunch & b = c->bunch.b;
+    double * const table[QPIC_B_COUNT] = {b.x, b.y, b.z, b.px, b.py, b.pz, b.gamma, b.n, b.ex, b.ey, b.ez, b.by, b.bz, b.chi};
+    return (f >= 0 && f < QPIC_B_COUNT) ? table[f] : nullptr;
+}
+
+int qpic_bunch_init(qpic_ctx * c, size_t count, const double * x, const double * y, const double * z, const double * px, const double * py,
+                    const double * pz, const double * gamma, const double * n, const int * species_id) {
+    if (!c) return QPIC_ERR_INVALID;
+    if (c->dist.on) return fail(c, QPIC_ERR_UNSUPPORTED, "beam particles are not supported in a slab-decomposed sweep");
+    if (c->bunch.nspecies == 0) return fail(c, QPIC_ERR_STATE, "qpic_bunch_set_species has to be called before qpic_bunch_init");
+    if (count > 0 && (!x || !y || !z || !px || !py || !pz || !gamma || !n || !species_id)) return fail(c, QPIC_ERR_INVALID, "beam particle arrays are NULL");
+    if (count > (size_t)std::numeric_limits<int>::max() - 1024) return fail(c, QPIC_ERR_INVALID, "too many beam particles for 32-bit indices");
+    const size_t n3 = (size_t)c->g.nx * c->g.n2;
+    if (n3 > (size_t)std::numeric_limits<int>::max() - SCAN_CHUNK) return fail(c, QPIC_ERR_UNSUPPORTED, "grid too large for the 32-bit cell keys of the beam deposit");
+    for (size_t p = 0; p < count; p++) {
+        if (species_id[p] < 0 || species_id[p] >= c->bunch.nspecies) return fail(c, QPIC_ERR_INVALID, "beam particle %zu has species id %d outside the species table", p, species_id[p]);
+    }
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    // rho_bunch / jx_bunch enter the psi sources of the slice graph: their addresses have to exist when it is captured
+    if ((c->graph_exec || c->graph_exec_fast) && (!c->f3[QPIC_F3_RHO_BUNCH] || !c->f3[QPIC_F3_JX_BUNCH])) {
+        return fail(c, QPIC_ERR_STATE, "beam particles must be set up before the first qpic_step of a context");
+    }
+    if (!c->f3[QPIC_F3_RHO_BUNCH]) QPIC_TRY(dev_alloc(c, &c->f3[QPIC_F3_RHO_BUNCH], n3));
+    if (!c->f3[QPIC_F3_JX_BUNCH]) QPIC_TRY(dev_alloc(c, &c->f3[QPIC_F3_JX_BUNCH], n3));
+    qpic_ctx::BunchState & S = c->bunch;
+    if ((int)count > S.capacity || !S.b.x) {
+        const size_t cap = count ? count : 1;
+        double ** arrays[QPIC_B_COUNT] = {&S.b.x, &S.b.y, &S.b.z, &S.b.px, &S.b.py, &S.b.pz, &S.b.gamma, &S.b.n, &S.b.ex, &S.b.ey, &S.b.ez, &S.b.by, &S.b.bz, &S.b.chi};
+        for (double ** a : arrays) QPIC_TRY(dev_alloc(c, a, cap));
+        QPIC_TRY(dev_alloc(c, &S.b.species, cap));
+        QPIC_TRY(dev_alloc(c, &S.cell, cap));
+        QPIC_TRY(dev_alloc(c, &S.tmp, cap));
+        QPIC_TRY(dev_alloc(c, &S.perm, cap));
+        S.capacity = (int)cap;
+    }
+    if (!S.count) {
+        S.nchunks = (int)((n3 + SCAN_CHUNK - 1) / SCAN_CHUNK);
+        QPIC_TRY(dev_alloc(c, &S.count, n3));
+        QPIC_TRY(dev_alloc(c, &S.start, n3 + 1));
+        QPIC_TRY(dev_alloc(c, &S.sums, (size_t)S.nchunks));
+    }
+    S.b.np = (int)count;
+    if (count) {
+        const double * src[8] = {x, y, z, px, py, pz, gamma, n};
+        double * dst[8] = {S.b.x, S.b.y, S.b.z, S.b.px, S.b.py, S.b.pz, S.b.gamma, S.b.n};
+        for (int a = 0; a < 8; a++) QPIC_CUDA(c, cudaMemcpyAsync(dst[a], src[a], sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+        QPIC_CUDA(c, cudaMemcpyAsync(S.b.species, species_id, sizeof(int) * count, cudaMemcpyHostToDevice, c->stream));
+        double * zeroed[6] = {S.b.ex, S.b.ey, S.b.ez, S.b.by, S.b.bz, S.b.chi};  // bunch_particle_3d's defaults (src/containers.h:54-59)
+        for (double * a : zeroed) QPIC_CUDA(c, cudaMemsetAsync(a, 0, sizeof(double) * count, c->stream));
+    }
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+size_t qpic_bunch_count(const qpic_ctx * c) { return c ? (size_t)c->bunch.b.np : 0; }
+
+int qpic_bunch_deposit_densities(qpic_ctx * c) {
+    if (!c) return QPIC_ERR_INVALID;
+    qpic_ctx::BunchState & S = c->bunch;
+    if (!S.count) return fail(c, QPIC_ERR_STATE, "qpic_bunch_deposit_densities called before qpic_bunch_init");
+    if (c->began && !c->finished) return fail(c, QPIC_ERR_STATE, "the bunch densities cannot change during a sweep");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    cudaStream_t st = c->stream;
+    const int n3 = c->g.nx * c->g.n2;
+    const int np = S.b.np;
+    QPIC_CUDA(c, cudaMemsetAsync(S.count, 0, sizeof(int) * (size_t)n3, st));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_bunch_locate_count, blocks_for(np, 256), 256, 0, st, S.b, c->g, S.cell, S.count);
+        QPIC_TRY(check_launch(c, "k_bunch_locate_count"));
+    }
+    QPIC_LAUNCH(k_scan_chunk_sums, S.nchunks, SCAN_THREADS, 0, st, c->ctl_scratch, S.count, n3, S.sums);
+    QPIC_TRY(check_launch(c, "k_scan_chunk_sums"));
+    QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, st, c->ctl_scratch, S.sums, S.nchunks);
+    QPIC_TRY(check_launch(c, "k_scan_sums"));
+    QPIC_LAUNCH(k_bunch_scan_apply, S.nchunks, SCAN_THREADS, 0, st, S.count, n3, S.sums, S.start);
+    QPIC_TRY(check_launch(c, "k_bunch_scan_apply"));
+    if (np > 0) {
+        QPIC_LAUNCH_FLAT(k_bunch_fill, blocks_for(np, 256), 256, 0, st, np, S.cell, S.count, S.tmp);
+        QPIC_TRY(check_launch(c, "k_bunch_fill"));
+        QPIC_LAUNCH_FLAT(k_bunch_rank, blocks_for(np, 256), 256, 0, st, np, S.cell, S.start, S.tmp, S.perm);
+        QPIC_TRY(check_launch(c, "k_bunch_rank"));
+    }
+    int blocks = blocks_for((size_t)n3, 256);
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    QPIC_LAUNCH_FLAT(k_bunch_deposit, blocks, 256, 0, st, c->g, S.b, S.species, S.start, S.perm, c->f3[QPIC_F3_RHO_BUNCH], c->f3[QPIC_F3_JX_BUNCH]);
+    QPIC_TRY(check_launch(c, "k_bunch_deposit"));
+    QPIC_CUDA(c, cudaStreamSynchronize(st));
+    return QPIC_OK;
+}
+
+int qpic_bunch_gather_fields(qpic_ctx * c, double field_schwinger) {
+    if (!c) return QPIC_ERR_INVALID;
+    qpic_ctx::BunchState & S = c->bunch;
+    if (!S.count) return fail(c, QPIC_ERR_STATE, "qpic_bunch_gather_fields called before qpic_bunch_init");
+    if (c->began && !c->finished) return fail(c, QPIC_ERR_STATE, "qpic_bunch_gather_fields called during a sweep (qpic_finish first)");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (S.b.np > 0) {
+        QPIC_LAUNCH_FLAT(k_bunch_gather, blocks_for(S.b.np, 128), 128, 0, c->stream, S.b, c->g, c->f3[QPIC_F3_EX], c->f3[QPIC_F3_EY], c->f3[QPIC_F3_EZ],
+                         c->f3[QPIC_F3_BY], c->f3[QPIC_F3_BZ], field_schwinger);
+        QPIC_TRY(check_launch(c, "k_bunch_gather"));
+    }
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_bunch_advance(qpic_ctx * c, double dt) {
+    if (!c) return QPIC_ERR_INVALID;
+    qpic_ctx::BunchState & S = c->bunch;
+    if (!S.count) return fail(c, QPIC_ERR_STATE, "qpic_bunch_advance called before qpic_bunch_init");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    if (S.b.np > 0) {
+        QPIC_LAUNCH_FLAT(k_bunch_advance, blocks_for(S.b.np, 256), 256, 0, c->stream, S.b, S.species, dt);
+        QPIC_TRY(check_launch(c, "k_bunch_advance"));
+    }
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_bunch_download(qpic_ctx * c, qpic_bunch_field f, double * dst) {
+    if (!c) return QPIC_ERR_INVALID;
+    double * src = bunch_array(c, f);
+    if (!src) return fail(c, QPIC_ERR_INVALID, "bad beam particle field id, or no beam particles were set up");
+    if (c->bunch.b.np == 0) return QPIC_OK;
+    if (!dst) return fail(c, QPIC_ERR_INVALID, "dst is NULL");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)c->bunch.b.np, cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+int qpic_bunch_upload(qpic_ctx * c, qpic_bunch_field f, const double * src) {
+    if (!c) return QPIC_ERR_INVALID;
+    double * dst = bunch_array(c, f);
+    if (!dst || !src) return fail(c, QPIC_ERR_INVALID, "bad beam particle field id / NULL src, or no beam particles were set up");
+    if (c->bunch.b.np == 0) return QPIC_OK;
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)c->bunch.b.np, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
 int qpic_timeline_reset(qpic_ctx * c) {
 #ifdef QPIC_TIMELINE
     const int zero = 0;

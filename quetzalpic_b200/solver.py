@@ -23,6 +23,10 @@ FIELDS_2D = ["psi", "psi_prev", "psi_middle", "rho", "jx", "jy", "jz", "jy_next"
 FIELDS_3D = ["aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "by", "bz"]
 SLICE_FIELDS_3D = ["psi", "rho", "jx", "jy", "jz"]  # filled slice by slice, like Output_writer::write_slice
 PARTICLE_FIELDS = ["y", "z", "py", "pz", "n", "gamma", "px"]
+BUNCH_FIELDS = ["x", "y", "z", "px", "py", "pz", "gamma", "n", "ex", "ey", "ez", "by", "bz", "chi"]  # bunch_particle_3d
+# built-in species, ids 0-3 (reference src/Config_reader.cpp:19-22): name -> (charge, mass, is_photon)
+SPECIES = {"electron": (-1.0, 1.0, False), "positron": (1.0, 1.0, False), "proton": (1.0, 1836.15267343, False), "photon": (0.0, 0.0, True)}
+SPECIES_IDS = {name: i for i, name in enumerate(SPECIES)}
 
 # every symbol include/qpic_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
@@ -35,6 +39,8 @@ ABI_SYMBOLS = [
     "qpic_profile_slices", "qpic_upload_a_sqr_slices", "qpic_download_slices3d", "qpic_alloc_pinned", "qpic_free_pinned",
     "qpic_fast_path_aborts", "qpic_wait_transfers", "qpic_timeline_reset", "qpic_timeline_read", "qpic_timeline_kernel_name",
     "qpic_dist_region_bytes", "qpic_dist_region", "qpic_dist_ipc_handle", "qpic_dist_attach_ipc", "qpic_dist_attach_pointers", "qpic_dist_row_range", "qpic_download_xy_cut",
+    "qpic_bunch_set_species", "qpic_bunch_init", "qpic_bunch_count", "qpic_bunch_deposit_densities", "qpic_bunch_gather_fields",
+    "qpic_bunch_advance", "qpic_bunch_download", "qpic_bunch_upload",
 ]
 
 
@@ -122,6 +128,15 @@ class QpicLibrary:
         L.qpic_dist_attach_ipc.argtypes = [vp, vp]
         L.qpic_dist_attach_pointers.argtypes = [vp, ctypes.POINTER(vp)]
         L.qpic_dist_row_range.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.qpic_bunch_set_species.argtypes = [vp, ci, vp, vp, vp]
+        L.qpic_bunch_init.argtypes = [vp, ctypes.c_size_t] + [vp] * 9
+        L.qpic_bunch_count.argtypes = [vp]
+        L.qpic_bunch_count.restype = ctypes.c_size_t
+        L.qpic_bunch_deposit_densities.argtypes = [vp]
+        L.qpic_bunch_gather_fields.argtypes = [vp, dbl]
+        L.qpic_bunch_advance.argtypes = [vp, dbl]
+        L.qpic_bunch_download.argtypes = [vp, ci, vp]
+        L.qpic_bunch_upload.argtypes = [vp, ci, vp]
         self.L = L
 
     def pinned_array(self, shape):
@@ -179,6 +194,89 @@ def powerlaw2d(power, radius, y0, z0, min_factor=0.0, max_factor=1e10, amplitude
         value = np.maximum(value, min_factor)
         return amplitude * value
     return profile
+
+
+def plasma_units(base_frequency_SI=1.0):
+    """Plasma_units (reference src/Plasma_units.h:16-33, constants src/constants.h:3-10): the two derived quantities the beam
+    path needs -- field_schwinger (chi) and number_density_norm (the macro-particle weight written to Bunch_NNN.h5)."""
+    pi = 3.141592653589793238
+    electron_mass, planck, c_light, e_charge = 9.1093837015e-28, 6.62607015e-27, 29979245800.0, 4.803204672997e-10
+    hbar = planck / (2 * pi)
+    frequency = float(base_frequency_SI)
+    wavenumber = frequency / c_light
+    density = electron_mass * frequency * frequency / (4 * pi * e_charge * e_charge)
+    return dict(frequency=frequency, plasma_wavenumber=wavenumber, wavelength=2 * pi / wavenumber, density=density,
+                number_density_norm=density / wavenumber / wavenumber / wavenumber,
+                field_schwinger=electron_mass * c_light * c_light / hbar / frequency)
+
+
+def gaussian3d(amplitude, width, r0):
+    """reference src/profiles.cpp:4-11 (vectorised)"""
+    def profile(x, y, z):
+        return amplitude * np.exp(-(x - r0[0]) * (x - r0[0]) / width[0] / width[0] - (y - r0[1]) * (y - r0[1]) / width[1] / width[1]
+                                  - (z - r0[2]) * (z - r0[2]) / width[2] / width[2])
+    return profile
+
+
+def parabolic3d(amplitude, xsize, rsize, r0):
+    """reference src/profiles.cpp:19-31"""
+    def profile(x, y, z):
+        r_squared = (y - r0[1]) * (y - r0[1]) + (z - r0[2]) * (z - r0[2])
+        x_rel_squared = (x - r0[0]) * (x - r0[0])
+        inside = (r_squared <= rsize * rsize) & (x_rel_squared < xsize * xsize)
+        return np.where(inside, amplitude * (1 - x_rel_squared / xsize / xsize) * (1 - r_squared / rsize / rsize), 0.0)
+    return profile
+
+
+def cylindrical3d(amplitude, xsize, rsize, r0):
+    """reference src/profiles.cpp:33-45"""
+    def profile(x, y, z):
+        r_squared = (y - r0[1]) * (y - r0[1]) + (z - r0[2]) * (z - r0[2])
+        x_rel_squared = (x - r0[0]) * (x - r0[0])
+        return np.where((r_squared <= rsize * rsize) & (x_rel_squared < xsize * xsize), amplitude, 0.0)
+    return profile
+
+
+def bunch_profile_from_table(table, l):
+    """The density profile Config_reader::parse_bunch_table builds from a [bunch] table (reference src/Config_reader.cpp:147-182)."""
+    shape = table["shape"]
+    y0, z0 = float(table.get("y0", 0.5 * l[1])), float(table.get("z0", 0.5 * l[2]))
+    if shape == "gaussian":
+        s = np.sqrt(8.0)
+        width = (table["xsigma"] / s, table["ysigma"] / s, table["zsigma"] / s)
+        return gaussian3d(float(table["rho0"]), width, (float(table.get("x0", table["xsigma"])), y0, z0))
+    if shape == "parabolic":
+        return parabolic3d(float(table["rho0"]), float(table["xsize"]), float(table["rsize"]), (float(table["x0"]), y0, z0))
+    if shape == "cylindrical":
+        return cylindrical3d(float(table["rho0"]), float(table["xsize"]), float(table["rsize"]), (float(table["x0"]), y0, z0))
+    raise ValueError(f'Bunch shape "{shape}" is not supported, use "gaussian", "parabolic", or "cylindrical".')
+
+
+def bunch_particle_lattice(n, l, ppc, rho, gamma, species="electron"):
+    """The particles System_3d::init_bunch_particles creates for one bunch (reference src/System_3d.cpp:767-803): a regular
+    lattice of ppc sub-cell points, kept where rho(x, y, z) > 0, x-major order; px = sqrt(gamma^2 - 1) (photons: gamma).
+    Returns a dict of the BUNCH_FIELDS that are set plus "species_id"."""
+    nx, ny, nz = n
+    dx, dy, dz = l[0] / nx, l[1] / ny, l[2] / nz
+    xx = (np.arange(ppc[0] * nx) + 0.5) * dx / ppc[0]
+    yy = (np.arange(ppc[1] * ny) + 0.5) * dy / ppc[1]
+    zz = (np.arange(ppc[2] * nz) + 0.5) * dz / ppc[2]
+    x, y, z = (a.ravel() for a in np.meshgrid(xx, yy, zz, indexing="ij"))
+    value = np.asarray(rho(x, y, z), dtype=np.float64)
+    keep = value > 0.0
+    count = int(keep.sum())
+    sid = SPECIES_IDS[species]
+    px0 = gamma if SPECIES[species][2] else np.sqrt(gamma * gamma - 1)
+    return dict(x=x[keep].copy(), y=y[keep].copy(), z=z[keep].copy(), px=np.full(count, px0), py=np.zeros(count), pz=np.zeros(count),
+                gamma=np.full(count, float(gamma)), n=(value[keep] / ppc[0] / ppc[1] / ppc[2]).copy(),
+                species_id=np.full(count, sid, dtype=np.int32))
+
+
+def concatenate_bunches(bunches):
+    """bunch_particles of System_3d: the bunches one after another (reference src/System_3d.cpp:157-162)"""
+    keys = ["x", "y", "z", "px", "py", "pz", "gamma", "n", "species_id"]
+    return {k: np.concatenate([b[k] for b in bunches]) if bunches else np.zeros(0, dtype=np.int32 if k == "species_id" else np.float64)
+            for k in keys}
 
 
 def gaussian_laser_widths(xsigma, ysigma, zsigma):
@@ -397,6 +495,45 @@ class WakefieldSolver:
         if a.shape != (self.particle_count,):
             raise ValueError("particle arrays have shape (particle_count,)")
         self._check(self.lib.L.qpic_upload_particles(self.ctx, PARTICLE_FIELDS.index(name), a.ctypes.data))
+
+    # -- beam particles: the part of System_3d::run around solve_wakefield (reference src/System_3d.cpp:199-236)
+    def bunch_init(self, particles, species=None):
+        """particles: dict with x, y, z, px, py, pz, gamma, n, species_id (see bunch_particle_lattice / concatenate_bunches);
+        species: list of (charge, mass, is_photon), default the four built-ins"""
+        table = list(SPECIES.values()) if species is None else list(species)
+        charge = np.array([s[0] for s in table], dtype=np.float64)
+        cmr = np.array([0.0 if s[1] == 0.0 else s[0] / s[1] for s in table], dtype=np.float64)  # src/Species_register.h:12-13
+        photon = np.array([1 if s[2] else 0 for s in table], dtype=np.int32)
+        self._check(self.lib.L.qpic_bunch_set_species(self.ctx, len(table), charge.ctypes.data, cmr.ctypes.data, photon.ctypes.data))
+        arrs = [np.ascontiguousarray(particles[k], dtype=np.float64) for k in ["x", "y", "z", "px", "py", "pz", "gamma", "n"]]
+        sid = np.ascontiguousarray(particles["species_id"], dtype=np.int32)
+        if any(a.shape != (sid.size,) for a in arrs):
+            raise ValueError("beam particle arrays must be 1-D and of equal length")
+        self._check(self.lib.L.qpic_bunch_init(self.ctx, sid.size, *[a.ctypes.data for a in arrs], sid.ctypes.data))
+
+    @property
+    def bunch_count(self):
+        return self.lib.L.qpic_bunch_count(self.ctx)
+
+    def deposit_bunch_densities(self):
+        self._check(self.lib.L.qpic_bunch_deposit_densities(self.ctx))
+
+    def deposit_wakefield_to_bunch(self, field_schwinger):
+        self._check(self.lib.L.qpic_bunch_gather_fields(self.ctx, float(field_schwinger)))
+
+    def advance_bunch_particles(self, dt):
+        self._check(self.lib.L.qpic_bunch_advance(self.ctx, float(dt)))
+
+    def bunch(self, name):
+        out = np.empty(self.bunch_count)
+        self._check(self.lib.L.qpic_bunch_download(self.ctx, BUNCH_FIELDS.index(name), out.ctypes.data))
+        return out
+
+    def set_bunch(self, name, value):
+        a = np.ascontiguousarray(value, dtype=np.float64)
+        if a.shape != (self.bunch_count,):
+            raise ValueError("beam particle arrays have shape (bunch_count,)")
+        self._check(self.lib.L.qpic_bunch_upload(self.ctx, BUNCH_FIELDS.index(name), a.ctypes.data))
 
     # -- slab-decomposed multi-GPU sweep (see quetzalpic_b200/dist.py)
     @property

@@ -4,7 +4,8 @@ import re
 
 import numpy as np
 
-from quetzalpic_b200 import gaussian_laser_widths, grid_dimensions, powerlaw2d, wake_particle_lattice
+from quetzalpic_b200 import (SPECIES, bunch_particle_lattice, bunch_profile_from_table, concatenate_bunches, gaussian_laser_widths,
+                             grid_dimensions, plasma_units, powerlaw2d, wake_particle_lattice)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -16,6 +17,11 @@ def parse_toml(path):
     for line in open(path):
         line = line.split("#", 1)[0].strip()
         if not line:
+            continue
+        m = re.match(r"\[\[(\w+)\]\]", line)
+        if m:  # array of tables
+            cur = {}
+            root.setdefault(m.group(1), []).append(cur)
             continue
         m = re.match(r"\[(\w+)\]", line)
         if m:
@@ -60,6 +66,40 @@ class Case:
                 rho0 = float(pl.get("rho0", -1))
         nx, ny, nz = self.n
         self.particles = wake_particle_lattice(ny, nz, l[1], l[2], self.ppcy, self.ppcz, profile=profile, rho0=rho0)
+
+    # -- beam side of System_3d (reference src/System_3d.cpp:106-162, :199-236)
+    def bunch_particles(self):
+        """bunch_particles of System_3d for the [bunch] / [[bunch]] tables of the input"""
+        tables = self.cfg.get("bunch", [])
+        tables = tables if isinstance(tables, list) else [tables]
+        bunches = []
+        for t in tables:
+            ppc = (int(t.get("ppcx", 1)), int(t.get("ppcy", 1)), int(t.get("ppcz", 1)))
+            bunches.append(bunch_particle_lattice(self.n, self.l, ppc, bunch_profile_from_table(t, self.l), float(t["gamma"]),
+                                                  t.get("species", "electron")))
+        return concatenate_bunches(bunches)
+
+    @property
+    def time_iterations(self):
+        dt = float(self.cfg.get("dt", self.l[0]))
+        return int(float(self.cfg.get("t_end", 0.0)) / dt) + 1, dt
+
+    def run_time_loop(self, make_backend, on_iteration):
+        """System_3d::run (reference src/System_3d.cpp:199-236) on either backend.  make_backend() -> (solver, beam) where
+        solver has init_wake_particles / solve_wakefield and beam has deposit_bunch_densities / deposit_wakefield_to_bunch /
+        advance_bunch_particles; on_iteration(ti, solver, beam) is called where the reference writes Bunch_NNN."""
+        iterations, dt = self.time_iterations
+        units = plasma_units(float(self.cfg.get("base_frequency_SI", 1.0)))
+        solver, beam = make_backend()
+        for ti in range(iterations):
+            beam.deposit_bunch_densities()
+            solver.init_wake_particles(*self.particles)  # solve_wakefield re-creates the plasma lattice, :262
+            solver.solve_wakefield()
+            beam.deposit_wakefield_to_bunch(units["field_schwinger"])
+            on_iteration(ti, solver, beam)
+            if ti < iterations - 1:
+                beam.advance_bunch_particles(dt)
+        return solver, beam
 
     @classmethod
     def from_toml(cls, name):

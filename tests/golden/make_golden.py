@@ -9,6 +9,8 @@ atomic deposits land in index order and the output is reproducible to the last b
 
 Fixtures:
   <name>.npz for the tiny inputs     every dataset of Fields_000.h5 (full 3-D) and Fields_xy_000.h5 + attributes
+  tiny_beam.npz                      beam-driven run over three time iterations (two charged bunches + a photon beam): every
+                                     dataset of Fields_NNN.h5 and Bunch_NNN.h5 per iteration   (python make_golden.py beam)
   laser_test_summary.npz             the shipped inputs/test/laser_test.toml (200^3): per-field min/max/L2 norm,
                                      per-slice L2 norms, on-axis lines [:, ny/2, nz/2], transverse lines through
                                      slice 100, and the value at [100,100,100]
@@ -59,9 +61,31 @@ def collect(workdir, log):
     return data
 
 
+BUNCH_NAMES = ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi", "weight"]
+
+
+def collect_time_loop(workdir, log, iterations):
+    """multi-iteration run with beam output: Fields_NNN (3-D) and Bunch_NNN of every time iteration"""
+    data = {"stdout": np.array(log), "iterations": np.array(iterations)}
+    for t in range(iterations):
+        for nm in NAMES_3D:
+            data[f"it{t}/f3/{nm}"] = np.load(os.path.join(workdir, f"Fields_{t:03d}.h5.d", nm + ".npy"))
+        for nm in BUNCH_NAMES:
+            data[f"it{t}/bunch/{nm}"] = np.load(os.path.join(workdir, f"Bunch_{t:03d}.h5.d", nm + ".npy"))
+        data[f"it{t}/photons"] = np.array(sorted(f for f in os.listdir(os.path.join(workdir, f"Photons_{t:03d}.h5.d")) if f.endswith(".npy")))
+    return data
+
+
 def main():
     if not os.path.exists(REF_EXE):
         sys.exit("build the reference first: make -C oracle ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "beam":  # only the time-loop fixture (added after the others)
+        with tempfile.TemporaryDirectory() as wd:
+            log = run_reference(os.path.join(HERE, "inputs", "tiny_beam.toml"), wd)
+            data = collect_time_loop(wd, log, 3)
+        np.savez_compressed(os.path.join(HERE, "tiny_beam.npz"), **data)
+        print("tiny_beam", data["it0/f3/psi"].shape, data["it0/bunch/x"].shape)
+        return
     for name in ["tiny_laser", "tiny_profile", "tiny_bunch", "tiny_bunch_stop"]:
         with tempfile.TemporaryDirectory() as wd:
             log = run_reference(os.path.join(HERE, "inputs", name + ".toml"), wd)

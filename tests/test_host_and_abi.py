@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = qp.load_library()
     for sym in declared:
         assert hasattr(lib.L, sym), sym
-    assert lib.L.qpic_abi_version() == 2
+    assert lib.L.qpic_abi_version() == 3
 
 
 def test_library_is_cuda_only_and_fails_loudly_without_device():

@@ -168,3 +168,38 @@ def test_linear_wake_known_answer():
     theory = np.array([np.trapezoid(0.5 * a[i:] * np.sin(x[i:] - x[i]), x[i:]) for i in range(nx)])
     assert rel_l2(psi, theory) < 0.08
     assert abs(np.abs(psi).max() / np.abs(theory).max() - 1.0) < 0.01
+
+
+def test_oracle_beam_time_loop_reproduces_reference(golden_dir):
+    """System_3d::run with beam particles (deposit_bunch_densities -> solve_wakefield -> deposit_wakefield_to_bunch ->
+    advance_bunch_particles) over three time iterations: the restatement (oracle/qo_bunch.c + qpic_oracle.c) must reproduce
+    Fields_NNN and Bunch_NNN of the unmodified reference.  Tolerance: the beam lattice is built with numpy's exp instead of
+    libm's (last-bit differences in the weights of the Gaussian bunch); everything else is the same arithmetic."""
+    from oracle.qo import OracleBunch
+    from quetzalpic_b200 import SPECIES, plasma_units
+    g = np.load(os.path.join(golden_dir, "tiny_beam.npz"))
+    case = Case.from_toml("tiny_beam")
+    particles = case.bunch_particles()
+    assert particles["x"].shape == g["it0/bunch/x"].shape
+    weight_norm = np.prod([case.l[a] / case.n[a] for a in range(3)]) * plasma_units(1.0)["number_density_norm"]
+    seen = []
+
+    def make_backend():
+        o = case.make_oracle()
+        return o, OracleBunch(o, particles, list(SPECIES.values()))
+
+    def check(ti, o, beam):
+        seen.append(ti)
+        for f in NAMES_3D + ["rho_bunch", "jx_bunch"]:
+            assert slice_rel_l2(o.field3d(f), g[f"it{ti}/f3/{f}"]) < 1e-13, (ti, f)
+        for f in NAMES_SLICE:
+            assert slice_rel_l2(o.field3d(f, per_slice=True), g[f"it{ti}/f3/{f}"]) < 1e-13, (ti, f)
+        for f in ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi"]:
+            assert rel_l2(beam[f], g[f"it{ti}/bunch/{f}"]) < 1e-13, (ti, f)
+        assert rel_l2(beam["n"] * weight_norm, g[f"it{ti}/bunch/weight"]) < 1e-13
+
+    case.run_time_loop(make_backend, check)
+    assert seen == [0, 1, 2]
+    # the beam moved and its fields are not trivial
+    assert np.abs(g["it2/bunch/py"]).max() > 1.0 and np.abs(g["it2/bunch/y"] - g["it0/bunch/y"]).max() > 1e-3
+    assert len(g["it0/photons"]) == 0  # Photons_NNN.h5 is created but stays empty without qed
