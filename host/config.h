@@ -131,6 +131,38 @@ struct Output_parameters {
     double z0 = 0;
 };
 
+// beam density profiles, reference src/profiles.cpp:4-45 (same expression order)
+inline std::function<double(double, double, double)> gaussian3d(double amplitude, double wx, double wy, double wz, double x0, double y0, double z0) {
+    return [=](double x, double y, double z) {
+        return amplitude * std::exp(-(x - x0) * (x - x0) / wx / wx - (y - y0) * (y - y0) / wy / wy - (z - z0) * (z - z0) / wz / wz);
+    };
+}
+inline std::function<double(double, double, double)> parabolic3d(double amplitude, double xsize, double rsize, double x0, double y0, double z0) {
+    return [=](double x, double y, double z) {
+        const double r_squared = (y - y0) * (y - y0) + (z - z0) * (z - z0);
+        const double x_rel_squared = (x - x0) * (x - x0);
+        if ((r_squared <= rsize * rsize) && (x_rel_squared < xsize * xsize)) {
+            return amplitude * (1 - x_rel_squared / xsize / xsize) * (1 - r_squared / rsize / rsize);
+        }
+        return 0.0;
+    };
+}
+inline std::function<double(double, double, double)> cylindrical3d(double amplitude, double xsize, double rsize, double x0, double y0, double z0) {
+    return [=](double x, double y, double z) {
+        const double r_squared = (y - y0) * (y - y0) + (z - z0) * (z - z0);
+        const double x_rel_squared = (x - x0) * (x - x0);
+        return ((r_squared <= rsize * rsize) && (x_rel_squared < xsize * xsize)) ? amplitude : 0.0;
+    };
+}
+
+// Bunch_parameters of the reference (src/System_parameters.h)
+struct Bunch_parameters {
+    int ppcx = 1, ppcy = 1, ppcz = 1;
+    double gamma = 1;
+    std::function<double(double, double, double)> rho;
+    int species_id = 0;
+};
+
 struct System_parameters {
     double lx = 0, ly = 0, lz = 0, dx = 0, dy = 0, dz = 0, dt = 0, t_end = 0;
     int ppcy = 1, ppcz = 1, magnetic_field_iterations = 1;
@@ -139,6 +171,7 @@ struct System_parameters {
     Laser_gaussian laser;
     std::function<double(double, double)> plasma_profile;  // (y, z) -> density, reference default constant2d(-1)
     int bunch_count = 0;
+    std::vector<Bunch_parameters> bunch_parameters_array;
     Output_parameters output;
     Species_register species;
 };
@@ -243,30 +276,40 @@ private:
         L.amplitude = 0.5 * a0 * a0;
     }
 
+    // Config_reader::parse_bunch_table (reference src/Config_reader.cpp:138-185): same keys, defaults and echo order
     void echo_bunch_table(const toml_lite::Table & t) {
-        optional<int>("ppcx", 1, t);
-        optional<int>("ppcy", 1, t);
-        optional<int>("ppcz", 1, t);
-        required<double>("gamma", t);
+        Bunch_parameters b;
+        b.ppcx = optional<int>("ppcx", 1, t);
+        b.ppcy = optional<int>("ppcy", 1, t);
+        b.ppcz = optional<int>("ppcz", 1, t);
+        b.gamma = required<double>("gamma", t);
         const std::string shape = required<std::string>("shape", t);
         if (shape == "gaussian") {
-            required<double>("rho0", t);
+            const double rho0 = required<double>("rho0", t);
             const double xsigma = required<double>("xsigma", t);
-            required<double>("ysigma", t);
-            required<double>("zsigma", t);
-            optional<double>("x0", xsigma, t);
+            const double ysigma = required<double>("ysigma", t);
+            const double zsigma = required<double>("zsigma", t);
+            const double x0 = optional<double>("x0", xsigma, t);
+            const double y0 = optional<double>("y0", 0.5 * params.ly, t);
+            const double z0 = optional<double>("z0", 0.5 * params.lz, t);
+            // full width at 1/e^2 -> Gauss parameter (:157-158)
+            b.rho = gaussian3d(rho0, xsigma / std::sqrt(8.0), ysigma / std::sqrt(8.0), zsigma / std::sqrt(8.0), x0, y0, z0);
         } else if (shape == "parabolic" || shape == "cylindrical") {
-            required<double>("rho0", t);
-            required<double>("xsize", t);
-            required<double>("rsize", t);
-            required<double>("x0", t);
+            const double rho0 = required<double>("rho0", t);
+            const double xsize = required<double>("xsize", t);
+            const double rsize = required<double>("rsize", t);
+            const double x0 = required<double>("x0", t);
+            const double y0 = optional<double>("y0", 0.5 * params.ly, t);
+            const double z0 = optional<double>("z0", 0.5 * params.lz, t);
+            b.rho = shape == "parabolic" ? parabolic3d(rho0, xsize, rsize, x0, y0, z0) : cylindrical3d(rho0, xsize, rsize, x0, y0, z0);
         } else {
             throw Config_exception("Bunch shape \"" + shape + "\" is not supported, use \"gaussian\", \"parabolic\", or \"cylindrical\".");
         }
-        optional<double>("y0", 0.5 * params.ly, t);
-        optional<double>("z0", 0.5 * params.lz, t);
         const std::string sp = optional<std::string>("species", "electron", t);
-        (void)params.species.find_species(sp);
+        b.species_id = params.species.find_species(sp);
+        // the reference stores the -1 of an unknown name and indexes the register with it (undefined behaviour): refuse instead
+        if (b.species_id < 0) throw Config_exception("Species \"" + sp + "\" is not registered");
+        params.bunch_parameters_array.push_back(b);
         params.bunch_count++;
     }
 

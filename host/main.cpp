@@ -5,7 +5,8 @@
 // the TOML keys / defaults / stdout echo (src/Config_reader.cpp), the banner printed by System_3d's constructor
 // (src/System_3d.cpp:91-152), the per-iteration messages of System_3d::run (:199-236) and the output datasets
 // (src/Output_writer.cpp; see output_npy.h for the file format).  solve_wakefield itself runs on the device.
-// Beam drivers ([bunch]) need the bunch deposit / push path, which is a "next" row: such inputs are refused.
+// Beam drivers ([bunch] / [[bunch]]): the particles are built here as System_3d::init_bunch_particles does and live on the device
+// (qpic_bunch_*); System_3d::run's time loop (src/System_3d.cpp:199-236) is the loop below.  qed = true is refused (not built).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -80,10 +81,37 @@ int main(int argc, char const * argv[]) {
     }
     out << "----------------------------------------" << std::endl;
 
-    if (params.bunch_count > 0) {
-        out << "This driver covers the plasma-wake path; [bunch] drivers need the bunch deposit / push path, which is not built yet." << std::endl;
-        return 2;
+    // beam particles, System_3d::count_bunch_particles / init_bunch_particles (src/System_3d.cpp:750-803): a lattice of ppc points per
+    // cell, kept where rho > 0, x-major order, bunch after bunch
+    struct {
+        std::vector<double> x, y, z, px, py, pz, gamma, n;
+        std::vector<int> species_id;
+    } beam;
+    for (const Bunch_parameters & b : params.bunch_parameters_array) {
+        const bool photon = params.species.get_species()[b.species_id].is_photon;
+        for (int i = 0; i < b.ppcx * nx; i++) {
+            for (int j = 0; j < b.ppcy * ny; j++) {
+                for (int k = 0; k < b.ppcz * nz; k++) {
+                    const double x = (i + 0.5) * dx / b.ppcx;
+                    const double y = (j + 0.5) * dy / b.ppcy;
+                    const double z = (k + 0.5) * dz / b.ppcz;
+                    const double value = b.rho(x, y, z);
+                    if (value > 0.0) {
+                        beam.x.push_back(x);
+                        beam.y.push_back(y);
+                        beam.z.push_back(z);
+                        beam.px.push_back(photon ? b.gamma : std::sqrt(b.gamma * b.gamma - 1));
+                        beam.py.push_back(0);
+                        beam.pz.push_back(0);
+                        beam.gamma.push_back(b.gamma);
+                        beam.n.push_back(value / b.ppcx / b.ppcy / b.ppcz);
+                        beam.species_id.push_back(b.species_id);
+                    }
+                }
+            }
+        }
     }
+    const size_t beam_count = beam.x.size();
 
     // plasma macro-particle lattice, System_3d::count_wake_particles / init_wake_particles (src/System_3d.cpp:708-748)
     std::vector<double> py, pz, pn;
@@ -104,13 +132,14 @@ int main(int argc, char const * argv[]) {
     const long array2d_memory = 12l * sizeof(double) * ny * nz;
     const long array3d_memory = 9l * sizeof(double) * nx * ny * nz;
     const long wake_particle_memory = 88l * static_cast<long>(py.size());  // sizeof(wake_particle_2d), src/containers.h:31-43
+    const long bunch_particle_memory = 120l * static_cast<long>(beam_count);  // sizeof(bunch_particle_3d), src/containers.h:45-61
     out << "Expected RAM usage:\n";
     out << "3D arrays:       " << memory_formatter(array3d_memory) << "\n"
         << "2D arrays:       " << memory_formatter(array2d_memory) << "\n"
         << "Fourier:         " << memory_formatter(fourier_memory) << "\n"
         << "Wake particles:  " << memory_formatter(wake_particle_memory) << "\n"
-        << "Bunch particles: " << memory_formatter(0) << "\n"
-        << "Total:           " << memory_formatter(array2d_memory + array3d_memory + wake_particle_memory + fourier_memory) << std::endl;
+        << "Bunch particles: " << memory_formatter(bunch_particle_memory) << "\n"
+        << "Total:           " << memory_formatter(array2d_memory + array3d_memory + wake_particle_memory + bunch_particle_memory + fourier_memory) << std::endl;
     out << "----------------------------------------" << std::endl;
 
     qpic_params p;
@@ -139,9 +168,28 @@ int main(int argc, char const * argv[]) {
             const Laser_gaussian & L = params.laser;
             check(qpic_set_laser_gaussian(ctx, L.amplitude, L.wx, L.wy, L.wz, L.x0, L.y0, L.z0), ctx);
         }
-        for (int ti = 0; ti < time_iterations; ti++) {  // System_3d::run (src/System_3d.cpp:199-236); no bunch => every sweep is identical
+        const bool with_beam = !params.bunch_parameters_array.empty();
+        if (with_beam) {
+            if (params.qed) {
+                out << "qed = true (photon emission, src/System_3d.cpp:887-921) is not covered by this driver." << std::endl;
+                qpic_destroy(ctx);
+                return 2;
+            }
+            std::vector<double> charge, cmr;
+            std::vector<int> is_photon;
+            for (const auto & sp : params.species.get_species()) {
+                charge.push_back(sp.charge);
+                cmr.push_back(sp.charge_to_mass_ratio);
+                is_photon.push_back(sp.is_photon ? 1 : 0);
+            }
+            check(qpic_bunch_set_species(ctx, (int)charge.size(), charge.data(), cmr.data(), is_photon.data()), ctx);
+            check(qpic_bunch_init(ctx, beam_count, beam.x.data(), beam.y.data(), beam.z.data(), beam.px.data(), beam.py.data(), beam.pz.data(),
+                                  beam.gamma.data(), beam.n.data(), beam.species_id.data()), ctx);
+        }
+        for (int ti = 0; ti < time_iterations; ti++) {  // System_3d::run (src/System_3d.cpp:199-236)
             out << "Iteration " << ti << std::endl;
             out << "Depositing bunch densities..." << std::endl;
+            if (with_beam) check(qpic_bunch_deposit_densities(ctx), ctx);
             out << "Solving wakefield" << std::flush;
             Output_writer writer(params.output.output3d, params.output.output_xy, params.output.output_bunch, params.output.z0, ti, nx, ny, nz, dx, dy, dz);
             check(qpic_init_wake_particles(ctx, py.data(), pz.data(), pn.data(), py.size()), ctx);
@@ -186,8 +234,8 @@ int main(int argc, char const * argv[]) {
                 if (xy_only) {
                     std::vector<double> cut((size_t)nx * ny);
                     for (const Entry & e : entries) {
-                        const bool bunch = (e.id == QPIC_F3_RHO_BUNCH || e.id == QPIC_F3_JX_BUNCH);  // no bunch in this driver: zeros (not resident)
-                        if (bunch) {
+                        const bool bunch = (e.id == QPIC_F3_RHO_BUNCH || e.id == QPIC_F3_JX_BUNCH);  // without a beam: zeros (not resident)
+                        if (bunch && !with_beam) {
                             std::fill(cut.begin(), cut.end(), 0.0);
                         } else {
                             check(qpic_download_xy_cut(ctx, e.id, 0, nx, cut.data()), ctx);
@@ -203,7 +251,22 @@ int main(int argc, char const * argv[]) {
                 }
             }
             out << "Depositing fields to particles..." << std::endl;
+            if (with_beam) check(qpic_bunch_gather_fields(ctx, units.field_schwinger), ctx);
+            if (params.output.output_bunch) {  // write_bunch_parameters (src/Output_writer.cpp:190-244)
+                const char * names[] = {"x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi"};
+                const qpic_bunch_field ids[] = {QPIC_B_X, QPIC_B_Y, QPIC_B_Z, QPIC_B_PX, QPIC_B_PY, QPIC_B_PZ, QPIC_B_GAMMA,
+                                                QPIC_B_EX, QPIC_B_EY, QPIC_B_EZ, QPIC_B_BY, QPIC_B_BZ, QPIC_B_CHI};
+                std::vector<double> col(beam_count ? beam_count : 1);
+                for (int a = 0; a < 13; a++) {
+                    if (with_beam) check(qpic_bunch_download(ctx, ids[a], col.data()), ctx);
+                    writer.write_bunch_dataset(names[a], col.data(), beam_count);
+                }
+                const double weight_norm = dx * dy * dz * units.number_density_norm;
+                for (size_t q = 0; q < beam_count; q++) col[q] = beam.n[q] * weight_norm;
+                writer.write_bunch_dataset("weight", col.data(), beam_count);
+            }
             out << "Advancing particles..." << std::endl;
+            if (with_beam && ti < time_iterations - 1) check(qpic_bunch_advance(ctx, params.dt), ctx);
             out << std::endl;
         }
     } catch (const std::exception & e) {

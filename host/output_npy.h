@@ -73,6 +73,7 @@ public:
         if (output_xy) mkdir(dirxy.c_str(), 0777);
         if (output_bunch) {
             std::snprintf(name, sizeof(name), "Bunch_%03d.h5.d", count);
+            dirbunch = name;
             mkdir(name, 0777);
         }
         std::snprintf(name, sizeof(name), "Photons_%03d.h5.d", count);  // always created (src/System_parameters.h:12)
@@ -106,12 +107,18 @@ public:
         write_attrs(dirxy + "/" + m.name + ".attrs", {dx, dy}, {m.ox, m.oy}, true, z0);
     }
 
+    // one 1-D dataset of Bunch_NNN.h5 (write_particle_parameters, src/Output_writer.cpp:190-236)
+    void write_bunch_dataset(const std::string & name, const double * values, size_t count) {
+        if (dirbunch.empty()) return;
+        write_npy(dirbunch + "/" + name + ".npy", values, {count});
+    }
+
 private:
     bool output3d, output_xy;
     double z0;
     int nx, ny, nz;
     double dx, dy, dz;
-    std::string dir3d, dirxy;
+    std::string dir3d, dirxy, dirbunch;
 };
 
 }  // namespace qhost

@@ -31,7 +31,7 @@ def split_sections(text):
     return text.split("----------------------------------------\n")
 
 
-@pytest.mark.parametrize("name", ["tiny_laser", "tiny_profile", "laser_test", "tiny_bunch"])
+@pytest.mark.parametrize("name", ["tiny_laser", "tiny_profile", "laser_test", "tiny_bunch", "tiny_bunch_stop", "tiny_beam"])
 def test_config_echo_and_banner_match_reference_stdout(name, golden_dir, tmp_path):
     gname = "laser_test_summary" if name == "laser_test" else name
     ref = str(np.load(os.path.join(golden_dir, gname + ".npz"))["stdout"])
@@ -41,9 +41,8 @@ def test_config_echo_and_banner_match_reference_stdout(name, golden_dir, tmp_pat
     assert got_s[1] == ref_s[1]
     # section 2 is the thread / device line; sections 3-5: grid + units + species banner (src/System_3d.cpp:91-120)
     assert got_s[3:6] == ref_s[3:6]
-    if "bunch" not in name:
-        # section 6: memory estimate (src/System_3d.cpp:136-150)
-        assert got_s[6] == ref_s[6]
+    # section 6: memory estimate incl. the beam particles the driver builds on the host (src/System_3d.cpp:122-150)
+    assert got_s[6] == ref_s[6]
 
 
 def test_missing_argument_and_bad_config(tmp_path):
@@ -97,3 +96,24 @@ def test_driver_fields_xy_only_uses_device_side_cuts(golden_dir, tmp_path):
         assert xy.shape == ref.shape
         scale = np.abs(g["f3/" + nm]).max()
         assert np.abs(xy - ref).max() <= 1e-9 * scale + 1e-300, nm
+
+
+@pytest.mark.gpu
+def test_driver_beam_time_loop_matches_reference(golden_dir, tmp_path):
+    """[[bunch]] input with t_end > 0: System_3d::run's time loop (src/System_3d.cpp:199-236) -- Fields_NNN, Bunch_NNN and the stdout
+    of every iteration against the unmodified reference"""
+    g = np.load(os.path.join(golden_dir, "tiny_beam.npz"))
+    r = run_driver("tiny_beam", str(tmp_path), golden_dir)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref_s, got_s = split_sections(str(g["stdout"])), split_sections(r.stdout)
+    assert got_s[7] == ref_s[7]  # "Iteration 0 ... Advancing particles..." x 3
+    for t in range(3):
+        for nm in ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi", "weight"]:
+            a = np.load(os.path.join(tmp_path, f"Bunch_{t:03d}.h5.d", nm + ".npy"))
+            b = g[f"it{t}/bunch/{nm}"]
+            assert a.shape == b.shape
+            assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(b), (t, nm)
+        for nm in NAMES:
+            a = np.load(os.path.join(tmp_path, f"Fields_{t:03d}.h5.d", nm + ".npy"))
+            assert slice_rel_l2(a, g[f"it{t}/f3/{nm}"]) < 1e-9, (t, nm)
+        assert os.path.isdir(os.path.join(tmp_path, f"Photons_{t:03d}.h5.d"))
