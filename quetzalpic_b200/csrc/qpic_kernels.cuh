@@ -144,6 +144,28 @@ __device__ __forceinline__ double ld_stream(const double * p) {
     return __ldcs(p);
 #endif
 }
+// the opposite hint: evict-last, for slot arrays that every B iteration of the slice reads again (A/B knob QPIC_PIN_MASK: bit i
+// = i-th slice invariant of k_particles_predict keeps its L2 lines; 0 = all streamed).  Measured on B200, config #2
+// (gpurun_out/r31_pin.log): mask 0 0.767 ms/slice, 0x3 0.771, 0x1f 0.786, 0x3ff 0.797 -- pinned invariants push the predictor's
+// outputs out of L2 and the latency-bound deposits that read them next lose more than the predictor gains.  Stays 0.
+#ifndef QPIC_PIN_MASK
+#define QPIC_PIN_MASK 0
+#endif
+template <int BIT>
+__device__ __forceinline__ double ld_invariant(const double * p) {
+#if defined(QPIC_EMU)
+    return *p;
+#else
+    if ((QPIC_PIN_MASK >> BIT) & 1) {
+        double v;
+        unsigned long long policy;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+        asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+        return v;
+    }
+    return ld_stream(p);
+#endif
+}
 struct Ctl {
     int slice;      // xi-slice being solved (nx-1 ... 0)
     int stop_tag;   // 0, or slice * STOP_TAG_STRIDE + iteration + 1 of the B-field solve that tripped the stop condition
@@ -754,11 +776,11 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double fy = P.fy_b[s], fz = P.fz_b[s];
     // issue the independent streaming loads before the dependent field gathers
-    const double q = ld_stream(P.q + s), gamma = P.gam[s];
-    const double py = ld_stream(P.py_s + s), pz = ld_stream(P.pz_s + s);
-    const double t1y = ld_stream(P.t1y + s), t1z = ld_stream(P.t1z + s), dpy = ld_stream(P.dpy + s), dpz = ld_stream(P.dpz + s);
-    const double y0 = ld_stream(P.y_s + s), z0 = ld_stream(P.z_s + s);
-    const double a_particle = ld_stream(P.ap + s), nw = P.nw_s[s];
+    const double q = ld_invariant<0>(P.q + s), gamma = P.gam[s];
+    const double py = ld_invariant<1>(P.py_s + s), pz = ld_invariant<2>(P.pz_s + s);
+    const double t1y = ld_invariant<3>(P.t1y + s), t1z = ld_invariant<4>(P.t1z + s), dpy = ld_invariant<5>(P.dpy + s), dpz = ld_invariant<6>(P.dpz + s);
+    const double y0 = ld_invariant<7>(P.y_s + s), z0 = ld_invariant<8>(P.z_s + s);
+    const double a_particle = ld_invariant<9>(P.ap + s), nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
