@@ -265,6 +265,7 @@ int main(int argc, char const * argv[]) {
                 for (size_t q = 0; q < beam_count; q++) col[q] = beam.n[q] * weight_norm;
                 writer.write_bunch_dataset("weight", col.data(), beam_count);
             }
+            writer.close();
             out << "Advancing particles..." << std::endl;
             if (with_beam && ti < time_iterations - 1) check(qpic_bunch_advance(ctx, params.dt), ctx);
             out << std::endl;

@@ -2,20 +2,25 @@
 //
 // The reference writes HDF5 (src/Output_writer.cpp): Fields_NNN.h5 with (nx,ny,nz) datasets + `steps` / `origin` attributes,
 // Fields_xy_NNN.h5 with (nx,ny) cuts at z0 + `steps` / `origin` / `plane` / `plane_coordinate`, Photons_NNN.h5, Bunch_NNN.h5.
-// libhdf5 does not exist in this image, so the same datasets are written as one NumPy file each:
-//     Fields_000.h5  ->  directory Fields_000.h5.d/ with <dataset>.npy and <dataset>.attrs ("name dtype count values...")
-// which is the layout oracle/shims/H5Cpp.h produces for the unmodified reference, so both outputs can be diffed directly.
-// A real HDF5 back end is a "next" row.
+// Two back ends, selected by the environment variable QPIC_OUTPUT_FORMAT = h5 (default) | npy | both:
+//   h5   the same files, written by the self-contained HDF5 writer of output_h5.h (libhdf5 does not exist in this image);
+//   npy  one NumPy file per dataset: Fields_000.h5 -> directory Fields_000.h5.d/ with <dataset>.npy and <dataset>.attrs
+//        ("name dtype count values..."), the layout oracle/shims/H5Cpp.h produces for the unmodified reference, so both
+//        outputs can be diffed directly.
 #pragma once
 
 #include <sys/stat.h>
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include "output_h5.h"
 
 namespace qhost {
 
@@ -64,27 +69,42 @@ class Output_writer {
 public:
     Output_writer(bool output3d, bool output_xy, bool output_bunch, double z0, int count, int nx, int ny, int nz, double dx, double dy, double dz)
         : output3d(output3d), output_xy(output_xy), z0(z0), nx(nx), ny(ny), nz(nz), dx(dx), dy(dy), dz(dz) {
+        const char * fmt_env = std::getenv("QPIC_OUTPUT_FORMAT");
+        const std::string format = fmt_env ? fmt_env : "h5";
+        if (format != "h5" && format != "npy" && format != "both") throw std::runtime_error("QPIC_OUTPUT_FORMAT must be h5, npy or both");
+        const bool npy = format != "h5", h5 = format != "npy";
         char name[64];
-        std::snprintf(name, sizeof(name), "Fields_%03d.h5.d", count);
-        dir3d = name;
-        std::snprintf(name, sizeof(name), "Fields_xy_%03d.h5.d", count);
-        dirxy = name;
-        if (output3d) mkdir(dir3d.c_str(), 0777);
-        if (output_xy) mkdir(dirxy.c_str(), 0777);
-        if (output_bunch) {
-            std::snprintf(name, sizeof(name), "Bunch_%03d.h5.d", count);
-            dirbunch = name;
-            mkdir(name, 0777);
-        }
-        std::snprintf(name, sizeof(name), "Photons_%03d.h5.d", count);  // always created (src/System_parameters.h:12)
-        mkdir(name, 0777);
+        // (the reference creates the four files in this order, src/Output_writer.cpp:142-156)
+        std::snprintf(name, sizeof(name), "Fields_%03d.h5", count);
+        if (output3d && npy) mkdir((dir3d = std::string(name) + ".d").c_str(), 0777);
+        if (output3d && h5) h5_3d.reset(new H5Writer(name));
+        std::snprintf(name, sizeof(name), "Fields_xy_%03d.h5", count);
+        if (output_xy && npy) mkdir((dirxy = std::string(name) + ".d").c_str(), 0777);
+        if (output_xy && h5) h5_xy.reset(new H5Writer(name));
+        std::snprintf(name, sizeof(name), "Bunch_%03d.h5", count);
+        if (output_bunch && npy) mkdir((dirbunch = std::string(name) + ".d").c_str(), 0777);
+        if (output_bunch && h5) h5_bunch.reset(new H5Writer(name));
+        std::snprintf(name, sizeof(name), "Photons_%03d.h5", count);  // always created (src/System_parameters.h:12); empty without qed
+        if (npy) mkdir((std::string(name) + ".d").c_str(), 0777);
+        if (h5) H5Writer(name).close();
+    }
+
+    // every file is complete (metadata + superblock written) only after close(); the destructor closes too
+    void close() {
+        if (h5_3d) h5_3d->close();
+        if (h5_xy) h5_xy->close();
+        if (h5_bunch) h5_bunch->close();
     }
 
     // a full (nx,ny,nz) array: whole to Fields, z-interpolated cut to Fields_xy (src/array_utils.cpp:7-24)
     void write_array(const Field_meta & m, const double * a) {
-        if (output3d) {
+        if (!dir3d.empty()) {
             write_npy(dir3d + "/" + m.name + ".npy", a, {(size_t)nx, (size_t)ny, (size_t)nz});
             write_attrs(dir3d + "/" + m.name + ".attrs", {dx, dy, dz}, {m.ox, m.oy, m.oz}, false, 0);
+        }
+        if (h5_3d) {  // write_array, src/Output_writer.cpp:7-26
+            h5_3d->add_dataset(m.name, {(uint64_t)nx, (uint64_t)ny, (uint64_t)nz}, a,
+                               {H5Attribute{"steps", H5Attribute::F64_ARRAY, {dx, dy, dz}, 0}, H5Attribute{"origin", H5Attribute::F64_ARRAY, {m.ox, m.oy, m.oz}, 0}});
         }
         if (output_xy) {
             const int k0 = static_cast<int>(std::floor((z0 - m.oz) / dz));
@@ -96,21 +116,27 @@ public:
                     cut[(size_t)i * ny + j] = (1 - z_frac) * row[k0] + z_frac * row[k0 + 1];
                 }
             }
-            write_npy(dirxy + "/" + m.name + ".npy", cut.data(), {(size_t)nx, (size_t)ny});
-            write_attrs(dirxy + "/" + m.name + ".attrs", {dx, dy}, {m.ox, m.oy}, true, z0);
+            write_xy(m, cut.data());
         }
     }
 
     // a cut that the device already evaluated (qpic_download_xy_cut): Fields_xy only
     void write_xy(const Field_meta & m, const double * cut) {
-        write_npy(dirxy + "/" + m.name + ".npy", cut, {(size_t)nx, (size_t)ny});
-        write_attrs(dirxy + "/" + m.name + ".attrs", {dx, dy}, {m.ox, m.oy}, true, z0);
+        if (!dirxy.empty()) {
+            write_npy(dirxy + "/" + m.name + ".npy", cut, {(size_t)nx, (size_t)ny});
+            write_attrs(dirxy + "/" + m.name + ".attrs", {dx, dy}, {m.ox, m.oy}, true, z0);
+        }
+        if (h5_xy) {  // write_array with a Plane::XY slice, src/Output_writer.cpp:28-60: plane = static_cast<int>(Plane::XY) = 1
+            h5_xy->add_dataset(m.name, {(uint64_t)nx, (uint64_t)ny}, cut,
+                               {H5Attribute{"steps", H5Attribute::F64_ARRAY, {dx, dy}, 0}, H5Attribute{"origin", H5Attribute::F64_ARRAY, {m.ox, m.oy}, 0},
+                                H5Attribute{"plane", H5Attribute::I32_SCALAR, {}, 1}, H5Attribute{"plane_coordinate", H5Attribute::F64_SCALAR, {z0}, 0}});
+        }
     }
 
     // one 1-D dataset of Bunch_NNN.h5 (write_particle_parameters, src/Output_writer.cpp:190-236)
     void write_bunch_dataset(const std::string & name, const double * values, size_t count) {
-        if (dirbunch.empty()) return;
-        write_npy(dirbunch + "/" + name + ".npy", values, {count});
+        if (!dirbunch.empty()) write_npy(dirbunch + "/" + name + ".npy", values, {count});
+        if (h5_bunch) h5_bunch->add_dataset(name, {(uint64_t)count}, values, {});
     }
 
 private:
@@ -119,6 +145,7 @@ private:
     int nx, ny, nz;
     double dx, dy, dz;
     std::string dir3d, dirxy, dirbunch;
+    std::unique_ptr<H5Writer> h5_3d, h5_xy, h5_bunch;
 };
 
 }  // namespace qhost

@@ -17,14 +17,27 @@ NAMES = ["aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "b
 
 
 def build_driver():
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host"), "all"], stdout=subprocess.DEVNULL)
 
 
 def run_driver(name, workdir, golden_dir):
     build_driver()
     toml = os.path.join(golden_dir, "inputs", name + ".toml")
     subprocess.check_call(["cp", toml, workdir])
-    return subprocess.run([DRIVER, name + ".toml"], cwd=workdir, capture_output=True, text=True)
+    # both output back ends: the HDF5 files (default, what the reference writes) and the .npy directories the goldens were made from
+    return subprocess.run([DRIVER, name + ".toml"], cwd=workdir, capture_output=True, text=True, env=dict(os.environ, QPIC_OUTPUT_FORMAT="both"))
+
+
+def check_h5_matches_npy(workdir, stem, names, attrs=()):
+    """the .h5 file holds exactly the datasets (and attributes) of the .npy directory"""
+    from h5mini import H5File
+    f = H5File(os.path.join(workdir, stem + ".h5"))
+    assert f.keys() == sorted(names)
+    for nm in names:
+        assert np.array_equal(f[nm], np.load(os.path.join(workdir, stem + ".h5.d", nm + ".npy"))), (stem, nm)
+        for a in attrs:
+            assert a in f.attrs(nm), (stem, nm, a)
+    return f
 
 
 def split_sections(text):
@@ -75,6 +88,14 @@ def test_driver_output_files_match_reference(name, golden_dir, tmp_path):
         assert np.allclose([float(v) for v in attrs["origin"].split()], g[f"f3/{nm}@origin"], rtol=0, atol=1e-15)
         assert np.allclose([float(v) for v in attrs["steps"].split()], g[f"f3/{nm}@steps"], rtol=0, atol=1e-15)
     assert os.path.isdir(os.path.join(tmp_path, "Photons_000.h5.d"))
+    # the HDF5 files: same datasets bit for bit, attributes of src/Output_writer.cpp:7-60
+    f3 = check_h5_matches_npy(str(tmp_path), "Fields_000", NAMES, ("steps", "origin"))
+    assert np.allclose(f3.attrs("jy")["origin"], g["f3/jy@origin"], rtol=0, atol=1e-15) and f3.attrs("jy")["steps"].shape == (3,)
+    fxy = check_h5_matches_npy(str(tmp_path), "Fields_xy_000", NAMES, ("steps", "origin", "plane", "plane_coordinate"))
+    assert fxy.attrs("psi")["plane"] == 1 and fxy.attrs("psi")["plane_coordinate"] == float(g["xy/psi@plane_coordinate"][0])
+    assert fxy.attrs("ez")["steps"].shape == (2,)
+    from h5mini import H5File
+    assert H5File(os.path.join(tmp_path, "Photons_000.h5")).keys() == []
 
 
 @pytest.mark.gpu
@@ -87,9 +108,9 @@ def test_driver_fields_xy_only_uses_device_side_cuts(golden_dir, tmp_path):
     text = open(os.path.join(golden_dir, "inputs", name + ".toml")).read().replace("fields_3d = true", "fields_3d = false")
     with open(os.path.join(tmp_path, name + ".toml"), "w") as f:
         f.write(text)
-    r = subprocess.run([DRIVER, name + ".toml"], cwd=str(tmp_path), capture_output=True, text=True)
+    r = subprocess.run([DRIVER, name + ".toml"], cwd=str(tmp_path), capture_output=True, text=True, env=dict(os.environ, QPIC_OUTPUT_FORMAT="both"))
     assert r.returncode == 0, r.stdout + r.stderr
-    assert not os.path.isdir(os.path.join(tmp_path, "Fields_000.h5.d"))
+    assert not os.path.isdir(os.path.join(tmp_path, "Fields_000.h5.d")) and not os.path.exists(os.path.join(tmp_path, "Fields_000.h5"))
     for nm in NAMES:
         xy = np.load(os.path.join(tmp_path, "Fields_xy_000.h5.d", nm + ".npy"))
         ref = g["xy/" + nm]
@@ -117,3 +138,31 @@ def test_driver_beam_time_loop_matches_reference(golden_dir, tmp_path):
             a = np.load(os.path.join(tmp_path, f"Fields_{t:03d}.h5.d", nm + ".npy"))
             assert slice_rel_l2(a, g[f"it{t}/f3/{nm}"]) < 1e-9, (t, nm)
         assert os.path.isdir(os.path.join(tmp_path, f"Photons_{t:03d}.h5.d"))
+        check_h5_matches_npy(str(tmp_path), f"Bunch_{t:03d}", ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi", "weight"])
+        check_h5_matches_npy(str(tmp_path), f"Fields_{t:03d}", NAMES, ("steps", "origin"))
+
+
+def test_hdf5_writer_subset_reads_back(tmp_path):
+    """host/output_h5.h (superblock v0, v1 object headers, group B-tree / symbol table node / local heap, contiguous float64
+    datasets, v1 attributes) read back by the independent reader tests/h5mini.py; known-answer bytes of the two datatype messages
+    and the structural invariants a libhdf5 reader relies on"""
+    from h5mini import H5File
+    build_driver()
+    subprocess.check_call([os.path.join(ROOT, "host", "_build", "h5_selftest"), str(tmp_path)])
+    f = H5File(os.path.join(tmp_path, "fields.h5"))
+    names = ["psi", "rho", "jx", "jy", "jz", "aSqr", "susceptibility", "rho_bunch", "jx_bunch", "ex", "ey", "ez", "by", "bz"]
+    assert f.keys() == sorted(names + ["cut", "empty"])  # strcmp order: "aSqr" < "by" < ... < "susceptibility"
+    ref = np.sin(0.1 * np.arange(60)).reshape(3, 4, 5)
+    for nm in names:
+        assert np.array_equal(f[nm], ref)
+        assert np.array_equal(f.attrs(nm)["steps"], [0.1, 0.2, 0.3]) and np.array_equal(f.attrs(nm)["origin"], [-0.05, 0.0, 0.15])
+    assert np.array_equal(f["cut"], (-1.5 * np.arange(12)).reshape(3, 4))
+    a = f.attrs("cut")
+    assert a["plane"] == 1 and a["plane"].dtype == np.int32 and a["plane_coordinate"] == 2.5
+    assert f["empty"].shape == (0,)
+    raw = open(os.path.join(tmp_path, "fields.h5"), "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and len(raw) % 8 == 0
+    # IEEE little-endian float64 / int32 datatype messages exactly as libhdf5 encodes H5T_NATIVE_DOUBLE / H5T_NATIVE_INT on x86-64
+    assert bytes.fromhex("11203f00080000000000400034 0b003 4ff030000".replace(" ", "")) in raw
+    assert bytes.fromhex("100800000400000000002000") in raw
+    assert H5File(os.path.join(tmp_path, "nothing.h5")).keys() == []
