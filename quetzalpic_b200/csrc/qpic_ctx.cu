@@ -826,14 +826,20 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             QPIC_TRY(dist_fill(c, sa, {DF_BY, DF_BZ}));
         }
     }
-    // rho and susceptibility(i) from the last executed iteration (see k_deposit_jx_rho_chi); reads the cell lists and
-    // fractions of (y,z), so it must finish before the push below rewrites them
-    if (M > 0) {
-        QPIC_TRY(enqueue_base_currents(c, sa, fast, false, true, true));
-        QPIC_TRY(dist_reduce(c, sa, halo_job({c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]}, {RB_RHO, RB_CHI}, {0, 1})));
-    }
-    // branch B: fields of this slice + the psi_prev / jy / jz roll;  branch A: push + cell lists of the new positions
+    // branch B: rho and susceptibility(i) from the last executed iteration (see k_deposit_jx_rho_chi), then the fields of this slice
+    // + the psi_prev / jy / jz roll;  branch A: push + cell lists of the new positions.  The deposit reads the cell lists and the
+    // slot arrays of (y, z): the push only writes particle-id arrays, so the two overlap (the deposit is latency bound, the push
+    // bandwidth bound); the cell sort below, which rewrites the lists, waits for the deposit.
     QPIC_TRY(stream_depend(c, sa, sb));
+    cudaEvent_t deposit_done = nullptr;
+    if (M > 0) {
+        QPIC_TRY(enqueue_base_currents(c, sb, fast, false, true, true));
+        QPIC_TRY(dist_reduce(c, sb, halo_job({c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]}, {RB_RHO, RB_CHI}, {0, 1})));
+        if (sb != sa) {
+            deposit_done = next_event(c);
+            QPIC_CUDA(c, cudaEventRecord(deposit_done, sb));
+        }
+    }
     {
         cudaStream_t keep = c->stream;
         c->stream = sb;
@@ -854,6 +860,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_LAUNCH(k_migrate_unpack, 148, 256, 0, sa, c->ctl, c->g, c->dist.v, c->P, c->P.np, c->count);
         QPIC_TRY(check_launch(c, "k_migrate_unpack"));
     }
+    if (deposit_done) QPIC_CUDA(c, cudaStreamWaitEvent(sa, deposit_done, 0));
     QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
         QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, sa, c->ctl, c->P, c->perm_b);
