@@ -66,6 +66,12 @@ inline std::string fmt_g4(double v) {  // "{:.4g}"
     return buf;
 }
 
+inline std::string fmt_g3(double v) {  // "{:.3g}"
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%.3g", v);
+    return buf;
+}
+
 class Config_exception : public std::runtime_error {
 public:
     explicit Config_exception(const std::string & m) : std::runtime_error(m) {}

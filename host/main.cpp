@@ -6,7 +6,7 @@
 // (src/System_3d.cpp:91-152), the per-iteration messages of System_3d::run (:199-236) and the output datasets
 // (src/Output_writer.cpp; see output_npy.h for the file format).  solve_wakefield itself runs on the device.
 // Beam drivers ([bunch] / [[bunch]]): the particles are built here as System_3d::init_bunch_particles does and live on the device
-// (qpic_bunch_*); System_3d::run's time loop (src/System_3d.cpp:199-236) is the loop below.  qed = true is refused (not built).
+// (qpic_bunch_*); System_3d::run's time loop (src/System_3d.cpp:199-236) is the loop below, including photon emission (qed = true).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -170,11 +170,6 @@ int main(int argc, char const * argv[]) {
         }
         const bool with_beam = !params.bunch_parameters_array.empty();
         if (with_beam) {
-            if (params.qed) {
-                out << "qed = true (photon emission, src/System_3d.cpp:887-921) is not covered by this driver." << std::endl;
-                qpic_destroy(ctx);
-                return 2;
-            }
             std::vector<double> charge, cmr;
             std::vector<int> is_photon;
             for (const auto & sp : params.species.get_species()) {
@@ -265,9 +260,41 @@ int main(int argc, char const * argv[]) {
                 for (size_t q = 0; q < beam_count; q++) col[q] = beam.n[q] * weight_norm;
                 writer.write_bunch_dataset("weight", col.data(), beam_count);
             }
-            writer.close();
             out << "Advancing particles..." << std::endl;
-            if (with_beam && ti < time_iterations - 1) check(qpic_bunch_advance(ctx, params.dt), ctx);
+            if (ti < time_iterations - 1) {
+                if (params.qed) {
+                    // advance_bunch_particles with qed (src/System_3d.cpp:887-921).  The uniform numbers are drawn here exactly as a
+                    // one-thread run of the reference draws them: two rand_double() (src/monte_carlo.cpp:7-9) per charged particle,
+                    // in particle order, from the C library generator that the reference never seeds.
+                    double max_radiation_probability = 0.0;
+                    size_t photon_count = 0;
+                    if (with_beam) {
+                        std::vector<double> u_emit(beam_count ? beam_count : 1), u_accept(beam_count ? beam_count : 1);
+                        for (size_t q = 0; q < beam_count; q++) {
+                            if (params.species.get_species()[beam.species_id[q]].is_photon) continue;
+                            u_emit[q] = static_cast<double>(rand()) / RAND_MAX;
+                            u_accept[q] = static_cast<double>(rand()) / RAND_MAX;
+                        }
+                        check(qpic_bunch_advance_qed(ctx, params.dt, units.frequency, u_emit.data(), u_accept.data(), 0, &max_radiation_probability, &photon_count), ctx);
+                    }
+                    out << "Max radiation probability " << fmt_g3(max_radiation_probability) << std::endl;
+                    const char * names[] = {"x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi"};
+                    const qpic_bunch_field ids[] = {QPIC_B_X, QPIC_B_Y, QPIC_B_Z, QPIC_B_PX, QPIC_B_PY, QPIC_B_PZ, QPIC_B_GAMMA,
+                                                    QPIC_B_EX, QPIC_B_EY, QPIC_B_EZ, QPIC_B_BY, QPIC_B_BZ, QPIC_B_CHI};
+                    std::vector<double> col(photon_count ? photon_count : 1);
+                    for (int a = 0; a < 13; a++) {
+                        if (photon_count) check(qpic_photons_download(ctx, ids[a], col.data()), ctx);
+                        writer.write_photon_dataset(names[a], col.data(), photon_count);
+                    }
+                    if (photon_count) check(qpic_photons_download(ctx, QPIC_B_N, col.data()), ctx);
+                    const double weight_norm = dx * dy * dz * units.number_density_norm;
+                    for (size_t q = 0; q < photon_count; q++) col[q] *= weight_norm;
+                    writer.write_photon_dataset("weight", col.data(), photon_count);
+                } else if (with_beam) {
+                    check(qpic_bunch_advance(ctx, params.dt), ctx);
+                }
+            }
+            writer.close();
             out << std::endl;
         }
     } catch (const std::exception & e) {

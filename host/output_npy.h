@@ -85,8 +85,8 @@ public:
         if (output_bunch && npy) mkdir((dirbunch = std::string(name) + ".d").c_str(), 0777);
         if (output_bunch && h5) h5_bunch.reset(new H5Writer(name));
         std::snprintf(name, sizeof(name), "Photons_%03d.h5", count);  // always created (src/System_parameters.h:12); empty without qed
-        if (npy) mkdir((std::string(name) + ".d").c_str(), 0777);
-        if (h5) H5Writer(name).close();
+        if (npy) mkdir((dirphotons = std::string(name) + ".d").c_str(), 0777);
+        if (h5) h5_photons.reset(new H5Writer(name));
     }
 
     // every file is complete (metadata + superblock written) only after close(); the destructor closes too
@@ -94,6 +94,7 @@ public:
         if (h5_3d) h5_3d->close();
         if (h5_xy) h5_xy->close();
         if (h5_bunch) h5_bunch->close();
+        if (h5_photons) h5_photons->close();
     }
 
     // a full (nx,ny,nz) array: whole to Fields, z-interpolated cut to Fields_xy (src/array_utils.cpp:7-24)
@@ -139,13 +140,19 @@ public:
         if (h5_bunch) h5_bunch->add_dataset(name, {(uint64_t)count}, values, {});
     }
 
+    // one 1-D dataset of Photons_NNN.h5 (write_photon_parameters, src/Output_writer.cpp:246-252; only written when qed = true)
+    void write_photon_dataset(const std::string & name, const double * values, size_t count) {
+        if (!dirphotons.empty()) write_npy(dirphotons + "/" + name + ".npy", values, {count});
+        if (h5_photons) h5_photons->add_dataset(name, {(uint64_t)count}, values, {});
+    }
+
 private:
     bool output3d, output_xy;
     double z0;
     int nx, ny, nz;
     double dx, dy, dz;
-    std::string dir3d, dirxy, dirbunch;
-    std::unique_ptr<H5Writer> h5_3d, h5_xy, h5_bunch;
+    std::string dir3d, dirxy, dirbunch, dirphotons;
+    std::unique_ptr<H5Writer> h5_3d, h5_xy, h5_bunch, h5_photons;
 };
 
 }  // namespace qhost

@@ -140,7 +140,7 @@ int qpic_set_current_slice(qpic_ctx * ctx, int slice);
  * One time iteration of the reference is
  *     qpic_bunch_deposit_densities; qpic_init_wake_particles; qpic_solve_wakefield; qpic_bunch_gather_fields;
  *     [Bunch_NNN output: qpic_bunch_download]; qpic_bunch_advance (all but the last iteration).
- * QED photon emission (qed = true, src/System_3d.cpp:887-921) is not covered. */
+ * With qed = true the last call is qpic_bunch_advance_qed, followed by the Photons_NNN output (qpic_photons_download). */
 typedef enum {
     QPIC_B_X = 0, QPIC_B_Y, QPIC_B_Z, QPIC_B_PX, QPIC_B_PY, QPIC_B_PZ, QPIC_B_GAMMA, QPIC_B_N,
     QPIC_B_EX, QPIC_B_EY, QPIC_B_EZ, QPIC_B_BY, QPIC_B_BZ, QPIC_B_CHI, QPIC_B_COUNT
@@ -160,6 +160,18 @@ int qpic_bunch_deposit_densities(qpic_ctx * ctx);
 int qpic_bunch_gather_fields(qpic_ctx * ctx, double field_schwinger);
 /* System_3d::advance_bunch_particles with qed == false (src/System_3d.cpp:862-886) */
 int qpic_bunch_advance(qpic_ctx * ctx, double dt);
+/* System_3d::advance_bunch_particles with qed == true (src/System_3d.cpp:862-921, W_new of src/monte_carlo.cpp:11-41, incl. the
+ * `p.py -= photon.px` of :917).  The reference draws two rand_double() per charged particle, in particle order when it runs on
+ * one thread: u_emit[p] is the photon energy fraction r (:890), u_accept[p] is compared with the emission probability (:897);
+ * host arrays of qpic_bunch_count doubles (entries of photon-species particles are ignored).  Both NULL: a counter-based
+ * generator on the device (Philox4x32-10 keyed by `seed`, the step number and the particle index).  frequency =
+ * Plasma_units::frequency.  Outputs (nullable): the reference's max_radiation_probability reduction and the number of photons
+ * emitted in this step; those photons (in particle order) stay available through qpic_photons_download until the next step. */
+int qpic_bunch_advance_qed(qpic_ctx * ctx, double dt, double frequency, const double * u_emit, const double * u_accept, unsigned long long seed,
+                           double * max_radiation_probability, size_t * photon_count);
+size_t qpic_photon_count(const qpic_ctx * ctx);
+/* x, y, z, px, py, pz, gamma, n of the photons of the last step; the field members and chi of a new photon are 0 */
+int qpic_photons_download(qpic_ctx * ctx, qpic_bunch_field f, double * dst);
 int qpic_bunch_download(qpic_ctx * ctx, qpic_bunch_field f, double * dst); /* qpic_bunch_count doubles */
 int qpic_bunch_upload(qpic_ctx * ctx, qpic_bunch_field f, const double * src);
 

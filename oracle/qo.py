@@ -213,3 +213,21 @@ class OracleBunch:
 
     def advance_bunch_particles(self, dt):
         self.L.qo_bunch_advance(ctypes.byref(self.s), self.cmr.ctypes.data, self.photon.ctypes.data, float(dt))
+
+    def advance_bunch_particles_qed(self, dt, frequency, u_emit, u_accept):
+        """qed = true (reference src/System_3d.cpp:887-921); returns (photons dict, max radiation probability)"""
+        L = self.L
+        L.qo_bunch_advance_qed.restype = ctypes.c_size_t
+        L.qo_bunch_advance_qed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_double,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        count = self.s.count
+        ph = {k: np.zeros(max(count, 1)) for k in BUNCH_FIELDS}
+        sid = np.zeros(max(count, 1), dtype=np.int32)
+        ps = QoBunch(0, *[ph[k].ctypes.data for k in BUNCH_FIELDS], sid.ctypes.data)
+        u1 = np.ascontiguousarray(u_emit, dtype=np.float64)
+        u2 = np.ascontiguousarray(u_accept, dtype=np.float64)
+        assert u1.shape == u2.shape == (count,)
+        maxp = ctypes.c_double(0.0)
+        n = L.qo_bunch_advance_qed(ctypes.byref(self.s), self.cmr.ctypes.data, self.photon.ctypes.data, float(dt), float(frequency),
+                                   u1.ctypes.data, u2.ctypes.data, ctypes.byref(ps), ctypes.byref(maxp))
+        return {k: v[:n].copy() for k, v in ph.items()}, maxp.value

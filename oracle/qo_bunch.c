@@ -123,3 +123,88 @@ void qo_bunch_advance(qo_bunch * b, const double * species_charge_to_mass, const
         }
     }
 }
+
+/* ---------------------------------------------------------------- photon emission (qed = true) */
+
+/* W_new, src/monte_carlo.cpp:11-41: differential emission probability per unit time; note the single-precision powf calls.
+ * Constants: src/constants.h:3-12. */
+double qo_w_new(double g, double r, double chi, double omega) {
+    const double PI = 3.141592653589793238;
+    const double ELECTRON_MASS_CGS = 9.1093837015e-28, PLANCK_CONST_CGS = 6.62607015e-27, SPEED_OF_LIGHT_CGS = 29979245800.0;
+    const double ELEMENTARY_CHARGE_CGS = 4.803204672997e-10;
+    const double PLANCK_CONST_BAR_CGS = PLANCK_CONST_CGS / (2 * PI);
+    const double FINE_STRUCTURE_CONSTANT = (ELEMENTARY_CHARGE_CGS * ELEMENTARY_CHARGE_CGS / PLANCK_CONST_BAR_CGS / SPEED_OF_LIGHT_CGS);
+    if ((1.0 - r) * g < 1.0 || chi == 0.0 || r == 0.0) return 0.0;
+    double rm = 1.0;
+    if (!(chi > 0.13333)) { /* :29-33 */
+        rm = chi / 0.13333;
+        r = r * rm;
+    }
+    const double coef = ELECTRON_MASS_CGS * SPEED_OF_LIGHT_CGS * SPEED_OF_LIGHT_CGS / (PLANCK_CONST_BAR_CGS * omega);
+    const double y = r / ((1.0 - r) * chi);
+    const double x = powf(y, 2.0 / 3.0);
+    const double exp_v = exp(-2.0 * y / 3.0);
+    const double iAiryapp = exp_v / (2.0 * sqrt(PI)) * powf(x + 0.80049, -0.75);
+    const double dAiryapp = -exp_v / (2.0 * sqrt(PI)) * powf((x + 0.70861 * (1.0 - 0.65 * x / (1.0 + x * x))), 0.25);
+    if (chi > 0.13333) return -FINE_STRUCTURE_CONSTANT * coef / (g * g) * (iAiryapp + (2.0 / x + chi * r * sqrt(x)) * dAiryapp);
+    return -rm * FINE_STRUCTURE_CONSTANT * coef / (g * g) * (iAiryapp + (2.0 / x + chi * r * sqrt(x)) * dAiryapp);
+}
+
+/* System_3d::advance_bunch_particles with qed == true, src/System_3d.cpp:862-921.  The reference draws two rand_double() per
+ * charged particle in particle order (one thread); here the caller supplies them: u_emit[i] (the photon energy fraction r, :890)
+ * and u_accept[i] (compared with the emission probability, :897), entries of photon-species particles unused.  Emitted photons
+ * are appended to `photons` (capacity >= b->count; x, y, z, px, py, pz, gamma, n are set, the rest stays as it is) in particle
+ * order.  Reproduces `p.py -= photon.px` (:917).  Returns the number of photons; *max_probability as the reference's reduction. */
+size_t qo_bunch_advance_qed(qo_bunch * b, const double * species_charge_to_mass, const int * species_is_photon, double dt, double frequency,
+                            const double * u_emit, const double * u_accept, qo_bunch * photons, double * max_probability) {
+    size_t emitted = 0;
+    double max_radiation_probability = 0.0;
+    for (size_t i = 0; i < b->count; i++) {
+        const int s = b->species_id[i];
+        if (species_is_photon[s]) {
+            b->x[i] += dt * (b->px[i] / b->gamma[i] - 1);
+            b->y[i] += dt * b->py[i] / b->gamma[i];
+            b->z[i] += dt * b->pz[i] / b->gamma[i];
+            b->gamma[i] = sqrt(b->px[i] * b->px[i] + b->py[i] * b->py[i] + b->pz[i] * b->pz[i]);
+            continue;
+        }
+        const double cmr = species_charge_to_mass[s];
+        const double fx = cmr * (b->ex[i] + (b->py[i] * b->bz[i] - b->pz[i] * b->by[i]) / b->gamma[i]);
+        const double fy = cmr * (b->ey[i] - b->px[i] * b->bz[i] / b->gamma[i]);
+        const double fz = cmr * (b->ez[i] + b->px[i] * b->by[i] / b->gamma[i]);
+        b->x[i] += dt * (b->px[i] / b->gamma[i] - 1);
+        b->y[i] += dt * b->py[i] / b->gamma[i];
+        b->z[i] += dt * b->pz[i] / b->gamma[i];
+        b->px[i] += dt * fx;
+        b->py[i] += dt * fy;
+        b->pz[i] += dt * fz;
+        b->gamma[i] = sqrt(1 + b->px[i] * b->px[i] + b->py[i] * b->py[i] + b->pz[i] * b->pz[i]);
+        double r = u_emit[i];
+        const double w = qo_w_new(b->gamma[i], r, b->chi[i], frequency);
+        const double radiation_probability = w * dt * b->gamma[i];
+        if (radiation_probability > max_radiation_probability) max_radiation_probability = radiation_probability;
+        if (u_accept[i] < radiation_probability) {
+            if (b->chi[i] < 0.13333) {
+                double rm = b->chi[i] / 0.13333;
+                r = r * rm;
+            }
+            const double qx = r * b->px[i], qy = r * b->py[i], qz = r * b->pz[i];
+            photons->x[emitted] = b->x[i];
+            photons->y[emitted] = b->y[i];
+            photons->z[emitted] = b->z[i];
+            photons->px[emitted] = qx;
+            photons->py[emitted] = qy;
+            photons->pz[emitted] = qz;
+            photons->n[emitted] = b->n[i];
+            photons->gamma[emitted] = sqrt(qx * qx + qy * qy + qz * qz);
+            emitted++;
+            b->px[i] -= qx;
+            b->py[i] -= qx; /* sic, :917 */
+            b->pz[i] -= qz;
+            b->gamma[i] = sqrt(1 + b->px[i] * b->px[i] + b->py[i] * b->py[i] + b->pz[i] * b->pz[i]);
+        }
+    }
+    photons->count = emitted;
+    if (max_probability) *max_probability = max_radiation_probability;
+    return emitted;
+}

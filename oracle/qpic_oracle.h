@@ -107,6 +107,12 @@ void qo_bunch_gather_fields(qo_bunch * b, int nx, int ny, int nz, double dx, dou
                             const double * ez, const double * by, const double * bz, double field_schwinger);
 /* advance_bunch_particles with qed == false (src/System_3d.cpp:862-886) */
 void qo_bunch_advance(qo_bunch * b, const double * species_charge_to_mass, const int * species_is_photon, double dt);
+/* W_new (src/monte_carlo.cpp:11-41) */
+double qo_w_new(double g, double r, double chi, double omega);
+/* advance_bunch_particles with qed == true (src/System_3d.cpp:862-921); the two uniform numbers per particle that the reference
+ * takes from rand() are supplied by the caller.  photons: capacity >= b->count; returns the number of emitted photons */
+size_t qo_bunch_advance_qed(qo_bunch * b, const double * species_charge_to_mass, const int * species_is_photon, double dt, double frequency,
+                            const double * u_emit, const double * u_accept, qo_bunch * photons, double * max_probability);
 
 #ifdef __cplusplus
 }

@@ -227,4 +227,145 @@ __global__ void k_bunch_advance(Bunch B, BunchSpecies S, double dt) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ photon emission (qed = true)
+
+// constants of W_new, formed on the host with the reference's expressions (src/monte_carlo.cpp:17, src/constants.h:3-12)
+struct QedConstants {
+    double coef;            // m c^2 / (hbar omega)
+    double fine_structure;  // e^2 / (hbar c)
+};
+
+// powf as the reference's libm evaluates it (single precision, correctly rounded in practice): the double-precision pow of the
+// float arguments, rounded to float.  CUDA's own powf differs from glibc's in the last bits, which would move the emission
+// probabilities by ~1e-7 relative.
+__device__ __forceinline__ double powf_like_libm(double a, double b) { return (double)(float)pow((double)(float)a, (double)(float)b); }
+
+// W_new (src/monte_carlo.cpp:11-41)
+__device__ __forceinline__ double w_new(double g, double r, double chi, const QedConstants & Q) {
+    const double PI = 3.141592653589793238;
+    if ((1.0 - r) * g < 1.0 || chi == 0.0 || r == 0.0) return 0.0;
+    double rm = 1.0;
+    const bool strong = chi > 0.13333;
+    if (!strong) {
+        rm = chi / 0.13333;
+        r = r * rm;
+    }
+    const double y = r / ((1.0 - r) * chi);
+    const double x = powf_like_libm(y, 2.0 / 3.0);
+    const double exp_v = exp(-2.0 * y / 3.0);
+    const double iAiryapp = exp_v / (2.0 * sqrt(PI)) * powf_like_libm(x + 0.80049, -0.75);
+    const double dAiryapp = -exp_v / (2.0 * sqrt(PI)) * powf_like_libm((x + 0.70861 * (1.0 - 0.65 * x / (1.0 + x * x))), 0.25);
+    const double bracket = iAiryapp + (2.0 / x + chi * r * sqrt(x)) * dAiryapp;
+    if (strong) return -Q.fine_structure * Q.coef / (g * g) * bracket;
+    return -rm * Q.fine_structure * Q.coef / (g * g) * bracket;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter = (particle, step, stream, 0), key = seed.  Used when the caller does not supply
+// the uniform numbers; every (seed, step, particle) gives the same two numbers whatever the launch shape.
+__device__ __forceinline__ void philox4x32_10(unsigned int c[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned int n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0;
+        c[1] = n1;
+        c[2] = n2;
+        c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ void philox_uniform_pair(unsigned long long seed, unsigned int step, unsigned int particle, double & u0, double & u1) {
+    unsigned int c[4] = {particle, step, 0x51454421u, 0u};
+    philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+    const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1], b = ((unsigned long long)c[2] << 32) | c[3];
+    u0 = (double)(a >> 11) * (1.0 / 9007199254740992.0);  // 53 bits, [0, 1)
+    u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct QedScratch {
+    int * flag;                      // 1 where the particle emitted this step (then overwritten by its exclusive prefix sum)
+    double *qx, *qy, *qz;            // momentum of the emitted photon, by particle
+    unsigned long long * max_bits;   // bit pattern of the largest non-negative emission probability (atomicMax: order independent)
+};
+
+// advance_bunch_particles with qed == true (src/System_3d.cpp:862-921).  u_emit / u_accept: the two rand_double() values of the
+// particle (:890, :897), or NULL = Philox.  Keeps `p.py -= photon.px` (:917).
+__global__ void k_bunch_advance_qed(Bunch B, BunchSpecies S, double dt, QedConstants Q, const double * __restrict__ u_emit,
+                                    const double * __restrict__ u_accept, unsigned long long seed, unsigned int step, QedScratch X) {
+    QPIC_KERNEL_BEGIN(KID_k_bunch_advance_qed);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B.np) return;
+    const int s = B.species[p];
+    double px = B.px[p], py = B.py[p], pz = B.pz[p];
+    double gamma = B.gamma[p];
+    B.x[p] += dt * (px / gamma - 1);
+    B.y[p] += dt * py / gamma;
+    B.z[p] += dt * pz / gamma;
+    int emitted = 0;
+    if (S.is_photon[s]) {
+        B.gamma[p] = sqrt(px * px + py * py + pz * pz);
+    } else {
+        const double cmr = S.charge_to_mass[s];
+        const double pex = B.ex[p], pey = B.ey[p], pez = B.ez[p], pby = B.by[p], pbz = B.bz[p];
+        const double fx = cmr * (pex + (py * pbz - pz * pby) / gamma);
+        const double fy = cmr * (pey - px * pbz / gamma);
+        const double fz = cmr * (pez + px * pby / gamma);
+        px += dt * fx;
+        py += dt * fy;
+        pz += dt * fz;
+        gamma = sqrt(1 + px * px + py * py + pz * pz);
+        double r, accept;
+        if (u_emit) {
+            r = u_emit[p];
+            accept = u_accept[p];
+        } else {
+            philox_uniform_pair(seed, step, (unsigned int)p, r, accept);
+        }
+        const double chi = B.chi[p];
+        const double w = w_new(gamma, r, chi, Q);
+        const double radiation_probability = w * dt * gamma;
+        if (radiation_probability > 0.0) atomicMax(X.max_bits, (unsigned long long)__double_as_longlong(radiation_probability));
+        if (accept < radiation_probability) {
+            if (chi < 0.13333) {
+                const double rm = chi / 0.13333;
+                r = r * rm;
+            }
+            const double qx = r * px, qy = r * py, qz = r * pz;
+            X.qx[p] = qx;
+            X.qy[p] = qy;
+            X.qz[p] = qz;
+            emitted = 1;
+            px -= qx;
+            py -= qx;  // sic: the reference subtracts photon.px from py (src/System_3d.cpp:917)
+            pz -= qz;
+            gamma = sqrt(1 + px * px + py * py + pz * pz);
+        }
+        B.px[p] = px;
+        B.py[p] = py;
+        B.pz[p] = pz;
+        B.gamma[p] = gamma;
+    }
+    X.flag[p] = emitted;
+}
+
+// photons in particle order (the order a one-thread reference run appends them in): start = exclusive prefix sum of the flags
+__global__ void k_bunch_photon_compact(Bunch B, QedScratch X, const int * __restrict__ start, Bunch photons) {
+    QPIC_KERNEL_BEGIN(KID_k_bunch_photon_compact);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B.np) return;
+    const int at = start[p];
+    if (start[p + 1] == at) return;
+    const double qx = X.qx[p], qy = X.qy[p], qz = X.qz[p];
+    photons.x[at] = B.x[p];
+    photons.y[at] = B.y[p];
+    photons.z[at] = B.z[p];
+    photons.px[at] = qx;
+    photons.py[at] = qy;
+    photons.pz[at] = qz;
+    photons.n[at] = B.n[p];
+    photons.gamma[at] = sqrt(qx * qx + qy * qy + qz * qz);
+}
+
 }  // namespace qpic

@@ -138,6 +138,13 @@ struct qpic_ctx {
         int *cell = nullptr, *tmp = nullptr, *perm = nullptr;     // per particle
         int *count = nullptr, *start = nullptr, *sums = nullptr;  // per cell of the (nx, ny, nz) grid / per scan chunk
         int nchunks = 0;
+        // photon emission (qed): photons of the last step, scratch of the emission kernel
+        Bunch photons = {};
+        QedScratch qed = {};
+        int *qed_start = nullptr, *qed_sums = nullptr;
+        int qed_capacity = 0;
+        unsigned int qed_step = 0;
+        double *u_emit = nullptr, *u_accept = nullptr;
     } bunch;
 
     // per-kernel profiling (qpic_profile_slices): an event after every launch of an eager slice
@@ -2084,6 +2091,89 @@ int qpic_bunch_upload(qpic_ctx * c, qpic_bunch_field f, const double * src) {
     if (c->bunch.b.np == 0) return QPIC_OK;
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)c->bunch.b.np, cudaMemcpyHostToDevice, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return QPIC_OK;
+}
+
+// advance_bunch_particles with qed == true (src/System_3d.cpp:862-921)
+int qpic_bunch_advance_qed(qpic_ctx * c, double dt, double frequency, const double * u_emit, const double * u_accept, unsigned long long seed,
+                           double * max_radiation_probability, size_t * photon_count) {
+    if (!c) return QPIC_ERR_INVALID;
+    qpic_ctx::BunchState & S = c->bunch;
+    if (!S.count) return fail(c, QPIC_ERR_STATE, "qpic_bunch_advance_qed called before qpic_bunch_init");
+    if ((u_emit == nullptr) != (u_accept == nullptr)) return fail(c, QPIC_ERR_INVALID, "u_emit and u_accept must be given together (or both NULL: device RNG)");
+    if (!(frequency > 0.0)) return fail(c, QPIC_ERR_INVALID, "the base plasma frequency must be positive");
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    cudaStream_t st = c->stream;
+    const int np = S.b.np;
+    if (S.qed_capacity < S.capacity) {
+        const size_t cap = (size_t)S.capacity;
+        double ** arrays[] = {&S.photons.x, &S.photons.y, &S.photons.z, &S.photons.px, &S.photons.py, &S.photons.pz, &S.photons.gamma, &S.photons.n,
+                              &S.qed.qx, &S.qed.qy, &S.qed.qz, &S.u_emit, &S.u_accept};
+        for (double ** a : arrays) QPIC_TRY(dev_alloc(c, a, cap));
+        QPIC_TRY(dev_alloc(c, &S.qed.flag, cap));
+        QPIC_TRY(dev_alloc(c, &S.qed_start, cap + 1));
+        QPIC_TRY(dev_alloc(c, &S.qed_sums, (cap + SCAN_CHUNK - 1) / SCAN_CHUNK));
+        QPIC_TRY(dev_alloc(c, &S.qed.max_bits, 1));
+        S.qed_capacity = S.capacity;
+    }
+    S.photons.np = 0;
+    double maxp = 0.0;
+    if (np > 0) {
+        if (u_emit) {
+            QPIC_CUDA(c, cudaMemcpyAsync(S.u_emit, u_emit, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+            QPIC_CUDA(c, cudaMemcpyAsync(S.u_accept, u_accept, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+        }
+        QPIC_CUDA(c, cudaMemsetAsync(S.qed.max_bits, 0, sizeof(unsigned long long), st));
+        // W_new's constants with the reference's expressions (src/monte_carlo.cpp:17, src/constants.h:3-12)
+        const double PI = 3.141592653589793238, ELECTRON_MASS_CGS = 9.1093837015e-28, PLANCK_CONST_CGS = 6.62607015e-27;
+        const double PLANCK_CONST_BAR_CGS = PLANCK_CONST_CGS / (2 * PI), SPEED_OF_LIGHT_CGS = 29979245800.0, ELEMENTARY_CHARGE_CGS = 4.803204672997e-10;
+        QedConstants Q;
+        Q.coef = ELECTRON_MASS_CGS * SPEED_OF_LIGHT_CGS * SPEED_OF_LIGHT_CGS / (PLANCK_CONST_BAR_CGS * frequency);
+        Q.fine_structure = (ELEMENTARY_CHARGE_CGS * ELEMENTARY_CHARGE_CGS / PLANCK_CONST_BAR_CGS / SPEED_OF_LIGHT_CGS);
+        QPIC_LAUNCH_FLAT(k_bunch_advance_qed, blocks_for(np, 128), 128, 0, st, S.b, S.species, dt, Q, u_emit ? (const double *)S.u_emit : (const double *)nullptr,
+                         u_emit ? (const double *)S.u_accept : (const double *)nullptr, seed, S.qed_step, S.qed);
+        QPIC_TRY(check_launch(c, "k_bunch_advance_qed"));
+        const int nchunks = (np + SCAN_CHUNK - 1) / SCAN_CHUNK;
+        QPIC_LAUNCH(k_scan_chunk_sums, nchunks, SCAN_THREADS, 0, st, c->ctl_scratch, S.qed.flag, np, S.qed_sums);
+        QPIC_TRY(check_launch(c, "k_scan_chunk_sums"));
+        QPIC_LAUNCH(k_scan_sums, 1, SCAN_THREADS, 0, st, c->ctl_scratch, S.qed_sums, nchunks);
+        QPIC_TRY(check_launch(c, "k_scan_sums"));
+        QPIC_LAUNCH(k_bunch_scan_apply, nchunks, SCAN_THREADS, 0, st, S.qed.flag, np, S.qed_sums, S.qed_start);
+        QPIC_TRY(check_launch(c, "k_bunch_scan_apply"));
+        Bunch ph = S.photons;
+        ph.np = np;
+        QPIC_LAUNCH_FLAT(k_bunch_photon_compact, blocks_for(np, 256), 256, 0, st, S.b, S.qed, S.qed_start, ph);
+        QPIC_TRY(check_launch(c, "k_bunch_photon_compact"));
+        int emitted = 0;
+        unsigned long long bits = 0;
+        QPIC_CUDA(c, cudaMemcpyAsync(&emitted, S.qed_start + np, sizeof(int), cudaMemcpyDeviceToHost, st));
+        QPIC_CUDA(c, cudaMemcpyAsync(&bits, S.qed.max_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        QPIC_CUDA(c, cudaStreamSynchronize(st));
+        S.photons.np = emitted;
+        std::memcpy(&maxp, &bits, sizeof(maxp));
+    }
+    S.qed_step++;
+    if (max_radiation_probability) *max_radiation_probability = maxp;
+    if (photon_count) *photon_count = (size_t)S.photons.np;
+    return QPIC_OK;
+}
+
+size_t qpic_photon_count(const qpic_ctx * c) { return c ? (size_t)c->bunch.photons.np : 0; }
+
+int qpic_photons_download(qpic_ctx * c, qpic_bunch_field f, double * dst) {
+    if (!c || f < 0 || f >= QPIC_B_COUNT) return fail(c, QPIC_ERR_INVALID, "bad photon field id");
+    const Bunch & ph = c->bunch.photons;
+    const size_t n = (size_t)ph.np;
+    if (n == 0) return QPIC_OK;
+    if (!dst) return fail(c, QPIC_ERR_INVALID, "dst is NULL");
+    const double * const table[QPIC_B_COUNT] = {ph.x, ph.y, ph.z, ph.px, ph.py, ph.pz, ph.gamma, ph.n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!table[f]) {  // ex, ey, ez, by, bz, chi of a freshly emitted photon: bunch_particle_3d's defaults (src/containers.h:54-59)
+        std::memset(dst, 0, sizeof(double) * n);
+        return QPIC_OK;
+    }
+    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, table[f], sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     return QPIC_OK;
 }

@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "qpic_fast_path_aborts", "qpic_wait_transfers", "qpic_timeline_reset", "qpic_timeline_read", "qpic_timeline_kernel_name",
     "qpic_dist_region_bytes", "qpic_dist_region", "qpic_dist_ipc_handle", "qpic_dist_attach_ipc", "qpic_dist_attach_pointers", "qpic_dist_row_range", "qpic_download_xy_cut",
     "qpic_bunch_set_species", "qpic_bunch_init", "qpic_bunch_count", "qpic_bunch_deposit_densities", "qpic_bunch_gather_fields",
-    "qpic_bunch_advance", "qpic_bunch_download", "qpic_bunch_upload",
+    "qpic_bunch_advance", "qpic_bunch_download", "qpic_bunch_upload", "qpic_bunch_advance_qed", "qpic_photon_count", "qpic_photons_download",
 ]
 
 
@@ -136,6 +136,10 @@ class QpicLibrary:
         L.qpic_bunch_gather_fields.argtypes = [vp, dbl]
         L.qpic_bunch_advance.argtypes = [vp, dbl]
         L.qpic_bunch_download.argtypes = [vp, ci, vp]
+        L.qpic_bunch_advance_qed.argtypes = [vp, dbl, dbl, vp, vp, ctypes.c_ulonglong, ctypes.POINTER(dbl), ctypes.POINTER(ctypes.c_size_t)]
+        L.qpic_photon_count.argtypes = [vp]
+        L.qpic_photon_count.restype = ctypes.c_size_t
+        L.qpic_photons_download.argtypes = [vp, ci, vp]
         L.qpic_bunch_upload.argtypes = [vp, ci, vp]
         self.L = L
 
@@ -523,6 +527,26 @@ class WakefieldSolver:
 
     def advance_bunch_particles(self, dt):
         self._check(self.lib.L.qpic_bunch_advance(self.ctx, float(dt)))
+
+    def advance_bunch_particles_qed(self, dt, frequency, u_emit=None, u_accept=None, seed=0):
+        """qed = true (reference src/System_3d.cpp:887-921).  u_emit / u_accept: the two uniform numbers per particle the reference
+        takes from rand(), or None = device-side Philox keyed by `seed`.  Returns (photons dict, max radiation probability)."""
+        maxp, count = ctypes.c_double(0.0), ctypes.c_size_t(0)
+        if u_emit is None:
+            p1 = p2 = None
+        else:
+            u1 = np.ascontiguousarray(u_emit, dtype=np.float64)
+            u2 = np.ascontiguousarray(u_accept, dtype=np.float64)
+            if not (u1.shape == u2.shape == (self.bunch_count,)):
+                raise ValueError("u_emit, u_accept must have shape (bunch_count,)")
+            p1, p2 = u1.ctypes.data, u2.ctypes.data
+        self._check(self.lib.L.qpic_bunch_advance_qed(self.ctx, float(dt), float(frequency), p1, p2, int(seed), ctypes.byref(maxp), ctypes.byref(count)))
+        photons = {}
+        for name in BUNCH_FIELDS:
+            out = np.empty(count.value)
+            self._check(self.lib.L.qpic_photons_download(self.ctx, BUNCH_FIELDS.index(name), out.ctypes.data))
+            photons[name] = out
+        return photons, maxp.value
 
     def bunch(self, name):
         out = np.empty(self.bunch_count)

@@ -66,6 +66,7 @@ class Case:
                 rho0 = float(pl.get("rho0", -1))
         nx, ny, nz = self.n
         self.particles = wake_particle_lattice(ny, nz, l[1], l[2], self.ppcy, self.ppcz, profile=profile, rho0=rho0)
+        self.photons = []  # (photons, max radiation probability) per step of a qed time loop
 
     # -- beam side of System_3d (reference src/System_3d.cpp:106-162, :199-236)
     def bunch_particles(self):
@@ -80,16 +81,43 @@ class Case:
         return concatenate_bunches(bunches)
 
     @property
+    def base_frequency(self):
+        """reference src/Config_reader.cpp:29-39, src/Plasma_units.h:11-13"""
+        if "base_density_CGS" in self.cfg:
+            pi, e, m = 3.141592653589793238, 4.803204672997e-10, 9.1093837015e-28
+            return float(np.sqrt(4 * pi * e * e * float(self.cfg["base_density_CGS"]) / m))
+        return float(self.cfg.get("base_frequency_SI", 1.0))
+
+    @property
     def time_iterations(self):
         dt = float(self.cfg.get("dt", self.l[0]))
         return int(float(self.cfg.get("t_end", 0.0)) / dt) + 1, dt
+
+    def reference_uniforms(self, species_ids, steps):
+        """The rand_double() values (reference src/monte_carlo.cpp:7-9) a ONE-thread run of the reference consumes in
+        advance_bunch_particles with qed = true (src/System_3d.cpp:890, :897): two per charged particle, in particle order, step
+        after step, from glibc's rand() in its default state (the reference never calls srand).  Returns [(u_emit, u_accept)] per step."""
+        import ctypes
+        libc = ctypes.CDLL(None)
+        libc.rand.restype = ctypes.c_int
+        libc.srand(1)  # == the state of a process that never seeded
+        rand_max = 2147483647
+        charged = np.array([not s[2] for s in SPECIES.values()])[np.asarray(species_ids)]
+        out = []
+        for _ in range(steps):
+            u1, u2 = np.zeros(len(charged)), np.zeros(len(charged))
+            for i in np.nonzero(charged)[0]:
+                u1[i] = libc.rand() / rand_max
+                u2[i] = libc.rand() / rand_max
+            out.append((u1, u2))
+        return out
 
     def run_time_loop(self, make_backend, on_iteration):
         """System_3d::run (reference src/System_3d.cpp:199-236) on either backend.  make_backend() -> (solver, beam) where
         solver has init_wake_particles / solve_wakefield and beam has deposit_bunch_densities / deposit_wakefield_to_bunch /
         advance_bunch_particles; on_iteration(ti, solver, beam) is called where the reference writes Bunch_NNN."""
         iterations, dt = self.time_iterations
-        units = plasma_units(float(self.cfg.get("base_frequency_SI", 1.0)))
+        units = plasma_units(self.base_frequency)
         solver, beam = make_backend()
         for ti in range(iterations):
             beam.deposit_bunch_densities()
@@ -98,7 +126,12 @@ class Case:
             beam.deposit_wakefield_to_bunch(units["field_schwinger"])
             on_iteration(ti, solver, beam)
             if ti < iterations - 1:
-                beam.advance_bunch_particles(dt)
+                if self.cfg.get("qed", False):
+                    if ti == 0:
+                        uniforms = self.reference_uniforms(self.bunch_particles()["species_id"], iterations - 1)
+                    self.photons.append(beam.advance_bunch_particles_qed(dt, units["frequency"], *uniforms[ti]))
+                else:
+                    beam.advance_bunch_particles(dt)
         return solver, beam
 
     @classmethod

@@ -11,6 +11,7 @@ Fixtures:
   <name>.npz for the tiny inputs     every dataset of Fields_000.h5 (full 3-D) and Fields_xy_000.h5 + attributes
   tiny_beam.npz                      beam-driven run over three time iterations (two charged bunches + a photon beam): every
                                      dataset of Fields_NNN.h5 and Bunch_NNN.h5 per iteration   (python make_golden.py beam)
+  tiny_qed.npz                       the same beams at gamma 4000 / 9000 with qed = true: Bunch_NNN and Photons_NNN    (... qed)
   laser_test_summary.npz             the shipped inputs/test/laser_test.toml (200^3): per-field min/max/L2 norm,
                                      per-slice L2 norms, on-axis lines [:, ny/2, nz/2], transverse lines through
                                      slice 100, and the value at [100,100,100]
@@ -76,9 +77,29 @@ def collect_time_loop(workdir, log, iterations):
     return data
 
 
+def collect_qed(workdir, log, iterations):
+    """qed = true: Bunch_NNN and Photons_NNN of every time iteration (the reference run with one thread draws rand() in particle
+    order from glibc's default seed, so the run is reproducible) + stdout with the "Max radiation probability" lines"""
+    data = {"stdout": np.array(log), "iterations": np.array(iterations)}
+    for t in range(iterations):
+        for nm in BUNCH_NAMES:
+            data[f"it{t}/bunch/{nm}"] = np.load(os.path.join(workdir, f"Bunch_{t:03d}.h5.d", nm + ".npy"))
+            path = os.path.join(workdir, f"Photons_{t:03d}.h5.d", nm + ".npy")
+            if os.path.exists(path):
+                data[f"it{t}/photons/{nm}"] = np.load(path)
+    return data
+
+
 def main():
     if not os.path.exists(REF_EXE):
         sys.exit("build the reference first: make -C oracle ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "qed":
+        with tempfile.TemporaryDirectory() as wd:
+            log = run_reference(os.path.join(HERE, "inputs", "tiny_qed.toml"), wd)
+            data = collect_qed(wd, log, 3)
+        np.savez_compressed(os.path.join(HERE, "tiny_qed.npz"), **data)
+        print("tiny_qed", data["it0/bunch/x"].shape, data["it0/photons/x"].shape, data["it1/photons/x"].shape)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "beam":  # only the time-loop fixture (added after the others)
         with tempfile.TemporaryDirectory() as wd:
             log = run_reference(os.path.join(HERE, "inputs", "tiny_beam.toml"), wd)

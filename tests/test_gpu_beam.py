@@ -144,3 +144,99 @@ def test_beam_call_order_errors():
             return  # development emulator: no CUDA graph, so late set-up is harmless there
         with pytest.raises(QpicError):
             s.bunch_init(ok)  # rho_bunch / jx_bunch cannot become resident after the slice graph was captured
+
+
+def test_qed_time_loop_matches_reference_fixture(golden_dir):
+    """qed = true (tests/golden/tiny_qed.npz, the unmodified reference on one thread): with the uniform numbers that run drew from
+    glibc's rand(), the device emits the same photons in the same order and leaves the same beam; 1e-9 over the time loop"""
+    from quetzalpic_b200 import plasma_units
+    g = np.load(os.path.join(golden_dir, "tiny_qed.npz"))
+    case = Case.from_toml("tiny_qed")
+    particles = case.bunch_particles()
+    weight_norm = np.prod([case.l[a] / case.n[a] for a in range(3)]) * plasma_units(case.base_frequency)["number_density_norm"]
+    worst = {}
+
+    def make_backend():
+        s = case.make_solver()
+        s.bunch_init(particles)
+        return s, s
+
+    def check(ti, s, beam):
+        for f in BUNCH_OUT:
+            worst[(ti, "bunch." + f)] = rel_l2(s.bunch(f), g[f"it{ti}/bunch/{f}"])
+
+    s, _ = case.run_time_loop(make_backend, check)
+    s.close()
+    assert len(case.photons) == 2
+    for ti, (ph, maxp) in enumerate(case.photons):
+        assert len(ph["x"]) == len(g[f"it{ti}/photons/x"]) > 20
+        for f in ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "chi"]:
+            worst[(ti, "photons." + f)] = rel_l2(ph[f], g[f"it{ti}/photons/{f}"])
+        worst[(ti, "photons.weight")] = rel_l2(ph["n"] * weight_norm, g[f"it{ti}/photons/weight"])
+        assert f"Max radiation probability {maxp:.3g}" in str(g["stdout"])
+    bad = {k: v for k, v in worst.items() if not v <= 1e-9}
+    assert not bad, bad
+
+
+def test_qed_step_matches_oracle_and_device_rng_statistics():
+    """one emission step from identical state against the oracle (supplied uniforms, weak and strong chi branches of W_new), then the
+    device generator: reproducible per (seed, step), different across steps, and an emission count within 5 sigma of the
+    expectation sum_p E_u[min(1, P_p(u))] estimated with numpy uniforms through the oracle"""
+    from oracle.qo import Oracle, OracleBunch
+    from quetzalpic_b200 import SPECIES, WakefieldSolver
+    rng = np.random.default_rng(11)
+    n, l, count = (8, 12, 12), (2.0, 3.0, 3.0), 40000
+    particles = random_beam(rng, n, l, count)
+    particles["px"] *= 40.0
+    particles["gamma"] = np.sqrt(np.where(particles["species_id"] == 3, 0.0, 1.0) + particles["px"] ** 2 + particles["py"] ** 2 + particles["pz"] ** 2)
+    fields = {f: rng.normal(0, 0.3, count) for f in ["ex", "ey", "ez", "by", "bz"]}
+    chi = np.abs(rng.normal(0, 0.2, count))  # both sides of 0.13333
+    chi[:50] = 0.0
+    frequency, dt = 5.64e13, 0.8
+    u1, u2 = rng.uniform(0, 1, count), rng.uniform(0, 1, count) * 0.3
+
+    def fresh_oracle():
+        ob = OracleBunch(Oracle(*n, *l, 0), particles, list(SPECIES.values()))
+        for f, v in fields.items():
+            ob[f][:] = v
+        ob["chi"][:] = chi
+        return ob
+
+    ob = fresh_oracle()
+    ref_photons, ref_max = ob.advance_bunch_particles_qed(dt, frequency, u1, u2)
+    assert 500 < len(ref_photons["x"]) < count
+
+    def fresh_solver():
+        s = WakefieldSolver(*n, *l, 0)
+        s.bunch_init(particles)
+        for f, v in fields.items():
+            s.set_bunch(f, v)
+        s.set_bunch("chi", chi)
+        return s
+
+    with fresh_solver() as s:
+        photons, maxp = s.advance_bunch_particles_qed(dt, frequency, u1, u2)
+        assert len(photons["x"]) == len(ref_photons["x"])
+        assert abs(maxp - ref_max) <= 1e-6 * ref_max  # single-precision powf inside W_new
+        for f in ["x", "y", "z", "px", "py", "pz", "gamma", "n"]:
+            assert rel_l2(photons[f], ref_photons[f]) < 1e-13, f
+        for f in ["x", "y", "z", "px", "py", "pz", "gamma"]:
+            assert rel_l2(s.bunch(f), ob[f]) < 1e-13, f
+    # device-side generator
+    counts = []
+    for seed in (1, 1, 2):
+        with fresh_solver() as s:
+            ph, _ = s.advance_bunch_particles_qed(dt, frequency, seed=seed)
+            first = ph["px"].copy()
+            ph2, _ = s.advance_bunch_particles_qed(dt, frequency, seed=seed)  # next step: new numbers
+            counts.append((len(first), first.sum(), len(ph2["px"])))
+    assert counts[0][:2] == counts[1][:2] and counts[0][:2] != counts[2][:2]
+    expect, var = 0.0, 0.0
+    trials = 16
+    for t in range(trials):  # Monte-Carlo estimate of the expected number of emissions with independent numpy uniforms
+        ob = fresh_oracle()
+        ph, _ = ob.advance_bunch_particles_qed(dt, frequency, rng.uniform(0, 1, count), rng.uniform(0, 1, count))
+        expect += len(ph["x"]) / trials
+        var += len(ph["x"]) ** 2 / trials
+    sigma = max(np.sqrt(max(var - expect ** 2, 0.0)), np.sqrt(expect))
+    assert abs(counts[0][0] - expect) < 5 * sigma + 5, (counts, expect, sigma)

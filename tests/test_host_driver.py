@@ -44,7 +44,7 @@ def split_sections(text):
     return text.split("----------------------------------------\n")
 
 
-@pytest.mark.parametrize("name", ["tiny_laser", "tiny_profile", "laser_test", "tiny_bunch", "tiny_bunch_stop", "tiny_beam"])
+@pytest.mark.parametrize("name", ["tiny_laser", "tiny_profile", "laser_test", "tiny_bunch", "tiny_bunch_stop", "tiny_beam", "tiny_qed"])
 def test_config_echo_and_banner_match_reference_stdout(name, golden_dir, tmp_path):
     gname = "laser_test_summary" if name == "laser_test" else name
     ref = str(np.load(os.path.join(golden_dir, gname + ".npz"))["stdout"])
@@ -140,6 +140,32 @@ def test_driver_beam_time_loop_matches_reference(golden_dir, tmp_path):
         assert os.path.isdir(os.path.join(tmp_path, f"Photons_{t:03d}.h5.d"))
         check_h5_matches_npy(str(tmp_path), f"Bunch_{t:03d}", ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi", "weight"])
         check_h5_matches_npy(str(tmp_path), f"Fields_{t:03d}", NAMES, ("steps", "origin"))
+
+
+@pytest.mark.gpu
+def test_driver_qed_run_matches_reference(golden_dir, tmp_path):
+    """qed = true: the driver draws the uniform numbers as a one-thread reference run does (glibc rand(), never seeded), so
+    Bunch_NNN, Photons_NNN (same photons, same order) and the "Max radiation probability" lines match the unmodified reference"""
+    from h5mini import H5File
+    g = np.load(os.path.join(golden_dir, "tiny_qed.npz"))
+    r = run_driver("tiny_qed", str(tmp_path), golden_dir)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref_s, got_s = split_sections(str(g["stdout"])), split_sections(r.stdout)
+    assert got_s[7] == ref_s[7]
+    names = ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi", "weight"]
+    for t in range(3):
+        for nm in names:
+            a = np.load(os.path.join(tmp_path, f"Bunch_{t:03d}.h5.d", nm + ".npy"))
+            b = g[f"it{t}/bunch/{nm}"]
+            assert np.linalg.norm(a - b) <= 1e-9 * np.linalg.norm(b), (t, nm)
+        f = H5File(os.path.join(tmp_path, f"Photons_{t:03d}.h5"))
+        if t == 2:
+            assert f.keys() == []  # no push after the last iteration (src/System_3d.cpp:222)
+            continue
+        assert f.keys() == sorted(names)
+        for nm in names:
+            b = g[f"it{t}/photons/{nm}"]
+            assert f[nm].shape == b.shape and np.linalg.norm(f[nm] - b) <= 1e-9 * np.linalg.norm(b) + 1e-300, (t, nm)
 
 
 def test_hdf5_writer_subset_reads_back(tmp_path):

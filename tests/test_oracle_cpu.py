@@ -203,3 +203,32 @@ def test_oracle_beam_time_loop_reproduces_reference(golden_dir):
     # the beam moved and its fields are not trivial
     assert np.abs(g["it2/bunch/py"]).max() > 1.0 and np.abs(g["it2/bunch/y"] - g["it0/bunch/y"]).max() > 1e-3
     assert len(g["it0/photons"]) == 0  # Photons_NNN.h5 is created but stays empty without qed
+
+
+def test_oracle_qed_time_loop_reproduces_reference(golden_dir):
+    """qed = true: the emission step (W_new, src/monte_carlo.cpp:11-41; src/System_3d.cpp:887-921 incl. `p.py -= photon.px`) with
+    the uniform numbers a one-thread reference run draws from glibc's rand(): same photons (count, order, momenta), same beam."""
+    from oracle.qo import OracleBunch
+    from quetzalpic_b200 import SPECIES, plasma_units
+    g = np.load(os.path.join(golden_dir, "tiny_qed.npz"))
+    case = Case.from_toml("tiny_qed")
+    particles = case.bunch_particles()
+    units = plasma_units(case.base_frequency)
+    weight_norm = np.prod([case.l[a] / case.n[a] for a in range(3)]) * units["number_density_norm"]
+
+    def make_backend():
+        o = case.make_oracle()
+        return o, OracleBunch(o, particles, list(SPECIES.values()))
+
+    def check(ti, o, beam):
+        for f in ["x", "y", "z", "px", "py", "pz", "gamma", "ex", "ey", "ez", "by", "bz", "chi"]:
+            assert rel_l2(beam[f], g[f"it{ti}/bunch/{f}"]) < 1e-12, (ti, f)
+
+    case.run_time_loop(make_backend, check)
+    assert len(case.photons) == 2
+    for ti, (ph, maxp) in enumerate(case.photons):
+        assert len(ph["x"]) == len(g[f"it{ti}/photons/x"]) > 20
+        for f in ["x", "y", "z", "px", "py", "pz", "gamma"]:
+            assert rel_l2(ph[f], g[f"it{ti}/photons/{f}"]) < 1e-12, (ti, f)
+        assert rel_l2(ph["n"] * weight_norm, g[f"it{ti}/photons/weight"]) < 1e-12
+        assert f"Max radiation probability {maxp:.3g}" in str(g["stdout"])

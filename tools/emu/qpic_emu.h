@@ -174,6 +174,17 @@ static inline int atomicMax(int * addr, int v) {
     if (v > old) *addr = v;
     return old;
 }
+static inline unsigned long long atomicMax(unsigned long long * addr, unsigned long long v) {
+    unsigned long long old = *addr;
+    if (v > old) *addr = v;
+    return old;
+}
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
+static inline long long __double_as_longlong(double v) {
+    long long r;
+    std::memcpy(&r, &v, sizeof(r));
+    return r;
+}
 static inline int atomicCAS(int * addr, int compare, int v) {
     int old = *addr;
     if (old == compare) *addr = v;
