@@ -493,7 +493,7 @@ int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bo
         const int mine = c->dist.on ? (full ? c->dist.ncols_full : c->dist.ncols_half) : ncols;
         double2 * cols = c->dist.on ? m.base[c->dist.v.rank] : c->spec;
         QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, cols, m.cpr, mine, inv + (size_t)col0 * c->g.ny,
-                    want_border_sums ? c->spec_row0 : (double2 *)nullptr, want_border_sums ? c->spec_colsum : (double2 *)nullptr, c->cols_ticket,
+                    want_border_sums ? c->spec_row0 : (double2 *)nullptr, want_border_sums ? c->spec_colsum : (double2 *)nullptr, c->dist.on ? c->cols_ticket : (int *)nullptr,
                     partials_map(c), c->dist.on ? c->dist.v.rank : 0, col0, nz);
     } else {
         QPIC_LAUNCH(k_fft_cols_solve<false>, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, ncols, ncols, L.spb, c->sy, c->sz, nz, D);
@@ -522,7 +522,8 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     if (c->pow2_z) {
         QPIC_LAUNCH((c->dist.on ? k_p2_rows_c2r<true> : k_p2_rows_c2r<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
                     row_first(c), ny, c->inv_scale, fuse ? 1 : 0, c->dist.on ? reinterpret_cast<const double *>(c->dist.region + c->dist.v.lay.partials) : c->partials,
-                    c->prm.psi_threshold - 1);
+                    c->prm.psi_threshold - 1, (fuse && !c->dist.on) ? (const double2 *)c->spec_row0 : (const double2 *)nullptr,
+                    (fuse && !c->dist.on) ? (const double2 *)c->spec_colsum : (const double2 *)nullptr);
     } else {
         QPIC_LAUNCH(k_fft_rows_c2r<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->spec, c->raw, ny, nz, R.spb, c->inv_scale);
     }

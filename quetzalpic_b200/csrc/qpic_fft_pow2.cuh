@@ -162,7 +162,8 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
 // partial sums the column kernels left in partials[rank][0..2] (one rank on a single GPU), in rank order.
 template <bool DIST>
 __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, SpecMap spec, double * __restrict__ dst, int ny, int row0,
-                              int ny_total, double inv_scale, int fix, const double * __restrict__ partials, double floor_value) {
+                              int ny_total, double inv_scale, int fix, const double * __restrict__ partials, double floor_value,
+                              const double2 * __restrict__ red_row0, const double2 * __restrict__ red_colsum) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2r);
     QPIC_DYN_SMEM(double2, sm);
     const Pow2Lane L = pow2_lane(sm, log2n);
@@ -170,7 +171,7 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
     // loads now, arithmetic after the transform (the divisions then hide behind the spectrum loads)
     double pa = 0.0, pb = 0.0, pc = 0.0;
-    if (fix) {
+    if (fix && !red_row0) {
         pc = partials[2];  // column 0 belongs to rank 0
 #pragma unroll
         for (int r = 0; r < 8; r++) {
@@ -195,6 +196,45 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
         }
         // Z_k = V0 + i V1;  Z_{n-k} = conj(V0) + i conj(V1)
         v[e] = mirror ? make_double2(v0.x + v1.y, v1.x - v0.y) : make_double2(v0.x - v1.y, v0.y + v1.x);
+    }
+    if (fix && red_row0) {
+        // single GPU: the Hermitian-weighted sums of Re U(0,k) and Re sum_j U(j,k) over the half spectrum, straight from what the
+        // column kernel left per column.  Every warp does the whole (tiny) reduction in the same fixed order -- lane l takes columns
+        // l, l + 32, ... ascending, then an xor-shuffle tree -- so all warps of all blocks hold identical sums and no barrier is
+        // needed; the loads sit behind the spectrum loads above and overlap them.
+        // (The last warp of a block may be partial -- blockDim is a multiple of 8 only -- so the tree runs over the first W lanes,
+        // W = the largest power of two that every warp of the block has, and lane 0 broadcasts.)
+        const int lane = threadIdx.x & 31;
+        const int rem = blockDim.x & 31;
+        const int W = rem == 0 ? 32 : (rem >= 16 ? 16 : 8);
+        if (W == 32) {
+            for (int kk = lane; kk <= nz / 2; kk += 32) {
+                const double wgt = (kk == 0 || 2 * kk == nz) ? 1.0 : 2.0;
+                pa += wgt * red_row0[kk].x;
+                pb += wgt * red_colsum[kk].x;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                pb += __shfl_xor_sync(0xffffffffu, pb, o);
+            }
+        } else {
+            const unsigned mask = __activemask();
+            if (lane < W) {
+                for (int kk = lane; kk <= nz / 2; kk += W) {
+                    const double wgt = (kk == 0 || 2 * kk == nz) ? 1.0 : 2.0;
+                    pa += wgt * red_row0[kk].x;
+                    pb += wgt * red_colsum[kk].x;
+                }
+            }
+            for (int o = W >> 1; o > 0; o >>= 1) {
+                pa += __shfl_xor_sync(mask, pa, o);
+                pb += __shfl_xor_sync(mask, pb, o);
+            }
+            pa = __shfl_sync(mask, pa, 0);
+            pb = __shfl_sync(mask, pb, 0);
+        }
+        pc = red_colsum[0].x;
     }
     if (cancelled(ctl)) return;
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
@@ -281,7 +321,9 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 #pragma unroll
         for (int e = 0; e < 8; e++) spec[(size_t)(L.t + e * L.e8) * ld + k] = v[e];
     }
-    if (colsum) {
+    if (colsum && ticket) {
+        // (Slab-decomposed sweeps only; on a single GPU the backward row kernel reduces row0[] / colsum[] itself, which removes
+        // this serial tail -- fence, ticket, one block's reduction -- from every real solve: 0.763 -> 0.751 ms/slice.)
         // The block that takes the last ticket sees every block's row0[] / colsum[] (release: fence before the ticket;
         // acquire: fence after it) and reduces them to the border mean -- see k_p2_rows_c2r for the formulas.
         __shared__ int is_last;

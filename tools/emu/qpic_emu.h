@@ -119,6 +119,7 @@ static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __threadfence_system() {}
 
+static inline unsigned __activemask() { return 0xffffffffu; }
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int lane, int = 32) {
     return qemu::warp_exchange(v, lane);
