@@ -125,6 +125,7 @@ struct qpic_ctx {
     double2 * b_src = nullptr;                     // sources of the By + i Bz solve formed by the jy/jz deposit (TileJob::b_src)
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
+    bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
     double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
     double * partials = nullptr;  // border-sum partials of the fused potential fix-up, [world][4] (inside the region when distributed)
@@ -642,6 +643,12 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
         j.b_jy = c->f2[QPIC_F2_JY];
         j.b_jz = c->f2[QPIC_F2_JZ];
         j.b_D = c->prm.magnetic_field_D;
+        if (!c->dist.on && c->jyjz_cell) {
+            // one visit per particle (k_tile_cell_deposit); A/B switch QPIC_JYJZ_CELL=0 selects the three-list kernel
+            const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (c->g.ny + LIST_TY - 1) / LIST_TY);
+            QPIC_LAUNCH(k_tile_cell_deposit, grid, dim3(LIST_BZ, LIST_BY), 0, st, c->ctl, c->g, c->start_b, c->P, j);
+            return check_launch(c, "k_tile_deposit_jy_jz");
+        }
         QPIC_LAUNCH(k_tile_list_deposit, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j);
         return check_launch(c, "k_tile_deposit_jy_jz");
     }
@@ -780,7 +787,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     for (int it = 0; it < M; it++) {
         if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
-            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count);
+            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
+                             (!fast || it == M - 1) ? 1 : 0);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
         // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored
@@ -1261,6 +1269,8 @@ static int create_impl(qpic_ctx * c) {
     {
         const char * e = getenv("QPIC_JYJZ_LISTS");
         c->jyjz_lists = !(e && e[0] == '0');
+        const char * e2 = getenv("QPIC_JYJZ_CELL");
+        c->jyjz_cell = !(e2 && e2[0] == '0');
         if (c->jyjz_lists && !p.force_general_deposit) {
             QPIC_TRY(dev_alloc(c, &c->bin_cnt, n2));
             QPIC_TRY(dev_alloc(c, &c->bin_lst, (size_t)BIN_K * n2));

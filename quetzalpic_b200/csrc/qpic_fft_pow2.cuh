@@ -288,31 +288,10 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
             v[e] = (j == 0 && k + col0 == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * rinv[e], v[e].y * rinv[e]);
         }
     }
-    if (colsum) {
-        // what the fused potential fix-up of k_p2_rows_c2r needs: U(0,k) and sum_j U(j,k), fixed-order reductions
-        __shared__ double2 red[32];
-        double2 acc = v[0];
-#pragma unroll
-        for (int e = 1; e < 8; e++) acc = cadd(acc, v[e]);
-        const int seg = L.e8 < 32 ? L.e8 : 32;
-        for (int o = seg >> 1; o > 0; o >>= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        }
-        if (L.e8 > 32) {
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-            __syncthreads();
-            if (L.t == 0) {
-                const int w0 = threadIdx.x >> 5, nw = L.e8 >> 5;
-                acc = red[w0];
-                for (int w = 1; w < nw; w++) acc = cadd(acc, red[w0 + w]);
-            }
-        }
-        if (live && L.t == 0) {
-            colsum[k] = acc;
-            row0[k] = v[0];  // thread t = 0 owns j = 0 in v[0]
-        }
-    }
+    // what the fused potential fix-up of k_p2_rows_c2r needs per column: U(0,k) -- element 0 before the backward transform -- and
+    // sum_j U(j,k), which IS element 0 of the unnormalised backward transform, so no reduction is needed: thread t = 0 of the
+    // sequence owns index 0 in v[0] both before and after the transform
+    if (colsum && live && L.t == 0) row0[k] = v[0];
     // the forward transform's last exchange buffer may still be read by slower threads of this sequence
     __syncthreads();
     fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy);
@@ -320,6 +299,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) spec[(size_t)(L.t + e * L.e8) * ld + k] = v[e];
+        if (colsum && L.t == 0) colsum[k] = v[0];
     }
     if (colsum && ticket) {
         // (Slab-decomposed sweeps only; on a single GPU the backward row kernel reduces row0[] / colsum[] itself, which removes

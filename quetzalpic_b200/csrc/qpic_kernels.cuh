@@ -766,9 +766,11 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 // Ctl::fast_fail if a particle leaves the +-1 cell window the tile deposit covers.
 // The corrector gamma / px (src/System_3d.cpp:498-508) and the values deposited at :520-527 depend only on py_next, pz_next,
 // so they are formed here as well: one streaming pass over the slot arrays per iteration instead of two.
+// store_px: only the last B iteration's px is read again (rho / susceptibility deposit, push); the general path's deposits read it
+// every iteration.
 template <bool FAST>
 __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
-                                    int * __restrict__ count) {
+                                    int * __restrict__ count, int store_px) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     // The control block is tested only before the first store: its load then overlaps the streaming loads instead of
     // heading the dependent chain (every slot < P.np is readable whatever the flags say).
@@ -806,7 +808,7 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
         const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) / q;
         const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) / q;
         P.gam[s] = gamma_c;
-        P.pxs[s] = px_c;
+        if (store_px) P.pxs[s] = px_c;
         store_currents<!FAST>(P, s, nw, gamma_c, px_c);  // the general path's node-centric deposit reads vrho / vchi
     }
     const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn / q, g.ly);
@@ -1200,6 +1202,10 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
 //         o[1].val hold py_next / pz_next.
 // Block = (TILE_ACC + 2 + MODE) x (TILE_ACC + 2 + MODE) threads: thread (sy, sz) <-> source cell (j0 - 2 + sy, k0 - 2 + sz) in phase
 // A, <-> target cell (j0 - 2 + sy, k0 - 2 + sz) for 1 <= sy, sz <= TILE_ACC in phase B (j0, k0: first node of the patch).
+// software pipeline in phase B of k_tile_bin_deposit<0>: measured slower (0.732 vs 0.726 ms/slice on config #2), stays off
+#ifndef QPIC_BIN_PIPE
+#define QPIC_BIN_PIPE 0
+#endif
 template <int MODE>
 inline size_t tile_bin_smem_bytes() {
     constexpr int NOUT = MODE == 0 ? 1 : 2;
@@ -1299,10 +1305,36 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                     }
                     mine[(q + 1) * TILE_CELLS] = e;
                 }
-                for (int i = 0; i < n; i++) {
-                    const int e = mine[i * TILE_CELLS];
-                    visit(e >> 2, (e >> 1) & 1, e & 1);
-                    if (MODE == 0 && job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz)] = e;
+                if (MODE == 0 && QPIC_BIN_PIPE) {
+                    // software pipeline: the particle data of entry i+1 is in flight while entry i is accumulated (the entries
+                    // themselves sit in shared memory); 40 registers without it, so there is room
+                    const int pub = wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz);
+                    int e = n > 0 ? mine[0] : 0;
+                    double fy = 0.0, fz = 0.0, pv = 0.0;
+                    if (n > 0) {
+                        const int s = e >> 2;
+                        fy = P.fy_m[s], fz = P.fz_m[s], pv = val[s];
+                    }
+                    for (int i = 0; i < n; i++) {
+                        const int ce = e;
+                        const double cfy = fy, cfz = fz, cv = job.o[a].sign * pv;
+                        if (i + 1 < n) {
+                            e = mine[(i + 1) * TILE_CELLS];
+                            const int s = e >> 2;
+                            fy = P.fy_m[s], fz = P.fz_m[s], pv = val[s];
+                        }
+                        c00 += cv * (1 - cfy) * (1 - cfz);
+                        c10 += cv * cfy * (1 - cfz);
+                        c01 += cv * (1 - cfy) * cfz;
+                        c11 += cv * cfy * cfz;
+                        if (job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + pub] = ce;
+                    }
+                } else {
+                    for (int i = 0; i < n; i++) {
+                        const int e = mine[i * TILE_CELLS];
+                        visit(e >> 2, (e >> 1) & 1, e & 1);
+                        if (MODE == 0 && job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz)] = e;
+                    }
                 }
             } else {
                 // crowded target (strong compression): scan the source window in order
@@ -1342,6 +1374,9 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
 // each list in slot order, lists in this order: deterministic.  No binning, no sort, no halo source cells, and a particle
 // of cell (jt, kt) that feeds both outputs gets its 1 / (1 + psi_middle) gather once.  Deposited values as in
 // k_tile_bin_deposit<1>: n py_next / (1 + psi_middle@particle), n pz_next / (1 + psi_middle@particle) (:483-485).
+#ifndef QPIC_AB_LIST
+#define QPIC_AB_LIST 0  // development A/B switches (timing only, wrong results): 1 = no psi_middle gather in the own-cell list, 2 = own-cell list only
+#endif
 #ifndef QPIC_LIST_MINB
 #define QPIC_LIST_MINB 3  // 64 registers: measured 0.794 ms/slice vs 0.931 (90 registers, 2 blocks / SM) and 0.829 (48, spills)
 #endif
@@ -1390,12 +1425,19 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             const int s = e >> 2, hy = (e >> 1) & 1, hz = e & 1;
             if (hy | hz) {
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
+#if QPIC_AB_LIST == 1
+                const double w = 1 + fy * fz;
+#else
                 const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw, fy, fz);
+#endif
                 const double nw = job.nw[s];
                 if (hy) add_y(nw * pyn[s] / w, fy - 0.5, fz);
                 if (hz) add_z(nw * pzn[s] / w, fy, fz - 0.5);
             }
         }
+#if QPIC_AB_LIST == 2
+        if (false)
+#endif
         for (int i = 0; i < n_y; i++) {
             const int e = e_y;
             if (i + 1 < n_y) e_y = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_y];
@@ -1406,6 +1448,9 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
                 add_y(job.nw[s] * pyn[s] / w, fy + 0.5, fz);
             }
         }
+#if QPIC_AB_LIST == 2
+        if (false)
+#endif
         for (int i = 0; i < n_z; i++) {
             const int e = e_z;
             if (i + 1 < n_z) e_z = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_z];
@@ -1461,6 +1506,168 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
     jzn += acc[5 * TILE_CELLS + (ay - 1) * TILE_ACC + az];
     jzn += acc[6 * TILE_CELLS + ay * TILE_ACC + az - 1];
     jzn += acc[7 * TILE_CELLS + (ay - 1) * TILE_ACC + az - 1];
+    job.o[0].out[t] = jyn;
+    job.o[1].out[t] = jzn;
+    if (job.b_src) {
+        // same expressions as k_p2_rows_b_forward
+        const int jp = wrap_inc(jt, g.ny), kp = wrap_inc(kt, g.nz);
+        const int jq = (jt == g.ny - 1) ? 0 : jt;
+        const double djz_dxi = (job.b_jz[t] - jzn) * g.inv_dx;
+        const double djy_dxi = (job.b_jy[t] - jyn) * g.inv_dx;
+        const double jxt = job.b_jx[t];
+        job.b_src[t] = make_double2(-job.b_D * job.b_by[t] - (job.b_jx[jt * g.nz + kp] - jxt) * g.inv_dz + djz_dxi,
+                                    -job.b_D * job.b_bz[jq * g.nz + kt] + (job.b_jx[jp * g.nz + kt] - jxt) * g.inv_dy - djy_dxi);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ jy / jz, one visit per particle
+// Single-GPU successor of k_tile_list_deposit (third session).  There a thread owns a STAGGERED target cell of both outputs and
+// walks three lists -- its own cell's and those of the cells above / to the right, filtering by the half-cell bits -- so every
+// list entry is scanned three times and a particle's 1 / (1 + psi_middle) is formed up to three times.  Here a thread owns the
+// UNSTAGGERED half-step cell (j, k), walks only that cell's list, and every particle is visited exactly once: its value
+// n p_next / (1 + psi_middle@particle) is formed once for both outputs and scattered to the thread's private NODE sums --
+// jy nodes (j-1 .. j+1) x (k, k+1) and jz nodes (j, j+1) x (k-1 .. k+1), 12 registers -- in list (= ascending slot) order.
+// After a barrier node (J, K) adds the six sums the cells around it hold for it, in a fixed order.  Deterministic; per
+// particle the products are the reference's (value * wy) * wz (src/array_utils.cpp:75-82 on the staggered grids of
+// src/System_3d.cpp:190-193).  Measured on config #2: own-list-only work of the old kernel was 11 us of its 29.5 us.
+// Block = (LIST_TY + 2) x (LIST_TZ + 2) = 16 x 18 = 288 threads (9 full warps): thread (ay, az) <-> cell (j0 - 1 + ay, k0 - 1 + az),
+// nodes of the block = cells with 1 <= ay <= LIST_TY, 1 <= az <= LIST_TZ.
+constexpr int LIST_TY = 14, LIST_TZ = 16;
+constexpr int LIST_BY = LIST_TY + 2, LIST_BZ = LIST_TZ + 2, LIST_THREADS = LIST_BY * LIST_BZ;
+
+// Measured on config #2 (gpurun_out, third session; whole-slice times): 3 blocks / SM (72 registers, spills) 0.742 ms, with the
+// two-deep pipeline 0.781 (more spills); 2 blocks / SM (96 registers, no spills) 0.731, with the pipeline 0.722.  The three-list
+// kernel: 0.762.
+#ifndef QPIC_CELL_MINB
+#define QPIC_CELL_MINB 2
+#endif
+#ifndef QPIC_CELL_PIPE
+#define QPIC_CELL_PIPE 1
+#endif
+__global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + 5);
+    __shared__ double acc[12 * LIST_THREADS];
+    const int ay = threadIdx.y, az = threadIdx.x;
+    const int tid = ay * LIST_BZ + az;
+    const int j0 = blockIdx.y * LIST_TY, k0 = blockIdx.x * LIST_TZ;
+    const int jt = j0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped cell of this thread
+    const int jw = wrap_near(jt, g.ny), kw = wrap_near(kt, g.nz);
+    const int cell = jw * g.nz + kw;
+    const int n = job.bin_cnt[cell];
+    const double * __restrict__ pyn = job.o[0].val;
+    const double * __restrict__ pzn = job.o[1].val;
+    // psi_middle at the four nodes of this cell: every particle of the list gathers from them (src/System_3d.cpp:480-482)
+    const int jw1 = wrap_inc(jw, g.ny), kw1 = wrap_inc(kw, g.nz);
+    const double p00 = job.psi_mid[jw * g.nz + kw], p10 = job.psi_mid[jw1 * g.nz + kw], p01 = job.psi_mid[jw * g.nz + kw1],
+                 p11 = job.psi_mid[jw1 * g.nz + kw1];
+    // jy node sums: ym* = row j-1, y0* = row j, yp* = row j+1; second index: column k / k+1.  jz: z*m = column k-1, z*0 = k, z*p = k+1.
+    double ym0 = 0.0, ym1 = 0.0, y00 = 0.0, y01 = 0.0, yp0 = 0.0, yp1 = 0.0;
+    double z0m = 0.0, z1m = 0.0, z00 = 0.0, z10 = 0.0, z0p = 0.0, z1p = 0.0;
+    auto visit5 = [&](double fy, double fz, double nw, double vy0, double vz0, int hy, int hz) {
+        // gather_node's expression on the preloaded corners
+        const double w = 1 + (p00 * (1 - fy) * (1 - fz) + p10 * fy * (1 - fz) + p01 * (1 - fy) * fz + p11 * fy * fz);
+        const double vy = nw * vy0 / w, vz = nw * vz0 / w;
+        {
+            // jy: staggered by dy/2 in y -- the lower node row is j (upper half of the cell) or j-1 (lower half)
+            const double wy = hy ? fy - 0.5 : fy + 0.5;
+            const double c00 = vy * (1 - wy) * (1 - fz), c10 = vy * wy * (1 - fz), c01 = vy * (1 - wy) * fz, c11 = vy * wy * fz;
+            ym0 += hy ? 0.0 : c00;
+            ym1 += hy ? 0.0 : c01;
+            y00 += hy ? c00 : c10;
+            y01 += hy ? c01 : c11;
+            yp0 += hy ? c10 : 0.0;
+            yp1 += hy ? c11 : 0.0;
+        }
+        {
+            const double wz = hz ? fz - 0.5 : fz + 0.5;
+            const double c00 = vz * (1 - fy) * (1 - wz), c10 = vz * fy * (1 - wz), c01 = vz * (1 - fy) * wz, c11 = vz * fy * wz;
+            z0m += hz ? 0.0 : c00;
+            z1m += hz ? 0.0 : c10;
+            z00 += hz ? c00 : c01;
+            z10 += hz ? c10 : c11;
+            z0p += hz ? c01 : 0.0;
+            z1p += hz ? c11 : 0.0;
+        }
+    };
+    auto visit = [&](int s, int hy, int hz) { visit5(P.fy_m[s], P.fz_m[s], job.nw[s], pyn[s], pzn[s], hy, hz); };
+    if (n <= BIN_K) {
+#if QPIC_CELL_PIPE
+        // two-deep software pipeline: entry i+2 and the particle data of entry i+1 are in flight while entry i is processed
+        int e_cur = job.bin_lst[cell];
+        int e_nxt = n > 1 ? job.bin_lst[(size_t)g.n2 + cell] : 0;
+        int s = e_cur >> 2;
+        double fy = 0.0, fz = 0.0, nw = 0.0, vy0 = 0.0, vz0 = 0.0;
+        if (n > 0) {
+            fy = P.fy_m[s], fz = P.fz_m[s], nw = job.nw[s], vy0 = pyn[s], vz0 = pzn[s];
+        }
+        for (int i = 0; i < n; i++) {
+            const int e = e_cur;
+            const double cfy = fy, cfz = fz, cnw = nw, cvy = vy0, cvz = vz0;
+            e_cur = e_nxt;
+            if (i + 2 < n) e_nxt = job.bin_lst[(size_t)(i + 2) * g.n2 + cell];
+            if (i + 1 < n) {
+                s = e_cur >> 2;
+                fy = P.fy_m[s], fz = P.fz_m[s], nw = job.nw[s], vy0 = pyn[s], vz0 = pzn[s];
+            }
+            visit5(cfy, cfz, cnw, cvy, cvz, (e >> 1) & 1, e & 1);
+        }
+#else
+        // the next entry is requested before the current one is processed (entry -> slot -> particle data is a dependent chain)
+        int e_next = job.bin_lst[cell];
+        for (int i = 0; i < n; i++) {
+            const int e = e_next;
+            if (i + 1 < n) e_next = job.bin_lst[(size_t)(i + 1) * g.n2 + cell];
+            visit(e >> 2, (e >> 1) & 1, e & 1);
+        }
+#endif
+    } else {
+        // a crowded cell was not listed (strong compression): scan the source window in order
+        for (int dy_ = -1; dy_ <= 1; dy_++) {
+            for (int dz_ = -1; dz_ <= 1; dz_++) {
+                const int src = wrap_near(jt + dy_, g.ny) * g.nz + wrap_near(kt + dz_, g.nz);
+                const int e1 = start[src + 1];
+                for (int s = start[src]; s < e1; s++) {
+                    const int code = P.off_m[s];
+                    if (dy_ + (code & 7) - 2 != 0 || dz_ + ((code >> 3) & 7) - 2 != 0) continue;
+                    visit(s, (code >> 6) & 1, (code >> 7) & 1);
+                }
+            }
+        }
+    }
+    if (cancelled(ctl)) return;
+    QPIC_KERNEL_TAIL();
+    acc[0 * LIST_THREADS + tid] = ym0;
+    acc[1 * LIST_THREADS + tid] = ym1;
+    acc[2 * LIST_THREADS + tid] = y00;
+    acc[3 * LIST_THREADS + tid] = y01;
+    acc[4 * LIST_THREADS + tid] = yp0;
+    acc[5 * LIST_THREADS + tid] = yp1;
+    acc[6 * LIST_THREADS + tid] = z0m;
+    acc[7 * LIST_THREADS + tid] = z1m;
+    acc[8 * LIST_THREADS + tid] = z00;
+    acc[9 * LIST_THREADS + tid] = z10;
+    acc[10 * LIST_THREADS + tid] = z0p;
+    acc[11 * LIST_THREADS + tid] = z1p;
+    __syncthreads();
+    if (ay < 1 || ay > LIST_TY || az < 1 || az > LIST_TZ || jt >= g.ny || kt >= g.nz) return;
+    // node (jt, kt).  jy: what the cells of rows jt+1 / jt / jt-1 hold for their row j-1 / j / j+1, columns kt (their k) and kt-1
+    // (their k+1); jz likewise with rows and columns exchanged.  Fixed order.
+    const int t = jt * g.nz + kt;
+    const int up = tid + LIST_BZ, dn = tid - LIST_BZ;
+    double jyn = 0.0, jzn = 0.0;
+    jyn += acc[2 * LIST_THREADS + tid];
+    jyn += acc[3 * LIST_THREADS + tid - 1];
+    jyn += acc[4 * LIST_THREADS + dn];
+    jyn += acc[5 * LIST_THREADS + dn - 1];
+    jyn += acc[0 * LIST_THREADS + up];
+    jyn += acc[1 * LIST_THREADS + up - 1];
+    jzn += acc[8 * LIST_THREADS + tid];
+    jzn += acc[9 * LIST_THREADS + dn];
+    jzn += acc[10 * LIST_THREADS + tid - 1];
+    jzn += acc[11 * LIST_THREADS + dn - 1];
+    jzn += acc[6 * LIST_THREADS + tid + 1];
+    jzn += acc[7 * LIST_THREADS + dn + 1];
     job.o[0].out[t] = jyn;
     job.o[1].out[t] = jzn;
     if (job.b_src) {
