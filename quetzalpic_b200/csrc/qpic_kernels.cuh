@@ -1206,6 +1206,8 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
 #ifndef QPIC_BIN_PIPE
 #define QPIC_BIN_PIPE 0
 #endif
+// (Timing-only A/B builds of k_tile_bin_deposit<0> on config #2: without the accumulation visits of phase B the slice is 17 us
+// shorter, without publishing the lists 6 us: about 12 of its 16 us per launch are phase A, the sort and the launch itself.)
 template <int MODE>
 inline size_t tile_bin_smem_bytes() {
     constexpr int NOUT = MODE == 0 ? 1 : 2;
@@ -1374,9 +1376,8 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
 // each list in slot order, lists in this order: deterministic.  No binning, no sort, no halo source cells, and a particle
 // of cell (jt, kt) that feeds both outputs gets its 1 / (1 + psi_middle) gather once.  Deposited values as in
 // k_tile_bin_deposit<1>: n py_next / (1 + psi_middle@particle), n pz_next / (1 + psi_middle@particle) (:483-485).
-#ifndef QPIC_AB_LIST
-#define QPIC_AB_LIST 0  // development A/B switches (timing only, wrong results): 1 = no psi_middle gather in the own-cell list, 2 = own-cell list only
-#endif
+// (Timing-only A/B builds on config #2: the two neighbour lists cost 11 us of this kernel's 29.5 us per launch, the psi_middle gather
+// of the own-cell list 2.8 us -- which led to k_tile_cell_deposit below, now the single-GPU default.)
 #ifndef QPIC_LIST_MINB
 #define QPIC_LIST_MINB 3  // 64 registers: measured 0.794 ms/slice vs 0.931 (90 registers, 2 blocks / SM) and 0.829 (48, spills)
 #endif
@@ -1425,19 +1426,12 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             const int s = e >> 2, hy = (e >> 1) & 1, hz = e & 1;
             if (hy | hz) {
                 const double fy = P.fy_m[s], fz = P.fz_m[s];
-#if QPIC_AB_LIST == 1
-                const double w = 1 + fy * fz;
-#else
                 const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw, fy, fz);
-#endif
                 const double nw = job.nw[s];
                 if (hy) add_y(nw * pyn[s] / w, fy - 0.5, fz);
                 if (hz) add_z(nw * pzn[s] / w, fy, fz - 0.5);
             }
         }
-#if QPIC_AB_LIST == 2
-        if (false)
-#endif
         for (int i = 0; i < n_y; i++) {
             const int e = e_y;
             if (i + 1 < n_y) e_y = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_y];
@@ -1448,9 +1442,6 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
                 add_y(job.nw[s] * pyn[s] / w, fy + 0.5, fz);
             }
         }
-#if QPIC_AB_LIST == 2
-        if (false)
-#endif
         for (int i = 0; i < n_z; i++) {
             const int e = e_z;
             if (i + 1 < n_z) e_z = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_z];
