@@ -602,12 +602,21 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 }
 
 // psi source from positions (y,z) [at_mid = 0] or the half-step positions [at_mid = 1] -> fft_in
+// single GPU with the published lists: the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their
+// cell directly and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
+bool stayers_direct(const qpic_ctx * c) { return !c->dist.on && c->jyjz_lists && c->jyjz_cell; }
+
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
     j.nout = 1;
     j.o[0] = tile_output(c->P.nw_s, -1.0, 1, nullptr, c->fft_in, 0);
     if (!at_mid) return launch_tile(c, st, j, false, "k_tile_deposit_charge");
     const dim3 block(TILE_ACC + 2, TILE_ACC + 2);
+    if (stayers_direct(c)) {
+        // stayers from registers, movers through the lists; publishes the movers for k_tile_cell_deposit
+        QPIC_LAUNCH(k_tile_stay_deposit, tile_grid(c), block, tile_stay_smem_bytes(), st, c->ctl, c->g, c->start_b, c->P, j);
+        return check_launch(c, "k_tile_deposit_charge_mid");
+    }
     QPIC_LAUNCH(k_tile_bin_deposit<0>, tile_grid(c), block, tile_bin_smem_bytes<0>(), st, c->ctl, c->g, c->start_b, c->P, j);
     return check_launch(c, "k_tile_deposit_charge_mid");
 }
@@ -643,7 +652,7 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
         j.b_jy = c->f2[QPIC_F2_JY];
         j.b_jz = c->f2[QPIC_F2_JZ];
         j.b_D = c->prm.magnetic_field_D;
-        if (!c->dist.on && c->jyjz_cell) {
+        if (stayers_direct(c)) {
             // one visit per particle (k_tile_cell_deposit); A/B switch QPIC_JYJZ_CELL=0 selects the three-list kernel
             const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (c->g.ny + LIST_TY - 1) / LIST_TY);
             QPIC_LAUNCH(k_tile_cell_deposit, grid, dim3(LIST_BZ, LIST_BY), 0, st, c->ctl, c->g, c->start_b, c->P, j);

@@ -1512,6 +1512,138 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
 }
 
 
+// ------------------------------------------------------------------------------------------------ psi_middle source, stayers direct
+// Single-GPU successor of k_tile_bin_deposit<0> (third session).  In laminar flow ~98 % of the particles end their half step in
+// the cell they started in ("stayers": offset code 0, 0).  Those need no binning: thread (sy, sz), which is the source-cell thread
+// AND the target-cell thread of cell (j0 - 2 + sy, k0 - 2 + sz), keeps its own first four particles (codes, fractions, weights) in
+// registers -- all loaded in ONE round trip after the slot range, before the barrier -- and only the movers go through the
+// shared-memory lists.  After the barrier a target cell accumulates in ascending slot order as before: movers that arrived from
+// lower cells, then its stayers (from registers), then movers from higher cells.  Same sums bit for bit as k_tile_bin_deposit<0>;
+// the dependent chain of a block shrinks from [range -> codes -> barrier -> entry -> data ...] to [range -> codes + data -> barrier].
+// Published for the jy/jz deposit of the iteration (k_tile_cell_deposit): the MOVERS of every cell only (count + sorted entries);
+// that kernel finds the stayers through the slot range and the offset codes, like this one.
+constexpr int STAY_CODE = 2 | (2 << 3);  // pack_offset's bits 0-5 for oy = oz = 0
+
+inline size_t tile_stay_smem_bytes() { return (size_t)TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int)); }
+
+#ifndef QPIC_STAY_MINB
+#define QPIC_STAY_MINB 1
+#endif
+__global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MINB)
+    k_tile_stay_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + 1);
+    QPIC_DYN_SMEM(double, acc);                                   // [4][TILE_CELLS]
+    int * cnt = reinterpret_cast<int *>(acc + 4 * TILE_CELLS);    // [TILE_CELLS]
+    int * lst = cnt + TILE_CELLS;                                 // [BIN_K][TILE_CELLS]
+    const int sy = threadIdx.y, sz = threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
+    const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
+    const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
+    const int cell = wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz);
+    const double * __restrict__ val = job.o[0].val;
+    for (int i = tid; i < TILE_CELLS; i += nthreads) cnt[i] = 0;
+    const int s0 = start[cell], s1 = start[cell + 1];
+    const double ion = tile_prefetch_ion<1>(g, job, sy - 1, sz - 1, ju, ku);
+    // own particles, first four: everything a visit needs, one round trip
+    int code[4];
+    double pfy[4], pfz[4], pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const bool have = s0 + u < s1;
+        code[u] = have ? P.off_m[s0 + u] : STAY_CODE;
+        pfy[u] = have ? P.fy_m[s0 + u] : 0.0;
+        pfz[u] = have ? P.fz_m[s0 + u] : 0.0;
+        pv[u] = have ? val[s0 + u] : 0.0;
+    }
+    __syncthreads();  // counters are zero
+
+    // ---- phase A: movers of this source cell -> list of their target cell
+    auto bin = [&](int s, int c) {
+        if ((c & 63) == STAY_CODE) return;
+        const int ty = sy - 1 + (c & 7) - 2, tz = sz - 1 + ((c >> 3) & 7) - 2;
+        if (ty >= 0 && ty < TILE_ACC && tz >= 0 && tz < TILE_ACC) {
+            const int t = ty * TILE_ACC + tz;
+            const int pos = atomicAdd(&cnt[t], 1);
+            if (pos < BIN_K) lst[pos * TILE_CELLS + t] = (s << 2) | (((c >> 6) & 1) << 1) | ((c >> 7) & 1);
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (s0 + u < s1) bin(s0 + u, code[u]);
+    }
+    for (int s = s0 + 4; s < s1; s++) bin(s, P.off_m[s]);
+    __syncthreads();
+
+    // ---- phase B: ordered accumulation per target cell
+    const bool is_target = sy >= 1 && sy <= TILE_ACC && sz >= 1 && sz <= TILE_ACC;
+    const int ty = sy - 1, tz = sz - 1;
+    const int tcell = ty * TILE_ACC + tz;
+    if (is_target) {
+        double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
+        const double sign = job.o[0].sign;
+        auto add = [&](double fy, double fz, double v) {
+            c00 += v * (1 - fy) * (1 - fz);
+            c10 += v * fy * (1 - fz);
+            c01 += v * (1 - fy) * fz;
+            c11 += v * fy * fz;
+        };
+        auto visit = [&](int s) { add(P.fy_m[s], P.fz_m[s], sign * val[s]); };
+        const int n = cnt[tcell];
+        if (job.bin_cnt) job.bin_cnt[cell] = n;  // (halo cells: same value from the neighbour block)
+        int * mine = lst + tcell;                // entry i at mine[i * TILE_CELLS]
+        if (n <= BIN_K) {
+            for (int i = 1; i < n; i++) {  // insertion sort: ascending slot = canonical order
+                const int e = mine[i * TILE_CELLS];
+                int q = i - 1;
+                while (q >= 0 && mine[q * TILE_CELLS] > e) {
+                    mine[(q + 1) * TILE_CELLS] = mine[q * TILE_CELLS];
+                    q--;
+                }
+                mine[(q + 1) * TILE_CELLS] = e;
+            }
+            int i = 0;
+            for (; i < n; i++) {  // movers from lower cells
+                const int e = mine[i * TILE_CELLS];
+                if ((e >> 2) >= s0) break;
+                visit(e >> 2);
+                if (job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + cell] = e;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {  // stayers, from registers
+                if (s0 + u < s1 && (code[u] & 63) == STAY_CODE) add(pfy[u], pfz[u], sign * pv[u]);
+            }
+            for (int s = s0 + 4; s < s1; s++) {
+                if ((P.off_m[s] & 63) == STAY_CODE) visit(s);
+            }
+            for (; i < n; i++) {  // movers from higher cells
+                const int e = mine[i * TILE_CELLS];
+                visit(e >> 2);
+                if (job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + cell] = e;
+            }
+        } else {
+            // crowded target (strong compression): scan the source window in order (stayers included)
+            for (int dy_ = -1; dy_ <= 1; dy_++) {
+                for (int dz_ = -1; dz_ <= 1; dz_++) {
+                    const int src = mod_wrap(ju + dy_, g.ny) * g.nz + mod_wrap(ku + dz_, g.nz);
+                    const int e1 = start[src + 1];
+                    for (int s = start[src]; s < e1; s++) {
+                        const int c = P.off_m[s];
+                        if (dy_ + (c & 7) - 2 == 0 && dz_ + ((c >> 3) & 7) - 2 == 0) visit(s);
+                    }
+                }
+            }
+        }
+        acc[0 * TILE_CELLS + tcell] = c00;
+        acc[1 * TILE_CELLS + tcell] = c10;
+        acc[2 * TILE_CELLS + tcell] = c01;
+        acc[3 * TILE_CELLS + tcell] = c11;
+    }
+    QPIC_KERNEL_TAIL();
+    __syncthreads();
+    if (cancelled(ctl)) return;
+    if (is_target) tile_store_nodes<1>(ctl, g, job, acc, ty, tz, ju, ku, ion);
+}
+
 // ------------------------------------------------------------------------------------------------ jy / jz, one visit per particle
 // Single-GPU successor of k_tile_list_deposit (third session).  There a thread owns a STAGGERED target cell of both outputs and
 // walks three lists -- its own cell's and those of the cells above / to the right, filtering by the half-cell bits -- so every
@@ -1583,35 +1715,33 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
     };
     auto visit = [&](int s, int hy, int hz) { visit5(P.fy_m[s], P.fz_m[s], job.nw[s], pyn[s], pzn[s], hy, hz); };
     if (n <= BIN_K) {
-#if QPIC_CELL_PIPE
-        // two-deep software pipeline: entry i+2 and the particle data of entry i+1 are in flight while entry i is processed
-        int e_cur = job.bin_lst[cell];
-        int e_nxt = n > 1 ? job.bin_lst[(size_t)g.n2 + cell] : 0;
-        int s = e_cur >> 2;
-        double fy = 0.0, fz = 0.0, nw = 0.0, vy0 = 0.0, vz0 = 0.0;
-        if (n > 0) {
-            fy = P.fy_m[s], fz = P.fz_m[s], nw = job.nw[s], vy0 = pyn[s], vz0 = pzn[s];
+        // the list holds the MOVERS that ended their half step in this cell (k_tile_stay_deposit), sorted by slot; the cell's own
+        // stayers are the particles of its slot range whose offset code is (0, 0).  Ascending slot order = movers from lower
+        // cells, stayers, movers from higher cells.  Stayers are the bulk: their data is loaded two particles at a time.
+        const int s0 = start[cell], s1 = start[cell + 1];
+        int i = 0;
+        int e = n > 0 ? job.bin_lst[cell] : 0;
+        for (; i < n && (e >> 2) < s0; ) {
+            const int ce = e;
+            i++;
+            if (i < n) e = job.bin_lst[(size_t)i * g.n2 + cell];
+            visit(ce >> 2, (ce >> 1) & 1, ce & 1);
         }
-        for (int i = 0; i < n; i++) {
-            const int e = e_cur;
-            const double cfy = fy, cfz = fz, cnw = nw, cvy = vy0, cvz = vz0;
-            e_cur = e_nxt;
-            if (i + 2 < n) e_nxt = job.bin_lst[(size_t)(i + 2) * g.n2 + cell];
-            if (i + 1 < n) {
-                s = e_cur >> 2;
-                fy = P.fy_m[s], fz = P.fz_m[s], nw = job.nw[s], vy0 = pyn[s], vz0 = pzn[s];
-            }
-            visit5(cfy, cfz, cnw, cvy, cvz, (e >> 1) & 1, e & 1);
+        for (int sb = s0; sb < s1; sb += 2) {
+            const bool two = sb + 1 < s1;
+            const int sB = two ? sb + 1 : sb;
+            const int cA = P.off_m[sb], cB = P.off_m[sB];
+            const double fyA = P.fy_m[sb], fzA = P.fz_m[sb], nwA = job.nw[sb], vyA = pyn[sb], vzA = pzn[sb];
+            const double fyB = P.fy_m[sB], fzB = P.fz_m[sB], nwB = job.nw[sB], vyB = pyn[sB], vzB = pzn[sB];
+            if ((cA & 63) == STAY_CODE) visit5(fyA, fzA, nwA, vyA, vzA, (cA >> 6) & 1, (cA >> 7) & 1);
+            if (two && (cB & 63) == STAY_CODE) visit5(fyB, fzB, nwB, vyB, vzB, (cB >> 6) & 1, (cB >> 7) & 1);
         }
-#else
-        // the next entry is requested before the current one is processed (entry -> slot -> particle data is a dependent chain)
-        int e_next = job.bin_lst[cell];
-        for (int i = 0; i < n; i++) {
-            const int e = e_next;
-            if (i + 1 < n) e_next = job.bin_lst[(size_t)(i + 1) * g.n2 + cell];
-            visit(e >> 2, (e >> 1) & 1, e & 1);
+        for (; i < n; ) {
+            const int ce = e;
+            i++;
+            if (i < n) e = job.bin_lst[(size_t)i * g.n2 + cell];
+            visit(ce >> 2, (ce >> 1) & 1, ce & 1);
         }
-#endif
     } else {
         // a crowded cell was not listed (strong compression): scan the source window in order
         for (int dy_ = -1; dy_ <= 1; dy_++) {
