@@ -72,7 +72,7 @@ KERNEL_BYTES = {
     "k_fft_rows_b_backward": lambda N, P: 8.0 * (4 * N),
     # particles
     "k_particles_gamma": lambda N, P: 8.0 * (17.5 * P),
-    "k_particles_predict": lambda N, P: 8.0 * (22 * P),  # predictor + corrector: reads 14.5, writes 7.5 doubles per particle
+    "k_particles_predict": lambda N, P: 8.0 * (21.2 * P),  # predictor + corrector: reads 14.5, writes 6.5 doubles per particle (+ px in the last of the M passes)
     "k_particles_advance": lambda N, P: 8.0 * (15 * P),
     "k_particles_to_slots": lambda N, P: 8.0 * (15.5 * P),
     "k_end_of_slice": lambda N, P: 8.0 * (17 * N),
@@ -86,11 +86,13 @@ KERNEL_BYTES = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels on the bench workload's transverse shape, from the
-# ncu capture committed as profiles/r02_launches_ncu.csv (cold-cache replays: an upper bound on the in-graph traffic)
+# ncu captures committed as profiles/r03_ncu_full_summary.txt (`ncu --set full`, third session: predictor, jy/jz and psi_middle
+# deposits, column / row transforms, push) and profiles/r02_launches_ncu.csv (the others); cold-cache replays: an upper bound on
+# the in-graph traffic
 NCU_TRAFFIC = {
-    "k_tile_deposit_jy_jz": 49.33e6, "k_tile_deposit_charge_mid": 32.52e6, "k_tile_deposit_jx": 26.57e6, "k_tile_deposit_charge": 26.57e6,
-    "k_tile_deposit_rho_chi": 43.01e6, "k_particles_predict": 135.73e6, "k_particles_gamma": 85.90e6, "k_particles_advance": 103.64e6,
-    "k_particles_to_slots": 83.92e6, "k_fft_cols_solve": 4.61e6, "k_fft_rows_b_forward": 14.70e6, "k_fft_rows_b_backward": 4.23e6,
+    "k_tile_deposit_jy_jz": 62.86e6, "k_tile_deposit_charge_mid": 32.55e6, "k_tile_deposit_jx": 26.57e6, "k_tile_deposit_charge": 26.57e6,
+    "k_tile_deposit_rho_chi": 43.01e6, "k_particles_predict": 139.64e6, "k_particles_gamma": 85.90e6, "k_particles_advance": 103.83e6,
+    "k_particles_to_slots": 83.92e6, "k_fft_cols_solve": 4.44e6, "k_fft_rows_b_forward": 14.70e6, "k_fft_rows_b_backward": 4.23e6,
     "k_fft_rows_r2c": 2.11e6, "k_fft_rows_c2r": 2.17e6,
 }
 
