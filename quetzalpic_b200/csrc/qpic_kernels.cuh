@@ -1661,7 +1661,8 @@ constexpr int LIST_BY = LIST_TY + 2, LIST_BZ = LIST_TZ + 2, LIST_THREADS = LIST_
 
 // Measured on config #2 (gpurun_out, third session; whole-slice times): 3 blocks / SM (72 registers, spills) 0.742 ms, with the
 // two-deep pipeline 0.781 (more spills); 2 blocks / SM (96 registers, no spills) 0.731, with the pipeline 0.722.  The three-list
-// kernel: 0.762.
+// kernel: 0.762.  With the stayers-direct lists (0.704): stayers four at a time 0.744, epilogue operands prefetched at kernel start
+// 0.718 (spills), both 0.756 -- more registers per thread lose here even without spills.
 #ifndef QPIC_CELL_MINB
 #define QPIC_CELL_MINB 2
 #endif
