@@ -83,7 +83,9 @@ typedef enum {
     QPIC_F3_COUNT
 } qpic_field3d;
 
-/* wake_particle_2d members that persist between slices (src/containers.h:31-43) */
+/* wake_particle_2d members that persist between slices (src/containers.h:31-43).  gamma and px are kept for inspection: they are
+ * those of the last solved slice once the sweep has reached slice 0; mid-sweep they are refreshed every slice only with the
+ * environment variable QPIC_TRACK_GAMMA_PX=1 (two scattered stores per particle and slice otherwise spent for nothing). */
 typedef enum { QPIC_P_Y = 0, QPIC_P_Z, QPIC_P_PY, QPIC_P_PZ, QPIC_P_N, QPIC_P_GAMMA, QPIC_P_PX, QPIC_P_COUNT } qpic_particle_field;
 
 /* ---- lifetime.  Replaces the allocation part of System_3d::System_3d (src/System_3d.cpp:155-193). */

@@ -126,6 +126,7 @@ struct qpic_ctx {
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
+    bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
     double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
     double * partials = nullptr;  // border-sum partials of the fused potential fix-up, [world][4] (inside the region when distributed)
@@ -874,7 +875,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     }
     if (np > 0) {
         QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->dist.on ? (const int *)nullptr : c->perm_b,
-                         c->f2[QPIC_F2_PSI_MIDDLE], c->count, migrate_view(c));
+                         c->f2[QPIC_F2_PSI_MIDDLE], c->count, migrate_view(c), c->track_gamma_px ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_advance"));
     }
     if (c->dist.on) {
@@ -1278,6 +1279,8 @@ static int create_impl(qpic_ctx * c) {
     {
         const char * e = getenv("QPIC_JYJZ_LISTS");
         c->jyjz_lists = !(e && e[0] == '0');
+        const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
+        c->track_gamma_px = e3 && e3[0] == '1';
         const char * e2 = getenv("QPIC_JYJZ_CELL");
         c->jyjz_cell = !(e2 && e2[0] == '0');
         if (c->jyjz_lists && !p.force_general_deposit) {

@@ -741,8 +741,12 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
         P.px[p] = px;
     }
     P.gam[s] = gamma;
-    P.pxs[s] = px;
-    store_currents<true>(P, s, nw, gamma, px);
+    if (!want_invariants) {
+        // only when no B iteration follows are these read again (deposits at :390-397, the slice-end deposit); otherwise every
+        // predictor pass overwrites them before their first use
+        P.pxs[s] = px;
+        store_currents<true>(P, s, nw, gamma, px);
+    }
     if (want_invariants) {
         P.q[s] = q;
         P.ap[s] = a_particle;
@@ -864,7 +868,7 @@ struct MigrateView {
 // Slab-decomposed runs: the id of a particle is simply its slot (perm_b == NULL); a particle whose new cell belongs to a
 // neighbouring rank is appended to that rank's inbox and its own entry is parked in the extra "emigrated" bucket n2.
 __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b, const double * __restrict__ psi_middle,
-                                    int * __restrict__ count, MigrateView mig) {
+                                    int * __restrict__ count, MigrateView mig, int track_gamma_px) {
     QPIC_KERNEL_BEGIN(KID_k_particles_advance);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -876,8 +880,12 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
     const double py = P.pyn[s], pz = P.pzn[s];
     P.py[p] = py;
     P.pz[p] = pz;
-    P.gamma[p] = P.gam[s];
-    P.px[p] = P.pxs[s];
+    if (track_gamma_px || ctl->slice <= 1) {
+        // gamma, px by particle id exist for inspection only (qpic_download_particles): slice 0 rewrites them (k_particles_gamma), so
+        // only the push of slice 1 has to leave them behind -- unless the caller wants them after every slice (QPIC_TRACK_GAMMA_PX=1)
+        P.gamma[p] = P.gam[s];
+        P.px[p] = P.pxs[s];
+    }
     const double w = 1 + psi_particle;
     const double y = wrap_fast(P.y_s[s] + g.dx * py / w, g.ly);
     const double z = wrap_fast(P.z_s[s] + g.dx * pz / w, g.lz);
@@ -1145,6 +1153,7 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
     double c00[NOUT], c10[NOUT], c01[NOUT], c11[NOUT];
 #pragma unroll
     for (int a = 0; a < NOUT; a++) c00[a] = c10[a] = c01[a] = c11[a] = 0.0;
+    const bool stopped_early = RHO_CHI && ctl->stop_tag != 0;
     // chunks of 4 particles: all loads of a chunk are issued before the (ordered) accumulation
     for (int sb = s0; sb < s1; sb += 4) {
         double fy[4], fz[4], v[NOUT][4];
@@ -1155,7 +1164,11 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
             fz[u] = P.fz_b[s];
             if (RHO_CHI) {
                 const double gamma = P.gam[s];
-                const double vx = P.pxs[s] / gamma;
+                // px of the last executed iteration.  The predictor stores it in its last pass only; when the |B| stop condition
+                // ended the slice in an earlier pass (this deposit then still runs: rho / susceptibility of the stopping iteration
+                // are output, src/System_3d.cpp:520-527 before :545-550) it is rebuilt from gamma - px = 1 + psi, exact up to rounding.
+                const double px = stopped_early ? gamma - P.q[s] : P.pxs[s];
+                const double vx = px / gamma;
                 const double r = P.nw_s[s] / (1 - vx);
                 v[0][u] = r;
                 v[NOUT - 1][u] = -r / gamma;
