@@ -131,6 +131,48 @@ def test_eager_and_graph_paths_are_bit_identical_and_deterministic():
             assert np.array_equal(v, other[k]), f"{k} differs between runs: deposition must be order-deterministic"
 
 
+@pytest.mark.parametrize("n,ppc,a0", [((10, 48, 40), (2, 2), 1.6), ((8, 30, 64), (3, 1), 2.4)])
+def test_deposit_kernel_generations_agree(n, ppc, a0, monkeypatch):
+    """The single-GPU default (stayers direct: k_tile_stay_deposit + k_tile_cell_deposit, one visit per particle) against the pair that
+    slab-decomposed sweeps keep using (k_tile_bin_deposit<0> + k_tile_list_deposit, QPIC_JYJZ_CELL=0) and against the general sorted
+    path: same sums in different association orders -> 1e-12; the psi_middle source deposit itself is bit-identical between the two
+    tile kernels (same ascending-slot order), which shows in psi of the first slices."""
+    case = Case.synthetic(n=n, d=(0.125, 0.25, 0.25), M=3, ppc=ppc, a0=a0)
+    runs = {}
+    for name, env, kw in [("cell", "1", {}), ("list", "0", {}), ("general", "1", {"force_general_deposit": True})]:
+        monkeypatch.setenv("QPIC_JYJZ_CELL", env)
+        with case.make_solver(keep_slices_3d=True, **kw) as s:
+            assert s.solve_wakefield() == -1
+            runs[name] = {f: s.field3d(f) for f in FIELDS} | {f + "_s": s.field3d(f, per_slice=True) for f in SLICE_FIELDS}
+    for other in ("list", "general"):
+        for k, v in runs["cell"].items():
+            assert slice_rel_l2(runs[other][k], v) < 1e-12, (other, k)
+    # last slice solved first: no B field yet, so psi of slice nx-1 depends on the charge deposit only
+    assert np.array_equal(runs["cell"]["psi_s"][-1], runs["list"]["psi_s"][-1])
+
+
+def test_particle_gamma_px_tracking(monkeypatch):
+    """gamma, px by particle id are inspection data: valid at the end of a sweep by default, after every slice with
+    QPIC_TRACK_GAMMA_PX=1 (include/qpic_b200.h)"""
+    case = Case.synthetic(n=(6, 16, 16), d=(0.2, 0.25, 0.25), M=2, ppc=(1, 1), a0=1.5)
+    o = case.make_oracle()
+    o.solve_wakefield()
+    with case.make_solver() as s:
+        s.solve_wakefield()
+        for f in ["gamma", "px"]:
+            assert rel_l2(s.particles(f), o.particles(f)) < 1e-12, f
+    monkeypatch.setenv("QPIC_TRACK_GAMMA_PX", "1")
+    o = case.make_oracle()
+    o.begin()
+    for _ in range(3):
+        o.step_slice()
+    with case.make_solver() as s:
+        s.begin()
+        s.step(3)
+        for f in ["gamma", "px", "py", "y"]:
+            assert rel_l2(s.particles(f), o.particles(f)) < 1e-12, f
+
+
 def test_per_slice_parity_from_identical_state():
     """Lock-step: before every slice the oracle's particle + field state is injected into the CUDA solver, both advance
     one slice, and everything the slice produced is compared at 1e-12."""
