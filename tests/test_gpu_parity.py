@@ -131,7 +131,8 @@ def test_eager_and_graph_paths_are_bit_identical_and_deterministic():
             assert np.array_equal(v, other[k]), f"{k} differs between runs: deposition must be order-deterministic"
 
 
-@pytest.mark.parametrize("n,ppc,a0", [((10, 48, 40), (2, 2), 1.6), ((8, 30, 64), (3, 1), 2.4)])
+@pytest.mark.parametrize("n,ppc,a0", [((10, 48, 40), (2, 2), 1.6), ((8, 30, 64), (3, 1), 2.4), ((6, 9, 11), (3, 3), 1.8), ((6, 13, 29), (1, 1), 2.0),
+                                      ((5, 17, 15), (2, 4), 1.2)])
 def test_deposit_kernel_generations_agree(n, ppc, a0, monkeypatch):
     """The single-GPU default (stayers direct: k_tile_stay_deposit + k_tile_cell_deposit, one visit per particle) against the pair that
     slab-decomposed sweeps keep using (k_tile_bin_deposit<0> + k_tile_list_deposit, QPIC_JYJZ_CELL=0) and against the general sorted
