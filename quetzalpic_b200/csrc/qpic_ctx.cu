@@ -582,6 +582,9 @@ TileJob tile_job(qpic_ctx * c) {
         j.list_row0 = c->dist.on ? (j.tile_row0 * TILE - 1 + c->g.ny) % c->g.ny : 0;
         j.list_rows = c->dist.on ? (c->dist.v.ny_loc / TILE + 2) * TILE + 1 : c->g.ny;
     }
+    // node rows of the launched tile rows
+    j.cell_row0 = c->dist.on ? j.tile_row0 * TILE : 0;
+    j.cell_rows = c->dist.on ? (c->dist.v.ny_loc / TILE + 2) * TILE : c->g.ny;
     return j;
 }
 
@@ -603,9 +606,9 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 }
 
 // psi source from positions (y,z) [at_mid = 0] or the half-step positions [at_mid = 1] -> fft_in
-// single GPU with the published lists: the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their
-// cell directly and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
-bool stayers_direct(const qpic_ctx * c) { return !c->dist.on && c->jyjz_lists && c->jyjz_cell; }
+// with the published lists the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their cell directly
+// and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
+bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists && c->jyjz_cell; }
 
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
@@ -655,7 +658,7 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
         j.b_D = c->prm.magnetic_field_D;
         if (stayers_direct(c)) {
             // one visit per particle (k_tile_cell_deposit); A/B switch QPIC_JYJZ_CELL=0 selects the three-list kernel
-            const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (c->g.ny + LIST_TY - 1) / LIST_TY);
+            const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (j.cell_rows + LIST_TY - 1) / LIST_TY);
             QPIC_LAUNCH(k_tile_cell_deposit, grid, dim3(LIST_BZ, LIST_BY), 0, st, c->ctl, c->g, c->start_b, c->P, j);
             return check_launch(c, "k_tile_deposit_jy_jz");
         }
@@ -1337,6 +1340,8 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_tile_bin_deposit<0>);
         QPIC_PRELOAD(k_tile_bin_deposit<1>);
         QPIC_PRELOAD(k_tile_list_deposit);
+        QPIC_PRELOAD(k_tile_stay_deposit);
+        QPIC_PRELOAD(k_tile_cell_deposit);
         QPIC_PRELOAD(k_particles_predict<true>);
         QPIC_PRELOAD(k_particles_gamma);
         QPIC_PRELOAD(k_particles_advance);

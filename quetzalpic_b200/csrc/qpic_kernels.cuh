@@ -1080,6 +1080,7 @@ struct TileJob {
     int * bin_cnt;
     int * bin_lst;
     int list_row0, list_rows;
+    int cell_row0, cell_rows;  // k_tile_cell_deposit: node rows launched (0, ny on a single GPU)
     // jy/jz job on a single GPU: the node that has just formed jy_next, jz_next also forms the sources of the By + i Bz solve
     // (src/System_3d.cpp:489-495, :530-536, :555-564 incl. the :563 quirk) into b_src, so that the forward rows of that solve
     // load one complex array instead of seven real ones with their stencils.  NULL: the row kernel builds them.
@@ -1550,7 +1551,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
     int * lst = cnt + TILE_CELLS;                                 // [BIN_K][TILE_CELLS]
     const int sy = threadIdx.y, sz = threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
-    const int j0 = blockIdx.y * TILE, k0 = blockIdx.x * TILE;
+    const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
     const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
     const int cell = wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz);
     const double * __restrict__ val = job.o[0].val;
@@ -1687,11 +1688,16 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
     __shared__ double acc[12 * LIST_THREADS];
     const int ay = threadIdx.y, az = threadIdx.x;
     const int tid = ay * LIST_BZ + az;
-    const int j0 = blockIdx.y * LIST_TY, k0 = blockIdx.x * LIST_TZ;
-    const int jt = j0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped cell of this thread
+    // node rows [cell_row0, cell_row0 + cell_rows) are launched: the whole grid on a single GPU, the slab and one tile row on
+    // either side in a slab-decomposed sweep (rows wrap; cell_row0 + cell_rows + LIST_TY < 2 ny)
+    const int r0 = blockIdx.y * LIST_TY, k0 = blockIdx.x * LIST_TZ;
+    const int jt = job.cell_row0 + r0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped cell of this thread
     const int jw = wrap_near(jt, g.ny), kw = wrap_near(kt, g.nz);
     const int cell = jw * g.nz + kw;
-    const int n = job.bin_cnt[cell];
+    // movers exist only where the psi_middle source deposit of this rank published them
+    int lr = jw - job.list_row0;
+    lr += (lr < 0) ? g.ny : 0;
+    const int n = lr < job.list_rows ? job.bin_cnt[cell] : 0;
     const double * __restrict__ pyn = job.o[0].val;
     const double * __restrict__ pzn = job.o[1].val;
     // psi_middle at the four nodes of this cell: every particle of the list gathers from them (src/System_3d.cpp:480-482)
@@ -1785,10 +1791,10 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
     acc[10 * LIST_THREADS + tid] = z0p;
     acc[11 * LIST_THREADS + tid] = z1p;
     __syncthreads();
-    if (ay < 1 || ay > LIST_TY || az < 1 || az > LIST_TZ || jt >= g.ny || kt >= g.nz) return;
+    if (ay < 1 || ay > LIST_TY || az < 1 || az > LIST_TZ || r0 + ay - 1 >= job.cell_rows || kt >= g.nz) return;
     // node (jt, kt).  jy: what the cells of rows jt+1 / jt / jt-1 hold for their row j-1 / j / j+1, columns kt (their k) and kt-1
     // (their k+1); jz likewise with rows and columns exchanged.  Fixed order.
-    const int t = jt * g.nz + kt;
+    const int t = jw * g.nz + kt;
     const int up = tid + LIST_BZ, dn = tid - LIST_BZ;
     double jyn = 0.0, jzn = 0.0;
     jyn += acc[2 * LIST_THREADS + tid];
@@ -1807,12 +1813,12 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
     job.o[1].out[t] = jzn;
     if (job.b_src) {
         // same expressions as k_p2_rows_b_forward
-        const int jp = wrap_inc(jt, g.ny), kp = wrap_inc(kt, g.nz);
-        const int jq = (jt == g.ny - 1) ? 0 : jt;
+        const int jp = wrap_inc(jw, g.ny), kp = wrap_inc(kt, g.nz);
+        const int jq = (jw == g.ny - 1) ? 0 : jw;
         const double djz_dxi = (job.b_jz[t] - jzn) * g.inv_dx;
         const double djy_dxi = (job.b_jy[t] - jyn) * g.inv_dx;
         const double jxt = job.b_jx[t];
-        job.b_src[t] = make_double2(-job.b_D * job.b_by[t] - (job.b_jx[jt * g.nz + kp] - jxt) * g.inv_dz + djz_dxi,
+        job.b_src[t] = make_double2(-job.b_D * job.b_by[t] - (job.b_jx[jw * g.nz + kp] - jxt) * g.inv_dz + djz_dxi,
                                     -job.b_D * job.b_bz[jq * g.nz + kt] + (job.b_jx[jp * g.nz + kt] - jxt) * g.inv_dy - djy_dxi);
     }
 }
