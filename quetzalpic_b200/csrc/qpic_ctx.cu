@@ -126,6 +126,11 @@ struct qpic_ctx {
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
+    // experimental (QPIC_PREDICT_DEPOSIT=1, single GPU): stayers of the psi_middle source summed by the predictor (k_particles_predict_dep)
+    bool predict_deposit = false;
+    StayOut stay = {};
+    int * stay_cnt[2] = {nullptr, nullptr};
+    int cur_it = 0;
     bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
     double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
@@ -609,13 +614,24 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 // with the published lists the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their cell directly
 // and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
 bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists && c->jyjz_cell; }
+bool predict_deposit_on(const qpic_ctx * c) { return c->predict_deposit && stayers_direct(c) && c->stay.corn != nullptr; }
 
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
     j.nout = 1;
     j.o[0] = tile_output(c->P.nw_s, -1.0, 1, nullptr, c->fft_in, 0);
-    if (!at_mid) return launch_tile(c, st, j, false, "k_tile_deposit_charge");
+    if (!at_mid) {
+        if (predict_deposit_on(c)) j.clear_cnt = c->stay_cnt[0];  // the first predictor pass of the slice counts its movers there
+        return launch_tile(c, st, j, false, "k_tile_deposit_charge");
+    }
     const dim3 block(TILE_ACC + 2, TILE_ACC + 2);
+    if (predict_deposit_on(c)) {
+        // the predictor of this iteration left the stayers' corner sums and the mover lists (k_particles_predict_dep)
+        StayOut so = c->stay;
+        so.cnt = c->stay_cnt[c->cur_it & 1];
+        QPIC_LAUNCH(k_tile_assemble, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j, so, c->stay_cnt[(c->cur_it + 1) & 1]);
+        return check_launch(c, "k_tile_deposit_charge_mid");
+    }
     if (stayers_direct(c)) {
         // stayers from registers, movers through the lists; publishes the movers for k_tile_cell_deposit
         QPIC_LAUNCH(k_tile_stay_deposit, tile_grid(c), block, tile_stay_smem_bytes(), st, c->ctl, c->g, c->start_b, c->P, j);
@@ -798,7 +814,13 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     if (c->dist.on && !fast) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps run on the sort-free deposit path only");
     QPIC_TRY(enqueue_slice_head(c, fast, M > 0, M == 0));
     for (int it = 0; it < M; it++) {
-        if (np > 0) {
+        c->cur_it = it;
+        if (np > 0 && fast && predict_deposit_on(c)) {
+            StayOut so = c->stay;
+            so.cnt = c->stay_cnt[it & 1];
+            QPIC_LAUNCH(k_particles_predict_dep, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so);
+            QPIC_TRY(check_launch(c, "k_particles_predict"));
+        } else if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
             QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
                              (!fast || it == M - 1) ? 1 : 0);
@@ -933,6 +955,19 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     QPIC_TRY(dev_alloc(c, &c->perm_b, count));
     QPIC_TRY(dev_alloc(c, &c->perm_m, count));
     QPIC_TRY(dev_alloc(c, &c->tmp, count));
+    if (c->predict_deposit && count > 0) {
+        // experimental predictor-side deposit: per-cell corner sums, per-warp pieces, double-buffered mover counters, unsorted lists
+        const size_t n2 = (size_t)c->g.n2, nwarps = (count + 31) / 32;
+        if (!c->stay.corn) {
+            QPIC_TRY(dev_alloc(c, &c->stay.corn, 4 * n2));
+            QPIC_TRY(dev_alloc(c, &c->stay_cnt[0], n2));
+            QPIC_TRY(dev_alloc(c, &c->stay_cnt[1], n2));
+            QPIC_TRY(dev_alloc(c, &c->stay.lst, (size_t)BIN_K * n2));
+        }
+        QPIC_TRY(dev_alloc(c, &c->stay.lead, 4 * nwarps));
+        QPIC_TRY(dev_alloc(c, &c->stay.trail, 4 * nwarps));
+        c->stay.sign = -1.0;
+    }
     return QPIC_OK;
 }
 
@@ -1282,6 +1317,8 @@ static int create_impl(qpic_ctx * c) {
     {
         const char * e = getenv("QPIC_JYJZ_LISTS");
         c->jyjz_lists = !(e && e[0] == '0');
+        const char * e4 = getenv("QPIC_PREDICT_DEPOSIT");
+        c->predict_deposit = e4 && e4[0] == '1' && !D.on && !p.force_general_deposit;
         const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
         c->track_gamma_px = e3 && e3[0] == '1';
         const char * e2 = getenv("QPIC_JYJZ_CELL");
@@ -1482,6 +1519,9 @@ int qpic_begin(qpic_ctx * c) {
     const int zero2[] = {QPIC_F2_PSI, QPIC_F2_PSI_PREV, QPIC_F2_PSI_MIDDLE, QPIC_F2_JY, QPIC_F2_JZ, QPIC_F2_JY_NEXT, QPIC_F2_JZ_NEXT,
                          QPIC_F2_BY_CUR, QPIC_F2_BZ_CUR, QPIC_F2_RHO_ION};
     for (int f : zero2) QPIC_CUDA(c, cudaMemsetAsync(c->f2[f], 0, sizeof(double) * n2, c->stream));
+    for (int * cnt : c->stay_cnt) {
+        if (cnt) QPIC_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * n2, c->stream));
+    }
     Ctl init;
     init.slice = g.nx - 1;
     init.stop_tag = 0;

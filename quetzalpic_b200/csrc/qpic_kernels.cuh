@@ -1081,6 +1081,7 @@ struct TileJob {
     int * bin_lst;
     int list_row0, list_rows;
     int cell_row0, cell_rows;  // k_tile_cell_deposit: node rows launched (0, ny on a single GPU)
+    int * clear_cnt;           // experimental predictor-side deposit: mover counters cleared by the slice's first charge deposit (per node)
     // jy/jz job on a single GPU: the node that has just formed jy_next, jz_next also forms the sources of the By + i Bz solve
     // (src/System_3d.cpp:489-495, :530-536, :555-564 incl. the :563 quirk) into b_src, so that the forward rows of that solve
     // load one complex array instead of seven real ones with their stencils.  NULL: the row kernel builds them.
@@ -1118,6 +1119,7 @@ __device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g
     const int t = j * g.nz + k;
     const size_t off3 = (size_t)ctl->slice * g.n2 + t;
     const bool own = (unsigned)(j - job.own_row0) < (unsigned)job.own_rows;
+    if (job.clear_cnt) job.clear_cnt[t] = 0;
 #pragma unroll
     for (int a = 0; a < NOUT; a++) {
         const TileOutput & o = job.o[a];
@@ -1656,6 +1658,203 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
     __syncthreads();
     if (cancelled(ctl)) return;
     if (is_target) tile_store_nodes<1>(ctl, g, job, acc, ty, tz, ju, ku, ion);
+}
+
+// ------------------------------------------------------------------------------------------------ psi_middle source from the predictor
+// EXPERIMENTAL (QPIC_PREDICT_DEPOSIT=1, single GPU): the predictor's lanes hold consecutive slots, i.e. the particles of a cell
+// sit in neighbouring lanes, so the stayers of a cell can be summed where they are produced: k_particles_predict_dep does a
+// warp-segmented sum of the four corner contributions (key = slice-start cell; a shuffle tree in lane order: deterministic) and
+// the last lane of every run writes it -- to corn[c] when the cell's particles lie inside this warp, else to the warp's leading /
+// trailing piece.  Movers are appended to the per-cell lists with integer atomics.  k_tile_assemble then needs one round trip per
+// cell (slot range, mover count, corner sums) instead of the particle data: it chains the pieces, adds the (sorted) movers around
+// them, publishes the sorted mover lists for k_tile_cell_deposit and forms the nodes.
+struct StayOut {
+    double * corn;   // [4][n2]: corner sums (c00, c10, c01, c11) of the stayers of cells whose run lies inside one warp
+    double * lead;   // [nwarps][4]: run that continues from the previous warp (may also continue into the next one)
+    double * trail;  // [nwarps][4]: run that starts in this warp and continues into the next one
+    int * cnt;       // movers per target cell (zero on entry)
+    int * lst;       // [BIN_K][n2], unsorted
+    double sign;     // -1: the psi source deposits -n (src/System_3d.cpp:349-353)
+};
+
+__global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
+                                        StayOut so) {
+    QPIC_KERNEL_BEGIN(KID_k_particles_predict);
+    const int s_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool have = s_raw < P.np;
+    const int s = have ? s_raw : P.np - 1;  // the tail lanes of the last warp stay for the shuffles and repeat the last particle
+    const int warp_base = s_raw - lane;
+    const int c = P.cell_b[s];
+    // the cells of the slots next to this warp: does its first / last run continue beyond it?
+    const int key_before = warp_base > 0 ? P.cell_b[warp_base - 1] : -2;
+    const int key_after = warp_base + 32 < P.np ? P.cell_b[warp_base + 32] : -2;
+    const int jc = c / g.nz, kc = c - jc * g.nz;
+    const double fy = P.fy_b[s], fz = P.fz_b[s];
+    const double q = ld_stream(P.q + s), gamma = P.gam[s];
+    const double py = ld_stream(P.py_s + s), pz = ld_stream(P.pz_s + s);
+    const double t1y = ld_stream(P.t1y + s), t1z = ld_stream(P.t1z + s), dpy = ld_stream(P.dpy + s), dpz = ld_stream(P.dpz + s);
+    const double y0 = ld_stream(P.y_s + s), z0 = ld_stream(P.z_s + s);
+    const double a_particle = ld_stream(P.ap + s), nw = P.nw_s[s];
+    int js, ks;
+    double fys, fzs;
+    stagger(jc, fy, g.ny, js, fys);
+    stagger(kc, fz, g.nz, ks, fzs);
+    const double by_particle = gather4(by, g.nz, jc, wrap_inc(jc, g.ny), ks, wrap_inc(ks, g.nz), fy, fzs);
+    const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
+    if (cancelled(ctl)) return;  // uniform over the grid
+    QPIC_KERNEL_TAIL();
+    // ---- exactly k_particles_predict<true> from here ...
+    double pyn = py - t1y;
+    pyn += g.dx * gamma * dpy / q;
+    pyn -= g.dx * bz_particle;
+    double pzn = pz - t1z;
+    pzn += g.dx * gamma * dpz / q;
+    pzn += g.dx * by_particle;
+    const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
+    const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) / q;
+    const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) / q;
+    const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn / q, g.ly);
+    const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn / q, g.lz);
+    int jm, km;
+    double f1, f2;
+    locate(ym, g.dy, g.ny, jm, f1);
+    locate(zm, g.dz, g.nz, km, f2);
+    const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
+    const bool bad = oy < -1 || oy > 1 || oz < -1 || oz > 1 || !(f1 >= 0.0) || !(f2 >= 0.0);
+    const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc) : pack_offset(oy, oz, f1, f2, kc);
+    if (have) {
+        P.pyn[s] = pyn;
+        P.pzn[s] = pzn;
+        P.gam[s] = gamma_c;
+        if (store_px) P.pxs[s] = px_c;
+        store_currents<false>(P, s, nw, gamma_c, px_c);
+        P.fy_m[s] = f1;
+        P.fz_m[s] = f2;
+        P.off_m[s] = code;
+        if (bad) atomicExch(&ctl->fast_fail, 1);
+    }
+    // ---- ... and the psi_middle source: stayers summed per cell, movers listed
+    const bool stay = have && !bad && oy == 0 && oz == 0;
+    if (have && !bad && !stay) {
+        const int target = jm * g.nz + km;
+        const int pos = atomicAdd(&so.cnt[target], 1);
+        if (pos < BIN_K) so.lst[(size_t)pos * g.n2 + target] = (s << 2) | (((code >> 6) & 1) << 1) | ((code >> 7) & 1);
+    }
+    const double v = stay ? so.sign * nw : 0.0;
+    double c00 = v * (1 - f1) * (1 - f2), c10 = v * f1 * (1 - f2), c01 = v * (1 - f1) * f2, c11 = v * f1 * f2;
+    if (!stay) c00 = c10 = c01 = c11 = 0.0;  // (NaN positions of a blown-up run)
+    const int key = have ? c : -3 - lane;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int k2 = __shfl_up_sync(0xffffffffu, key, d);
+        const double t00 = __shfl_up_sync(0xffffffffu, c00, d), t10 = __shfl_up_sync(0xffffffffu, c10, d);
+        const double t01 = __shfl_up_sync(0xffffffffu, c01, d), t11 = __shfl_up_sync(0xffffffffu, c11, d);
+        if (lane >= d && k2 == key) {
+            c00 += t00;
+            c10 += t10;
+            c01 += t01;
+            c11 += t11;
+        }
+    }
+    const int key_next = __shfl_down_sync(0xffffffffu, key, 1);
+    const int key_first = __shfl_sync(0xffffffffu, key, 0);
+    if (have && (lane == 31 || key_next != key)) {
+        const bool from_before = key == key_first && key == key_before;
+        const bool into_after = lane == 31 && key == key_after;
+        const int w = warp_base >> 5;
+        if (from_before) {
+            so.lead[4 * w + 0] = c00, so.lead[4 * w + 1] = c10, so.lead[4 * w + 2] = c01, so.lead[4 * w + 3] = c11;
+        } else if (into_after) {
+            so.trail[4 * w + 0] = c00, so.trail[4 * w + 1] = c10, so.trail[4 * w + 2] = c01, so.trail[4 * w + 3] = c11;
+        } else {
+            so.corn[0 * (size_t)g.n2 + c] = c00;
+            so.corn[1 * (size_t)g.n2 + c] = c10;
+            so.corn[2 * (size_t)g.n2 + c] = c01;
+            so.corn[3 * (size_t)g.n2 + c] = c11;
+        }
+    }
+}
+
+// nodes of the psi_middle source from what k_particles_predict_dep left; block = TILE_ACC x TILE_ACC target cells as in k_tile_deposit.
+// cnt_next: the mover counters of the next iteration's predictor (double buffered) are cleared by the cells' owner threads.
+__global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, StayOut so,
+                                                              int * __restrict__ cnt_next) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + 1);
+    __shared__ double acc[4 * TILE_CELLS];
+    const int ay = threadIdx.y, az = threadIdx.x;
+    const int tcell = ay * TILE_ACC + az;
+    const int jt = blockIdx.y * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
+    const int cell = wrap_near(jt, g.ny) * g.nz + wrap_near(kt, g.nz);
+    const bool owner = ay >= 1 && az >= 1 && jt < g.ny && kt < g.nz;
+    const int s0 = start[cell], s1 = start[cell + 1];
+    const int n = so.cnt[cell];
+    const double ion = tile_prefetch_ion<1>(g, job, ay, az, jt, kt);
+    const double k00 = so.corn[0 * (size_t)g.n2 + cell], k10 = so.corn[1 * (size_t)g.n2 + cell], k01 = so.corn[2 * (size_t)g.n2 + cell],
+                 k11 = so.corn[3 * (size_t)g.n2 + cell];
+    const double * __restrict__ val = job.o[0].val;
+    double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
+    auto visit = [&](int s) {
+        const double fy = P.fy_m[s], fz = P.fz_m[s], v = so.sign * val[s];
+        c00 += v * (1 - fy) * (1 - fz);
+        c10 += v * fy * (1 - fz);
+        c01 += v * (1 - fy) * fz;
+        c11 += v * fy * fz;
+    };
+    auto stayers = [&]() {
+        if (s1 <= s0) return;
+        const int w0 = s0 >> 5, w1 = (s1 - 1) >> 5;
+        if (w0 == w1) {
+            c00 += k00, c10 += k10, c01 += k01, c11 += k11;
+        } else {
+            c00 += so.trail[4 * w0 + 0], c10 += so.trail[4 * w0 + 1], c01 += so.trail[4 * w0 + 2], c11 += so.trail[4 * w0 + 3];
+            for (int w = w0 + 1; w <= w1; w++) c00 += so.lead[4 * w + 0], c10 += so.lead[4 * w + 1], c01 += so.lead[4 * w + 2], c11 += so.lead[4 * w + 3];
+        }
+    };
+    if (n <= BIN_K) {
+        int e[BIN_K];
+        for (int i = 0; i < n; i++) e[i] = so.lst[(size_t)i * g.n2 + cell];
+        for (int i = 1; i < n; i++) {  // insertion sort: ascending slot
+            const int x = e[i];
+            int q = i - 1;
+            while (q >= 0 && e[q] > x) {
+                e[q + 1] = e[q];
+                q--;
+            }
+            e[q + 1] = x;
+        }
+        int i = 0;
+        for (; i < n && (e[i] >> 2) < s0; i++) visit(e[i] >> 2);
+        stayers();
+        for (; i < n; i++) visit(e[i] >> 2);
+        if (owner && job.bin_lst) {
+            for (int q = 0; q < n; q++) job.bin_lst[(size_t)q * g.n2 + cell] = e[q];
+        }
+    } else {
+        // crowded target (strong compression): scan the source window in order, stayers included
+        for (int dy_ = -1; dy_ <= 1; dy_++) {
+            for (int dz_ = -1; dz_ <= 1; dz_++) {
+                const int src = mod_wrap(jt + dy_, g.ny) * g.nz + mod_wrap(kt + dz_, g.nz);
+                const int e1 = start[src + 1];
+                for (int s = start[src]; s < e1; s++) {
+                    const int cd = P.off_m[s];
+                    if (dy_ + (cd & 7) - 2 == 0 && dz_ + ((cd >> 3) & 7) - 2 == 0) visit(s);
+                }
+            }
+        }
+    }
+    if (cancelled(ctl)) return;
+    if (owner) {
+        if (job.bin_cnt) job.bin_cnt[cell] = n;
+        if (cnt_next) cnt_next[cell] = 0;
+    }
+    QPIC_KERNEL_TAIL();
+    acc[0 * TILE_CELLS + tcell] = c00;
+    acc[1 * TILE_CELLS + tcell] = c10;
+    acc[2 * TILE_CELLS + tcell] = c01;
+    acc[3 * TILE_CELLS + tcell] = c11;
+    __syncthreads();
+    tile_store_nodes<1>(ctl, g, job, acc, ay, az, jt, kt, ion);
 }
 
 // ------------------------------------------------------------------------------------------------ jy / jz, one visit per particle
