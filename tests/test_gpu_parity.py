@@ -140,12 +140,14 @@ def test_deposit_kernel_generations_agree(n, ppc, a0, monkeypatch):
     tile kernels (same ascending-slot order), which shows in psi of the first slices."""
     case = Case.synthetic(n=n, d=(0.125, 0.25, 0.25), M=3, ppc=ppc, a0=a0)
     runs = {}
-    for name, env, kw in [("cell", "1", {}), ("list", "0", {}), ("general", "1", {"force_general_deposit": True})]:
+    for name, env, kw in [("cell", "1", {}), ("list", "0", {}), ("general", "1", {"force_general_deposit": True}), ("predict", "1", {})]:
         monkeypatch.setenv("QPIC_JYJZ_CELL", env)
+        # "predict": the stayers of the psi_middle source are summed by the predictor (warp-segmented reduction) and k_tile_assemble forms the nodes
+        monkeypatch.setenv("QPIC_PREDICT_DEPOSIT", "1" if name == "predict" else "0")
         with case.make_solver(keep_slices_3d=True, **kw) as s:
             assert s.solve_wakefield() == -1
             runs[name] = {f: s.field3d(f) for f in FIELDS} | {f + "_s": s.field3d(f, per_slice=True) for f in SLICE_FIELDS}
-    for other in ("list", "general"):
+    for other in ("list", "general", "predict"):
         for k, v in runs["cell"].items():
             assert slice_rel_l2(runs[other][k], v) < 1e-12, (other, k)
     # last slice solved first: no B field yet, so psi of slice nx-1 depends on the charge deposit only
