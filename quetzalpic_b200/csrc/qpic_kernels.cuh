@@ -1668,6 +1668,10 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
 // trailing piece.  Movers are appended to the per-cell lists with integer atomics.  k_tile_assemble then needs one round trip per
 // cell (slot range, mover count, corner sums) instead of the particle data: it chains the pieces, adds the (sorted) movers around
 // them, publishes the sorted mover lists for k_tile_cell_deposit and forms the nodes.
+// Measured (B200, in-graph timeline gpurun_out/r38_timeline_*.txt, config #2): k_tile_assemble 8.8 us against 15.6 us for
+// k_tile_stay_deposit, but the predictor grows from 29.8 to 36.6 us (it is bandwidth- AND issue-bound: ~100 more instructions and 32
+// more bytes per cell) and the jy/jz deposit from 23.6 to 26.8 us (the particle data it reads is no longer warmed in L2 by the
+// deposit before it): 0.700 vs 0.696 ms/slice -- a wash, so it stays off.  Config #3 (1024^2, M = 10) gains: 4.51 vs 4.68 ms/slice.
 struct StayOut {
     double * corn;   // [4][n2]: corner sums (c00, c10, c01, c11) of the stayers of cells whose run lies inside one warp
     double * lead;   // [nwarps][4]: run that continues from the previous warp (may also continue into the next one)
