@@ -1749,9 +1749,10 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     double c00 = v * (1 - f1) * (1 - f2), c10 = v * f1 * (1 - f2), c01 = v * (1 - f1) * f2, c11 = v * f1 * f2;
     if (!stay) c00 = c10 = c01 = c11 = 0.0;  // (NaN positions of a blown-up run)
     const int key = have ? c : -3 - lane;
-#pragma unroll
+    // keys are sorted, so once no lane finds its key d lanes below, none will at a larger distance: runs of 4-8 particles need 3 steps
     for (int d = 1; d < 32; d <<= 1) {
         const int k2 = __shfl_up_sync(0xffffffffu, key, d);
+        if (!__any_sync(0xffffffffu, lane >= d && k2 == key)) break;
         const double t00 = __shfl_up_sync(0xffffffffu, c00, d), t10 = __shfl_up_sync(0xffffffffu, c10, d);
         const double t01 = __shfl_up_sync(0xffffffffu, c01, d), t11 = __shfl_up_sync(0xffffffffu, c11, d);
         if (lane >= d && k2 == key) {
