@@ -126,8 +126,9 @@ struct qpic_ctx {
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
-    // experimental (QPIC_PREDICT_DEPOSIT=1, single GPU): stayers of the psi_middle source summed by the predictor (k_particles_predict_dep)
+    // stayers of the psi_middle source summed by the predictor (k_particles_predict_dep + k_tile_assemble); chosen by problem size, see alloc_particles
     bool predict_deposit = false;
+    int predict_deposit_mode = -1;  // -1 auto, 0 off, 1 on
     StayOut stay = {};
     int * stay_cnt[2] = {nullptr, nullptr};
     int cur_it = 0;
@@ -957,6 +958,15 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     QPIC_TRY(dev_alloc(c, &c->perm_b, count));
     QPIC_TRY(dev_alloc(c, &c->perm_m, count));
     QPIC_TRY(dev_alloc(c, &c->tmp, count));
+    // Predictor-side psi_middle source deposit (k_particles_predict_dep + k_tile_assemble): measured on B200 -- config #2 (512^2, 4 ppc)
+    // 0.700 vs 0.696 ms/slice (a wash), config #3 (1024^2, 4 ppc, M = 10) 4.50 vs 4.62, config #4 on one GPU (4096^2, 16 ppc) 133.4 vs
+    // 150.4: it wins when the per-iteration working set is far beyond L2 or a cell holds many particles (the tile kernel loads only
+    // four of them in its first round trip); config #4 on two GPUs 69.6 vs 79.0 ms/slice.  Auto rule: >= 8 particles per cell on average
+    // (per rank: of the whole grid's cells), or >= 2^20 cells.
+    if (!c->prm.force_general_deposit && c->jyjz_lists && c->jyjz_cell) {
+        const bool big = count >= 8 * (size_t)c->g.n2 || (size_t)c->g.n2 >= ((size_t)1 << 20);
+        c->predict_deposit = c->predict_deposit_mode == 1 || (c->predict_deposit_mode == -1 && big);
+    }
     if (c->predict_deposit && count > 0) {
         // experimental predictor-side deposit: per-cell corner sums, per-warp pieces, double-buffered mover counters, unsorted lists
         const size_t n2 = (size_t)c->g.n2, nwarps = (count + 31) / 32;
@@ -1319,8 +1329,11 @@ static int create_impl(qpic_ctx * c) {
     {
         const char * e = getenv("QPIC_JYJZ_LISTS");
         c->jyjz_lists = !(e && e[0] == '0');
+        // QPIC_PREDICT_DEPOSIT = 1 / 0 forces the predictor-side psi_middle deposit on / off; unset: decided from the problem size when
+        // the particles arrive (alloc_particles)
         const char * e4 = getenv("QPIC_PREDICT_DEPOSIT");
-        c->predict_deposit = e4 && e4[0] == '1' && !D.on && !p.force_general_deposit;
+        c->predict_deposit_mode = (e4 && (e4[0] == '0' || e4[0] == '1')) ? e4[0] - '0' : -1;
+        c->predict_deposit = false;
         const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
         c->track_gamma_px = e3 && e3[0] == '1';
         const char * e2 = getenv("QPIC_JYJZ_CELL");

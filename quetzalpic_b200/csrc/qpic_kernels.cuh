@@ -1686,13 +1686,15 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     const int s_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool have = s_raw < P.np;
-    const int s = have ? s_raw : P.np - 1;  // the tail lanes of the last warp stay for the shuffles and repeat the last particle
+    const int live = live_count(ctl, P.np);  // (slab-decomposed sweeps: the live particles of this rank)
+    if (s_raw - lane >= live) return;        // whole warp beyond the live range (uniform per warp)
+    const bool have = s_raw < live;
+    const int s = have ? s_raw : live - 1;  // the tail lanes of the last warp stay for the shuffles and repeat the last particle
     const int warp_base = s_raw - lane;
     const int c = P.cell_b[s];
     // the cells of the slots next to this warp: does its first / last run continue beyond it?
     const int key_before = warp_base > 0 ? P.cell_b[warp_base - 1] : -2;
-    const int key_after = warp_base + 32 < P.np ? P.cell_b[warp_base + 32] : -2;
+    const int key_after = warp_base + 32 < live ? P.cell_b[warp_base + 32] : -2;
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double fy = P.fy_b[s], fz = P.fz_b[s];
     const double q = ld_stream(P.q + s), gamma = P.gam[s];
@@ -1789,7 +1791,7 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(const Ctl * ctl, G
     __shared__ double acc[4 * TILE_CELLS];
     const int ay = threadIdx.y, az = threadIdx.x;
     const int tcell = ay * TILE_ACC + az;
-    const int jt = blockIdx.y * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
+    const int jt = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
     const int cell = wrap_near(jt, g.ny) * g.nz + wrap_near(kt, g.nz);
     const bool owner = ay >= 1 && az >= 1 && jt < g.ny && kt < g.nz;
     const int s0 = start[cell], s1 = start[cell + 1];
