@@ -177,3 +177,33 @@ def test_ipc_handle_exchange_over_gloo_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [(0, [0, 1], [64, 64]), (1, [0, 1], [64, 64])]
+
+
+def test_beam_lattice_and_units_match_reference(golden_dir):
+    """Host-side set-up of the beam path: bunch_particle_lattice restates System_3d::init_bunch_particles (reference
+    src/System_3d.cpp:767-803) -- positions, momenta and order are bit-identical to the unmodified reference's Bunch_000 output, weights
+    up to numpy's exp -- and plasma_units restates src/Plasma_units.h (checked against the banner the reference printed)."""
+    import os
+    import re
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cases import Case
+    from quetzalpic_b200 import plasma_units
+    g = np.load(os.path.join(golden_dir, "tiny_qed.npz"))
+    case = Case.from_toml("tiny_qed")
+    p = case.bunch_particles()
+    for f in ["x", "y", "z", "px", "py", "pz", "gamma"]:
+        assert np.array_equal(p[f], g[f"it0/bunch/{f}"]), f
+    units = plasma_units(case.base_frequency)
+    weight_norm = np.prod([case.l[a] / case.n[a] for a in range(3)]) * units["number_density_norm"]
+    assert np.allclose(p["n"] * weight_norm, g["it0/bunch/weight"], rtol=1e-14, atol=0)
+    # three bunches, one after the other: electrons (parabolic, 2x1x2 per cell), positrons (Gaussian, every cell), photons (cylinder)
+    sid = p["species_id"]
+    assert list(sid[np.r_[True, sid[1:] != sid[:-1]]]) == [0, 1, 3]
+    assert (sid == 1).sum() == case.n[0] * case.n[1] * case.n[2]
+    banner = str(g["stdout"])
+    for key, label, fmt in [("frequency", "Frequency", "{:.4g} rad/s"), ("density", "Density", "{:.4g} cm^-3"), ("wavelength", "Wavelength", "{:.4g} cm")]:
+        m = re.search(label + r" (\S+) ", banner)
+        assert m and float(m.group(1)) == float(fmt.split(" ")[0].format(units[key])), (key, m.group(1) if m else None)
+    m = re.search(r"Schwinger field in plasma units: (\S+)", banner)
+    assert float(m.group(1)) == float("{:.4g}".format(units["field_schwinger"]))
