@@ -961,13 +961,14 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     // Predictor-side psi_middle source deposit (k_particles_predict_dep + k_tile_assemble): measured on B200 -- config #2 (512^2, 4 ppc)
     // 0.700 vs 0.696 ms/slice (a wash), config #3 (1024^2, 4 ppc, M = 10) 4.50 vs 4.62, config #4 on one GPU (4096^2, 16 ppc) 133.4 vs
     // 150.4: it wins when the per-iteration working set is far beyond L2 or a cell holds many particles (the tile kernel loads only
-    // four of them in its first round trip); config #4 on two GPUs 69.6 vs 79.0 ms/slice.  Auto rule (single GPU): >= 8 particles per cell
-    // on average, or >= 2^20 cells.
+    // four of them in its first round trip); config #4 on two GPUs 69.6 vs 79.0 ms/slice.  Auto rule: >= 8 particles per cell on average,
+    // or >= 2^20 cells.
     if (!c->prm.force_general_deposit && c->jyjz_lists && c->jyjz_cell) {
-        // (slab-decomposed sweeps: `count` is the capacity of the arrays, which says nothing about the density; there the path is
-        // taken only on request, QPIC_PREDICT_DEPOSIT=1 -- it was validated on 2 GPUs, config #4: 69.6 vs 79.0 ms/slice)
-        const bool big = count >= 8 * (size_t)c->g.n2 || (size_t)c->g.n2 >= ((size_t)1 << 20);
-        c->predict_deposit = c->predict_deposit_mode == 1 || (c->predict_deposit_mode == -1 && big && !c->dist.on);
+        // (slab-decomposed sweeps: `count` is the capacity of the arrays; the density follows from the particles this rank was handed,
+        // which sit on 1 / world of the cells.  Validated on 2 GPUs, config #4: 69.6 vs 79.0 ms/slice.)
+        const size_t held = c->dist.on ? (size_t)c->dist.live0 * (size_t)c->prm.dist_world : count;
+        const bool big = held >= 8 * (size_t)c->g.n2 || (size_t)c->g.n2 >= ((size_t)1 << 20);
+        c->predict_deposit = c->predict_deposit_mode == 1 || (c->predict_deposit_mode == -1 && big);
     }
     if (c->predict_deposit && count > 0) {
         // experimental predictor-side deposit: per-cell corner sums, per-warp pieces, double-buffered mover counters, unsorted lists
