@@ -158,6 +158,10 @@ class Oracle:
         p = self.L.qo_particles(self.ctx, PARTICLE_FIELDS.index(name))
         return np.ctypeslib.as_array(p, shape=(max(self.particle_count, 1),))[: self.particle_count]
 
+    def set_particles(self, name, value):
+        """overwrite one particle field (the views above alias the oracle's memory)"""
+        self.particles(name)[:] = np.asarray(value, dtype=np.float64)
+
     def field2d(self, name):
         p = self.L.qo_field2d_ptr(self.ctx, FIELDS_2D.index(name))
         return np.ctypeslib.as_array(p, shape=(self.ny, self.nz))

@@ -506,7 +506,7 @@ int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bo
     } else {
         QPIC_LAUNCH(k_fft_cols_solve<false>, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan, c->fy.tw, c->spec, ncols, ncols, L.spb, c->sy, c->sz, nz, D);
     }
-    return check_launch(c, "k_fft_cols_solve");
+    return check_launch(c, full ? "k_fft_cols_solve_b" : "k_fft_cols_solve");
 }
 
 // real solve: fft_in -> raw (= solution / ny / nz).  With fixed_dst != NULL and both axes on the power-of-two engine the
@@ -1541,6 +1541,15 @@ int qpic_begin(qpic_ctx * c) {
     for (int f : zero2) QPIC_CUDA(c, cudaMemsetAsync(c->f2[f], 0, sizeof(double) * n2, c->stream));
     for (int * cnt : c->stay_cnt) {
         if (cnt) QPIC_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * n2, c->stream));
+    }
+    // The per-slice datasets psi, rho, jx, jy, jz live in the output file of ONE time iteration in the reference (Output_writer is
+    // constructed per iteration, src/System_3d.cpp:209, and initialize_slice_array creates zero-filled datasets): slices a sweep
+    // never reaches -- it stopped on |B| > threshold_B -- must read 0, not the previous sweep's values.
+    for (int f = QPIC_F3_PSI; f < QPIC_F3_COUNT; f++) {
+        if (c->f3[f]) QPIC_CUDA(c, cudaMemsetAsync(c->f3[f], 0, sizeof(double) * n3, c->stream));
+    }
+    for (double * cut : c->xy) {
+        if (cut) QPIC_CUDA(c, cudaMemsetAsync(cut, 0, sizeof(double) * (size_t)g.nx * g.ny, c->stream));
     }
     Ctl init;
     init.slice = g.nx - 1;

@@ -15,6 +15,9 @@ Fixtures:
   laser_test_summary.npz             the shipped inputs/test/laser_test.toml (200^3): per-field min/max/L2 norm,
                                      per-slice L2 norms, on-axis lines [:, ny/2, nz/2], transverse lines through
                                      slice 100, and the value at [100,100,100]
+  baseline512_6slices_summary.npz    BASELINE config #2's transverse problem (512 x 512, 2 x 2 ppc, M = 5, a0 = 1) on a 6-slice box:
+                                     the same summary per field, transverse lines through slice 2, every 8th point of the
+                                     xy cuts and of slice 1                                         (python make_golden.py baseline512)
 """
 import os
 import shutil
@@ -99,6 +102,28 @@ def main():
             data = collect_qed(wd, log, 3)
         np.savez_compressed(os.path.join(HERE, "tiny_qed.npz"), **data)
         print("tiny_qed", data["it0/bunch/x"].shape, data["it0/photons/x"].shape, data["it1/photons/x"].shape)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "baseline512":
+        with tempfile.TemporaryDirectory() as wd:
+            log = run_reference(os.path.join(HERE, "inputs", "baseline512_6slices.toml"), wd)
+            data = collect(wd, log)
+        summary = {"stdout": data["stdout"], "stopped": data["stopped"]}
+        for nm in NAMES_3D:
+            a = data["f3/" + nm]
+            nx, ny, nz = a.shape
+            summary[nm + "/min"] = a.min()
+            summary[nm + "/max"] = a.max()
+            summary[nm + "/l2"] = np.linalg.norm(a)
+            summary[nm + "/slice_l2"] = np.sqrt((a ** 2).sum(axis=(1, 2)))
+            summary[nm + "/axis"] = a[:, ny // 2, nz // 2].copy()
+            summary[nm + "/line_y"] = a[2, :, nz // 2].copy()
+            summary[nm + "/line_z"] = a[2, ny // 2, :].copy()
+            summary[nm + "/line_y_off"] = a[1, :, nz // 2 + 37].copy()   # off-axis lines: the on-axis ones of by / bz vanish by symmetry
+            summary[nm + "/line_z_off"] = a[1, ny // 2 - 53, :].copy()
+            summary[nm + "/xy"] = data["xy/" + nm][:, ::8].copy()
+            summary[nm + "/plane"] = a[1, ::8, ::8].copy()
+        np.savez_compressed(os.path.join(HERE, "baseline512_6slices_summary.npz"), **summary)
+        print("baseline512_6slices summary written", data["f3/psi"].shape)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "beam":  # only the time-loop fixture (added after the others)
         with tempfile.TemporaryDirectory() as wd:

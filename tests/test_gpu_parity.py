@@ -356,3 +356,32 @@ def test_wave_breaking_statistics_within_bounds():
             assert abs(a.std() - b.std()) <= 1e-9 * b.std(), f
             assert abs(a.mean() - b.mean()) <= 1e-9 * max(b.std(), abs(b.mean())), f
             assert abs(np.abs(a).max() - np.abs(b).max()) <= 1e-9 * np.abs(b).max(), f
+
+
+def test_second_sweep_that_stops_early_leaves_unreached_slices_zero():
+    """Time loop of System_3d::run (src/System_3d.cpp:199-236): every iteration writes a fresh Fields file (Output_writer per iteration,
+    :209), so the per-slice datasets of slices a stopped sweep never reached are 0 -- not what the previous sweep of the same context
+    left there.  Sweep 1 runs to the end, sweep 2 trips |B| > threshold_B at slice 6: slices 1..5 must read 0, slice 0 is still emitted."""
+    nx, ny, nz = 10, 32, 32
+    case = Case.synthetic(n=(nx, ny, nz), d=(0.2, 0.1, 0.1), M=2, ppc=(1, 1), a0=1.0)
+    x = (np.arange(nx) * 0.2)[:, None, None]
+    y = (np.arange(ny) * 0.1)[None, :, None]
+    z = (np.arange(nz) * 0.1)[None, None, :]
+    bunch = -20000.0 * np.exp(-((x - 1.2) / 0.05) ** 2 - ((y - 1.6) / 0.5) ** 2 - ((z - 1.6) / 0.5) ** 2)
+    o = case.make_oracle()
+    o.set_bunch_sources(bunch, bunch)
+    o.solve_wakefield()
+    stop = o.stopped_at
+    assert 2 <= stop < nx - 1
+    with case.make_solver(keep_slices_3d=True, keep_xy_cuts=True) as s:
+        s.upload_bunch_sources(np.zeros_like(bunch), np.zeros_like(bunch))
+        assert s.solve_wakefield() == -1
+        assert np.abs(s.field3d("psi", per_slice=True)[1:stop]).max() > 0
+        s.upload_bunch_sources(bunch, bunch)
+        s.init_wake_particles(*case.particles)
+        assert s.solve_wakefield() == stop
+        for f in SLICE_FIELDS:
+            a = s.field3d(f, per_slice=True)
+            assert not a[1:stop].any(), f
+            assert slice_rel_l2(a[stop:], o.field3d(f, per_slice=True)[stop:]) < 1e-7, f
+            assert not s.xy_cut(f, per_slice=True)[1:stop].any(), f

@@ -45,6 +45,34 @@ def test_oracle_reproduces_reference_output(name, golden_dir):
             assert slice_rel_l2(a, b) < 1e-13, f
 
 
+def summary_errors(field, g, f, line_slice, off_slice=None):
+    """worst deviation of a full (nx, ny, nz) field from the summary lines / planes a make_golden.py summary fixture holds"""
+    nx, ny, nz = field.shape
+    out = [rel_l2(field[:, ny // 2, nz // 2], g[f + "/axis"]), abs(np.linalg.norm(field) - g[f + "/l2"]) / max(float(g[f + "/l2"]), 1e-300),
+           rel_l2(field[line_slice, :, nz // 2], g[f + "/line_y"]), rel_l2(field[line_slice, ny // 2, :], g[f + "/line_z"])]
+    if off_slice is not None:
+        out += [rel_l2(field[off_slice, :, nz // 2 + 37], g[f + "/line_y_off"]), rel_l2(field[off_slice, ny // 2 - 53, :], g[f + "/line_z_off"]),
+                rel_l2(field[off_slice, ::8, ::8], g[f + "/plane"])]
+    return max(out)
+
+
+def test_oracle_reproduces_reference_on_the_baseline_transverse_problem(golden_dir):
+    """BASELINE config #2's transverse problem (512 x 512 cells, 2 x 2 ppc, M = 5, a0 = 1; 6-slice box): the oracle against the
+    summary of the unmodified reference's output (tests/golden/make_golden.py baseline512).  Bit for bit on every stored line."""
+    g = np.load(os.path.join(golden_dir, "baseline512_6slices_summary.npz"))
+    case = Case.from_toml("baseline512_6slices")
+    assert case.n == (6, 512, 512) and case.particles[0].size == 1 << 20
+    o = case.make_oracle()
+    o.solve_wakefield()
+    assert o.stopped_at == -1 and not bool(g["stopped"])
+    for f in NAMES_3D + NAMES_SLICE:
+        a = o.field3d(f, per_slice=f in NAMES_SLICE)
+        assert np.array_equal(a[:, 256, 256], g[f + "/axis"]), f
+        assert np.array_equal(a[1, 256 - 53, :], g[f + "/line_z_off"]), f
+        assert np.array_equal(a[1, ::8, ::8], g[f + "/plane"]), f
+        assert summary_errors(a, g, f, 2, 1) == 0.0, f
+
+
 def test_stop_condition_slice_matches_reference(golden_dir):
     g = np.load(os.path.join(golden_dir, "tiny_bunch_stop.npz"))
     _, o = run_oracle_on_fixture("tiny_bunch_stop", g)
