@@ -94,6 +94,9 @@ void qpic_destroy(qpic_ctx * ctx);
 /* message of the last failure on ctx (ctx == NULL: of the last failed qpic_create in this thread) */
 const char * qpic_last_error(const qpic_ctx * ctx);
 int qpic_abi_version(void);
+/* hash of the sources this binary was compiled from (__graft_entry__.build embeds it); the Python loader refuses a library whose
+ * hash differs from the sources next to it, so a stale in-tree binary cannot be used silently */
+const char * qpic_source_hash(void);
 
 /* ---- inputs */
 /* a_sqr(i,j,k) = amplitude * exp(-sum_c (x_c - r0_c)^2 / w_c^2) at nodes x = i*dx ...; replaces init_a_sqr with

@@ -4,6 +4,7 @@
 // (reference src/System_3d.cpp:328-619) is a fixed sequence of kernels that read the slice index from device
 // memory, so it is captured ONCE into a CUDA graph and replayed nx-1 times; the host only polls the stop flag
 // every few dozen slices.  All field and particle arrays stay resident in HBM for the whole sweep.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -64,6 +65,11 @@ struct qpic_ctx {
     int cur = 0;          // host mirror of Ctl::slice
     int stopped_at = -1;
     int since_poll = 0;
+    // lagged poll (qpic_step without `done`): the control block is copied asynchronously behind the slices queued so far and looked
+    // at one polling interval later, so the host never waits for the device while it is only queueing work
+    bool lagged = false, snap_pending = false;
+    Ctl * ctl_snap = nullptr;  // pinned
+    cudaEvent_t ev_snap = nullptr;
 
     // device state
     Ctl * ctl = nullptr;
@@ -91,6 +97,15 @@ struct qpic_ctx {
     };
     FftLaunch rows_real, rows_cplx, cols_half, cols_full;
     bool pow2_y = false, pow2_z = false;
+    // one cooperative kernel per solve (k_p2_solve_real / k_p2_solve_b): single GPU, both axes on the power-of-two engine
+    struct FusedSolve {
+        bool on = false;
+        int threads = 0;
+        size_t smem = 0;
+        int grid_real = 0, grid_b = 0;
+        int log2spb_rows = 0, log2spb_cols = 0;
+        unsigned int * bar = nullptr;  // {arrival count, generation} of the grid barrier
+    } fused;
     double inv_scale = 0.0;  // 1/(ny*nz) when that is exactly representable (power of two), else 0 = divide
     struct InvSymbol {
         double D;
@@ -123,6 +138,7 @@ struct qpic_ctx {
         std::vector<void *> opened;                // cudaIpcOpenMemHandle mappings
     } dist;
     double2 * b_src = nullptr;                     // sources of the By + i Bz solve formed by the jy/jz deposit (TileJob::b_src)
+    double2 * pair_src = nullptr;                  // qpic_solve_helmholtz_pair_host: the two sources as one complex array
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
@@ -286,12 +302,13 @@ int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaun
         // as many sequences per block as it takes to cover the batch with <= 148 blocks, within the kernels' thread (register)
         // and shared-memory limits.
         int spb = (nseq + 147) / 148;
-        while (spb > 1 && (spb * e8 > lim.max_threads || sizeof(double2) * 2 * (size_t)spb * n > lim.max_dyn_smem)) spb--;
+        const size_t per_seq = sizeof(double2) * 2 * (size_t)p2_pad_len(n);  // two alternating (padded) exchange buffers per sequence
+        while (spb > 1 && (spb * e8 > lim.max_threads || spb * per_seq > lim.max_dyn_smem)) spb--;
         if (spb < 1) spb = 1;
         while (spb * e8 < 32) spb *= 2;
         L->spb = spb;
         L->threads = spb * e8;
-        L->smem = sizeof(double2) * 2 * (size_t)spb * n;  // two alternating exchange buffers per sequence
+        L->smem = spb * per_seq;
     } else {
         L->spb = 1;
         L->threads = pick_threads(n / 4);
@@ -518,6 +535,17 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     const bool fuse = fixed_dst != nullptr && c->pow2_y && c->pow2_z;
     if (fused) *fused = fuse;
     if (c->dist.on && !fuse) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the fused power-of-two solve");
+#ifndef QPIC_EMU
+    if (c->fused.on) {
+        const double * inv = nullptr;
+        QPIC_TRY(get_inv_symbol(c, D, false, &inv));
+        const SolveShape S = {c->fz.plan.log2n, c->fy.plan.log2n, c->fused.log2spb_rows, c->fused.log2spb_cols};
+        QPIC_LAUNCH_COOP(k_p2_solve_real, c->fused.grid_real, c->fused.threads, c->fused.smem, st, ctl, S, (const double2 *)c->fz.tw, (const double2 *)c->fy.tw,
+                         (const double *)c->fft_in, c->spec, fuse ? fixed_dst : c->raw, inv, c->spec_row0, c->spec_colsum, c->fused.bar, c->inv_scale, fuse ? 1 : 0,
+                         c->prm.psi_threshold - 1);
+        return check_launch(c, "k_fft_solve_real");
+    }
+#endif
     if (c->pow2_z) {
         QPIC_LAUNCH((c->dist.on ? k_p2_rows_r2c<true> : k_p2_rows_r2c<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
     } else {
@@ -859,6 +887,20 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         }
         QPIC_TRY(stream_depend(c, sb, sa));
         // By + i Bz in one complex solve
+#ifndef QPIC_EMU
+        if (c->fused.on) {
+            const bool pre = fast && c->jyjz_lists && c->b_src;
+            const double * inv = nullptr;
+            QPIC_TRY(get_inv_symbol(c, c->prm.magnetic_field_D, true, &inv));
+            const SolveShape S = {c->fz.plan.log2n, c->fy.plan.log2n, c->fused.log2spb_rows, c->fused.log2spb_cols};
+            auto kern = pre ? k_p2_solve_b<true> : k_p2_solve_b<false>;
+            QPIC_LAUNCH_COOP(kern, c->fused.grid_b, c->fused.threads, c->fused.smem, sa, c->ctl, S, (const double2 *)c->fz.tw, (const double2 *)c->fy.tw, c->g,
+                             c->prm.magnetic_field_D, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (const double *)c->f2[QPIC_F2_JX], (const double *)c->f2[QPIC_F2_JY],
+                             (const double *)c->f2[QPIC_F2_JZ], (const double *)c->f2[QPIC_F2_JY_NEXT], (const double *)c->f2[QPIC_F2_JZ_NEXT], (const double2 *)c->b_src,
+                             c->spec, inv, c->fused.bar, c->prm.threshold_B, it, c->inv_scale);
+            QPIC_TRY(check_launch(c, "k_fft_solve_b"));
+        } else
+#endif
         {
             const qpic_ctx::FftLaunch & R = c->rows_cplx;
             if (c->pow2_z) {
@@ -990,28 +1032,27 @@ int alloc_particles(qpic_ctx * c, size_t count) {
 //   stop condition  -> the sweep is over (src/System_3d.cpp:588-591);
 //   fast-path abort -> roll the slice back (By/Bz of the slice start = row i+1 of the 3-D arrays, or zero for the first
 //                      slice; nothing else the slice wrote is read before being rewritten) and schedule the general path.
-int poll_ctl(qpic_ctx * c) {
-    QPIC_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
-    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->since_poll = 0;
+int handle_ctl(qpic_ctx * c, const Ctl & seen) {
     if (c->dist.on) {
         static const char * why[] = {"", "an exchange barrier timed out (a peer stopped or the ranks diverged)", "more emigrants in one slice than the inbox holds",
                                      "particle_capacity exceeded after migration", "a particle moved further than the neighbouring slab"};
-        const int e = c->ctl_host->dist_error;
+        const int e = seen.dist_error;
         if (e != 0) return fail(c, QPIC_ERR_STATE, "distributed sweep failed on rank %d: %s", c->dist.v.rank, why[e > 0 && e < 5 ? e : 0]);
-        if (c->ctl_host->fast_fail != 0) {
+        if (seen.fast_fail != 0) {
             return fail(c, QPIC_ERR_UNSUPPORTED, "rank %d: a half step moved a particle by more than one cell; the sorted-deposit fallback is not available in distributed sweeps",
                         c->dist.v.rank);
         }
     }
-    if (c->ctl_host->stop_tag != 0) {
-        c->stopped_at = (c->ctl_host->stop_tag - 1) / STOP_TAG_STRIDE;
+    if (seen.stop_tag != 0) {
+        c->stopped_at = (seen.stop_tag - 1) / STOP_TAG_STRIDE;
         c->cur = c->stopped_at;
         c->done = true;
         return QPIC_OK;
     }
-    if (c->ctl_host->fast_fail != 0) {
-        const int slice = c->ctl_host->slice;
+    if (seen.fast_fail != 0) {
+        // (a lagged snapshot is as good as a fresh one here: once the flag is up every later kernel, including the slice counter, is
+        // a no-op until the host clears it)
+        const int slice = seen.slice;
         const size_t n2 = (size_t)c->g.n2;
         if (slice < c->g.nx - 1) {
             QPIC_CUDA(c, cudaMemcpyAsync(c->f2[QPIC_F2_BY_CUR], c->f3[QPIC_F3_BY] + n2 * (slice + 1), sizeof(double) * n2, cudaMemcpyDeviceToDevice, c->stream));
@@ -1020,6 +1061,7 @@ int poll_ctl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaMemsetAsync(c->f2[QPIC_F2_BY_CUR], 0, sizeof(double) * n2, c->stream));
             QPIC_CUDA(c, cudaMemsetAsync(c->f2[QPIC_F2_BZ_CUR], 0, sizeof(double) * n2, c->stream));
         }
+        *c->ctl_host = seen;
         c->ctl_host->fast_fail = 0;
         QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));
         QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1029,6 +1071,31 @@ int poll_ctl(qpic_ctx * c) {
         if (c->general_penalty < 4096) c->general_penalty *= 2;
         c->fast_aborts++;
     }
+    return QPIC_OK;
+}
+
+int poll_ctl(qpic_ctx * c) {
+    c->snap_pending = false;  // superseded by the fresh copy below
+    QPIC_CUDA(c, cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->since_poll = 0;
+    const Ctl seen = *c->ctl_host;
+    return handle_ctl(c, seen);
+}
+
+// the non-blocking variant: act on the snapshot requested one interval ago, request the next one
+int poll_ctl_lagged(qpic_ctx * c) {
+    c->since_poll = 0;
+    if (c->snap_pending) {
+        QPIC_CUDA(c, cudaEventSynchronize(c->ev_snap));
+        c->snap_pending = false;
+        const Ctl seen = *c->ctl_snap;
+        QPIC_TRY(handle_ctl(c, seen));
+        if (c->done || seen.fast_fail != 0) return QPIC_OK;  // (after a rollback the stream is idle: nothing to snapshot)
+    }
+    QPIC_CUDA(c, cudaMemcpyAsync(c->ctl_snap, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+    QPIC_CUDA(c, cudaEventRecord(c->ev_snap, c->stream));
+    c->snap_pending = true;
     return QPIC_OK;
 }
 
@@ -1085,7 +1152,7 @@ int launch_slices(qpic_ctx * c, int count) {
         if (!fast && c->general_left > 0) c->general_left--;
         c->cur--;
         launched++;
-        if (M > 0 && ++c->since_poll >= c->prm.stop_check_interval) QPIC_TRY(poll_ctl(c));
+        if (M > 0 && ++c->since_poll >= c->prm.stop_check_interval) QPIC_TRY(c->lagged ? poll_ctl_lagged(c) : poll_ctl(c));
     }
     return QPIC_OK;
 }
@@ -1111,6 +1178,14 @@ int resolve(qpic_ctx * c) {
 extern "C" {
 
 int qpic_abi_version(void) { return QPIC_ABI_VERSION; }
+
+#ifndef QPIC_SOURCE_HASH
+#define QPIC_SOURCE_HASH "unknown"
+#endif
+const char * qpic_source_hash(void) {
+    static const char tag[] = QPIC_SOURCE_HASH;  // "QPICSRC:<16 hex digits>" (the prefix lets build() find it in the file)
+    return std::strncmp(tag, "QPICSRC:", 8) == 0 ? tag + 8 : tag;
+}
 
 void qpic_default_params(qpic_params * p) {
     if (!p) return;
@@ -1146,6 +1221,8 @@ void qpic_destroy(qpic_ctx * c) {
     for (void * m : c->dist.opened) cudaIpcCloseMemHandle(m);
 #endif
     if (c->ctl_host) cudaFreeHost(c->ctl_host);
+    if (c->ctl_snap) cudaFreeHost(c->ctl_snap);
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1286,9 +1363,66 @@ static int create_impl(qpic_ctx * c) {
         QPIC_TRY(get_inv_symbol(c, p.magnetic_field_D, true, &unused));
     }
 
+#ifndef QPIC_EMU
+    // EXPERIMENT, off by default (QPIC_FUSED_SOLVE=1): one cooperative kernel per solve with grid-wide barriers between rows / columns /
+    // rows (single GPU, power-of-two axes up to 4096 points).  Measured on B200, config #2 (gpurun_out/r42_ab.log, r41_timeline*.txt):
+    // 686 us/slice against 658 for the three launches -- in the timeline build a fused solve takes 15.8 us against 13.1 + two launch gaps
+    // (a grid barrier costs ~1.3 us: drain the block's stores, one atomic round trip, one poll round trip), and a cooperative grid does
+    // not share the device with the concurrent jx-deposit branch.
+    // T threads per block: at least one sequence of either axis, 128 by default (QPIC_SOLVE_THREADS); the grid is the number of units of
+    // the widest phase, capped by what the device holds at once.
+    {
+        const char * e = getenv("QPIC_FUSED_SOLVE");
+        const int longest = g.ny > g.nz ? g.ny : g.nz;
+        if (!D.on && c->pow2_y && c->pow2_z && longest <= 4096 && (e && e[0] == '1')) {
+            int T = 128;
+            if (const char * t = getenv("QPIC_SOLVE_THREADS")) T = atoi(t);
+            if (T < 32 || (T & (T - 1)) != 0) T = 128;
+            while (T < longest / 8) T *= 2;
+            if (T > 512) T = 512;
+            qpic_ctx::FusedSolve & F = c->fused;
+            auto log2i = [](int v) {
+                int l = 0;
+                while ((1 << l) < v) l++;
+                return l;
+            };
+            F.threads = T;
+            F.log2spb_rows = log2i(T / (g.nz / 8));
+            F.log2spb_cols = log2i(T / (g.ny / 8));
+            const size_t s_rows = sizeof(double2) * 2 * ((size_t)p2_pad_len(g.nz) << F.log2spb_rows);
+            const size_t s_cols = sizeof(double2) * 2 * ((size_t)p2_pad_len(g.ny) << F.log2spb_cols);
+            F.smem = s_rows > s_cols ? s_rows : s_cols;
+            if (F.smem <= SMEM_OPTIN_LIMIT) {
+                if (F.smem > SMEM_DEFAULT_LIMIT) {
+                    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_solve_real, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem));
+                    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_solve_b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem));
+                    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_solve_b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem));
+                }
+                cudaDeviceProp prop;
+                QPIC_CUDA(c, cudaGetDeviceProperties(&prop, p.device));
+                int per_sm_real = 0, per_sm_b = 0, per_sm_b2 = 0;
+                QPIC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_real, k_p2_solve_real, T, F.smem));
+                QPIC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_p2_solve_b<true>, T, F.smem));
+                QPIC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b2, k_p2_solve_b<false>, T, F.smem));
+                if (per_sm_b2 < per_sm_b) per_sm_b = per_sm_b2;
+                auto units = [](int n, int log2spb) { return (n + (1 << log2spb) - 1) >> log2spb; };
+                const int u_real = std::max(units(g.ny / 2, F.log2spb_rows), units(g.nz / 2 + 1, F.log2spb_cols));
+                const int u_b = std::max(units(g.ny, F.log2spb_rows), units(g.nz, F.log2spb_cols));
+                if (prop.cooperativeLaunch && per_sm_real > 0 && per_sm_b > 0) {
+                    F.grid_real = std::min(u_real, per_sm_real * prop.multiProcessorCount);
+                    F.grid_b = std::min(u_b, per_sm_b * prop.multiProcessorCount);
+                    QPIC_TRY(dev_alloc(c, &F.bar, 2));
+                    F.on = true;
+                }
+            }
+        }
+    }
+#endif
     QPIC_TRY(dev_alloc(c, &c->ctl, 1));
     QPIC_TRY(dev_alloc(c, &c->ctl_scratch, 1));
     QPIC_CUDA(c, cudaMallocHost(&c->ctl_host, sizeof(Ctl)));
+    QPIC_CUDA(c, cudaMallocHost(&c->ctl_snap, sizeof(Ctl)));
+    QPIC_CUDA(c, cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
     if (D.on) {
         // the exchange region: same layout on every rank
         DistView & v = D.v;
@@ -1583,6 +1717,7 @@ int qpic_begin(qpic_ctx * c) {
     c->finished = false;
     c->began = true;
     c->since_poll = 0;
+    c->snap_pending = false;
     c->general_left = 0;
     c->general_penalty = 16;
     return QPIC_OK;
@@ -1600,7 +1735,9 @@ int qpic_step(qpic_ctx * c, int max_slices, int * done) {
     long want = (long)c->target - max_slices;
     if (want < -1) want = -1;
     c->target = (int)want;
+    c->lagged = (done == nullptr);
     if (!c->done) QPIC_TRY(launch_slices(c, c->cur - c->target));
+    c->lagged = false;
     if (done) {
         // the caller wants a definite answer: wait, and redo whatever a fast-path abort cancelled
         QPIC_TRY(resolve(c));
@@ -1802,6 +1939,29 @@ int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inou
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
     const int ny = c->g.ny, nz = c->g.nz;
+#ifndef QPIC_EMU
+    if (c->fused.on) {
+        // the sweep's own kernel (k_p2_solve_b with ready-made sources): (a, b) interleaved into one complex array on the host
+        if (!c->pair_src) QPIC_TRY(dev_alloc(c, &c->pair_src, n2, false));
+        std::vector<double2> h(n2);
+        for (size_t t = 0; t < n2; t++) h[t] = make_double2(inout_a[t], inout_b[t]);
+        QPIC_CUDA(c, cudaMemcpyAsync(c->pair_src, h.data(), sizeof(double2) * n2, cudaMemcpyHostToDevice, c->stream));
+        const double * inv = nullptr;
+        QPIC_TRY(get_inv_symbol(c, D, true, &inv));
+        const SolveShape S = {c->fz.plan.log2n, c->fy.plan.log2n, c->fused.log2spb_rows, c->fused.log2spb_cols};
+        QPIC_LAUNCH_COOP(k_p2_solve_b<true>, c->fused.grid_b, c->fused.threads, c->fused.smem, c->stream, c->ctl_scratch, S, (const double2 *)c->fz.tw,
+                         (const double2 *)c->fy.tw, c->g, D, c->fft_in, c->fft_in2, (const double *)nullptr, (const double *)nullptr, (const double *)nullptr,
+                         (const double *)nullptr, (const double *)nullptr, (const double2 *)c->pair_src, c->spec, inv, c->fused.bar,
+                         std::numeric_limits<double>::infinity(), 0, c->inv_scale);
+        QPIC_TRY(check_launch(c, "k_fft_solve_b"));
+        QPIC_CUDA(c, cudaMemcpyAsync(inout_a, c->fft_in, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
+        QPIC_CUDA(c, cudaMemcpyAsync(inout_b, c->fft_in2, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
+        QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+        QPIC_CUDA(c, cudaMemsetAsync(c->ctl_scratch, 0, sizeof(Ctl), c->stream));
+        QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
+        return QPIC_OK;
+    }
+#endif
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout_a, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in2, inout_b, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
     {

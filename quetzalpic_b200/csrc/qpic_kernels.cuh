@@ -75,9 +75,11 @@ enum KernelId {
     KID_k_bunch_advance,
     KID_k_bunch_advance_qed,
     KID_k_bunch_photon_compact,
+    KID_k_p2_solve_real,
+    KID_k_p2_solve_b,
     KID_COUNT
 };
-#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack", "k_xy_cut", "k_xy_lines", "k_bunch_locate_count", "k_bunch_scan_apply", "k_bunch_fill", "k_bunch_rank", "k_bunch_deposit", "k_bunch_gather", "k_bunch_advance", "k_bunch_advance_qed", "k_bunch_photon_compact" }
+#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack", "k_xy_cut", "k_xy_lines", "k_bunch_locate_count", "k_bunch_scan_apply", "k_bunch_fill", "k_bunch_rank", "k_bunch_deposit", "k_bunch_gather", "k_bunch_advance", "k_bunch_advance_qed", "k_bunch_photon_compact", "k_p2_solve_real", "k_p2_solve_b" }
 
 #ifdef QPIC_EMU
 #define QPIC_KERNEL_BEGIN(id) ((void)0)

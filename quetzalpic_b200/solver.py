@@ -30,7 +30,7 @@ SPECIES_IDS = {name: i for i, name in enumerate(SPECIES)}
 
 # every symbol include/qpic_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
-    "qpic_default_params", "qpic_create", "qpic_destroy", "qpic_last_error", "qpic_abi_version",
+    "qpic_default_params", "qpic_create", "qpic_destroy", "qpic_last_error", "qpic_abi_version", "qpic_source_hash",
     "qpic_set_laser_gaussian", "qpic_upload_a_sqr", "qpic_upload_bunch_sources", "qpic_init_wake_particles",
     "qpic_solve_wakefield", "qpic_begin", "qpic_step", "qpic_finish", "qpic_synchronize", "qpic_current_slice",
     "qpic_stopped_at", "qpic_download_field3d", "qpic_download_slice3d", "qpic_download_field2d",
@@ -159,12 +159,33 @@ class QpicLibrary:
 
 _product_library = None
 
+CSRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+ABI_HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "qpic_b200.h")
+
+
+def source_hash():
+    """sha256 (first 16 hex digits) over the CUDA sources and the ABI header: what __graft_entry__.build() embeds in the library"""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh", ".h"))) + [ABI_HEADER]
+    for path in files:
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
+
 
 def load_library():
-    """The product library, quetzalpic_b200/libqpic_b200.so (CUDA, sm_100a)."""
+    """The product library, quetzalpic_b200/libqpic_b200.so (CUDA, sm_100a).  Refuses a binary that was not built from the sources
+    next to it (the .so is git-ignored and travels with the tree: a stale one must not be used silently)."""
     global _product_library
     if _product_library is None:
-        _product_library = QpicLibrary(LIBRARY_PATH)
+        lib = QpicLibrary(LIBRARY_PATH)
+        lib.L.qpic_source_hash.restype = ctypes.c_char_p
+        built_from = lib.L.qpic_source_hash().decode()
+        if os.path.isdir(CSRC_DIR) and built_from != source_hash():
+            raise RuntimeError(f"{LIBRARY_PATH} was built from other sources (embedded hash {built_from}, sources {source_hash()}): "
+                               "rebuild it with python -c 'import __graft_entry__ as g; g.build()'")
+        _product_library = lib
     return _product_library
 
 

@@ -50,7 +50,8 @@ def test_config2_transverse_problem_matches_oracle_and_reference(golden_dir):
             assert summary_errors(a, g, f, 2, 1) < 1e-11, f
             ref_xy = g[f + "/xy"]
             got_xy = s.xy_cut(f, per_slice=f in SLICE_FIELDS)[:, ::8]
-            assert np.abs(got_xy - ref_xy).max() <= 1e-11 * max(np.abs(ref_xy).max(), 1e-300), f
+            scale = max(abs(float(g[f + "/min"])), abs(float(g[f + "/max"])), 1e-300)  # (the cut of ez lies in its symmetry plane: noise)
+            assert np.abs(got_xy - ref_xy).max() <= 1e-11 * scale, f
 
 
 def test_config2_per_slice_parity_from_identical_state():
@@ -70,7 +71,6 @@ def test_config2_per_slice_parity_from_identical_state():
     py0, pz0 = rng.normal(0.0, 0.4, y.size), rng.normal(0.0, 0.4, y.size)
     with case.make_solver(a_sqr=o.field3d("aSqr"), keep_slices_3d=True) as s:
         s.begin()
-        worst = 0.0
         for i in range(nx - 1, 0, -1):
             if i == nx - 1:
                 o.set_particles("py", py0)
@@ -87,17 +87,19 @@ def test_config2_per_slice_parity_from_identical_state():
             s.current_slice = i
             assert o.step_slice() == 0
             s.step(1)
+            # (the first slice of a neutral plasma has psi, ex ~ 1e-18: rounding noise, so errors are measured against at least
+            # 1e-6 per node -- the fields of this case are O(1e-2 .. 1))
+            floor = 1e-6 * np.sqrt(case.n[1] * case.n[2])
+            errs = {}
             for f in FIELDS:
                 ref = o.field3d(f)[i]
-                if np.linalg.norm(ref) > 0:
-                    worst = max(worst, rel_l2(s.slice3d(f, i), ref))
+                errs[f] = np.linalg.norm(s.slice3d(f, i) - ref) / max(np.linalg.norm(ref), floor)
             for f in SLICE_FIELDS:
                 ref = o.field3d(f, per_slice=True)[i]
-                if np.linalg.norm(ref) > 0:
-                    worst = max(worst, rel_l2(s.slice3d(f, i, per_slice=True), ref))
+                errs[f + "_s"] = np.linalg.norm(s.slice3d(f, i, per_slice=True) - ref) / max(np.linalg.norm(ref), floor)
             for f in ["y", "z", "py", "pz"]:
-                worst = max(worst, rel_l2(s.particles(f), o.particles(f)))
-            assert worst <= 1e-12, f"slice {i}: {worst}"
+                errs["p." + f] = rel_l2(s.particles(f), o.particles(f))
+            assert max(errs.values()) <= 1e-12, f"slice {i}: {errs}"
         assert s.fast_path_aborts == 0
 
 

@@ -46,13 +46,16 @@ def test_oracle_reproduces_reference_output(name, golden_dir):
 
 
 def summary_errors(field, g, f, line_slice, off_slice=None):
-    """worst deviation of a full (nx, ny, nz) field from the summary lines / planes a make_golden.py summary fixture holds"""
+    """worst deviation of a full (nx, ny, nz) field from the summary lines / planes a make_golden.py summary fixture holds, relative to
+    the field's largest value (lines on symmetry planes hold rounding noise only: ez, by, bz on the axis of a centred laser)"""
     nx, ny, nz = field.shape
-    out = [rel_l2(field[:, ny // 2, nz // 2], g[f + "/axis"]), abs(np.linalg.norm(field) - g[f + "/l2"]) / max(float(g[f + "/l2"]), 1e-300),
-           rel_l2(field[line_slice, :, nz // 2], g[f + "/line_y"]), rel_l2(field[line_slice, ny // 2, :], g[f + "/line_z"])]
+    scale = max(abs(float(g[f + "/min"])), abs(float(g[f + "/max"])), 1e-300)
+    pairs = [(field[:, ny // 2, nz // 2], g[f + "/axis"]), (field[line_slice, :, nz // 2], g[f + "/line_y"]), (field[line_slice, ny // 2, :], g[f + "/line_z"])]
     if off_slice is not None:
-        out += [rel_l2(field[off_slice, :, nz // 2 + 37], g[f + "/line_y_off"]), rel_l2(field[off_slice, ny // 2 - 53, :], g[f + "/line_z_off"]),
-                rel_l2(field[off_slice, ::8, ::8], g[f + "/plane"])]
+        pairs += [(field[off_slice, :, nz // 2 + 37], g[f + "/line_y_off"]), (field[off_slice, ny // 2 - 53, :], g[f + "/line_z_off"]),
+                  (field[off_slice, ::8, ::8], g[f + "/plane"])]
+    out = [np.abs(np.asarray(a) - np.asarray(b)).max() / scale for a, b in pairs]
+    out.append(abs(np.linalg.norm(field) - g[f + "/l2"]) / max(float(g[f + "/l2"]), 1e-300))
     return max(out)
 
 
