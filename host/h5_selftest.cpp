@@ -24,6 +24,17 @@ int main(int argc, char ** argv) {
         w.close();
     }
     {
+        // the small sample committed as tests/golden/h5_writer_sample.h5 (for readers this image does not have: h5py, h5dump)
+        H5Writer w(dir + "/sample.h5");
+        const double a[6] = {1.0, 2.0, 3.0, 4.0, 5.0, 6.0}, b[2] = {-0.5, 0.25};
+        H5Attribute steps{"steps", H5Attribute::F64_ARRAY, {0.1, 0.2, 0.3}, 0}, origin{"origin", H5Attribute::F64_ARRAY, {-0.05, 0.0, 0.15}, 0};
+        H5Attribute plane{"plane", H5Attribute::I32_SCALAR, {}, 1}, coord{"plane_coordinate", H5Attribute::F64_SCALAR, {2.5}, 0};
+        w.add_dataset("psi", {1, 2, 3}, a, {steps, origin});
+        w.add_dataset("ex", {1, 2}, b, {steps, origin, plane, coord});
+        w.add_dataset("x", {0}, nullptr, {});
+        w.close();
+    }
+    {
         H5Writer w(dir + "/nothing.h5");  // Photons_NNN.h5 without qed: a file with an empty root group
         w.close();
     }

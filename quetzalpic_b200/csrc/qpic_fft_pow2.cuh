@@ -278,8 +278,17 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
                                 int * __restrict__ ticket, SpecMap partials, int my_rank, int col0, int nz) {
     QPIC_KERNEL_BEGIN(colsum ? KID_k_p2_cols_solve : KID_COUNT + 16);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane(sm, log2n);
-    const int k = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
+    // The spb columns of a block are ADJACENT and interleaved over the threads (column index fastest) and in shared memory, so the lanes
+    // of a warp touch spb * 16 contiguous bytes of every spectrum row: full 32-byte sectors from two columns per block on (one
+    // column per 64 consecutive threads used half of every sector and 32 lines per warp-wide load).
+    Pow2Lane L;
+    const int spb = blockDim.x >> (log2n - 3);
+    L.e8 = 1 << (log2n - 3);
+    L.b = threadIdx.x % spb;
+    L.t = threadIdx.x / spb;
+    L.xa = sm + L.b;
+    L.xb = L.xa + (size_t)p2_pad_len(1 << log2n) * spb;
+    const int k = blockIdx.x * spb + L.b;
     const bool live = k < ncols;
     const int ny = 1 << log2n;
     double2 v[8];
@@ -290,7 +299,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 #pragma unroll
     for (int e = 0; e < 8; e++) rinv[e] = live ? inv_symbol[(size_t)k * ny + L.t + e * L.e8] : 0.0;
     if (cancelled(ctl)) return;
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twy);
+    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twy, spb);
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) {
@@ -304,7 +313,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
     if (colsum && live && L.t == 0) row0[k] = v[0];
     // the forward transform's last exchange buffer may still be read by slower threads of this sequence
     __syncthreads();
-    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy);
+    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy, spb);
     QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll

@@ -192,3 +192,134 @@ def test_hdf5_writer_subset_reads_back(tmp_path):
     assert bytes.fromhex("11203f00080000000000400034 0b003 4ff030000".replace(" ", "")) in raw
     assert bytes.fromhex("100800000400000000002000") in raw
     assert H5File(os.path.join(tmp_path, "nothing.h5")).keys() == []
+
+
+def test_hdf5_file_structures_follow_the_format_specification(tmp_path, golden_dir):
+    """Byte-level check of host/output_h5.h against the structures a libhdf5 / h5py reader parses first ("HDF5 File Format
+    Specification", version-0 superblock, version-1 B-tree / symbol table node / local heap / object headers), field by field with
+    struct offsets taken from the specification's tables -- independent of tests/h5mini.py.  The writer's output for a fixed small
+    input is also committed as tests/golden/h5_writer_sample.h5 (so that a later environment WITH h5py can open it: datasets "psi"
+    (1, 2, 3) = 1..6 with attributes steps / origin, "ex" (1, 2) with plane / plane_coordinate as well, empty "x") and must be
+    reproduced byte for byte."""
+    import struct
+    build_driver()
+    subprocess.check_call([os.path.join(ROOT, "host", "_build", "h5_selftest"), str(tmp_path)])
+    raw = open(os.path.join(tmp_path, "sample.h5"), "rb").read()
+    assert raw == open(os.path.join(golden_dir, "h5_writer_sample.h5"), "rb").read()
+    UNDEF = 0xFFFFFFFFFFFFFFFF
+    u8 = lambda o: raw[o]
+    u16 = lambda o: struct.unpack_from("<H", raw, o)[0]
+    u32 = lambda o: struct.unpack_from("<I", raw, o)[0]
+    u64 = lambda o: struct.unpack_from("<Q", raw, o)[0]
+    # ---- superblock, version 0 (spec II.A)
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n"
+    assert [u8(8), u8(9), u8(10), u8(11), u8(12)] == [0, 0, 0, 0, 0]      # superblock / free-space / root entry / reserved / shared header versions
+    assert (u8(13), u8(14), u8(15)) == (8, 8, 0)                          # size of offsets, size of lengths, reserved
+    leaf_k, internal_k = u16(16), u16(18)
+    assert leaf_k >= 1 and internal_k >= 1 and u32(20) == 0               # group leaf / internal node K, file consistency flags
+    assert u64(24) == 0 and u64(32) == UNDEF and u64(40) == len(raw) and u64(48) == UNDEF   # base, free-space info, EOF, driver info
+    # root group symbol table entry (spec III.C): link name offset, object header address, cache type 1 + scratch = B-tree, heap addresses
+    assert u64(56) == 0 and u32(72) == 1 and u32(76) == 0
+    root_header, btree, heap = u64(64), u64(80), u64(88)
+    assert all(a % 8 == 0 and 96 <= a < len(raw) for a in (root_header, btree, heap))
+    # ---- local heap (spec III.D): signature, version 0, reserved, data segment size, free-list head, data segment address
+    assert raw[heap:heap + 4] == b"HEAP" and raw[heap + 4:heap + 8] == b"\0\0\0\0"
+    seg_size, free_head, seg = u64(heap + 8), u64(heap + 16), u64(heap + 24)
+    assert seg % 8 == 0 and seg + seg_size <= len(raw) and raw[seg] == 0   # offset 0 of the segment holds the empty string
+    assert free_head % 8 == 0 and free_head + 16 <= seg_size
+    assert u64(seg + free_head) == 1 and u64(seg + free_head + 8) == seg_size - free_head  # one free block: next = 1 (none), size to the end
+    # ---- group B-tree node (spec III.A.1): signature, node type 0, level 0, entries used, siblings, key / child / key
+    assert raw[btree:btree + 4] == b"TREE" and (u8(btree + 4), u8(btree + 5), u16(btree + 6)) == (0, 0, 1)
+    assert u64(btree + 8) == UNDEF and u64(btree + 16) == UNDEF
+    key0, snod, key1 = u64(btree + 24), u64(btree + 32), u64(btree + 40)
+    assert key0 == 0 and btree + 24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8 <= len(raw)   # the node has room for 2K children, 2K+1 keys
+    # ---- symbol table node (spec III.B): signature, version 1, reserved, number of symbols, 40-byte entries
+    assert raw[snod:snod + 4] == b"SNOD" and (u8(snod + 4), u8(snod + 5)) == (1, 0)
+    nsym = u16(snod + 6)
+    assert nsym == 3 <= 2 * leaf_k
+
+    def heap_string(off):
+        end = raw.index(b"\0", seg + off)
+        return raw[seg + off:end].decode()
+
+    names, headers = [], []
+    for i in range(nsym):
+        e = snod + 8 + 40 * i
+        names.append(heap_string(u64(e)))
+        headers.append(u64(e + 8))
+        assert u32(e + 16) == 0 and u32(e + 20) == 0 and raw[e + 24:e + 40] == bytes(16)   # cache type 0, reserved, empty scratch pad
+    assert names == sorted(names) == ["ex", "psi", "x"] and heap_string(key1) == "x"           # strcmp order; key 1 = largest name of the child
+
+    def messages(addr):
+        """version-1 object header (spec IV.A.1.a): version, reserved, message count, reference count, header size, padding to 8"""
+        assert (u8(addr), u8(addr + 1)) == (1, 0) and u32(addr + 4) == 1
+        count, size = u16(addr + 2), u32(addr + 8)
+        assert u32(addr + 12) == 0
+        out, o = [], addr + 16
+        for _ in range(count):
+            mtype, msize, flags = u16(o), u16(o + 2), u8(o + 4)
+            assert msize % 8 == 0 and raw[o + 5:o + 8] == b"\0\0\0"
+            out.append((mtype, raw[o + 8:o + 8 + msize], flags))
+            o += 8 + msize
+        assert o == addr + 16 + size
+        return out
+
+    # root group: exactly one symbol table message (0x0011) naming the same B-tree and heap
+    (mtype, body, _), = messages(root_header)
+    assert mtype == 0x0011 and struct.unpack("<QQ", body) == (btree, heap)
+
+    expect = {"psi": ((1, 2, 3), np.arange(1.0, 7.0)), "ex": ((1, 2), np.array([-0.5, 0.25])), "x": ((0,), np.zeros(0))}
+    for name, addr in zip(names, headers):
+        dims, data = expect[name]
+        msgs = messages(addr)
+        by_type = {}
+        for mtype, body, flags in msgs:
+            by_type.setdefault(mtype, []).append(body)
+        # dataspace (0x0001, version 1): version, rank, flags, reserved (5 bytes), dimension sizes
+        ds, = by_type[0x0001]
+        assert ds[0] == 1 and ds[1] == len(dims) and ds[2] == 0 and ds[3:8] == bytes(5)
+        assert struct.unpack_from(f"<{len(dims)}Q", ds, 8) == dims
+        # datatype (0x0003): class 1 (floating point) version 1; bit field 0x20 = little endian, mantissa normalisation 2 (implied msb);
+        # byte 1 = sign location 63; size 8; properties: bit offset 0, precision 64, exponent location 52 size 11, mantissa location 0
+        # size 52, exponent bias 1023 -- the encoding of H5T_IEEE_F64LE
+        dt, = by_type[0x0003]
+        assert dt[0] == 0x11 and dt[1] == 0x20 and dt[2] == 63 and dt[3] == 0 and struct.unpack_from("<I", dt, 4)[0] == 8
+        assert struct.unpack_from("<HHBBBBI", dt, 8) == (0, 64, 52, 11, 0, 52, 1023)
+        # layout (0x0008, version 3): class 1 = contiguous, data address, size in bytes
+        lay, = by_type[0x0008]
+        assert lay[0] == 3 and lay[1] == 1
+        data_addr, nbytes = struct.unpack_from("<QQ", lay, 2)
+        assert nbytes == 8 * data.size
+        if data.size:
+            assert data_addr % 8 == 0 and np.array_equal(np.frombuffer(raw, "<f8", data.size, data_addr), data)
+        else:
+            assert data_addr == UNDEF
+        # attributes (0x000C, version 1): version, reserved, name size (with NUL), datatype size, dataspace size, then the three parts,
+        # each padded to a multiple of 8 bytes
+        attrs = {}
+        for a in by_type.get(0x000C, []):
+            assert a[0] == 1 and a[1] == 0
+            nsz, tsz, ssz = struct.unpack_from("<HHH", a, 2)
+            pad = lambda v: (v + 7) // 8 * 8
+            o = 8
+            aname = a[o:o + nsz].rstrip(b"\0").decode()
+            assert a[o + nsz - 1] == 0
+            o += pad(nsz)
+            atype = a[o:o + tsz]
+            o += pad(tsz)
+            aspace = a[o:o + ssz]
+            o += pad(ssz)
+            rank = aspace[1]
+            adims = struct.unpack_from(f"<{rank}Q", aspace, 8) if rank else ()
+            n = int(np.prod(adims)) if rank else 1
+            if atype[0] == 0x11:
+                attrs[aname] = np.frombuffer(a, "<f8", n, o)
+            else:
+                # class 0 (fixed point) version 1, little endian, signed (bit 3), size 4, bit offset 0, precision 32: H5T_STD_I32LE
+                assert atype[0] == 0x10 and atype[1] == 0x08 and struct.unpack_from("<I", atype, 4)[0] == 4 and struct.unpack_from("<HH", atype, 8) == (0, 32)
+                attrs[aname] = np.frombuffer(a, "<i4", n, o)
+        if name in ("psi", "ex"):
+            assert np.array_equal(attrs["steps"], [0.1, 0.2, 0.3]) and np.array_equal(attrs["origin"], [-0.05, 0.0, 0.15])
+        if name == "ex":
+            assert attrs["plane"][0] == 1 and attrs["plane_coordinate"][0] == 2.5
+        assert set(by_type) <= {0x0001, 0x0003, 0x0005, 0x0008, 0x000C, 0x0000}
