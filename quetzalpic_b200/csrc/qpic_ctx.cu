@@ -29,6 +29,10 @@
 
 using namespace qpic;
 
+#ifndef QPIC_PBLOCK
+#define QPIC_PBLOCK 128  // threads per block of the particle kernels (one particle per thread)
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -762,7 +766,7 @@ int enqueue_slice_head(qpic_ctx * c, bool fast, bool want_invariants, bool with_
     cudaStream_t st = c->stream;
     QPIC_TRY(enqueue_potential(c, st, fast, 0, c->f2[QPIC_F2_PSI]));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, 128), 128, 0, st, c->ctl, c->g, c->P, c->perm_b, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
+        QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, st, c->ctl, c->g, c->P, c->perm_b, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
                          want_invariants ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_gamma"));
     }
@@ -847,11 +851,11 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         if (np > 0 && fast && predict_deposit_on(c)) {
             StayOut so = c->stay;
             so.cnt = c->stay_cnt[it & 1];
-            QPIC_LAUNCH(k_particles_predict_dep, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so);
+            QPIC_LAUNCH(k_particles_predict_dep, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         } else if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
-            QPIC_LAUNCH_FLAT(predict, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
+            QPIC_LAUNCH_FLAT(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
                              (!fast || it == M - 1) ? 1 : 0);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
@@ -878,7 +882,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             QPIC_TRY(dist_reduce(c, sa, halo_job({c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT]}, {RB_JY, RB_JZ})));
         } else {
             if (np > 0) {
-                QPIC_LAUNCH_FLAT(k_particles_currents_yz, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
+                QPIC_LAUNCH_FLAT(k_particles_currents_yz, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_PSI_MIDDLE]);
                 QPIC_TRY(check_launch(c, "k_particles_currents_yz"));
             }
             QPIC_LAUNCH_FLAT(k_deposit_jy_jz, blocks_for(n2, 128), 128, 0, sa, c->ctl, c->g, lists_mid(c), c->P.vjy, c->P.vjz, c->f2[QPIC_F2_JY_NEXT],
@@ -944,7 +948,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(rc);
     }
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, 128), 128, 0, sa, c->ctl, c->g, c->P, c->dist.on ? (const int *)nullptr : c->perm_b,
+        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->dist.on ? (const int *)nullptr : c->perm_b,
                          c->f2[QPIC_F2_PSI_MIDDLE], c->count, migrate_view(c), c->track_gamma_px ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_advance"));
     }
@@ -959,7 +963,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     if (deposit_done) QPIC_CUDA(c, cudaStreamWaitEvent(sa, deposit_done, 0));
     QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, sa, c->ctl, c->P, c->perm_b);
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->P, c->perm_b);
         QPIC_TRY(check_launch(c, "k_particles_to_slots"));
     }
     // (the last block of k_end_of_slice has moved Ctl::slice on)
@@ -979,7 +983,7 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
     }
     QPIC_TRY(enqueue_sort(c, c->stream, ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, 128), 128, 0, c->stream, ctl, c->P, c->perm_b);
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, c->stream, ctl, c->P, c->perm_b);
         QPIC_TRY(check_launch(c, "k_particles_to_slots"));
     }
     c->lists_dirty = false;
@@ -1269,6 +1273,11 @@ static int create_impl(qpic_ctx * c) {
     g.inv_dx = 1.0 / g.dx;
     g.inv_dy = 1.0 / g.dy;
     g.inv_dz = 1.0 / g.dz;
+    {
+        int e;
+        g.exact_dy = std::frexp(g.dy, &e) == 0.5 ? 1 : 0;
+        g.exact_dz = std::frexp(g.dz, &e) == 0.5 ? 1 : 0;
+    }
 
     const size_t n2 = (size_t)g.n2, n3 = n2 * g.nx;
     qpic_ctx::Dist & D = c->dist;
@@ -2388,7 +2397,7 @@ int qpic_bunch_advance_qed(qpic_ctx * c, double dt, double frequency, const doub
         QedConstants Q;
         Q.coef = ELECTRON_MASS_CGS * SPEED_OF_LIGHT_CGS * SPEED_OF_LIGHT_CGS / (PLANCK_CONST_BAR_CGS * frequency);
         Q.fine_structure = (ELEMENTARY_CHARGE_CGS * ELEMENTARY_CHARGE_CGS / PLANCK_CONST_BAR_CGS / SPEED_OF_LIGHT_CGS);
-        QPIC_LAUNCH_FLAT(k_bunch_advance_qed, blocks_for(np, 128), 128, 0, st, S.b, S.species, dt, Q, u_emit ? (const double *)S.u_emit : (const double *)nullptr,
+        QPIC_LAUNCH_FLAT(k_bunch_advance_qed, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, st, S.b, S.species, dt, Q, u_emit ? (const double *)S.u_emit : (const double *)nullptr,
                          u_emit ? (const double *)S.u_accept : (const double *)nullptr, seed, S.qed_step, S.qed);
         QPIC_TRY(check_launch(c, "k_bunch_advance_qed"));
         const int nchunks = (np + SCAN_CHUNK - 1) / SCAN_CHUNK;

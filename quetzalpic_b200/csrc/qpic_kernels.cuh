@@ -204,6 +204,9 @@ struct Geom {
     // 1/dx, 1/dy, 1/dz: finite differences multiply by these instead of dividing (exact when the step is a power of two,
     // as in the BASELINE grids; otherwise within an ulp of the reference's quotient).  Positions -> cells keep the division.
     double inv_dx, inv_dy, inv_dz;
+    // dy / dz is a power of two (all BASELINE grids): y * inv_dy IS y / dy bit for bit, so locate_fast may multiply (an FP64 division
+    // costs ~30 instructions; the particle kernels spent most of their issue slots on divisions)
+    int exact_dy, exact_dz;
 };
 
 // ------------------------------------------------------------------------------------------------ index helpers
@@ -213,6 +216,17 @@ struct Geom {
 // index out of bounds there (asserts are compiled out); we map it to the same periodic point, cell 0.
 __device__ __forceinline__ void locate(double y, double d, int n, int & jc, double & f) {
     const double t = y / d;
+    jc = (int)t;
+    f = t - (double)jc;
+    if (jc >= n) {
+        jc = 0;
+        f = 0.0;
+    }
+}
+
+// the same with the quotient formed as y * (1/d) where that is exact (d a power of two); otherwise the division
+__device__ __forceinline__ void locate_fast(double y, double d, double inv_d, int exact, int n, int & jc, double & f) {
+    const double t = exact ? y * inv_d : y / d;
     jc = (int)t;
     f = t - (double)jc;
     if (jc >= n) {
@@ -733,8 +747,11 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     const double psi_particle = gather_node(psi, g.ny, g.nz, jc, kc, fy, fz);
     const double py = P.py_s[s], pz = P.pz_s[s], nw = P.nw_s[s];
     const double q = 1 + psi_particle;
-    const double gamma = 0.5 * (1 + py * py + pz * pz + a_particle + q * q) / q;
-    const double px = 0.5 * (1 + py * py + pz * pz + a_particle - q * q) / q;
+    // Divisions by 1 + psi@p are products with ONE reciprocal (within an ulp of the reference's quotients; tolerance 1e-12): the four
+    // quotients of this kernel and the six of the predictor were ~60 % of their instructions.
+    const double rq = 1.0 / q;
+    const double gamma = 0.5 * (1 + py * py + pz * pz + a_particle + q * q) * rq;
+    const double px = 0.5 * (1 + py * py + pz * pz + a_particle - q * q) * rq;
     if (!want_invariants) {
         // no B iterations / no push follow (M = 0 or slice 0): this is the final gamma, px of the particle (the push
         // writes them otherwise)
@@ -752,8 +769,8 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     if (want_invariants) {
         P.q[s] = q;
         P.ap[s] = a_particle;
-        P.t1y[s] = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz) / q;
-        P.t1z[s] = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz) / q;
+        P.t1y[s] = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz) * rq;
+        P.t1z[s] = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz) * rq;
         P.dpy[s] = gather_yder(psi, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz);
         P.dpz[s] = gather_zder(psi, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz);
     }
@@ -774,8 +791,11 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 // so they are formed here as well: one streaming pass over the slot arrays per iteration instead of two.
 // store_px: only the last B iteration's px is read again (rho / susceptibility deposit, push); the general path's deposits read it
 // every iteration.
+#ifndef QPIC_PREDICT_MINB
+#define QPIC_PREDICT_MINB 1
+#endif
 template <bool FAST>
-__global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
+__global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
                                     int * __restrict__ count, int store_px) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     // The control block is tested only before the first store: its load then overlaps the streaming loads instead of
@@ -800,29 +820,30 @@ __global__ void k_particles_predict(Ctl * ctl, Geom g, Particles P, const double
     const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
     if (cancelled(ctl) || s >= live_count(ctl, P.np)) return;
     QPIC_KERNEL_TAIL();
+    const double rq = 1.0 / q;  // (see k_particles_gamma)
     double pyn = py - t1y;
-    pyn += g.dx * gamma * dpy / q;
+    pyn += g.dx * gamma * dpy * rq;
     pyn -= g.dx * bz_particle;
     double pzn = pz - t1z;
-    pzn += g.dx * gamma * dpz / q;
+    pzn += g.dx * gamma * dpz * rq;
     pzn += g.dx * by_particle;
     P.pyn[s] = pyn;
     P.pzn[s] = pzn;
     {
         // corrector (the gamma read above was the previous iteration's; this thread owns element s)
         const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
-        const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) / q;
-        const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) / q;
+        const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) * rq;
+        const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) * rq;
         P.gam[s] = gamma_c;
         if (store_px) P.pxs[s] = px_c;
         store_currents<!FAST>(P, s, nw, gamma_c, px_c);  // the general path's node-centric deposit reads vrho / vchi
     }
-    const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn / q, g.ly);
-    const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn / q, g.lz);
+    const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn * rq, g.ly);
+    const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn * rq, g.lz);
     int jm, km;
     double f1, f2;
-    locate(ym, g.dy, g.ny, jm, f1);
-    locate(zm, g.dz, g.nz, km, f2);
+    locate_fast(ym, g.dy, g.inv_dy, g.exact_dy, g.ny, jm, f1);
+    locate_fast(zm, g.dz, g.inv_dz, g.exact_dz, g.nz, km, f2);
     const int cm = jm * g.nz + km;
     if (!FAST) P.cell_m[s] = cm;  // only the general path's cell sort reads it
     P.fy_m[s] = f1;
@@ -888,15 +909,15 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
         P.gamma[p] = P.gam[s];
         P.px[p] = P.pxs[s];
     }
-    const double w = 1 + psi_particle;
-    const double y = wrap_fast(P.y_s[s] + g.dx * py / w, g.ly);
-    const double z = wrap_fast(P.z_s[s] + g.dx * pz / w, g.lz);
+    const double rw = 1.0 / (1 + psi_particle);  // (see k_particles_gamma)
+    const double y = wrap_fast(P.y_s[s] + g.dx * py * rw, g.ly);
+    const double z = wrap_fast(P.z_s[s] + g.dx * pz * rw, g.lz);
     P.y[p] = y;
     P.z[p] = z;
     int jn, kn;
     double f1, f2;
-    locate(y, g.dy, g.ny, jn, f1);
-    locate(z, g.dz, g.nz, kn, f2);
+    locate_fast(y, g.dy, g.inv_dy, g.exact_dy, g.ny, jn, f1);
+    locate_fast(z, g.dz, g.inv_dz, g.exact_dz, g.nz, kn, f2);
     int cn = jn * g.nz + kn;
     if (mig.enabled) {
         const double nw = P.nw_s[s];
@@ -1713,21 +1734,22 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     if (cancelled(ctl)) return;  // uniform over the grid
     QPIC_KERNEL_TAIL();
     // ---- exactly k_particles_predict<true> from here ...
+    const double rq = 1.0 / q;  // (see k_particles_gamma)
     double pyn = py - t1y;
-    pyn += g.dx * gamma * dpy / q;
+    pyn += g.dx * gamma * dpy * rq;
     pyn -= g.dx * bz_particle;
     double pzn = pz - t1z;
-    pzn += g.dx * gamma * dpz / q;
+    pzn += g.dx * gamma * dpz * rq;
     pzn += g.dx * by_particle;
     const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
-    const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) / q;
-    const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) / q;
-    const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn / q, g.ly);
-    const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn / q, g.lz);
+    const double gamma_c = 0.5 * (1 + p_squared + a_particle + q * q) * rq;
+    const double px_c = 0.5 * (1 + p_squared + a_particle - q * q) * rq;
+    const double ym = wrap_fast(y0 + 0.5 * g.dx * pyn * rq, g.ly);
+    const double zm = wrap_fast(z0 + 0.5 * g.dx * pzn * rq, g.lz);
     int jm, km;
     double f1, f2;
-    locate(ym, g.dy, g.ny, jm, f1);
-    locate(zm, g.dz, g.nz, km, f2);
+    locate_fast(ym, g.dy, g.inv_dy, g.exact_dy, g.ny, jm, f1);
+    locate_fast(zm, g.dz, g.inv_dz, g.exact_dz, g.nz, km, f2);
     const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
     const bool bad = oy < -1 || oy > 1 || oz < -1 || oz > 1 || !(f1 >= 0.0) || !(f2 >= 0.0);
     const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc) : pack_offset(oy, oz, f1, f2, kc);
@@ -1917,8 +1939,8 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
     double z0m = 0.0, z1m = 0.0, z00 = 0.0, z10 = 0.0, z0p = 0.0, z1p = 0.0;
     auto visit5 = [&](double fy, double fz, double nw, double vy0, double vz0, int hy, int hz) {
         // gather_node's expression on the preloaded corners
-        const double w = 1 + (p00 * (1 - fy) * (1 - fz) + p10 * fy * (1 - fz) + p01 * (1 - fy) * fz + p11 * fy * fz);
-        const double vy = nw * vy0 / w, vz = nw * vz0 / w;
+        const double rw = 1.0 / (1 + (p00 * (1 - fy) * (1 - fz) + p10 * fy * (1 - fz) + p01 * (1 - fy) * fz + p11 * fy * fz));
+        const double vy = nw * vy0 * rw, vz = nw * vz0 * rw;  // one reciprocal instead of two quotients (within an ulp)
         {
             // jy: staggered by dy/2 in y -- the lower node row is j (upper half of the cell) or j-1 (lower half)
             const double wy = hy ? fy - 0.5 : fy + 0.5;
