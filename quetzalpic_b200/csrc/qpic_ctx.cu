@@ -963,7 +963,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     if (deposit_done) QPIC_CUDA(c, cudaStreamWaitEvent(sa, deposit_done, 0));
     QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->P, c->perm_b);
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->perm_b);
         QPIC_TRY(check_launch(c, "k_particles_to_slots"));
     }
     // (the last block of k_end_of_slice has moved Ctl::slice on)
@@ -983,7 +983,7 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
     }
     QPIC_TRY(enqueue_sort(c, c->stream, ctl, c->P.cell_p, c->start_b, c->perm_b));
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, c->stream, ctl, c->P, c->perm_b);
+        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, c->stream, ctl, c->g, c->P, c->perm_b);
         QPIC_TRY(check_launch(c, "k_particles_to_slots"));
     }
     c->lists_dirty = false;

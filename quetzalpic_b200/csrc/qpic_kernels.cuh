@@ -715,8 +715,15 @@ __device__ __forceinline__ double wrap_fast(double y, double l) {
     return wrap_coordinate(y, l);
 }
 
+// Position of a particle from its cell descriptor.  With d a power of two t = y / d is exact, jc = (int)t and f = t - jc are exact, so
+// (jc + f) * d IS y bit for bit: the slot copies y_s / z_s (16 bytes per particle and predictor pass of HBM traffic) are not needed on
+// such an axis.  Otherwise the stored copy is read.
+__device__ __forceinline__ double slot_position(int exact, int jc, double f, double d, const double * __restrict__ stored, int s) {
+    return exact ? ((double)jc + f) * d : ld_stream(stored + s);
+}
+
 // after the cell sort of the slice-start positions: copy the particle's slice inputs from id order to slot order
-__global__ void k_particles_to_slots(const Ctl * ctl, Particles P, const int * __restrict__ perm_b) {
+__global__ void k_particles_to_slots(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b) {
     QPIC_KERNEL_BEGIN(KID_k_particles_to_slots);
     if (cancelled(ctl)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -725,8 +732,9 @@ __global__ void k_particles_to_slots(const Ctl * ctl, Particles P, const int * _
     P.cell_b[s] = P.cell_p[p];
     P.fy_b[s] = P.fy_p[p];
     P.fz_b[s] = P.fz_p[p];
-    P.y_s[s] = P.y[p];
-    P.z_s[s] = P.z[p];
+    // (on an axis whose step is a power of two the kernels rebuild the position from the cell descriptor, exactly: see slot_position)
+    if (!g.exact_dy) P.y_s[s] = P.y[p];
+    if (!g.exact_dz) P.z_s[s] = P.z[p];
     P.py_s[s] = P.py[p];
     P.pz_s[s] = P.pz[p];
     P.nw_s[s] = P.nw[p];
@@ -809,7 +817,7 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     const double q = ld_invariant<0>(P.q + s), gamma = P.gam[s];
     const double py = ld_invariant<1>(P.py_s + s), pz = ld_invariant<2>(P.pz_s + s);
     const double t1y = ld_invariant<3>(P.t1y + s), t1z = ld_invariant<4>(P.t1z + s), dpy = ld_invariant<5>(P.dpy + s), dpz = ld_invariant<6>(P.dpz + s);
-    const double y0 = ld_invariant<7>(P.y_s + s), z0 = ld_invariant<8>(P.z_s + s);
+    const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
     const double a_particle = ld_invariant<9>(P.ap + s), nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
@@ -910,8 +918,8 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
         P.px[p] = P.pxs[s];
     }
     const double rw = 1.0 / (1 + psi_particle);  // (see k_particles_gamma)
-    const double y = wrap_fast(P.y_s[s] + g.dx * py * rw, g.ly);
-    const double z = wrap_fast(P.z_s[s] + g.dx * pz * rw, g.lz);
+    const double y = wrap_fast(slot_position(g.exact_dy, jc, P.fy_b[s], g.dy, P.y_s, s) + g.dx * py * rw, g.ly);
+    const double z = wrap_fast(slot_position(g.exact_dz, kc, P.fz_b[s], g.dz, P.z_s, s) + g.dx * pz * rw, g.lz);
     P.y[p] = y;
     P.z[p] = z;
     int jn, kn;
@@ -1723,7 +1731,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const double q = ld_stream(P.q + s), gamma = P.gam[s];
     const double py = ld_stream(P.py_s + s), pz = ld_stream(P.pz_s + s);
     const double t1y = ld_stream(P.t1y + s), t1z = ld_stream(P.t1z + s), dpy = ld_stream(P.dpy + s), dpz = ld_stream(P.dpz + s);
-    const double y0 = ld_stream(P.y_s + s), z0 = ld_stream(P.z_s + s);
+    const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
     const double a_particle = ld_stream(P.ap + s), nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;

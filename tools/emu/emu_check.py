@@ -28,6 +28,8 @@ CASES = {
     "odd": dict(n=(5, 15, 9), l=(1.0, 3.0, 1.8), M=2, ppc=(1, 2), a0=1.0, sig=(0.8, 1.6, 1.0), x0=0.6),
     "p64": dict(n=(4, 64, 128), l=(0.8, 6.4, 12.8), M=2, ppc=(1, 1), a0=1.3, sig=(0.8, 3.0, 6.0), x0=0.5),
     "p256": dict(n=(3, 256, 64), l=(0.6, 25.6, 6.4), M=1, ppc=(1, 1), a0=1.3, sig=(0.8, 12.0, 3.0), x0=0.4),
+    # power-of-two steps (dy = dz = 1/16): the kernels rebuild positions from the cell descriptor and locate cells by multiplication
+    "exact": dict(n=(6, 32, 48), l=(0.75, 2.0, 3.0), M=3, ppc=(2, 2), a0=2.0, sig=(0.6, 0.8, 1.0), x0=0.4),
     "m0": dict(n=(4, 8, 12), l=(0.8, 1.6, 2.4), M=0, ppc=(1, 1), a0=1.0, sig=(0.8, 1.6, 1.0), x0=0.5),
 }
 
