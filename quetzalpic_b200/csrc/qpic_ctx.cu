@@ -146,6 +146,10 @@ struct qpic_ctx {
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
     bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
     bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
+    // half steps beyond one cell stay on the sort-free path (FarMovers, qpic_kernels.cuh); QPIC_FAR_MOVERS=0: they raise the rollback as in round 1
+    bool far_movers = true;
+    int * far_cnt[2] = {nullptr, nullptr};
+    int * far_lst = nullptr;
     // stayers of the psi_middle source summed by the predictor (k_particles_predict_dep + k_tile_assemble); chosen by problem size, see alloc_particles
     bool predict_deposit = false;
     int predict_deposit_mode = -1;  // -1 auto, 0 off, 1 on
@@ -647,6 +651,17 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 // with the published lists the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their cell directly
 // and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
 bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists && c->jyjz_cell; }
+// far-mover lists of B iteration c->cur_it (only with the stayers-direct tile kernels on a single GPU and without the predictor-side deposit,
+// whose own lists take every mover)
+FarMovers far_view(const qpic_ctx * c, bool fast) {
+    FarMovers f = {nullptr, nullptr, nullptr};
+    if (fast && c->far_movers && c->far_cnt[0] && !(c->predict_deposit && c->stay.corn)) {
+        f.cnt = c->far_cnt[c->cur_it & 1];
+        f.lst = c->far_lst;
+        f.clear = c->far_cnt[(c->cur_it + 1) & 1];
+    }
+    return f;
+}
 bool predict_deposit_on(const qpic_ctx * c) { return c->predict_deposit && stayers_direct(c) && c->stay.corn != nullptr; }
 
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
@@ -655,6 +670,7 @@ int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     j.o[0] = tile_output(c->P.nw_s, -1.0, 1, nullptr, c->fft_in, 0);
     if (!at_mid) {
         if (predict_deposit_on(c)) j.clear_cnt = c->stay_cnt[0];  // the first predictor pass of the slice counts its movers there
+        else if (c->far_movers && c->far_cnt[0]) j.clear_cnt = c->far_cnt[0];  // ... or its far movers
         return launch_tile(c, st, j, false, "k_tile_deposit_charge");
     }
     const dim3 block(TILE_ACC + 2, TILE_ACC + 2);
@@ -667,7 +683,7 @@ int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     }
     if (stayers_direct(c)) {
         // stayers from registers, movers through the lists; publishes the movers for k_tile_cell_deposit
-        QPIC_LAUNCH(k_tile_stay_deposit, tile_grid(c), block, tile_stay_smem_bytes(), st, c->ctl, c->g, c->start_b, c->P, j);
+        QPIC_LAUNCH(k_tile_stay_deposit, tile_grid(c), block, tile_stay_smem_bytes(), st, c->ctl, c->g, c->start_b, c->P, j, far_view(c, true));
         return check_launch(c, "k_tile_deposit_charge_mid");
     }
     QPIC_LAUNCH(k_tile_bin_deposit<0>, tile_grid(c), block, tile_bin_smem_bytes<0>(), st, c->ctl, c->g, c->start_b, c->P, j);
@@ -856,7 +872,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         } else if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
             QPIC_LAUNCH_FLAT(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
-                             (!fast || it == M - 1) ? 1 : 0);
+                             (!fast || it == M - 1) ? 1 : 0, far_view(c, fast && stayers_direct(c) && !c->dist.on));
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
         // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored.  (Forking it after
@@ -1028,6 +1044,7 @@ int alloc_particles(qpic_ctx * c, size_t count) {
         QPIC_TRY(dev_alloc(c, &c->stay.lead, 4 * nwarps));
         QPIC_TRY(dev_alloc(c, &c->stay.trail, 4 * nwarps));
         c->stay.sign = -1.0;
+        c->stay.allow_far = (c->far_movers && !c->dist.on) ? 1 : 0;
     }
     return QPIC_OK;
 }
@@ -1064,6 +1081,13 @@ int handle_ctl(qpic_ctx * c, const Ctl & seen) {
         } else {
             QPIC_CUDA(c, cudaMemsetAsync(c->f2[QPIC_F2_BY_CUR], 0, sizeof(double) * n2, c->stream));
             QPIC_CUDA(c, cudaMemsetAsync(c->f2[QPIC_F2_BZ_CUR], 0, sizeof(double) * n2, c->stream));
+        }
+        // (the aborted slice may have left far-mover entries behind: its deposits, which clear the counters, became no-ops)
+        for (int * cnt : c->far_cnt) {
+            if (cnt) QPIC_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * n2, c->stream));
+        }
+        for (int * cnt : c->stay_cnt) {
+            if (cnt) QPIC_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * n2, c->stream));
         }
         *c->ctl_host = seen;
         c->ctl_host->fast_fail = 0;
@@ -1484,6 +1508,13 @@ static int create_impl(qpic_ctx * c) {
         c->track_gamma_px = e3 && e3[0] == '1';
         const char * e2 = getenv("QPIC_JYJZ_CELL");
         c->jyjz_cell = !(e2 && e2[0] == '0');
+        const char * e9 = getenv("QPIC_FAR_MOVERS");
+        c->far_movers = !(e9 && e9[0] == '0') && !D.on && c->jyjz_lists && c->jyjz_cell && !p.force_general_deposit;
+        if (c->far_movers) {
+            QPIC_TRY(dev_alloc(c, &c->far_cnt[0], n2));
+            QPIC_TRY(dev_alloc(c, &c->far_cnt[1], n2));
+            QPIC_TRY(dev_alloc(c, &c->far_lst, (size_t)FAR_K * n2));
+        }
         if (c->jyjz_lists && !p.force_general_deposit) {
             QPIC_TRY(dev_alloc(c, &c->bin_cnt, n2));
             QPIC_TRY(dev_alloc(c, &c->bin_lst, (size_t)BIN_K * n2));
@@ -1683,6 +1714,9 @@ int qpic_begin(qpic_ctx * c) {
                          QPIC_F2_BY_CUR, QPIC_F2_BZ_CUR, QPIC_F2_RHO_ION};
     for (int f : zero2) QPIC_CUDA(c, cudaMemsetAsync(c->f2[f], 0, sizeof(double) * n2, c->stream));
     for (int * cnt : c->stay_cnt) {
+        if (cnt) QPIC_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * n2, c->stream));
+    }
+    for (int * cnt : c->far_cnt) {
         if (cnt) QPIC_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(int) * n2, c->stream));
     }
     // The per-slice datasets psi, rho, jx, jy, jz live in the output file of ONE time iteration in the reference (Output_writer is

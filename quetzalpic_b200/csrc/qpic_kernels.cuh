@@ -784,6 +784,24 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     }
 }
 
+// ---- far movers: half steps beyond the +-1 cell window of the tile deposits (round 2)
+// The tile kernels find the particles that land in a target cell by looking at the cells around it, which is only complete while every half step
+// stays within one cell.  A particle that goes further (bubble sheath, trajectory crossing) used to raise Ctl::fast_fail: the host discarded the slice
+// and redid it -- and the next 16, 32, ... -- on the sorted path.  Now the predictor appends such a particle to a per-TARGET-cell list in global memory
+// (integer atomics: only the order of a list depends on scheduling) and marks its offset code FAR; the psi_middle source deposit merges a target
+// cell's far entries into its shared-memory mover list before the list is sorted by slot, so they are accumulated -- and published for the jy/jz deposit
+// -- exactly where ascending slot order puts them: same sums, bit for bit, as the sorted path.  The counters are double buffered over the B
+// iterations (halo target cells are read by two blocks, so the reader cannot clear them): deposit `it` reads cnt[it & 1] and clears cnt[(it + 1) & 1];
+// the slice's first charge deposit clears cnt[0].  Only a list overflow (more than FAR_K far arrivals in one cell, or a crowded cell that also has far
+// arrivals) still takes the rollback.
+constexpr int FAR_K = 8;
+constexpr int FAR_CODE = 7 | (7 << 3);  // bits 0-5 of an offset code: neither a stayer nor inside any tile window
+struct FarMovers {
+    int * cnt;   // [n2] arrivals per target cell of THIS iteration (NULL: far movers abort, as in round 1 and on slabs)
+    int * lst;   // [FAR_K][n2] entries slot << 2 | hy << 1 | hz
+    int * clear; // [n2] the other buffer: cleared by the deposit's owner threads
+};
+
 // minimal-image cell offset jm - jc folded into [-n/2, n/2]
 __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
     int o = jm - jc;
@@ -804,7 +822,7 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 #endif
 template <bool FAST>
 __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
-                                    int * __restrict__ count, int store_px) {
+                                    int * __restrict__ count, int store_px, FarMovers far) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     // The control block is tested only before the first store: its load then overlaps the streaming loads instead of
     // heading the dependent chain (every slot < P.np is readable whatever the flags say).
@@ -859,9 +877,16 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     if (FAST) {
         const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
         // !(f >= 0) catches the NaN positions of a blown-up run
-        if (oy < -1 || oy > 1 || oz < -1 || oz > 1 || !(f1 >= 0.0) || !(f2 >= 0.0)) {
+        if (!(f1 >= 0.0) || !(f2 >= 0.0)) {
             atomicExch(&ctl->fast_fail, 1);
             P.off_m[s] = pack_offset(0, 0, 0.0, 0.0, kc);
+        } else if (oy < -1 || oy > 1 || oz < -1 || oz > 1) {
+            // far mover: listed under its target cell (see FarMovers)
+            const int hy = f1 >= 0.5 ? 1 : 0, hz = f2 >= 0.5 ? 1 : 0;
+            const int pos = far.cnt ? atomicAdd(&far.cnt[cm], 1) : FAR_K;
+            if (pos < FAR_K) far.lst[(size_t)pos * g.n2 + cm] = (s << 2) | (hy << 1) | hz;
+            else atomicExch(&ctl->fast_fail, 1);
+            P.off_m[s] = FAR_CODE | (hy << 6) | (hz << 7) | ((kc & 3) << 8);
         } else {
             P.off_m[s] = pack_offset(oy, oz, f1, f2, kc);
         }
@@ -1296,6 +1321,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                 if (sb + u >= s1) break;
                 const int oy = (code[u] & 7) - 2, oz = ((code[u] >> 3) & 7) - 2;
                 const int hy = (code[u] >> 6) & 1, hz = (code[u] >> 7) & 1;
+                if ((code[u] & 63) == FAR_CODE) continue;  // (never produced on the paths that use this kernel)
 #pragma unroll
                 for (int a = 0; a < NOUT; a++) {
                     // on a staggered grid a particle in the lower half of its cell belongs to the staggered cell below
@@ -1577,7 +1603,7 @@ inline size_t tile_stay_smem_bytes() { return (size_t)TILE_CELLS * (4 * sizeof(d
 #define QPIC_STAY_MINB 1
 #endif
 __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MINB)
-    k_tile_stay_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    k_tile_stay_deposit(Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, FarMovers far) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 1);
     QPIC_DYN_SMEM(double, acc);                                   // [4][TILE_CELLS]
     int * cnt = reinterpret_cast<int *>(acc + 4 * TILE_CELLS);    // [TILE_CELLS]
@@ -1591,6 +1617,10 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
     for (int i = tid; i < TILE_CELLS; i += nthreads) cnt[i] = 0;
     const int s0 = start[cell], s1 = start[cell + 1];
     const double ion = tile_prefetch_ion<1>(g, job, sy - 1, sz - 1, ju, ku);
+    const bool is_target = sy >= 1 && sy <= TILE_ACC && sz >= 1 && sz <= TILE_ACC;
+    // far arrivals of this (target) cell, listed by the predictor; almost always none
+    const int nfar = (far.cnt && is_target) ? far.cnt[cell] : 0;
+    if (far.clear && is_target && sy >= 2 && sz >= 2 && ju < g.ny && ku < g.nz) far.clear[cell] = 0;  // the node owner of the cell clears the other buffer
     // own particles, first four: everything a visit needs, one round trip
     int code[4];
     double pfy[4], pfz[4], pv[4];
@@ -1606,7 +1636,7 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
 
     // ---- phase A: movers of this source cell -> list of their target cell
     auto bin = [&](int s, int c) {
-        if ((c & 63) == STAY_CODE) return;
+        if ((c & 63) == STAY_CODE || (c & 63) == FAR_CODE) return;
         const int ty = sy - 1 + (c & 7) - 2, tz = sz - 1 + ((c >> 3) & 7) - 2;
         if (ty >= 0 && ty < TILE_ACC && tz >= 0 && tz < TILE_ACC) {
             const int t = ty * TILE_ACC + tz;
@@ -1619,10 +1649,14 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
         if (s0 + u < s1) bin(s0 + u, code[u]);
     }
     for (int s = s0 + 4; s < s1; s++) bin(s, P.off_m[s]);
+    // far arrivals join the list of their target cell (this thread's own cell)
+    for (int i = 0; i < nfar && i < FAR_K; i++) {
+        const int pos = atomicAdd(&cnt[(sy - 1) * TILE_ACC + sz - 1], 1);
+        if (pos < BIN_K) lst[pos * TILE_CELLS + (sy - 1) * TILE_ACC + sz - 1] = far.lst[(size_t)i * g.n2 + cell];
+    }
     __syncthreads();
 
     // ---- phase B: ordered accumulation per target cell
-    const bool is_target = sy >= 1 && sy <= TILE_ACC && sz >= 1 && sz <= TILE_ACC;
     const int ty = sy - 1, tz = sz - 1;
     const int tcell = ty * TILE_ACC + tz;
     if (is_target) {
@@ -1668,7 +1702,9 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
                 if (job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + cell] = e;
             }
         } else {
-            // crowded target (strong compression): scan the source window in order (stayers included)
+            // crowded target (strong compression): scan the source window in order (stayers included).  The window does not see far
+            // arrivals: a crowded cell that has some takes the rollback.
+            if (nfar > 0) atomicExch(&ctl->fast_fail, 1);
             for (int dy_ = -1; dy_ <= 1; dy_++) {
                 for (int dz_ = -1; dz_ <= 1; dz_++) {
                     const int src = mod_wrap(ju + dy_, g.ny) * g.nz + mod_wrap(ku + dz_, g.nz);
@@ -1710,6 +1746,7 @@ struct StayOut {
     int * cnt;       // movers per target cell (zero on entry)
     int * lst;       // [BIN_K][n2], unsorted
     double sign;     // -1: the psi source deposits -n (src/System_3d.cpp:349-353)
+    int allow_far;   // half steps beyond one cell are listed like the other movers (single GPU); 0: they raise Ctl::fast_fail (slabs)
 };
 
 __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
@@ -1759,8 +1796,14 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     locate_fast(ym, g.dy, g.inv_dy, g.exact_dy, g.ny, jm, f1);
     locate_fast(zm, g.dz, g.inv_dz, g.exact_dz, g.nz, km, f2);
     const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
-    const bool bad = oy < -1 || oy > 1 || oz < -1 || oz > 1 || !(f1 >= 0.0) || !(f2 >= 0.0);
-    const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc) : pack_offset(oy, oz, f1, f2, kc);
+    const bool bad_position = !(f1 >= 0.0) || !(f2 >= 0.0);  // NaN positions of a blown-up run
+    // a half step beyond one cell: listed under its target cell like every mover of this kernel, but marked (offset code FAR, upper half
+    // of the counter) because the in-order window scan that serves crowded cells would not find it
+    const bool beyond = oy < -1 || oy > 1 || oz < -1 || oz > 1;
+    const bool bad = bad_position || (beyond && !so.allow_far);
+    const bool farm = !bad && beyond;
+    const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc)
+                         : (farm ? (FAR_CODE | ((f1 >= 0.5) ? 64 : 0) | ((f2 >= 0.5) ? 128 : 0) | ((kc & 3) << 8)) : pack_offset(oy, oz, f1, f2, kc));
     if (have) {
         P.pyn[s] = pyn;
         P.pzn[s] = pzn;
@@ -1776,8 +1819,9 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const bool stay = have && !bad && oy == 0 && oz == 0;
     if (have && !bad && !stay) {
         const int target = jm * g.nz + km;
-        const int pos = atomicAdd(&so.cnt[target], 1);
+        const int pos = atomicAdd(&so.cnt[target], farm ? 0x10001 : 1) & 0xffff;
         if (pos < BIN_K) so.lst[(size_t)pos * g.n2 + target] = (s << 2) | (((code >> 6) & 1) << 1) | ((code >> 7) & 1);
+        else if (farm) atomicExch(&ctl->fast_fail, 1);
     }
     const double v = stay ? so.sign * nw : 0.0;
     double c00 = v * (1 - f1) * (1 - f2), c10 = v * f1 * (1 - f2), c01 = v * (1 - f1) * f2, c11 = v * f1 * f2;
@@ -1817,7 +1861,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
 
 // nodes of the psi_middle source from what k_particles_predict_dep left; block = TILE_ACC x TILE_ACC target cells as in k_tile_deposit.
 // cnt_next: the mover counters of the next iteration's predictor (double buffered) are cleared by the cells' owner threads.
-__global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, StayOut so,
+__global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, StayOut so,
                                                               int * __restrict__ cnt_next) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 1);
     __shared__ double acc[4 * TILE_CELLS];
@@ -1827,7 +1871,8 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(const Ctl * ctl, G
     const int cell = wrap_near(jt, g.ny) * g.nz + wrap_near(kt, g.nz);
     const bool owner = ay >= 1 && az >= 1 && jt < g.ny && kt < g.nz;
     const int s0 = start[cell], s1 = start[cell + 1];
-    const int n = so.cnt[cell];
+    const int nraw = so.cnt[cell];
+    const int n = nraw & 0xffff, nfar = nraw >> 16;  // movers that arrived in this cell / how many of them from beyond the +-1 window
     const double ion = tile_prefetch_ion<1>(g, job, ay, az, jt, kt);
     const double k00 = so.corn[0 * (size_t)g.n2 + cell], k10 = so.corn[1 * (size_t)g.n2 + cell], k01 = so.corn[2 * (size_t)g.n2 + cell],
                  k11 = so.corn[3 * (size_t)g.n2 + cell];
@@ -1870,7 +1915,9 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(const Ctl * ctl, G
             for (int q = 0; q < n; q++) job.bin_lst[(size_t)q * g.n2 + cell] = e[q];
         }
     } else {
-        // crowded target (strong compression): scan the source window in order, stayers included
+        // crowded target (strong compression): scan the source window in order, stayers included (far arrivals are not in the window:
+        // a crowded cell that has some takes the rollback)
+        if (nfar > 0) atomicExch(&ctl->fast_fail, 1);
         for (int dy_ = -1; dy_ <= 1; dy_++) {
             for (int dz_ = -1; dz_ <= 1; dz_++) {
                 const int src = mod_wrap(jt + dy_, g.ny) * g.nz + mod_wrap(kt + dz_, g.nz);
