@@ -386,9 +386,9 @@ int check_launch(qpic_ctx * c, const char * what) {
 }
 
 // lists of the slice-start positions: values in slot order (identity permutation) ...
-CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, nullptr, c->P.fy_b, c->P.fz_b}; }
+CellLists lists_base(qpic_ctx * c) { return CellLists{c->start_b, nullptr, c->P.fyz_b}; }
 // lists of the half-step positions: permutation of slots
-CellLists lists_mid(qpic_ctx * c) { return CellLists{c->start_m, c->perm_m, c->P.fy_m, c->P.fz_m}; }
+CellLists lists_mid(qpic_ctx * c) { return CellLists{c->start_m, c->perm_m, c->P.fyz_m}; }
 
 // ---- where things live, single GPU vs one slab of a distributed grid
 int row_first(const qpic_ctx * c) { return c->dist.on ? c->dist.v.row0 : 0; }
@@ -708,8 +708,9 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     TileJob j = tile_job(c);
     j.nout = 2;
     // values n py_next / (1 + psi_middle@particle) are formed inside the deposit (no k_particles_currents_yz on this path)
-    j.o[0] = tile_output(c->P.pyn, 1.0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
-    j.o[1] = tile_output(c->P.pzn, 1.0, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
+    // (the kernels read py_next / pz_next from the paired slot array P.pyzn; `val` is unused by this job)
+    j.o[0] = tile_output(nullptr, 1.0, 0, nullptr, c->f2[QPIC_F2_JY_NEXT], 0);
+    j.o[1] = tile_output(nullptr, 1.0, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
     j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
     j.nw = c->P.nw_s;
     if (c->jyjz_lists) {
@@ -1009,10 +1010,10 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
 int alloc_particles(qpic_ctx * c, size_t count) {
     Particles & P = c->P;
     P.np = (int)count;
-    double ** dbl[] = {&P.y,   &P.z,   &P.py,  &P.pz,  &P.nw,   &P.gamma, &P.px,  &P.fy_p, &P.fz_p, &P.fy_b, &P.fz_b, &P.y_s, &P.z_s, &P.py_s, &P.pz_s,
-                       &P.nw_s, &P.gam, &P.pxs, &P.pyn, &P.pzn,  &P.fy_m,  &P.fz_m, &P.q,    &P.ap,   &P.t1y,  &P.t1z,  &P.dpy, &P.dpz, &P.vjx,  &P.vrho,
-                       &P.vchi, &P.vjy, &P.vjz};
+    double ** dbl[] = {&P.y, &P.z, &P.py, &P.pz, &P.nw, &P.gamma, &P.px, &P.fy_p, &P.fz_p, &P.y_s, &P.z_s, &P.nw_s, &P.gam, &P.pxs, &P.vjx, &P.vrho, &P.vchi, &P.vjy, &P.vjz};
     for (double ** p : dbl) QPIC_TRY(dev_alloc(c, p, count));
+    double2 ** pairs[] = {&P.fyz_b, &P.pyz_s, &P.pyzn, &P.fyz_m, &P.qa, &P.t1, &P.dp};
+    for (double2 ** p : pairs) QPIC_TRY(dev_alloc(c, p, count));
     QPIC_TRY(dev_alloc(c, &P.cell_p, count));
     QPIC_TRY(dev_alloc(c, &P.cell_b, count));
     QPIC_TRY(dev_alloc(c, &P.cell_m, count));
@@ -1687,8 +1688,9 @@ int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, c
         // (re)allocation: the previous arrays stay owned by the context until qpic_destroy
         QPIC_TRY(alloc_particles(c, capacity));
     } else {
-        double * zero[] = {c->P.py, c->P.pz, c->P.pyn, c->P.pzn, c->P.gamma, c->P.px, c->P.gam, c->P.pxs};
+        double * zero[] = {c->P.py, c->P.pz, c->P.gamma, c->P.px, c->P.gam, c->P.pxs};
         for (double * p : zero) QPIC_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * capacity, c->stream));
+        QPIC_CUDA(c, cudaMemsetAsync(c->P.pyzn, 0, sizeof(double2) * capacity, c->stream));
     }
     if (count > 0) {
         QPIC_CUDA(c, cudaMemcpyAsync(c->P.y, y, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));

@@ -148,6 +148,13 @@ __device__ __forceinline__ double ld_stream(const double * p) {
     return __ldcs(p);
 #endif
 }
+__device__ __forceinline__ double2 ld_stream2(const double2 * p) {
+#if defined(QPIC_NO_STREAM_HINT) || defined(QPIC_EMU)
+    return *p;
+#else
+    return __ldcs(p);
+#endif
+}
 // the opposite hint: evict-last, for slot arrays that every B iteration of the slice reads again (A/B knob QPIC_PIN_MASK: bit i
 // = i-th slice invariant of k_particles_predict keeps its L2 lines; 0 = all streamed).  Measured on B200, config #2
 // (gpurun_out/r31_pin.log): mask 0 0.767 ms/slice, 0x3 0.771, 0x1f 0.786, 0x3ff 0.797 -- pinned invariants push the predictor's
@@ -469,8 +476,7 @@ __global__ void k_sort_rank(const Ctl * ctl, int np, const int * __restrict__ ce
 struct CellLists {
     const int * start;  // n2 + 1
     const int * perm;   // np, indices grouped by cell; NULL = identity (the value arrays are already in list order)
-    const double * fy;
-    const double * fz;
+    const double2 * fyz;  // (fy, fz) per particle
 };
 
 // psi source: fourier.in = jx_bunch(i) - rho_bunch(i) - rho_ion, then deposit of -n (src/System_3d.cpp:342-353, :446-457)
@@ -499,7 +505,8 @@ __global__ void k_deposit_charge(const Ctl * ctl, Geom g, CellLists L, const dou
             const int e = L.start[c + 1];
             for (int s = L.start[c]; s < e; s++) {
                 const int p = L.perm ? L.perm[s] : s;
-                const double f1 = L.fy[p], f2 = L.fz[p];
+                const double2 f12 = L.fyz[p];
+                const double f1 = f12.x, f2 = f12.y;
                 const double wy = oy ? f1 : 1 - f1;
                 const double wz = oz ? f2 : 1 - f2;
                 acc += -nw[p] * wy * wz;
@@ -539,7 +546,8 @@ __global__ void k_deposit_jx_rho_chi(const Ctl * ctl, Geom g, CellLists L, const
             const int e = L.start[c + 1];
             for (int s = L.start[c]; s < e; s++) {
                 const int p = L.perm ? L.perm[s] : s;
-                const double f1 = L.fy[p], f2 = L.fz[p];
+                const double2 f12 = L.fyz[p];
+                const double f1 = f12.x, f2 = f12.y;
                 const double wy = oy ? f1 : 1 - f1;
                 const double wz = oz ? f2 : 1 - f2;
                 if (WITH_JX) ajx += vjx[p] * wy * wz;
@@ -604,7 +612,8 @@ __global__ void k_deposit_jy_jz(const Ctl * ctl, Geom g, CellLists L, const doub
             const int e = L.start[c + 1];
             for (int s = L.start[c]; s < e; s++) {
                 const int p = L.perm ? L.perm[s] : s;
-                const double f1 = L.fy[p], f2 = L.fz[p];
+                const double2 f12 = L.fyz[p];
+                const double f1 = f12.x, f2 = f12.y;
                 double wys, wzn, wyn, wzs;
                 // jy_next: staggered in y, node centred in z;  jz_next: node centred in y, staggered in z
                 const bool in_jy = staggered_weight(ry, f1, wys) & node_weight(rz, f2, wzn);
@@ -665,19 +674,22 @@ struct Particles {
     double *fy_p, *fz_p;            // fractional position inside it
     // ---- by slot
     int * cell_b;                   // copies of the above in slot order
-    double *fy_b, *fz_b;
-    double *y_s, *z_s, *py_s, *pz_s, *nw_s;
+    // Slot arrays that are always used together are stored as PAIRS (double2): one 16-byte load per lane instead of two 8-byte loads from
+    // two streams -- half the load instructions and L1 wavefronts of every kernel below, and a cell's particles read by one thread of a
+    // tile kernel become 16-byte pieces of a sector instead of 8-byte ones.
+    double2 * fyz_b;                // (fy, fz) of (y, z)
+    double *y_s, *z_s, *nw_s;       // (y_s, z_s: only on axes whose step is not a power of two, see slot_position)
+    double2 * pyz_s;                // (py, pz) at the slice start
     double *gam, *pxs;              // gamma, px of the current iteration
-    double *pyn, *pzn;              // py_next, pz_next
+    double2 * pyzn;                 // (py_next, pz_next)
     int * cell_m;                   // cell of (y_middle, z_middle)
     int * off_m;                    // packed minimal-image cell offset of the half step + half-cell bits (see pack_offset)
-    double *fy_m, *fz_m;
+    double2 * fyz_m;                // (fy, fz) of the half-step position
     // slice invariants of the B iterations (the reference re-gathers them every iteration, src/System_3d.cpp:419-423,
     // :501-502; (y,z), psi and a_sqr(i) do not change inside the iteration loop)
-    double *q;                      // 1 + psi@p
-    double *ap;                     // a_sqr@p
-    double *t1y, *t1z;              // dx*0.5*d(a_sqr)/dy@p / (1+psi@p), same for z
-    double *dpy, *dpz;              // dpsi/dy@p, dpsi/dz@p
+    double2 * qa;                   // (1 + psi@p, a_sqr@p)
+    double2 * t1;                   // dx*0.5*d(a_sqr)/dy@p / (1+psi@p), same for z
+    double2 * dp;                   // (dpsi/dy@p, dpsi/dz@p)
     double *vjx, *vrho, *vchi, *vjy, *vjz;  // per-particle deposit values
 };
 
@@ -730,13 +742,11 @@ __global__ void k_particles_to_slots(const Ctl * ctl, Geom g, Particles P, const
     if (s >= live_count(ctl, P.np)) return;
     const int p = perm_b[s];
     P.cell_b[s] = P.cell_p[p];
-    P.fy_b[s] = P.fy_p[p];
-    P.fz_b[s] = P.fz_p[p];
+    P.fyz_b[s] = make_double2(P.fy_p[p], P.fz_p[p]);
     // (on an axis whose step is a power of two the kernels rebuild the position from the cell descriptor, exactly: see slot_position)
     if (!g.exact_dy) P.y_s[s] = P.y[p];
     if (!g.exact_dz) P.z_s[s] = P.z[p];
-    P.py_s[s] = P.py[p];
-    P.pz_s[s] = P.pz[p];
+    P.pyz_s[s] = make_double2(P.py[p], P.pz[p]);
     P.nw_s[s] = P.nw[p];
 }
 
@@ -750,10 +760,12 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     const double * a_sqr = a_sqr3 + (size_t)ctl->slice * g.n2;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double fy = P.fy_b[s], fz = P.fz_b[s];
+    const double2 fyz = P.fyz_b[s];
+    const double fy = fyz.x, fz = fyz.y;
     const double a_particle = gather_node(a_sqr, g.ny, g.nz, jc, kc, fy, fz);
     const double psi_particle = gather_node(psi, g.ny, g.nz, jc, kc, fy, fz);
-    const double py = P.py_s[s], pz = P.pz_s[s], nw = P.nw_s[s];
+    const double2 pyz = P.pyz_s[s];
+    const double py = pyz.x, pz = pyz.y, nw = P.nw_s[s];
     const double q = 1 + psi_particle;
     // Divisions by 1 + psi@p are products with ONE reciprocal (within an ulp of the reference's quotients; tolerance 1e-12): the four
     // quotients of this kernel and the six of the predictor were ~60 % of their instructions.
@@ -775,12 +787,10 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
         store_currents<true>(P, s, nw, gamma, px);
     }
     if (want_invariants) {
-        P.q[s] = q;
-        P.ap[s] = a_particle;
-        P.t1y[s] = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz) * rq;
-        P.t1z[s] = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz) * rq;
-        P.dpy[s] = gather_yder(psi, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz);
-        P.dpz[s] = gather_zder(psi, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz);
+        P.qa[s] = make_double2(q, a_particle);
+        P.t1[s] = make_double2(g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz) * rq,
+                               g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz) * rq);
+        P.dp[s] = make_double2(gather_yder(psi, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz), gather_zder(psi, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz));
     }
 }
 
@@ -830,13 +840,15 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     if (s >= P.np) return;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double fy = P.fy_b[s], fz = P.fz_b[s];
-    // issue the independent streaming loads before the dependent field gathers
-    const double q = ld_invariant<0>(P.q + s), gamma = P.gam[s];
-    const double py = ld_invariant<1>(P.py_s + s), pz = ld_invariant<2>(P.pz_s + s);
-    const double t1y = ld_invariant<3>(P.t1y + s), t1z = ld_invariant<4>(P.t1z + s), dpy = ld_invariant<5>(P.dpy + s), dpz = ld_invariant<6>(P.dpz + s);
+    const double2 fyz = P.fyz_b[s];
+    const double fy = fyz.x, fz = fyz.y;
+    // issue the independent streaming loads (16 bytes each) before the dependent field gathers
+    const double2 qa = ld_stream2(P.qa + s), pyz = ld_stream2(P.pyz_s + s), t1 = ld_stream2(P.t1 + s), dp = ld_stream2(P.dp + s);
+    const double q = qa.x, gamma = P.gam[s];
+    const double py = pyz.x, pz = pyz.y;
+    const double t1y = t1.x, t1z = t1.y, dpy = dp.x, dpz = dp.y;
     const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
-    const double a_particle = ld_invariant<9>(P.ap + s), nw = P.nw_s[s];
+    const double a_particle = qa.y, nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -853,8 +865,7 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     double pzn = pz - t1z;
     pzn += g.dx * gamma * dpz * rq;
     pzn += g.dx * by_particle;
-    P.pyn[s] = pyn;
-    P.pzn[s] = pzn;
+    P.pyzn[s] = make_double2(pyn, pzn);
     {
         // corrector (the gamma read above was the previous iteration's; this thread owns element s)
         const double p_squared = 0.25 * (py + pyn) * (py + pyn) + 0.25 * (pz + pzn) * (pz + pzn);
@@ -872,8 +883,7 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     locate_fast(zm, g.dz, g.inv_dz, g.exact_dz, g.nz, km, f2);
     const int cm = jm * g.nz + km;
     if (!FAST) P.cell_m[s] = cm;  // only the general path's cell sort reads it
-    P.fy_m[s] = f1;
-    P.fz_m[s] = f2;
+    P.fyz_m[s] = make_double2(f1, f2);
     if (FAST) {
         const int oy = cell_offset(jm, jc, g.ny), oz = cell_offset(km, kc, g.nz);
         // !(f >= 0) catches the NaN positions of a blown-up run
@@ -903,11 +913,13 @@ __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, co
     if (s >= live_count(ctl, P.np)) return;
     const int cm = P.cell_m[s];
     const int jm = cm / g.nz, km = cm - jm * g.nz;
-    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, P.fy_m[s], P.fz_m[s]);
+    const double2 fm = P.fyz_m[s];
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jm, km, fm.x, fm.y);
     const double nw = P.nw_s[s];
     const double w = 1 + psi_particle;
-    P.vjy[s] = nw * P.pyn[s] / w;
-    P.vjz[s] = nw * P.pzn[s] / w;
+    const double2 pn = P.pyzn[s];
+    P.vjy[s] = nw * pn.x / w;
+    P.vjz[s] = nw * pn.y / w;
 }
 
 // ---- particle migration of slab-decomposed runs (qpic_dist.cuh): where emigrants of k_particles_advance go
@@ -932,8 +944,10 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
     const int p = perm_b ? perm_b[s] : s;
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jc, kc, P.fy_b[s], P.fz_b[s]);
-    const double py = P.pyn[s], pz = P.pzn[s];
+    const double2 fyz = P.fyz_b[s];
+    const double psi_particle = gather_node(psi_middle, g.ny, g.nz, jc, kc, fyz.x, fyz.y);
+    const double2 pn = P.pyzn[s];
+    const double py = pn.x, pz = pn.y;
     P.py[p] = py;
     P.pz[p] = pz;
     if (track_gamma_px || ctl->slice <= 1) {
@@ -943,8 +957,8 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
         P.px[p] = P.pxs[s];
     }
     const double rw = 1.0 / (1 + psi_particle);  // (see k_particles_gamma)
-    const double y = wrap_fast(slot_position(g.exact_dy, jc, P.fy_b[s], g.dy, P.y_s, s) + g.dx * py * rw, g.ly);
-    const double z = wrap_fast(slot_position(g.exact_dz, kc, P.fz_b[s], g.dz, P.z_s, s) + g.dx * pz * rw, g.lz);
+    const double y = wrap_fast(slot_position(g.exact_dy, jc, fyz.x, g.dy, P.y_s, s) + g.dx * py * rw, g.ly);
+    const double z = wrap_fast(slot_position(g.exact_dz, kc, fyz.y, g.dz, P.z_s, s) + g.dx * pz * rw, g.lz);
     P.y[p] = y;
     P.z[p] = z;
     int jn, kn;
@@ -1219,14 +1233,15 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int s = sb + u < s1 ? sb + u : s0;
-            fy[u] = P.fy_b[s];
-            fz[u] = P.fz_b[s];
+            const double2 fyz = P.fyz_b[s];
+            fy[u] = fyz.x;
+            fz[u] = fyz.y;
             if (RHO_CHI) {
                 const double gamma = P.gam[s];
                 // px of the last executed iteration.  The predictor stores it in its last pass only; when the |B| stop condition
                 // ended the slice in an earlier pass (this deposit then still runs: rho / susceptibility of the stopping iteration
                 // are output, src/System_3d.cpp:520-527 before :545-550) it is rebuilt from gamma - px = 1 + psi, exact up to rounding.
-                const double px = stopped_early ? gamma - P.q[s] : P.pxs[s];
+                const double px = stopped_early ? gamma - P.qa[s].x : P.pxs[s];
                 const double vx = px / gamma;
                 const double r = P.nw_s[s] / (1 - vx);
                 v[0][u] = r;
@@ -1348,14 +1363,16 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
             double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
             const double * __restrict__ val = job.o[a].val;
             auto visit = [&](int s, int hy, int hz) {
-                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double2 fm = P.fyz_m[s];
+                const double fy = fm.x, fz = fm.y;
                 double v;
                 if (MODE == 1) {
                     // psi_middle at the particle: its own (unstaggered) half-step cell.  (Staging the block's psi_middle tile in shared
                     // memory was measured slower: 37.0 vs 34.7 us -- the gather hits L1 anyway and the extra registers spill.)
                     const int jm = wrap_near(ju + ((stag_y(a) && !hy) ? 1 : 0), g.ny), km = wrap_near(ku + ((stag_z(a) && !hz) ? 1 : 0), g.nz);
                     const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
-                    v = job.nw[s] * val[s] / w;
+                    const double2 pn = P.pyzn[s];  // (MODE 1: output 0 deposits py_next, output 1 pz_next)
+                    v = job.nw[s] * (a == 0 ? pn.x : pn.y) / w;
                 } else {
                     v = job.o[a].sign * val[s];
                 }
@@ -1388,7 +1405,8 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                     double fy = 0.0, fz = 0.0, pv = 0.0;
                     if (n > 0) {
                         const int s = e >> 2;
-                        fy = P.fy_m[s], fz = P.fz_m[s], pv = val[s];
+                        const double2 fm = P.fyz_m[s];
+                        fy = fm.x, fz = fm.y, pv = val[s];
                     }
                     for (int i = 0; i < n; i++) {
                         const int ce = e;
@@ -1396,7 +1414,8 @@ __global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
                         if (i + 1 < n) {
                             e = mine[(i + 1) * TILE_CELLS];
                             const int s = e >> 2;
-                            fy = P.fy_m[s], fz = P.fz_m[s], pv = val[s];
+                            const double2 fm = P.fyz_m[s];
+                            fy = fm.x, fz = fm.y, pv = val[s];
                         }
                         c00 += cv * (1 - cfy) * (1 - cfz);
                         c10 += cv * cfy * (1 - cfz);
@@ -1472,8 +1491,7 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
     const int n_c = listed(jw) ? job.bin_cnt[cell_c] : 0;
     const int n_y = listed(jw1) ? job.bin_cnt[cell_y] : 0;
     const int n_z = listed(jw) ? job.bin_cnt[cell_z] : 0;
-    const double * __restrict__ pyn = job.o[0].val;
-    const double * __restrict__ pzn = job.o[1].val;
+    const double2 * __restrict__ pyzn = P.pyzn;
     double y00 = 0.0, y10 = 0.0, y01 = 0.0, y11 = 0.0;  // jy corner sums of staggered cell (jt, kt)
     double z00 = 0.0, z10 = 0.0, z01 = 0.0, z11 = 0.0;  // jz
     auto add_y = [&](double v, double wy, double wz) {
@@ -1498,11 +1516,12 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             if (i + 1 < n_c) e_c = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_c];
             const int s = e >> 2, hy = (e >> 1) & 1, hz = e & 1;
             if (hy | hz) {
-                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double2 fm = P.fyz_m[s], pn = pyzn[s];
+                const double fy = fm.x, fz = fm.y;
                 const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw, fy, fz);
                 const double nw = job.nw[s];
-                if (hy) add_y(nw * pyn[s] / w, fy - 0.5, fz);
-                if (hz) add_z(nw * pzn[s] / w, fy, fz - 0.5);
+                if (hy) add_y(nw * pn.x / w, fy - 0.5, fz);
+                if (hz) add_z(nw * pn.y / w, fy, fz - 0.5);
             }
         }
         for (int i = 0; i < n_y; i++) {
@@ -1510,9 +1529,10 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             if (i + 1 < n_y) e_y = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_y];
             if (!((e >> 1) & 1)) {
                 const int s = e >> 2;
-                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double2 fm = P.fyz_m[s];
+                const double fy = fm.x, fz = fm.y;
                 const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw1, kw, fy, fz);
-                add_y(job.nw[s] * pyn[s] / w, fy + 0.5, fz);
+                add_y(job.nw[s] * pyzn[s].x / w, fy + 0.5, fz);
             }
         }
         for (int i = 0; i < n_z; i++) {
@@ -1520,9 +1540,10 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
             if (i + 1 < n_z) e_z = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_z];
             if (!(e & 1)) {
                 const int s = e >> 2;
-                const double fy = P.fy_m[s], fz = P.fz_m[s];
+                const double2 fm = P.fyz_m[s];
+                const double fy = fm.x, fz = fm.y;
                 const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw1, fy, fz);
-                add_z(job.nw[s] * pzn[s] / w, fy, fz + 0.5);
+                add_z(job.nw[s] * pyzn[s].y / w, fy, fz + 0.5);
             }
         }
     } else {
@@ -1538,10 +1559,11 @@ __global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposi
                         const int hy = (code >> 6) & 1, hz = (code >> 7) & 1;
                         const int need_y = (a == 0 && !hy) ? 1 : 0, need_z = (a == 1 && !hz) ? 1 : 0;
                         if (dy_ + (code & 7) - 2 - need_y != 0 || dz_ + ((code >> 3) & 7) - 2 - need_z != 0) continue;
-                        const double fy = P.fy_m[s], fz = P.fz_m[s];
+                        const double2 fm = P.fyz_m[s];
+                        const double fy = fm.x, fz = fm.y;
                         const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, wrap_near(jt + need_y, g.ny), wrap_near(kt + need_z, g.nz), fy, fz);
-                        if (a == 0) add_y(job.nw[s] * pyn[s] / w, hy ? fy - 0.5 : fy + 0.5, fz);
-                        else add_z(job.nw[s] * pzn[s] / w, fy, hz ? fz - 0.5 : fz + 0.5);
+                        if (a == 0) add_y(job.nw[s] * pyzn[s].x / w, hy ? fy - 0.5 : fy + 0.5, fz);
+                        else add_z(job.nw[s] * pyzn[s].y / w, fy, hz ? fz - 0.5 : fz + 0.5);
                     }
                 }
             }
@@ -1628,8 +1650,9 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
     for (int u = 0; u < 4; u++) {
         const bool have = s0 + u < s1;
         code[u] = have ? P.off_m[s0 + u] : STAY_CODE;
-        pfy[u] = have ? P.fy_m[s0 + u] : 0.0;
-        pfz[u] = have ? P.fz_m[s0 + u] : 0.0;
+        const double2 fm = have ? P.fyz_m[s0 + u] : make_double2(0.0, 0.0);
+        pfy[u] = fm.x;
+        pfz[u] = fm.y;
         pv[u] = have ? val[s0 + u] : 0.0;
     }
     __syncthreads();  // counters are zero
@@ -1668,7 +1691,10 @@ __global__ void __launch_bounds__((TILE_ACC + 2) * (TILE_ACC + 2), QPIC_STAY_MIN
             c01 += v * (1 - fy) * fz;
             c11 += v * fy * fz;
         };
-        auto visit = [&](int s) { add(P.fy_m[s], P.fz_m[s], sign * val[s]); };
+        auto visit = [&](int s) {
+            const double2 fm = P.fyz_m[s];
+            add(fm.x, fm.y, sign * val[s]);
+        };
         const int n = cnt[tcell];
         if (job.bin_cnt) job.bin_cnt[cell] = n;  // (halo cells: same value from the neighbour block)
         int * mine = lst + tcell;                // entry i at mine[i * TILE_CELLS]
@@ -1764,12 +1790,14 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const int key_before = warp_base > 0 ? P.cell_b[warp_base - 1] : -2;
     const int key_after = warp_base + 32 < live ? P.cell_b[warp_base + 32] : -2;
     const int jc = c / g.nz, kc = c - jc * g.nz;
-    const double fy = P.fy_b[s], fz = P.fz_b[s];
-    const double q = ld_stream(P.q + s), gamma = P.gam[s];
-    const double py = ld_stream(P.py_s + s), pz = ld_stream(P.pz_s + s);
-    const double t1y = ld_stream(P.t1y + s), t1z = ld_stream(P.t1z + s), dpy = ld_stream(P.dpy + s), dpz = ld_stream(P.dpz + s);
+    const double2 fyz = P.fyz_b[s];
+    const double fy = fyz.x, fz = fyz.y;
+    const double2 qa = ld_stream2(P.qa + s), pyz = ld_stream2(P.pyz_s + s), t1 = ld_stream2(P.t1 + s), dp = ld_stream2(P.dp + s);
+    const double q = qa.x, gamma = P.gam[s];
+    const double py = pyz.x, pz = pyz.y;
+    const double t1y = t1.x, t1z = t1.y, dpy = dp.x, dpz = dp.y;
     const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
-    const double a_particle = ld_stream(P.ap + s), nw = P.nw_s[s];
+    const double a_particle = qa.y, nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -1805,13 +1833,11 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc)
                          : (farm ? (FAR_CODE | ((f1 >= 0.5) ? 64 : 0) | ((f2 >= 0.5) ? 128 : 0) | ((kc & 3) << 8)) : pack_offset(oy, oz, f1, f2, kc));
     if (have) {
-        P.pyn[s] = pyn;
-        P.pzn[s] = pzn;
+        P.pyzn[s] = make_double2(pyn, pzn);
         P.gam[s] = gamma_c;
         if (store_px) P.pxs[s] = px_c;
         store_currents<false>(P, s, nw, gamma_c, px_c);
-        P.fy_m[s] = f1;
-        P.fz_m[s] = f2;
+        P.fyz_m[s] = make_double2(f1, f2);
         P.off_m[s] = code;
         if (bad) atomicExch(&ctl->fast_fail, 1);
     }
@@ -1879,7 +1905,8 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g,
     const double * __restrict__ val = job.o[0].val;
     double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
     auto visit = [&](int s) {
-        const double fy = P.fy_m[s], fz = P.fz_m[s], v = so.sign * val[s];
+        const double2 fm = P.fyz_m[s];
+        const double fy = fm.x, fz = fm.y, v = so.sign * val[s];
         c00 += v * (1 - fy) * (1 - fz);
         c10 += v * fy * (1 - fz);
         c01 += v * (1 - fy) * fz;
@@ -1983,8 +2010,8 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
     int lr = jw - job.list_row0;
     lr += (lr < 0) ? g.ny : 0;
     const int n = lr < job.list_rows ? job.bin_cnt[cell] : 0;
-    const double * __restrict__ pyn = job.o[0].val;
-    const double * __restrict__ pzn = job.o[1].val;
+    const double2 * __restrict__ pyzn = P.pyzn;
+    const double2 * __restrict__ fyzm = P.fyz_m;
     // psi_middle at the four nodes of this cell: every particle of the list gathers from them (src/System_3d.cpp:480-482)
     const int jw1 = wrap_inc(jw, g.ny), kw1 = wrap_inc(kw, g.nz);
     const double p00 = job.psi_mid[jw * g.nz + kw], p10 = job.psi_mid[jw1 * g.nz + kw], p01 = job.psi_mid[jw * g.nz + kw1],
@@ -2018,7 +2045,10 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
             z1p += hz ? c11 : 0.0;
         }
     };
-    auto visit = [&](int s, int hy, int hz) { visit5(P.fy_m[s], P.fz_m[s], job.nw[s], pyn[s], pzn[s], hy, hz); };
+    auto visit = [&](int s, int hy, int hz) {
+        const double2 fm = fyzm[s], pn = pyzn[s];
+        visit5(fm.x, fm.y, job.nw[s], pn.x, pn.y, hy, hz);
+    };
     if (n <= BIN_K) {
         // the list holds the MOVERS that ended their half step in this cell (k_tile_stay_deposit), sorted by slot; the cell's own
         // stayers are the particles of its slot range whose offset code is (0, 0).  Ascending slot order = movers from lower
@@ -2036,8 +2066,10 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
             const bool two = sb + 1 < s1;
             const int sB = two ? sb + 1 : sb;
             const int cA = P.off_m[sb], cB = P.off_m[sB];
-            const double fyA = P.fy_m[sb], fzA = P.fz_m[sb], nwA = job.nw[sb], vyA = pyn[sb], vzA = pzn[sb];
-            const double fyB = P.fy_m[sB], fzB = P.fz_m[sB], nwB = job.nw[sB], vyB = pyn[sB], vzB = pzn[sB];
+            const double2 fA = fyzm[sb], pA = pyzn[sb], fB = fyzm[sB], pB = pyzn[sB];
+            const double nwA = job.nw[sb], nwB = job.nw[sB];
+            const double fyA = fA.x, fzA = fA.y, vyA = pA.x, vzA = pA.y;
+            const double fyB = fB.x, fzB = fB.y, vyB = pB.x, vzB = pB.y;
             if ((cA & 63) == STAY_CODE) visit5(fyA, fzA, nwA, vyA, vzA, (cA >> 6) & 1, (cA >> 7) & 1);
             if (two && (cB & 63) == STAY_CODE) visit5(fyB, fzB, nwB, vyB, vzB, (cB >> 6) & 1, (cB >> 7) & 1);
         }
