@@ -651,14 +651,24 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 // with the published lists the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their cell directly
 // and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
 bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists && c->jyjz_cell; }
+// slabs: target rows whose deposits (corner rows j, j + 1; the staggered jy rows j - 1 .. j + 1) stay inside own rows + DIST_HALO halo rows
+void far_rows(const qpic_ctx * c, int * row_lo, int * row_n) {
+    *row_lo = 0;
+    *row_n = 0;
+    if (c->dist.on) {
+        *row_lo = (c->dist.v.row0 - DIST_HALO + 1 + c->g.ny) % c->g.ny;
+        *row_n = c->dist.v.ny_loc + 2 * DIST_HALO - 2;
+    }
+}
 // far-mover lists of B iteration c->cur_it (only with the stayers-direct tile kernels on a single GPU and without the predictor-side deposit,
 // whose own lists take every mover)
 FarMovers far_view(const qpic_ctx * c, bool fast) {
-    FarMovers f = {nullptr, nullptr, nullptr};
+    FarMovers f = {nullptr, nullptr, nullptr, 0, 0};
     if (fast && c->far_movers && c->far_cnt[0] && !(c->predict_deposit && c->stay.corn)) {
         f.cnt = c->far_cnt[c->cur_it & 1];
         f.lst = c->far_lst;
         f.clear = c->far_cnt[(c->cur_it + 1) & 1];
+        far_rows(c, &f.row_lo, &f.row_n);
     }
     return f;
 }
@@ -873,7 +883,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         } else if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
             QPIC_LAUNCH_FLAT(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
-                             (!fast || it == M - 1) ? 1 : 0, far_view(c, fast && stayers_direct(c) && !c->dist.on));
+                             (!fast || it == M - 1) ? 1 : 0, far_view(c, fast && stayers_direct(c)));
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
         // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored.  (Forking it after
@@ -1045,7 +1055,8 @@ int alloc_particles(qpic_ctx * c, size_t count) {
         QPIC_TRY(dev_alloc(c, &c->stay.lead, 4 * nwarps));
         QPIC_TRY(dev_alloc(c, &c->stay.trail, 4 * nwarps));
         c->stay.sign = -1.0;
-        c->stay.allow_far = (c->far_movers && !c->dist.on) ? 1 : 0;
+        c->stay.allow_far = c->far_movers ? 1 : 0;
+        far_rows(c, &c->stay.far_row_lo, &c->stay.far_row_n);
     }
     return QPIC_OK;
 }
@@ -1061,8 +1072,10 @@ int handle_ctl(qpic_ctx * c, const Ctl & seen) {
         const int e = seen.dist_error;
         if (e != 0) return fail(c, QPIC_ERR_STATE, "distributed sweep failed on rank %d: %s", c->dist.v.rank, why[e > 0 && e < 5 ? e : 0]);
         if (seen.fast_fail != 0) {
-            return fail(c, QPIC_ERR_UNSUPPORTED, "rank %d: a half step moved a particle by more than one cell; the sorted-deposit fallback is not available in distributed sweeps",
-                        c->dist.v.rank);
+            return fail(c, QPIC_ERR_UNSUPPORTED,
+                        "rank %d: a half step carried a particle beyond the %d halo rows of its slab (or a far-mover list overflowed); the sorted-deposit fallback "
+                        "is not available in distributed sweeps",
+                        c->dist.v.rank, DIST_HALO);
         }
     }
     if (seen.stop_tag != 0) {
@@ -1510,7 +1523,7 @@ static int create_impl(qpic_ctx * c) {
         const char * e2 = getenv("QPIC_JYJZ_CELL");
         c->jyjz_cell = !(e2 && e2[0] == '0');
         const char * e9 = getenv("QPIC_FAR_MOVERS");
-        c->far_movers = !(e9 && e9[0] == '0') && !D.on && c->jyjz_lists && c->jyjz_cell && !p.force_general_deposit;
+        c->far_movers = !(e9 && e9[0] == '0') && c->jyjz_lists && c->jyjz_cell && !p.force_general_deposit;
         if (c->far_movers) {
             QPIC_TRY(dev_alloc(c, &c->far_cnt[0], n2));
             QPIC_TRY(dev_alloc(c, &c->far_cnt[1], n2));

@@ -25,7 +25,9 @@
 namespace qpic {
 
 constexpr int DIST_MAX = 8;
-constexpr int DIST_HALO = 2;
+// halo rows on either side of a slab: 2 suffice for the gathers and the +-1 cell movers; 4 let half steps of up to three cells cross a
+// slab edge on the sort-free path (far movers, qpic_kernels.cuh) -- the halo reduce carries their partial sums to the owner
+constexpr int DIST_HALO = 4;
 // reduce buffers, one per deposit target so that a buffer is reused only a whole iteration later
 enum DistReduceSlot { RB_CHARGE = 0, RB_JX, RB_JY, RB_JZ, RB_RHO, RB_CHI, RB_COUNT };
 // fields that live inside the exchange region because neighbours write their halo rows

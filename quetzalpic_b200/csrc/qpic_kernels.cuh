@@ -807,10 +807,21 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
 constexpr int FAR_K = 8;
 constexpr int FAR_CODE = 7 | (7 << 3);  // bits 0-5 of an offset code: neither a stayer nor inside any tile window
 struct FarMovers {
-    int * cnt;   // [n2] arrivals per target cell of THIS iteration (NULL: far movers abort, as in round 1 and on slabs)
+    int * cnt;   // [n2] arrivals per target cell of THIS iteration (NULL: far movers abort, as in round 1)
     int * lst;   // [FAR_K][n2] entries slot << 2 | hy << 1 | hz
     int * clear; // [n2] the other buffer: cleared by the deposit's owner threads
+    // slab-decomposed sweeps: the target rows a rank can deposit into = its own rows and the halo rows whose partial sums the halo reduce
+    // carries to the neighbour (row_n == 0: every row, single GPU); a far mover that lands outside still takes the abort
+    int row_lo, row_n;
 };
+
+__device__ __forceinline__ bool far_row_ok(int row_lo, int row_n, int jm, int ny) {
+    if (row_n == 0) return true;
+    int rel = jm - row_lo;
+    rel += (rel < 0) ? ny : 0;
+    rel -= (rel >= ny) ? ny : 0;
+    return rel < row_n;
+}
 
 // minimal-image cell offset jm - jc folded into [-n/2, n/2]
 __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
@@ -893,7 +904,7 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
         } else if (oy < -1 || oy > 1 || oz < -1 || oz > 1) {
             // far mover: listed under its target cell (see FarMovers)
             const int hy = f1 >= 0.5 ? 1 : 0, hz = f2 >= 0.5 ? 1 : 0;
-            const int pos = far.cnt ? atomicAdd(&far.cnt[cm], 1) : FAR_K;
+            const int pos = (far.cnt && far_row_ok(far.row_lo, far.row_n, jm, g.ny)) ? atomicAdd(&far.cnt[cm], 1) : FAR_K;
             if (pos < FAR_K) far.lst[(size_t)pos * g.n2 + cm] = (s << 2) | (hy << 1) | hz;
             else atomicExch(&ctl->fast_fail, 1);
             P.off_m[s] = FAR_CODE | (hy << 6) | (hz << 7) | ((kc & 3) << 8);
@@ -1772,7 +1783,8 @@ struct StayOut {
     int * cnt;       // movers per target cell (zero on entry)
     int * lst;       // [BIN_K][n2], unsorted
     double sign;     // -1: the psi source deposits -n (src/System_3d.cpp:349-353)
-    int allow_far;   // half steps beyond one cell are listed like the other movers (single GPU); 0: they raise Ctl::fast_fail (slabs)
+    int allow_far;   // half steps beyond one cell are listed like the other movers; 0: they raise Ctl::fast_fail
+    int far_row_lo, far_row_n;  // slabs: legal target rows of a far mover, see FarMovers (0 rows: all)
 };
 
 __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
@@ -1828,7 +1840,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     // a half step beyond one cell: listed under its target cell like every mover of this kernel, but marked (offset code FAR, upper half
     // of the counter) because the in-order window scan that serves crowded cells would not find it
     const bool beyond = oy < -1 || oy > 1 || oz < -1 || oz > 1;
-    const bool bad = bad_position || (beyond && !so.allow_far);
+    const bool bad = bad_position || (beyond && !(so.allow_far && far_row_ok(so.far_row_lo, so.far_row_n, jm, g.ny)));
     const bool farm = !bad && beyond;
     const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc)
                          : (farm ? (FAR_CODE | ((f1 >= 0.5) ? 64 : 0) | ((f2 >= 0.5) ? 128 : 0) | ((kc & 3) << 8)) : pack_offset(oy, oz, f1, f2, kc));

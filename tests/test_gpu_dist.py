@@ -85,3 +85,38 @@ def test_stop_condition_reaches_every_rank():
         assert g.solve_wakefield() == [6, 6]
         for f in FIELDS:
             assert slice_rel_l2(g.field3d(f), o.field3d(f)) < 1e-9, f
+
+
+@pytest.mark.parametrize("predict_deposit", ["0", "1"], ids=["tile-kernels", "predictor-side-deposit"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_sweep_with_half_steps_beyond_one_cell(world, predict_deposit, monkeypatch):
+    """Strong drive on a coarse xi step: half steps cross more than one cell, also across slab edges (reference: any displacement is
+    legal, src/array_utils.cpp:85-118).  Round 1 stopped a distributed sweep with an error here; now the far movers are listed under their
+    target cell by the predictor (both kernel pairs: the tile kernels and the predictor-side deposit that config #4 selects), the psi_middle
+    source deposit merges them in slot order and the 4-row halo reduce carries what lands beyond the slab edge to its owner."""
+    from quetzalpic_b200.dist import SlabGroup
+    monkeypatch.setenv("QPIC_PREDICT_DEPOSIT", predict_deposit)
+    nx, ny, nz = 8, 64 * world // 2 * 2, 64
+    case = Case.synthetic(n=(nx, ny, nz), d=(0.5, 0.1, 0.1), M=2, ppc=(2, 1), a0=3.0, sigma=(0.8, 3.0, 3.0))
+    wx, wy, wz = case.laser[1:4]
+    case.laser = (case.laser[0], wx, wy, wz, 0.6 * nx * 0.5, 0.1 * ny / world + 0.4, 3.2)  # next to the edge between ranks 0 and 1
+    o = case.make_oracle()
+    # the case is meant to have far movers (without the lists -- QPIC_FAR_MOVERS=0 -- the sweep ends with QPIC_ERR_UNSUPPORTED on slabs): in the
+    # oracle's sweep some full steps exceed two cells, i.e. half steps exceed one
+    o.begin()
+    worst = 0.0
+    for _ in range(nx - 1):
+        y0 = o.particles("y").copy()
+        o.step_slice()
+        dy = np.abs(o.particles("y") - y0)
+        worst = max(worst, np.minimum(dy, case.l[1] - dy).max() / 0.1)
+    o.finish()
+    assert worst > 2.0, worst
+    y, z, w = case.particles
+    with SlabGroup(world, nx, ny, nz, case.l[0], case.l[1], case.l[2], case.M, devices=devices_for(world), stop_check_interval=2) as g:
+        g.set_laser_gaussian(*case.laser)
+        g.init_wake_particles(y, z, w)
+        assert g.solve_wakefield() == [o.stopped_at] * world
+        assert sum(s.particle_count for s in g.ranks) == y.size
+        for f in FIELDS:
+            assert slice_rel_l2(g.field3d(f), o.field3d(f)) < 1e-10, f

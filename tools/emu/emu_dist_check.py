@@ -19,7 +19,7 @@ EMU = QpicLibrary(os.path.join(ROOT, "tools", "emu", "_build", "libqpic_emu_debu
 def main():
     world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     nx, ny, nz = int(os.environ.get("NX", "5")), 64 * (world // 2), 64
-    lx, ly, lz = 0.2 * nx, 6.4 * (world // 2), 6.4
+    lx, ly, lz = float(os.environ.get("DX", "0.2")) * nx, 6.4 * (world // 2), 6.4
     M = 2
     a0 = float(os.environ.get("A0", "1.6"))
     wx, wy, wz = gaussian_laser_widths(0.8, 3.0, 3.0)
@@ -33,7 +33,7 @@ def main():
         g.init_wake_particles(y, z, n)
         before = [s.particle_count for s in g.ranks]
         stopped = g.solve_wakefield()
-        print('  particles per rank', before, '->', [s.particle_count for s in g.ranks])
+        print('  particles per rank', before, '->', [s.particle_count for s in g.ranks], ' fast-path aborts', [s.fast_path_aborts for s in g.ranks])
         worst = 0.0
         for f in ["susceptibility", "ex", "ey", "ez", "by", "bz"]:
             a, b = g.field3d(f), o.field3d(f)
