@@ -488,7 +488,7 @@ int stream_depend(qpic_ctx * c, cudaStream_t from, cudaStream_t to) {
 }
 
 // count[] (already accumulated by a particle kernel) -> start[], perm[] in canonical order
-int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cell, int * start, int * perm) {
+int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cell, int * start, int * perm, bool with_slot_copies = false) {
     // distributed: bucket n2 collects the entries of emigrated particles; the live count is the start of that bucket
     const int n2 = c->g.n2 + (c->dist.on ? 1 : 0), np = c->P.np;
     int * live_out = (c->dist.on && ctl == c->ctl) ? &c->ctl->np1 : nullptr;
@@ -506,8 +506,14 @@ int enqueue_sort(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, const int * cel
     if (np > 0) {
         QPIC_LAUNCH_FLAT(k_sort_fill, blocks_for(np, 256), 256, 0, st, ctl, np, cell, c->cursor, c->tmp);
         QPIC_TRY(check_launch(c, "k_sort_fill"));
-        QPIC_LAUNCH_FLAT(k_sort_rank, blocks_for(np, 256), 256, 0, st, ctl, np, cell, start, c->tmp, perm);
-        QPIC_TRY(check_launch(c, "k_sort_rank"));
+        if (with_slot_copies) {
+            // (cell == P.cell_p here: the sort of the slice-start positions, whose slot copies ride along)
+            QPIC_LAUNCH_FLAT(k_rank_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, st, ctl, c->g, c->P, np, (const int *)start, (const int *)c->tmp, perm);
+            QPIC_TRY(check_launch(c, "k_particles_to_slots"));
+        } else {
+            QPIC_LAUNCH_FLAT(k_sort_rank, blocks_for(np, 256), 256, 0, st, ctl, np, cell, start, c->tmp, perm);
+            QPIC_TRY(check_launch(c, "k_sort_rank"));
+        }
     }
     return QPIC_OK;
 }
@@ -988,11 +994,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(check_launch(c, "k_migrate_unpack"));
     }
     if (deposit_done) QPIC_CUDA(c, cudaStreamWaitEvent(sa, deposit_done, 0));
-    QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b));
-    if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->perm_b);
-        QPIC_TRY(check_launch(c, "k_particles_to_slots"));
-    }
+    QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_p, c->start_b, c->perm_b, true));
     // (the last block of k_end_of_slice has moved Ctl::slice on)
     QPIC_TRY(stream_depend(c, sb, sa));
     return QPIC_OK;
@@ -1008,11 +1010,7 @@ int enqueue_rebuild_base_lists(qpic_ctx * c) {
         QPIC_LAUNCH_FLAT(k_locate_count, blocks_for(live, 256), 256, 0, c->stream, live, c->g, c->P.y, c->P.z, c->P.cell_p, c->P.fy_p, c->P.fz_p, c->count);
         QPIC_TRY(check_launch(c, "k_locate_count"));
     }
-    QPIC_TRY(enqueue_sort(c, c->stream, ctl, c->P.cell_p, c->start_b, c->perm_b));
-    if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_to_slots, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, c->stream, ctl, c->g, c->P, c->perm_b);
-        QPIC_TRY(check_launch(c, "k_particles_to_slots"));
-    }
+    QPIC_TRY(enqueue_sort(c, c->stream, ctl, c->P.cell_p, c->start_b, c->perm_b, true));
     c->lists_dirty = false;
     return QPIC_OK;
 }
@@ -1590,7 +1588,7 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_particles_predict<true>);
         QPIC_PRELOAD(k_particles_gamma);
         QPIC_PRELOAD(k_particles_advance);
-        QPIC_PRELOAD(k_particles_to_slots);
+        QPIC_PRELOAD(k_rank_to_slots);
         QPIC_PRELOAD(k_locate_count);
         QPIC_PRELOAD(k_scan_chunk_sums);
         QPIC_PRELOAD(k_scan_sums);

@@ -734,20 +734,31 @@ __device__ __forceinline__ double slot_position(int exact, int jc, double f, dou
     return exact ? ((double)jc + f) * d : ld_stream(stored + s);
 }
 
-// after the cell sort of the slice-start positions: copy the particle's slice inputs from id order to slot order
-__global__ void k_particles_to_slots(const Ctl * ctl, Geom g, Particles P, const int * __restrict__ perm_b) {
+// After the cell sort of the slice-start positions the particle's slice inputs are copied from id order to slot order.  k_sort_rank and that
+// copy in one pass (the sort of the slice-start positions is always followed by the slot copies):
+// entry t of the bucket-filled list finds its canonical position (ascending particle id inside the cell) and copies its particle's slice
+// inputs straight to that slot.  One launch and one pass over perm less per slice.
+__global__ void k_rank_to_slots(const Ctl * ctl, Geom g, Particles P, int np, const int * __restrict__ start, const int * __restrict__ tmp, int * __restrict__ perm) {
     QPIC_KERNEL_BEGIN(KID_k_particles_to_slots);
     if (cancelled(ctl)) return;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= live_count(ctl, P.np)) return;
-    const int p = perm_b[s];
-    P.cell_b[s] = P.cell_p[p];
-    P.fyz_b[s] = make_double2(P.fy_p[p], P.fz_p[p]);
-    // (on an axis whose step is a power of two the kernels rebuild the position from the cell descriptor, exactly: see slot_position)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= entry_count(ctl, np)) return;
+    const int p = tmp[t];
+    const int c = P.cell_p[p];
+    const int b = start[c], e = start[c + 1];
+    // this particle's data: in flight while the bucket is ranked
+    const double fy = P.fy_p[p], fz = P.fz_p[p], py = P.py[p], pz = P.pz[p], nw = P.nw[p];
+    int rank = 0;
+    for (int u = b; u < e; u++) rank += (tmp[u] < p) ? 1 : 0;
+    const int s = b + rank;
+    perm[s] = p;
+    if (s >= live_count(ctl, P.np)) return;  // (slab-decomposed sweeps: the bucket of emigrated entries lies beyond the live slots)
+    P.cell_b[s] = c;
+    P.fyz_b[s] = make_double2(fy, fz);
     if (!g.exact_dy) P.y_s[s] = P.y[p];
     if (!g.exact_dz) P.z_s[s] = P.z[p];
-    P.pyz_s[s] = make_double2(P.py[p], P.pz[p]);
-    P.nw_s[s] = P.nw[p];
+    P.pyz_s[s] = make_double2(py, pz);
+    P.nw_s[s] = nw;
 }
 
 // initial gamma, px (src/System_3d.cpp:368-378) + the values deposited at :390-397 + iteration invariants
