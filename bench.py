@@ -419,6 +419,9 @@ def run_b200_arm(args, w):
     for name, (count, tot) in prof.items():
         per_launch_ms = tot / count
         nbytes = kernel_algorithmic_bytes(name, N, P)
+        if name == "k_particles_predict" and "k_particles_gamma" not in prof and M > 0:
+            # the first predictor pass of a slice does k_particles_gamma's work (predict_inputs<true>): its 8(d) share is spread over the M launches
+            nbytes += kernel_algorithmic_bytes("k_particles_gamma", N, P) / M
         dram = NCU_DRAM_BYTES.get(name)
         alg_sum += nbytes * count / 8.0
         if dram:

@@ -98,6 +98,7 @@ struct qpic_ctx {
     struct FftLaunch {
         int spb = 1, threads = 128, blocks = 1;
         size_t smem = 0;
+        bool wide = false;  // power-of-two engine: the WIDE build of the kernels (<= 896 threads, one exchange buffer per sequence)
     };
     FftLaunch rows_real, rows_cplx, cols_half, cols_full;
     bool pow2_y = false, pow2_z = false;
@@ -156,6 +157,7 @@ struct qpic_ctx {
     StayOut stay = {};
     int * stay_cnt[2] = {nullptr, nullptr};
     int cur_it = 0;
+    bool fuse_gamma = true;                        // the first predictor pass of a slice does k_particles_gamma's work (QPIC_FUSE_GAMMA=0: separate kernel)
     bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
     double * xy_scratch = nullptr;  // qpic_download_xy_cut: (nx, ny) staging for the cuts of resident 3-D arrays
@@ -302,21 +304,37 @@ KernelLimits kernel_limits(K... kernels) {
     return lim;
 }
 
-int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what, const KernelLimits & lim = KernelLimits()) {
+// lim: the narrow builds of the kernels (power-of-two engine) / the generic engine's kernels; lim_wide: the WIDE builds
+int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what, const KernelLimits & lim = KernelLimits(),
+                    const KernelLimits & lim_wide = KernelLimits()) {
     const int n = P.n;
     if (P.log2n > 0) {
         const int e8 = n / 8;
         // These kernels are latency bound (a few warps per SM at most), so the fastest shape is ONE wave of fat blocks:
         // as many sequences per block as it takes to cover the batch with <= 148 blocks, within the kernels' thread (register)
-        // and shared-memory limits.
-        int spb = (nseq + 147) / 148;
-        const size_t per_seq = sizeof(double2) * 2 * (size_t)p2_pad_len(n);  // two alternating (padded) exchange buffers per sequence
-        while (spb > 1 && (spb * e8 > lim.max_threads || spb * per_seq > lim.max_dyn_smem)) spb--;
-        if (spb < 1) spb = 1;
-        while (spb * e8 < 32) spb *= 2;
+        // and shared-memory limits.  Where two alternating exchange buffers per sequence do not leave room for that (1024-point axes:
+        // 1024 sequences want 7 per block = 262 KB) the single-buffer mode -- one more barrier per exchange -- is used if it saves a wave.
+        auto fit = [&](size_t per_seq, const KernelLimits & lim) {
+            int spb = (nseq + 147) / 148;
+            while (spb > 1 && (spb * e8 > lim.max_threads || spb * per_seq > lim.max_dyn_smem)) spb--;
+            if (spb < 1) spb = 1;
+            while (spb * e8 < 32) spb *= 2;
+            return spb;
+        };
+        const size_t one = sizeof(double2) * (size_t)p2_pad_len(n);
+        const int spb2 = fit(2 * one, lim), spb1 = fit(one, lim_wide);
+        const int waves2 = ((nseq + spb2 - 1) / spb2 + 147) / 148, waves1 = ((nseq + spb1 - 1) / spb1 + 147) / 148;
+        const bool single = waves1 < waves2;
+        const int spb = single ? spb1 : spb2;
+        L->wide = single;
         L->spb = spb;
         L->threads = spb * e8;
-        L->smem = spb * per_seq;
+        L->smem = spb * (single ? one : 2 * one);
+        const KernelLimits & use = single ? lim_wide : lim;
+        if (L->threads > use.max_threads) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d needs more than %d threads per block", what, n, use.max_threads);
+        if (L->smem > use.max_dyn_smem) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d does not fit the shared-memory transform", what, n);
+        L->blocks = (nseq + L->spb - 1) / L->spb;
+        return QPIC_OK;
     } else {
         L->spb = 1;
         L->threads = pick_threads(n / 4);
@@ -531,7 +549,7 @@ int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bo
         const int col0 = c->dist.on ? (full ? c->dist.col0_full : c->dist.col0_half) : 0;
         const int mine = c->dist.on ? (full ? c->dist.ncols_full : c->dist.ncols_half) : ncols;
         double2 * cols = c->dist.on ? m.base[c->dist.v.rank] : c->spec;
-        QPIC_LAUNCH(k_p2_cols_solve, L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, cols, m.cpr, mine, inv + (size_t)col0 * c->g.ny,
+        QPIC_LAUNCH((L.wide ? k_p2_cols_solve<true> : k_p2_cols_solve<false>), L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, cols, m.cpr, mine, inv + (size_t)col0 * c->g.ny,
                     want_border_sums ? c->spec_row0 : (double2 *)nullptr, want_border_sums ? c->spec_colsum : (double2 *)nullptr, c->dist.on ? c->cols_ticket : (int *)nullptr,
                     partials_map(c), c->dist.on ? c->dist.v.rank : 0, col0, nz);
     } else {
@@ -561,7 +579,7 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     }
 #endif
     if (c->pow2_z) {
-        QPIC_LAUNCH((c->dist.on ? k_p2_rows_r2c<true> : k_p2_rows_r2c<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
+        QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_r2c<true, true> : k_p2_rows_r2c<false, true>) : (c->dist.on ? k_p2_rows_r2c<true> : k_p2_rows_r2c<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_r2c<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz, R.spb);
     }
@@ -570,7 +588,7 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     QPIC_TRY(enqueue_columns(c, st, ctl, D, false, fuse));
     QPIC_TRY(dist_barrier(c, st));  // every rank's columns (and border-sum partials) are done
     if (c->pow2_z) {
-        QPIC_LAUNCH((c->dist.on ? k_p2_rows_c2r<true> : k_p2_rows_c2r<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
+        QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_c2r<true, true> : k_p2_rows_c2r<false, true>) : (c->dist.on ? k_p2_rows_c2r<true> : k_p2_rows_c2r<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
                     row_first(c), ny, c->inv_scale, fuse ? 1 : 0, c->dist.on ? reinterpret_cast<const double *>(c->dist.region + c->dist.v.lay.partials) : c->partials,
                     c->prm.psi_threshold - 1, (fuse && !c->dist.on) ? (const double2 *)c->spec_row0 : (const double2 *)nullptr,
                     (fuse && !c->dist.on) ? (const double2 *)c->spec_colsum : (const double2 *)nullptr);
@@ -588,7 +606,7 @@ int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, doub
 int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, double * bz, double threshold, int iteration) {
     const qpic_ctx::FftLaunch & R = c->rows_cplx;
     if (c->pow2_z) {
-        QPIC_LAUNCH((c->dist.on ? k_p2_rows_b_backward<true> : k_p2_rows_b_backward<false>), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
+        QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_b_backward<true, true> : k_p2_rows_b_backward<false, true>) : (c->dist.on ? k_p2_rows_b_backward<true> : k_p2_rows_b_backward<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
                     c->inv_scale, row_first(c), row_count(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_b_backward<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
@@ -798,7 +816,8 @@ int enqueue_slice_head(qpic_ctx * c, bool fast, bool want_invariants, bool with_
     const int np = c->P.np;
     cudaStream_t st = c->stream;
     QPIC_TRY(enqueue_potential(c, st, fast, 0, c->f2[QPIC_F2_PSI]));
-    if (np > 0) {
+    // with B iterations to follow, the first predictor pass gathers the invariants and forms the initial gamma itself (predict_inputs<true>)
+    if (np > 0 && !(want_invariants && c->fuse_gamma)) {
         QPIC_LAUNCH_FLAT(k_particles_gamma, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, st, c->ctl, c->g, c->P, c->perm_b, c->f3[QPIC_F3_ASQR], c->f2[QPIC_F2_PSI],
                          want_invariants ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_gamma"));
@@ -884,12 +903,15 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         if (np > 0 && fast && predict_deposit_on(c)) {
             StayOut so = c->stay;
             so.cnt = c->stay_cnt[it & 1];
-            QPIC_LAUNCH(k_particles_predict_dep, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so);
+            auto predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true> : k_particles_predict_dep<false>;
+            QPIC_LAUNCH(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so,
+                        (const double *)c->f3[QPIC_F3_ASQR], (const double *)c->f2[QPIC_F2_PSI]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         } else if (np > 0) {
             auto predict = fast ? k_particles_predict<true> : k_particles_predict<false>;
+            if (it == 0 && c->fuse_gamma) predict = fast ? k_particles_predict<true, true> : k_particles_predict<false, true>;
             QPIC_LAUNCH_FLAT(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], c->count,
-                             (!fast || it == M - 1) ? 1 : 0, far_view(c, fast && stayers_direct(c)));
+                             (!fast || it == M - 1) ? 1 : 0, far_view(c, fast && stayers_direct(c)), (const double *)c->f3[QPIC_F3_ASQR], (const double *)c->f2[QPIC_F2_PSI]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
         }
         // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored.  (Forking it after
@@ -943,6 +965,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             if (c->pow2_z) {
                 const bool pre = fast && c->jyjz_lists && c->b_src;
                 auto kern = c->dist.on ? k_p2_rows_b_forward<true, false> : (pre ? k_p2_rows_b_forward<false, true> : k_p2_rows_b_forward<false, false>);
+                if (R.wide) kern = c->dist.on ? k_p2_rows_b_forward<true, false, true> : (pre ? k_p2_rows_b_forward<false, true, true> : k_p2_rows_b_forward<false, false, true>);
                 QPIC_LAUNCH(kern, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D, c->f2[QPIC_F2_BY_CUR],
                             c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT],
                             (const double2 *)c->b_src, spec_map(c, true), row_first(c), row_count(c));
@@ -1355,12 +1378,16 @@ static int create_impl(qpic_ctx * c) {
     c->pow2_z = c->fz.plan.log2n > 0;
     const KernelLimits lim_real = kernel_limits(k_p2_rows_r2c<false>, k_p2_rows_r2c<true>, k_p2_rows_c2r<false>, k_p2_rows_c2r<true>);
     const KernelLimits lim_cplx = kernel_limits(k_p2_rows_b_forward<false, false>, k_p2_rows_b_forward<false, true>, k_p2_rows_b_forward<true, false>, k_p2_rows_b_backward<false>, k_p2_rows_b_backward<true>,
-                                                k_p2_rows_c2c);
-    const KernelLimits lim_cols = kernel_limits(k_p2_cols_solve);
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform", lim_real));
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform", lim_cplx));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform", lim_cols));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform", lim_cols));
+                                                k_p2_rows_c2c<false>);
+    const KernelLimits lim_cols = kernel_limits(k_p2_cols_solve<false>);
+    const KernelLimits wide_real = kernel_limits(k_p2_rows_r2c<false, true>, k_p2_rows_r2c<true, true>, k_p2_rows_c2r<false, true>, k_p2_rows_c2r<true, true>);
+    const KernelLimits wide_cplx = kernel_limits(k_p2_rows_b_forward<false, false, true>, k_p2_rows_b_forward<false, true, true>, k_p2_rows_b_forward<true, false, true>,
+                                                 k_p2_rows_b_backward<false, true>, k_p2_rows_b_backward<true, true>, k_p2_rows_c2c<true>);
+    const KernelLimits wide_cols = kernel_limits(k_p2_cols_solve<true>);
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform", lim_real, wide_real));
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform", lim_cplx, wide_cplx));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform", lim_cols, wide_cols));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform", lim_cols, wide_cols));
     if (!c->pow2_y) {
         // generic engine: two adjacent columns per block when they fit, so that global accesses are 32-byte sectors
         const int cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;
@@ -1391,11 +1418,22 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_r2c<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_r2c<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_c2r<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_c2r<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<false, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_backward<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_backward<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
         }
         if (cols_max > SMEM_DEFAULT_LIMIT) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
         }
     }
     if (tile_bin_smem_bytes<1>() > SMEM_DEFAULT_LIMIT) {
@@ -1516,6 +1554,8 @@ static int create_impl(qpic_ctx * c) {
         const char * e4 = getenv("QPIC_PREDICT_DEPOSIT");
         c->predict_deposit_mode = (e4 && (e4[0] == '0' || e4[0] == '1')) ? e4[0] - '0' : -1;
         c->predict_deposit = false;
+        const char * e5 = getenv("QPIC_FUSE_GAMMA");
+        c->fuse_gamma = !(e5 && e5[0] == '0');
         const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
         c->track_gamma_px = e3 && e3[0] == '1';
         const char * e2 = getenv("QPIC_JYJZ_CELL");
@@ -1583,7 +1623,9 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_tile_list_deposit);
         QPIC_PRELOAD(k_tile_stay_deposit);
         QPIC_PRELOAD(k_tile_cell_deposit);
-        QPIC_PRELOAD(k_particles_predict_dep);
+        QPIC_PRELOAD(k_particles_predict_dep<false>);
+        QPIC_PRELOAD(k_particles_predict_dep<true>);
+        QPIC_PRELOAD((k_particles_predict<true, true>));
         QPIC_PRELOAD(k_tile_assemble);
         QPIC_PRELOAD(k_particles_predict<true>);
         QPIC_PRELOAD(k_particles_gamma);
@@ -1599,7 +1641,12 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_init_a_sqr);
         QPIC_PRELOAD(k_p2_rows_r2c<true>);
         QPIC_PRELOAD(k_p2_rows_c2r<true>);
-        QPIC_PRELOAD(k_p2_cols_solve);
+        QPIC_PRELOAD(k_p2_cols_solve<false>);
+        QPIC_PRELOAD(k_p2_cols_solve<true>);
+        QPIC_PRELOAD((k_p2_rows_r2c<true, true>));
+        QPIC_PRELOAD((k_p2_rows_c2r<true, true>));
+        QPIC_PRELOAD((k_p2_rows_b_forward<true, false, true>));
+        QPIC_PRELOAD((k_p2_rows_b_backward<true, true>));
         QPIC_PRELOAD((k_p2_rows_b_forward<true, false>));
         QPIC_PRELOAD(k_p2_rows_b_backward<true>);
 #undef QPIC_PRELOAD
@@ -2023,7 +2070,7 @@ int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inou
     {
         const qpic_ctx::FftLaunch & R = c->rows_cplx;
         if (c->pow2_z) {
-            QPIC_LAUNCH(k_p2_rows_c2c, R.blocks, R.threads, R.smem, c->stream, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny);
+            QPIC_LAUNCH((R.wide ? k_p2_rows_c2c<true> : k_p2_rows_c2c<false>), R.blocks, R.threads, R.smem, c->stream, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny);
         } else {
             QPIC_LAUNCH(k_fft_rows_c2c<false>, R.blocks, R.threads, R.smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny, nz, R.spb);
         }

@@ -28,7 +28,7 @@ __host__ __device__ __forceinline__ int p2_pad_len(int n) { return n + (n >> 3) 
 
 // one transform of the sequence whose exchange buffers are xa / xb (p2_pad_len(n) points each, element i at [p2_pad(i) * stride]:
 // stride > 1 interleaves the sequences of a block, see p2_lane_cols); v[e] = point t + (n/8) e
-template <bool INV>
+template <bool INV, bool SINGLE = false>
 __device__ __forceinline__ void fft_pow2_regs(double2 (&v)[8], double2 * xa, double2 * xb, int t, int log2n, const double2 * __restrict__ tw, int stride = 1) {
     const int le8 = log2n - 3;
     int log2s = 0;
@@ -59,6 +59,9 @@ __device__ __forceinline__ void fft_pow2_regs(double2 (&v)[8], double2 * xa, dou
         const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
         const double2 w7 = cmul(w4, w3);
         double2 * y = flip ? xb : xa;
+        // SINGLE: one buffer instead of two alternating ones (xa == xb, the WIDE kernels: half the shared memory, so that more sequences
+        // fit a block on the long axes): every thread must have finished reading the previous exchange before it is overwritten
+        if (SINGLE && log2s > 0) __syncthreads();
         const int base = q + ((8 * p) << log2s);
         y[p2_pad(base) * stride] = v[0];
         y[p2_pad(base + (1 << log2s)) * stride] = cmul(v[1], w1);
@@ -105,11 +108,19 @@ __device__ __forceinline__ double2 * spec_at(const SpecMap & m, int j, int k) {
 }
 
 // thread layout shared by all kernels below: blockDim.x = spb * n/8; sequence b = threadIdx.x / (n/8), lane t
+// Every kernel below exists in two builds (last template argument WIDE):
+//   narrow  <= 512 threads per block (no register pressure: the 512-point axes of config #2 run 128-thread blocks), two alternating exchange buffers;
+//   wide    <= 896 threads = 7 sequences of a 1024-point axis in one block (1024 sequences on 148 SMs = one wave of 147 blocks) at 72 registers
+//           (a few spilled words) with ONE exchange buffer per sequence (P2_SINGLE).  Chosen by size_fft_launch where it saves a wave.
+constexpr int P2_WIDE_THREADS = 896, P2_NARROW_THREADS = 512;
+#define P2_BOUNDS __launch_bounds__(WIDE ? P2_WIDE_THREADS : P2_NARROW_THREADS)
 struct Pow2Lane {
     int b, t, e8;
     double2 *xa, *xb;
 };
 
+// SINGLE: one exchange buffer per sequence (see fft_pow2_regs)
+template <bool SINGLE = false>
 __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
     Pow2Lane L;
     const int le8 = log2n - 3;
@@ -117,8 +128,13 @@ __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
     L.e8 = 1 << le8;
     L.b = threadIdx.x >> le8;
     L.t = threadIdx.x & (L.e8 - 1);
-    L.xa = sm + (size_t)L.b * 2 * plen;
-    L.xb = L.xa + plen;
+    if (SINGLE) {
+        L.xa = sm + (size_t)L.b * plen;
+        L.xb = L.xa;
+    } else {
+        L.xa = sm + (size_t)L.b * 2 * plen;
+        L.xb = L.xa + plen;
+    }
     return L;
 }
 
@@ -126,12 +142,12 @@ __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
 
 // forward rows, two real rows per sequence -> half spectra spec[ny][nzh]
 // rows [row0, row0 + ny) of src (a full-size array)
-template <bool DIST>
-__global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, SpecMap spec, int ny,
+template <bool DIST, bool WIDE = false>
+__global__ void P2_BOUNDS k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, SpecMap spec, int ny,
                               int row0) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_r2c);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane(sm, log2n);
+    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
     const int nz = 1 << log2n, nzh = nz / 2 + 1;
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
     double2 v[8];
@@ -141,7 +157,7 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
         v[e] = make_double2(j0 < ny ? src[(size_t)(row0 + j0) * nz + k] : 0.0, j1 < ny ? src[(size_t)(row0 + j1) * nz + k] : 0.0);
     }
     if (cancelled(ctl)) return;  // tested after the loads are in flight (uniform over the block)
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     // the split needs Z_k and Z_{n-k}: one more exchange.  The last exchange of the transform used the other buffer
     // (or none at all), so this buffer is free once every thread has left the transform's final read.
@@ -170,13 +186,13 @@ __global__ void k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __rest
 // The column kernel's last block reduces these sums with a fixed-order tree and leaves the mean in *border_mean.
 // `ny` rows starting at global row `row0` of a field with ny_total rows.  The border mean is assembled from the per-rank
 // partial sums the column kernels left in partials[rank][0..2] (one rank on a single GPU), in rank order.
-template <bool DIST>
-__global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, SpecMap spec, double * __restrict__ dst, int ny, int row0,
+template <bool DIST, bool WIDE = false>
+__global__ void P2_BOUNDS k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, SpecMap spec, double * __restrict__ dst, int ny, int row0,
                               int ny_total, double inv_scale, int fix, const double * __restrict__ partials, double floor_value,
                               const double2 * __restrict__ red_row0, const double2 * __restrict__ red_colsum) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2r);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane(sm, log2n);
+    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
     const int nz = 1 << log2n;
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
     // loads now, arithmetic after the transform (the divisions then hide behind the spectrum loads)
@@ -247,7 +263,7 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
         pc = red_colsum[0].x;
     }
     if (cancelled(ctl)) return;
-    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<true, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     double mean = 0.0;
     if (fix) {
@@ -273,7 +289,8 @@ __global__ void k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __rest
 
 // ------------------------------------------------------------------------------------------------ columns + symbol
 // one column per sequence; inv_symbol is [ncols][ny] (column-major for this kernel), entry (k=0, j=0) = 0
-__global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
+template <bool WIDE = false>
+__global__ void P2_BOUNDS k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
                                 const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum,
                                 int * __restrict__ ticket, SpecMap partials, int my_rank, int col0, int nz) {
     QPIC_KERNEL_BEGIN(colsum ? KID_k_p2_cols_solve : KID_COUNT + 16);
@@ -287,7 +304,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
     L.b = threadIdx.x % spb;
     L.t = threadIdx.x / spb;
     L.xa = sm + L.b;
-    L.xb = L.xa + (size_t)p2_pad_len(1 << log2n) * spb;
+    L.xb = WIDE ? L.xa : L.xa + (size_t)p2_pad_len(1 << log2n) * spb;
     const int k = blockIdx.x * spb + L.b;
     const bool live = k < ncols;
     const int ny = 1 << log2n;
@@ -299,7 +316,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 #pragma unroll
     for (int e = 0; e < 8; e++) rinv[e] = live ? inv_symbol[(size_t)k * ny + L.t + e * L.e8] : 0.0;
     if (cancelled(ctl)) return;
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twy, spb);
+    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twy, spb);
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) {
@@ -313,7 +330,7 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
     if (colsum && live && L.t == 0) row0[k] = v[0];
     // the forward transform's last exchange buffer may still be read by slower threads of this sequence
     __syncthreads();
-    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twy, spb);
+    fft_pow2_regs<true, WIDE>(v, L.xa, L.xb, L.t, log2n, twy, spb);
     QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll
@@ -379,14 +396,14 @@ __global__ void k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __re
 
 // see k_fft_rows_b_forward (qpic_fft.cuh) for the source terms (src/System_3d.cpp:489-495, :530-536, :555-564 incl. :563)
 // PRE: the sources were already formed by the jy/jz deposit (TileJob::b_src) and are simply loaded
-template <bool DIST, bool PRE>
-__global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
+template <bool DIST, bool PRE, bool WIDE = false>
+__global__ void P2_BOUNDS k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
                                     const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                     const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
                                     const double2 * __restrict__ b_src, SpecMap spec, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_forward);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane(sm, log2n);
+    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
     const int nz = g.nz, ny = g.ny;
     const int jl = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const int j = row0 + jl;
@@ -411,7 +428,7 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
         }
     }
     if (cancelled(ctl)) return;
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll
@@ -420,13 +437,13 @@ __global__ void k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * 
 }
 
 // by(i) = re/ny/nz, bz(i) = im/ny/nz and the stop test (src/System_3d.cpp:541-552, :569-580)
-template <bool DIST>
-__global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, SpecMap spec, double * __restrict__ by,
+template <bool DIST, bool WIDE = false>
+__global__ void P2_BOUNDS k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, SpecMap spec, double * __restrict__ by,
                                      double * __restrict__ bz, double threshold, int iteration, double inv_scale, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_backward);
     // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane(sm, log2n);
+    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
     const int nz = g.nz, ny = g.ny;
     const int jl = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const int j = row0 + jl;
@@ -437,7 +454,7 @@ __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __res
     const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
     const int tag = ctl->stop_tag;
     if ((tag != 0 && tag != my_tag) || ctl->fast_fail) return;
-    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<true, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     if (!live) return;
     bool bad = false;
@@ -455,11 +472,12 @@ __global__ void k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __res
 }
 
 // plain complex rows (exposed Helmholtz-pair building block)
-__global__ void k_p2_rows_c2c(int log2n, const double2 * __restrict__ twz, const double * __restrict__ re, const double * __restrict__ im,
+template <bool WIDE = false>
+__global__ void P2_BOUNDS k_p2_rows_c2c(int log2n, const double2 * __restrict__ twz, const double * __restrict__ re, const double * __restrict__ im,
                               double2 * __restrict__ spec, int ny) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2c);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane(sm, log2n);
+    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
     const int nz = 1 << log2n;
     const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const bool live = j < ny;
@@ -469,7 +487,7 @@ __global__ void k_p2_rows_c2c(int log2n, const double2 * __restrict__ twz, const
         const size_t gidx = (size_t)j * nz + L.t + e * L.e8;
         v[e] = live ? make_double2(re[gidx], im[gidx]) : make_double2(0.0, 0.0);
     }
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) spec[(size_t)j * nz + L.t + e * L.e8] = v[e];

@@ -805,6 +805,49 @@ __global__ void k_particles_gamma(const Ctl * ctl, Geom g, Particles P, const in
     }
 }
 
+// What a predictor pass needs per particle besides py, pz and the B gathers: the slice invariants and the previous iteration's gamma.
+// FIRST (iteration 0 of a slice): k_particles_gamma's work is done here instead -- psi, a_sqr and their derivatives are gathered at the particle,
+// the initial gamma (src/System_3d.cpp:368-378) is formed, and predict_store_invariants leaves the invariants for iterations 1 .. M-1.  That saves
+// the separate pass over the slot arrays (100 bytes per particle, one launch) that only produced inputs of this kernel.  Later iterations stream
+// the stored values (read once per pass: evict-first).
+struct PredictIn {
+    double q, gamma, a_particle, t1y, t1z, dpy, dpz;
+};
+
+template <bool FIRST>
+__device__ __forceinline__ PredictIn predict_inputs(const Ctl * ctl, const Geom & g, const Particles & P, int s, int jc, int kc, double fy, double fz, double py, double pz,
+                                                    const double * __restrict__ a_sqr3, const double * __restrict__ psi) {
+    PredictIn in;
+    if (FIRST) {
+        const double * a_sqr = a_sqr3 + (size_t)ctl->slice * g.n2;
+        in.a_particle = gather_node(a_sqr, g.ny, g.nz, jc, kc, fy, fz);
+        const double psi_particle = gather_node(psi, g.ny, g.nz, jc, kc, fy, fz);
+        in.q = 1 + psi_particle;
+        const double rq = 1.0 / in.q;  // (see k_particles_gamma)
+        in.gamma = 0.5 * (1 + py * py + pz * pz + in.a_particle + in.q * in.q) * rq;
+        in.t1y = g.dx * 0.5 * gather_yder(a_sqr, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz) * rq;
+        in.t1z = g.dx * 0.5 * gather_zder(a_sqr, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz) * rq;
+        in.dpy = gather_yder(psi, g.ny, g.nz, g.inv_dy, jc, kc, fy, fz);
+        in.dpz = gather_zder(psi, g.ny, g.nz, g.inv_dz, jc, kc, fy, fz);
+    } else {
+        const double2 qa = ld_stream2(P.qa + s), t1 = ld_stream2(P.t1 + s), dp = ld_stream2(P.dp + s);
+        in.q = qa.x;
+        in.a_particle = qa.y;
+        in.gamma = P.gam[s];
+        in.t1y = t1.x, in.t1z = t1.y, in.dpy = dp.x, in.dpz = dp.y;
+    }
+    return in;
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void predict_store_invariants(const Particles & P, int s, const PredictIn & in) {
+    if (FIRST) {
+        P.qa[s] = make_double2(in.q, in.a_particle);
+        P.t1[s] = make_double2(in.t1y, in.t1z);
+        P.dp[s] = make_double2(in.dpy, in.dpz);
+    }
+}
+
 // ---- far movers: half steps beyond the +-1 cell window of the tile deposits (round 2)
 // The tile kernels find the particles that land in a target cell by looking at the cells around it, which is only complete while every half step
 // stays within one cell.  A particle that goes further (bubble sheath, trajectory crossing) used to raise Ctl::fast_fail: the host discarded the slice
@@ -852,9 +895,9 @@ __device__ __forceinline__ int cell_offset(int jm, int jc, int n) {
 #ifndef QPIC_PREDICT_MINB
 #define QPIC_PREDICT_MINB 1
 #endif
-template <bool FAST>
+template <bool FAST, bool FIRST = false>
 __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz,
-                                    int * __restrict__ count, int store_px, FarMovers far) {
+                                    int * __restrict__ count, int store_px, FarMovers far, const double * __restrict__ a_sqr3, const double * __restrict__ psi) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     // The control block is tested only before the first store: its load then overlaps the streaming loads instead of
     // heading the dependent chain (every slot < P.np is readable whatever the flags say).
@@ -865,12 +908,13 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     const double2 fyz = P.fyz_b[s];
     const double fy = fyz.x, fz = fyz.y;
     // issue the independent streaming loads (16 bytes each) before the dependent field gathers
-    const double2 qa = ld_stream2(P.qa + s), pyz = ld_stream2(P.pyz_s + s), t1 = ld_stream2(P.t1 + s), dp = ld_stream2(P.dp + s);
-    const double q = qa.x, gamma = P.gam[s];
+    const double2 pyz = ld_stream2(P.pyz_s + s);
     const double py = pyz.x, pz = pyz.y;
-    const double t1y = t1.x, t1z = t1.y, dpy = dp.x, dpz = dp.y;
+    const PredictIn in = predict_inputs<FIRST>(ctl, g, P, s, jc, kc, fy, fz, py, pz, a_sqr3, psi);
+    const double q = in.q, gamma = in.gamma, a_particle = in.a_particle;
+    const double t1y = in.t1y, t1z = in.t1z, dpy = in.dpy, dpz = in.dpz;
     const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
-    const double a_particle = qa.y, nw = P.nw_s[s];
+    const double nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -880,6 +924,7 @@ __global__ void __launch_bounds__(256, QPIC_PREDICT_MINB) k_particles_predict(Ct
     const double bz_particle = gather4(bz, g.nz, js, wrap_inc(js, g.ny), kc, wrap_inc(kc, g.nz), fys, fz);
     if (cancelled(ctl) || s >= live_count(ctl, P.np)) return;
     QPIC_KERNEL_TAIL();
+    predict_store_invariants<FIRST>(P, s, in);
     const double rq = 1.0 / q;  // (see k_particles_gamma)
     double pyn = py - t1y;
     pyn += g.dx * gamma * dpy * rq;
@@ -1798,8 +1843,9 @@ struct StayOut {
     int far_row_lo, far_row_n;  // slabs: legal target rows of a far mover, see FarMovers (0 rows: all)
 };
 
+template <bool FIRST = false>
 __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
-                                        StayOut so) {
+                                        StayOut so, const double * __restrict__ a_sqr3, const double * __restrict__ psi) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     const int s_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -1815,12 +1861,13 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double2 fyz = P.fyz_b[s];
     const double fy = fyz.x, fz = fyz.y;
-    const double2 qa = ld_stream2(P.qa + s), pyz = ld_stream2(P.pyz_s + s), t1 = ld_stream2(P.t1 + s), dp = ld_stream2(P.dp + s);
-    const double q = qa.x, gamma = P.gam[s];
+    const double2 pyz = ld_stream2(P.pyz_s + s);
     const double py = pyz.x, pz = pyz.y;
-    const double t1y = t1.x, t1z = t1.y, dpy = dp.x, dpz = dp.y;
+    const PredictIn in = predict_inputs<FIRST>(ctl, g, P, s, jc, kc, fy, fz, py, pz, a_sqr3, psi);
+    const double q = in.q, gamma = in.gamma, a_particle = in.a_particle;
+    const double t1y = in.t1y, t1z = in.t1z, dpy = in.dpy, dpz = in.dpz;
     const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
-    const double a_particle = qa.y, nw = P.nw_s[s];
+    const double nw = P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -1856,6 +1903,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const int code = bad ? pack_offset(0, 0, 0.0, 0.0, kc)
                          : (farm ? (FAR_CODE | ((f1 >= 0.5) ? 64 : 0) | ((f2 >= 0.5) ? 128 : 0) | ((kc & 3) << 8)) : pack_offset(oy, oz, f1, f2, kc));
     if (have) {
+        predict_store_invariants<FIRST>(P, s, in);
         P.pyzn[s] = make_double2(pyn, pzn);
         P.gam[s] = gamma_c;
         if (store_px) P.pxs[s] = px_c;
