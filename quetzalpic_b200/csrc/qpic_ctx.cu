@@ -157,6 +157,7 @@ struct qpic_ctx {
     StayOut stay = {};
     int * stay_cnt[2] = {nullptr, nullptr};
     int cur_it = 0;
+    bool fold_jx = true;                           // predictor-side deposit: the jx deposit at (y, z) rides along (QPIC_FOLD_JX=0: separate tile kernel)
     bool fuse_gamma = true;                        // the first predictor pass of a slice does k_particles_gamma's work (QPIC_FUSE_GAMMA=0: separate kernel)
     bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
@@ -697,6 +698,8 @@ FarMovers far_view(const qpic_ctx * c, bool fast) {
     return f;
 }
 bool predict_deposit_on(const qpic_ctx * c) { return c->predict_deposit && stayers_direct(c) && c->stay.corn != nullptr; }
+// ... and the jx deposit of the iteration with it (k_particles_predict_dep<., true> + k_tile_assemble<true>)
+bool fold_jx_on(const qpic_ctx * c) { return predict_deposit_on(c) && c->fold_jx && c->stay.xcorn != nullptr; }
 
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
@@ -712,7 +715,13 @@ int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
         // the predictor of this iteration left the stayers' corner sums and the mover lists (k_particles_predict_dep)
         StayOut so = c->stay;
         so.cnt = c->stay_cnt[c->cur_it & 1];
-        QPIC_LAUNCH(k_tile_assemble, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j, so, c->stay_cnt[(c->cur_it + 1) & 1]);
+        if (fold_jx_on(c)) {
+            j.nout = 2;
+            j.o[1] = tile_output(c->P.vjx, 1.0, 2, c->f3[QPIC_F3_JX_BUNCH], c->f2[QPIC_F2_JX], 0);
+            QPIC_LAUNCH(k_tile_assemble<true>, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j, so, c->stay_cnt[(c->cur_it + 1) & 1]);
+        } else {
+            QPIC_LAUNCH(k_tile_assemble<false>, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j, so, c->stay_cnt[(c->cur_it + 1) & 1]);
+        }
         return check_launch(c, "k_tile_deposit_charge_mid");
     }
     if (stayers_direct(c)) {
@@ -882,7 +891,7 @@ MigrateView migrate_view(qpic_ctx * c) {
     m.cap = v.mig_cap;
     // box 0 of a rank collects what its upper neighbour sends down, box 1 what its lower neighbour sends up
     m.out[0] = reinterpret_cast<double *>(v.base[v.below] + v.lay.inbox);
-    m.out[1] = reinterpret_cast<double *>(v.base[v.above] + v.lay.inbox) + (size_t)5 * v.mig_cap;
+    m.out[1] = reinterpret_cast<double *>(v.base[v.above] + v.lay.inbox) + (size_t)6 * v.mig_cap;
     m.out_count = c->dist.out_count;
     m.error = &c->ctl->dist_error;
     return m;
@@ -904,6 +913,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             StayOut so = c->stay;
             so.cnt = c->stay_cnt[it & 1];
             auto predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true> : k_particles_predict_dep<false>;
+            if (fold_jx_on(c)) predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true, true> : k_particles_predict_dep<false, true>;
             QPIC_LAUNCH(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so,
                         (const double *)c->f3[QPIC_F3_ASQR], (const double *)c->f2[QPIC_F2_PSI]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
@@ -917,8 +927,12 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         // branch B: the jx deposit at (y,z) needs only the corrector values the predictor kernel has just stored.  (Forking it after
         // the psi_middle source deposit instead, so that it overlaps the three transform kernels of the solve rather than the other
         // tile kernel, was measured: 0.696 -> 0.740 ms/slice -- a tile deposit next to the few-warp transform kernels delays them.)
-        QPIC_TRY(stream_depend(c, sa, sb));
-        QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
+        // (With the predictor-side deposit the jx sums were formed by the predictor and k_tile_assemble writes jx: no branch B.)
+        const bool jx_folded = np > 0 && fast && fold_jx_on(c);
+        if (!jx_folded) {
+            QPIC_TRY(stream_depend(c, sa, sb));
+            QPIC_TRY(enqueue_base_currents(c, sb, fast, true, false, false));
+        }
         // branch A: psi_middle, then jy_next / jz_next
         if (!fast) QPIC_TRY(enqueue_sort(c, sa, c->ctl, c->P.cell_m, c->start_m, c->perm_m));
         if (c->dist.on) {
@@ -932,7 +946,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             QPIC_TRY(enqueue_potential(c, sa, fast, 1, c->f2[QPIC_F2_PSI_MIDDLE]));
         }
         if (fast) {
-            if (c->jyjz_lists && c->b_src) QPIC_TRY(stream_depend(c, sb, sa));  // the deposit's epilogue reads jx (branch B)
+            if (c->jyjz_lists && c->b_src && !jx_folded) QPIC_TRY(stream_depend(c, sb, sa));  // the deposit's epilogue reads jx (branch B)
             QPIC_TRY(enqueue_tile_jy_jz(c, sa));
             QPIC_TRY(dist_reduce(c, sa, halo_job({c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT]}, {RB_JY, RB_JZ})));
         } else {
@@ -944,7 +958,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
                              c->f2[QPIC_F2_JZ_NEXT]);
             QPIC_TRY(check_launch(c, "k_deposit_jy_jz"));
         }
-        QPIC_TRY(stream_depend(c, sb, sa));
+        if (!jx_folded) QPIC_TRY(stream_depend(c, sb, sa));
         // By + i Bz in one complex solve
 #ifndef QPIC_EMU
         if (c->fused.on) {
@@ -1049,6 +1063,7 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     QPIC_TRY(dev_alloc(c, &P.cell_b, count));
     QPIC_TRY(dev_alloc(c, &P.cell_m, count));
     QPIC_TRY(dev_alloc(c, &P.off_m, count));
+    if (c->dist.on) QPIC_TRY(dev_alloc(c, &P.akey, 2 * (size_t)c->dist.v.mig_cap));  // sort keys of a slice's arrivals
     QPIC_TRY(dev_alloc(c, &c->perm_b, count));
     QPIC_TRY(dev_alloc(c, &c->perm_m, count));
     QPIC_TRY(dev_alloc(c, &c->tmp, count));
@@ -1072,9 +1087,14 @@ int alloc_particles(qpic_ctx * c, size_t count) {
             QPIC_TRY(dev_alloc(c, &c->stay_cnt[0], n2));
             QPIC_TRY(dev_alloc(c, &c->stay_cnt[1], n2));
             QPIC_TRY(dev_alloc(c, &c->stay.lst, (size_t)BIN_K * n2));
+            if (c->fold_jx) QPIC_TRY(dev_alloc(c, &c->stay.xcorn, 4 * n2));
         }
         QPIC_TRY(dev_alloc(c, &c->stay.lead, 4 * nwarps));
         QPIC_TRY(dev_alloc(c, &c->stay.trail, 4 * nwarps));
+        if (c->fold_jx) {
+            QPIC_TRY(dev_alloc(c, &c->stay.xlead, 4 * nwarps));
+            QPIC_TRY(dev_alloc(c, &c->stay.xtrail, 4 * nwarps));
+        }
         c->stay.sign = -1.0;
         c->stay.allow_far = c->far_movers ? 1 : 0;
         far_rows(c, &c->stay.far_row_lo, &c->stay.far_row_n);
@@ -1518,13 +1538,13 @@ static int create_impl(qpic_ctx * c) {
             return at;
         };
         L.flags = take(sizeof(long long) * DIST_MAX);
-        L.stops = take(sizeof(int) * DIST_MAX);
+        L.stops = take(sizeof(int) * 2 * DIST_MAX);
         L.partials = take(sizeof(double) * 4 * DIST_MAX);
         L.inbox_count = take(sizeof(int) * 2);
         const int cpr_max = D.cpr_half > D.cpr_full ? D.cpr_half : D.cpr_full;
         L.cols = take(sizeof(double2) * (size_t)g.ny * cpr_max);
         L.rbuf = take(sizeof(double) * RB_COUNT * 2 * DIST_HALO * g.nz);
-        L.inbox = take(sizeof(double) * 2 * 5 * (size_t)v.mig_cap);
+        L.inbox = take(sizeof(double) * 2 * 6 * (size_t)v.mig_cap);
         for (int f = 0; f < DF_COUNT; f++) L.field[f] = take(sizeof(double) * n2);
         L.total = off;
         QPIC_TRY(dev_alloc(c, &D.region, L.total));
@@ -1554,6 +1574,8 @@ static int create_impl(qpic_ctx * c) {
         const char * e4 = getenv("QPIC_PREDICT_DEPOSIT");
         c->predict_deposit_mode = (e4 && (e4[0] == '0' || e4[0] == '1')) ? e4[0] - '0' : -1;
         c->predict_deposit = false;
+        const char * e6 = getenv("QPIC_FOLD_JX");
+        c->fold_jx = !(e6 && e6[0] == '0');
         const char * e5 = getenv("QPIC_FUSE_GAMMA");
         c->fuse_gamma = !(e5 && e5[0] == '0');
         const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
@@ -1625,8 +1647,11 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_tile_cell_deposit);
         QPIC_PRELOAD(k_particles_predict_dep<false>);
         QPIC_PRELOAD(k_particles_predict_dep<true>);
+        QPIC_PRELOAD((k_particles_predict_dep<false, true>));
+        QPIC_PRELOAD((k_particles_predict_dep<true, true>));
+        QPIC_PRELOAD(k_tile_assemble<false>);
+        QPIC_PRELOAD(k_tile_assemble<true>);
         QPIC_PRELOAD((k_particles_predict<true, true>));
-        QPIC_PRELOAD(k_tile_assemble);
         QPIC_PRELOAD(k_particles_predict<true>);
         QPIC_PRELOAD(k_particles_gamma);
         QPIC_PRELOAD(k_particles_advance);
@@ -1795,7 +1820,8 @@ int qpic_begin(qpic_ctx * c) {
     init.dist_error = 0;
     init.np1 = c->dist.on ? c->dist.live0 + 1 : 0;
     init.np_p1 = init.np1;
-    init.pad[0] = init.pad[1] = 0;
+    init.mig_base1 = 0;
+    init.pad = 0;
     if (c->dist.on && !c->dist.attached) return fail(c, QPIC_ERR_STATE, "distributed context: attach the peers' exchange regions first (qpic_dist_attach_*)");
     *c->ctl_host = init;
     QPIC_CUDA(c, cudaMemcpyAsync(c->ctl, c->ctl_host, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream));

@@ -35,12 +35,12 @@ enum DistField { DF_PSI = 0, DF_PSI_MIDDLE, DF_BY, DF_BZ, DF_JX, DF_COUNT };
 
 struct DistLayout {  // byte offsets inside an exchange region (identical on all ranks)
     size_t flags;        // long long[DIST_MAX]: epoch of the last barrier each rank has entered
-    size_t stops;        // int[DIST_MAX]: Ctl::stop_tag of each rank as of its last barrier
+    size_t stops;        // int[2][DIST_MAX]: Ctl::stop_tag of each rank as of its last barrier, double buffered by the parity of the epoch
     size_t partials;     // double[DIST_MAX][4]: border-sum partials of the fused potential fix-up
     size_t inbox_count;  // int[2]
     size_t cols;         // double2[ny * cpr_max]: this rank's columns of the spectrum
     size_t rbuf;         // double[RB_COUNT][2][DIST_HALO * nz]
-    size_t inbox;        // double[2][5][mig_cap]
+    size_t inbox;        // double[2][6][mig_cap]
     size_t field[DF_COUNT];  // double[ny * nz]
     size_t total;
 };
@@ -111,7 +111,10 @@ __global__ void k_xchg_barrier(DistView d, Ctl * ctl) {
     }
     __syncthreads();
     const int q = threadIdx.x;
-    if (q < d.world) reinterpret_cast<int *>(dist_base(d, q) + d.lay.stops)[d.rank] = ctl->stop_tag;
+    // (slot of this epoch's parity: a fast peer that is already in barrier ep + 1 writes the other slot, and it cannot reach ep + 2 before this
+    // rank has arrived at ep + 1, i.e. has read its tag of epoch ep)
+    const int par = (int)(ep & 1) * DIST_MAX;
+    if (q < d.world) reinterpret_cast<int *>(dist_base(d, q) + d.lay.stops)[par + d.rank] = ctl->stop_tag;
     __threadfence_system();
     if (q < d.world) {
         st_release_sys(reinterpret_cast<long long *>(dist_base(d, q) + d.lay.flags) + d.rank, ep);
@@ -124,7 +127,7 @@ __global__ void k_xchg_barrier(DistView d, Ctl * ctl) {
             }
         }
         // rank q's tag was stored before its flag (release) and is read after it (acquire)
-        const int peer_tag = reinterpret_cast<const int *>(dist_base(d, d.rank) + d.lay.stops)[q];
+        const int peer_tag = reinterpret_cast<const int *>(dist_base(d, d.rank) + d.lay.stops)[par + q];
         if (peer_tag != 0) atomicCAS(&ctl->stop_tag, 0, peer_tag);
     }
     __threadfence_system();
@@ -233,13 +236,15 @@ __global__ void k_migrate_unpack(Ctl * ctl, Geom g, DistView d, Particles P, int
             atomicExch(d.error, 3);
             continue;
         }
-        const double * b = box + (size_t)side * 5 * d.mig_cap;
+        const double * b = box + (size_t)side * 6 * d.mig_cap;
         const double y = b[0 * (size_t)d.mig_cap + i], z = b[1 * (size_t)d.mig_cap + i];
         P.y[p] = y;
         P.z[p] = z;
         P.py[p] = b[2 * (size_t)d.mig_cap + i];
         P.pz[p] = b[3 * (size_t)d.mig_cap + i];
         P.nw[p] = b[4 * (size_t)d.mig_cap + i];
+        // canonical order of the arrivals inside a cell: (side, slot on the sending rank), see sort_key; slots < 2^30
+        P.akey[t] = (side << 30) | (int)b[5 * (size_t)d.mig_cap + i];
         P.gamma[p] = 0.0;
         P.px[p] = 0.0;
         int jn, kn;
@@ -256,6 +261,7 @@ __global__ void k_migrate_unpack(Ctl * ctl, Geom g, DistView d, Particles P, int
         int total = base + n0 + n1;
         if (total > capacity) total = capacity;
         ctl->np_p1 = total + 1;
+        ctl->mig_base1 = base + 1;
     }
 }
 

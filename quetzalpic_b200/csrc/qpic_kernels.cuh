@@ -187,7 +187,8 @@ struct Ctl {
     // the static count the kernel was launched with -- what a zero-initialised control block of a single-GPU run gives):
     int np1;        // live slots of this slice
     int np_p1;      // entries of the particle-id arrays (live + emigrated + just arrived) the cell sort has to look at
-    int pad[2];
+    int mig_base1;  // first entry of this slice's arrivals + 1 (k_migrate_unpack; 0: none), see sort_key
+    int pad;
 };
 
 __device__ __forceinline__ int live_count(const Ctl * ctl, int np_static) {
@@ -671,6 +672,7 @@ struct Particles {
     double *y, *z, *py, *pz, *nw;
     double *gamma, *px;             // src/containers.h:41-42 (kept for inspection / dumps)
     int * cell_p;                   // cell of (y,z)
+    int * akey;                     // slab-decomposed sweeps: sort keys of this slice's arrivals (see sort_key); NULL on a single GPU
     double *fy_p, *fz_p;            // fractional position inside it
     // ---- by slot
     int * cell_b;                   // copies of the above in slot order
@@ -734,6 +736,15 @@ __device__ __forceinline__ double slot_position(int exact, int jc, double f, dou
     return exact ? ((double)jc + f) * d : ld_stream(stored + s);
 }
 
+// Canonical order inside a cell = ascending sort key.  The key of an entry is its index in the particle-id arrays -- except for the particles
+// that arrived from a neighbouring GPU in this slice: k_migrate_unpack appends them in the order the senders' atomics resolved, so their key is
+// (side, slot they had on the sending rank) instead, after every resident: the sums of a slab-decomposed sweep are then bit-reproducible from
+// run to run like the single-GPU ones (by induction the senders' slot orders are).  akey == NULL (single GPU): the index itself.
+__device__ __forceinline__ long long sort_key(int x, int mig_base1, const int * __restrict__ akey) {
+    if (akey == nullptr || mig_base1 == 0 || x < mig_base1 - 1) return x;
+    return ((long long)1 << 32) + akey[x - (mig_base1 - 1)];
+}
+
 // After the cell sort of the slice-start positions the particle's slice inputs are copied from id order to slot order.  k_sort_rank and that
 // copy in one pass (the sort of the slice-start positions is always followed by the slot copies):
 // entry t of the bucket-filled list finds its canonical position (ascending particle id inside the cell) and copies its particle's slice
@@ -749,7 +760,13 @@ __global__ void k_rank_to_slots(const Ctl * ctl, Geom g, Particles P, int np, co
     // this particle's data: in flight while the bucket is ranked
     const double fy = P.fy_p[p], fz = P.fz_p[p], py = P.py[p], pz = P.pz[p], nw = P.nw[p];
     int rank = 0;
-    for (int u = b; u < e; u++) rank += (tmp[u] < p) ? 1 : 0;
+    if (P.akey == nullptr || ctl->mig_base1 == 0) {
+        for (int u = b; u < e; u++) rank += (tmp[u] < p) ? 1 : 0;
+    } else {
+        const int mb = ctl->mig_base1;
+        const long long kp = sort_key(p, mb, P.akey);
+        for (int u = b; u < e; u++) rank += (sort_key(tmp[u], mb, P.akey) < kp) ? 1 : 0;
+    }
     const int s = b + rank;
     perm[s] = p;
     if (s >= live_count(ctl, P.np)) return;  // (slab-decomposed sweeps: the bucket of emigrated entries lies beyond the live slots)
@@ -993,7 +1010,7 @@ __global__ void k_particles_currents_yz(const Ctl * ctl, Geom g, Particles P, co
 struct MigrateView {
     int enabled;
     int row0, ny_loc, cap;
-    double * out[2];   // peer inboxes: [0] of the rank below (its "from above" box), [1] of the rank above; SoA [5][cap]
+    double * out[2];   // peer inboxes: [0] of the rank below (its "from above" box), [1] of the rank above; SoA [6][cap] (y z py pz n + sender's slot)
     int * out_count;   // local int[2]
     int * error;
 };
@@ -1050,6 +1067,7 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
                 b[2 * (size_t)mig.cap + i] = py;
                 b[3 * (size_t)mig.cap + i] = pz;
                 b[4 * (size_t)mig.cap + i] = nw;
+                b[5 * (size_t)mig.cap + i] = (double)s;  // sort key of the arrival on the receiving rank (see sort_key)
             }
             cn = g.n2;  // the "emigrated" bucket
         }
@@ -1836,6 +1854,9 @@ struct StayOut {
     double * corn;   // [4][n2]: corner sums (c00, c10, c01, c11) of the stayers of cells whose run lies inside one warp
     double * lead;   // [nwarps][4]: run that continues from the previous warp (may also continue into the next one)
     double * trail;  // [nwarps][4]: run that starts in this warp and continues into the next one
+    // FOLD_JX: the jx deposit at (y, z) (src/System_3d.cpp:511-527) rides along -- every particle is a "stayer" of its slice-start cell there, the
+    // corrector's value n vx / (1 - vx) and the fractions are in the predictor's registers: same three arrays, sums of v (1-fy)(1-fz) ... v fy fz
+    double *xcorn, *xlead, *xtrail;
     int * cnt;       // movers per target cell (zero on entry)
     int * lst;       // [BIN_K][n2], unsorted
     double sign;     // -1: the psi source deposits -n (src/System_3d.cpp:349-353)
@@ -1843,7 +1864,7 @@ struct StayOut {
     int far_row_lo, far_row_n;  // slabs: legal target rows of a far mover, see FarMovers (0 rows: all)
 };
 
-template <bool FIRST = false>
+template <bool FIRST = false, bool FOLD_JX = false>
 __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
                                         StayOut so, const double * __restrict__ a_sqr3, const double * __restrict__ psi) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
@@ -1907,7 +1928,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
         P.pyzn[s] = make_double2(pyn, pzn);
         P.gam[s] = gamma_c;
         if (store_px) P.pxs[s] = px_c;
-        store_currents<false>(P, s, nw, gamma_c, px_c);
+        if (!FOLD_JX) store_currents<false>(P, s, nw, gamma_c, px_c);  // (FOLD_JX: no jx tile deposit reads the value)
         P.fyz_m[s] = make_double2(f1, f2);
         P.off_m[s] = code;
         if (bad) atomicExch(&ctl->fast_fail, 1);
@@ -1921,20 +1942,26 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
         else if (farm) atomicExch(&ctl->fast_fail, 1);
     }
     const double v = stay ? so.sign * nw : 0.0;
-    double c00 = v * (1 - f1) * (1 - f2), c10 = v * f1 * (1 - f2), c01 = v * (1 - f1) * f2, c11 = v * f1 * f2;
-    if (!stay) c00 = c10 = c01 = c11 = 0.0;  // (NaN positions of a blown-up run)
+    constexpr int NV = FOLD_JX ? 8 : 4;
+    double cs[NV];
+    cs[0] = v * (1 - f1) * (1 - f2), cs[1] = v * f1 * (1 - f2), cs[2] = v * (1 - f1) * f2, cs[3] = v * f1 * f2;
+    if (!stay) cs[0] = cs[1] = cs[2] = cs[3] = 0.0;  // (NaN positions of a blown-up run)
+    if (FOLD_JX) {
+        // store_currents' value, k_tile_deposit's products (at the slice-start fractions)
+        const double vx = px_c / gamma_c;
+        const double vj = have ? nw * vx / (1 - vx) : 0.0;
+        cs[4] = vj * (1 - fy) * (1 - fz), cs[5] = vj * fy * (1 - fz), cs[6] = vj * (1 - fy) * fz, cs[7] = vj * fy * fz;
+    }
     const int key = have ? c : -3 - lane;
     // keys are sorted, so once no lane finds its key d lanes below, none will at a larger distance: runs of 4-8 particles need 3 steps
     for (int d = 1; d < 32; d <<= 1) {
         const int k2 = __shfl_up_sync(0xffffffffu, key, d);
         if (!__any_sync(0xffffffffu, lane >= d && k2 == key)) break;
-        const double t00 = __shfl_up_sync(0xffffffffu, c00, d), t10 = __shfl_up_sync(0xffffffffu, c10, d);
-        const double t01 = __shfl_up_sync(0xffffffffu, c01, d), t11 = __shfl_up_sync(0xffffffffu, c11, d);
-        if (lane >= d && k2 == key) {
-            c00 += t00;
-            c10 += t10;
-            c01 += t01;
-            c11 += t11;
+        const bool take = lane >= d && k2 == key;
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const double t = __shfl_up_sync(0xffffffffu, cs[i], d);
+            if (take) cs[i] += t;
         }
     }
     const int key_next = __shfl_down_sync(0xffffffffu, key, 1);
@@ -1944,24 +1971,38 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
         const bool into_after = lane == 31 && key == key_after;
         const int w = warp_base >> 5;
         if (from_before) {
-            so.lead[4 * w + 0] = c00, so.lead[4 * w + 1] = c10, so.lead[4 * w + 2] = c01, so.lead[4 * w + 3] = c11;
+#pragma unroll
+            for (int i = 0; i < 4; i++) so.lead[4 * w + i] = cs[i];
+            if (FOLD_JX) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) so.xlead[4 * w + i] = cs[4 + i];
+            }
         } else if (into_after) {
-            so.trail[4 * w + 0] = c00, so.trail[4 * w + 1] = c10, so.trail[4 * w + 2] = c01, so.trail[4 * w + 3] = c11;
+#pragma unroll
+            for (int i = 0; i < 4; i++) so.trail[4 * w + i] = cs[i];
+            if (FOLD_JX) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) so.xtrail[4 * w + i] = cs[4 + i];
+            }
         } else {
-            so.corn[0 * (size_t)g.n2 + c] = c00;
-            so.corn[1 * (size_t)g.n2 + c] = c10;
-            so.corn[2 * (size_t)g.n2 + c] = c01;
-            so.corn[3 * (size_t)g.n2 + c] = c11;
+#pragma unroll
+            for (int i = 0; i < 4; i++) so.corn[i * (size_t)g.n2 + c] = cs[i];
+            if (FOLD_JX) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) so.xcorn[i * (size_t)g.n2 + c] = cs[4 + i];
+            }
         }
     }
 }
 
 // nodes of the psi_middle source from what k_particles_predict_dep left; block = TILE_ACC x TILE_ACC target cells as in k_tile_deposit.
 // cnt_next: the mover counters of the next iteration's predictor (double buffered) are cleared by the cells' owner threads.
+// FOLD_JX: second output = jx at (y, z) from the predictor's jx sums (no movers there: a cell's sum is its corner sum or its chain of pieces)
+template <bool FOLD_JX = false>
 __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, StayOut so,
                                                               int * __restrict__ cnt_next) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 1);
-    __shared__ double acc[4 * TILE_CELLS];
+    __shared__ double acc[(FOLD_JX ? 8 : 4) * TILE_CELLS];
     const int ay = threadIdx.y, az = threadIdx.x;
     const int tcell = ay * TILE_ACC + az;
     const int jt = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
@@ -1975,6 +2016,16 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g,
                  k11 = so.corn[3 * (size_t)g.n2 + cell];
     const double * __restrict__ val = job.o[0].val;
     double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
+    double x00 = 0.0, x10 = 0.0, x01 = 0.0, x11 = 0.0;
+    if (FOLD_JX && s1 > s0) {
+        const int w0 = s0 >> 5, w1 = (s1 - 1) >> 5;
+        if (w0 == w1) {
+            x00 = so.xcorn[0 * (size_t)g.n2 + cell], x10 = so.xcorn[1 * (size_t)g.n2 + cell], x01 = so.xcorn[2 * (size_t)g.n2 + cell], x11 = so.xcorn[3 * (size_t)g.n2 + cell];
+        } else {
+            x00 = so.xtrail[4 * w0 + 0], x10 = so.xtrail[4 * w0 + 1], x01 = so.xtrail[4 * w0 + 2], x11 = so.xtrail[4 * w0 + 3];
+            for (int w = w0 + 1; w <= w1; w++) x00 += so.xlead[4 * w + 0], x10 += so.xlead[4 * w + 1], x01 += so.xlead[4 * w + 2], x11 += so.xlead[4 * w + 3];
+        }
+    }
     auto visit = [&](int s) {
         const double2 fm = P.fyz_m[s];
         const double fy = fm.x, fz = fm.y, v = so.sign * val[s];
@@ -2037,8 +2088,14 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g,
     acc[1 * TILE_CELLS + tcell] = c10;
     acc[2 * TILE_CELLS + tcell] = c01;
     acc[3 * TILE_CELLS + tcell] = c11;
+    if (FOLD_JX) {
+        acc[4 * TILE_CELLS + tcell] = x00;
+        acc[5 * TILE_CELLS + tcell] = x10;
+        acc[6 * TILE_CELLS + tcell] = x01;
+        acc[7 * TILE_CELLS + tcell] = x11;
+    }
     __syncthreads();
-    tile_store_nodes<1>(ctl, g, job, acc, ay, az, jt, kt, ion);
+    tile_store_nodes<FOLD_JX ? 2 : 1>(ctl, g, job, acc, ay, az, jt, kt, ion);
 }
 
 // ------------------------------------------------------------------------------------------------ jy / jz, one visit per particle
