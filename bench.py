@@ -57,7 +57,7 @@ SURVEY_BYTES = {
     "k_tile_deposit_charge": (1, 3), "k_fft_rows_r2c": (5, 0), "k_fft_cols_solve": (2, 0), "k_fft_rows_c2r": (4, 0),
     "k_fft_solve_real": (11, 0), "k_fft_solve_b": (18, 0),
     "k_particles_gamma": (2, 7),            # gathers 2; reads y z py pz n, writes gamma px
-    "k_tile_deposit_rho_chi": (5, 0),       # rho / jx / chi targets of the once-per-slice deposit (its particle reads are in the 7 above)
+    "k_tile_deposit_rho_chi": (5, 0), "k_tile_fold_rho_chi": (5, 0),       # rho / jx / chi targets of the once-per-slice deposit (its particle reads are in the 7 above)
     "k_particles_advance": (1, 8), "k_end_of_slice": (9, 0),
     # per B iteration: predictor 10 + corrector share 6 of the "11" (the other 5 = the jy/jz deposit's reads); gathers 4 + 2
     "k_particles_predict": (6, 16),
@@ -422,6 +422,11 @@ def run_b200_arm(args, w):
         if name == "k_particles_predict" and "k_particles_gamma" not in prof and M > 0:
             # the first predictor pass of a slice does k_particles_gamma's work (predict_inputs<true>): its 8(d) share is spread over the M launches
             nbytes += kernel_algorithmic_bytes("k_particles_gamma", N, P) / M
+        if name == "k_tile_deposit_charge_mid" and "k_tile_deposit_jx" not in prof:
+            # predictor-side deposit with the jx deposit riding along: k_tile_assemble<true> writes the jx target as well
+            nbytes += kernel_algorithmic_bytes("k_tile_deposit_jx", N, P)
+        if name == "k_tile_deposit_rho_chi" and "k_tile_fold_rho_chi" in prof:
+            nbytes = 0.0  # launched, but returns at once unless the |B| stop ended the slice early: k_tile_fold_rho_chi wrote the targets
         dram = NCU_DRAM_BYTES.get(name)
         alg_sum += nbytes * count / 8.0
         if dram:

@@ -155,8 +155,11 @@ struct qpic_ctx {
     bool predict_deposit = false;
     int predict_deposit_mode = -1;  // -1 auto, 0 off, 1 on
     StayOut stay = {};
+    int rc_folded_now = 0;  // set around the slice-end launch of the rho / susceptibility tile kernel, see TileJob::rc_folded
     int * stay_cnt[2] = {nullptr, nullptr};
     int cur_it = 0;
+    int fold_rc_mode = -1;                         // ... and rho / susceptibility in the last pass of a slice: QPIC_FOLD_RHO_CHI = 0 / 1, unset: by density
+    bool fold_rc = false;
     bool fold_jx = true;                           // predictor-side deposit: the jx deposit at (y, z) rides along (QPIC_FOLD_JX=0: separate tile kernel)
     bool fuse_gamma = true;                        // the first predictor pass of a slice does k_particles_gamma's work (QPIC_FUSE_GAMMA=0: separate kernel)
     bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
@@ -700,6 +703,8 @@ FarMovers far_view(const qpic_ctx * c, bool fast) {
 bool predict_deposit_on(const qpic_ctx * c) { return c->predict_deposit && stayers_direct(c) && c->stay.corn != nullptr; }
 // ... and the jx deposit of the iteration with it (k_particles_predict_dep<., true> + k_tile_assemble<true>)
 bool fold_jx_on(const qpic_ctx * c) { return predict_deposit_on(c) && c->fold_jx && c->stay.xcorn != nullptr; }
+// ... and, in the last pass of a slice, rho and susceptibility(i) (k_particles_predict_dep<., 2> + k_tile_fold_rho_chi)
+bool fold_rc_on(const qpic_ctx * c) { return fold_jx_on(c) && c->stay.rcorn != nullptr; }
 
 int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
     TileJob j = tile_job(c);
@@ -743,6 +748,7 @@ int enqueue_tile_base_currents(qpic_ctx * c, cudaStream_t st, bool with_jx, bool
         j.o[n++] = tile_output(c->P.vchi, 1.0, 0, nullptr, c->f3[QPIC_F3_SUSCEPTIBILITY], 1);
     }
     j.nout = n;
+    if (with_rho_chi && !with_jx && final_pass) j.rc_folded = c->rc_folded_now;
     return launch_tile(c, st, j, final_pass, with_jx ? (with_rho_chi ? "k_tile_deposit_jx_rho_chi" : "k_tile_deposit_jx") : "k_tile_deposit_rho_chi");
 }
 
@@ -913,7 +919,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             StayOut so = c->stay;
             so.cnt = c->stay_cnt[it & 1];
             auto predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true> : k_particles_predict_dep<false>;
-            if (fold_jx_on(c)) predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true, true> : k_particles_predict_dep<false, true>;
+            if (fold_jx_on(c)) predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true, 1> : k_particles_predict_dep<false, 1>;
+            if (fold_rc_on(c) && it == M - 1) predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true, 2> : k_particles_predict_dep<false, 2>;
             QPIC_LAUNCH(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so,
                         (const double *)c->f3[QPIC_F3_ASQR], (const double *)c->f2[QPIC_F2_PSI]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
@@ -1003,7 +1010,20 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
     QPIC_TRY(stream_depend(c, sa, sb));
     cudaEvent_t deposit_done = nullptr;
     if (M > 0) {
+        const bool rc_folded = np > 0 && fast && fold_rc_on(c);
+        if (rc_folded) {
+            // the last predictor pass left the per-cell sums; the tile kernel below then only serves a slice that the |B| stop condition
+            // ended before that pass
+            TileJob j = tile_job(c);
+            j.nout = 2;
+            j.o[0] = tile_output(c->P.vrho, 1.0, 2, c->f3[QPIC_F3_RHO_BUNCH], c->f2[QPIC_F2_RHO], 0);
+            j.o[1] = tile_output(c->P.vchi, 1.0, 0, nullptr, c->f3[QPIC_F3_SUSCEPTIBILITY], 1);
+            QPIC_LAUNCH(k_tile_fold_rho_chi, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, sb, c->ctl, c->g, c->start_b, j, c->stay, M - 1);
+            QPIC_TRY(check_launch(c, "k_tile_fold_rho_chi"));
+        }
+        c->rc_folded_now = rc_folded ? M : 0;
         QPIC_TRY(enqueue_base_currents(c, sb, fast, false, true, true));
+        c->rc_folded_now = 0;
         QPIC_TRY(dist_reduce(c, sb, halo_job({c->f2[QPIC_F2_RHO], c->f3[QPIC_F3_SUSCEPTIBILITY]}, {RB_RHO, RB_CHI}, {0, 1})));
         if (sb != sa) {
             deposit_done = next_event(c);
@@ -1067,17 +1087,21 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     QPIC_TRY(dev_alloc(c, &c->perm_b, count));
     QPIC_TRY(dev_alloc(c, &c->perm_m, count));
     QPIC_TRY(dev_alloc(c, &c->tmp, count));
-    // Predictor-side psi_middle source deposit (k_particles_predict_dep + k_tile_assemble): measured on B200 -- config #2 (512^2, 4 ppc)
-    // 0.700 vs 0.696 ms/slice (a wash), config #3 (1024^2, 4 ppc, M = 10) 4.50 vs 4.62, config #4 on one GPU (4096^2, 16 ppc) 133.4 vs
-    // 150.4: it wins when the per-iteration working set is far beyond L2 or a cell holds many particles (the tile kernel loads only
-    // four of them in its first round trip); config #4 on two GPUs 69.6 vs 79.0 ms/slice.  Auto rule: >= 8 particles per cell on average,
-    // or >= 2^20 cells.
+    // Predictor-side deposits (k_particles_predict_dep + k_tile_assemble + k_tile_fold_rho_chi).  Round 1: psi_middle source only, a wash on
+    // config #2 (0.700 vs 0.696 ms/slice) and a gain on the big grids (config #3 4.50 vs 4.62, config #4 on one GPU 133.4 vs 150.4), so it was
+    // chosen by size.  Round 2: the jx deposit and, in a slice's last pass, rho / susceptibility ride along (no tile kernel reads the particles
+    // for them any more, no second stream in the B iterations): config #2 568 vs 600 us/slice, config #3 3.64 vs 3.79 ms, config #4 98.1 vs
+    // 106.2 ms -- on by default for every size; QPIC_PREDICT_DEPOSIT=0 selects the tile kernels.
     if (!c->prm.force_general_deposit && c->jyjz_lists && c->jyjz_cell) {
-        // (slab-decomposed sweeps: `count` is the capacity of the arrays; the density follows from the particles this rank was handed,
-        // which sit on 1 / world of the cells.  Validated on 2 GPUs, config #4: 69.6 vs 79.0 ms/slice.)
+        c->predict_deposit = c->predict_deposit_mode != 0;
+    }
+    {
+        // rho / susceptibility from the last pass: the tile kernel it replaces runs on the second stream next to the push, so at 4 particles per
+        // cell nothing is gained (config #2 564 vs 562 us/slice, config #3 3589 vs 3595); at 16 per cell the pass over the particles it saves
+        // counts (config #4 on one GPU 96.0 vs 97.6 ms/slice).  Automatic: >= 8 particles per cell.  (Slab-decomposed sweeps: density of the
+        // particles this rank was handed, which sit on 1 / world of the cells.)
         const size_t held = c->dist.on ? (size_t)c->dist.live0 * (size_t)c->prm.dist_world : count;
-        const bool big = held >= 8 * (size_t)c->g.n2 || (size_t)c->g.n2 >= ((size_t)1 << 20);
-        c->predict_deposit = c->predict_deposit_mode == 1 || (c->predict_deposit_mode == -1 && big);
+        c->fold_rc = c->fold_rc_mode == 1 || (c->fold_rc_mode == -1 && held >= 8 * (size_t)c->g.n2);
     }
     if (c->predict_deposit && count > 0) {
         // experimental predictor-side deposit: per-cell corner sums, per-warp pieces, double-buffered mover counters, unsorted lists
@@ -1088,12 +1112,17 @@ int alloc_particles(qpic_ctx * c, size_t count) {
             QPIC_TRY(dev_alloc(c, &c->stay_cnt[1], n2));
             QPIC_TRY(dev_alloc(c, &c->stay.lst, (size_t)BIN_K * n2));
             if (c->fold_jx) QPIC_TRY(dev_alloc(c, &c->stay.xcorn, 4 * n2));
+            if (c->fold_jx && c->fold_rc) QPIC_TRY(dev_alloc(c, &c->stay.rcorn, 8 * n2));
         }
         QPIC_TRY(dev_alloc(c, &c->stay.lead, 4 * nwarps));
         QPIC_TRY(dev_alloc(c, &c->stay.trail, 4 * nwarps));
         if (c->fold_jx) {
             QPIC_TRY(dev_alloc(c, &c->stay.xlead, 4 * nwarps));
             QPIC_TRY(dev_alloc(c, &c->stay.xtrail, 4 * nwarps));
+        }
+        if (c->fold_jx && c->fold_rc) {
+            QPIC_TRY(dev_alloc(c, &c->stay.rlead, 8 * nwarps));
+            QPIC_TRY(dev_alloc(c, &c->stay.rtrail, 8 * nwarps));
         }
         c->stay.sign = -1.0;
         c->stay.allow_far = c->far_movers ? 1 : 0;
@@ -1574,6 +1603,8 @@ static int create_impl(qpic_ctx * c) {
         const char * e4 = getenv("QPIC_PREDICT_DEPOSIT");
         c->predict_deposit_mode = (e4 && (e4[0] == '0' || e4[0] == '1')) ? e4[0] - '0' : -1;
         c->predict_deposit = false;
+        const char * e7 = getenv("QPIC_FOLD_RHO_CHI");
+        c->fold_rc_mode = (e7 && (e7[0] == '0' || e7[0] == '1')) ? e7[0] - '0' : -1;
         const char * e6 = getenv("QPIC_FOLD_JX");
         c->fold_jx = !(e6 && e6[0] == '0');
         const char * e5 = getenv("QPIC_FUSE_GAMMA");
@@ -1647,8 +1678,11 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_tile_cell_deposit);
         QPIC_PRELOAD(k_particles_predict_dep<false>);
         QPIC_PRELOAD(k_particles_predict_dep<true>);
-        QPIC_PRELOAD((k_particles_predict_dep<false, true>));
-        QPIC_PRELOAD((k_particles_predict_dep<true, true>));
+        QPIC_PRELOAD((k_particles_predict_dep<false, 1>));
+        QPIC_PRELOAD((k_particles_predict_dep<true, 1>));
+        QPIC_PRELOAD((k_particles_predict_dep<false, 2>));
+        QPIC_PRELOAD((k_particles_predict_dep<true, 2>));
+        QPIC_PRELOAD(k_tile_fold_rho_chi);
         QPIC_PRELOAD(k_tile_assemble<false>);
         QPIC_PRELOAD(k_tile_assemble<true>);
         QPIC_PRELOAD((k_particles_predict<true, true>));
@@ -2603,7 +2637,7 @@ long qpic_timeline_read(qpic_ctx * c, long long * records, long cap) {
 const char * qpic_timeline_kernel_name(int kid) {
     static const char * names[] = QPIC_KERNEL_NAMES;
     static const char * tile[] = {"k_tile_deposit_charge", "k_tile_deposit_charge_mid", "k_tile_deposit_jx", "?", "?", "k_tile_deposit_jy_jz", "?", "?", "?", "?",
-                                  "k_tile_deposit_rho_chi", "?", "?", "?", "?", "?", "k_p2_cols_solve_complex"};
+                                  "k_tile_deposit_rho_chi", "k_tile_fold_rho_chi", "?", "?", "?", "?", "k_p2_cols_solve_complex"};
     if (kid >= 0 && kid < KID_COUNT) return names[kid];
     if (kid >= KID_COUNT && kid <= KID_COUNT + 16) return tile[kid - KID_COUNT];
     return "";

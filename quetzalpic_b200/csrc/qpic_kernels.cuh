@@ -1236,6 +1236,7 @@ struct TileJob {
     int * bin_lst;
     int list_row0, list_rows;
     int cell_row0, cell_rows;  // k_tile_cell_deposit: node rows launched (0, ny on a single GPU)
+    int rc_folded;             // k_tile_deposit<2, true, true>: last B iteration + 1 when k_tile_fold_rho_chi serves the slices whose last predictor pass ran (0: off)
     int * clear_cnt;           // experimental predictor-side deposit: mover counters cleared by the slice's first charge deposit (per node)
     // jy/jz job on a single GPU: the node that has just formed jy_next, jz_next also forms the sources of the By + i Bz solve
     // (src/System_3d.cpp:489-495, :530-536, :555-564 incl. the :563 quirk) into b_src, so that the forward rows of that solve
@@ -1306,6 +1307,11 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
     const int tcell = ay * TILE_ACC + az;
     const int jt = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
     const int cell = wrap_near(jt, g.ny) * g.nz + wrap_near(kt, g.nz);
+    if (RHO_CHI && job.rc_folded) {
+        // only the slices that the |B| stop condition ended before their last predictor pass are left to this kernel (see k_tile_fold_rho_chi)
+        const int tag = ctl->stop_tag;
+        if (tag == 0 || (tag - 1) % STOP_TAG_STRIDE == job.rc_folded - 1) return;
+    }
     const int s0 = start[cell], s1 = start[cell + 1];
     const double ion = tile_prefetch_ion<NOUT>(g, job, ay, az, jt, kt);
     double c00[NOUT], c10[NOUT], c01[NOUT], c11[NOUT];
@@ -1857,6 +1863,8 @@ struct StayOut {
     // FOLD_JX: the jx deposit at (y, z) (src/System_3d.cpp:511-527) rides along -- every particle is a "stayer" of its slice-start cell there, the
     // corrector's value n vx / (1 - vx) and the fractions are in the predictor's registers: same three arrays, sums of v (1-fy)(1-fz) ... v fy fz
     double *xcorn, *xlead, *xtrail;
+    // FOLD 2 (last pass of a slice): rho and susceptibility(i) (:520-527) likewise, 8 sums: n / (1 - vx) and -n / (1 - vx) / gamma times the four weights
+    double *rcorn, *rlead, *rtrail;
     int * cnt;       // movers per target cell (zero on entry)
     int * lst;       // [BIN_K][n2], unsorted
     double sign;     // -1: the psi source deposits -n (src/System_3d.cpp:349-353)
@@ -1864,10 +1872,11 @@ struct StayOut {
     int far_row_lo, far_row_n;  // slabs: legal target rows of a far mover, see FarMovers (0 rows: all)
 };
 
-template <bool FIRST = false, bool FOLD_JX = false>
+template <bool FIRST = false, int FOLD = 0>
 __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
                                         StayOut so, const double * __restrict__ a_sqr3, const double * __restrict__ psi) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
+    constexpr bool FOLD_JX = FOLD >= 1;
     const int s_raw = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int live = live_count(ctl, P.np);  // (slab-decomposed sweeps: the live particles of this rank)
@@ -1942,7 +1951,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
         else if (farm) atomicExch(&ctl->fast_fail, 1);
     }
     const double v = stay ? so.sign * nw : 0.0;
-    constexpr int NV = FOLD_JX ? 8 : 4;
+    constexpr int NV = FOLD == 2 ? 16 : (FOLD == 1 ? 8 : 4);
     double cs[NV];
     cs[0] = v * (1 - f1) * (1 - f2), cs[1] = v * f1 * (1 - f2), cs[2] = v * (1 - f1) * f2, cs[3] = v * f1 * f2;
     if (!stay) cs[0] = cs[1] = cs[2] = cs[3] = 0.0;  // (NaN positions of a blown-up run)
@@ -1951,6 +1960,13 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
         const double vx = px_c / gamma_c;
         const double vj = have ? nw * vx / (1 - vx) : 0.0;
         cs[4] = vj * (1 - fy) * (1 - fz), cs[5] = vj * fy * (1 - fz), cs[6] = vj * (1 - fy) * fz, cs[7] = vj * fy * fz;
+        if (FOLD == 2) {
+            // k_tile_deposit<2, ., true>'s values
+            const double r = have ? nw / (1 - vx) : 0.0;
+            const double ch = -r / gamma_c;
+            cs[8] = r * (1 - fy) * (1 - fz), cs[9] = r * fy * (1 - fz), cs[10] = r * (1 - fy) * fz, cs[11] = r * fy * fz;
+            cs[12] = ch * (1 - fy) * (1 - fz), cs[13] = ch * fy * (1 - fz), cs[14] = ch * (1 - fy) * fz, cs[15] = ch * fy * fz;
+        }
     }
     const int key = have ? c : -3 - lane;
     // keys are sorted, so once no lane finds its key d lanes below, none will at a larger distance: runs of 4-8 particles need 3 steps
@@ -1977,6 +1993,10 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
 #pragma unroll
                 for (int i = 0; i < 4; i++) so.xlead[4 * w + i] = cs[4 + i];
             }
+            if (FOLD == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) so.rlead[8 * w + i] = cs[8 + i];
+            }
         } else if (into_after) {
 #pragma unroll
             for (int i = 0; i < 4; i++) so.trail[4 * w + i] = cs[i];
@@ -1984,12 +2004,20 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
 #pragma unroll
                 for (int i = 0; i < 4; i++) so.xtrail[4 * w + i] = cs[4 + i];
             }
+            if (FOLD == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) so.rtrail[8 * w + i] = cs[8 + i];
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; i++) so.corn[i * (size_t)g.n2 + c] = cs[i];
             if (FOLD_JX) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) so.xcorn[i * (size_t)g.n2 + c] = cs[4 + i];
+            }
+            if (FOLD == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) so.rcorn[i * (size_t)g.n2 + c] = cs[8 + i];
             }
         }
     }
@@ -2096,6 +2124,44 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g,
     }
     __syncthreads();
     tile_store_nodes<FOLD_JX ? 2 : 1>(ctl, g, job, acc, ay, az, jt, kt, ion);
+}
+
+// rho and susceptibility(i) of the slice from the sums the LAST predictor pass left (k_particles_predict_dep<., 2>): no particle is read.
+// Runs like k_tile_deposit<2, true, true> (FINAL_PASS) -- except when the |B| stop condition ended the slice before the last pass ran: the sums
+// do not exist then and the tile kernel, which is launched right after this one with TileJob::rc_folded set, does the work instead.
+__global__ void __launch_bounds__(TILE_CELLS) k_tile_fold_rho_chi(const Ctl * ctl, Geom g, const int * __restrict__ start, TileJob job, StayOut so, int last_it) {
+    QPIC_KERNEL_BEGIN(KID_COUNT + 11);
+    __shared__ double acc[8 * TILE_CELLS];
+    const int ay = threadIdx.y, az = threadIdx.x;
+    const int tcell = ay * TILE_ACC + az;
+    const int jt = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE - 1 + ay, kt = blockIdx.x * TILE - 1 + az;  // unwrapped target cell
+    const int cell = wrap_near(jt, g.ny) * g.nz + wrap_near(kt, g.nz);
+    const int s0 = start[cell], s1 = start[cell + 1];
+    double r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = 0.0;
+    if (s1 > s0) {
+        const int w0 = s0 >> 5, w1 = (s1 - 1) >> 5;
+        if (w0 == w1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = so.rcorn[i * (size_t)g.n2 + cell];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = so.rtrail[8 * w0 + i];
+            for (int w = w0 + 1; w <= w1; w++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) r[i] += so.rlead[8 * w + i];
+            }
+        }
+    }
+    const int tag = ctl->stop_tag;
+    if (ctl->fast_fail) return;
+    if (tag != 0 && ((tag - 1) / STOP_TAG_STRIDE != ctl->slice || (tag - 1) % STOP_TAG_STRIDE != last_it)) return;
+    QPIC_KERNEL_TAIL();
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i * TILE_CELLS + tcell] = r[i];
+    __syncthreads();
+    tile_store_nodes<2>(ctl, g, job, acc, ay, az, jt, kt, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------ jy / jz, one visit per particle
