@@ -139,6 +139,61 @@ struct TlSpan {
 #endif
 #endif
 
+// L2 residency hints for what one kernel writes and the next tile kernel reads (the predictor's half-step outputs -> jy/jz deposit): stores marked
+// evict-last keep their lines in the 126 MB L2 while the predictor streams ~100 MB of read-once slot arrays past them; the consumer's loads mark
+// them evict-first again.  A/B knob QPIC_L2_KEEP (bits): 1 the predictor's half-step outputs are stored evict-last, 2 the jy/jz deposit's loads of them are evict-first,
+// 4 the predictor's load of the weights (read again by the jy/jz deposit) is evict-last, 8 its corner-sum stores are.  (sm_100: the plain .L2::evict_* qualifiers need
+// 256-bit accesses, so the hint travels as a createpolicy descriptor.)
+#ifndef QPIC_L2_KEEP
+#define QPIC_L2_KEEP 1
+#endif
+#if QPIC_L2_KEEP && !defined(QPIC_EMU)
+__device__ __forceinline__ unsigned long long l2_policy_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_keep(double2 * p, double2 v) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(l2_policy_last()) : "memory");
+}
+__device__ __forceinline__ void st_keep1(double * p, double v) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(l2_policy_last()) : "memory");
+}
+__device__ __forceinline__ double ld_keep1(const double * p) {
+    double r;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(l2_policy_last()));
+    return r;
+}
+__device__ __forceinline__ void st_keep(int * p, int v) {
+    asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_last()) : "memory");
+}
+#else
+__device__ __forceinline__ void st_keep(double2 * p, double2 v) { *p = v; }
+__device__ __forceinline__ void st_keep(int * p, int v) { *p = v; }
+__device__ __forceinline__ void st_keep1(double * p, double v) { *p = v; }
+__device__ __forceinline__ double ld_keep1(const double * p) { return *p; }
+#endif
+#if (QPIC_L2_KEEP & 2) && !defined(QPIC_EMU)
+__device__ __forceinline__ double2 ld_release(const double2 * p) {
+    double2 r;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(l2_policy_first()));
+    return r;
+}
+__device__ __forceinline__ int ld_release(const int * p) {
+    int r;
+    asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_first()));
+    return r;
+}
+#else
+__device__ __forceinline__ double2 ld_release(const double2 * p) { return *p; }
+__device__ __forceinline__ int ld_release(const int * p) { return *p; }
+#endif
+
 // streaming load: the line is marked evict-first in L2.  For slot arrays that are read once per iteration, so that they do not
 // push out the arrays the deposit kernels are about to read.
 __device__ __forceinline__ double ld_stream(const double * p) {
@@ -1897,7 +1952,7 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
     const double q = in.q, gamma = in.gamma, a_particle = in.a_particle;
     const double t1y = in.t1y, t1z = in.t1z, dpy = in.dpy, dpz = in.dpz;
     const double y0 = slot_position(g.exact_dy, jc, fy, g.dy, P.y_s, s), z0 = slot_position(g.exact_dz, kc, fz, g.dz, P.z_s, s);
-    const double nw = P.nw_s[s];
+    const double nw = (QPIC_L2_KEEP & 4) ? ld_keep1(P.nw_s + s) : P.nw_s[s];
     int js, ks;
     double fys, fzs;
     stagger(jc, fy, g.ny, js, fys);
@@ -1934,12 +1989,12 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
                          : (farm ? (FAR_CODE | ((f1 >= 0.5) ? 64 : 0) | ((f2 >= 0.5) ? 128 : 0) | ((kc & 3) << 8)) : pack_offset(oy, oz, f1, f2, kc));
     if (have) {
         predict_store_invariants<FIRST>(P, s, in);
-        P.pyzn[s] = make_double2(pyn, pzn);
+        st_keep(P.pyzn + s, make_double2(pyn, pzn));
         P.gam[s] = gamma_c;
         if (store_px) P.pxs[s] = px_c;
         if (!FOLD_JX) store_currents<false>(P, s, nw, gamma_c, px_c);  // (FOLD_JX: no jx tile deposit reads the value)
-        P.fyz_m[s] = make_double2(f1, f2);
-        P.off_m[s] = code;
+        st_keep(P.fyz_m + s, make_double2(f1, f2));
+        st_keep(P.off_m + s, code);
         if (bad) atomicExch(&ctl->fast_fail, 1);
     }
     // ---- ... and the psi_middle source: stayers summed per cell, movers listed
@@ -2010,10 +2065,16 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) so.corn[i * (size_t)g.n2 + c] = cs[i];
+            for (int i = 0; i < 4; i++) {
+                if (QPIC_L2_KEEP & 8) st_keep1(so.corn + i * (size_t)g.n2 + c, cs[i]);
+                else so.corn[i * (size_t)g.n2 + c] = cs[i];
+            }
             if (FOLD_JX) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) so.xcorn[i * (size_t)g.n2 + c] = cs[4 + i];
+                for (int i = 0; i < 4; i++) {
+                    if (QPIC_L2_KEEP & 8) st_keep1(so.xcorn + i * (size_t)g.n2 + c, cs[4 + i]);
+                    else so.xcorn[i * (size_t)g.n2 + c] = cs[4 + i];
+                }
             }
             if (FOLD == 2) {
 #pragma unroll
@@ -2189,6 +2250,9 @@ constexpr int LIST_BY = LIST_TY + 2, LIST_BZ = LIST_TZ + 2, LIST_THREADS = LIST_
 #ifndef QPIC_CELL_PIPE
 #define QPIC_CELL_PIPE 1
 #endif
+#ifndef QPIC_CELL_UNROLL
+#define QPIC_CELL_UNROLL 2
+#endif
 __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 5);
     __shared__ double acc[12 * LIST_THREADS];
@@ -2256,16 +2320,23 @@ __global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_depo
             if (i < n) e = job.bin_lst[(size_t)i * g.n2 + cell];
             visit(ce >> 2, (ce >> 1) & 1, ce & 1);
         }
-        for (int sb = s0; sb < s1; sb += 2) {
-            const bool two = sb + 1 < s1;
-            const int sB = two ? sb + 1 : sb;
-            const int cA = P.off_m[sb], cB = P.off_m[sB];
-            const double2 fA = fyzm[sb], pA = pyzn[sb], fB = fyzm[sB], pB = pyzn[sB];
-            const double nwA = job.nw[sb], nwB = job.nw[sB];
-            const double fyA = fA.x, fzA = fA.y, vyA = pA.x, vzA = pA.y;
-            const double fyB = fB.x, fzB = fB.y, vyB = pB.x, vzB = pB.y;
-            if ((cA & 63) == STAY_CODE) visit5(fyA, fzA, nwA, vyA, vzA, (cA >> 6) & 1, (cA >> 7) & 1);
-            if (two && (cB & 63) == STAY_CODE) visit5(fyB, fzB, nwB, vyB, vzB, (cB >> 6) & 1, (cB >> 7) & 1);
+        for (int sb = s0; sb < s1; sb += QPIC_CELL_UNROLL) {
+            // QPIC_CELL_UNROLL particles per round trip (out-of-range ones repeat the first and are skipped)
+            int cd[QPIC_CELL_UNROLL];
+            double2 fm[QPIC_CELL_UNROLL], pn[QPIC_CELL_UNROLL];
+            double nwv[QPIC_CELL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < QPIC_CELL_UNROLL; u++) {
+                const int sU = sb + u < s1 ? sb + u : sb;
+                cd[u] = ld_release(P.off_m + sU);
+                fm[u] = ld_release(fyzm + sU);
+                pn[u] = ld_release(pyzn + sU);
+                nwv[u] = job.nw[sU];
+            }
+#pragma unroll
+            for (int u = 0; u < QPIC_CELL_UNROLL; u++) {
+                if (sb + u < s1 && (cd[u] & 63) == STAY_CODE) visit5(fm[u].x, fm[u].y, nwv[u], pn[u].x, pn[u].y, (cd[u] >> 6) & 1, (cd[u] >> 7) & 1);
+            }
         }
         for (; i < n; ) {
             const int ce = e;
