@@ -161,8 +161,6 @@ struct qpic_ctx {
     int fold_rc_mode = -1;                         // ... and rho / susceptibility in the last pass of a slice: QPIC_FOLD_RHO_CHI = 0 / 1, unset: by density
     bool fold_rc = false;
     bool fold_jx = true;                           // predictor-side deposit: the jx deposit at (y, z) rides along (QPIC_FOLD_JX=0: separate tile kernel)
-    bool identity_push = true;                     // single GPU: the push rewrites the id arrays in slot order (QPIC_IDENTITY_PUSH=0: scatter by particle id)
-    double * pscratch = nullptr;                   // np doubles: staging of qpic_download_particles / qpic_upload_particles in that mode
     bool fuse_gamma = true;                        // the first predictor pass of a slice does k_particles_gamma's work (QPIC_FUSE_GAMMA=0: separate kernel)
     bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
     double * xy[5] = {};          // keep_xy_cuts: (nx, ny) cuts of psi, rho, jx, jy, jz
@@ -1040,7 +1038,7 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         QPIC_TRY(rc);
     }
     if (np > 0) {
-        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, (c->dist.on || c->P.orig_a) ? (const int *)nullptr : c->perm_b,
+        QPIC_LAUNCH_FLAT(k_particles_advance, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->dist.on ? (const int *)nullptr : c->perm_b,
                          c->f2[QPIC_F2_PSI_MIDDLE], c->count, migrate_view(c), c->track_gamma_px ? 1 : 0);
         QPIC_TRY(check_launch(c, "k_particles_advance"));
     }
@@ -1086,12 +1084,6 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     QPIC_TRY(dev_alloc(c, &P.cell_m, count));
     QPIC_TRY(dev_alloc(c, &P.off_m, count));
     if (c->dist.on) QPIC_TRY(dev_alloc(c, &P.akey, 2 * (size_t)c->dist.v.mig_cap));  // sort keys of a slice's arrivals
-    if (!c->dist.on && c->identity_push && count > 0) {
-        QPIC_TRY(dev_alloc(c, &P.orig_a, count));
-        QPIC_TRY(dev_alloc(c, &P.orig_b, count));
-        if (!P.push_count) QPIC_TRY(dev_alloc(c, &P.push_count, 1));
-        QPIC_TRY(dev_alloc(c, &c->pscratch, count));
-    }
     QPIC_TRY(dev_alloc(c, &c->perm_b, count));
     QPIC_TRY(dev_alloc(c, &c->perm_m, count));
     QPIC_TRY(dev_alloc(c, &c->tmp, count));
@@ -1615,8 +1607,6 @@ static int create_impl(qpic_ctx * c) {
         c->fold_rc_mode = (e7 && (e7[0] == '0' || e7[0] == '1')) ? e7[0] - '0' : -1;
         const char * e6 = getenv("QPIC_FOLD_JX");
         c->fold_jx = !(e6 && e6[0] == '0');
-        const char * e8 = getenv("QPIC_IDENTITY_PUSH");
-        c->identity_push = !(e8 && e8[0] == '0');
         const char * e5 = getenv("QPIC_FUSE_GAMMA");
         c->fuse_gamma = !(e5 && e5[0] == '0');
         const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
@@ -1823,12 +1813,6 @@ int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, c
         QPIC_CUDA(c, cudaMemcpyAsync(c->P.y, y, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
         QPIC_CUDA(c, cudaMemcpyAsync(c->P.z, z, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
         QPIC_CUDA(c, cudaMemcpyAsync(c->P.nw, n, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
-    }
-    if (c->P.orig_a && count > 0) {
-        // the id arrays are in the caller's order again
-        QPIC_LAUNCH_FLAT(k_iota, blocks_for(count, 256), 256, 0, c->stream, (int)count, c->P.orig_a);
-        QPIC_TRY(check_launch(c, "k_iota"));
-        QPIC_CUDA(c, cudaMemsetAsync(c->P.push_count, 0, sizeof(int), c->stream));
     }
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->lists_dirty = true;
@@ -2057,32 +2041,12 @@ static double * particle_array(qpic_ctx * c, qpic_particle_field f) {
     }
 }
 
-// index space of the particle-id arrays -> caller's particle id (NULL: they are in the caller's order), see Particles::orig_a
-static int id_map(qpic_ctx * c, const int ** map) {
-    *map = nullptr;
-    if (!c->P.orig_a) return QPIC_OK;
-    int pushes = 0;
-    QPIC_CUDA(c, cudaMemcpyAsync(&pushes, c->P.push_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
-    *map = (pushes & 1) ? c->P.orig_b : c->P.orig_a;
-    return QPIC_OK;
-}
-
 int qpic_download_particles(qpic_ctx * c, qpic_particle_field f, double * dst) {
     if (!c) return QPIC_ERR_INVALID;
     if (c->dist.on) return fail(c, QPIC_ERR_UNSUPPORTED, "particle arrays of a distributed sweep have no caller order");
     double * src = particle_array(c, f);
     if (!src) return fail(c, QPIC_ERR_INVALID, "bad particle field id");
     if (c->P.np == 0) return QPIC_OK;
-    QPIC_CUDA(c, cudaSetDevice(c->prm.device));
-    if (c->began && !c->finished) QPIC_TRY(resolve(c));
-    const int * map = nullptr;
-    QPIC_TRY(id_map(c, &map));
-    if (map) {
-        QPIC_LAUNCH_FLAT(k_particles_reorder, blocks_for(c->P.np, 256), 256, 0, c->stream, c->P.np, map, (const double *)src, c->pscratch, 1);
-        QPIC_TRY(check_launch(c, "k_particles_reorder"));
-        src = c->pscratch;
-    }
     return copy_out(c, src, dst, (size_t)c->P.np);
 }
 
@@ -2093,14 +2057,7 @@ int qpic_upload_particles(qpic_ctx * c, qpic_particle_field f, const double * sr
     if (!dst || f == QPIC_P_GAMMA || f == QPIC_P_PX || !src) return fail(c, QPIC_ERR_INVALID, "only y, z, py, pz, n can be uploaded");
     if (c->P.np == 0) return QPIC_OK;
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
-    if (c->began && !c->finished) QPIC_TRY(resolve(c));
-    const int * map = nullptr;
-    QPIC_TRY(id_map(c, &map));
-    QPIC_CUDA(c, cudaMemcpyAsync(map ? c->pscratch : dst, src, sizeof(double) * (size_t)c->P.np, cudaMemcpyHostToDevice, c->stream));
-    if (map) {
-        QPIC_LAUNCH_FLAT(k_particles_reorder, blocks_for(c->P.np, 256), 256, 0, c->stream, c->P.np, map, (const double *)c->pscratch, dst, 0);
-        QPIC_TRY(check_launch(c, "k_particles_reorder"));
-    }
+    QPIC_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)c->P.np, cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
     if (f == QPIC_P_Y || f == QPIC_P_Z) c->lists_dirty = true;
     return QPIC_OK;

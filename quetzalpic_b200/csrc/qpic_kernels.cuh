@@ -382,18 +382,6 @@ __global__ void k_init_a_sqr(Geom g, double * __restrict__ a, double amp, double
     }
 }
 
-// caller's order <-> index space of the particle-id arrays (see Particles::orig_a): dst[id[p]] = src[p] / dst[p] = src[id[p]]; id = NULL: iota
-__global__ void k_particles_reorder(int np, const int * __restrict__ id, const double * __restrict__ src, double * __restrict__ dst, int to_caller) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    if (to_caller) dst[id[p]] = src[p];
-    else dst[p] = src[id[p]];
-}
-__global__ void k_iota(int n, int * __restrict__ a) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n) a[p] = p;
-}
-
 // cell descriptors of (y, z) + per-cell population count (integer atomics: order independent)
 __global__ void k_locate_count(int np, Geom g, const double * __restrict__ y, const double * __restrict__ z, int * __restrict__ cell,
                                double * __restrict__ fy, double * __restrict__ fz, int * __restrict__ count) {
@@ -739,13 +727,6 @@ struct Particles {
     double *y, *z, *py, *pz, *nw;
     double *gamma, *px;             // src/containers.h:41-42 (kept for inspection / dumps)
     int * cell_p;                   // cell of (y,z)
-    // Single GPU (round 2): the push writes the particle-id arrays at index s (its slot) instead of scattering to perm_b[s], and the slot copies of
-    // the next slice gather from ~sorted indices: both passes coalesce.  The index space p of the id arrays therefore changes with every push;
-    // orig_a / orig_b hold "index -> caller's particle id" for the index space of the id arrays (buffer *push_count & 1) and for the slot space
-    // that the last cell sort produced (the other buffer), so that the ABI still reads / writes particles in the caller's order.  NULL: id arrays
-    // stay in the caller's order (perm_b scatter, round 1) / slab-decomposed sweeps (no caller order).
-    int *orig_a, *orig_b;
-    int * push_count;
     int * akey;                     // slab-decomposed sweeps: sort keys of this slice's arrivals (see sort_key); NULL on a single GPU
     double *fy_p, *fz_p;            // fractional position inside it
     // ---- by slot
@@ -843,12 +824,6 @@ __global__ void k_rank_to_slots(const Ctl * ctl, Geom g, Particles P, int np, co
     }
     const int s = b + rank;
     perm[s] = p;
-    if (P.orig_a) {
-        const int par = *P.push_count & 1;
-        const int * __restrict__ of_index = par ? P.orig_b : P.orig_a;
-        int * __restrict__ of_slot = par ? P.orig_a : P.orig_b;
-        of_slot[s] = of_index[p];
-    }
     if (s >= live_count(ctl, P.np)) return;  // (slab-decomposed sweeps: the bucket of emigrated entries lies beyond the live slots)
     P.cell_b[s] = c;
     P.fyz_b[s] = make_double2(fy, fz);
@@ -1106,7 +1081,6 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= live_count(ctl, P.np)) return;
     const int p = perm_b ? perm_b[s] : s;
-    if (P.push_count && s == 0) atomicAdd(P.push_count, 1);  // the id arrays change their index space with this push (see Particles::orig_a)
     const int c = P.cell_b[s];
     const int jc = c / g.nz, kc = c - jc * g.nz;
     const double2 fyz = P.fyz_b[s];
@@ -1131,9 +1105,9 @@ __global__ void k_particles_advance(const Ctl * ctl, Geom g, Particles P, const 
     locate_fast(y, g.dy, g.inv_dy, g.exact_dy, g.ny, jn, f1);
     locate_fast(z, g.dz, g.inv_dz, g.exact_dz, g.nz, kn, f2);
     int cn = jn * g.nz + kn;
-    if (!perm_b) P.nw[p] = P.nw_s[s];  // (the weight moves with the particle when the id arrays are rewritten in slot order)
     if (mig.enabled) {
         const double nw = P.nw_s[s];
+        P.nw[p] = nw;
         int rel = jn - mig.row0;  // row relative to the slab, minimal image
         if (2 * rel > g.ny) rel -= g.ny;
         if (2 * rel < -g.ny) rel += g.ny;
