@@ -55,7 +55,6 @@ def algorithmic_bytes_per_slice(N, P, M):
 SURVEY_BYTES = {
     # once per slice: psi solve 12 = deposit target 1 + rows 5 + columns 2 + rows 2 + normalise/clamp 2 (fused into the backward rows)
     "k_tile_deposit_charge": (1, 3), "k_fft_rows_r2c": (5, 0), "k_fft_cols_solve": (2, 0), "k_fft_rows_c2r": (4, 0),
-    "k_fft_solve_real": (11, 0), "k_fft_solve_b": (18, 0),
     "k_particles_gamma": (2, 7),            # gathers 2; reads y z py pz n, writes gamma px
     "k_tile_deposit_rho_chi": (5, 0), "k_tile_fold_rho_chi": (5, 0),       # rho / jx / chi targets of the once-per-slice deposit (its particle reads are in the 7 above)
     "k_particles_advance": (1, 8), "k_end_of_slice": (9, 0),

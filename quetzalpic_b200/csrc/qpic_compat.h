@@ -37,22 +37,7 @@ inline cudaError_t launch_kernel(void (*kernel)(Exp...), dim3 grid, dim3 block, 
 }
 // cooperative launch: the driver guarantees that all blocks of the grid are resident at the same time (what a grid-wide barrier
 // inside the kernel needs); valid inside stream capture (the attribute becomes a kernel node attribute)
-template <class... Exp, class... Act>
-inline cudaError_t launch_cooperative(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Act &&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Act>(args)...);
-}
 }  // namespace qpic
-#define QPIC_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) (void)qpic::launch_cooperative(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
 #define QPIC_LAUNCH(kernel, grid, block, smem, stream, ...) (void)qpic::launch_kernel(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
 #define QPIC_LAUNCH_FLAT(kernel, grid, block, smem, stream, ...) (void)qpic::launch_kernel(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
 #define QPIC_DYN_SMEM(type, name)                                        \

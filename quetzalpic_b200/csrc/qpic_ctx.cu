@@ -102,15 +102,6 @@ struct qpic_ctx {
     };
     FftLaunch rows_real, rows_cplx, cols_half, cols_full;
     bool pow2_y = false, pow2_z = false;
-    // one cooperative kernel per solve (k_p2_solve_real / k_p2_solve_b): single GPU, both axes on the power-of-two engine
-    struct FusedSolve {
-        bool on = false;
-        int threads = 0;
-        size_t smem = 0;
-        int grid_real = 0, grid_b = 0;
-        int log2spb_rows = 0, log2spb_cols = 0;
-        unsigned int * bar = nullptr;  // {arrival count, generation} of the grid barrier
-    } fused;
     double inv_scale = 0.0;  // 1/(ny*nz) when that is exactly representable (power of two), else 0 = divide
     struct InvSymbol {
         double D;
@@ -143,10 +134,8 @@ struct qpic_ctx {
         std::vector<void *> opened;                // cudaIpcOpenMemHandle mappings
     } dist;
     double2 * b_src = nullptr;                     // sources of the By + i Bz solve formed by the jy/jz deposit (TileJob::b_src)
-    double2 * pair_src = nullptr;                  // qpic_solve_helmholtz_pair_host: the two sources as one complex array
     int *bin_cnt = nullptr, *bin_lst = nullptr;  // per-cell lists of the half-step positions (TileJob::bin_cnt)
-    bool jyjz_lists = true;                        // QPIC_JYJZ_LISTS=0: bin again in the jy/jz deposit (A/B)
-    bool jyjz_cell = true;                         // QPIC_JYJZ_CELL=0: three-list kernel instead of one visit per particle (A/B)
+    bool jyjz_lists = true;                        // mover lists of the half-step positions exist (false: force_general_deposit, no fast path)
     // half steps beyond one cell stay on the sort-free path (FarMovers, qpic_kernels.cuh); QPIC_FAR_MOVERS=0: they raise the rollback as in round 1
     bool far_movers = true;
     int * far_cnt[2] = {nullptr, nullptr};
@@ -571,17 +560,6 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     const bool fuse = fixed_dst != nullptr && c->pow2_y && c->pow2_z;
     if (fused) *fused = fuse;
     if (c->dist.on && !fuse) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the fused power-of-two solve");
-#ifndef QPIC_EMU
-    if (c->fused.on) {
-        const double * inv = nullptr;
-        QPIC_TRY(get_inv_symbol(c, D, false, &inv));
-        const SolveShape S = {c->fz.plan.log2n, c->fy.plan.log2n, c->fused.log2spb_rows, c->fused.log2spb_cols};
-        QPIC_LAUNCH_COOP(k_p2_solve_real, c->fused.grid_real, c->fused.threads, c->fused.smem, st, ctl, S, (const double2 *)c->fz.tw, (const double2 *)c->fy.tw,
-                         (const double *)c->fft_in, c->spec, fuse ? fixed_dst : c->raw, inv, c->spec_row0, c->spec_colsum, c->fused.bar, c->inv_scale, fuse ? 1 : 0,
-                         c->prm.psi_threshold - 1);
-        return check_launch(c, "k_fft_solve_real");
-    }
-#endif
     if (c->pow2_z) {
         QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_r2c<true, true> : k_p2_rows_r2c<false, true>) : (c->dist.on ? k_p2_rows_r2c<true> : k_p2_rows_r2c<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
     } else {
@@ -678,7 +656,7 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 // psi source from positions (y,z) [at_mid = 0] or the half-step positions [at_mid = 1] -> fft_in
 // with the published lists the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their cell directly
 // and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
-bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists && c->jyjz_cell; }
+bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists; }
 // slabs: target rows whose deposits (corner rows j, j + 1; the staggered jy rows j - 1 .. j + 1) stay inside own rows + DIST_HALO halo rows
 void far_rows(const qpic_ctx * c, int * row_lo, int * row_n) {
     *row_lo = 0;
@@ -729,12 +707,9 @@ int enqueue_tile_charge(qpic_ctx * c, cudaStream_t st, int at_mid) {
         }
         return check_launch(c, "k_tile_deposit_charge_mid");
     }
-    if (stayers_direct(c)) {
-        // stayers from registers, movers through the lists; publishes the movers for k_tile_cell_deposit
-        QPIC_LAUNCH(k_tile_stay_deposit, tile_grid(c), block, tile_stay_smem_bytes(), st, c->ctl, c->g, c->start_b, c->P, j, far_view(c, true));
-        return check_launch(c, "k_tile_deposit_charge_mid");
-    }
-    QPIC_LAUNCH(k_tile_bin_deposit<0>, tile_grid(c), block, tile_bin_smem_bytes<0>(), st, c->ctl, c->g, c->start_b, c->P, j);
+    if (!stayers_direct(c)) return fail(c, QPIC_ERR_STATE, "the sort-free deposit path needs the mover lists (force_general_deposit is set)");
+    // stayers from registers, movers through the lists; publishes the movers for k_tile_cell_deposit
+    QPIC_LAUNCH(k_tile_stay_deposit, tile_grid(c), block, tile_stay_smem_bytes(), st, c->ctl, c->g, c->start_b, c->P, j, far_view(c, true));
     return check_launch(c, "k_tile_deposit_charge_mid");
 }
 
@@ -762,26 +737,18 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     j.o[1] = tile_output(nullptr, 1.0, 0, nullptr, c->f2[QPIC_F2_JZ_NEXT], 0);
     j.psi_mid = c->f2[QPIC_F2_PSI_MIDDLE];
     j.nw = c->P.nw_s;
-    if (c->jyjz_lists) {
-        // the lists of the half-step positions were published by the psi_middle source deposit of this iteration
-        j.b_src = c->b_src;
-        j.b_by = c->f2[QPIC_F2_BY_CUR];
-        j.b_bz = c->f2[QPIC_F2_BZ_CUR];
-        j.b_jx = c->f2[QPIC_F2_JX];
-        j.b_jy = c->f2[QPIC_F2_JY];
-        j.b_jz = c->f2[QPIC_F2_JZ];
-        j.b_D = c->prm.magnetic_field_D;
-        if (stayers_direct(c)) {
-            // one visit per particle (k_tile_cell_deposit); A/B switch QPIC_JYJZ_CELL=0 selects the three-list kernel
-            const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (j.cell_rows + LIST_TY - 1) / LIST_TY);
-            QPIC_LAUNCH(k_tile_cell_deposit, grid, dim3(LIST_BZ, LIST_BY), 0, st, c->ctl, c->g, c->start_b, c->P, j);
-            return check_launch(c, "k_tile_deposit_jy_jz");
-        }
-        QPIC_LAUNCH(k_tile_list_deposit, tile_grid(c), dim3(TILE_ACC, TILE_ACC), 0, st, c->ctl, c->g, c->start_b, c->P, j);
-        return check_launch(c, "k_tile_deposit_jy_jz");
-    }
-    const dim3 block(TILE_ACC + 3, TILE_ACC + 3);
-    QPIC_LAUNCH(k_tile_bin_deposit<1>, tile_grid(c), block, tile_bin_smem_bytes<1>(), st, c->ctl, c->g, c->start_b, c->P, j);
+    if (!stayers_direct(c)) return fail(c, QPIC_ERR_STATE, "the sort-free deposit path needs the mover lists (force_general_deposit is set)");
+    // the mover lists of the half-step positions were published by the psi_middle source kernel of this iteration
+    j.b_src = c->b_src;
+    j.b_by = c->f2[QPIC_F2_BY_CUR];
+    j.b_bz = c->f2[QPIC_F2_BZ_CUR];
+    j.b_jx = c->f2[QPIC_F2_JX];
+    j.b_jy = c->f2[QPIC_F2_JY];
+    j.b_jz = c->f2[QPIC_F2_JZ];
+    j.b_D = c->prm.magnetic_field_D;
+    // one visit per particle
+    const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (j.cell_rows + LIST_TY - 1) / LIST_TY);
+    QPIC_LAUNCH(k_tile_cell_deposit, grid, dim3(LIST_BZ, LIST_BY), 0, st, c->ctl, c->g, c->start_b, c->P, j);
     return check_launch(c, "k_tile_deposit_jy_jz");
 }
 
@@ -967,20 +934,6 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         }
         if (!jx_folded) QPIC_TRY(stream_depend(c, sb, sa));
         // By + i Bz in one complex solve
-#ifndef QPIC_EMU
-        if (c->fused.on) {
-            const bool pre = fast && c->jyjz_lists && c->b_src;
-            const double * inv = nullptr;
-            QPIC_TRY(get_inv_symbol(c, c->prm.magnetic_field_D, true, &inv));
-            const SolveShape S = {c->fz.plan.log2n, c->fy.plan.log2n, c->fused.log2spb_rows, c->fused.log2spb_cols};
-            auto kern = pre ? k_p2_solve_b<true> : k_p2_solve_b<false>;
-            QPIC_LAUNCH_COOP(kern, c->fused.grid_b, c->fused.threads, c->fused.smem, sa, c->ctl, S, (const double2 *)c->fz.tw, (const double2 *)c->fy.tw, c->g,
-                             c->prm.magnetic_field_D, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (const double *)c->f2[QPIC_F2_JX], (const double *)c->f2[QPIC_F2_JY],
-                             (const double *)c->f2[QPIC_F2_JZ], (const double *)c->f2[QPIC_F2_JY_NEXT], (const double *)c->f2[QPIC_F2_JZ_NEXT], (const double2 *)c->b_src,
-                             c->spec, inv, c->fused.bar, c->prm.threshold_B, it, c->inv_scale);
-            QPIC_TRY(check_launch(c, "k_fft_solve_b"));
-        } else
-#endif
         {
             const qpic_ctx::FftLaunch & R = c->rows_cplx;
             if (c->pow2_z) {
@@ -1092,7 +1045,7 @@ int alloc_particles(qpic_ctx * c, size_t count) {
     // chosen by size.  Round 2: the jx deposit and, in a slice's last pass, rho / susceptibility ride along (no tile kernel reads the particles
     // for them any more, no second stream in the B iterations): config #2 568 vs 600 us/slice, config #3 3.64 vs 3.79 ms, config #4 98.1 vs
     // 106.2 ms -- on by default for every size; QPIC_PREDICT_DEPOSIT=0 selects the tile kernels.
-    if (!c->prm.force_general_deposit && c->jyjz_lists && c->jyjz_cell) {
+    if (!c->prm.force_general_deposit && c->jyjz_lists) {
         c->predict_deposit = c->predict_deposit_mode != 0;
     }
     {
@@ -1485,9 +1438,6 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
         }
     }
-    if (tile_bin_smem_bytes<1>() > SMEM_DEFAULT_LIMIT) {
-        QPIC_CUDA(c, cudaFuncSetAttribute(k_tile_bin_deposit<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bin_smem_bytes<1>()));
-    }
     // the inverse-symbol tables of the two operators of the sweep (psi: D = 0, half spectrum; By + i Bz: D, full spectrum)
     if (c->pow2_y) {
         const double * unused = nullptr;
@@ -1495,61 +1445,6 @@ static int create_impl(qpic_ctx * c) {
         QPIC_TRY(get_inv_symbol(c, p.magnetic_field_D, true, &unused));
     }
 
-#ifndef QPIC_EMU
-    // EXPERIMENT, off by default (QPIC_FUSED_SOLVE=1): one cooperative kernel per solve with grid-wide barriers between rows / columns /
-    // rows (single GPU, power-of-two axes up to 4096 points).  Measured on B200, config #2 (gpurun_out/r42_ab.log, r41_timeline*.txt):
-    // 686 us/slice against 658 for the three launches -- in the timeline build a fused solve takes 15.8 us against 13.1 + two launch gaps
-    // (a grid barrier costs ~1.3 us: drain the block's stores, one atomic round trip, one poll round trip), and a cooperative grid does
-    // not share the device with the concurrent jx-deposit branch.
-    // T threads per block: at least one sequence of either axis, 128 by default (QPIC_SOLVE_THREADS); the grid is the number of units of
-    // the widest phase, capped by what the device holds at once.
-    {
-        const char * e = getenv("QPIC_FUSED_SOLVE");
-        const int longest = g.ny > g.nz ? g.ny : g.nz;
-        if (!D.on && c->pow2_y && c->pow2_z && longest <= 4096 && (e && e[0] == '1')) {
-            int T = 128;
-            if (const char * t = getenv("QPIC_SOLVE_THREADS")) T = atoi(t);
-            if (T < 32 || (T & (T - 1)) != 0) T = 128;
-            while (T < longest / 8) T *= 2;
-            if (T > 512) T = 512;
-            qpic_ctx::FusedSolve & F = c->fused;
-            auto log2i = [](int v) {
-                int l = 0;
-                while ((1 << l) < v) l++;
-                return l;
-            };
-            F.threads = T;
-            F.log2spb_rows = log2i(T / (g.nz / 8));
-            F.log2spb_cols = log2i(T / (g.ny / 8));
-            const size_t s_rows = sizeof(double2) * 2 * ((size_t)p2_pad_len(g.nz) << F.log2spb_rows);
-            const size_t s_cols = sizeof(double2) * 2 * ((size_t)p2_pad_len(g.ny) << F.log2spb_cols);
-            F.smem = s_rows > s_cols ? s_rows : s_cols;
-            if (F.smem <= SMEM_OPTIN_LIMIT) {
-                if (F.smem > SMEM_DEFAULT_LIMIT) {
-                    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_solve_real, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem));
-                    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_solve_b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem));
-                    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_solve_b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem));
-                }
-                cudaDeviceProp prop;
-                QPIC_CUDA(c, cudaGetDeviceProperties(&prop, p.device));
-                int per_sm_real = 0, per_sm_b = 0, per_sm_b2 = 0;
-                QPIC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_real, k_p2_solve_real, T, F.smem));
-                QPIC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_p2_solve_b<true>, T, F.smem));
-                QPIC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b2, k_p2_solve_b<false>, T, F.smem));
-                if (per_sm_b2 < per_sm_b) per_sm_b = per_sm_b2;
-                auto units = [](int n, int log2spb) { return (n + (1 << log2spb) - 1) >> log2spb; };
-                const int u_real = std::max(units(g.ny / 2, F.log2spb_rows), units(g.nz / 2 + 1, F.log2spb_cols));
-                const int u_b = std::max(units(g.ny, F.log2spb_rows), units(g.nz, F.log2spb_cols));
-                if (prop.cooperativeLaunch && per_sm_real > 0 && per_sm_b > 0) {
-                    F.grid_real = std::min(u_real, per_sm_real * prop.multiProcessorCount);
-                    F.grid_b = std::min(u_b, per_sm_b * prop.multiProcessorCount);
-                    QPIC_TRY(dev_alloc(c, &F.bar, 2));
-                    F.on = true;
-                }
-            }
-        }
-    }
-#endif
     QPIC_TRY(dev_alloc(c, &c->ctl, 1));
     QPIC_TRY(dev_alloc(c, &c->ctl_scratch, 1));
     QPIC_CUDA(c, cudaMallocHost(&c->ctl_host, sizeof(Ctl)));
@@ -1596,10 +1491,8 @@ static int create_impl(qpic_ctx * c) {
         QPIC_TRY(dev_alloc(c, &c->f3[f], n3));
     }
     {
-        const char * e = getenv("QPIC_JYJZ_LISTS");
-        c->jyjz_lists = !(e && e[0] == '0');
-        // QPIC_PREDICT_DEPOSIT = 1 / 0 forces the predictor-side psi_middle deposit on / off; unset: decided from the problem size when
-        // the particles arrive (alloc_particles)
+        c->jyjz_lists = true;
+        // QPIC_PREDICT_DEPOSIT = 0 selects the tile kernels (k_tile_stay_deposit + jx tile deposit) instead of the predictor-side deposits
         const char * e4 = getenv("QPIC_PREDICT_DEPOSIT");
         c->predict_deposit_mode = (e4 && (e4[0] == '0' || e4[0] == '1')) ? e4[0] - '0' : -1;
         c->predict_deposit = false;
@@ -1611,10 +1504,8 @@ static int create_impl(qpic_ctx * c) {
         c->fuse_gamma = !(e5 && e5[0] == '0');
         const char * e3 = getenv("QPIC_TRACK_GAMMA_PX");
         c->track_gamma_px = e3 && e3[0] == '1';
-        const char * e2 = getenv("QPIC_JYJZ_CELL");
-        c->jyjz_cell = !(e2 && e2[0] == '0');
         const char * e9 = getenv("QPIC_FAR_MOVERS");
-        c->far_movers = !(e9 && e9[0] == '0') && c->jyjz_lists && c->jyjz_cell && !p.force_general_deposit;
+        c->far_movers = !(e9 && e9[0] == '0') && !p.force_general_deposit;
         if (c->far_movers) {
             QPIC_TRY(dev_alloc(c, &c->far_cnt[0], n2));
             QPIC_TRY(dev_alloc(c, &c->far_cnt[1], n2));
@@ -1671,9 +1562,6 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD((k_tile_deposit<2, false>));
         QPIC_PRELOAD((k_tile_deposit<3, false>));
         QPIC_PRELOAD((k_tile_deposit<2, true, true>));
-        QPIC_PRELOAD(k_tile_bin_deposit<0>);
-        QPIC_PRELOAD(k_tile_bin_deposit<1>);
-        QPIC_PRELOAD(k_tile_list_deposit);
         QPIC_PRELOAD(k_tile_stay_deposit);
         QPIC_PRELOAD(k_tile_cell_deposit);
         QPIC_PRELOAD(k_particles_predict_dep<false>);
@@ -2102,29 +1990,6 @@ int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inou
     QPIC_CUDA(c, cudaSetDevice(c->prm.device));
     const size_t n2 = (size_t)c->g.n2;
     const int ny = c->g.ny, nz = c->g.nz;
-#ifndef QPIC_EMU
-    if (c->fused.on) {
-        // the sweep's own kernel (k_p2_solve_b with ready-made sources): (a, b) interleaved into one complex array on the host
-        if (!c->pair_src) QPIC_TRY(dev_alloc(c, &c->pair_src, n2, false));
-        std::vector<double2> h(n2);
-        for (size_t t = 0; t < n2; t++) h[t] = make_double2(inout_a[t], inout_b[t]);
-        QPIC_CUDA(c, cudaMemcpyAsync(c->pair_src, h.data(), sizeof(double2) * n2, cudaMemcpyHostToDevice, c->stream));
-        const double * inv = nullptr;
-        QPIC_TRY(get_inv_symbol(c, D, true, &inv));
-        const SolveShape S = {c->fz.plan.log2n, c->fy.plan.log2n, c->fused.log2spb_rows, c->fused.log2spb_cols};
-        QPIC_LAUNCH_COOP(k_p2_solve_b<true>, c->fused.grid_b, c->fused.threads, c->fused.smem, c->stream, c->ctl_scratch, S, (const double2 *)c->fz.tw,
-                         (const double2 *)c->fy.tw, c->g, D, c->fft_in, c->fft_in2, (const double *)nullptr, (const double *)nullptr, (const double *)nullptr,
-                         (const double *)nullptr, (const double *)nullptr, (const double2 *)c->pair_src, c->spec, inv, c->fused.bar,
-                         std::numeric_limits<double>::infinity(), 0, c->inv_scale);
-        QPIC_TRY(check_launch(c, "k_fft_solve_b"));
-        QPIC_CUDA(c, cudaMemcpyAsync(inout_a, c->fft_in, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
-        QPIC_CUDA(c, cudaMemcpyAsync(inout_b, c->fft_in2, sizeof(double) * n2, cudaMemcpyDeviceToHost, c->stream));
-        QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
-        QPIC_CUDA(c, cudaMemsetAsync(c->ctl_scratch, 0, sizeof(Ctl), c->stream));
-        QPIC_CUDA(c, cudaStreamSynchronize(c->stream));
-        return QPIC_OK;
-    }
-#endif
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in, inout_a, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
     QPIC_CUDA(c, cudaMemcpyAsync(c->fft_in2, inout_b, sizeof(double) * n2, cudaMemcpyHostToDevice, c->stream));
     {

@@ -494,332 +494,4 @@ __global__ void P2_BOUNDS k_p2_rows_c2c(int log2n, const double2 * __restrict__ 
     }
 }
 
-
-// ================================================================================================ one kernel per solve
-// Single GPU, both axes on the power-of-two engine: rows -> columns (forward, x 1/symbol, backward) -> rows of ONE solve run as the
-// three phases of one cooperatively launched kernel with a grid-wide barrier between them, instead of three launches (33 -> 11
-// transform launches per slice at M = 5).  A 512 x 512 transform is ~4 warps of work per SM and entirely latency bound: what the
-// fusion removes per solve is two kernel boundaries (drain + ~1.4 us launch gap + ramp-up + cold L1 / instruction fetch) for
-// two barriers of well under a microsecond each.  The spectrum still travels through global memory between the phases, but it
-// never leaves L2 (2 - 4 MB), and it is read back with ld.global.cg: L2 is the point of coherence between the SMs.
-//
-// Thread layout: blockDim.x = T threads, the same for all phases; a "unit" of work is what one block does at a time:
-//   row phases     spb_rows = T / (nz/8) sequences, back to back in shared memory (thread = (sequence b, lane t), t fastest);
-//   column phase   spb_cols = T / (ny/8) ADJACENT columns, interleaved in shared memory (thread = (lane t, column b), b fastest), so that
-//                  the lanes of a warp read / write spb_cols * 16 contiguous bytes of a spectrum row: full 32-byte sectors from two
-//                  columns on (the one-column-per-64-threads layout of k_p2_cols_solve uses half of every sector it touches).
-// Blocks loop over units (grid <= the number of co-resident blocks), so any grid size works.
-#ifndef QPIC_EMU
-struct SolveShape {
-    int log2nz, log2ny;
-    int log2spb_rows, log2spb_cols;
-};
-
-__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int * p) {
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// bar[0]: arrival count, bar[1]: generation.  Self-resetting (the last block to arrive zeroes the count BEFORE it bumps the
-// generation), so the same two words serve every barrier of every launch.  Needs all blocks of the grid co-resident: the
-// kernels that use it are launched with cudaLaunchAttributeCooperative.
-__device__ __forceinline__ void grid_barrier(unsigned int * bar) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int gen = ld_relaxed_u32(bar + 1);  // read before arriving: the generation cannot move until this block has arrived
-        __threadfence();                                   // release: this block's stores (ordered before by the barrier above) are visible
-        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-            atomicExch(bar, 0u);
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            // bounded (a few seconds): a block that could never become resident must not hang the device; giving up leaves garbage in
-            // a sweep whose results the parity tests would reject, but returns the GPU
-            for (long spins = 0; ld_relaxed_u32(bar + 1) == gen && spins < (1L << 24); spins++) {
-            }
-        }
-        __threadfence();  // acquire
-    }
-    __syncthreads();
-}
-
-struct P2Lane {
-    int b, t, e8, stride;
-    double2 *xa, *xb;
-};
-
-// sequences back to back (row phases)
-__device__ __forceinline__ P2Lane p2_lane_rows(double2 * sm, int log2n) {
-    P2Lane L;
-    const int le8 = log2n - 3;
-    const int plen = p2_pad_len(1 << log2n);
-    L.e8 = 1 << le8;
-    L.b = threadIdx.x >> le8;
-    L.t = threadIdx.x & (L.e8 - 1);
-    L.stride = 1;
-    L.xa = sm + (size_t)L.b * 2 * plen;
-    L.xb = L.xa + plen;
-    return L;
-}
-
-// sequences interleaved, sequence index fastest over the threads (column phase)
-__device__ __forceinline__ P2Lane p2_lane_cols(double2 * sm, int log2n, int log2spb) {
-    P2Lane L;
-    const int plen = p2_pad_len(1 << log2n);
-    L.e8 = 1 << (log2n - 3);
-    L.b = threadIdx.x & ((1 << log2spb) - 1);
-    L.t = threadIdx.x >> log2spb;
-    L.stride = 1 << log2spb;
-    L.xa = sm + L.b;
-    L.xb = L.xa + ((size_t)plen << log2spb);
-    return L;
-}
-
-__device__ __forceinline__ double2 ldcg2(const double2 * p) { return __ldcg(p); }
-
-// ---- phase bodies (one unit each; the caller loops over units and separates them with __syncthreads())
-
-// two real rows per sequence -> half spectra spec[ny][nzh]
-__device__ __forceinline__ void p2_unit_rows_r2c(const P2Lane & L, int log2nz, const double2 * __restrict__ twz, const double * __restrict__ src,
-                                                 double2 * __restrict__ spec, int ny, int pair) {
-    const int nz = 1 << log2nz, nzh = nz / 2 + 1;
-    const int j0 = 2 * pair;
-    const bool live = j0 < ny;
-    double2 v[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int k = L.t + e * L.e8;
-        v[e] = live ? make_double2(src[(size_t)j0 * nz + k], src[(size_t)(j0 + 1) * nz + k]) : make_double2(0.0, 0.0);
-    }
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2nz, twz);
-    __syncthreads();
-    double2 * z = L.xa;
-#pragma unroll
-    for (int e = 0; e < 8; e++) z[p2_pad(L.t + e * L.e8)] = v[e];
-    __syncthreads();
-    if (!live) return;
-    for (int k = L.t; k < nzh; k += L.e8) {
-        const double2 zk = z[p2_pad(k)];
-        const double2 zm = z[p2_pad(k == 0 ? 0 : nz - k)];
-        // U0 = (Z_k + conj(Z_{n-k})) / 2,  U1 = (Z_k - conj(Z_{n-k})) / (2i)
-        spec[(size_t)j0 * nzh + k] = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
-        spec[(size_t)(j0 + 1) * nzh + k] = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
-    }
-}
-
-// column k: forward, x 1 / symbol, backward; optionally U(0,k) and sum_j U(j,k) for the fused potential fix-up (see k_p2_rows_c2r)
-__device__ __forceinline__ void p2_unit_cols(const P2Lane & L, int log2ny, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
-                                             const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum, int k) {
-    const bool live = k < ncols;
-    const int ny = 1 << log2ny;
-    double2 v[8];
-    double rinv[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = live ? ldcg2(spec + (size_t)(L.t + e * L.e8) * ld + k) : make_double2(0.0, 0.0);
-#pragma unroll
-    for (int e = 0; e < 8; e++) rinv[e] = live ? inv_symbol[(size_t)k * ny + L.t + e * L.e8] : 0.0;
-    fft_pow2_regs<false>(v, L.xa, L.xb, L.t, log2ny, twy, L.stride);
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int j = L.t + e * L.e8;
-        v[e] = (j == 0 && k == 0) ? make_double2(0.0, 0.0) : make_double2(v[e].x * rinv[e], v[e].y * rinv[e]);
-    }
-    if (row0 && live && L.t == 0) row0[k] = v[0];
-    __syncthreads();  // the forward transform's last exchange buffer may still be read by slower threads
-    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2ny, twy, L.stride);
-    if (live) {
-#pragma unroll
-        for (int e = 0; e < 8; e++) spec[(size_t)(L.t + e * L.e8) * ld + k] = v[e];
-        if (colsum && L.t == 0) colsum[k] = v[0];
-    }
-}
-
-// two half spectra -> two real rows, scaled; with fix != 0 the potential fix-up (border mean, clamp) is applied, see k_p2_rows_c2r
-__device__ __forceinline__ void p2_unit_rows_c2r(const P2Lane & L, int log2nz, const double2 * __restrict__ twz, const double2 * __restrict__ spec,
-                                                 double * __restrict__ dst, int ny, int pair, double inv_scale, int fix, double mean, double floor_value) {
-    const int nz = 1 << log2nz, nzh = nz / 2 + 1;
-    const int j0 = 2 * pair;
-    const bool live = j0 < ny;
-    double2 v[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int i = L.t + e * L.e8;
-        const bool mirror = i > nz / 2;
-        const int k = mirror ? nz - i : i;
-        double2 v0 = live ? ldcg2(spec + (size_t)j0 * nzh + k) : make_double2(0.0, 0.0);
-        double2 v1 = live ? ldcg2(spec + (size_t)(j0 + 1) * nzh + k) : make_double2(0.0, 0.0);
-        if (k == 0 || 2 * k == nz) {
-            v0.y = 0.0;
-            v1.y = 0.0;
-        }
-        v[e] = mirror ? make_double2(v0.x + v1.y, v1.x - v0.y) : make_double2(v0.x - v1.y, v0.y + v1.x);
-    }
-    fft_pow2_regs<true>(v, L.xa, L.xb, L.t, log2nz, twz);
-    if (!live) return;
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int k = L.t + e * L.e8;
-        double a = scale_result(v[e].x, ny, nz, inv_scale), b = scale_result(v[e].y, ny, nz, inv_scale);
-        if (fix) {
-            a -= mean;
-            b -= mean;
-            if (a < floor_value) a = floor_value;
-            if (b < floor_value) b = floor_value;
-        }
-        dst[(size_t)j0 * nz + k] = a;
-        dst[(size_t)(j0 + 1) * nz + k] = b;
-    }
-}
-
-// (laplacian - D) u = src on the (ny, nz) grid; fix: u <- max(u - border mean, floor) (src/System_3d.cpp:686-706, :30-47, :830-841)
-__global__ void __launch_bounds__(512)
-    k_p2_solve_real(const Ctl * ctl, SolveShape S, const double2 * __restrict__ twz, const double2 * __restrict__ twy, const double * __restrict__ src,
-                    double2 * __restrict__ spec, double * __restrict__ dst, const double * __restrict__ inv_symbol, double2 * __restrict__ row0,
-                    double2 * __restrict__ colsum, unsigned int * bar, double inv_scale, int fix, double floor_value) {
-    QPIC_KERNEL_BEGIN(KID_k_p2_solve_real);
-    QPIC_DYN_SMEM(double2, sm);
-    // A cancelled sweep skips the work but still meets at the barriers: nothing that runs concurrently with a solve changes the flags,
-    // so all blocks decide alike -- and if that ever stopped being true the price would be garbage in a cancelled slice, not a hang.
-    const bool dead = cancelled(ctl);
-    const int nz = 1 << S.log2nz, ny = 1 << S.log2ny, nzh = nz / 2 + 1;
-    if (!dead) {
-        const P2Lane L = p2_lane_rows(sm, S.log2nz);
-        const int npairs = ny >> 1;
-        for (int u = blockIdx.x; (u << S.log2spb_rows) < npairs; u += gridDim.x) {
-            p2_unit_rows_r2c(L, S.log2nz, twz, src, spec, ny, (u << S.log2spb_rows) + L.b);
-            __syncthreads();
-        }
-    }
-    grid_barrier(bar);
-    if (!dead) {
-        const P2Lane L = p2_lane_cols(sm, S.log2ny, S.log2spb_cols);
-        for (int u = blockIdx.x; (u << S.log2spb_cols) < nzh; u += gridDim.x) {
-            p2_unit_cols(L, S.log2ny, twy, spec, nzh, nzh, inv_symbol, fix ? row0 : nullptr, fix ? colsum : nullptr, (u << S.log2spb_cols) + L.b);
-            __syncthreads();
-        }
-    }
-    grid_barrier(bar);
-    if (!dead) {
-        const P2Lane L = p2_lane_rows(sm, S.log2nz);
-        double mean = 0.0;
-        if (fix) {
-            // Hermitian-weighted sums of Re U(0,k) and Re sum_j U(j,k) over the half spectrum; every warp of every block reduces the
-            // nz/2+1 per-column values in the same fixed order (lane l takes columns l, l + 32, ... ascending, then an xor tree), so all
-            // threads subtract bit-identical means.  Lanes of a partial last warp see the same values through the tree over W lanes.
-            const int lane = threadIdx.x & 31;
-            const int rem = blockDim.x & 31;
-            const int W = rem == 0 ? 32 : (rem >= 16 ? 16 : 8);
-            const unsigned mask = __activemask();
-            double pa = 0.0, pb = 0.0;
-            if (lane < W) {
-                for (int kk = lane; kk <= nz / 2; kk += W) {
-                    const double wgt = (kk == 0 || 2 * kk == nz) ? 1.0 : 2.0;
-                    pa += wgt * ldcg2(row0 + kk).x;
-                    pb += wgt * ldcg2(colsum + kk).x;
-                }
-            }
-            for (int o = W >> 1; o > 0; o >>= 1) {
-                pa += __shfl_xor_sync(mask, pa, o);
-                pb += __shfl_xor_sync(mask, pb, o);
-            }
-            pa = __shfl_sync(mask, pa, 0);
-            pb = __shfl_sync(mask, pb, 0);
-            const double pc = ldcg2(colsum).x;
-            const double s_col0 = pa / nz;          // sum_j u(j,0)
-            const double s_row0 = pc / ny;          // sum_k u(0,k)
-            const double u00 = pb / ny / nz;        // u(0,0), counted in both
-            mean = (s_col0 + s_row0 - u00) / (ny + nz - 1);
-        }
-        const int npairs = ny >> 1;
-        for (int u = blockIdx.x; (u << S.log2spb_rows) < npairs; u += gridDim.x) {
-            p2_unit_rows_c2r(L, S.log2nz, twz, spec, dst, ny, (u << S.log2spb_rows) + L.b, inv_scale, fix, mean, floor_value);
-            __syncthreads();
-        }
-    }
-}
-
-// By + i Bz in one complex Helmholtz solve, sources to stop test (src/System_3d.cpp:529-580)
-template <bool PRE>
-__global__ void __launch_bounds__(512)
-    k_p2_solve_b(Ctl * ctl, SolveShape S, const double2 * __restrict__ twz, const double2 * __restrict__ twy, Geom g, double D, double * __restrict__ by,
-                 double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy, const double * __restrict__ jz,
-                 const double * __restrict__ jy_next, const double * __restrict__ jz_next, const double2 * __restrict__ b_src, double2 * __restrict__ spec,
-                 const double * __restrict__ inv_symbol, unsigned int * bar, double threshold, int iteration, double inv_scale) {
-    QPIC_KERNEL_BEGIN(KID_k_p2_solve_b);
-    QPIC_DYN_SMEM(double2, sm);
-    // (read once, before this kernel's own backward rows can raise the stop tag; see k_p2_solve_real)
-    const bool dead = cancelled(ctl);
-    const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
-    const int nz = g.nz, ny = g.ny;
-    if (!dead) {
-        const P2Lane L = p2_lane_rows(sm, S.log2nz);
-        for (int u = blockIdx.x; (u << S.log2spb_rows) < ny; u += gridDim.x) {
-            const int j = (u << S.log2spb_rows) + L.b;
-            const bool live = j < ny;
-            const int jp = live ? wrap_inc(j, ny) : 0;
-            const int jq = (j == ny - 1) ? 0 : j;
-            double2 v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int k = L.t + e * L.e8;
-                if (live && PRE) {
-                    v[e] = b_src[(size_t)j * nz + k];
-                } else if (live) {
-                    const int t = j * nz + k;
-                    const int kp = wrap_inc(k, nz);
-                    const double djz_dxi = (jz[t] - jz_next[t]) * g.inv_dx;
-                    const double djy_dxi = (jy[t] - jy_next[t]) * g.inv_dx;
-                    const double jxt = jx[t];
-                    v[e] = make_double2(-D * by[t] - (jx[j * nz + kp] - jxt) * g.inv_dz + djz_dxi, -D * bz[jq * nz + k] + (jx[jp * nz + k] - jxt) * g.inv_dy - djy_dxi);
-                } else {
-                    v[e] = make_double2(0.0, 0.0);
-                }
-            }
-            fft_pow2_regs<false>(v, L.xa, L.xb, L.t, S.log2nz, twz);
-            if (live) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) spec[(size_t)j * nz + L.t + e * L.e8] = v[e];
-            }
-            __syncthreads();
-        }
-    }
-    grid_barrier(bar);
-    if (!dead) {
-        const P2Lane L = p2_lane_cols(sm, S.log2ny, S.log2spb_cols);
-        for (int u = blockIdx.x; (u << S.log2spb_cols) < nz; u += gridDim.x) {
-            p2_unit_cols(L, S.log2ny, twy, spec, nz, nz, inv_symbol, nullptr, nullptr, (u << S.log2spb_cols) + L.b);
-            __syncthreads();
-        }
-    }
-    grid_barrier(bar);
-    if (!dead) {
-        const P2Lane L = p2_lane_rows(sm, S.log2nz);
-        bool bad = false;
-        for (int u = blockIdx.x; (u << S.log2spb_rows) < ny; u += gridDim.x) {
-            const int j = (u << S.log2spb_rows) + L.b;
-            const bool live = j < ny;
-            double2 v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[e] = live ? ldcg2(spec + (size_t)j * nz + L.t + e * L.e8) : make_double2(0.0, 0.0);
-            fft_pow2_regs<true>(v, L.xa, L.xb, L.t, S.log2nz, twz);
-            if (live) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int k = L.t + e * L.e8;
-                    const double vy = scale_result(v[e].x, ny, nz, inv_scale);
-                    const double vz = scale_result(v[e].y, ny, nz, inv_scale);
-                    by[(size_t)j * nz + k] = vy;
-                    bz[(size_t)j * nz + k] = vz;
-                    // !(|v| <= threshold) is true for |v| > threshold and for NaN
-                    if (!(fabs(vy) <= threshold) || !(fabs(vz) <= threshold)) bad = true;
-                }
-            }
-            __syncthreads();
-        }
-        if (bad) atomicExch(&ctl->stop_tag, my_tag);
-    }
-}
-#endif  // QPIC_EMU
-
 }  // namespace qpic

@@ -75,11 +75,9 @@ enum KernelId {
     KID_k_bunch_advance,
     KID_k_bunch_advance_qed,
     KID_k_bunch_photon_compact,
-    KID_k_p2_solve_real,
-    KID_k_p2_solve_b,
     KID_COUNT
 };
-#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack", "k_xy_cut", "k_xy_lines", "k_bunch_locate_count", "k_bunch_scan_apply", "k_bunch_fill", "k_bunch_rank", "k_bunch_deposit", "k_bunch_gather", "k_bunch_advance", "k_bunch_advance_qed", "k_bunch_photon_compact", "k_p2_solve_real", "k_p2_solve_b" }
+#define QPIC_KERNEL_NAMES { "k_init_a_sqr", "k_locate_count", "k_scan_chunk_sums", "k_scan_sums", "k_scan_apply", "k_sort_fill", "k_sort_rank", "k_deposit_charge", "k_deposit_jx_rho_chi", "k_deposit_jy_jz", "k_potential_fixup", "k_particles_to_slots", "k_particles_gamma", "k_particles_predict", "k_particles_currents_yz", "k_particles_advance", "k_end_of_slice", "k_next_slice", "k_tile_deposit", "k_fft_rows_r2c", "k_fft_rows_c2r", "k_fft_cols_solve", "k_fft_rows_b_forward", "k_fft_rows_b_backward", "k_fft_rows_c2c", "k_p2_rows_r2c", "k_p2_rows_c2r", "k_p2_cols_solve", "k_p2_rows_b_forward", "k_p2_rows_b_backward", "k_p2_rows_c2c", "k_xchg_barrier", "k_halo_reduce_send", "k_halo_reduce_add", "k_halo_fill", "k_migrate_publish", "k_migrate_unpack", "k_xy_cut", "k_xy_lines", "k_bunch_locate_count", "k_bunch_scan_apply", "k_bunch_fill", "k_bunch_rank", "k_bunch_deposit", "k_bunch_gather", "k_bunch_advance", "k_bunch_advance_qed", "k_bunch_photon_compact" }
 
 #ifdef QPIC_EMU
 #define QPIC_KERNEL_BEGIN(id) ((void)0)
@@ -1248,14 +1246,13 @@ __global__ void k_xy_lines(const Ctl * ctl, Geom g, XyLines o, XyCut node, XyCut
 // atomics, no dependence on scheduling: bit-reproducible.
 //
 //   k_tile_deposit       deposits at (y,z): the target cell IS the source cell, a thread walks its own cell's particles.
-//   k_tile_bin_deposit   deposits at the half-step position: a particle moves by at most one cell per half step (checked by
-//                        the predictor, Ctl::fast_fail), so the particles that can land in the block's target cells sit in
-//                        its source cells = targets + 1 ring (+1 more on the high side of a half-cell staggered grid).
-//                        Phase A: one thread per SOURCE cell reads the packed offset codes of its particles and appends
-//                        each slot to the list of its target cell in shared memory (integer atomics -- only the order of
-//                        the list depends on scheduling).  Phase B: one thread per TARGET cell sorts its short list by slot
-//                        (canonical order) and accumulates.  Lists longer than BIN_K fall back to an in-order scan of the
-//                        source window.  Every particle visit is useful work: no divergent window scans.
+//   half-step deposits   (k_tile_stay_deposit / k_tile_assemble for the psi_middle source, k_tile_cell_deposit for jy / jz): ~98 % of the particles
+//                        end their half step in the cell they started in and are summed in place; the movers are binned per TARGET cell
+//                        (integer atomics -- only the order of a list depends on scheduling), the target cell sorts its short list by slot
+//                        (canonical order) and accumulates movers from lower cells, its stayers, movers from higher cells.  Lists longer
+//                        than BIN_K fall back to an in-order scan of the source window.  (Rounds 1-2 went through three earlier
+//                        generations -- presence-mask window scans, k_tile_bin_deposit, k_tile_list_deposit -- that are documented in
+//                        DESIGN.md section 4.1 and live in the commit history.)
 constexpr int TILE = 16;
 constexpr int TILE_ACC = TILE + 1;
 constexpr int TILE_CELLS = TILE_ACC * TILE_ACC;
@@ -1283,8 +1280,8 @@ struct TileJob {
     TileOutput o[TILE_MAX_OUT];
     const double *jxb3, *rhob3, *rho_ion;  // for bg_mode 1
     const double *psi_mid, *nw;            // jy/jz job
-    // Per-cell lists of the half-step positions, left in global memory by the psi_middle source deposit (k_tile_bin_deposit<0>)
-    // for the jy/jz deposit of the same iteration (k_tile_list_deposit): bin_cnt[cell] entries bin_lst[i * n2 + cell], sorted by
+    // Per-cell MOVER lists of the half-step positions, left in global memory by the psi_middle source kernel (k_tile_stay_deposit /
+    // k_tile_assemble) for the jy/jz deposit of the same iteration (k_tile_cell_deposit): bin_cnt[cell] entries bin_lst[i * n2 + cell], sorted by
     // slot, entry = slot << 2 | hy << 1 | hz; a count above BIN_K means "not listed, scan the window".  list_row0 / list_rows:
     // the cell rows whose lists were written (all of them on a single GPU).
     int * bin_cnt;
@@ -1353,8 +1350,17 @@ __device__ __forceinline__ void tile_store_nodes(const Ctl * ctl, const Geom & g
 
 // RHO_CHI (NOUT = 2): the outputs are rho and susceptibility(i) and the deposited values n / (1 - px/gamma), -n / (1 - px/gamma) / gamma
 // (src/System_3d.cpp:520-527, same expressions as store_currents) are formed here from the corrector's gamma, px.
+#ifndef QPIC_TD_MINB
+#define QPIC_TD_MINB 0
+#endif
 template <int NOUT, bool FINAL_PASS, bool RHO_CHI = false>
-__global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+__global__ void
+#if QPIC_TD_MINB > 0
+    __launch_bounds__(TILE_CELLS, QPIC_TD_MINB)
+#else
+    __launch_bounds__(TILE_CELLS)
+#endif
+    k_tile_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
     QPIC_KERNEL_BEGIN(KID_COUNT + (job.o[0].bg_mode == 2 ? 2 : 0) + (FINAL_PASS ? 8 : 0));
     // (the control block is tested after the particle loop: see k_particles_predict)
     __shared__ double acc[NOUT * 4 * TILE_CELLS];
@@ -1429,337 +1435,13 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_deposit(const Ctl * ctl, Ge
     tile_store_nodes<NOUT>(ctl, g, job, acc, ay, az, jt, kt, ion);
 }
 
-// MODE 0: psi_middle source = jx_bunch(i) - rho_bunch(i) - rho_ion + deposit(-n) at the half-step positions (src/System_3d.cpp:446-457)
-// MODE 1: (jy_next, jz_next), staggered by half a cell in y / z (src/System_3d.cpp:472-486, :190-193); the deposited values
-//         n py_next / (1 + psi_middle@particle), n pz_next / (1 + psi_middle@particle) (:483-485) are formed here; o[0].val /
-//         o[1].val hold py_next / pz_next.
-// Block = (TILE_ACC + 2 + MODE) x (TILE_ACC + 2 + MODE) threads: thread (sy, sz) <-> source cell (j0 - 2 + sy, k0 - 2 + sz) in phase
-// A, <-> target cell (j0 - 2 + sy, k0 - 2 + sz) for 1 <= sy, sz <= TILE_ACC in phase B (j0, k0: first node of the patch).
-// software pipeline in phase B of k_tile_bin_deposit<0>: measured slower (0.732 vs 0.726 ms/slice on config #2), stays off
-#ifndef QPIC_BIN_PIPE
-#define QPIC_BIN_PIPE 0
-#endif
-// (Timing-only A/B builds of k_tile_bin_deposit<0> on config #2: without the accumulation visits of phase B the slice is 17 us
-// shorter, without publishing the lists 6 us: about 12 of its 16 us per launch are phase A, the sort and the launch itself.)
-template <int MODE>
-inline size_t tile_bin_smem_bytes() {
-    constexpr int NOUT = MODE == 0 ? 1 : 2;
-    return (size_t)NOUT * TILE_CELLS * (4 * sizeof(double) + (BIN_K + 1) * sizeof(int));
-}
-
-template <int MODE>
-__global__ void __launch_bounds__((TILE_ACC + 2 + MODE) * (TILE_ACC + 2 + MODE))
-    k_tile_bin_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
-    QPIC_KERNEL_BEGIN(KID_COUNT + 1 + 4 * MODE);
-    // (The control block is tested before the final stores only: see k_particles_predict.  Splitting the two outputs of
-    // MODE 1 over separate blocks was measured slower: 36.9 vs 34.8 us.)
-    constexpr int NOUT = MODE == 0 ? 1 : 2;
-    QPIC_DYN_SMEM(double, acc);                                            // [NOUT][4][TILE_CELLS]
-    int * cnt = reinterpret_cast<int *>(acc + NOUT * 4 * TILE_CELLS);      // [NOUT][TILE_CELLS]
-    int * lst = cnt + NOUT * TILE_CELLS;                                   // [NOUT][BIN_K][TILE_CELLS]
-    const int sy = threadIdx.y, sz = threadIdx.x;
-    const int nthreads = blockDim.x * blockDim.y, tid = sy * blockDim.x + sz;
-    const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
-    const int ju = j0 - 2 + sy, ku = k0 - 2 + sz;  // unwrapped cell of this thread
-    // staggering of output a in y / z
-    auto stag_y = [](int a) { return MODE == 1 && a == 0; };
-    auto stag_z = [](int a) { return MODE == 1 && a == 1; };
-
-    for (int i = tid; i < NOUT * TILE_CELLS; i += nthreads) cnt[i] = 0;
-    const double ion = tile_prefetch_ion<NOUT>(g, job, sy - 1, sz - 1, ju, ku);
-    __syncthreads();
-
-    // ---- phase A: bin the particles of this source cell
-    {
-        const int cell = wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz);
-        const int s0 = start[cell], s1 = start[cell + 1];
-        for (int sb = s0; sb < s1; sb += 4) {
-            int code[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) code[u] = P.off_m[sb + u < s1 ? sb + u : s0];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (sb + u >= s1) break;
-                const int oy = (code[u] & 7) - 2, oz = ((code[u] >> 3) & 7) - 2;
-                const int hy = (code[u] >> 6) & 1, hz = (code[u] >> 7) & 1;
-                if ((code[u] & 63) == FAR_CODE) continue;  // (never produced on the paths that use this kernel)
-#pragma unroll
-                for (int a = 0; a < NOUT; a++) {
-                    // on a staggered grid a particle in the lower half of its cell belongs to the staggered cell below
-                    const int ty = sy - 1 + oy - ((stag_y(a) && !hy) ? 1 : 0);
-                    const int tz = sz - 1 + oz - ((stag_z(a) && !hz) ? 1 : 0);
-                    if (ty >= 0 && ty < TILE_ACC && tz >= 0 && tz < TILE_ACC) {
-                        const int t = ty * TILE_ACC + tz;
-                        const int pos = atomicAdd(&cnt[a * TILE_CELLS + t], 1);
-                        if (pos < BIN_K) lst[(a * BIN_K + pos) * TILE_CELLS + t] = ((sb + u) << 2) | (hy << 1) | hz;
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B: ordered accumulation per target cell
-    const bool is_target = sy >= 1 && sy <= TILE_ACC && sz >= 1 && sz <= TILE_ACC;
-    const int ty = sy - 1, tz = sz - 1;
-    const int tcell = ty * TILE_ACC + tz;
-    if (is_target) {
-#pragma unroll
-        for (int a = 0; a < NOUT; a++) {
-            double c00 = 0.0, c10 = 0.0, c01 = 0.0, c11 = 0.0;
-            const double * __restrict__ val = job.o[a].val;
-            auto visit = [&](int s, int hy, int hz) {
-                const double2 fm = P.fyz_m[s];
-                const double fy = fm.x, fz = fm.y;
-                double v;
-                if (MODE == 1) {
-                    // psi_middle at the particle: its own (unstaggered) half-step cell.  (Staging the block's psi_middle tile in shared
-                    // memory was measured slower: 37.0 vs 34.7 us -- the gather hits L1 anyway and the extra registers spill.)
-                    const int jm = wrap_near(ju + ((stag_y(a) && !hy) ? 1 : 0), g.ny), km = wrap_near(ku + ((stag_z(a) && !hz) ? 1 : 0), g.nz);
-                    const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jm, km, fy, fz);
-                    const double2 pn = P.pyzn[s];  // (MODE 1: output 0 deposits py_next, output 1 pz_next)
-                    v = job.nw[s] * (a == 0 ? pn.x : pn.y) / w;
-                } else {
-                    v = job.o[a].sign * val[s];
-                }
-                const double wy = stag_y(a) ? (hy ? fy - 0.5 : fy + 0.5) : fy;
-                const double wz = stag_z(a) ? (hz ? fz - 0.5 : fz + 0.5) : fz;
-                c00 += v * (1 - wy) * (1 - wz);
-                c10 += v * wy * (1 - wz);
-                c01 += v * (1 - wy) * wz;
-                c11 += v * wy * wz;
-            };
-            const int n = cnt[a * TILE_CELLS + tcell];
-            if (MODE == 0 && job.bin_cnt) job.bin_cnt[wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz)] = n;  // (halo cells: same value from the neighbour block)
-            int * mine = lst + a * BIN_K * TILE_CELLS + tcell;  // entry i at mine[i * TILE_CELLS]
-            if (n <= BIN_K) {
-                // insertion sort: ascending slot = canonical order
-                for (int i = 1; i < n; i++) {
-                    const int e = mine[i * TILE_CELLS];
-                    int q = i - 1;
-                    while (q >= 0 && mine[q * TILE_CELLS] > e) {
-                        mine[(q + 1) * TILE_CELLS] = mine[q * TILE_CELLS];
-                        q--;
-                    }
-                    mine[(q + 1) * TILE_CELLS] = e;
-                }
-                if (MODE == 0 && QPIC_BIN_PIPE) {
-                    // software pipeline: the particle data of entry i+1 is in flight while entry i is accumulated (the entries
-                    // themselves sit in shared memory); 40 registers without it, so there is room
-                    const int pub = wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz);
-                    int e = n > 0 ? mine[0] : 0;
-                    double fy = 0.0, fz = 0.0, pv = 0.0;
-                    if (n > 0) {
-                        const int s = e >> 2;
-                        const double2 fm = P.fyz_m[s];
-                        fy = fm.x, fz = fm.y, pv = val[s];
-                    }
-                    for (int i = 0; i < n; i++) {
-                        const int ce = e;
-                        const double cfy = fy, cfz = fz, cv = job.o[a].sign * pv;
-                        if (i + 1 < n) {
-                            e = mine[(i + 1) * TILE_CELLS];
-                            const int s = e >> 2;
-                            const double2 fm = P.fyz_m[s];
-                            fy = fm.x, fz = fm.y, pv = val[s];
-                        }
-                        c00 += cv * (1 - cfy) * (1 - cfz);
-                        c10 += cv * cfy * (1 - cfz);
-                        c01 += cv * (1 - cfy) * cfz;
-                        c11 += cv * cfy * cfz;
-                        if (job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + pub] = ce;
-                    }
-                } else {
-                    for (int i = 0; i < n; i++) {
-                        const int e = mine[i * TILE_CELLS];
-                        visit(e >> 2, (e >> 1) & 1, e & 1);
-                        if (MODE == 0 && job.bin_cnt) job.bin_lst[(size_t)i * g.n2 + wrap_near(ju, g.ny) * g.nz + wrap_near(ku, g.nz)] = e;
-                    }
-                }
-            } else {
-                // crowded target (strong compression): scan the source window in order
-                const int hi_y = stag_y(a) ? 2 : 1, hi_z = stag_z(a) ? 2 : 1;
-                for (int dy_ = -1; dy_ <= hi_y; dy_++) {
-                    for (int dz_ = -1; dz_ <= hi_z; dz_++) {
-                        const int cell = mod_wrap(ju + dy_, g.ny) * g.nz + mod_wrap(ku + dz_, g.nz);
-                        const int e1 = start[cell + 1];
-                        for (int s = start[cell]; s < e1; s++) {
-                            const int code = P.off_m[s];
-                            const int hy = (code >> 6) & 1, hz = (code >> 7) & 1;
-                            const int ry = dy_ + (code & 7) - 2 - ((stag_y(a) && !hy) ? 1 : 0);
-                            const int rz = dz_ + ((code >> 3) & 7) - 2 - ((stag_z(a) && !hz) ? 1 : 0);
-                            if (ry == 0 && rz == 0) visit(s, hy, hz);
-                        }
-                    }
-                }
-            }
-            double * acc_a = acc + a * 4 * TILE_CELLS;
-            acc_a[0 * TILE_CELLS + tcell] = c00;
-            acc_a[1 * TILE_CELLS + tcell] = c10;
-            acc_a[2 * TILE_CELLS + tcell] = c01;
-            acc_a[3 * TILE_CELLS + tcell] = c11;
-        }
-    }
-    QPIC_KERNEL_TAIL();
-    __syncthreads();
-    if (cancelled(ctl)) return;
-    if (is_target) tile_store_nodes<NOUT>(ctl, g, job, acc, ty, tz, ju, ku, ion);
-}
-
-// jy_next (staggered by dy/2 in y) and jz_next (dz/2 in z) from the lists the psi_middle source deposit of the same iteration
-// published (src/System_3d.cpp:472-486, :190-193).  Thread = target cell (jt, kt) of BOTH outputs:
-//   list of cell (jt, kt):     upper-half-in-y particles -> jy target (jt, kt);  upper-half-in-z particles -> jz target (jt, kt)
-//   list of cell (jt+1, kt):   lower-half-in-y particles -> jy target (jt, kt)   (they belong to the staggered cell below)
-//   list of cell (jt, kt+1):   lower-half-in-z particles -> jz target (jt, kt)
-// each list in slot order, lists in this order: deterministic.  No binning, no sort, no halo source cells, and a particle
-// of cell (jt, kt) that feeds both outputs gets its 1 / (1 + psi_middle) gather once.  Deposited values as in
-// k_tile_bin_deposit<1>: n py_next / (1 + psi_middle@particle), n pz_next / (1 + psi_middle@particle) (:483-485).
-// (Timing-only A/B builds on config #2: the two neighbour lists cost 11 us of this kernel's 29.5 us per launch, the psi_middle gather
-// of the own-cell list 2.8 us -- which led to k_tile_cell_deposit below, now the single-GPU default.)
-#ifndef QPIC_LIST_MINB
-#define QPIC_LIST_MINB 3  // 64 registers: measured 0.794 ms/slice vs 0.931 (90 registers, 2 blocks / SM) and 0.829 (48, spills)
-#endif
-__global__ void __launch_bounds__(TILE_CELLS, QPIC_LIST_MINB) k_tile_list_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
-    QPIC_KERNEL_BEGIN(KID_COUNT + 5);
-    __shared__ double acc[2 * 4 * TILE_CELLS];
-    const int ay = threadIdx.y, az = threadIdx.x;
-    const int tcell = ay * TILE_ACC + az;
-    const int j0 = ((job.tile_row0 + (int)blockIdx.y) % job.tile_rows) * TILE, k0 = blockIdx.x * TILE;
-    const int jt = j0 - 1 + ay, kt = k0 - 1 + az;  // unwrapped target cell
-    const int jw = wrap_near(jt, g.ny), kw = wrap_near(kt, g.nz);
-    const int jw1 = wrap_near(jt + 1, g.ny), kw1 = wrap_near(kt + 1, g.nz);
-    const int cell_c = jw * g.nz + kw, cell_y = jw1 * g.nz + kw, cell_z = jw * g.nz + kw1;
-    auto listed = [&](int j) {  // rows whose lists exist (distributed sweeps list only the tile rows around the slab)
-        int r = j - job.list_row0;
-        r += (r < 0) ? g.ny : 0;
-        return r < job.list_rows;
-    };
-    const int n_c = listed(jw) ? job.bin_cnt[cell_c] : 0;
-    const int n_y = listed(jw1) ? job.bin_cnt[cell_y] : 0;
-    const int n_z = listed(jw) ? job.bin_cnt[cell_z] : 0;
-    const double2 * __restrict__ pyzn = P.pyzn;
-    double y00 = 0.0, y10 = 0.0, y01 = 0.0, y11 = 0.0;  // jy corner sums of staggered cell (jt, kt)
-    double z00 = 0.0, z10 = 0.0, z01 = 0.0, z11 = 0.0;  // jz
-    auto add_y = [&](double v, double wy, double wz) {
-        y00 += v * (1 - wy) * (1 - wz);
-        y10 += v * wy * (1 - wz);
-        y01 += v * (1 - wy) * wz;
-        y11 += v * wy * wz;
-    };
-    auto add_z = [&](double v, double wy, double wz) {
-        z00 += v * (1 - wy) * (1 - wz);
-        z10 += v * wy * (1 - wz);
-        z01 += v * (1 - wy) * wz;
-        z11 += v * wy * wz;
-    };
-    // first entries of the three lists: fetched together with the counts (position 0 exists whatever the count); inside the loops
-    // the next entry is requested before the current one is processed, so the head of each dependent chain (entry -> slot ->
-    // particle data) overlaps the previous visit
-    int e_c = job.bin_lst[cell_c], e_y = job.bin_lst[cell_y], e_z = job.bin_lst[cell_z];
-    if (n_c <= BIN_K && n_y <= BIN_K && n_z <= BIN_K) {
-        for (int i = 0; i < n_c; i++) {
-            const int e = e_c;
-            if (i + 1 < n_c) e_c = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_c];
-            const int s = e >> 2, hy = (e >> 1) & 1, hz = e & 1;
-            if (hy | hz) {
-                const double2 fm = P.fyz_m[s], pn = pyzn[s];
-                const double fy = fm.x, fz = fm.y;
-                const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw, fy, fz);
-                const double nw = job.nw[s];
-                if (hy) add_y(nw * pn.x / w, fy - 0.5, fz);
-                if (hz) add_z(nw * pn.y / w, fy, fz - 0.5);
-            }
-        }
-        for (int i = 0; i < n_y; i++) {
-            const int e = e_y;
-            if (i + 1 < n_y) e_y = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_y];
-            if (!((e >> 1) & 1)) {
-                const int s = e >> 2;
-                const double2 fm = P.fyz_m[s];
-                const double fy = fm.x, fz = fm.y;
-                const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw1, kw, fy, fz);
-                add_y(job.nw[s] * pyzn[s].x / w, fy + 0.5, fz);
-            }
-        }
-        for (int i = 0; i < n_z; i++) {
-            const int e = e_z;
-            if (i + 1 < n_z) e_z = job.bin_lst[(size_t)(i + 1) * g.n2 + cell_z];
-            if (!(e & 1)) {
-                const int s = e >> 2;
-                const double2 fm = P.fyz_m[s];
-                const double fy = fm.x, fz = fm.y;
-                const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, jw, kw1, fy, fz);
-                add_z(job.nw[s] * pyzn[s].y / w, fy, fz + 0.5);
-            }
-        }
-    } else {
-        // a crowded cell was not listed (strong compression): scan the source window of either output in order
-        for (int a = 0; a < 2; a++) {
-            const int hi_y = a == 0 ? 2 : 1, hi_z = a == 1 ? 2 : 1;
-            for (int dy_ = -1; dy_ <= hi_y; dy_++) {
-                for (int dz_ = -1; dz_ <= hi_z; dz_++) {
-                    const int cell = wrap_near(jt + dy_, g.ny) * g.nz + wrap_near(kt + dz_, g.nz);
-                    const int e1 = start[cell + 1];
-                    for (int s = start[cell]; s < e1; s++) {
-                        const int code = P.off_m[s];
-                        const int hy = (code >> 6) & 1, hz = (code >> 7) & 1;
-                        const int need_y = (a == 0 && !hy) ? 1 : 0, need_z = (a == 1 && !hz) ? 1 : 0;
-                        if (dy_ + (code & 7) - 2 - need_y != 0 || dz_ + ((code >> 3) & 7) - 2 - need_z != 0) continue;
-                        const double2 fm = P.fyz_m[s];
-                        const double fy = fm.x, fz = fm.y;
-                        const double w = 1 + gather_node(job.psi_mid, g.ny, g.nz, wrap_near(jt + need_y, g.ny), wrap_near(kt + need_z, g.nz), fy, fz);
-                        if (a == 0) add_y(job.nw[s] * pyzn[s].x / w, hy ? fy - 0.5 : fy + 0.5, fz);
-                        else add_z(job.nw[s] * pyzn[s].y / w, fy, hz ? fz - 0.5 : fz + 0.5);
-                    }
-                }
-            }
-        }
-    }
-    if (cancelled(ctl)) return;
-    QPIC_KERNEL_TAIL();
-    acc[0 * TILE_CELLS + tcell] = y00;
-    acc[1 * TILE_CELLS + tcell] = y10;
-    acc[2 * TILE_CELLS + tcell] = y01;
-    acc[3 * TILE_CELLS + tcell] = y11;
-    acc[4 * TILE_CELLS + tcell] = z00;
-    acc[5 * TILE_CELLS + tcell] = z10;
-    acc[6 * TILE_CELLS + tcell] = z01;
-    acc[7 * TILE_CELLS + tcell] = z11;
-    __syncthreads();
-    if (ay < 1 || az < 1 || jt >= g.ny || kt >= g.nz) return;
-    // node (jt, kt): corner sums of its four neighbouring staggered cells, in the fixed order of tile_store_nodes
-    const int t = jt * g.nz + kt;
-    double jyn = 0.0, jzn = 0.0;
-    jyn += acc[0 * TILE_CELLS + ay * TILE_ACC + az];
-    jyn += acc[1 * TILE_CELLS + (ay - 1) * TILE_ACC + az];
-    jyn += acc[2 * TILE_CELLS + ay * TILE_ACC + az - 1];
-    jyn += acc[3 * TILE_CELLS + (ay - 1) * TILE_ACC + az - 1];
-    jzn += acc[4 * TILE_CELLS + ay * TILE_ACC + az];
-    jzn += acc[5 * TILE_CELLS + (ay - 1) * TILE_ACC + az];
-    jzn += acc[6 * TILE_CELLS + ay * TILE_ACC + az - 1];
-    jzn += acc[7 * TILE_CELLS + (ay - 1) * TILE_ACC + az - 1];
-    job.o[0].out[t] = jyn;
-    job.o[1].out[t] = jzn;
-    if (job.b_src) {
-        // same expressions as k_p2_rows_b_forward
-        const int jp = wrap_inc(jt, g.ny), kp = wrap_inc(kt, g.nz);
-        const int jq = (jt == g.ny - 1) ? 0 : jt;
-        const double djz_dxi = (job.b_jz[t] - jzn) * g.inv_dx;
-        const double djy_dxi = (job.b_jy[t] - jyn) * g.inv_dx;
-        const double jxt = job.b_jx[t];
-        job.b_src[t] = make_double2(-job.b_D * job.b_by[t] - (job.b_jx[jt * g.nz + kp] - jxt) * g.inv_dz + djz_dxi,
-                                    -job.b_D * job.b_bz[jq * g.nz + kt] + (job.b_jx[jp * g.nz + kt] - jxt) * g.inv_dy - djy_dxi);
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------ psi_middle source, stayers direct
-// Single-GPU successor of k_tile_bin_deposit<0> (third session).  In laminar flow ~98 % of the particles end their half step in
+// Successor of the shared-memory binning deposit of round 1 (k_tile_bin_deposit<0>, removed).  In laminar flow ~98 % of the particles end their half step in
 // the cell they started in ("stayers": offset code 0, 0).  Those need no binning: thread (sy, sz), which is the source-cell thread
 // AND the target-cell thread of cell (j0 - 2 + sy, k0 - 2 + sz), keeps its own first four particles (codes, fractions, weights) in
 // registers -- all loaded in ONE round trip after the slot range, before the barrier -- and only the movers go through the
 // shared-memory lists.  After the barrier a target cell accumulates in ascending slot order as before: movers that arrived from
-// lower cells, then its stayers (from registers), then movers from higher cells.  Same sums bit for bit as k_tile_bin_deposit<0>;
+// lower cells, then its stayers (from registers), then movers from higher cells.  Same sums bit for bit as the binning kernel's;
 // the dependent chain of a block shrinks from [range -> codes -> barrier -> entry -> data ...] to [range -> codes + data -> barrier].
 // Published for the jy/jz deposit of the iteration (k_tile_cell_deposit): the MOVERS of every cell only (count + sorted entries);
 // that kernel finds the stayers through the slot range and the offset codes, like this one.
@@ -1927,8 +1609,15 @@ struct StayOut {
     int far_row_lo, far_row_n;  // slabs: legal target rows of a far mover, see FarMovers (0 rows: all)
 };
 
+#ifndef QPIC_PDEP_MINB
+#define QPIC_PDEP_MINB 1
+#endif
 template <bool FIRST = false, int FOLD = 0>
-__global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
+__global__ void
+#if QPIC_PDEP_MINB > 1
+    __launch_bounds__(128, QPIC_PDEP_MINB)
+#endif
+    k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const double * __restrict__ by, const double * __restrict__ bz, int store_px,
                                         StayOut so, const double * __restrict__ a_sqr3, const double * __restrict__ psi) {
     QPIC_KERNEL_BEGIN(KID_k_particles_predict);
     constexpr bool FOLD_JX = FOLD >= 1;
@@ -2087,8 +1776,13 @@ __global__ void k_particles_predict_dep(Ctl * ctl, Geom g, Particles P, const do
 // nodes of the psi_middle source from what k_particles_predict_dep left; block = TILE_ACC x TILE_ACC target cells as in k_tile_deposit.
 // cnt_next: the mover counters of the next iteration's predictor (double buffered) are cleared by the cells' owner threads.
 // FOLD_JX: second output = jx at (y, z) from the predictor's jx sums (no movers there: a cell's sum is its corner sum or its chain of pieces)
+// Blocks per SM the compiler must leave room for: 4 = 48 registers.  Measured on config #2 (us/slice, gpurun_out/r75_ab.log): unspecified (58
+// registers, 3 blocks) 561, 4 -> 550, 5 / 6 (32 registers, spills) 588 / 584; an explicit 1 lets the compiler take 104 registers: 597.
+#ifndef QPIC_ASM_MINB
+#define QPIC_ASM_MINB 4
+#endif
 template <bool FOLD_JX = false>
-__global__ void __launch_bounds__(TILE_CELLS) k_tile_assemble(Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, StayOut so,
+__global__ void __launch_bounds__(TILE_CELLS, QPIC_ASM_MINB) k_tile_assemble(Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job, StayOut so,
                                                               int * __restrict__ cnt_next) {
     QPIC_KERNEL_BEGIN(KID_COUNT + 1);
     __shared__ double acc[(FOLD_JX ? 8 : 4) * TILE_CELLS];
@@ -2226,7 +1920,7 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_fold_rho_chi(const Ctl * ct
 }
 
 // ------------------------------------------------------------------------------------------------ jy / jz, one visit per particle
-// Single-GPU successor of k_tile_list_deposit (third session).  There a thread owns a STAGGERED target cell of both outputs and
+// Successor of round 1's three-list kernel (k_tile_list_deposit, removed).  There a thread owns a STAGGERED target cell of both outputs and
 // walks three lists -- its own cell's and those of the cells above / to the right, filtering by the half-cell bits -- so every
 // list entry is scanned three times and a particle's 1 / (1 + psi_middle) is formed up to three times.  Here a thread owns the
 // UNSTAGGERED half-step cell (j, k), walks only that cell's list, and every particle is visited exactly once: its value

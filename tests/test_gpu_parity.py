@@ -158,24 +158,22 @@ def test_eager_and_graph_paths_are_bit_identical_and_deterministic():
 @pytest.mark.parametrize("n,ppc,a0", [((10, 48, 40), (2, 2), 1.6), ((8, 30, 64), (3, 1), 2.4), ((6, 9, 11), (3, 3), 1.8), ((6, 13, 29), (1, 1), 2.0),
                                       ((5, 17, 15), (2, 4), 1.2)])
 def test_deposit_kernel_generations_agree(n, ppc, a0, monkeypatch):
-    """The single-GPU default (stayers direct: k_tile_stay_deposit + k_tile_cell_deposit, one visit per particle) against the pair that
-    slab-decomposed sweeps keep using (k_tile_bin_deposit<0> + k_tile_list_deposit, QPIC_JYJZ_CELL=0) and against the general sorted
-    path: same sums in different association orders -> 1e-12; the psi_middle source deposit itself is bit-identical between the two
-    tile kernels (same ascending-slot order), which shows in psi of the first slices."""
+    """The kernel sets of the sort-free path against each other and against the general sorted path: same sums in different association
+    orders -> 1e-12.  "tile": round 1's set (k_tile_stay_deposit + jx tile deposit + k_tile_cell_deposit, QPIC_PREDICT_DEPOSIT=0);
+    "predict": the default -- the psi_middle source (stayers) and jx are summed by the predictor (warp-segmented sums) and k_tile_assemble
+    forms the nodes; "predict_rc": rho / susceptibility from the last pass as well; "predict_only_charge": jx by its tile kernel."""
     case = Case.synthetic(n=n, d=(0.125, 0.25, 0.25), M=3, ppc=ppc, a0=a0)
     runs = {}
-    for name, env, kw in [("cell", "1", {}), ("list", "0", {}), ("general", "1", {"force_general_deposit": True}), ("predict", "1", {})]:
-        monkeypatch.setenv("QPIC_JYJZ_CELL", env)
-        # "predict": the stayers of the psi_middle source are summed by the predictor (warp-segmented reduction) and k_tile_assemble forms the nodes
-        monkeypatch.setenv("QPIC_PREDICT_DEPOSIT", "1" if name == "predict" else "0")
+    for name, kw in [("tile", {}), ("general", {"force_general_deposit": True}), ("predict", {}), ("predict_rc", {}), ("predict_only_charge", {})]:
+        monkeypatch.setenv("QPIC_PREDICT_DEPOSIT", "1" if name.startswith("predict") else "0")
+        monkeypatch.setenv("QPIC_FOLD_RHO_CHI", "1" if name == "predict_rc" else "0")
+        monkeypatch.setenv("QPIC_FOLD_JX", "0" if name == "predict_only_charge" else "1")
         with case.make_solver(keep_slices_3d=True, **kw) as s:
             assert s.solve_wakefield() == -1
             runs[name] = {f: s.field3d(f) for f in FIELDS} | {f + "_s": s.field3d(f, per_slice=True) for f in SLICE_FIELDS}
-    for other in ("list", "general", "predict"):
-        for k, v in runs["cell"].items():
+    for other in ("general", "predict", "predict_rc", "predict_only_charge"):
+        for k, v in runs["tile"].items():
             assert slice_rel_l2(runs[other][k], v) < 1e-12, (other, k)
-    # last slice solved first: no B field yet, so psi of slice nx-1 depends on the charge deposit only
-    assert np.array_equal(runs["cell"]["psi_s"][-1], runs["list"]["psi_s"][-1])
 
 
 def test_particle_gamma_px_tracking(monkeypatch):
@@ -237,10 +235,15 @@ def test_per_slice_parity_from_identical_state():
             assert worst <= TOL_SLICE, f"slice {i}: {worst}"
 
 
+@pytest.mark.parametrize("fold_rho_chi", [None, "1"], ids=["default", "rho-chi-from-the-last-predictor-pass"])
 @pytest.mark.parametrize("name", ["tiny_laser", "tiny_profile", "tiny_bunch", "tiny_bunch_stop"])
-def test_sweep_matches_reference_golden(name, golden_dir):
-    """CUDA path vs the output of the UNMODIFIED reference (tests/golden/*.npz, made by make_golden.py)."""
+def test_sweep_matches_reference_golden(name, fold_rho_chi, golden_dir, monkeypatch):
+    """CUDA path vs the output of the UNMODIFIED reference (tests/golden/*.npz, made by make_golden.py).  Second variant: rho and
+    susceptibility formed from the per-cell sums of the last predictor pass (k_tile_fold_rho_chi, which dense runs -- >= 8 particles per
+    cell -- select by themselves); tiny_bunch_stop then also exercises the slice that the |B| stop ends before that pass (the tile kernel's job)."""
     import os
+    if fold_rho_chi is not None:
+        monkeypatch.setenv("QPIC_FOLD_RHO_CHI", fold_rho_chi)
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     case = Case.from_toml(name)
     assert case.n == g["f3/psi"].shape

@@ -1,5 +1,5 @@
 """A/B timing helper (GPU box): graph-replayed slices of a BASELINE shape, device-timed (CUDA events on the solver's stream).
-  QPIC_FUSED_SOLVE=0 python tools/ab.py linear512 --slices 512 --reps 3
+  QPIC_PREDICT_DEPOSIT=0 python tools/ab.py linear512 --slices 512 --reps 3
 Prints one line per repetition: us/slice, kernels/slice.  Environment variables select the variant."""
 import argparse
 import os
