@@ -9,7 +9,11 @@ One bench "step" = SLICES_PER_STEP consecutive xi-slices of that sweep (push + a
 
 N > 1 (torchrun, one rank per GPU): the xi-loop is causally sequential, so a sweep never spans GPUs; ranks run
 independent members of the a0 / density parameter scan (BASELINE.json configs[4]), no data-path collective,
-"scaling": "weak".  `value` = total pushes of all ranks / max-over-ranks device time.
+"scaling": "weak".  `value` = total pushes of all ranks / max-over-ranks device time.  The same JSON line then carries, for N > 1,
+`scan_members` (per-rank ms, a0, rho0, fast-path aborts), `control_identical_members` (all ranks on the SAME member: separates interference
+from member cost) and `slab4096`: BASELINE config #4 (64 x 4096^2, 16 ppc) slab-decomposed over the N GPUs (tools/dist_run.py: the
+real multi-GPU path -- distributed transposes, halo exchange, particle migration over NVLink peer memory), with a parity probe against
+the single-GPU kernels.
 
 --impl reference times the reference's own OpenMP CPU implementation of the same path on this box's host cores:
 oracle/_ref/quasistatic_pic_fast = the UNMODIFIED reference sources built by oracle/Makefile (falls back to the

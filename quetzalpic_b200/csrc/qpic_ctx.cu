@@ -23,6 +23,10 @@
 #include "qpic_dist.cuh"
 #include "qpic_bunch.cuh"
 
+// build (MODE) of a power-of-two transform kernel: P2_PICK(mode, kernel, other template arguments...) / P2_PICK0(mode, kernel)
+#define P2_PICK(mode, K, ...) ((mode) == 2 ? K<__VA_ARGS__, 2> : ((mode) == 1 ? K<__VA_ARGS__, 1> : K<__VA_ARGS__, 0>))
+#define P2_PICK0(mode, K) ((mode) == 2 ? K<2> : ((mode) == 1 ? K<1> : K<0>))
+
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
 #endif
@@ -98,7 +102,7 @@ struct qpic_ctx {
     struct FftLaunch {
         int spb = 1, threads = 128, blocks = 1;
         size_t smem = 0;
-        bool wide = false;  // power-of-two engine: the WIDE build of the kernels (<= 896 threads, one exchange buffer per sequence)
+        int mode = 0;  // power-of-two engine: build of the kernels (0 narrow, 1 wide, 2 deep: see qpic_fft_pow2.cuh)
     };
     FftLaunch rows_real, rows_cplx, cols_half, cols_full;
     bool pow2_y = false, pow2_z = false;
@@ -209,6 +213,17 @@ template <class T>
 int dev_alloc(qpic_ctx * c, T ** p, size_t count, bool zero = true) {
     void * raw = nullptr;
     const size_t bytes = (count ? count : 1) * sizeof(T);
+    if (*p) {
+        // re-allocation (qpic_init_wake_particles with another particle count on a context without a captured graph): the previous buffer
+        // is released instead of staying with the context until qpic_destroy
+        auto it = std::find(c->allocations.begin(), c->allocations.end(), static_cast<void *>(*p));
+        if (it != c->allocations.end()) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(*it);
+            c->allocations.erase(it);
+        }
+        *p = nullptr;
+    }
     cudaError_t e = cudaMalloc(&raw, bytes);
     if (e != cudaSuccess) return fail(c, QPIC_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     c->allocations.push_back(raw);
@@ -297,35 +312,49 @@ KernelLimits kernel_limits(K... kernels) {
     return lim;
 }
 
-// lim: the narrow builds of the kernels (power-of-two engine) / the generic engine's kernels; lim_wide: the WIDE builds
-int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what, const KernelLimits & lim = KernelLimits(),
-                    const KernelLimits & lim_wide = KernelLimits()) {
+// lim[0]: the narrow builds of the kernels (power-of-two engine) / the generic engine's kernels; lim[1], lim[2]: the wide and deep builds
+int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaunch * L, const char * what, const KernelLimits * lim3) {
+    const KernelLimits none;
+    const KernelLimits & lim = lim3 ? lim3[0] : none;
     const int n = P.n;
     if (P.log2n > 0) {
         const int e8 = n / 8;
-        // These kernels are latency bound (a few warps per SM at most), so the fastest shape is ONE wave of fat blocks:
-        // as many sequences per block as it takes to cover the batch with <= 148 blocks, within the kernels' thread (register)
-        // and shared-memory limits.  Where two alternating exchange buffers per sequence do not leave room for that (1024-point axes:
-        // 1024 sequences want 7 per block = 262 KB) the single-buffer mode -- one more barrier per exchange -- is used if it saves a wave.
-        auto fit = [&](size_t per_seq, const KernelLimits & lim) {
+        // These kernels are latency bound (a few warps per SM at most), so the fastest shape is ONE wave of fat blocks: as many sequences per
+        // block as it takes to cover the batch with <= 148 blocks, within the kernels' thread (register) and shared-memory limits.  Where two
+        // alternating exchange buffers per sequence do not leave room for that, a single-buffer build -- one more barrier per exchange -- is
+        // used if it saves waves: wide (1024-point axes: 7 sequences per block instead of 4) or deep (4096-point axes: a sequence fills a
+        // block, two blocks per SM instead of one).
+        const size_t one = sizeof(double2) * (size_t)p2_pad_len(n);
+        int best = -1, best_spb = 1;
+        long best_waves = 0;
+        const char * e_deep = getenv("QPIC_FFT_DEEP");  // A/B: 0 = narrow / wide builds only
+        const int modes = lim3 ? ((e_deep && e_deep[0] == '0') ? 2 : 3) : 1;
+        for (int mode = 0; mode < modes; mode++) {
+            const KernelLimits & lm = lim3 ? lim3[mode] : none;
+            const size_t per_seq = mode == 0 ? 2 * one : one;
             int spb = (nseq + 147) / 148;
-            while (spb > 1 && (spb * e8 > lim.max_threads || spb * per_seq > lim.max_dyn_smem)) spb--;
+            while (spb > 1 && (spb * e8 > lm.max_threads || spb * per_seq > lm.max_dyn_smem)) spb--;
             if (spb < 1) spb = 1;
             while (spb * e8 < 32) spb *= 2;
-            return spb;
-        };
-        const size_t one = sizeof(double2) * (size_t)p2_pad_len(n);
-        const int spb2 = fit(2 * one, lim), spb1 = fit(one, lim_wide);
-        const int waves2 = ((nseq + spb2 - 1) / spb2 + 147) / 148, waves1 = ((nseq + spb1 - 1) / spb1 + 147) / 148;
-        const bool single = waves1 < waves2;
-        const int spb = single ? spb1 : spb2;
-        L->wide = single;
-        L->spb = spb;
-        L->threads = spb * e8;
-        L->smem = spb * (single ? one : 2 * one);
-        const KernelLimits & use = single ? lim_wide : lim;
-        if (L->threads > use.max_threads) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d needs more than %d threads per block", what, n, use.max_threads);
-        if (L->smem > use.max_dyn_smem) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d does not fit the shared-memory transform", what, n);
+            if (spb * e8 > lm.max_threads || spb * per_seq > lm.max_dyn_smem) continue;
+            // resident blocks per SM: shared memory (227 KB per SM, 1 KB reserved per block) and the register budget the build was compiled for
+            long per_sm = (long)(SMEM_OPTIN_LIMIT / (spb * per_seq + 1024));
+            const long by_regs = mode == 2 ? 2 : 1;  // (narrow / wide: a block of several hundred threads at 70-110 registers)
+            if (per_sm > by_regs) per_sm = by_regs;
+            if (per_sm < 1) per_sm = 1;
+            const long blocks = (nseq + spb - 1) / spb;
+            const long waves = (blocks + 148 * per_sm - 1) / (148 * per_sm);
+            if (best < 0 || waves < best_waves) {
+                best = mode;
+                best_spb = spb;
+                best_waves = waves;
+            }
+        }
+        if (best < 0) return fail(c, QPIC_ERR_UNSUPPORTED, "%s: length %d does not fit the shared-memory transform", what, n);
+        L->mode = best;
+        L->spb = best_spb;
+        L->threads = best_spb * e8;
+        L->smem = best_spb * (best == 0 ? 2 * one : one);
         L->blocks = (nseq + L->spb - 1) / L->spb;
         return QPIC_OK;
     } else {
@@ -542,7 +571,7 @@ int enqueue_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D, bo
         const int col0 = c->dist.on ? (full ? c->dist.col0_full : c->dist.col0_half) : 0;
         const int mine = c->dist.on ? (full ? c->dist.ncols_full : c->dist.ncols_half) : ncols;
         double2 * cols = c->dist.on ? m.base[c->dist.v.rank] : c->spec;
-        QPIC_LAUNCH((L.wide ? k_p2_cols_solve<true> : k_p2_cols_solve<false>), L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, cols, m.cpr, mine, inv + (size_t)col0 * c->g.ny,
+        QPIC_LAUNCH(P2_PICK0(L.mode, k_p2_cols_solve), L.blocks, L.threads, L.smem, st, ctl, c->fy.plan.log2n, c->fy.tw, cols, m.cpr, mine, inv + (size_t)col0 * c->g.ny,
                     want_border_sums ? c->spec_row0 : (double2 *)nullptr, want_border_sums ? c->spec_colsum : (double2 *)nullptr, c->dist.on ? c->cols_ticket : (int *)nullptr,
                     partials_map(c), c->dist.on ? c->dist.v.rank : 0, col0, nz);
     } else {
@@ -561,7 +590,7 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     if (fused) *fused = fuse;
     if (c->dist.on && !fuse) return fail(c, QPIC_ERR_UNSUPPORTED, "distributed sweeps need the fused power-of-two solve");
     if (c->pow2_z) {
-        QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_r2c<true, true> : k_p2_rows_r2c<false, true>) : (c->dist.on ? k_p2_rows_r2c<true> : k_p2_rows_r2c<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
+        QPIC_LAUNCH((c->dist.on ? P2_PICK(R.mode, k_p2_rows_r2c, true) : P2_PICK(R.mode, k_p2_rows_r2c, false)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->fft_in, spec_map(c, false), row_count(c), row_first(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_r2c<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->fft_in, c->spec, ny, nz, R.spb);
     }
@@ -570,7 +599,7 @@ int enqueue_real_solve(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, double D,
     QPIC_TRY(enqueue_columns(c, st, ctl, D, false, fuse));
     QPIC_TRY(dist_barrier(c, st));  // every rank's columns (and border-sum partials) are done
     if (c->pow2_z) {
-        QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_c2r<true, true> : k_p2_rows_c2r<false, true>) : (c->dist.on ? k_p2_rows_c2r<true> : k_p2_rows_c2r<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
+        QPIC_LAUNCH((c->dist.on ? P2_PICK(R.mode, k_p2_rows_c2r, true) : P2_PICK(R.mode, k_p2_rows_c2r, false)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, spec_map(c, false), fuse ? fixed_dst : c->raw, row_count(c),
                     row_first(c), ny, c->inv_scale, fuse ? 1 : 0, c->dist.on ? reinterpret_cast<const double *>(c->dist.region + c->dist.v.lay.partials) : c->partials,
                     c->prm.psi_threshold - 1, (fuse && !c->dist.on) ? (const double2 *)c->spec_row0 : (const double2 *)nullptr,
                     (fuse && !c->dist.on) ? (const double2 *)c->spec_colsum : (const double2 *)nullptr);
@@ -588,7 +617,7 @@ int enqueue_complex_columns(qpic_ctx * c, cudaStream_t st, const Ctl * ctl, doub
 int enqueue_b_backward(qpic_ctx * c, cudaStream_t st, Ctl * ctl, double * by, double * bz, double threshold, int iteration) {
     const qpic_ctx::FftLaunch & R = c->rows_cplx;
     if (c->pow2_z) {
-        QPIC_LAUNCH((R.wide ? (c->dist.on ? k_p2_rows_b_backward<true, true> : k_p2_rows_b_backward<false, true>) : (c->dist.on ? k_p2_rows_b_backward<true> : k_p2_rows_b_backward<false>)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
+        QPIC_LAUNCH((c->dist.on ? P2_PICK(R.mode, k_p2_rows_b_backward, true) : P2_PICK(R.mode, k_p2_rows_b_backward, false)), R.blocks, R.threads, R.smem, st, ctl, c->fz.plan.log2n, c->fz.tw, c->g, spec_map(c, true), by, bz, threshold, iteration,
                     c->inv_scale, row_first(c), row_count(c));
     } else {
         QPIC_LAUNCH(k_fft_rows_b_backward<false>, R.blocks, R.threads, R.smem, st, ctl, c->fz.plan, c->fz.tw, c->g, c->spec, by, bz, threshold, iteration,
@@ -938,8 +967,8 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
             const qpic_ctx::FftLaunch & R = c->rows_cplx;
             if (c->pow2_z) {
                 const bool pre = fast && c->jyjz_lists && c->b_src;
-                auto kern = c->dist.on ? k_p2_rows_b_forward<true, false> : (pre ? k_p2_rows_b_forward<false, true> : k_p2_rows_b_forward<false, false>);
-                if (R.wide) kern = c->dist.on ? k_p2_rows_b_forward<true, false, true> : (pre ? k_p2_rows_b_forward<false, true, true> : k_p2_rows_b_forward<false, false, true>);
+                auto kern = c->dist.on ? P2_PICK(R.mode, k_p2_rows_b_forward, true, false)
+                                       : (pre ? P2_PICK(R.mode, k_p2_rows_b_forward, false, true) : P2_PICK(R.mode, k_p2_rows_b_forward, false, false));
                 QPIC_LAUNCH(kern, R.blocks, R.threads, R.smem, sa, c->ctl, c->fz.plan.log2n, c->fz.tw, c->g, c->prm.magnetic_field_D, c->f2[QPIC_F2_BY_CUR],
                             c->f2[QPIC_F2_BZ_CUR], c->f2[QPIC_F2_JX], c->f2[QPIC_F2_JY], c->f2[QPIC_F2_JZ], c->f2[QPIC_F2_JY_NEXT], c->f2[QPIC_F2_JZ_NEXT],
                             (const double2 *)c->b_src, spec_map(c, true), row_first(c), row_count(c));
@@ -1378,18 +1407,20 @@ static int create_impl(qpic_ctx * c) {
     }
     c->pow2_y = c->fy.plan.log2n > 0;
     c->pow2_z = c->fz.plan.log2n > 0;
-    const KernelLimits lim_real = kernel_limits(k_p2_rows_r2c<false>, k_p2_rows_r2c<true>, k_p2_rows_c2r<false>, k_p2_rows_c2r<true>);
-    const KernelLimits lim_cplx = kernel_limits(k_p2_rows_b_forward<false, false>, k_p2_rows_b_forward<false, true>, k_p2_rows_b_forward<true, false>, k_p2_rows_b_backward<false>, k_p2_rows_b_backward<true>,
-                                                k_p2_rows_c2c<false>);
-    const KernelLimits lim_cols = kernel_limits(k_p2_cols_solve<false>);
-    const KernelLimits wide_real = kernel_limits(k_p2_rows_r2c<false, true>, k_p2_rows_r2c<true, true>, k_p2_rows_c2r<false, true>, k_p2_rows_c2r<true, true>);
-    const KernelLimits wide_cplx = kernel_limits(k_p2_rows_b_forward<false, false, true>, k_p2_rows_b_forward<false, true, true>, k_p2_rows_b_forward<true, false, true>,
-                                                 k_p2_rows_b_backward<false, true>, k_p2_rows_b_backward<true, true>, k_p2_rows_c2c<true>);
-    const KernelLimits wide_cols = kernel_limits(k_p2_cols_solve<true>);
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform", lim_real, wide_real));
-    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform", lim_cplx, wide_cplx));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform", lim_cols, wide_cols));
-    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform", lim_cols, wide_cols));
+    KernelLimits lim_real[3], lim_cplx[3], lim_cols[3];
+#define P2_LIMITS(M)                                                                                                                                  \
+    lim_real[M] = kernel_limits(k_p2_rows_r2c<false, M>, k_p2_rows_r2c<true, M>, k_p2_rows_c2r<false, M>, k_p2_rows_c2r<true, M>);                   \
+    lim_cplx[M] = kernel_limits(k_p2_rows_b_forward<false, false, M>, k_p2_rows_b_forward<false, true, M>, k_p2_rows_b_forward<true, false, M>,      \
+                                k_p2_rows_b_backward<false, M>, k_p2_rows_b_backward<true, M>, k_p2_rows_c2c<M>);                                    \
+    lim_cols[M] = kernel_limits(k_p2_cols_solve<M>);
+    P2_LIMITS(0)
+    P2_LIMITS(1)
+    P2_LIMITS(2)
+#undef P2_LIMITS
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, (row_count(c) + 1) / 2, &c->rows_real, "row transform", lim_real));
+    QPIC_TRY(size_fft_launch(c, c->fz.plan, row_count(c), &c->rows_cplx, "row transform", lim_cplx));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? (D.ncols_half > 0 ? D.ncols_half : 1) : g.nz / 2 + 1, &c->cols_half, "column transform", lim_cols));
+    QPIC_TRY(size_fft_launch(c, c->fy.plan, D.on ? D.ncols_full : g.nz, &c->cols_full, "column transform", lim_cols));
     if (!c->pow2_y) {
         // generic engine: two adjacent columns per block when they fit, so that global accesses are 32-byte sectors
         const int cpb = (sizeof(double2) * 2 * 2 * (size_t)g.ny <= SMEM_DEFAULT_LIMIT) ? 2 : 1;
@@ -1411,31 +1442,27 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_rows_c2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_r2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2r<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_b_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_r2c<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_r2c<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_c2r<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_c2r<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<false, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_backward<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_backward<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+#define P2_SMEM(M)                                                                                                            \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_r2c<false, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));              \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_r2c<true, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));               \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_c2r<false, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));              \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_c2r<true, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));               \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<false, false, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b)); \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<false, true, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));  \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_forward<true, false, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));  \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_backward<false, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));       \
+    QPIC_CUDA(c, cudaFuncSetAttribute((k_p2_rows_b_backward<true, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, b));        \
+    QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_rows_c2c<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+            P2_SMEM(0)
+            P2_SMEM(1)
+            P2_SMEM(2)
+#undef P2_SMEM
         }
         if (cols_max > SMEM_DEFAULT_LIMIT) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_fft_cols_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
-            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
+            QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
         }
     }
     // the inverse-symbol tables of the two operators of the sweep (psi: D = 0, half spectrum; By + i Bz: D, full spectrum)
@@ -1586,16 +1613,16 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD(k_sort_rank);
         QPIC_PRELOAD(k_end_of_slice);
         QPIC_PRELOAD(k_init_a_sqr);
-        QPIC_PRELOAD(k_p2_rows_r2c<true>);
-        QPIC_PRELOAD(k_p2_rows_c2r<true>);
-        QPIC_PRELOAD(k_p2_cols_solve<false>);
-        QPIC_PRELOAD(k_p2_cols_solve<true>);
-        QPIC_PRELOAD((k_p2_rows_r2c<true, true>));
-        QPIC_PRELOAD((k_p2_rows_c2r<true, true>));
-        QPIC_PRELOAD((k_p2_rows_b_forward<true, false, true>));
-        QPIC_PRELOAD((k_p2_rows_b_backward<true, true>));
-        QPIC_PRELOAD((k_p2_rows_b_forward<true, false>));
-        QPIC_PRELOAD(k_p2_rows_b_backward<true>);
+#define P2_PRELOAD(M)                                        \
+    QPIC_PRELOAD((k_p2_rows_r2c<true, M>));                  \
+    QPIC_PRELOAD((k_p2_rows_c2r<true, M>));                  \
+    QPIC_PRELOAD(k_p2_cols_solve<M>);                        \
+    QPIC_PRELOAD((k_p2_rows_b_forward<true, false, M>));     \
+    QPIC_PRELOAD((k_p2_rows_b_backward<true, M>));
+        P2_PRELOAD(0)
+        P2_PRELOAD(1)
+        P2_PRELOAD(2)
+#undef P2_PRELOAD
 #undef QPIC_PRELOAD
     }
 #endif
@@ -1690,7 +1717,7 @@ int qpic_init_wake_particles(qpic_ctx * c, const double * y, const double * z, c
         return fail(c, QPIC_ERR_STATE, "the particle count cannot change after the first qpic_step of a context");
     }
     if ((int)capacity != c->P.np || !c->P.y) {
-        // (re)allocation: the previous arrays stay owned by the context until qpic_destroy
+        // (re)allocation: dev_alloc releases the previous arrays
         QPIC_TRY(alloc_particles(c, capacity));
     } else {
         double * zero[] = {c->P.py, c->P.pz, c->P.gamma, c->P.px, c->P.gam, c->P.pxs};
@@ -1995,7 +2022,7 @@ int qpic_solve_helmholtz_pair_host(qpic_ctx * c, double * inout_a, double * inou
     {
         const qpic_ctx::FftLaunch & R = c->rows_cplx;
         if (c->pow2_z) {
-            QPIC_LAUNCH((R.wide ? k_p2_rows_c2c<true> : k_p2_rows_c2c<false>), R.blocks, R.threads, R.smem, c->stream, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny);
+            QPIC_LAUNCH(P2_PICK0(R.mode, k_p2_rows_c2c), R.blocks, R.threads, R.smem, c->stream, c->fz.plan.log2n, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny);
         } else {
             QPIC_LAUNCH(k_fft_rows_c2c<false>, R.blocks, R.threads, R.smem, c->stream, c->fz.plan, c->fz.tw, c->fft_in, c->fft_in2, c->spec, ny, nz, R.spb);
         }

@@ -59,7 +59,7 @@ __device__ __forceinline__ void fft_pow2_regs(double2 (&v)[8], double2 * xa, dou
         const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
         const double2 w7 = cmul(w4, w3);
         double2 * y = flip ? xb : xa;
-        // SINGLE: one buffer instead of two alternating ones (xa == xb, the WIDE kernels: half the shared memory, so that more sequences
+        // SINGLE: one buffer instead of two alternating ones (xa == xb, the wide / deep builds of the kernels: half the shared memory, so that more sequences
         // fit a block on the long axes): every thread must have finished reading the previous exchange before it is overwritten
         if (SINGLE && log2s > 0) __syncthreads();
         const int base = q + ((8 * p) << log2s);
@@ -108,12 +108,15 @@ __device__ __forceinline__ double2 * spec_at(const SpecMap & m, int j, int k) {
 }
 
 // thread layout shared by all kernels below: blockDim.x = spb * n/8; sequence b = threadIdx.x / (n/8), lane t
-// Every kernel below exists in two builds (last template argument WIDE):
-//   narrow  <= 512 threads per block (no register pressure: the 512-point axes of config #2 run 128-thread blocks), two alternating exchange buffers;
-//   wide    <= 896 threads = 7 sequences of a 1024-point axis in one block (1024 sequences on 148 SMs = one wave of 147 blocks) at 72 registers
-//           (a few spilled words) with ONE exchange buffer per sequence (P2_SINGLE).  Chosen by size_fft_launch where it saves a wave.
+// Every kernel below exists in three builds (last template argument MODE):
+//   0 narrow  <= 512 threads per block (no register cap: the 512-point axes of config #2 run 128-thread blocks), two alternating exchange buffers;
+//   1 wide    <= 896 threads = 7 sequences of a 1024-point axis in one block (1024 sequences on 148 SMs = one wave of 147 blocks) at 72 registers
+//             (a few spilled words) with ONE exchange buffer per sequence (one more barrier per exchange);
+//   2 deep    <= 512 threads at 64 registers with one exchange buffer: TWO blocks per SM where a sequence fills a block (4096-point axes: 512
+//             threads and 66 KB per sequence), so that one block's loads overlap the other's passes.
+// size_fft_launch picks the build that needs the fewest waves (ties: narrow, wide, deep).
 constexpr int P2_WIDE_THREADS = 896, P2_NARROW_THREADS = 512;
-#define P2_BOUNDS __launch_bounds__(WIDE ? P2_WIDE_THREADS : P2_NARROW_THREADS)
+#define P2_BOUNDS __launch_bounds__(MODE == 1 ? P2_WIDE_THREADS : P2_NARROW_THREADS, MODE == 2 ? 2 : 0)
 struct Pow2Lane {
     int b, t, e8;
     double2 *xa, *xb;
@@ -142,12 +145,12 @@ __device__ __forceinline__ Pow2Lane pow2_lane(double2 * sm, int log2n) {
 
 // forward rows, two real rows per sequence -> half spectra spec[ny][nzh]
 // rows [row0, row0 + ny) of src (a full-size array)
-template <bool DIST, bool WIDE = false>
+template <bool DIST, int MODE = 0>
 __global__ void P2_BOUNDS k_p2_rows_r2c(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, const double * __restrict__ src, SpecMap spec, int ny,
                               int row0) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_r2c);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
+    const Pow2Lane L = pow2_lane<MODE != 0>(sm, log2n);
     const int nz = 1 << log2n, nzh = nz / 2 + 1;
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
     double2 v[8];
@@ -157,7 +160,7 @@ __global__ void P2_BOUNDS k_p2_rows_r2c(const Ctl * ctl, int log2n, const double
         v[e] = make_double2(j0 < ny ? src[(size_t)(row0 + j0) * nz + k] : 0.0, j1 < ny ? src[(size_t)(row0 + j1) * nz + k] : 0.0);
     }
     if (cancelled(ctl)) return;  // tested after the loads are in flight (uniform over the block)
-    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<false, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     // the split needs Z_k and Z_{n-k}: one more exchange.  The last exchange of the transform used the other buffer
     // (or none at all), so this buffer is free once every thread has left the transform's final read.
@@ -186,13 +189,13 @@ __global__ void P2_BOUNDS k_p2_rows_r2c(const Ctl * ctl, int log2n, const double
 // The column kernel's last block reduces these sums with a fixed-order tree and leaves the mean in *border_mean.
 // `ny` rows starting at global row `row0` of a field with ny_total rows.  The border mean is assembled from the per-rank
 // partial sums the column kernels left in partials[rank][0..2] (one rank on a single GPU), in rank order.
-template <bool DIST, bool WIDE = false>
+template <bool DIST, int MODE = 0>
 __global__ void P2_BOUNDS k_p2_rows_c2r(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, SpecMap spec, double * __restrict__ dst, int ny, int row0,
                               int ny_total, double inv_scale, int fix, const double * __restrict__ partials, double floor_value,
                               const double2 * __restrict__ red_row0, const double2 * __restrict__ red_colsum) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2r);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
+    const Pow2Lane L = pow2_lane<MODE != 0>(sm, log2n);
     const int nz = 1 << log2n;
     const int j0 = 2 * (blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b), j1 = j0 + 1;
     // loads now, arithmetic after the transform (the divisions then hide behind the spectrum loads)
@@ -263,7 +266,7 @@ __global__ void P2_BOUNDS k_p2_rows_c2r(const Ctl * ctl, int log2n, const double
         pc = red_colsum[0].x;
     }
     if (cancelled(ctl)) return;
-    fft_pow2_regs<true, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<true, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     double mean = 0.0;
     if (fix) {
@@ -289,7 +292,7 @@ __global__ void P2_BOUNDS k_p2_rows_c2r(const Ctl * ctl, int log2n, const double
 
 // ------------------------------------------------------------------------------------------------ columns + symbol
 // one column per sequence; inv_symbol is [ncols][ny] (column-major for this kernel), entry (k=0, j=0) = 0
-template <bool WIDE = false>
+template <int MODE = 0>
 __global__ void P2_BOUNDS k_p2_cols_solve(const Ctl * ctl, int log2n, const double2 * __restrict__ twy, double2 * __restrict__ spec, int ld, int ncols,
                                 const double * __restrict__ inv_symbol, double2 * __restrict__ row0, double2 * __restrict__ colsum,
                                 int * __restrict__ ticket, SpecMap partials, int my_rank, int col0, int nz) {
@@ -304,7 +307,7 @@ __global__ void P2_BOUNDS k_p2_cols_solve(const Ctl * ctl, int log2n, const doub
     L.b = threadIdx.x % spb;
     L.t = threadIdx.x / spb;
     L.xa = sm + L.b;
-    L.xb = WIDE ? L.xa : L.xa + (size_t)p2_pad_len(1 << log2n) * spb;
+    L.xb = MODE != 0 ? L.xa : L.xa + (size_t)p2_pad_len(1 << log2n) * spb;
     const int k = blockIdx.x * spb + L.b;
     const bool live = k < ncols;
     const int ny = 1 << log2n;
@@ -316,7 +319,7 @@ __global__ void P2_BOUNDS k_p2_cols_solve(const Ctl * ctl, int log2n, const doub
 #pragma unroll
     for (int e = 0; e < 8; e++) rinv[e] = live ? inv_symbol[(size_t)k * ny + L.t + e * L.e8] : 0.0;
     if (cancelled(ctl)) return;
-    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twy, spb);
+    fft_pow2_regs<false, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twy, spb);
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) {
@@ -330,7 +333,7 @@ __global__ void P2_BOUNDS k_p2_cols_solve(const Ctl * ctl, int log2n, const doub
     if (colsum && live && L.t == 0) row0[k] = v[0];
     // the forward transform's last exchange buffer may still be read by slower threads of this sequence
     __syncthreads();
-    fft_pow2_regs<true, WIDE>(v, L.xa, L.xb, L.t, log2n, twy, spb);
+    fft_pow2_regs<true, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twy, spb);
     QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll
@@ -396,14 +399,14 @@ __global__ void P2_BOUNDS k_p2_cols_solve(const Ctl * ctl, int log2n, const doub
 
 // see k_fft_rows_b_forward (qpic_fft.cuh) for the source terms (src/System_3d.cpp:489-495, :530-536, :555-564 incl. :563)
 // PRE: the sources were already formed by the jy/jz deposit (TileJob::b_src) and are simply loaded
-template <bool DIST, bool PRE, bool WIDE = false>
+template <bool DIST, bool PRE, int MODE = 0>
 __global__ void P2_BOUNDS k_p2_rows_b_forward(const Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, double D, const double * __restrict__ by,
                                     const double * __restrict__ bz, const double * __restrict__ jx, const double * __restrict__ jy,
                                     const double * __restrict__ jz, const double * __restrict__ jy_next, const double * __restrict__ jz_next,
                                     const double2 * __restrict__ b_src, SpecMap spec, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_forward);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
+    const Pow2Lane L = pow2_lane<MODE != 0>(sm, log2n);
     const int nz = g.nz, ny = g.ny;
     const int jl = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const int j = row0 + jl;
@@ -428,7 +431,7 @@ __global__ void P2_BOUNDS k_p2_rows_b_forward(const Ctl * ctl, int log2n, const 
         }
     }
     if (cancelled(ctl)) return;
-    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<false, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     if (live) {
 #pragma unroll
@@ -437,13 +440,13 @@ __global__ void P2_BOUNDS k_p2_rows_b_forward(const Ctl * ctl, int log2n, const 
 }
 
 // by(i) = re/ny/nz, bz(i) = im/ny/nz and the stop test (src/System_3d.cpp:541-552, :569-580)
-template <bool DIST, bool WIDE = false>
+template <bool DIST, int MODE = 0>
 __global__ void P2_BOUNDS k_p2_rows_b_backward(Ctl * ctl, int log2n, const double2 * __restrict__ twz, Geom g, SpecMap spec, double * __restrict__ by,
                                      double * __restrict__ bz, double threshold, int iteration, double inv_scale, int row0, int nrows) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_b_backward);
     // blocks of THIS launch may already have raised the flag; only an earlier launch's flag cancels the work
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
+    const Pow2Lane L = pow2_lane<MODE != 0>(sm, log2n);
     const int nz = g.nz, ny = g.ny;
     const int jl = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const int j = row0 + jl;
@@ -454,7 +457,7 @@ __global__ void P2_BOUNDS k_p2_rows_b_backward(Ctl * ctl, int log2n, const doubl
     const int my_tag = ctl->slice * STOP_TAG_STRIDE + iteration + 1;
     const int tag = ctl->stop_tag;
     if ((tag != 0 && tag != my_tag) || ctl->fast_fail) return;
-    fft_pow2_regs<true, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<true, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twz);
     QPIC_KERNEL_TAIL();
     if (!live) return;
     bool bad = false;
@@ -472,12 +475,12 @@ __global__ void P2_BOUNDS k_p2_rows_b_backward(Ctl * ctl, int log2n, const doubl
 }
 
 // plain complex rows (exposed Helmholtz-pair building block)
-template <bool WIDE = false>
+template <int MODE = 0>
 __global__ void P2_BOUNDS k_p2_rows_c2c(int log2n, const double2 * __restrict__ twz, const double * __restrict__ re, const double * __restrict__ im,
                               double2 * __restrict__ spec, int ny) {
     QPIC_KERNEL_BEGIN(KID_k_p2_rows_c2c);
     QPIC_DYN_SMEM(double2, sm);
-    const Pow2Lane L = pow2_lane<WIDE>(sm, log2n);
+    const Pow2Lane L = pow2_lane<MODE != 0>(sm, log2n);
     const int nz = 1 << log2n;
     const int j = blockIdx.x * (blockDim.x >> (log2n - 3)) + L.b;
     const bool live = j < ny;
@@ -487,7 +490,7 @@ __global__ void P2_BOUNDS k_p2_rows_c2c(int log2n, const double2 * __restrict__ 
         const size_t gidx = (size_t)j * nz + L.t + e * L.e8;
         v[e] = live ? make_double2(re[gidx], im[gidx]) : make_double2(0.0, 0.0);
     }
-    fft_pow2_regs<false, WIDE>(v, L.xa, L.xb, L.t, log2n, twz);
+    fft_pow2_regs<false, MODE != 0>(v, L.xa, L.xb, L.t, log2n, twz);
     if (live) {
 #pragma unroll
         for (int e = 0; e < 8; e++) spec[(size_t)j * nz + L.t + e * L.e8] = v[e];

@@ -413,3 +413,23 @@ def test_second_sweep_that_stops_early_leaves_unreached_slices_zero():
             assert not a[1:stop].any(), f
             assert slice_rel_l2(a[stop:], o.field3d(f, per_slice=True)[stop:]) < 1e-7, f
             assert not s.xy_cut(f, per_slice=True)[1:stop].any(), f
+
+
+def test_reinitialising_particles_releases_the_previous_arrays():
+    """qpic_init_wake_particles with another particle count re-allocates the ~40 particle arrays; the previous ones are released (round 1 kept
+    them until qpic_destroy, so a plasma profile whose particle count varies grew the device memory without bound)."""
+    import torch
+    from quetzalpic_b200 import WakefieldSolver, wake_particle_lattice
+    n = 256
+    with WakefieldSolver(4, n, n, 0.8, 25.6, 25.6, 2) as s:
+        small = wake_particle_lattice(n, n, 25.6, 25.6, 2, 2)   # 262 144 particles
+        large = wake_particle_lattice(n, n, 25.6, 25.6, 4, 4)   # 1 048 576 particles: ~0.35 GB of particle arrays
+        free = []
+        for it in range(8):
+            s.init_wake_particles(*(large if it % 2 == 0 else small))
+            torch.cuda.synchronize()
+            free.append(torch.cuda.mem_get_info()[0])
+        # same count -> same footprint, whatever happened in between
+        assert abs(free[6] - free[2]) < 32 << 20, free
+        assert abs(free[7] - free[3]) < 32 << 20, free
+        s.solve_wakefield()
