@@ -344,7 +344,9 @@ int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaun
             if (per_sm < 1) per_sm = 1;
             const long blocks = (nseq + spb - 1) / spb;
             const long waves = (blocks + 148 * per_sm - 1) / (148 * per_sm);
-            if (best < 0 || waves < best_waves) {
+            const char * e_pref = getenv("QPIC_FFT_PREFER_DEEP");  // A/B: ties go to the deep build
+            const bool prefer = e_pref && e_pref[0] == '1' && mode == 2 && waves == best_waves;
+            if (best < 0 || waves < best_waves || prefer) {
                 best = mode;
                 best_spb = spb;
                 best_waves = waves;
