@@ -153,6 +153,7 @@ struct qpic_ctx {
     int cur_it = 0;
     int fold_rc_mode = -1;                         // ... and rho / susceptibility in the last pass of a slice: QPIC_FOLD_RHO_CHI = 0 / 1, unset: by density
     bool fold_rc = false;
+    bool dense_cells = false;                      // >= 8 particles per cell: k_particles_predict_dep<., ., SRED = true>
     bool fold_jx = true;                           // predictor-side deposit: the jx deposit at (y, z) rides along (QPIC_FOLD_JX=0: separate tile kernel)
     bool fuse_gamma = true;                        // the first predictor pass of a slice does k_particles_gamma's work (QPIC_FUSE_GAMMA=0: separate kernel)
     bool track_gamma_px = false;                   // QPIC_TRACK_GAMMA_PX=1: gamma, px by particle id after EVERY slice (default: at the end of the sweep)
@@ -344,9 +345,8 @@ int size_fft_launch(qpic_ctx * c, const FftPlan & P, int nseq, qpic_ctx::FftLaun
             if (per_sm < 1) per_sm = 1;
             const long blocks = (nseq + spb - 1) / spb;
             const long waves = (blocks + 148 * per_sm - 1) / (148 * per_sm);
-            const char * e_pref = getenv("QPIC_FFT_PREFER_DEEP");  // A/B: ties go to the deep build
-            const bool prefer = e_pref && e_pref[0] == '1' && mode == 2 && waves == best_waves;
-            if (best < 0 || waves < best_waves || prefer) {
+            // (ties stay with the earlier build: at 1024 points wide and deep both need one wave, wide measured 3514 vs 3540 us/slice on config #3)
+            if (best < 0 || waves < best_waves) {
                 best = mode;
                 best_spb = spb;
                 best_waves = waves;
@@ -916,9 +916,19 @@ int enqueue_slice_full(qpic_ctx * c, bool fast) {
         if (np > 0 && fast && predict_deposit_on(c)) {
             StayOut so = c->stay;
             so.cnt = c->stay_cnt[it & 1];
-            auto predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true> : k_particles_predict_dep<false>;
-            if (fold_jx_on(c)) predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true, 1> : k_particles_predict_dep<false, 1>;
-            if (fold_rc_on(c) && it == M - 1) predict = (it == 0 && c->fuse_gamma) ? k_particles_predict_dep<true, 2> : k_particles_predict_dep<false, 2>;
+            const bool first = it == 0 && c->fuse_gamma;
+            auto predict = first ? k_particles_predict_dep<true> : k_particles_predict_dep<false>;
+            if (fold_jx_on(c)) {
+                const bool last_rc = fold_rc_on(c) && it == M - 1;
+                // (dense cells: the per-cell sums leave the warp through shared memory, see k_particles_predict_dep)
+                if (c->dense_cells) {
+                    predict = last_rc ? (first ? k_particles_predict_dep<true, 2, true> : k_particles_predict_dep<false, 2, true>)
+                                      : (first ? k_particles_predict_dep<true, 1, true> : k_particles_predict_dep<false, 1, true>);
+                } else {
+                    predict = last_rc ? (first ? k_particles_predict_dep<true, 2> : k_particles_predict_dep<false, 2>)
+                                      : (first ? k_particles_predict_dep<true, 1> : k_particles_predict_dep<false, 1>);
+                }
+            }
             QPIC_LAUNCH(predict, blocks_for(np, QPIC_PBLOCK), QPIC_PBLOCK, 0, sa, c->ctl, c->g, c->P, c->f2[QPIC_F2_BY_CUR], c->f2[QPIC_F2_BZ_CUR], (it == M - 1) ? 1 : 0, so,
                         (const double *)c->f3[QPIC_F3_ASQR], (const double *)c->f2[QPIC_F2_PSI]);
             QPIC_TRY(check_launch(c, "k_particles_predict"));
@@ -1086,6 +1096,9 @@ int alloc_particles(qpic_ctx * c, size_t count) {
         // particles this rank was handed, which sit on 1 / world of the cells.)
         const size_t held = c->dist.on ? (size_t)c->dist.live0 * (size_t)c->prm.dist_world : count;
         c->fold_rc = c->fold_rc_mode == 1 || (c->fold_rc_mode == -1 && held >= 8 * (size_t)c->g.n2);
+        // the same density decides how the predictor's per-cell sums leave the warp (QPIC_DENSE_CELLS = 0 / 1 forces it)
+        const char * e_dense = getenv("QPIC_DENSE_CELLS");
+        c->dense_cells = (e_dense && (e_dense[0] == '0' || e_dense[0] == '1')) ? e_dense[0] == '1' : held >= 8 * (size_t)c->g.n2;
     }
     if (c->predict_deposit && count > 0) {
         // experimental predictor-side deposit: per-cell corner sums, per-warp pieces, double-buffered mover counters, unsorted lists
@@ -1599,6 +1612,10 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD((k_particles_predict_dep<true, 1>));
         QPIC_PRELOAD((k_particles_predict_dep<false, 2>));
         QPIC_PRELOAD((k_particles_predict_dep<true, 2>));
+        QPIC_PRELOAD((k_particles_predict_dep<false, 1, true>));
+        QPIC_PRELOAD((k_particles_predict_dep<true, 1, true>));
+        QPIC_PRELOAD((k_particles_predict_dep<false, 2, true>));
+        QPIC_PRELOAD((k_particles_predict_dep<true, 2, true>));
         QPIC_PRELOAD(k_tile_fold_rho_chi);
         QPIC_PRELOAD(k_tile_assemble<false>);
         QPIC_PRELOAD(k_tile_assemble<true>);

@@ -1612,7 +1612,12 @@ struct StayOut {
 #ifndef QPIC_PDEP_MINB
 #define QPIC_PDEP_MINB 1
 #endif
-template <bool FIRST = false, int FOLD = 0>
+
+// SRED: how the per-cell sums leave the warp.  false: shuffle tree over the lanes of a run (as many steps as the longest run needs) -- the
+// cheaper one for short runs (4 particles per cell: 551 vs 567 us/slice on config #2, 3514 vs 3629 on config #3); true: through shared memory,
+// lane (k, r) adds value k over run r left to right -- independent of the run length, the cheaper one for dense cells (16 per cell: 91.7 vs
+// 94.8 ms/slice on config #4).  Chosen by the host from the density (>= 8 particles per cell).
+template <bool FIRST = false, int FOLD = 0, bool SRED = false>
 __global__ void
 #if QPIC_PDEP_MINB > 1
     __launch_bounds__(128, QPIC_PDEP_MINB)
@@ -1713,6 +1718,46 @@ __global__ void
         }
     }
     const int key = have ? c : -3 - lane;
+    if constexpr (SRED) {
+    // Segmented sums through shared memory: every lane parks its NV contributions in the warp's tile; lane (k, r) then adds value k over run r
+    // in slot order (runs = maximal groups of lanes with the same cell; 32 / NV runs per round).  Same association order as the tile kernels
+    // (a plain left-to-right sum per cell), ~half the instructions of the shuffle tree, and independent of the run length.
+    {
+        constexpr int WARPS = 4;  // QPIC_PBLOCK / 32
+        __shared__ double red[WARPS][NV][33];
+        __shared__ int run_start[WARPS][34];
+        const int wib = (threadIdx.x >> 5) & (WARPS - 1);
+#pragma unroll
+        for (int i = 0; i < NV; i++) red[wib][i][lane] = cs[i];
+        const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool starts = lane == 0 || key_prev != key;
+        const unsigned smask = __ballot_sync(0xffffffffu, starts);
+        const int nruns = __popc(smask);
+        if (starts) run_start[wib][__popc(smask & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) run_start[wib][nruns] = 32;
+        __syncwarp();
+        constexpr int RPR = 32 / NV;  // runs per round
+        const int k = lane % NV, rr = lane / NV;
+        const int w = warp_base >> 5;
+        const int key_first = __shfl_sync(0xffffffffu, key, 0), key_last = __shfl_sync(0xffffffffu, key, 31);
+        for (int base = 0; base < nruns; base += RPR) {
+            const int r = base + rr;
+            const bool mine = r < nruns;
+            const int st = mine ? run_start[wib][r] : 0, en = mine ? run_start[wib][r + 1] : 0;
+            const int kr = __shfl_sync(0xffffffffu, key, st);  // the run's cell (negative: lanes beyond the live range)
+            if (!mine || kr < 0) continue;
+            double sum = red[wib][k][st];
+            for (int q = st + 1; q < en; q++) sum += red[wib][k][q];
+            const bool from_before = st == 0 && kr == key_first && kr == key_before;
+            const bool into_after = en == 32 && kr == key_last && kr == key_after;
+            double * dst;
+            if (from_before) dst = k < 4 ? so.lead + 4 * w + k : (k < 8 ? so.xlead + 4 * w + (k - 4) : so.rlead + 8 * w + (k - 8));
+            else if (into_after) dst = k < 4 ? so.trail + 4 * w + k : (k < 8 ? so.xtrail + 4 * w + (k - 4) : so.rtrail + 8 * w + (k - 8));
+            else dst = k < 4 ? so.corn + k * (size_t)g.n2 + kr : (k < 8 ? so.xcorn + (k - 4) * (size_t)g.n2 + kr : so.rcorn + (k - 8) * (size_t)g.n2 + kr);
+            *dst = sum;
+        }
+    }
+    } else {
     // keys are sorted, so once no lane finds its key d lanes below, none will at a larger distance: runs of 4-8 particles need 3 steps
     for (int d = 1; d < 32; d <<= 1) {
         const int k2 = __shfl_up_sync(0xffffffffu, key, d);
@@ -1770,6 +1815,7 @@ __global__ void
                 for (int i = 0; i < 8; i++) so.rcorn[i * (size_t)g.n2 + c] = cs[8 + i];
             }
         }
+    }
     }
 }
 

@@ -124,12 +124,15 @@ def test_slab_sweep_with_half_steps_beyond_one_cell(world, predict_deposit, monk
             assert slice_rel_l2(g.field3d(f), o.field3d(f)) < 1e-10, f
 
 
+@pytest.mark.parametrize("dense", ["0", "1"], ids=["shuffle-sums", "shared-memory-sums"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_slab_sweep_is_bit_reproducible(world):
+def test_slab_sweep_is_bit_reproducible(world, dense, monkeypatch):
     """Particles that migrate between ranks are appended on the receiving rank in the order the senders' atomics resolved; the cell sort
     orders them by (side, slot on the sending rank) -- sort_key in qpic_kernels.cuh -- so every per-cell sum, and with it every field of
     the sweep, is the same bit for bit from run to run (round 1: only up to the order of the particles inside a cell)."""
     from quetzalpic_b200.dist import SlabGroup
+    monkeypatch.setenv("QPIC_DENSE_CELLS", dense)   # (what config #4's 16 particles per cell select)
+    monkeypatch.setenv("QPIC_FOLD_RHO_CHI", dense)
     nx, ny, nz = 10, 64 * world // 2 * 2, 64
     a0 = 2.5
     case = Case.synthetic(n=(nx, ny, nz), d=(0.3, 0.1, 0.1), M=2, ppc=(2, 2), a0=a0, sigma=(1.0, 2.0, 2.5))

@@ -164,14 +164,17 @@ def test_deposit_kernel_generations_agree(n, ppc, a0, monkeypatch):
     forms the nodes; "predict_rc": rho / susceptibility from the last pass as well; "predict_only_charge": jx by its tile kernel."""
     case = Case.synthetic(n=n, d=(0.125, 0.25, 0.25), M=3, ppc=ppc, a0=a0)
     runs = {}
-    for name, kw in [("tile", {}), ("general", {"force_general_deposit": True}), ("predict", {}), ("predict_rc", {}), ("predict_only_charge", {})]:
+    for name, kw in [("tile", {}), ("general", {"force_general_deposit": True}), ("predict", {}), ("predict_rc", {}), ("predict_only_charge", {}),
+                     ("predict_dense", {})]:
         monkeypatch.setenv("QPIC_PREDICT_DEPOSIT", "1" if name.startswith("predict") else "0")
-        monkeypatch.setenv("QPIC_FOLD_RHO_CHI", "1" if name == "predict_rc" else "0")
+        monkeypatch.setenv("QPIC_FOLD_RHO_CHI", "1" if name in ("predict_rc", "predict_dense") else "0")
+        # "predict_dense": what >= 8 particles per cell select -- the per-cell sums leave the warp through shared memory (left-to-right sums)
+        monkeypatch.setenv("QPIC_DENSE_CELLS", "1" if name == "predict_dense" else "0")
         monkeypatch.setenv("QPIC_FOLD_JX", "0" if name == "predict_only_charge" else "1")
         with case.make_solver(keep_slices_3d=True, **kw) as s:
             assert s.solve_wakefield() == -1
             runs[name] = {f: s.field3d(f) for f in FIELDS} | {f + "_s": s.field3d(f, per_slice=True) for f in SLICE_FIELDS}
-    for other in ("general", "predict", "predict_rc", "predict_only_charge"):
+    for other in ("general", "predict", "predict_rc", "predict_only_charge", "predict_dense"):
         for k, v in runs["tile"].items():
             assert slice_rel_l2(runs[other][k], v) < 1e-12, (other, k)
 
@@ -244,6 +247,7 @@ def test_sweep_matches_reference_golden(name, fold_rho_chi, golden_dir, monkeypa
     import os
     if fold_rho_chi is not None:
         monkeypatch.setenv("QPIC_FOLD_RHO_CHI", fold_rho_chi)
+        monkeypatch.setenv("QPIC_DENSE_CELLS", "1")  # ... and with them the shared-memory form of the predictor's segmented sums
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     case = Case.from_toml(name)
     assert case.n == g["f3/psi"].shape

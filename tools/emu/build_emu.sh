@@ -5,7 +5,7 @@ set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(cd "$HERE/../.." && pwd)
 mkdir -p "$HERE/_build"
-/usr/bin/g++ -std=c++14 -O1 -g -fPIC -shared -DQPIC_EMU -I"$HERE" -I"$ROOT/quetzalpic_b200/csrc" \
+/usr/bin/g++ -std=c++17 -O1 -g -fPIC -shared -DQPIC_EMU -I"$HERE" -I"$ROOT/quetzalpic_b200/csrc" \
     $QPIC_EMU_FLAGS -Wall -Wno-unused-function -Wno-unknown-pragmas -Wno-unused-variable \
     -x c++ "$ROOT/quetzalpic_b200/csrc/qpic_ctx.cu" "$HERE/qpic_emu.cpp" \
     -o "$HERE/_build/libqpic_emu_debug.so"

@@ -120,6 +120,7 @@ static inline void __threadfence_block() {}
 static inline void __threadfence_system() {}
 
 static inline unsigned __activemask() { return 0xffffffffu; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline unsigned __ballot_sync(unsigned, int pred);
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 template <class T>
