@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--warm", type=int, default=96)
     ap.add_argument("--out", default=None)
     ap.add_argument("--dump", action="store_true", help="print every record of the first timed slice")
+    ap.add_argument("--xy", action="store_true", help="keep_xy_cuts: the Fields_xy output contract of the end-to-end arm")
     a = ap.parse_args()
     build()
     lib = QpicLibrary(TL_LIB)
@@ -54,7 +55,7 @@ def main():
     n, nx = a.n, a.nx
     l = 32.0
     dx = 0.015625
-    s = WakefieldSolver(nx, n, n, nx * dx, l, l, a.M, stop_check_interval=10 ** 6, library=lib)
+    s = WakefieldSolver(nx, n, n, nx * dx, l, l, a.M, stop_check_interval=10 ** 6, library=lib, keep_xy_cuts=a.xy)
     s.set_laser_gaussian(0.5 * a.a0 ** 2, *gaussian_laser_widths(4.0, 8.0, 8.0), nx * dx - 2.0, 0.5 * l, 0.5 * l)
     y, z, w = wake_particle_lattice(n, n, l, l, a.ppc, a.ppc)
     s.init_wake_particles(y, z, w)
