@@ -146,3 +146,37 @@ def test_slab_sweep_with_4096_point_axes(world, n):
         assert sum(s.particle_count for s in g.ranks) == y.size
         for f in FIELDS:
             assert slice_rel_l2(g.field3d(f), o.field3d(f)) < 1e-11, f
+
+
+def test_config4_density_selects_the_dense_cell_kernels_single_gpu():
+    """BASELINE config #4's density (4 x 4 = 16 particles per cell) on a 256 x 256 grid, 4-slice box through the laser: at >= 8 particles per
+    cell the library selects, by itself, the shared-memory form of the predictor's per-cell sums and rho / susceptibility from the last
+    predictor pass (k_particles_predict_dep<., 2, true> + k_tile_fold_rho_chi) -- nothing is forced through the environment here."""
+    case = Case.synthetic(n=(4, 256, 256), d=(0.015625, 0.125, 0.125), M=5, ppc=(4, 4), a0=1.5, sigma=(4.0, 8.0, 8.0), x0=0.03)
+    o = case.make_oracle()
+    o.solve_wakefield()
+    with case.make_solver(keep_slices_3d=True) as s:
+        assert s.solve_wakefield() == -1
+        worst = sweep_errors(s, o)
+    assert max(worst.values()) < 1e-11, worst
+
+
+def test_config4_density_on_slabs():
+    """... and on two slabs (the rule uses the density of the particles a rank was handed): 16 particles per cell, migration across the slab edge."""
+    import torch
+    from quetzalpic_b200.dist import SlabGroup
+    nx, ny, nz = 4, 256, 128
+    case = Case.synthetic(n=(nx, ny, nz), d=(0.2, 0.1, 0.1), M=3, ppc=(4, 4), a0=1.8, sigma=(1.2, 5.0, 4.0))
+    wx, wy, wz = case.laser[1:4]
+    case.laser = (case.laser[0], wx, wy, wz, 0.4, 0.1 * ny / 2 - 0.33, 0.05 * nz)
+    o = case.make_oracle()
+    o.solve_wakefield()
+    y, z, w = case.particles
+    devs = [r % torch.cuda.device_count() for r in range(2)]
+    with SlabGroup(2, nx, ny, nz, case.l[0], case.l[1], case.l[2], case.M, devices=devs, stop_check_interval=4) as g:
+        g.set_laser_gaussian(*case.laser)
+        g.init_wake_particles(y, z, w)
+        assert g.solve_wakefield() == [-1, -1]
+        assert sum(s.particle_count for s in g.ranks) == y.size
+        for f in FIELDS:
+            assert slice_rel_l2(g.field3d(f), o.field3d(f)) < 1e-11, f
