@@ -112,6 +112,25 @@ def test_bench_bytes_formula():
     assert abs(bench.algorithmic_bytes_per_slice(512 * 512, 4 * 512 * 512, 5) - 1.554e9) < 1e6
 
 
+def test_bench_per_kernel_bytes_add_up_to_the_slice_formula():
+    """bench.py's per-kernel table (SURVEY 8(d) apportioned to our kernels) must add up to 8 [(29 + 44 M) N + (18 + 21 M) P] over the launches of a
+    slice -- for the round-1 kernel set and for the round-2 one, where the first predictor pass does k_particles_gamma's work and k_tile_assemble
+    writes the jx target (bench.py folds their shares into the kernels that took the work over)."""
+    import bench
+    N, P, M = 512 * 512, 4 * 512 * 512, 5
+    per_slice = {"k_tile_deposit_charge": 1, "k_fft_rows_r2c": M + 1, "k_fft_cols_solve": M + 1, "k_fft_rows_c2r": M + 1, "k_particles_gamma": 1,
+                 "k_tile_deposit_rho_chi": 1, "k_particles_advance": 1, "k_end_of_slice": 1, "k_particles_predict": M, "k_tile_deposit_charge_mid": M,
+                 "k_tile_deposit_jy_jz": M, "k_tile_deposit_jx": M, "k_fft_rows_b_forward": M, "k_fft_cols_solve_b": M, "k_fft_rows_b_backward": M}
+    total = sum(n * bench.kernel_algorithmic_bytes(k, N, P) for k, n in per_slice.items())
+    assert abs(total - bench.algorithmic_bytes_per_slice(N, P, M)) < 1.0
+    # the static DRAM-traffic table covers every kernel of the default slice that moves data
+    default_slice = [k for k in per_slice if k not in ("k_particles_gamma", "k_tile_deposit_jx")]
+    missing = [k for k in default_slice if k not in bench.NCU_DRAM_BYTES]
+    assert not missing, missing
+    for k, (nbytes, source) in bench.NCU_DRAM_BYTES.items():
+        assert nbytes >= 0 and os.path.exists(os.path.join(os.path.dirname(bench.__file__), source)), (k, source)
+
+
 # ---- host logic of the slab-decomposed sweep (quetzalpic_b200/dist.py)
 
 def test_slab_partition_covers_every_particle_once():
