@@ -779,8 +779,15 @@ int enqueue_tile_jy_jz(qpic_ctx * c, cudaStream_t st) {
     j.b_jz = c->f2[QPIC_F2_JZ];
     j.b_D = c->prm.magnetic_field_D;
     // one visit per particle
-    const dim3 grid((c->g.nz + LIST_TZ - 1) / LIST_TZ, (j.cell_rows + LIST_TY - 1) / LIST_TY);
-    QPIC_LAUNCH(k_tile_cell_deposit, grid, dim3(LIST_BZ, LIST_BY), 0, st, c->ctl, c->g, c->start_b, c->P, j);
+    if (c->dense_cells) {
+        constexpr int TZ = 32;
+        const dim3 grid((c->g.nz + TZ - 1) / TZ, (j.cell_rows + LIST_TY - 1) / LIST_TY);
+        QPIC_LAUNCH(k_tile_cell_deposit<TZ>, grid, dim3(TZ + 2, LIST_BY), sizeof(double) * 12 * LIST_BY * (TZ + 2), st, c->ctl, c->g, c->start_b, c->P, j);
+    } else {
+        constexpr int TZ = 16;
+        const dim3 grid((c->g.nz + TZ - 1) / TZ, (j.cell_rows + LIST_TY - 1) / LIST_TY);
+        QPIC_LAUNCH(k_tile_cell_deposit<TZ>, grid, dim3(TZ + 2, LIST_BY), sizeof(double) * 12 * LIST_BY * (TZ + 2), st, c->ctl, c->g, c->start_b, c->P, j);
+    }
     return check_launch(c, "k_tile_deposit_jy_jz");
 }
 
@@ -1494,6 +1501,7 @@ static int create_impl(qpic_ctx * c) {
             QPIC_CUDA(c, cudaFuncSetAttribute(k_p2_cols_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_max));
         }
     }
+    QPIC_CUDA(c, cudaFuncSetAttribute(k_tile_cell_deposit<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 12 * LIST_BY * 34)));
     // the inverse-symbol tables of the two operators of the sweep (psi: D = 0, half spectrum; By + i Bz: D, full spectrum)
     if (c->pow2_y) {
         const double * unused = nullptr;
@@ -1621,7 +1629,8 @@ static int create_impl(qpic_ctx * c) {
         QPIC_PRELOAD((k_tile_deposit<3, false>));
         QPIC_PRELOAD((k_tile_deposit<2, true, true>));
         QPIC_PRELOAD(k_tile_stay_deposit);
-        QPIC_PRELOAD(k_tile_cell_deposit);
+        QPIC_PRELOAD(k_tile_cell_deposit<16>);
+        QPIC_PRELOAD(k_tile_cell_deposit<32>);
         QPIC_PRELOAD(k_particles_predict_dep<false>);
         QPIC_PRELOAD(k_particles_predict_dep<true>);
         QPIC_PRELOAD((k_particles_predict_dep<false, 1>));

@@ -1977,8 +1977,10 @@ __global__ void __launch_bounds__(TILE_CELLS) k_tile_fold_rho_chi(const Ctl * ct
 // src/System_3d.cpp:190-193).  Measured on config #2: own-list-only work of the old kernel was 11 us of its 29.5 us.
 // Block = (LIST_TY + 2) x (LIST_TZ + 2) = 16 x 18 = 288 threads (9 full warps): thread (ay, az) <-> cell (j0 - 1 + ay, k0 - 1 + az),
 // nodes of the block = cells with 1 <= ay <= LIST_TY, 1 <= az <= LIST_TZ.
-constexpr int LIST_TY = 14, LIST_TZ = 16;
-constexpr int LIST_BY = LIST_TY + 2, LIST_BZ = LIST_TZ + 2, LIST_THREADS = LIST_BY * LIST_BZ;
+// Two tile widths (template argument TZ): 14 x 16 nodes (288 threads, two blocks per SM) and, for dense cells (>= 8 particles per cell), 14 x 32
+// nodes (544 threads, one block per SM): 21 % instead of 29 % of the visits are halo cells' -- config #4 on one GPU 91.7 -> 89.7 ms/slice; at 4
+// particles per cell the wide tile gains nothing (550.5 vs 549.8 us/slice on config #2, 3517 vs 3484 on config #3).
+constexpr int LIST_TY = 14, LIST_BY = LIST_TY + 2;
 
 // Measured on config #2 (gpurun_out, third session; whole-slice times): 3 blocks / SM (72 registers, spills) 0.742 ms, with the
 // two-deep pipeline 0.781 (more spills); 2 blocks / SM (96 registers, no spills) 0.731, with the pipeline 0.722.  The three-list
@@ -1997,9 +1999,12 @@ constexpr int LIST_BY = LIST_TY + 2, LIST_BZ = LIST_TZ + 2, LIST_THREADS = LIST_
 #ifndef QPIC_CELL_EPI_PREFETCH
 #define QPIC_CELL_EPI_PREFETCH 1
 #endif
-__global__ void __launch_bounds__(LIST_THREADS, QPIC_CELL_MINB) k_tile_cell_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+template <int LIST_TZ>
+__global__ void __launch_bounds__(LIST_BY * (LIST_TZ + 2), LIST_TZ == 16 ? QPIC_CELL_MINB : 1)
+    k_tile_cell_deposit(const Ctl * ctl, Geom g, const int * __restrict__ start, Particles P, TileJob job) {
+    constexpr int LIST_BZ = LIST_TZ + 2, LIST_THREADS = LIST_BY * LIST_BZ;
     QPIC_KERNEL_BEGIN(KID_COUNT + 5);
-    __shared__ double acc[12 * LIST_THREADS];
+    QPIC_DYN_SMEM(double, acc);  // [12][LIST_THREADS]
     const int ay = threadIdx.y, az = threadIdx.x;
     const int tid = ay * LIST_BZ + az;
     // node rows [cell_row0, cell_row0 + cell_rows) are launched: the whole grid on a single GPU, the slab and one tile row on
