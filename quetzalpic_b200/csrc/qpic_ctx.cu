@@ -687,7 +687,7 @@ int launch_tile(qpic_ctx * c, cudaStream_t st, TileJob & j, bool final_pass, con
 
 // psi source from positions (y,z) [at_mid = 0] or the half-step positions [at_mid = 1] -> fft_in
 // with the published lists the psi_middle source deposit and the jy/jz deposit treat the particles that stay in their cell directly
-// and exchange only the movers (k_tile_stay_deposit / k_tile_cell_deposit); QPIC_JYJZ_CELL=0 selects the older pair
+// and exchange only the movers (k_tile_stay_deposit / k_tile_assemble, k_tile_cell_deposit)
 bool stayers_direct(const qpic_ctx * c) { return c->jyjz_lists; }
 // slabs: target rows whose deposits (corner rows j, j + 1; the staggered jy rows j - 1 .. j + 1) stay inside own rows + DIST_HALO halo rows
 void far_rows(const qpic_ctx * c, int * row_lo, int * row_n) {
